@@ -1,0 +1,391 @@
+"""ctypes wrappers over the CPU oracle (oracle/phb_oracle.c) and the compiled reference harness.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs; never by physher_b200/.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "_build", "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libref_harness.so")
+REFERENCE_ROOT = "/root/reference"
+
+
+def build(ref: bool = True) -> None:
+    """Compile the restatement and, when /root/reference is present, the reference itself."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    if ref and os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "phyc")):
+        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
+
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_bp = C.POINTER(C.c_uint8)
+
+
+class _Problem(C.Structure):
+    _fields_ = [
+        ("T", C.c_int), ("N", C.c_int), ("S", C.c_int), ("C", C.c_int), ("P", C.c_int), ("root", C.c_int),
+        ("left", _ip), ("right", _ip), ("parent", _ip),
+        ("tip_mode", C.c_int), ("tip_states", _bp), ("tip_partials", _dp), ("weights", _dp),
+        ("evec", _dp), ("eval", _dp), ("ivec", _dp), ("P_override", _dp), ("dP_override", _dp),
+        ("freqs", _dp), ("rates", _dp), ("props", _dp), ("bl", _dp),
+        ("scale", C.c_int), ("scaling_threshold", C.c_double),
+        ("include_root_freqs", C.c_int), ("compat_scaled_gradient", C.c_int), ("unrooted", C.c_int),
+    ]
+
+
+class _Result(C.Structure):
+    _fields_ = [
+        ("lnl", C.c_double), ("pattern_lnl", _dp), ("grad", _dp), ("cat_grad", _dp),
+        ("lower", _dp), ("upper", _dp), ("matrices", _dp), ("dmatrices", _dp), ("scaling", _dp),
+    ]
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+@dataclass
+class Problem:
+    """Plain-array description of one tree-likelihood evaluation (shared by oracle and GPU tests)."""
+
+    left: np.ndarray
+    right: np.ndarray
+    parent: np.ndarray
+    root: int
+    nstate: int
+    tip_states: np.ndarray | None  # uint8 [T][P]
+    weights: np.ndarray  # [P]
+    freqs: np.ndarray
+    rates: np.ndarray
+    props: np.ndarray
+    bl: np.ndarray
+    evec: np.ndarray | None = None
+    eval: np.ndarray | None = None
+    ivec: np.ndarray | None = None
+    tip_partials: np.ndarray | None = None  # [T][P][S]
+    use_tip_states: bool = True
+    P_override: np.ndarray | None = None
+    dP_override: np.ndarray | None = None
+    scale: bool = False
+    scaling_threshold: float = 1e-40
+    include_root_freqs: bool = False
+    compat_scaled_gradient: bool = False
+    unrooted: bool = True
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def ntips(self):
+        return (self.left.shape[0] + 1) // 2
+
+    @property
+    def nnodes(self):
+        return self.left.shape[0]
+
+    @property
+    def npatterns(self):
+        return self.weights.shape[0]
+
+    @property
+    def ncat(self):
+        return self.rates.shape[0]
+
+
+_lib = None
+
+
+def _oracle():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build(ref=False)
+        _lib = C.CDLL(ORACLE_SO)
+        _lib.oracle_evaluate.argtypes = [C.POINTER(_Problem), C.POINTER(_Result)]
+        _lib.oracle_evaluate.restype = C.c_int
+        _lib.oracle_p_t.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, _dp]
+        _lib.oracle_dp_dt.argtypes = [C.c_int, _dp, _dp, _dp, C.c_double, _dp]
+    return _lib
+
+
+def evaluate(pb: Problem, gradient: bool = True, partials: bool = False, matrices: bool = False) -> dict:
+    """Run the C restatement. Returns dict(lnl, pattern_lnl, grad, cat_grad[, lower, upper, matrices, dmatrices, scaling])."""
+    lib = _oracle()
+    N, S, Cc, P = pb.nnodes, pb.nstate, pb.ncat, pb.npatterns
+    keep = []
+
+    def c64(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        keep.append(a)
+        return a
+
+    def c32(a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        keep.append(a)
+        return a
+
+    cp = _Problem()
+    cp.T, cp.N, cp.S, cp.C, cp.P, cp.root = pb.ntips, N, S, Cc, P, int(pb.root)
+    cp.left, cp.right, cp.parent = _i(c32(pb.left)), _i(c32(pb.right)), _i(c32(pb.parent))
+    cp.tip_mode = 0 if pb.use_tip_states else 1
+    if pb.tip_states is not None:
+        ts = np.ascontiguousarray(pb.tip_states, dtype=np.uint8)
+        keep.append(ts)
+        cp.tip_states = ts.ctypes.data_as(_bp)
+    if pb.tip_partials is not None:
+        cp.tip_partials = _d(c64(pb.tip_partials))
+    cp.weights = _d(c64(pb.weights))
+    if pb.evec is not None:
+        cp.evec, cp.eval, cp.ivec = _d(c64(pb.evec)), _d(c64(pb.eval)), _d(c64(pb.ivec))
+    if pb.P_override is not None:
+        cp.P_override = _d(c64(pb.P_override))
+    if pb.dP_override is not None:
+        cp.dP_override = _d(c64(pb.dP_override))
+    cp.freqs, cp.rates, cp.props, cp.bl = _d(c64(pb.freqs)), _d(c64(pb.rates)), _d(c64(pb.props)), _d(c64(pb.bl))
+    cp.scale = int(pb.scale)
+    cp.scaling_threshold = pb.scaling_threshold
+    cp.include_root_freqs = int(pb.include_root_freqs)
+    cp.compat_scaled_gradient = int(pb.compat_scaled_gradient)
+    cp.unrooted = int(pb.unrooted)
+
+    out = {"pattern_lnl": np.zeros(P)}
+    res = _Result()
+    res.pattern_lnl = _d(out["pattern_lnl"])
+    if gradient:
+        out["grad"] = np.zeros(N)
+        out["cat_grad"] = np.zeros((N, Cc))
+        res.grad, res.cat_grad = _d(out["grad"]), _d(out["cat_grad"])
+    if partials:
+        out["lower"] = np.zeros((N, Cc, P, S))
+        out["scaling"] = np.zeros((N, P))
+        res.lower, res.scaling = _d(out["lower"]), _d(out["scaling"])
+        if gradient:
+            out["upper"] = np.zeros((N, Cc, P, S))
+            res.upper = _d(out["upper"])
+    if matrices:
+        out["matrices"] = np.zeros((N, Cc, S, S))
+        out["dmatrices"] = np.zeros((N, Cc, S, S))
+        res.matrices, res.dmatrices = _d(out["matrices"]), _d(out["dmatrices"])
+    rc = lib.oracle_evaluate(C.byref(cp), C.byref(res))
+    if rc != 0:
+        raise MemoryError("oracle_evaluate failed")
+    out["lnl"] = res.lnl
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# compiled reference (oracle/_ref)
+# ---------------------------------------------------------------------------------------------
+
+FLAG_TREE_MODEL = 1 << 0  # treelikelihood.h:32-38
+FLAG_SITE_MODEL = 1 << 1
+FLAG_SUBSTITUTION_MODEL = 1 << 2
+FLAG_BRANCH_MODEL = 1 << 6
+
+_ref = None
+
+
+def reference_available() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def _reflib():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(f"{REF_SO} missing: run `make -C oracle ref` where /root/reference exists")
+        L = C.CDLL(REF_SO)
+        L.refh_create.argtypes = [C.c_char_p]
+        L.refh_create.restype = C.c_void_p
+        L.refh_free.argtypes = [C.c_void_p]
+        L.refh_create_codon.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_char_p), C.c_double, C.c_double]
+        L.refh_create_codon.restype = C.c_void_p
+        L.refh_dims.argtypes = [C.c_void_p, _ip]
+        L.refh_topology.argtypes = [C.c_void_p, _ip, _ip, _ip]
+        L.refh_branch_lengths.argtypes = [C.c_void_p, _dp, _dp]
+        L.refh_set_branch_lengths.argtypes = [C.c_void_p, _dp]
+        L.refh_tip_states.argtypes = [C.c_void_p, _bp]
+        L.refh_tip_partials.argtypes = [C.c_void_p, _dp]
+        L.refh_weights.argtypes = [C.c_void_p, _dp]
+        L.refh_model.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp]
+        L.refh_model.restype = C.c_int
+        L.refh_sitemodel.argtypes = [C.c_void_p, _dp, _dp]
+        L.refh_matrices.argtypes = [C.c_void_p, _dp, _dp]
+        L.refh_use_rescaling.argtypes = [C.c_void_p, C.c_int]
+        L.refh_rescaling.argtypes = [C.c_void_p]
+        L.refh_rescaling.restype = C.c_int
+        L.refh_enable_sse.argtypes = [C.c_void_p, C.c_int]
+        L.refh_set_include_jacobian.argtypes = [C.c_void_p, C.c_int]
+        L.refh_use_generic_kernels.argtypes = [C.c_void_p]
+        L.refh_logP.argtypes = [C.c_void_p]
+        L.refh_logP.restype = C.c_double
+        L.refh_pattern_lnl.argtypes = [C.c_void_p, _dp]
+        L.refh_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int, _dp, C.c_int]
+        L.refh_gradient.restype = C.c_int
+        L.refh_partials.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.refh_partials.restype = C.c_int
+        L.refh_scaling_factors.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.refh_scaling_factors.restype = C.c_int
+        L.refh_time_logP.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.refh_time_logP.restype = C.c_double
+        L.refh_time_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.refh_time_gradient.restype = C.c_double
+        _ref = L
+    return _ref
+
+
+class Reference:
+    """One `treelikelihood` Model of the unmodified reference, built from a JSON dict."""
+
+    def __init__(self, spec: dict | None = None, codon: dict | None = None):
+        self.L = _reflib()
+        if codon is not None:
+            names = list(codon["sequences"].keys())
+            n = len(names)
+            a_names = (C.c_char_p * n)(*[s.encode() for s in names])
+            a_seqs = (C.c_char_p * n)(*[codon["sequences"][s].encode() for s in names])
+            self.h = self.L.refh_create_codon(codon["newick"].encode(), n, a_names, a_seqs,
+                                              float(codon["kappa"]), float(codon["omega"]))
+        else:
+            text = json.dumps({"model": spec}).encode()
+            self.h = self.L.refh_create(text)
+        dims = np.zeros(10, np.int32)
+        self.L.refh_dims(self.h, _i(dims))
+        (self.T, self.N, self.S, self.C, self.P, self.root, self.time_mode, _scale, self.use_tip_states, self.root_right) = [int(x) for x in dims]
+
+    def close(self):
+        if self.h:
+            self.L.refh_free(self.h)
+            self.h = None
+
+    def logP(self) -> float:
+        return float(self.L.refh_logP(self.h))
+
+    def pattern_lnl(self):
+        out = np.zeros(self.P)
+        self.L.refh_pattern_lnl(self.h, _d(out))
+        return out
+
+    def gradient(self, flags=FLAG_TREE_MODEL, include_root_freqs=-1):
+        cap = 4 * self.N + 64
+        out = np.zeros(cap)
+        n = self.L.refh_gradient(self.h, flags, include_root_freqs, _d(out), cap)
+        return out[:n].copy()
+
+    def use_rescaling(self, use: bool):
+        self.L.refh_use_rescaling(self.h, int(use))
+
+    def rescaling(self) -> bool:
+        return bool(self.L.refh_rescaling(self.h))
+
+    def enable_sse(self, v: bool):
+        self.L.refh_enable_sse(self.h, int(v))
+
+    def set_include_jacobian(self, v: bool):
+        self.L.refh_set_include_jacobian(self.h, int(v))
+
+    def use_generic_kernels(self):
+        self.L.refh_use_generic_kernels(self.h)
+
+    def set_branch_lengths(self, bl):
+        bl = np.ascontiguousarray(bl, dtype=np.float64)
+        self.L.refh_set_branch_lengths(self.h, _d(bl))
+
+    def partials(self, idx):
+        out = np.zeros((self.C, self.P, self.S))
+        ok = self.L.refh_partials(self.h, idx, _d(out))
+        return out if ok else None
+
+    def scaling_factors(self, idx):
+        out = np.zeros(self.P)
+        ok = self.L.refh_scaling_factors(self.h, idx, _d(out))
+        return out if ok else None
+
+    def time_logP(self, iters):
+        last = C.c_double(0)
+        return float(self.L.refh_time_logP(self.h, iters, C.byref(last))), last.value
+
+    def time_gradient(self, iters, flags=FLAG_TREE_MODEL, include_root_freqs=-1):
+        return float(self.L.refh_time_gradient(self.h, flags, include_root_freqs, iters))
+
+    def problem(self, **kw) -> Problem:
+        """Export every input of the hot path as plain arrays (ids and pattern order as the reference has them)."""
+        N, S, Cc, P, T = self.N, self.S, self.C, self.P, self.T
+        left, right, parent = (np.zeros(N, np.int32) for _ in range(3))
+        self.L.refh_topology(self.h, _i(left), _i(right), _i(parent))
+        bl, dt = np.zeros(N), np.zeros(N)
+        self.L.refh_branch_lengths(self.h, _d(bl), _d(dt))
+        ts = np.zeros((T, P), np.uint8)
+        self.L.refh_tip_states(self.h, ts.ctypes.data_as(_bp))
+        tp = np.zeros((T, P, S))
+        self.L.refh_tip_partials(self.h, _d(tp))
+        w = np.zeros(P)
+        self.L.refh_weights(self.h, _d(w))
+        evec, ev, ivec, freqs = np.zeros((S, S)), np.zeros(S), np.zeros((S, S)), np.zeros(S)
+        has_eigen = self.L.refh_model(self.h, _d(evec), _d(ev), _d(ivec), _d(freqs))
+        rates, props = np.zeros(Cc), np.zeros(Cc)
+        self.L.refh_sitemodel(self.h, _d(rates), _d(props))
+        pb = Problem(left=left, right=right, parent=parent, root=self.root, nstate=S, tip_states=ts, weights=w,
+                     freqs=freqs, rates=rates, props=props, bl=bl, tip_partials=tp,
+                     use_tip_states=bool(self.use_tip_states), unrooted=not self.time_mode)
+        if has_eigen:
+            pb.evec, pb.eval, pb.ivec = evec, ev, ivec
+        else:
+            Pm, dPm = self.matrices()
+            pb.P_override, pb.dP_override = Pm, dPm
+        pb.meta["time_elapsed"] = dt
+        for k, v in kw.items():
+            setattr(pb, k, v)
+        return pb
+
+    def matrices(self):
+        Pm = np.zeros((self.N, self.C, self.S, self.S))
+        dPm = np.zeros_like(Pm)
+        self.L.refh_matrices(self.h, _d(Pm), _d(dPm))
+        return Pm, dPm
+
+
+def treelikelihood_spec(newick: str, sequences: dict, model: dict, categories: int = 1, alpha: float = 0.5,
+                        tipstates: bool = False, sse: bool = True, datatype: str = "nucleotide",
+                        time_tree: dict | None = None) -> dict:
+    """JSON for the reference's `treelikelihood` object (treelikelihood.c:819-942), inline data only."""
+    sitemodel = {"id": "sitemodel", "type": "sitemodel", "substitutionmodel": model}
+    if categories > 1:
+        sitemodel["distribution"] = {
+            "distribution": "gamma", "categories": categories,
+            "parameters": {"shape": {"id": "alpha", "type": "parameter", "value": alpha, "lower": 0}},
+        }
+    tree = {"id": "tree", "type": "tree", "parameters": "tree.distances", "newick": newick}
+    spec = {
+        "id": "treelikelihood", "type": "treelikelihood", "tipstates": tipstates, "sse": sse,
+        "sitepattern": {"id": "patterns", "type": "sitepattern", "datatype": datatype,
+                        "alignment": {"id": "seqs", "type": "alignment", "sequences": sequences}},
+        "sitemodel": sitemodel, "tree": tree,
+    }
+    if time_tree:
+        tree.update(time_tree["tree"])
+        spec["branchmodel"] = time_tree["branchmodel"]
+    return spec
+
+
+def nucleotide_model_spec(name: str, freqs=None, rates=None, kappa=None) -> dict:
+    freqs = [0.25] * 4 if freqs is None else list(map(float, freqs))
+    m = {"id": "sm", "type": "substitutionmodel", "model": name, "datatype": "nucleotide",
+         "frequencies": {"id": "freqs", "type": "Simplex", "values": freqs}}
+    if name == "gtr":
+        m["rates"] = {"id": "gtr_rates", "type": "Simplex", "values": list(map(float, rates))}
+    if name == "hky":
+        m["rates"] = {"kappa": {"id": "kappa", "type": "parameter", "value": float(kappa), "lower": 0}}
+    return m

@@ -1,0 +1,352 @@
+/*
+ * phb_oracle.c -- plain-C restatement of physher's tree-likelihood hot path (see phb_oracle.h).
+ *
+ * TEST INFRASTRUCTURE ONLY: never linked into or called from the product path.
+ * Parity status: PINNED against tests/test_tree_likelihood.c known answers and against the
+ * compiled reference (oracle/_ref), see tests/test_oracle.py.
+ *
+ * Layouts follow the reference: partials [cat][pattern][state] (treelikelihood.c:1028),
+ * matrices [cat][i = parent state][j = child state] row-major (substmodel.c:547-555).
+ */
+#include "phb_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* substmodel.c:518-557 (_p_t): P = V diag(exp(lambda t)) V^-1, fabs() on every entry (:552) */
+void oracle_p_t(int S, const double *evec, const double *eval, const double *ivec, double t, double *P) {
+	double *pp = (double *)malloc(sizeof(double) * S * S);
+	for (int i = 0; i < S; i++) {
+		double e = exp(eval[i] * t);
+		for (int j = 0; j < S; j++) pp[i * S + j] = ivec[i * S + j] * e;
+	}
+	for (int i = 0; i < S; i++) {
+		for (int j = 0; j < S; j++) {
+			double acc = 0.0;
+			for (int k = 0; k < S; k++) acc += pp[k * S + j] * evec[i * S + k];
+			P[i * S + j] = fabs(acc);
+		}
+	}
+	free(pp);
+}
+
+/* substmodel.c:695-723 (_dp_dt): dP/dt = V diag(lambda exp(lambda t)) V^-1, no fabs */
+void oracle_dp_dt(int S, const double *evec, const double *eval, const double *ivec, double t, double *dP) {
+	double *pp = (double *)malloc(sizeof(double) * S * S);
+	for (int i = 0; i < S; i++) {
+		double e = eval[i] * exp(eval[i] * t);
+		for (int j = 0; j < S; j++) pp[i * S + j] = ivec[i * S + j] * e;
+	}
+	for (int i = 0; i < S; i++) {
+		for (int j = 0; j < S; j++) {
+			double acc = 0.0;
+			for (int k = 0; k < S; k++) acc += pp[k * S + j] * evec[i * S + k];
+			dP[i * S + j] = acc;
+		}
+	}
+	free(pp);
+}
+
+typedef struct Work {
+	const OracleProblem *pb;
+	double *mat;    /* [N][C][S][S] */
+	double *dmat;   /* [N][C][S][S] */
+	double *lower;  /* [N][C][P][S] */
+	double *upper;  /* [N][C][P][S] */
+	double *sf;     /* [2N][P] scaling factors: lower at n, upper at N+n */
+	size_t psize;   /* C*P*S */
+	size_t msize;   /* C*S*S */
+} Work;
+
+static int is_tip(const OracleProblem *pb, int n) { return pb->left[n] < 0; }
+
+/* does this node own a partials buffer?  (treelikelihood.c:963-968: tips have none in state mode) */
+static int has_partials(const OracleProblem *pb, int n) {
+	return !is_tip(pb, n) || pb->tip_mode == ORACLE_TIP_PARTIALS;
+}
+
+/*
+ * message[i] = sum_j M[c][i][j] * X[c,k,j] for one child operand, all (c,k).
+ *  - partial operand: treelikelihoodX.c:502-577 (partials_undefined_and_undefined inner sums)
+ *  - state operand, P matrices: treelikelihoodX.c:166-289 / treelikelihood4.c:922-992:
+ *    known state -> column of M; unknown state (>= S) -> factor 1
+ *  - state operand, derivative matrices (prob_matrix == 0): unknown state -> real row sums,
+ *    treelikelihoodX.c:918-929 / treelikelihood4.c:1734-1746
+ */
+static void message(const Work *w, const double *M /*[C][S][S]*/, const double *X /*[C][P][S] or NULL*/,
+                    const uint8_t *states /*[P] or NULL*/, int prob_matrix, double *out /*[C][P][S]*/) {
+	const OracleProblem *pb = w->pb;
+	const int S = pb->S, C = pb->C, P = pb->P;
+	for (int c = 0; c < C; c++) {
+		const double *Mc = M + (size_t)c * S * S;
+		for (int k = 0; k < P; k++) {
+			double *o = out + ((size_t)c * P + k) * S;
+			if (X != NULL) {
+				const double *x = X + ((size_t)c * P + k) * S;
+				for (int i = 0; i < S; i++) {
+					double acc = 0.0;
+					for (int j = 0; j < S; j++) acc += Mc[i * S + j] * x[j];
+					o[i] = acc;
+				}
+			} else {
+				int s = states[k];
+				if (s < S) {
+					for (int i = 0; i < S; i++) o[i] = Mc[i * S + s];
+				} else if (prob_matrix) {
+					for (int i = 0; i < S; i++) o[i] = 1.0;
+				} else {
+					for (int i = 0; i < S; i++) {
+						double acc = 0.0;
+						for (int j = 0; j < S; j++) acc += Mc[i * S + j];
+						o[i] = acc;
+					}
+				}
+			}
+		}
+	}
+}
+
+static const double *node_partials(const Work *w, int idx /* < N lower, >= N upper */) {
+	const OracleProblem *pb = w->pb;
+	if (idx >= pb->N) return w->upper + (size_t)(idx - pb->N) * w->psize;
+	if (!has_partials(pb, idx)) return NULL;
+	return w->lower + (size_t)idx * w->psize;
+}
+
+static const uint8_t *node_states(const Work *w, int idx) {
+	const OracleProblem *pb = w->pb;
+	if (idx >= pb->N || has_partials(pb, idx)) return NULL;
+	return pb->tip_states + (size_t)idx * pb->P;
+}
+
+/* SingleTreeLikelihood_scalePartials, treelikelihood.c:1790-1836 */
+static void scale_partials(Work *w, int out_idx, int in1, int in2) {
+	const OracleProblem *pb = w->pb;
+	const int S = pb->S, C = pb->C, P = pb->P;
+	double *p = (double *)node_partials(w, out_idx);
+	double *sf = w->sf + (size_t)out_idx * P;
+	const double *sf1 = (in1 >= 0 && node_partials(w, in1) != NULL) ? w->sf + (size_t)in1 * P : NULL;
+	const double *sf2 = (in2 >= 0 && node_partials(w, in2) != NULL) ? w->sf + (size_t)in2 * P : NULL;
+	for (int k = 0; k < P; k++) {
+		double m = 0.0;
+		for (int c = 0; c < C; c++)
+			for (int i = 0; i < S; i++) {
+				double v = p[((size_t)c * P + k) * S + i];
+				if (v > m) m = v;
+			}
+		if (m < pb->scaling_threshold) {
+			for (int c = 0; c < C; c++)
+				for (int i = 0; i < S; i++) p[((size_t)c * P + k) * S + i] /= m;
+			sf[k] = log(m);
+		} else {
+			sf[k] = 0.0;
+		}
+		if (sf1) sf[k] += sf1[k];
+		if (sf2) sf[k] += sf2[k];
+	}
+}
+
+/*
+ * update_partials(out, p1, m1, p2, m2): out = (M1 x1) o (M2 x2); p2 < 0 => single child.
+ * treelikelihoodX.c:43-102 (dispatch), treelikelihood4.c:1409-1467.
+ */
+static void update_partials(Work *w, int out_idx, int p1, int m1, int p2, int m2, double *tmp) {
+	const OracleProblem *pb = w->pb;
+	double *out = (double *)node_partials(w, out_idx);
+	message(w, w->mat + (size_t)m1 * w->msize, node_partials(w, p1), node_states(w, p1), 1, out);
+	if (p2 >= 0) {
+		message(w, w->mat + (size_t)m2 * w->msize, node_partials(w, p2), node_states(w, p2), 1, tmp);
+		for (size_t e = 0; e < w->psize; e++) out[e] *= tmp[e];
+	}
+	if (pb->scale) scale_partials(w, out_idx, p1, p2);
+}
+
+/* _calculate_partials, treelikelihood.c:1645-1734 (every node dirty) */
+static void lower_pass(Work *w, int n, double *tmp) {
+	const OracleProblem *pb = w->pb;
+	if (is_tip(pb, n)) return;
+	lower_pass(w, pb->left[n], tmp);
+	lower_pass(w, pb->right[n], tmp);
+	update_partials(w, n, pb->left[n], pb->left[n], pb->right[n], pb->right[n], tmp);
+}
+
+/* update_upper_partials, treelikelihood.c:2129-2161; upper index = id + N */
+static void upper_pass(Work *w, int n, double *tmp) {
+	const OracleProblem *pb = w->pb;
+	const int N = pb->N;
+	if (n != pb->root) {
+		int parent = pb->parent[n];
+		int sib = pb->left[parent] == n ? pb->right[parent] : pb->left[parent];
+		if (parent != pb->root) {
+			/* u_n = (P_p u_p) o (P_s L_s) */
+			update_partials(w, N + n, N + parent, parent, sib, sib, tmp);
+		} else {
+			/* u_n = P_s L_s, optionally times the root frequencies (:2148-2153) */
+			update_partials(w, N + n, sib, sib, -1, -1, tmp);
+			if (pb->include_root_freqs) {
+				double *u = w->upper + (size_t)n * w->psize;
+				for (size_t e = 0; e < w->psize; e++) u[e] *= pb->freqs[e % pb->S];
+			}
+		}
+	}
+	if (!is_tip(pb, n)) {
+		upper_pass(w, pb->left[n], tmp);
+		upper_pass(w, pb->right[n], tmp);
+	}
+}
+
+int oracle_evaluate(const OracleProblem *pb, OracleResult *res) {
+	const int S = pb->S, C = pb->C, P = pb->P, N = pb->N;
+	Work w;
+	w.pb = pb;
+	w.psize = (size_t)C * P * S;
+	w.msize = (size_t)C * S * S;
+	const int want_grad = res->grad != NULL || res->cat_grad != NULL || res->upper != NULL;
+	w.mat = (double *)calloc((size_t)N * w.msize, sizeof(double));
+	w.dmat = (double *)calloc((size_t)N * w.msize, sizeof(double));
+	w.lower = (double *)calloc((size_t)N * w.psize, sizeof(double));
+	w.upper = want_grad ? (double *)calloc((size_t)N * w.psize, sizeof(double)) : NULL;
+	w.sf = (double *)calloc((size_t)2 * N * P, sizeof(double));
+	double *tmp = (double *)malloc(sizeof(double) * w.psize);
+	double *tmp2 = (double *)malloc(sizeof(double) * w.psize);
+	if (!w.mat || !w.dmat || !w.lower || !w.sf || !tmp || !tmp2 || (want_grad && !w.upper)) return 1;
+
+	/* transition matrices, treelikelihood.c:1672-1696 (t = bl * rate_c) */
+	for (int n = 0; n < N; n++) {
+		if (n == pb->root) continue;
+		for (int c = 0; c < C; c++) {
+			double *M = w.mat + (size_t)n * w.msize + (size_t)c * S * S;
+			double *dM = w.dmat + (size_t)n * w.msize + (size_t)c * S * S;
+			if (pb->P_override) {
+				memcpy(M, pb->P_override + (size_t)n * w.msize + (size_t)c * S * S, sizeof(double) * S * S);
+			} else {
+				oracle_p_t(S, pb->evec, pb->eval, pb->ivec, pb->bl[n] * pb->rates[c], M);
+			}
+			if (pb->dP_override) {
+				memcpy(dM, pb->dP_override + (size_t)n * w.msize + (size_t)c * S * S, sizeof(double) * S * S);
+			} else {
+				oracle_dp_dt(S, pb->evec, pb->eval, pb->ivec, pb->bl[n] * pb->rates[c], dM);
+			}
+		}
+	}
+
+	/* tip partials replicated over categories, treelikelihood.c:1106-1117 */
+	if (pb->tip_mode == ORACLE_TIP_PARTIALS) {
+		for (int t = 0; t < pb->T; t++)
+			for (int c = 0; c < C; c++)
+				memcpy(w.lower + (size_t)t * w.psize + (size_t)c * P * S, pb->tip_partials + (size_t)t * P * S,
+				       sizeof(double) * P * S);
+	}
+
+	lower_pass(&w, pb->root, tmp);
+
+	/* integrate_partials_general (treelikelihoodX.c:128-164), node_log_likelihoods_general (:104-126),
+	 * weighted sum (treelikelihood.c:1482-1487) */
+	double *plk = (double *)malloc(sizeof(double) * P);
+	const double *Lr = w.lower + (size_t)pb->root * w.psize;
+	double lnl = 0.0;
+	for (int k = 0; k < P; k++) {
+		double site = 0.0;
+		for (int i = 0; i < S; i++) {
+			double r = 0.0;
+			for (int c = 0; c < C; c++) {
+				double v = Lr[((size_t)c * P + k) * S + i];
+				r += (C == 1) ? v : v * pb->props[c];
+			}
+			site += pb->freqs[i] * r;
+		}
+		plk[k] = log(site);
+		if (pb->scale) plk[k] += w.sf[(size_t)pb->root * P + k]; /* getLogScalingFactor, :1838-1845 */
+		lnl += plk[k] * pb->weights[k];
+	}
+	res->lnl = lnl;
+	if (res->pattern_lnl) memcpy(res->pattern_lnl, plk, sizeof(double) * P);
+
+	if (want_grad) {
+		upper_pass(&w, pb->root, tmp);
+		double *cg = (double *)calloc((size_t)N * C, sizeof(double));
+		/* gradient_cat_branch_lengths, treelikelihood.c:2793-2941 and aux :2715-2789 */
+		for (int n = 0; n < N; n++) {
+			if (n == pb->root) continue;
+			const double *U = w.upper + (size_t)n * w.psize;
+			/* spare = (dP L_n) o U_n : calculate_branch_partials, treelikelihoodX.c:878-1001 */
+			message(&w, w.dmat + (size_t)n * w.msize, node_partials(&w, n), node_states(&w, n), 0, tmp);
+			for (size_t e = 0; e < w.psize; e++) tmp[e] *= U[e];
+			if (pb->scale) {
+				/* spare2 = (P L_n) o U_n  (:2722-2723); same helper => unknown states use row sums */
+				message(&w, w.mat + (size_t)n * w.msize, node_partials(&w, n), node_states(&w, n), 0, tmp2);
+				for (size_t e = 0; e < w.psize; e++) tmp2[e] *= U[e];
+			}
+			if (pb->scale && !pb->compat_scaled_gradient) {
+				/* exact form under rescaling: sum_k w_k * (sum_c prop_c rate_c num[c,k]) / (sum_c prop_c den[c,k]);
+				 * stored so that sum_c cg[n,c] prop_c rate_c reproduces it (cg[n,c] shares one denominator). */
+				for (int k = 0; k < P; k++) {
+					double den = 0.0;
+					for (int c = 0; c < C; c++) {
+						double d = 0.0;
+						for (int i = 0; i < S; i++)
+							d += (pb->include_root_freqs ? 1.0 : pb->freqs[i]) * tmp2[((size_t)c * P + k) * S + i];
+						den += (C == 1 ? 1.0 : pb->props[c]) * d;
+					}
+					for (int c = 0; c < C; c++) {
+						double num = 0.0;
+						for (int i = 0; i < S; i++)
+							num += (pb->include_root_freqs ? 1.0 : pb->freqs[i]) * tmp[((size_t)c * P + k) * S + i];
+						cg[(size_t)n * C + c] += num / den * pb->weights[k];
+					}
+				}
+				continue;
+			}
+			for (int c = 0; c < C; c++) {
+				double acc = 0.0;
+				for (int k = 0; k < P; k++) {
+					double num = 0.0, den = 0.0;
+					for (int i = 0; i < S; i++) {
+						double f = pb->include_root_freqs ? 1.0 : pb->freqs[i];
+						num += f * tmp[((size_t)c * P + k) * S + i];
+						if (pb->scale) den += f * tmp2[((size_t)c * P + k) * S + i];
+					}
+					if (!pb->scale) den = exp(plk[k]); /* pattern_likelihoods, :3207-3210 */
+					acc += num / den * pb->weights[k];
+				}
+				cg[(size_t)n * C + c] = acc;
+			}
+		}
+		/* unrooted: the root's right child carries no gradient, treelikelihood.c:3249-3255 */
+		if (pb->unrooted) {
+			int r = pb->right[pb->root];
+			for (int c = 0; c < C; c++) cg[(size_t)r * C + c] = 0.0;
+		}
+		if (res->cat_grad) memcpy(res->cat_grad, cg, sizeof(double) * N * C);
+		if (res->grad) {
+			/* gradient_branch_length_from_cat_inplace, :3129-3143; only applied when C > 1 (:3258-3266) */
+			for (int n = 0; n < N; n++) {
+				if (C == 1) {
+					res->grad[n] = cg[n];
+				} else {
+					double g = 0.0;
+					for (int c = 0; c < C; c++) g += cg[(size_t)n * C + c] * pb->props[c] * pb->rates[c];
+					res->grad[n] = g;
+				}
+			}
+		}
+		free(cg);
+	}
+
+	if (res->lower) memcpy(res->lower, w.lower, sizeof(double) * N * w.psize);
+	if (res->upper) memcpy(res->upper, w.upper, sizeof(double) * N * w.psize);
+	if (res->matrices) memcpy(res->matrices, w.mat, sizeof(double) * N * w.msize);
+	if (res->dmatrices) memcpy(res->dmatrices, w.dmat, sizeof(double) * N * w.msize);
+	if (res->scaling) memcpy(res->scaling, w.sf, sizeof(double) * N * P);
+
+	free(plk);
+	free(tmp);
+	free(tmp2);
+	free(w.mat);
+	free(w.dmat);
+	free(w.lower);
+	free(w.upper);
+	free(w.sf);
+	return 0;
+}

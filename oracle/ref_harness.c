@@ -1,0 +1,349 @@
+/*
+ * ref_harness.c -- thin C harness over the UNMODIFIED reference (libphyc compiled from
+ * /root/reference by oracle/Makefile into oracle/_ref/).
+ *
+ * TEST INFRASTRUCTURE ONLY.  Used to (a) validate oracle/phb_oracle.c, (b) generate the golden
+ * fixtures under tests/golden/ (oracle/make_golden.py) and (c) time the reference's CPU path for
+ * bench.py's cpu_baseline / --impl reference legs.  Never loaded by the product path.
+ *
+ * It builds a "treelikelihood" Model through the reference's own JSON constructor
+ * (treelikelihood.c:819) from a JSON text passed by the caller (inline "sequences" and "newick",
+ * so no files are needed at run time) and exposes plain-array getters for everything the
+ * B200 path takes as input and everything it must reproduce.
+ *
+ * Compiled against the reference headers where they lie (-I/root/reference/src); this file
+ * contains no reference code.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "phyc/branchmodel.h"
+#include "phyc/datatype.h"
+#include "phyc/gy94.h"
+#include "phyc/sequence.h"
+#include "phyc/simplex.h"
+#include "phyc/hashtable.h"
+#include "phyc/matrix.h"
+#include "phyc/mjson.h"
+#include "phyc/parameters.h"
+#include "phyc/sitemodel.h"
+#include "phyc/sitepattern.h"
+#include "phyc/substmodel.h"
+#include "phyc/tree.h"
+#include "phyc/treelikelihood.h"
+
+typedef struct RefH {
+	Hashtable *hash;
+	json_node *json;
+	Model *model;
+	SingleTreeLikelihood *tlk;
+} RefH;
+
+void *refh_create(const char *json_text) {
+	RefH *h = (RefH *)calloc(1, sizeof(RefH));
+	h->hash = new_Hashtable_string(100);
+	hashtable_set_key_ownership(h->hash, false);
+	hashtable_set_value_ownership(h->hash, false);
+	h->json = create_json_tree(json_text);
+	json_node *child = h->json->children[0];
+	h->model = new_TreeLikelihoodModel_from_json(child, h->hash);
+	h->tlk = (SingleTreeLikelihood *)h->model->obj;
+	if (Tree_is_time_mode(h->tlk->tree)) Tree_update_heights(h->tlk->tree);
+	return h;
+}
+
+/*
+ * GY94 codon model built through the C API: the JSON factory has empty GY94/MG94 branches
+ * (substmodel.c:1526-1537) and the shipped >= 60-state dispatcher is stale (SURVEY 8c caveat 1),
+ * so the generic function pointers are installed by hand and tip partials are used.
+ */
+void *refh_create_codon(const char *newick, int n, const char **names, const char **seqs, double kappa, double omega) {
+	RefH *h = (RefH *)calloc(1, sizeof(RefH));
+	DataType *dt = new_CodonDataType(0);
+	Sequences *aln = new_Sequences(n);
+	for (int i = 0; i < n; i++) Sequences_add(aln, new_Sequence(names[i], seqs[i]));
+	aln->datatype = dt;
+	SitePattern *sp = new_SitePattern(aln);
+	free_Sequences(aln);
+	Tree *tree = new_Tree(newick, true);
+	Model *mtree = new_TreeModel("tree", tree);
+	int S = dt->state_count(dt);
+	double *f = (double *)malloc(sizeof(double) * S);
+	for (int i = 0; i < S; i++) f[i] = 1.0 / S;
+	Simplex *fs = new_Simplex_with_values("freqs", f, S);
+	free(f);
+	Model *mfs = new_SimplexModel("freqs", fs);
+	SubstitutionModel *m = new_GY94_with_values(fs, omega, kappa, 0);
+	Model *mm = new_SubstitutionModel2("sm", m, mfs, NULL);
+	SiteModel *sm = new_SiteModel_with_parameters(NULL, NULL, 1, DISTRIBUTION_UNIFORM, false, QUADRATURE_QUANTILE_MEDIAN);
+	Model *msm = new_SiteModel2("sitemodel", sm, NULL);
+	SingleTreeLikelihood *tlk = new_SingleTreeLikelihood(tree, m, sm, sp, NULL, false);
+	h->model = new_TreeLikelihoodModel("treelikelihood", tlk, mtree, mm, msm, NULL);
+	h->tlk = tlk;
+	extern void refh_use_generic_kernels(void *);
+	refh_use_generic_kernels(h);
+	return h;
+}
+
+void refh_free(void *vh) {
+	RefH *h = (RefH *)vh;
+	if (h->hash != NULL) { /* models built by hand are left to the process exit */
+		h->model->free(h->model);
+		free_Hashtable(h->hash);
+		json_free_tree(h->json);
+	}
+	free(h);
+}
+
+/* out: T, N, S, C, P, root, time_mode, scale, use_tip_states, right child of root */
+void refh_dims(void *vh, int *out) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	out[0] = Tree_tip_count(tlk->tree);
+	out[1] = Tree_node_count(tlk->tree);
+	out[2] = tlk->m->nstate;
+	out[3] = tlk->cat_count;
+	out[4] = tlk->pattern_count;
+	out[5] = Node_id(Tree_root(tlk->tree));
+	out[6] = Tree_is_time_mode(tlk->tree);
+	out[7] = tlk->scale;
+	out[8] = tlk->use_tip_states;
+	out[9] = Node_id(Tree_root(tlk->tree)->right);
+}
+
+void refh_topology(void *vh, int *left, int *right, int *parent) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	int N = Tree_node_count(tlk->tree);
+	for (int i = 0; i < N; i++) {
+		Node *n = Tree_node(tlk->tree, i);
+		int id = Node_id(n);
+		left[id] = n->left ? Node_id(n->left) : -1;
+		right[id] = n->right ? Node_id(n->right) : -1;
+		parent[id] = n->parent ? Node_id(n->parent) : -1;
+	}
+}
+
+/* effective branch lengths as _calculate_partials reads them (treelikelihood.c:1652-1663) */
+void refh_branch_lengths(void *vh, double *bl, double *dt) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	int N = Tree_node_count(tlk->tree);
+	int time_mode = Tree_is_time_mode(tlk->tree);
+	if (time_mode) Tree_update_heights(tlk->tree);
+	for (int i = 0; i < N; i++) {
+		Node *n = Tree_node(tlk->tree, i);
+		int id = Node_id(n);
+		if (Node_isroot(n)) {
+			bl[id] = 0;
+			if (dt) dt[id] = 0;
+			continue;
+		}
+		if (tlk->bm == NULL || !time_mode) {
+			bl[id] = Node_distance(n);
+			if (dt) dt[id] = 0;
+		} else {
+			bl[id] = tlk->bm->get(tlk->bm, n) * Node_time_elapsed(n);
+			if (dt) dt[id] = Node_time_elapsed(n);
+		}
+	}
+}
+
+void refh_set_branch_lengths(void *vh, const double *bl) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	int N = Tree_node_count(tlk->tree);
+	for (int i = 0; i < N; i++) {
+		Node *n = Tree_node(tlk->tree, i);
+		if (!Node_isroot(n)) Node_set_distance(n, bl[Node_id(n)]);
+	}
+	SingleTreeLikelihood_update_all_nodes(tlk);
+}
+
+/* uint8 states per tip node id (rows follow node ids through tlk->mapping) */
+void refh_tip_states(void *vh, uint8_t *out) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	int N = Tree_node_count(tlk->tree);
+	int P = tlk->pattern_count;
+	for (int i = 0; i < N; i++) {
+		Node *n = Tree_node(tlk->tree, i);
+		if (!Node_isleaf(n)) continue;
+		int id = Node_id(n);
+		memcpy(out + (size_t)id * P, tlk->sp->patterns[tlk->mapping[id]], P);
+	}
+}
+
+/* tip partials [T][P][S] through sp->get_partials (treelikelihood.c:1109) */
+void refh_tip_partials(void *vh, double *out) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	int N = Tree_node_count(tlk->tree);
+	int P = tlk->pattern_count, S = tlk->m->nstate;
+	for (int i = 0; i < N; i++) {
+		Node *n = Tree_node(tlk->tree, i);
+		if (!Node_isleaf(n)) continue;
+		int id = Node_id(n);
+		tlk->sp->get_partials(tlk->sp, tlk->mapping[id], out + (size_t)id * P * S);
+	}
+}
+
+void refh_weights(void *vh, double *out) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	memcpy(out, tlk->sp->weights, sizeof(double) * tlk->pattern_count);
+}
+
+/* eigen system + frequencies; returns 1 when the model keeps an eigen decomposition */
+int refh_model(void *vh, double *evec, double *eval, double *ivec, double *freqs) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	SubstitutionModel *m = tlk->m;
+	int S = m->nstate;
+	const double *f = tlk->get_root_frequencies(tlk);
+	memcpy(freqs, f, sizeof(double) * S);
+	if (m->need_update) {
+		m->update_Q(m);
+		if (m->eigendcmp != NULL && m->modeltype != JC69) update_eigen_system(m);
+	}
+	if (m->eigendcmp == NULL || m->modeltype == JC69) return 0;
+	for (int i = 0; i < S; i++) {
+		eval[i] = m->eigendcmp->eval[i];
+		for (int j = 0; j < S; j++) {
+			evec[i * S + j] = m->eigendcmp->evec[i][j];
+			ivec[i * S + j] = m->eigendcmp->Invevec[i][j];
+		}
+	}
+	return 1;
+}
+
+void refh_sitemodel(void *vh, double *rates, double *props) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	tlk->sm->update(tlk->sm);
+	double *p = tlk->sm->get_proportions(tlk->sm);
+	for (int c = 0; c < tlk->cat_count; c++) {
+		rates[c] = tlk->sm->get_rate(tlk->sm, c);
+		props[c] = p[c];
+	}
+}
+
+/* row-major P(t) and dP/dt per (node, category) straight from m->p_t / m->dp_dt */
+void refh_matrices(void *vh, double *Pm, double *dPm) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	int N = Tree_node_count(tlk->tree);
+	int S = tlk->m->nstate, C = tlk->cat_count;
+	double *bl = (double *)malloc(sizeof(double) * N);
+	refh_branch_lengths(vh, bl, NULL);
+	tlk->sm->update(tlk->sm);
+	for (int id = 0; id < N; id++) {
+		for (int c = 0; c < C; c++) {
+			double t = bl[id] * tlk->sm->get_rate(tlk->sm, c);
+			size_t off = ((size_t)id * C + c) * S * S;
+			if (id == Node_id(Tree_root(tlk->tree))) {
+				memset(Pm + off, 0, sizeof(double) * S * S);
+				memset(dPm + off, 0, sizeof(double) * S * S);
+				continue;
+			}
+			tlk->m->p_t(tlk->m, t, Pm + off);
+			tlk->m->dp_dt(tlk->m, t, dPm + off);
+		}
+	}
+	free(bl);
+}
+
+void refh_use_rescaling(void *vh, int use) { SingleTreeLikelihood_use_rescaling(((RefH *)vh)->tlk, use != 0); }
+int refh_rescaling(void *vh) { return ((RefH *)vh)->tlk->scale; }
+void refh_enable_sse(void *vh, int v) { SingleTreeLikelihood_enable_SSE(((RefH *)vh)->tlk, v != 0); }
+void refh_set_include_jacobian(void *vh, int v) { ((RefH *)vh)->tlk->include_jacobian = v != 0; }
+
+/* codon and other >= 60-state models: the shipped dispatcher is stale (SURVEY 8c caveat 1) */
+void refh_use_generic_kernels(void *vh) {
+	extern void update_partials_general(SingleTreeLikelihood *, int, int, int, int, int);
+	extern void integrate_partials_general(const SingleTreeLikelihood *, const double *, const double *, double *);
+	extern void node_log_likelihoods_general(const SingleTreeLikelihood *, const double *, const double *, double *);
+	extern void calculate_branch_partials(SingleTreeLikelihood *, double *, int, int, int);
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	tlk->update_partials = update_partials_general;
+	tlk->integrate_partials = integrate_partials_general;
+	tlk->node_log_likelihoods = node_log_likelihoods_general;
+	tlk->calculate_per_cat_partials = calculate_branch_partials;
+}
+
+/* full recomputation, protocol of examples/benchmarking.c:466-471 */
+double refh_logP(void *vh) {
+	RefH *h = (RefH *)vh;
+	SingleTreeLikelihood_update_all_nodes(h->tlk);
+	h->tlk->m->need_update = true;
+	return h->model->logP(h->model);
+}
+
+void refh_pattern_lnl(void *vh, double *out) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	memcpy(out, tlk->pattern_lk, sizeof(double) * tlk->pattern_count);
+}
+
+/*
+ * TreeLikelihood_initialize_gradient(flags) then TreeLikelihood_gradient (treelikelihood.c:237,320).
+ * include_root_freqs: -1 keep what initialize_gradient set, else override (public field, :123).
+ * Returns the gradient length; out receives min(length, cap) values.
+ */
+int refh_gradient(void *vh, int flags, int include_root_freqs, double *out, int cap) {
+	RefH *h = (RefH *)vh;
+	size_t len = TreeLikelihood_initialize_gradient(h->model, flags);
+	if (include_root_freqs >= 0) h->tlk->include_root_freqs = include_root_freqs != 0;
+	SingleTreeLikelihood_update_all_nodes(h->tlk);
+	h->tlk->m->need_update = true;
+	double *g = TreeLikelihood_gradient(h->model);
+	for (size_t i = 0; i < len && (int)i < cap; i++) out[i] = g[i];
+	return (int)len;
+}
+
+/* copy of one partials buffer: idx < N lower (NULL for state tips -> returns 0), idx >= N upper */
+int refh_partials(void *vh, int idx, double *out) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	double *p = tlk->partials[tlk->current_partials_indexes[idx]][idx];
+	if (p == NULL) return 0;
+	memcpy(out, p, sizeof(double) * tlk->partials_size);
+	return 1;
+}
+
+int refh_scaling_factors(void *vh, int idx, double *out) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	if (!tlk->scale || tlk->scaling_factors == NULL) return 0;
+	double *p = tlk->scaling_factors[tlk->current_partials_indexes[idx]][idx];
+	if (p == NULL) return 0;
+	memcpy(out, p, sizeof(double) * tlk->pattern_count);
+	return 1;
+}
+
+static double now_s(void) {
+	struct timespec ts;
+	clock_gettime(CLOCK_MONOTONIC_RAW, &ts);
+	return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+/* seconds per lnL evaluation, examples/benchmarking.c:466-471 */
+double refh_time_logP(void *vh, int iters, double *last) {
+	RefH *h = (RefH *)vh;
+	double v = 0;
+	double t0 = now_s();
+	for (int i = 0; i < iters; i++) {
+		SingleTreeLikelihood_update_all_nodes(h->tlk);
+		h->tlk->m->need_update = true;
+		v = h->model->logP(h->model);
+	}
+	double t1 = now_s();
+	if (last) *last = v;
+	return (t1 - t0) / iters;
+}
+
+/* seconds per lnL + gradient evaluation, examples/benchmarking.c:498-503 */
+double refh_time_gradient(void *vh, int flags, int include_root_freqs, int iters) {
+	RefH *h = (RefH *)vh;
+	TreeLikelihood_initialize_gradient(h->model, flags);
+	if (include_root_freqs >= 0) h->tlk->include_root_freqs = include_root_freqs != 0;
+	double t0 = now_s();
+	for (int i = 0; i < iters; i++) {
+		SingleTreeLikelihood_update_all_nodes(h->tlk);
+		h->tlk->m->need_update = true;
+		TreeLikelihood_gradient(h->model);
+	}
+	double t1 = now_s();
+	return (t1 - t0) / iters;
+}

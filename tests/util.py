@@ -1,0 +1,46 @@
+"""Shared helpers for the parity tests: golden fixtures -> oracle.Problem, tolerances."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+
+from oracle import oracle as O
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# north_star: lnL and every branch gradient within 1e-10 relative in FP64.
+# Gradient entries are compared relative to max(|g|, |g|_inf * 1e-6).
+RTOL = 1e-10
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def load_golden(name: str):
+    z = dict(np.load(os.path.join(GOLDEN, name + ".npz")))
+    pb = O.Problem(
+        left=z["left"], right=z["right"], parent=z["parent"], root=int(z["root"]), nstate=int(z["nstate"]),
+        tip_states=z["tip_states"], weights=z["weights"], freqs=z["freqs"], rates=z["rates"], props=z["props"], bl=z["bl"],
+        use_tip_states=bool(z["use_tip_states"]), unrooted=bool(z["unrooted"]),
+    )
+    if "tip_partials" in z:
+        pb.tip_partials = z["tip_partials"].astype(np.float64)
+    if "evec" in z:
+        pb.evec, pb.eval, pb.ivec = z["evec"], z["eval"], z["ivec"]
+    else:
+        pb.P_override, pb.dP_override = z["P_override"], z["dP_override"]
+    pb.meta["time_elapsed"] = z["time_elapsed"]
+    return pb, z
+
+
+def rel_err(a: float, b: float) -> float:
+    return abs(a - b) / max(abs(b), 1e-300)
+
+
+def grad_err(g: np.ndarray, ref: np.ndarray) -> float:
+    scale = np.maximum(np.abs(ref), np.abs(ref).max() * 1e-6)
+    scale = np.where(scale == 0, 1.0, scale)
+    return float(np.max(np.abs(g - ref) / scale))
