@@ -1,0 +1,150 @@
+/*
+ * physher_b200.h -- C ABI of the B200-native tree-likelihood path.
+ *
+ * Drop-in boundary for physher's src/phyc/treelikelihood*.c (reference paths below are relative
+ * to /root/reference/src/phyc/).  Plain pointers and sizes only; the caller keeps ownership of
+ * every array it passes.  All arrays are host memory unless a name ends in `_device`.
+ *
+ * The object mirrors `struct _SingleTreeLikelihood` (treelikelihood.h:46-124).  Where the
+ * reference reads its collaborators through raw struct pointers on every evaluation
+ * (Tree*, SubstitutionModel*, SiteModel*, SitePattern*; treelikelihood.c:1007), this ABI takes the
+ * same data as plain arrays through setters; a setter marks the matching state dirty exactly as
+ * the reference's listener does (_treelikelihood_handle_change, treelikelihood.c:73-114).
+ * INTEGRATION.md shows the glue a physher maintainer adds on top of these entry points.
+ *
+ * Node ids: tips 0..T-1, internal nodes T..2T-2 (tree.c:183-199); N = 2T-1.
+ * Layouts: matrices [node][category][i = parent state][j = child state] row-major
+ * (substmodel.c:547-555); partials [category][pattern][state] (treelikelihood.c:1028).
+ *
+ * Error convention: functions return PHB_OK (0) or a negative PHB_E* code and keep a message
+ * retrievable with phb_last_error().  The reference has no error codes (stderr + exit(),
+ * treelikelihood.c:1099-1100); the glue maps a non-zero return to that behaviour.  Numerical
+ * conventions are kept: NaN lnL marks everything dirty, +-inf lnL switches rescaling on and
+ * recomputes (treelikelihood.c:1489-1519); the gradient is NaN-filled when lnL is NaN/inf (:328-332).
+ * There is NO CPU fallback: without a CUDA device every compute entry point fails with PHB_ECUDA.
+ */
+#ifndef PHYSHER_B200_H
+#define PHYSHER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHB_OK 0
+#define PHB_EINVAL (-1) /* bad argument                                   */
+#define PHB_ECUDA (-2)  /* CUDA runtime error / no device                 */
+#define PHB_ENOMEM (-3) /* host or device allocation failed               */
+#define PHB_ESTATE (-4) /* call order: an input has not been set yet      */
+
+/* gradient request flags == TREELIKELIHOOD_FLAG_* (treelikelihood.h:32-38) */
+#define PHB_FLAG_TREE_MODEL (1 << 0)
+#define PHB_FLAG_SITE_MODEL (1 << 1)
+#define PHB_FLAG_SUBSTITUTION_MODEL (1 << 2)
+#define PHB_FLAG_BRANCH_MODEL (1 << 6)
+
+/* options for phb_tlk_set_option */
+#define PHB_OPT_INCLUDE_ROOT_FREQS 1     /* tlk->include_root_freqs (treelikelihood.h:123); default 0 = exact form */
+#define PHB_OPT_COMPAT_SCALED_GRADIENT 2 /* 1: per-category normalisation under rescaling as treelikelihood.c:2721-2738 */
+#define PHB_OPT_UNROOTED 3               /* 1 (default): zero the root's right child gradient (treelikelihood.c:3249-3255) */
+#define PHB_OPT_KERNELS 4                /* PHB_KERNELS_* : force a kernel family (testing / profiling) */
+#define PHB_OPT_SCALING_THRESHOLD_EXP 5  /* tlk->scaling_threshold = 10^-value (default 40, treelikelihood.c:1121) */
+
+#define PHB_KERNELS_AUTO 0    /* by state count, like the function-pointer dispatch at treelikelihood.c:1067-1165 */
+#define PHB_KERNELS_GENERIC 1 /* node-at-a-time kernels, any state count, materialised upper partials */
+#define PHB_KERNELS_FUSED 2   /* whole-tree walk kernels (4 states) / tensor-core kernels (20, 61 states) */
+
+typedef struct phb_tlk phb_tlk; /* mirrors SingleTreeLikelihood */
+
+const char *phb_last_error(void);
+int phb_device_count(void);
+const char *phb_version(void);
+
+/* new_SingleTreeLikelihood (treelikelihood.c:1007-1185).
+ * left/right: [N] child ids (-1 for tips).  use_tip_states as the reference's argument:
+ * non-zero => tips are uint8 states (state >= nstate is unknown), zero => tip partial vectors.
+ * device: CUDA ordinal.  Returns NULL on failure (see phb_last_error). */
+phb_tlk *phb_tlk_create(int ntips, int nstate, int ncat, int npatterns, const int *left, const int *right, int root,
+                        int use_tip_states, int device);
+
+/* free_SingleTreeLikelihood (treelikelihood.c:1187-1230) */
+void phb_tlk_free(phb_tlk *tlk);
+
+/* SitePattern inputs (sitepattern.h:68-82): patterns[taxon][pattern] by TIP NODE ID and weights[pattern] */
+int phb_tlk_set_tip_states(phb_tlk *tlk, const uint8_t *states /* [T][P] */);
+int phb_tlk_set_tip_partials(phb_tlk *tlk, const double *partials /* [T][P][S], sp->get_partials */);
+int phb_tlk_set_pattern_weights(phb_tlk *tlk, const double *weights /* [P] */);
+
+/* SubstitutionModel inputs: the host-side eigen decomposition (eigen.h EigenDecomposition) ... */
+int phb_tlk_set_eigen(phb_tlk *tlk, const double *evec, const double *eval, const double *ivec);
+/* ... or, for closed-form models (jc69.c:73, hky.c:230), explicit P and dP/dt [N][C][S][S] from m->p_t / m->dp_dt */
+int phb_tlk_set_matrices(phb_tlk *tlk, const double *P, const double *dP);
+/* tlk->get_root_frequencies (treelikelihood.c:1946-1953) */
+int phb_tlk_set_frequencies(phb_tlk *tlk, const double *freqs /* [S] */);
+
+/* SiteModel inputs: sm->get_rate(c) (already times mu) and sm->get_proportions (sitemodel.h:38-73) */
+int phb_tlk_set_site_model(phb_tlk *tlk, const double *rates /* [C] */, const double *proportions /* [C] */);
+
+/* branch lengths as _calculate_partials reads them (treelikelihood.c:1652-1663): Node_distance or rate*dt */
+int phb_tlk_set_branch_lengths(phb_tlk *tlk, const double *bl /* [N], root entry ignored */);
+int phb_tlk_set_branch_length(phb_tlk *tlk, int node, double bl); /* + SingleTreeLikelihood_update_one_node */
+
+/* SingleTreeLikelihood_update_all_nodes / _update_one_node (treelikelihood.c:1737-1751) */
+void phb_tlk_update_all_nodes(phb_tlk *tlk);
+int phb_tlk_update_one_node(phb_tlk *tlk, int node);
+
+/* SingleTreeLikelihood_use_rescaling / _rescaling (treelikelihood.h:163-164) */
+int phb_tlk_use_rescaling(phb_tlk *tlk, int use);
+int phb_tlk_rescaling(const phb_tlk *tlk);
+
+int phb_tlk_set_option(phb_tlk *tlk, int option, int value);
+
+/* tlk->calculate (treelikelihood.c:1552 -> _calculate_simple :1454): cached unless something is dirty */
+int phb_tlk_calculate(phb_tlk *tlk, double *lnl);
+
+/* per-pattern log likelihoods, tlk->pattern_lk (treelikelihood.c:1480) */
+int phb_tlk_pattern_log_likelihoods(phb_tlk *tlk, double *out /* [P] */);
+
+/* TreeLikelihood_initialize_gradient (treelikelihood.c:237-318): returns the gradient length for `flags`.
+ * Supported here: PHB_FLAG_TREE_MODEL on branch-length trees => N entries indexed by node id. */
+size_t phb_tlk_initialize_gradient(phb_tlk *tlk, int flags);
+
+/* TreeLikelihood_gradient (treelikelihood.c:320-340): lnL + pre-order pass + branch gradients.
+ * *grad points at a buffer OWNED BY tlk (as in the reference), valid until the next call. */
+int phb_tlk_gradient(phb_tlk *tlk, const double **grad);
+
+/* cat_branch_gradient [N][C] of the last gradient call (gradient_cat_branch_lengths, treelikelihood.c:2793) */
+int phb_tlk_cat_branch_gradient(phb_tlk *tlk, double *out /* [N][C] */);
+
+/* Copy of one partials buffer [C][P][S]: index < N lower partials of that node, >= N upper partials of node
+ * index-N (tlk->partials[..][index], treelikelihood.h:62; used by asr.c:60).  Generic kernels only. */
+int phb_tlk_get_partials(phb_tlk *tlk, int index, double *out);
+/* Transition matrices as the device built them, [N][C][S][S] each (either pointer may be NULL) */
+int phb_tlk_get_matrices(phb_tlk *tlk, double *P, double *dP);
+
+/*
+ * Multi-GPU / batched entry points (no counterpart in the reference).
+ *
+ * phb_tlk_gradient_device: same work as phb_tlk_gradient, result left ON THE DEVICE as
+ * out_device[0] = lnL, out_device[1..N] = gradient by node id, ordered on the tlk's stream, so that a
+ * pattern-sharded caller can all-reduce [lnL, grad] once (NCCL) without a host round trip.
+ * The NaN / +-inf handling of phb_tlk_gradient is the caller's job here (it needs the reduced lnL).
+ */
+int phb_tlk_gradient_device(phb_tlk *tlk, double *out_device /* [1+N] */);
+/* cudaStream_t the tlk launches on (as void*), for ordering external work after it */
+void *phb_tlk_stream(phb_tlk *tlk);
+int phb_tlk_synchronize(phb_tlk *tlk);
+
+/* B branch-length vectors sharing topology, patterns and models: lnl[b], grad[b][N]. */
+int phb_tlk_gradient_batch(phb_tlk *tlk, int nbatch, const double *bl /* [B][N] */, double *lnl /* [B] */,
+                           double *grad /* [B][N] */);
+
+/* number of kernel launches issued by this tlk since creation (bench.py's gpu_launches) */
+long long phb_tlk_launch_count(const phb_tlk *tlk);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

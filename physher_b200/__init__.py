@@ -1,0 +1,21 @@
+"""physher_b200 -- B200-native (sm_100a) tree-likelihood path behind physher's SingleTreeLikelihood API.
+
+The product is the C-ABI shared library `libphysher_b200.so` (include/physher_b200.h); this package
+holds its sources (csrc/), the in-tree build and a ctypes mirror of the reference interface used by
+the tests and the benchmark.  There is no CPU fallback: importing works anywhere, computing needs a GPU.
+"""
+from .treelikelihood import (  # noqa: F401
+    FLAG_TREE_MODEL,
+    KERNELS_AUTO,
+    KERNELS_FUSED,
+    KERNELS_GENERIC,
+    PhysherB200Error,
+    SingleTreeLikelihood,
+    device_count,
+    load_library,
+)
+
+__all__ = [
+    "SingleTreeLikelihood", "PhysherB200Error", "load_library", "device_count",
+    "FLAG_TREE_MODEL", "KERNELS_AUTO", "KERNELS_GENERIC", "KERNELS_FUSED",
+]

@@ -1,0 +1,83 @@
+// phb_ctx.cuh -- device context shared by the kernel translation units (internal).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "phb_cuda.h"
+
+struct phbc_ctx {
+	int device, T, N, S, C, P, root, tip_kind;
+	cudaStream_t stream;
+	int num_sms;
+	size_t smem_optin;
+
+	// inputs
+	uint8_t *d_tip_states;   // [T][P]
+	double *d_tip_partials;  // [T][P][S]
+	double *d_weights;       // [P]
+	double *d_evec, *d_eval, *d_ivec;  // eigen system
+	double *d_qmat;          // [S][S] Q = V diag(eval) V^-1 (rate matrix, for dP = Q P)
+	double *d_freqs, *d_rates, *d_props;
+	double *d_bl;            // [bl_cap][N]
+	double *h_bl;            // pinned staging
+	int bl_cap;
+	bool have_eigen;
+
+	// node-at-a-time state
+	double *d_P, *d_dP;      // [N][C][S*S]
+	double *d_lower;         // [N-T][C][P][S]
+	double *d_upper;         // [N][C][P][S]   (lazy)
+	double *d_sf;            // [2N][P]        (lazy)
+	phbc_op *d_lower_ops, *d_upper_ops;
+	int n_lower_ops, n_upper_ops;
+	int *h_lower_level_off, *h_upper_level_off;
+	int n_lower_levels, n_upper_levels;
+
+	// fused walk state (phb_nuc4.cu)
+	phbc_post_op *d_post_ops;
+	phbc_pre_op *d_pre_ops;
+	int n_post, n_pre, post_slots, pre_slots;
+	double *d_walk_mats;     // schedule-ordered transition matrices
+	double *d_walk_lower;    // per-CTA lower-partial scratch
+	double *d_walk_gacc;     // per-CTA gradient accumulators
+	size_t walk_lower_bytes, walk_gacc_bytes, walk_mats_bytes;
+
+	// outputs
+	double *d_pattern_lnl;   // [P]
+	double *d_result;        // [result_cap][1+N]
+	int result_cap;
+	double *d_cat_grad;      // [N][C]
+	double *d_scratch;       // reduction scratch
+	size_t scratch_bytes;
+
+	long long launches;
+};
+
+extern thread_local char phbc_errbuf[512];
+
+#define PHBC_CHECK(call)                                                                                     \
+	do {                                                                                                     \
+		cudaError_t e__ = (call);                                                                            \
+		if (e__ != cudaSuccess) {                                                                            \
+			snprintf(phbc_errbuf, sizeof(phbc_errbuf), "%s:%d: %s: %s", __FILE__, __LINE__, #call,          \
+			         cudaGetErrorString(e__));                                                               \
+			return -2;                                                                                       \
+		}                                                                                                    \
+	} while (0)
+
+int phbc_ensure_scratch(phbc_ctx *ctx, size_t bytes);
+
+// generic node-at-a-time path (phb_cuda.cu)
+int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
+// fused 4-state walk path (phb_nuc4.cu)
+int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
+bool phbc_nuc4_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);
+
+// shared device helpers
+__device__ __forceinline__ double phb_warp_sum(double v) {
+#pragma unroll
+	for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+	return v;
+}

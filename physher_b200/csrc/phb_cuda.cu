@@ -1,0 +1,724 @@
+// phb_cuda.cu -- device context, uploads, transition-matrix kernel and the generic
+// node-at-a-time kernels (any state count) of the B200 tree-likelihood path.
+//
+// The generic kernels restate, one launch per tree level, what the reference does one node at a
+// time through tlk->update_partials / integrate_partials / node_log_likelihoods /
+// calculate_per_cat_partials (treelikelihood.h:90-111).  They materialise upper partials like the
+// reference (treelikelihood.c:2129-2161) and are the fallback for state counts without a
+// specialised path, for explicit (closed-form) matrices and for phb_tlk_get_partials.
+// The fast paths live in phb_nuc4.cu (4 states) and phb_dmma.cu (20 / 61 states).
+#include "phb_ctx.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+thread_local char phbc_errbuf[512] = "";
+
+extern "C" const char *phbc_last_error(void) { return phbc_errbuf; }
+
+extern "C" int phbc_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+
+template <typename T>
+static int dev_alloc(T **p, size_t count) {
+	PHBC_CHECK(cudaMalloc((void **)p, count * sizeof(T) > 0 ? count * sizeof(T) : 8));
+	return 0;
+}
+
+extern "C" phbc_ctx *phbc_create(int device, int ntips, int nstate, int ncat, int npatterns, int root, int tip_kind) {
+	int ndev = phbc_device_count();
+	if (ndev <= 0) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "no CUDA device visible: the B200 path has no CPU fallback");
+		return NULL;
+	}
+	if (device < 0 || device >= ndev) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "device %d out of range (%d visible)", device, ndev);
+		return NULL;
+	}
+	if (cudaSetDevice(device) != cudaSuccess) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "cudaSetDevice(%d) failed", device);
+		return NULL;
+	}
+	phbc_ctx *ctx = (phbc_ctx *)calloc(1, sizeof(phbc_ctx));
+	if (!ctx) return NULL;
+	ctx->device = device;
+	ctx->T = ntips;
+	ctx->N = 2 * ntips - 1;
+	ctx->S = nstate;
+	ctx->C = ncat;
+	ctx->P = npatterns;
+	ctx->root = root;
+	ctx->tip_kind = tip_kind;
+	cudaDeviceProp prop;
+	cudaGetDeviceProperties(&prop, device);
+	ctx->num_sms = prop.multiProcessorCount;
+	ctx->smem_optin = prop.sharedMemPerBlockOptin;
+	const size_t S = nstate, C = ncat, P = npatterns, N = ctx->N, T = ntips;
+	bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+	ok = ok && dev_alloc(&ctx->d_weights, P) == 0;
+	ok = ok && dev_alloc(&ctx->d_evec, S * S) == 0 && dev_alloc(&ctx->d_ivec, S * S) == 0 && dev_alloc(&ctx->d_eval, S) == 0;
+	ok = ok && dev_alloc(&ctx->d_qmat, S * S) == 0;
+	ok = ok && dev_alloc(&ctx->d_freqs, S) == 0 && dev_alloc(&ctx->d_rates, C) == 0 && dev_alloc(&ctx->d_props, C) == 0;
+	ok = ok && dev_alloc(&ctx->d_pattern_lnl, P) == 0;
+	ok = ok && dev_alloc(&ctx->d_cat_grad, N * C) == 0;
+	ctx->result_cap = 1;
+	ok = ok && dev_alloc(&ctx->d_result, (size_t)ctx->result_cap * (1 + N)) == 0;
+	ctx->bl_cap = 1;
+	ok = ok && dev_alloc(&ctx->d_bl, N) == 0;
+	ok = ok && cudaMallocHost((void **)&ctx->h_bl, N * sizeof(double)) == cudaSuccess;
+	if (tip_kind == PHBC_TIP_STATES)
+		ok = ok && dev_alloc(&ctx->d_tip_states, T * P) == 0;
+	else
+		ok = ok && dev_alloc(&ctx->d_tip_partials, T * P * S) == 0;
+	if (!ok) {
+		if (!phbc_errbuf[0]) snprintf(phbc_errbuf, sizeof(phbc_errbuf), "device allocation failed");
+		phbc_destroy(ctx);
+		return NULL;
+	}
+	return ctx;
+}
+
+extern "C" void phbc_destroy(phbc_ctx *ctx) {
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	void *bufs[] = {ctx->d_tip_states, ctx->d_tip_partials, ctx->d_weights, ctx->d_evec, ctx->d_eval, ctx->d_ivec, ctx->d_qmat,
+	                ctx->d_freqs, ctx->d_rates, ctx->d_props, ctx->d_bl, ctx->d_P, ctx->d_dP, ctx->d_lower, ctx->d_upper,
+	                ctx->d_sf, ctx->d_lower_ops, ctx->d_upper_ops, ctx->d_post_ops, ctx->d_pre_ops, ctx->d_walk_mats,
+	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch};
+	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
+		if (bufs[i]) cudaFree(bufs[i]);
+	if (ctx->h_bl) cudaFreeHost(ctx->h_bl);
+	free(ctx->h_lower_level_off);
+	free(ctx->h_upper_level_off);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	free(ctx);
+}
+
+int phbc_ensure_scratch(phbc_ctx *ctx, size_t bytes) {
+	if (bytes <= ctx->scratch_bytes) return 0;
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+	if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+	ctx->d_scratch = NULL;
+	ctx->scratch_bytes = 0;
+	PHBC_CHECK(cudaMalloc((void **)&ctx->d_scratch, bytes));
+	ctx->scratch_bytes = bytes;
+	return 0;
+}
+
+template <typename T>
+static int upload_array(phbc_ctx *ctx, T **dst, const T *src, size_t count) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	if (*dst) {
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		cudaFree(*dst);
+		*dst = NULL;
+	}
+	if (count == 0) return 0;
+	PHBC_CHECK(cudaMalloc((void **)dst, count * sizeof(T)));
+	PHBC_CHECK(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+	return 0;
+}
+
+extern "C" int phbc_set_schedule(phbc_ctx *ctx, const phbc_schedule *s) {
+	int rc;
+	if ((rc = upload_array(ctx, &ctx->d_lower_ops, s->lower_ops, (size_t)s->n_lower_ops))) return rc;
+	if ((rc = upload_array(ctx, &ctx->d_upper_ops, s->upper_ops, (size_t)s->n_upper_ops))) return rc;
+	if ((rc = upload_array(ctx, &ctx->d_post_ops, s->post_ops, (size_t)s->n_post))) return rc;
+	if ((rc = upload_array(ctx, &ctx->d_pre_ops, s->pre_ops, (size_t)s->n_pre))) return rc;
+	ctx->n_lower_ops = s->n_lower_ops;
+	ctx->n_upper_ops = s->n_upper_ops;
+	ctx->n_lower_levels = s->n_lower_levels;
+	ctx->n_upper_levels = s->n_upper_levels;
+	ctx->n_post = s->n_post;
+	ctx->n_pre = s->n_pre;
+	ctx->post_slots = s->post_slots;
+	ctx->pre_slots = s->pre_slots;
+	free(ctx->h_lower_level_off);
+	free(ctx->h_upper_level_off);
+	ctx->h_lower_level_off = (int *)malloc(sizeof(int) * (s->n_lower_levels + 1));
+	ctx->h_upper_level_off = (int *)malloc(sizeof(int) * (s->n_upper_levels + 1));
+	memcpy(ctx->h_lower_level_off, s->lower_level_off, sizeof(int) * (s->n_lower_levels + 1));
+	memcpy(ctx->h_upper_level_off, s->upper_level_off, sizeof(int) * (s->n_upper_levels + 1));
+	return 0;
+}
+
+#define UPLOAD(dst, src, count)                                                                                \
+	do {                                                                                                       \
+		PHBC_CHECK(cudaSetDevice(ctx->device));                                                                \
+		PHBC_CHECK(cudaMemcpyAsync(dst, src, (count) * sizeof(*(src)), cudaMemcpyHostToDevice, ctx->stream));  \
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));                                                        \
+	} while (0)
+
+extern "C" int phbc_upload_tip_states(phbc_ctx *ctx, const uint8_t *states) {
+	if (!ctx->d_tip_states) return -1;
+	UPLOAD(ctx->d_tip_states, states, (size_t)ctx->T * ctx->P);
+	return 0;
+}
+extern "C" int phbc_upload_tip_partials(phbc_ctx *ctx, const double *partials) {
+	if (!ctx->d_tip_partials) return -1;
+	UPLOAD(ctx->d_tip_partials, partials, (size_t)ctx->T * ctx->P * ctx->S);
+	return 0;
+}
+extern "C" int phbc_upload_weights(phbc_ctx *ctx, const double *w) {
+	UPLOAD(ctx->d_weights, w, (size_t)ctx->P);
+	return 0;
+}
+extern "C" int phbc_upload_eigen(phbc_ctx *ctx, const double *evec, const double *eval, const double *ivec) {
+	const int S = ctx->S;
+	UPLOAD(ctx->d_evec, evec, (size_t)S * S);
+	UPLOAD(ctx->d_eval, eval, (size_t)S);
+	UPLOAD(ctx->d_ivec, ivec, (size_t)S * S);
+	// Q = V diag(lambda) V^-1, used by the fused kernels as dP/dt = Q P(t)
+	double *q = (double *)malloc(sizeof(double) * S * S);
+	for (int i = 0; i < S; i++)
+		for (int j = 0; j < S; j++) {
+			double acc = 0;
+			for (int k = 0; k < S; k++) acc += evec[i * S + k] * eval[k] * ivec[k * S + j];
+			q[i * S + j] = acc;
+		}
+	cudaError_t e = cudaMemcpyAsync(ctx->d_qmat, q, sizeof(double) * S * S, cudaMemcpyHostToDevice, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	free(q);
+	PHBC_CHECK(e);
+	ctx->have_eigen = true;
+	return 0;
+}
+extern "C" int phbc_upload_freqs(phbc_ctx *ctx, const double *freqs) {
+	UPLOAD(ctx->d_freqs, freqs, (size_t)ctx->S);
+	return 0;
+}
+extern "C" int phbc_upload_site_model(phbc_ctx *ctx, const double *rates, const double *props) {
+	UPLOAD(ctx->d_rates, rates, (size_t)ctx->C);
+	UPLOAD(ctx->d_props, props, (size_t)ctx->C);
+	return 0;
+}
+
+static int ensure_node_matrices(phbc_ctx *ctx) {
+	const size_t n = (size_t)ctx->N * ctx->C * ctx->S * ctx->S;
+	if (!ctx->d_P) PHBC_CHECK(cudaMalloc((void **)&ctx->d_P, n * sizeof(double)));
+	if (!ctx->d_dP) PHBC_CHECK(cudaMalloc((void **)&ctx->d_dP, n * sizeof(double)));
+	return 0;
+}
+
+extern "C" int phbc_upload_matrices(phbc_ctx *ctx, const double *P, const double *dP) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	int rc = ensure_node_matrices(ctx);
+	if (rc) return rc;
+	const size_t n = (size_t)ctx->N * ctx->C * ctx->S * ctx->S;
+	UPLOAD(ctx->d_P, P, n);
+	UPLOAD(ctx->d_dP, dP, n);
+	return 0;
+}
+
+extern "C" int phbc_upload_branch_lengths(phbc_ctx *ctx, const double *bl, int nbatch) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	const size_t N = ctx->N;
+	if (nbatch > ctx->bl_cap) {
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_bl);
+		cudaFreeHost(ctx->h_bl);
+		ctx->d_bl = NULL;
+		ctx->h_bl = NULL;
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_bl, (size_t)nbatch * N * sizeof(double)));
+		PHBC_CHECK(cudaMallocHost((void **)&ctx->h_bl, (size_t)nbatch * N * sizeof(double)));
+		ctx->bl_cap = nbatch;
+	}
+	if (nbatch > ctx->result_cap) {
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_result);
+		ctx->d_result = NULL;
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_result, (size_t)nbatch * (1 + N) * sizeof(double)));
+		ctx->result_cap = nbatch;
+	}
+	// the previous async copy out of the pinned staging buffer must have completed
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+	memcpy(ctx->h_bl, bl, (size_t)nbatch * N * sizeof(double));
+	PHBC_CHECK(cudaMemcpyAsync(ctx->d_bl, ctx->h_bl, (size_t)nbatch * N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// transition matrices:  P(t) = |V exp(L t) V^-1|,  dP/dt = V L exp(L t) V^-1   (substmodel.c:518-557, 695-723)
+// one CTA per (node, category)
+// ---------------------------------------------------------------------------------------------
+
+__global__ void k_transition_matrices(int S, int C, int root, const double *__restrict__ evec, const double *__restrict__ eval,
+                                      const double *__restrict__ ivec, const double *__restrict__ bl,
+                                      const double *__restrict__ rates, double *__restrict__ Pm, double *__restrict__ dPm) {
+	extern __shared__ double sm[];
+	double *ex = sm;       // exp(lambda_k t)
+	double *lex = sm + S;  // lambda_k exp(lambda_k t)
+	const int node = blockIdx.x, c = blockIdx.y;
+	if (node == root) return;
+	const double t = bl[node] * rates[c];
+	for (int k = threadIdx.x; k < S; k += blockDim.x) {
+		const double l = eval[k];
+		const double e = exp(l * t);
+		ex[k] = e;
+		lex[k] = l * e;
+	}
+	__syncthreads();
+	const size_t base = ((size_t)node * C + c) * S * S;
+	for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
+		const int i = e / S, j = e % S;
+		double p = 0.0, d = 0.0;
+		for (int k = 0; k < S; k++) {
+			const double vi = evec[i * S + k] * ivec[k * S + j];
+			p += vi * ex[k];
+			d += vi * lex[k];
+		}
+		Pm[base + e] = fabs(p);
+		dPm[base + e] = d;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic kernels
+// ---------------------------------------------------------------------------------------------
+
+struct Bufs {
+	const uint8_t *tip_states;
+	const double *tip_partials;
+	double *lower;
+	double *upper;
+	double *sf;
+	int T, N, S, C, P, tip_kind;
+};
+
+__device__ __forceinline__ const double *partial_ptr(const Bufs &b, int idx, int c) {
+	const size_t PS = (size_t)b.P * b.S;
+	if (idx < b.T) return b.tip_partials + (size_t)idx * PS;
+	if (idx < b.N) return b.lower + ((size_t)(idx - b.T) * b.C + c) * PS;
+	return b.upper + ((size_t)(idx - b.N) * b.C + c) * PS;
+}
+
+__device__ __forceinline__ bool is_state_tip(const Bufs &b, int idx) { return idx < b.T && b.tip_kind == PHBC_TIP_STATES; }
+
+// message_i = sum_j M[i][j] x[j]; state tips gather a column, unknown states give 1 for probability
+// matrices and the real row sum for derivative matrices (treelikelihoodX.c:166-289, 878-1001).
+__device__ __forceinline__ double message(const Bufs &b, int idx, int c, const double *M, int p, int i, bool prob) {
+	const int S = b.S;
+	if (is_state_tip(b, idx)) {
+		const int s = b.tip_states[(size_t)idx * b.P + p];
+		if (s < S) return M[i * S + s];
+		if (prob) return 1.0;
+		double acc = 0.0;
+		for (int j = 0; j < S; j++) acc += M[i * S + j];
+		return acc;
+	}
+	const double *x = partial_ptr(b, idx, c) + (size_t)p * S;
+	double acc = 0.0;
+	for (int j = 0; j < S; j++) acc += M[i * S + j] * x[j];
+	return acc;
+}
+
+#define GEN_PBLK 32
+
+// out = (M_a x_a) o (M_b x_b) [o pi]; grid (ceil(P/32), C, ops in level)   -- K1-K4, K8
+__global__ void k_generic_combine(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ Pm,
+                                  const double *__restrict__ freqs) {
+	extern __shared__ double sm[];
+	const int S = b.S, SS = S * S;
+	double *mA = sm, *mB = sm + SS;
+	const phbc_op op = ops[blockIdx.z];
+	const int c = blockIdx.y;
+	for (int e = threadIdx.x; e < SS; e += blockDim.x) {
+		mA[e] = Pm[((size_t)op.a_mat * b.C + c) * SS + e];
+		if (op.b >= 0) mB[e] = Pm[((size_t)op.b_mat * b.C + c) * SS + e];
+	}
+	__syncthreads();
+	double *out = (double *)partial_ptr(b, op.out, c);
+	const int p0 = blockIdx.x * GEN_PBLK;
+	for (int e = threadIdx.x; e < GEN_PBLK * S; e += blockDim.x) {
+		const int p = p0 + e / S, i = e % S;
+		if (p >= b.P) break;
+		double v = message(b, op.a, c, mA, p, i, true);
+		if (op.b >= 0) v *= message(b, op.b, c, mB, p, i, true);
+		if ((op.flags & 1) && freqs != NULL) v *= freqs[i];
+		out[(size_t)p * S + i] = v;
+	}
+}
+
+// SingleTreeLikelihood_scalePartials (treelikelihood.c:1790-1836); grid (ceil(P/128), ops in level)   -- K5
+__global__ void k_generic_scale(Bufs b, const phbc_op *__restrict__ ops, double threshold) {
+	const phbc_op op = ops[blockIdx.y];
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= b.P) return;
+	const int S = b.S;
+	double m = 0.0;
+	for (int c = 0; c < b.C; c++) {
+		const double *x = partial_ptr(b, op.out, c) + (size_t)p * S;
+		for (int i = 0; i < S; i++) m = x[i] > m ? x[i] : m;
+	}
+	double sf = 0.0;
+	if (m < threshold) {
+		for (int c = 0; c < b.C; c++) {
+			double *x = (double *)partial_ptr(b, op.out, c) + (size_t)p * S;
+			for (int i = 0; i < S; i++) x[i] /= m;
+		}
+		sf = log(m);
+	}
+	// children that own partials carry scaling factors; state tips do not (treelikelihood.c:1795-1796)
+	if (!is_state_tip(b, op.a)) sf += b.sf[(size_t)op.a * b.P + p];
+	if (op.b >= 0 && !is_state_tip(b, op.b)) sf += b.sf[(size_t)op.b * b.P + p];
+	b.sf[(size_t)op.out * b.P + p] = sf;
+}
+
+// integrate_partials + node_log_likelihoods + weighted sum (treelikelihoodX.c:104-164, treelikelihood.c:1482-1487)  -- K6, K7
+__global__ void k_generic_root(Bufs b, int root, const double *__restrict__ freqs, const double *__restrict__ props,
+                               const double *__restrict__ weights, int scale, double *__restrict__ pattern_lnl,
+                               double *__restrict__ block_sums) {
+	__shared__ double red[32];
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	double v = 0.0;
+	if (p < b.P) {
+		const int S = b.S;
+		double site = 0.0;
+		for (int i = 0; i < S; i++) {
+			double r = 0.0;
+			for (int c = 0; c < b.C; c++) {
+				const double x = partial_ptr(b, root, c)[(size_t)p * S + i];
+				r += (b.C == 1) ? x : x * props[c];
+			}
+			site += freqs[i] * r;
+		}
+		double plk = log(site);
+		if (scale) plk += b.sf[(size_t)root * b.P + p];
+		pattern_lnl[p] = plk;
+		v = plk * weights[p];
+	}
+	v = phb_warp_sum(v);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		double s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+		s = phb_warp_sum(s);
+		if (threadIdx.x == 0) block_sums[blockIdx.x] = s;
+	}
+}
+
+// deterministic final sum of n values by one CTA: out[0] = sum
+__global__ void k_sum_blocks(const double *__restrict__ in, int n, double *__restrict__ out) {
+	__shared__ double red[32];
+	double v = 0.0;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) v += in[i];
+	v = phb_warp_sum(v);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		double s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+		s = phb_warp_sum(s);
+		if (threadIdx.x == 0) out[0] = s;
+	}
+}
+
+#define GEN_MAXC 32
+#define GEN_PGRAD 256
+
+// calculate_branch_partials + gradient_cat_branch_lengths (treelikelihoodX.c:878-1001, treelikelihood.c:2793-2941,
+// 2715-2789); grid (ceil(P/256), N-1 non-root nodes), one thread per pattern                           -- K9, K10
+__global__ void k_generic_branch_gradient(Bufs b, int root, const double *__restrict__ Pm, const double *__restrict__ dPm,
+                                          const double *__restrict__ freqs, const double *__restrict__ props,
+                                          const double *__restrict__ weights, const double *__restrict__ pattern_lnl,
+                                          int scale, int compat, int include_root_freqs, double *__restrict__ partial /* [N][C][tiles] */) {
+	extern __shared__ double sm[];
+	__shared__ double red[GEN_PGRAD / 32];
+	const int S = b.S, SS = S * S;
+	double *dM = sm, *M = sm + SS;
+	int node = blockIdx.y;
+	if (node >= root) node++;  // skip the root
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool live = p < b.P;
+	double numc[GEN_MAXC], denc[GEN_MAXC];
+	for (int c = 0; c < b.C; c++) {
+		__syncthreads();
+		for (int e = threadIdx.x; e < SS; e += blockDim.x) {
+			dM[e] = dPm[((size_t)node * b.C + c) * SS + e];
+			if (scale) M[e] = Pm[((size_t)node * b.C + c) * SS + e];
+		}
+		__syncthreads();
+		double num = 0.0, den = 0.0;
+		if (live) {
+			const double *U = partial_ptr(b, b.N + node, c) + (size_t)p * S;
+			for (int i = 0; i < S; i++) {
+				const double f = include_root_freqs ? 1.0 : freqs[i];
+				const double u = f * U[i];
+				num += u * message(b, node, c, dM, p, i, false);
+				if (scale) den += u * message(b, node, c, M, p, i, false);
+			}
+		}
+		numc[c] = num;
+		denc[c] = den;
+	}
+	double den_all = 0.0;
+	if (scale && !compat)
+		for (int c = 0; c < b.C; c++) den_all += (b.C == 1 ? 1.0 : props[c]) * denc[c];
+	const double w = live ? weights[p] : 0.0;
+	const double lk = (live && !scale) ? exp(pattern_lnl[p]) : 1.0;  // pattern_likelihoods, treelikelihood.c:3207-3210
+	for (int c = 0; c < b.C; c++) {
+		double v = 0.0;
+		if (live) {
+			const double den = !scale ? lk : (compat ? denc[c] : den_all);
+			v = numc[c] / den * w;
+		}
+		v = phb_warp_sum(v);
+		__syncthreads();
+		if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			double s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+			s = phb_warp_sum(s);
+			if (threadIdx.x == 0) partial[((size_t)node * b.C + c) * gridDim.x + blockIdx.x] = s;
+		}
+	}
+}
+
+// cat_grad[n][c] = sum over tiles (fixed order); one thread per (node, category)
+__global__ void k_generic_gradient_reduce(int N, int C, int root, int tiles, const double *__restrict__ partial,
+                                          double *__restrict__ cat_grad) {
+	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= N * C) return;
+	const int node = e / C;
+	double s = 0.0;
+	if (node != root)
+		for (int t = 0; t < tiles; t++) s += partial[(size_t)e * tiles + t];
+	cat_grad[e] = s;
+}
+
+// gradient_branch_length_from_cat_inplace (treelikelihood.c:3129-3143): applied only when C > 1 (:3258-3266)
+__global__ void k_collapse_categories(int N, int C, const double *__restrict__ cat_grad, const double *__restrict__ props,
+                                      const double *__restrict__ rates, double *__restrict__ result /* [1+N] */) {
+	const int n = blockIdx.x * blockDim.x + threadIdx.x;
+	if (n >= N) return;
+	double g;
+	if (C == 1) {
+		g = cat_grad[n];
+	} else {
+		g = cat_grad[(size_t)n * C] * props[0] * rates[0];
+		for (int c = 1; c < C; c++) g += cat_grad[(size_t)n * C + c] * props[c] * rates[c];
+	}
+	result[1 + n] = g;
+}
+
+static Bufs make_bufs(phbc_ctx *ctx) {
+	Bufs b;
+	b.tip_states = ctx->d_tip_states;
+	b.tip_partials = ctx->d_tip_partials;
+	b.lower = ctx->d_lower;
+	b.upper = ctx->d_upper;
+	b.sf = ctx->d_sf;
+	b.T = ctx->T;
+	b.N = ctx->N;
+	b.S = ctx->S;
+	b.C = ctx->C;
+	b.P = ctx->P;
+	b.tip_kind = ctx->tip_kind;
+	return b;
+}
+
+int phbc_launch_transition_matrices(phbc_ctx *ctx, int batch_index) {
+	int rc = ensure_node_matrices(ctx);
+	if (rc) return rc;
+	const int S = ctx->S;
+	dim3 grid(ctx->N, ctx->C);
+	const int threads = S * S >= 256 ? 256 : (S * S >= 64 ? 64 : 32);
+	k_transition_matrices<<<grid, threads, 2 * S * sizeof(double), ctx->stream>>>(
+	    S, ctx->C, ctx->root, ctx->d_evec, ctx->d_eval, ctx->d_ivec, ctx->d_bl + (size_t)batch_index * ctx->N, ctx->d_rates,
+	    ctx->d_P, ctx->d_dP);
+	ctx->launches++;
+	PHBC_CHECK(cudaGetLastError());
+	return 0;
+}
+
+int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	const size_t S = ctx->S, C = ctx->C, P = ctx->P, N = ctx->N, T = ctx->T;
+	if (C > GEN_MAXC) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "generic kernels support at most %d rate categories", GEN_MAXC);
+		return -1;
+	}
+	const size_t psize = C * P * S;
+	if (!ctx->d_lower) PHBC_CHECK(cudaMalloc((void **)&ctx->d_lower, (N - T) * psize * sizeof(double)));
+	if (o->want_gradient && !ctx->d_upper) PHBC_CHECK(cudaMalloc((void **)&ctx->d_upper, N * psize * sizeof(double)));
+	if (o->scale && !ctx->d_sf) {
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_sf, 2 * N * P * sizeof(double)));
+		PHBC_CHECK(cudaMemsetAsync(ctx->d_sf, 0, 2 * N * P * sizeof(double), ctx->stream));
+	}
+	int rc;
+	if (!o->explicit_matrices) {
+		if (!ctx->have_eigen) {
+			snprintf(phbc_errbuf, sizeof(phbc_errbuf), "no eigen system and no explicit matrices set");
+			return -4;
+		}
+		if ((rc = phbc_launch_transition_matrices(ctx, o->batch_index))) return rc;
+	} else if (!ctx->d_P) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "explicit matrices requested but not uploaded");
+		return -4;
+	}
+	Bufs b = make_bufs(ctx);
+	const size_t smem = 2 * S * S * sizeof(double);
+	if (smem > 48 * 1024) {
+		PHBC_CHECK(cudaFuncSetAttribute(k_generic_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		PHBC_CHECK(cudaFuncSetAttribute(k_generic_branch_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	}
+	const int ptiles = (int)((P + GEN_PBLK - 1) / GEN_PBLK);
+	// post-order, one launch per level
+	for (int l = 0; l < ctx->n_lower_levels; l++) {
+		const int beg = ctx->h_lower_level_off[l], cnt = ctx->h_lower_level_off[l + 1] - beg;
+		if (cnt <= 0) continue;
+		for (int z0 = 0; z0 < cnt; z0 += 65535) {
+			const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
+			k_generic_combine<<<dim3(ptiles, (unsigned)C, zc), 128, smem, ctx->stream>>>(b, ctx->d_lower_ops + beg + z0, ctx->d_P, ctx->d_freqs);
+			ctx->launches++;
+			if (o->scale) {
+				k_generic_scale<<<dim3((unsigned)((P + 127) / 128), zc), 128, 0, ctx->stream>>>(b, ctx->d_lower_ops + beg + z0, o->scaling_threshold);
+				ctx->launches++;
+			}
+		}
+	}
+	// root
+	const int rblocks = (int)((P + 255) / 256);
+	const size_t gtiles = (P + GEN_PGRAD - 1) / GEN_PGRAD;
+	size_t need = rblocks * sizeof(double);
+	if (o->want_gradient && N * C * gtiles * sizeof(double) > need) need = N * C * gtiles * sizeof(double);
+	if ((rc = phbc_ensure_scratch(ctx, need))) return rc;
+	double *result = ctx->d_result + (size_t)o->batch_index * (1 + N);
+	k_generic_root<<<rblocks, 256, 0, ctx->stream>>>(b, ctx->root, ctx->d_freqs, ctx->d_props, ctx->d_weights, o->scale,
+	                                                  ctx->d_pattern_lnl, ctx->d_scratch);
+	k_sum_blocks<<<1, 256, 0, ctx->stream>>>(ctx->d_scratch, rblocks, result);
+	ctx->launches += 2;
+	if (o->want_gradient) {
+		for (int l = 0; l < ctx->n_upper_levels; l++) {
+			const int beg = ctx->h_upper_level_off[l], cnt = ctx->h_upper_level_off[l + 1] - beg;
+			if (cnt <= 0) continue;
+			for (int z0 = 0; z0 < cnt; z0 += 65535) {
+				const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
+				// the include_root_freqs flag travels in op.flags, set by the host per evaluation option
+				k_generic_combine<<<dim3(ptiles, (unsigned)C, zc), 128, smem, ctx->stream>>>(b, ctx->d_upper_ops + beg + z0, ctx->d_P,
+				                                                                           o->include_root_freqs ? ctx->d_freqs : NULL);
+				ctx->launches++;
+				if (o->scale) {
+					k_generic_scale<<<dim3((unsigned)((P + 127) / 128), zc), 128, 0, ctx->stream>>>(b, ctx->d_upper_ops + beg + z0, o->scaling_threshold);
+					ctx->launches++;
+				}
+			}
+		}
+		for (int y0 = 0; y0 < (int)N - 1; y0 += 65535) {
+			// blockIdx.y enumerates non-root nodes; chunks keep gridDim.y within limits
+			const int yc = (int)N - 1 - y0 < 65535 ? (int)N - 1 - y0 : 65535;
+			if (y0 != 0) {
+				snprintf(phbc_errbuf, sizeof(phbc_errbuf), "generic gradient kernel supports at most 65535 branches");
+				return -1;
+			}
+			k_generic_branch_gradient<<<dim3((unsigned)gtiles, yc), GEN_PGRAD, smem, ctx->stream>>>(
+			    b, ctx->root, ctx->d_P, ctx->d_dP, ctx->d_freqs, ctx->d_props, ctx->d_weights, ctx->d_pattern_lnl, o->scale,
+			    o->compat_scaled_gradient, o->include_root_freqs, ctx->d_scratch);
+			ctx->launches++;
+		}
+		k_generic_gradient_reduce<<<(unsigned)((N * C + 127) / 128), 128, 0, ctx->stream>>>((int)N, (int)C, ctx->root, (int)gtiles,
+		                                                                                 ctx->d_scratch, ctx->d_cat_grad);
+		k_collapse_categories<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>((int)N, (int)C, ctx->d_cat_grad, ctx->d_props,
+		                                                                          ctx->d_rates, result);
+		ctx->launches += 2;
+	}
+	PHBC_CHECK(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int phbc_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
+	if (o->batch_index < 0 || o->batch_index >= ctx->bl_cap || o->batch_index >= ctx->result_cap) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "batch index %d out of range", o->batch_index);
+		return -1;
+	}
+	if (o->kernels != 1 /* PHB_KERNELS_GENERIC */ && phbc_nuc4_supported(ctx, o)) return phbc_nuc4_evaluate(ctx, o);
+	if (o->kernels == 2 /* PHB_KERNELS_FUSED */) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "fused kernels not available for this configuration (S=%d)", ctx->S);
+		return -1;
+	}
+	return phbc_generic_evaluate(ctx, o);
+}
+
+extern "C" int phbc_result_to_device(phbc_ctx *ctx, int batch_index, double *out_device) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	PHBC_CHECK(cudaMemcpyAsync(out_device, ctx->d_result + (size_t)batch_index * (1 + ctx->N), (1 + (size_t)ctx->N) * sizeof(double),
+	                           cudaMemcpyDeviceToDevice, ctx->stream));
+	return 0;
+}
+
+extern "C" int phbc_download_results(phbc_ctx *ctx, int nbatch, double *lnl, double *grad) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	const size_t N = ctx->N, row = 1 + N;
+	double *h = (double *)malloc((size_t)nbatch * row * sizeof(double));
+	if (!h) return -3;
+	cudaError_t e = cudaMemcpyAsync(h, ctx->d_result, (size_t)nbatch * row * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (e == cudaSuccess) {
+		for (int b = 0; b < nbatch; b++) {
+			if (lnl) lnl[b] = h[b * row];
+			if (grad) memcpy(grad + (size_t)b * N, h + b * row + 1, N * sizeof(double));
+		}
+	}
+	free(h);
+	PHBC_CHECK(e);
+	return 0;
+}
+
+#define DOWNLOAD(dst, src, count)                                                                              \
+	do {                                                                                                       \
+		PHBC_CHECK(cudaSetDevice(ctx->device));                                                                \
+		PHBC_CHECK(cudaMemcpyAsync(dst, src, (count) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));  \
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));                                                        \
+	} while (0)
+
+extern "C" int phbc_download_cat_grad(phbc_ctx *ctx, double *out) {
+	DOWNLOAD(out, ctx->d_cat_grad, (size_t)ctx->N * ctx->C);
+	return 0;
+}
+extern "C" int phbc_download_pattern_lnl(phbc_ctx *ctx, double *out) {
+	DOWNLOAD(out, ctx->d_pattern_lnl, (size_t)ctx->P);
+	return 0;
+}
+extern "C" int phbc_download_partials(phbc_ctx *ctx, int index, double *out) {
+	const size_t psize = (size_t)ctx->C * ctx->P * ctx->S;
+	if (index < 0 || index >= 2 * ctx->N) return -1;
+	if (index < ctx->T) {
+		if (!ctx->d_tip_partials) return -1;
+		for (int c = 0; c < ctx->C; c++)
+			DOWNLOAD(out + (size_t)c * ctx->P * ctx->S, ctx->d_tip_partials + (size_t)index * ctx->P * ctx->S, (size_t)ctx->P * ctx->S);
+		return 0;
+	}
+	if (index < ctx->N) {
+		if (!ctx->d_lower) return -4;
+		DOWNLOAD(out, ctx->d_lower + (size_t)(index - ctx->T) * psize, psize);
+		return 0;
+	}
+	if (!ctx->d_upper) return -4;
+	DOWNLOAD(out, ctx->d_upper + (size_t)(index - ctx->N) * psize, psize);
+	return 0;
+}
+extern "C" int phbc_download_matrices(phbc_ctx *ctx, double *P, double *dP) {
+	if (!ctx->d_P) return -4;
+	const size_t n = (size_t)ctx->N * ctx->C * ctx->S * ctx->S;
+	if (P) DOWNLOAD(P, ctx->d_P, n);
+	if (dP) DOWNLOAD(dP, ctx->d_dP, n);
+	return 0;
+}
+extern "C" int phbc_synchronize(phbc_ctx *ctx) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+extern "C" void *phbc_stream(phbc_ctx *ctx) { return (void *)ctx->stream; }
+extern "C" long long phbc_launch_count(const phbc_ctx *ctx) { return ctx->launches; }

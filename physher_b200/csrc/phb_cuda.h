@@ -1,0 +1,120 @@
+/*
+ * phb_cuda.h -- thin C-ABI layer between the C host code (phb_treelikelihood.c) and the sm_100a
+ * kernels (phb_cuda.cu, phb_nuc4.cu, phb_dmma.cu).  Internal: the public ABI is include/physher_b200.h.
+ *
+ * The host side owns all control flow (dirty flags, caching, schedules, gradient assembly); this
+ * layer owns device memory, the stream and the kernel launches.  No torch types anywhere.
+ */
+#ifndef PHB_CUDA_H
+#define PHB_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct phbc_ctx phbc_ctx;
+
+/* tip representations on the device */
+#define PHBC_TIP_STATES 0   /* uint8 [T][P]; >= S unknown                                         */
+#define PHBC_TIP_PARTIALS 1 /* double [T][P][S] (category stride 0)                               */
+
+/*
+ * One partial-update op of the node-at-a-time ("generic") kernels; mirrors the reference's
+ * update_partials(tlk, out, p1, m1, p2, m2) (treelikelihood.h:91): out = (M[m1] x[p1]) o (M[m2] x[p2]).
+ * Buffer indices: < T tip, T..N-1 lower partials, N + node upper partials.  b < 0: single child.
+ */
+typedef struct phbc_op {
+	int out;
+	int a, a_mat;
+	int b, b_mat;
+	int flags; /* bit 0: multiply the result by the root frequencies (treelikelihood.c:2148-2153) */
+} phbc_op;
+
+/* Whole-tree walk schedules of the fused 4-state kernels (see phb_nuc4.cu). Operand kinds: */
+#define PHBC_W_TIP 0  /* idx = tip node id                                  */
+#define PHBC_W_SLOT 1 /* idx = shared-memory slot                           */
+#define PHBC_W_ROOT 2 /* pre-order only: the parent is the root (W = 1 or pi) */
+
+typedef struct phbc_post_op { /* one internal node, DFS post-order                                */
+	int16_t a_kind, b_kind;
+	int a_idx, b_idx;        /* tip id or slot                                                    */
+	int a_node, b_node;      /* node ids of the children (matrix owners)                          */
+	int dst_slot;            /* slot receiving the result                                         */
+	int node;                /* node id of the result (row T.. of the lower scratch)               */
+} phbc_post_op;
+
+typedef struct phbc_pre_op { /* one internal node acting as parent, DFS pre-order                 */
+	int16_t u_kind;          /* PHBC_W_SLOT or PHBC_W_ROOT                                        */
+	int16_t a_tip, b_tip;    /* 1 when the child is a tip                                         */
+	int u_slot;              /* slot holding U_parent                                             */
+	int node;                /* parent node id (matrix P_node when not the root)                  */
+	int a_node, b_node;      /* children node ids                                                 */
+	int a_slot, b_slot;      /* slots receiving U_a / U_b for internal children (-1: not kept)    */
+} phbc_pre_op;
+
+typedef struct phbc_schedule {
+	int n_lower_ops, n_lower_levels;
+	const phbc_op *lower_ops;   /* grouped by level, children before parents                      */
+	const int *lower_level_off; /* [n_lower_levels + 1]                                           */
+	int n_upper_ops, n_upper_levels;
+	const phbc_op *upper_ops;   /* grouped by depth, parents before children                      */
+	const int *upper_level_off;
+	int n_post, n_pre;
+	const phbc_post_op *post_ops;
+	const phbc_pre_op *pre_ops;
+	int post_slots, pre_slots;  /* shared-memory slots the walks need                             */
+} phbc_schedule;
+
+int phbc_device_count(void);
+const char *phbc_last_error(void);
+
+phbc_ctx *phbc_create(int device, int ntips, int nstate, int ncat, int npatterns, int root, int tip_kind);
+void phbc_destroy(phbc_ctx *ctx);
+
+int phbc_set_schedule(phbc_ctx *ctx, const phbc_schedule *s);
+int phbc_upload_tip_states(phbc_ctx *ctx, const uint8_t *states);
+int phbc_upload_tip_partials(phbc_ctx *ctx, const double *partials);
+int phbc_upload_weights(phbc_ctx *ctx, const double *w);
+int phbc_upload_eigen(phbc_ctx *ctx, const double *evec, const double *eval, const double *ivec);
+int phbc_upload_matrices(phbc_ctx *ctx, const double *P, const double *dP);
+int phbc_upload_freqs(phbc_ctx *ctx, const double *freqs);
+int phbc_upload_site_model(phbc_ctx *ctx, const double *rates, const double *props);
+int phbc_upload_branch_lengths(phbc_ctx *ctx, const double *bl, int nbatch); /* [nbatch][N], pinned staging */
+
+typedef struct phbc_eval_opts {
+	int kernels;                 /* PHB_KERNELS_*                                                  */
+	int scale;                   /* rescaling on                                                   */
+	double scaling_threshold;
+	int include_root_freqs;
+	int compat_scaled_gradient;
+	int want_gradient;
+	int explicit_matrices;       /* matrices were uploaded, do not rebuild them from the eigen system */
+	int batch_index;             /* which uploaded branch-length vector                            */
+} phbc_eval_opts;
+
+/*
+ * One evaluation, asynchronous on the ctx stream: transition matrices, post-order pass, root
+ * integration, and (want_gradient) the pre-order pass with the branch-gradient reductions.
+ * Results stay on the device: result[0] = lnL, result[1..N] = d lnL / d bl by node id
+ * (before the unrooted convention is applied), cat_grad [N][C].
+ */
+int phbc_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
+/* copy results of evaluation slot `batch_index` into out_device[0..N] on the stream (device to device) */
+int phbc_result_to_device(phbc_ctx *ctx, int batch_index, double *out_device);
+/* blocking download of result slots [0, nbatch): lnl[b], grad[b][N] (either may be NULL) */
+int phbc_download_results(phbc_ctx *ctx, int nbatch, double *lnl, double *grad);
+int phbc_download_cat_grad(phbc_ctx *ctx, double *out);
+int phbc_download_pattern_lnl(phbc_ctx *ctx, double *out);
+int phbc_download_partials(phbc_ctx *ctx, int index, double *out);
+int phbc_download_matrices(phbc_ctx *ctx, double *P, double *dP);
+int phbc_synchronize(phbc_ctx *ctx);
+void *phbc_stream(phbc_ctx *ctx);
+long long phbc_launch_count(const phbc_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

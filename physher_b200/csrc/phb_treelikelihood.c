@@ -1,0 +1,802 @@
+/*
+ * phb_treelikelihood.c -- host side of the B200 tree likelihood, in C like the reference's host code.
+ *
+ * Mirrors the control flow of src/phyc/treelikelihood.c: construction (new_SingleTreeLikelihood,
+ * :1007-1185), dirty flags and caching (_calculate_simple :1454-1526, update_* :1737-1771),
+ * NaN / inf handling with the automatic switch to rescaling (:1489-1519), gradient entry points
+ * (TreeLikelihood_initialize_gradient :237-318, TreeLikelihood_gradient :320-340) and the unrooted
+ * convention (:3249-3255).  All numerics run on the device through the thin layer in phb_cuda.h;
+ * this file contains no arithmetic on partials.
+ *
+ * It also turns the tree into the launch schedules the kernels consume:
+ *   - level lists for the node-at-a-time kernels (children before parents / parents before children);
+ *   - linear whole-tree walks for the fused kernels: a post-order walk ordered so that the number of
+ *     live intermediate partials is the tree's Strahler number (larger-need child first) and a
+ *     pre-order walk with the same property, each with its shared-memory slot assignment.
+ */
+#include "../../include/physher_b200.h"
+#include "phb_cuda.h"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct phb_tlk {
+	int T, N, S, C, P, root;
+	int use_tip_states, device;
+	int *left, *right, *parent;
+	double *bl; /* [N] host copy, as Node_distance would return */
+	phbc_ctx *ctx;
+
+	/* tlk->update_nodes / update / update_upper (treelikelihood.h:79-80,114) */
+	unsigned char *update_nodes;
+	int update, update_upper;
+
+	int scale; /* tlk->scale */
+	double scaling_threshold;
+	int include_root_freqs, compat_scaled_gradient, unrooted, kernels;
+
+	int have_tips, have_weights, have_eigen, have_matrices, have_freqs, have_site, have_bl;
+	int bl_dirty;
+
+	double lk; /* tlk->lk */
+	int prepared_gradient;
+	double *gradient; /* owned, like tlk->gradient */
+	size_t gradient_length;
+	int gradient_valid;
+
+	/* schedules (host copies kept for introspection) */
+	phbc_op *lower_ops, *upper_ops;
+	int *lower_level_off, *upper_level_off;
+	phbc_post_op *post_ops;
+	phbc_pre_op *pre_ops;
+	int n_lower_levels, n_upper_levels, post_slots, pre_slots;
+};
+
+static _Thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+
+static int dev_fail(int rc) { return fail(rc == -3 ? PHB_ENOMEM : (rc == -1 ? PHB_EINVAL : (rc == -4 ? PHB_ESTATE : PHB_ECUDA)), "%s", phbc_last_error()); }
+
+const char *phb_last_error(void) { return g_err; }
+int phb_device_count(void) { return phbc_device_count(); }
+const char *phb_version(void) { return "physher_b200 0.1 (sm_100a)"; }
+
+/* ------------------------------------------------------------------------------------------- */
+/* schedules                                                                                   */
+/* ------------------------------------------------------------------------------------------- */
+
+static int is_tip(const phb_tlk *t, int n) { return t->left[n] < 0; }
+
+/* level lists: lower level = 1 + max(children levels) (tips 0); upper level = depth below the root */
+static int build_level_schedules(phb_tlk *t) {
+	const int N = t->N, T = t->T;
+	int *level = (int *)calloc(N, sizeof(int));
+	int *depth = (int *)calloc(N, sizeof(int));
+	int *order = (int *)malloc(sizeof(int) * N); /* pre-order */
+	int *stack = (int *)malloc(sizeof(int) * N);
+	if (!level || !depth || !order || !stack) return PHB_ENOMEM;
+	int sp = 0, cnt = 0;
+	stack[sp++] = t->root;
+	while (sp) {
+		int n = stack[--sp];
+		order[cnt++] = n;
+		if (!is_tip(t, n)) {
+			depth[t->left[n]] = depth[n] + 1;
+			depth[t->right[n]] = depth[n] + 1;
+			stack[sp++] = t->right[n];
+			stack[sp++] = t->left[n];
+		}
+	}
+	if (cnt != N) {
+		free(level); free(depth); free(order); free(stack);
+		return fail(PHB_EINVAL, "topology is not a rooted binary tree over %d nodes (visited %d)", N, cnt);
+	}
+	int maxlevel = 0, maxdepth = 0;
+	for (int k = N - 1; k >= 0; k--) { /* reverse pre-order: children before parents */
+		int n = order[k];
+		if (!is_tip(t, n)) {
+			int a = level[t->left[n]], b = level[t->right[n]];
+			level[n] = 1 + (a > b ? a : b);
+		}
+		if (level[n] > maxlevel) maxlevel = level[n];
+		if (depth[n] > maxdepth) maxdepth = depth[n];
+	}
+	/* lower ops: internal nodes grouped by level 1..maxlevel */
+	t->n_lower_levels = maxlevel;
+	t->lower_level_off = (int *)calloc(maxlevel + 2, sizeof(int));
+	t->lower_ops = (phbc_op *)malloc(sizeof(phbc_op) * (N - T > 0 ? N - T : 1));
+	for (int n = 0; n < N; n++)
+		if (!is_tip(t, n)) t->lower_level_off[level[n]]++; /* count at index level (1-based) */
+	{
+		int acc = 0;
+		for (int l = 1; l <= maxlevel; l++) {
+			int c = t->lower_level_off[l];
+			t->lower_level_off[l - 1] = acc;
+			acc += c;
+		}
+		t->lower_level_off[maxlevel] = acc;
+	}
+	int *fill = (int *)calloc(maxlevel + 1, sizeof(int));
+	for (int n = 0; n < N; n++) {
+		if (is_tip(t, n)) continue;
+		int l = level[n] - 1;
+		phbc_op *op = &t->lower_ops[t->lower_level_off[l] + fill[l]++];
+		op->out = n;
+		op->a = t->left[n];
+		op->a_mat = t->left[n];
+		op->b = t->right[n];
+		op->b_mat = t->right[n];
+		op->flags = 0;
+	}
+	free(fill);
+	/* upper ops: every non-root node, grouped by depth 1..maxdepth (update_upper_partials, treelikelihood.c:2129-2161) */
+	t->n_upper_levels = maxdepth;
+	t->upper_level_off = (int *)calloc(maxdepth + 2, sizeof(int));
+	t->upper_ops = (phbc_op *)malloc(sizeof(phbc_op) * (N > 1 ? N - 1 : 1));
+	for (int n = 0; n < N; n++)
+		if (n != t->root) t->upper_level_off[depth[n]]++;
+	{
+		int acc = 0;
+		for (int d = 1; d <= maxdepth; d++) {
+			int c = t->upper_level_off[d];
+			t->upper_level_off[d - 1] = acc;
+			acc += c;
+		}
+		t->upper_level_off[maxdepth] = acc;
+	}
+	fill = (int *)calloc(maxdepth + 1, sizeof(int));
+	for (int n = 0; n < N; n++) {
+		if (n == t->root) continue;
+		int d = depth[n] - 1;
+		int parent = t->parent[n];
+		int sib = t->left[parent] == n ? t->right[parent] : t->left[parent];
+		phbc_op *op = &t->upper_ops[t->upper_level_off[d] + fill[d]++];
+		op->out = N + n;
+		if (parent != t->root) { /* u_n = (P_p u_p) o (P_s L_s) */
+			op->a = N + parent;
+			op->a_mat = parent;
+			op->b = sib;
+			op->b_mat = sib;
+			op->flags = 0;
+		} else { /* u_n = P_s L_s [o pi] */
+			op->a = sib;
+			op->a_mat = sib;
+			op->b = -1;
+			op->b_mat = -1;
+			op->flags = 1;
+		}
+	}
+	free(fill);
+	free(level);
+	free(depth);
+	free(order);
+	free(stack);
+	return PHB_OK;
+}
+
+/* Strahler-style register need of the subtree below n (tips need none) */
+static void compute_need(const phb_tlk *t, int *need, int *size) {
+	/* node ids are not guaranteed to be a post-order: iterate with an explicit stack */
+	const int N = t->N;
+	int *stack = (int *)malloc(sizeof(int) * 2 * N);
+	int sp = 0;
+	stack[sp++] = t->root;
+	stack[sp++] = 0;
+	while (sp) {
+		int state = stack[--sp];
+		int n = stack[--sp];
+		if (is_tip(t, n)) {
+			need[n] = 0;
+			size[n] = 1;
+			continue;
+		}
+		if (state == 0) {
+			stack[sp++] = n;
+			stack[sp++] = 1;
+			stack[sp++] = t->left[n];
+			stack[sp++] = 0;
+			stack[sp++] = t->right[n];
+			stack[sp++] = 0;
+		} else {
+			int a = need[t->left[n]], b = need[t->right[n]];
+			need[n] = a == b ? a + 1 : (a > b ? a : b);
+			size[n] = 1 + size[t->left[n]] + size[t->right[n]];
+		}
+	}
+	free(stack);
+}
+
+typedef struct SlotPool {
+	unsigned char *used;
+	int cap, high;
+} SlotPool;
+
+static int slot_alloc(SlotPool *p) {
+	for (int s = 0; s < p->cap; s++)
+		if (!p->used[s]) {
+			p->used[s] = 1;
+			if (s + 1 > p->high) p->high = s + 1;
+			return s;
+		}
+	return -1;
+}
+
+/* whole-tree walks for the fused kernels */
+static int build_walk_schedules(phb_tlk *t) {
+	const int N = t->N, T = t->T;
+	const int nint = N - T;
+	int *need = (int *)malloc(sizeof(int) * N);
+	int *size = (int *)malloc(sizeof(int) * N);
+	int *slot_of = (int *)malloc(sizeof(int) * N);
+	int *stack = (int *)malloc(sizeof(int) * 2 * N);
+	SlotPool pool;
+	pool.cap = N + 1;
+	pool.used = (unsigned char *)calloc(pool.cap, 1);
+	pool.high = 0;
+	t->post_ops = (phbc_post_op *)malloc(sizeof(phbc_post_op) * (nint > 0 ? nint : 1));
+	t->pre_ops = (phbc_pre_op *)malloc(sizeof(phbc_pre_op) * (nint > 0 ? nint : 1));
+	if (!need || !size || !slot_of || !stack || !pool.used || !t->post_ops || !t->pre_ops) return PHB_ENOMEM;
+	compute_need(t, need, size);
+
+	/* post-order: visit the child with the larger need first so that at most need[root] results are live */
+	int sp = 0, nops = 0;
+	stack[sp++] = t->root;
+	stack[sp++] = 0;
+	while (sp) {
+		int state = stack[--sp];
+		int n = stack[--sp];
+		if (is_tip(t, n)) continue;
+		int a = t->left[n], b = t->right[n];
+		if (state == 0) {
+			stack[sp++] = n;
+			stack[sp++] = 1;
+			int first = need[a] >= need[b] ? a : b;
+			int second = first == a ? b : a;
+			stack[sp++] = second; /* popped after `first` */
+			stack[sp++] = 0;
+			stack[sp++] = first;
+			stack[sp++] = 0;
+		} else {
+			phbc_post_op *op = &t->post_ops[nops++];
+			op->node = n;
+			op->a_node = a;
+			op->b_node = b;
+			op->a_kind = is_tip(t, a) ? PHBC_W_TIP : PHBC_W_SLOT;
+			op->b_kind = is_tip(t, b) ? PHBC_W_TIP : PHBC_W_SLOT;
+			op->a_idx = is_tip(t, a) ? a : slot_of[a];
+			op->b_idx = is_tip(t, b) ? b : slot_of[b];
+			/* slots are thread-private in the kernel: operands may be released before the result is placed */
+			if (!is_tip(t, a)) pool.used[slot_of[a]] = 0;
+			if (!is_tip(t, b)) pool.used[slot_of[b]] = 0;
+			op->dst_slot = slot_alloc(&pool);
+			slot_of[n] = op->dst_slot;
+		}
+	}
+	t->post_slots = pool.high;
+
+	/* pre-order over internal nodes: the parent's op yields U for both children; descend first into the
+	 * child whose subtree needs fewer slots, the other one waits in its slot */
+	memset(pool.used, 0, pool.cap);
+	pool.high = 0;
+	/* need over the tree of INTERNAL nodes only */
+	int *pneed = (int *)calloc(N, sizeof(int));
+	{
+		/* process nodes children-before-parents using the post-order op list */
+		for (int k = 0; k < nops; k++) {
+			int n = t->post_ops[k].node;
+			int a = t->left[n], b = t->right[n];
+			int ia = !is_tip(t, a), ib = !is_tip(t, b);
+			if (!ia && !ib) pneed[n] = 1;
+			else if (ia && !ib) pneed[n] = pneed[a] > 1 ? pneed[a] : 1;
+			else if (!ia && ib) pneed[n] = pneed[b] > 1 ? pneed[b] : 1;
+			else {
+				int lo = pneed[a] < pneed[b] ? pneed[a] : pneed[b];
+				int hi = pneed[a] < pneed[b] ? pneed[b] : pneed[a];
+				pneed[n] = lo + 1 > hi ? lo + 1 : hi;
+			}
+		}
+	}
+	int npre = 0;
+	sp = 0;
+	stack[sp++] = t->root;
+	while (sp) {
+		int n = stack[--sp];
+		int a = t->left[n], b = t->right[n];
+		phbc_pre_op *op = &t->pre_ops[npre++];
+		op->node = n;
+		op->a_node = a;
+		op->b_node = b;
+		op->a_tip = (int16_t)is_tip(t, a);
+		op->b_tip = (int16_t)is_tip(t, b);
+		if (n == t->root) {
+			op->u_kind = PHBC_W_ROOT;
+			op->u_slot = -1;
+		} else {
+			op->u_kind = PHBC_W_SLOT;
+			op->u_slot = slot_of[n];
+			pool.used[slot_of[n]] = 0; /* consumed by this op */
+		}
+		op->a_slot = op->b_slot = -1;
+		if (!op->a_tip) slot_of[a] = op->a_slot = slot_alloc(&pool);
+		if (!op->b_tip) slot_of[b] = op->b_slot = slot_alloc(&pool);
+		/* push so that the smaller-need internal child is popped first */
+		if (!op->a_tip && !op->b_tip) {
+			int first = pneed[a] <= pneed[b] ? a : b;
+			int second = first == a ? b : a;
+			stack[sp++] = second;
+			stack[sp++] = first;
+		} else if (!op->a_tip) {
+			stack[sp++] = a;
+		} else if (!op->b_tip) {
+			stack[sp++] = b;
+		}
+	}
+	t->pre_slots = pool.high > 0 ? pool.high : 1;
+	if (t->post_slots < 1) t->post_slots = 1;
+	free(pneed);
+	free(need);
+	free(size);
+	free(slot_of);
+	free(stack);
+	free(pool.used);
+	if (nops != nint || npre != nint) return fail(PHB_EINVAL, "walk schedule covers %d/%d of %d internal nodes", nops, npre, nint);
+	return PHB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* construction                                                                                */
+/* ------------------------------------------------------------------------------------------- */
+
+phb_tlk *phb_tlk_create(int ntips, int nstate, int ncat, int npatterns, const int *left, const int *right, int root,
+                        int use_tip_states, int device) {
+	if (ntips < 2 || nstate < 2 || ncat < 1 || npatterns < 1 || !left || !right) {
+		fail(PHB_EINVAL, "phb_tlk_create: need ntips >= 2, nstate >= 2, ncat >= 1, npatterns >= 1 and a topology");
+		return NULL;
+	}
+	if (use_tip_states && nstate > 255) {
+		fail(PHB_EINVAL, "phb_tlk_create: uint8 tip states need nstate <= 255");
+		return NULL;
+	}
+	const int N = 2 * ntips - 1;
+	if (root < 0 || root >= N) {
+		fail(PHB_EINVAL, "phb_tlk_create: root %d out of range", root);
+		return NULL;
+	}
+	phb_tlk *t = (phb_tlk *)calloc(1, sizeof(phb_tlk));
+	if (!t) return NULL;
+	t->T = ntips;
+	t->N = N;
+	t->S = nstate;
+	t->C = ncat;
+	t->P = npatterns;
+	t->root = root;
+	t->use_tip_states = use_tip_states != 0;
+	t->device = device;
+	t->left = (int *)malloc(sizeof(int) * N);
+	t->right = (int *)malloc(sizeof(int) * N);
+	t->parent = (int *)malloc(sizeof(int) * N);
+	t->bl = (double *)calloc(N, sizeof(double));
+	t->update_nodes = (unsigned char *)malloc(N);
+	if (!t->left || !t->right || !t->parent || !t->bl || !t->update_nodes) {
+		phb_tlk_free(t);
+		fail(PHB_ENOMEM, "phb_tlk_create: out of memory");
+		return NULL;
+	}
+	for (int n = 0; n < N; n++) t->parent[n] = -1;
+	for (int n = 0; n < N; n++) {
+		t->left[n] = left[n];
+		t->right[n] = right[n];
+		const int tip = left[n] < 0;
+		if ((left[n] < 0) != (right[n] < 0) || (tip && n >= ntips) || (!tip && n < ntips) || left[n] >= N || right[n] >= N) {
+			phb_tlk_free(t);
+			fail(PHB_EINVAL, "phb_tlk_create: node %d breaks the id convention (tips 0..T-1, internal T..2T-2)", n);
+			return NULL;
+		}
+		if (!tip) {
+			t->parent[left[n]] = n;
+			t->parent[right[n]] = n;
+		}
+	}
+	memset(t->update_nodes, 1, N); /* treelikelihood.c:1054-1059 */
+	t->update = 1;
+	t->update_upper = 1;
+	t->scale = 0;
+	t->scaling_threshold = 1.e-40; /* treelikelihood.c:1121 */
+	t->include_root_freqs = 0;
+	t->compat_scaled_gradient = 0;
+	t->unrooted = 1;
+	t->kernels = PHB_KERNELS_AUTO;
+	int rc = build_level_schedules(t);
+	if (rc == PHB_OK) rc = build_walk_schedules(t);
+	if (rc != PHB_OK) {
+		phb_tlk_free(t);
+		return NULL;
+	}
+	t->ctx = phbc_create(device, ntips, nstate, ncat, npatterns, root, use_tip_states ? PHBC_TIP_STATES : PHBC_TIP_PARTIALS);
+	if (!t->ctx) {
+		fail(PHB_ECUDA, "%s", phbc_last_error());
+		phb_tlk_free(t);
+		return NULL;
+	}
+	phbc_schedule s;
+	memset(&s, 0, sizeof(s));
+	s.n_lower_ops = N - ntips;
+	s.n_lower_levels = t->n_lower_levels;
+	s.lower_ops = t->lower_ops;
+	s.lower_level_off = t->lower_level_off;
+	s.n_upper_ops = N - 1;
+	s.n_upper_levels = t->n_upper_levels;
+	s.upper_ops = t->upper_ops;
+	s.upper_level_off = t->upper_level_off;
+	s.n_post = N - ntips;
+	s.n_pre = N - ntips;
+	s.post_ops = t->post_ops;
+	s.pre_ops = t->pre_ops;
+	s.post_slots = t->post_slots;
+	s.pre_slots = t->pre_slots;
+	if ((rc = phbc_set_schedule(t->ctx, &s))) {
+		dev_fail(rc);
+		phb_tlk_free(t);
+		return NULL;
+	}
+	return t;
+}
+
+void phb_tlk_free(phb_tlk *t) {
+	if (!t) return;
+	if (t->ctx) phbc_destroy(t->ctx);
+	free(t->left);
+	free(t->right);
+	free(t->parent);
+	free(t->bl);
+	free(t->update_nodes);
+	free(t->gradient);
+	free(t->lower_ops);
+	free(t->upper_ops);
+	free(t->lower_level_off);
+	free(t->upper_level_off);
+	free(t->post_ops);
+	free(t->pre_ops);
+	free(t);
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* inputs                                                                                      */
+/* ------------------------------------------------------------------------------------------- */
+
+void phb_tlk_update_all_nodes(phb_tlk *t) { /* treelikelihood.c:1737-1744 */
+	memset(t->update_nodes, 1, t->N);
+	t->update = 1;
+	t->update_upper = 1;
+}
+
+int phb_tlk_update_one_node(phb_tlk *t, int node) { /* treelikelihood.c:1747-1751 */
+	if (node < 0 || node >= t->N) return fail(PHB_EINVAL, "node %d out of range", node);
+	t->update_nodes[node] = 1;
+	t->update = 1;
+	t->update_upper = 1;
+	return PHB_OK;
+}
+
+int phb_tlk_set_tip_states(phb_tlk *t, const uint8_t *states) {
+	if (!t->use_tip_states) return fail(PHB_ESTATE, "tlk was created with use_tip_states = false");
+	int rc = phbc_upload_tip_states(t->ctx, states);
+	if (rc) return dev_fail(rc);
+	t->have_tips = 1;
+	phb_tlk_update_all_nodes(t);
+	return PHB_OK;
+}
+
+int phb_tlk_set_tip_partials(phb_tlk *t, const double *partials) {
+	if (t->use_tip_states) return fail(PHB_ESTATE, "tlk was created with use_tip_states = true");
+	int rc = phbc_upload_tip_partials(t->ctx, partials);
+	if (rc) return dev_fail(rc);
+	t->have_tips = 1;
+	phb_tlk_update_all_nodes(t);
+	return PHB_OK;
+}
+
+int phb_tlk_set_pattern_weights(phb_tlk *t, const double *w) {
+	int rc = phbc_upload_weights(t->ctx, w);
+	if (rc) return dev_fail(rc);
+	t->have_weights = 1;
+	phb_tlk_update_all_nodes(t);
+	return PHB_OK;
+}
+
+int phb_tlk_set_eigen(phb_tlk *t, const double *evec, const double *eval, const double *ivec) {
+	int rc = phbc_upload_eigen(t->ctx, evec, eval, ivec);
+	if (rc) return dev_fail(rc);
+	t->have_eigen = 1;
+	t->have_matrices = 0;
+	phb_tlk_update_all_nodes(t); /* substitution model changed: _treelikelihood_handle_change, :73-114 */
+	return PHB_OK;
+}
+
+int phb_tlk_set_matrices(phb_tlk *t, const double *P, const double *dP) {
+	int rc = phbc_upload_matrices(t->ctx, P, dP);
+	if (rc) return dev_fail(rc);
+	t->have_matrices = 1;
+	phb_tlk_update_all_nodes(t);
+	return PHB_OK;
+}
+
+int phb_tlk_set_frequencies(phb_tlk *t, const double *freqs) {
+	int rc = phbc_upload_freqs(t->ctx, freqs);
+	if (rc) return dev_fail(rc);
+	t->have_freqs = 1;
+	phb_tlk_update_all_nodes(t);
+	return PHB_OK;
+}
+
+int phb_tlk_set_site_model(phb_tlk *t, const double *rates, const double *props) {
+	int rc = phbc_upload_site_model(t->ctx, rates, props);
+	if (rc) return dev_fail(rc);
+	t->have_site = 1;
+	phb_tlk_update_all_nodes(t);
+	return PHB_OK;
+}
+
+int phb_tlk_set_branch_lengths(phb_tlk *t, const double *bl) {
+	for (int n = 0; n < t->N; n++) {
+		if (n != t->root && bl[n] < 0) /* treelikelihood.c:1659-1662 exits on a negative length */
+			return fail(PHB_EINVAL, "calculate_partials: node %d branch length = %E", n, bl[n]);
+	}
+	memcpy(t->bl, bl, sizeof(double) * t->N);
+	t->have_bl = 1;
+	t->bl_dirty = 1;
+	phb_tlk_update_all_nodes(t);
+	return PHB_OK;
+}
+
+int phb_tlk_set_branch_length(phb_tlk *t, int node, double bl) {
+	if (node < 0 || node >= t->N) return fail(PHB_EINVAL, "node %d out of range", node);
+	if (bl < 0) return fail(PHB_EINVAL, "calculate_partials: node %d branch length = %E", node, bl);
+	t->bl[node] = bl;
+	t->bl_dirty = 1;
+	return phb_tlk_update_one_node(t, node);
+}
+
+int phb_tlk_use_rescaling(phb_tlk *t, int use) { /* SingleTreeLikelihood_use_rescaling */
+	t->scale = use != 0;
+	phb_tlk_update_all_nodes(t);
+	return PHB_OK;
+}
+
+int phb_tlk_rescaling(const phb_tlk *t) { return t->scale; }
+
+int phb_tlk_set_option(phb_tlk *t, int option, int value) {
+	switch (option) {
+	case PHB_OPT_INCLUDE_ROOT_FREQS: t->include_root_freqs = value != 0; break;
+	case PHB_OPT_COMPAT_SCALED_GRADIENT: t->compat_scaled_gradient = value != 0; break;
+	case PHB_OPT_UNROOTED: t->unrooted = value != 0; break;
+	case PHB_OPT_KERNELS:
+		if (value < PHB_KERNELS_AUTO || value > PHB_KERNELS_FUSED) return fail(PHB_EINVAL, "unknown kernel family %d", value);
+		t->kernels = value;
+		break;
+	case PHB_OPT_SCALING_THRESHOLD_EXP: t->scaling_threshold = pow(10.0, -(double)value); break;
+	default: return fail(PHB_EINVAL, "unknown option %d", option);
+	}
+	t->update_upper = 1;
+	if (option != PHB_OPT_UNROOTED) t->update = 1;
+	return PHB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* evaluation                                                                                  */
+/* ------------------------------------------------------------------------------------------- */
+
+static int check_ready(const phb_tlk *t) {
+	if (!t->have_tips) return fail(PHB_ESTATE, "tip states / partials not set");
+	if (!t->have_weights) return fail(PHB_ESTATE, "pattern weights not set");
+	if (!t->have_eigen && !t->have_matrices) return fail(PHB_ESTATE, "substitution model not set");
+	if (!t->have_freqs) return fail(PHB_ESTATE, "frequencies not set");
+	if (!t->have_site) return fail(PHB_ESTATE, "site model not set");
+	if (!t->have_bl) return fail(PHB_ESTATE, "branch lengths not set");
+	return PHB_OK;
+}
+
+static void fill_opts(const phb_tlk *t, phbc_eval_opts *o, int want_gradient, int batch_index) {
+	memset(o, 0, sizeof(*o));
+	o->kernels = t->kernels;
+	o->scale = t->scale;
+	o->scaling_threshold = t->scaling_threshold;
+	o->include_root_freqs = t->include_root_freqs;
+	o->compat_scaled_gradient = t->compat_scaled_gradient;
+	o->want_gradient = want_gradient;
+	o->explicit_matrices = t->have_matrices;
+	o->batch_index = batch_index;
+}
+
+/* one full evaluation with the reference's NaN / inf handling (treelikelihood.c:1489-1519) */
+static int evaluate_once(phb_tlk *t, int want_gradient, double *lnl, double *grad_out) {
+	int rc = check_ready(t);
+	if (rc) return rc;
+	if (t->bl_dirty || 1) {
+		if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+		t->bl_dirty = 0;
+	}
+	phbc_eval_opts o;
+	for (int attempt = 0; attempt < 2; attempt++) {
+		fill_opts(t, &o, want_gradient, 0);
+		if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
+		if ((rc = phbc_download_results(t->ctx, 1, lnl, want_gradient ? grad_out : NULL))) return dev_fail(rc);
+		if (isinf(*lnl) && !t->scale) {
+			fprintf(stdout, "_calculate: rescaling %f\n", *lnl); /* same message as treelikelihood.c:1497 */
+			t->scale = 1;
+			continue;
+		}
+		break;
+	}
+	return PHB_OK;
+}
+
+int phb_tlk_calculate(phb_tlk *t, double *lnl) {
+	if (!t->update) { /* cached, treelikelihood.c:1458-1460 */
+		*lnl = t->lk;
+		return PHB_OK;
+	}
+	int rc = evaluate_once(t, 0, &t->lk, NULL);
+	if (rc) return rc;
+	*lnl = t->lk;
+	if (isnan(t->lk)) { /* :1489-1495 */
+		phb_tlk_update_all_nodes(t);
+		return PHB_OK;
+	}
+	memset(t->update_nodes, 0, t->N);
+	t->update = 0;
+	t->update_upper = 1;
+	return PHB_OK;
+}
+
+int phb_tlk_pattern_log_likelihoods(phb_tlk *t, double *out) {
+	double lnl;
+	int rc = phb_tlk_calculate(t, &lnl);
+	if (rc) return rc;
+	if ((rc = phbc_download_pattern_lnl(t->ctx, out))) return dev_fail(rc);
+	return PHB_OK;
+}
+
+size_t phb_tlk_initialize_gradient(phb_tlk *t, int flags) {
+	if (flags == 0) flags = PHB_FLAG_TREE_MODEL;
+	t->prepared_gradient = flags;
+	size_t len = 0;
+	if (flags & PHB_FLAG_TREE_MODEL) len += (size_t)t->N; /* branch-length trees: node count, treelikelihood.c:271-274 */
+	if (t->gradient == NULL || t->gradient_length < len) {
+		double *g = (double *)realloc(t->gradient, sizeof(double) * (len > 0 ? len : 1));
+		if (!g) {
+			fail(PHB_ENOMEM, "out of memory");
+			return 0;
+		}
+		t->gradient = g;
+	}
+	t->gradient_length = len;
+	t->update_upper = 1;
+	return len;
+}
+
+static void apply_unrooted(const phb_tlk *t, double *g) {
+	g[t->root] = 0.0;
+	if (t->unrooted) g[t->right[t->root]] = 0.0; /* treelikelihood.c:3249-3255 */
+}
+
+int phb_tlk_gradient(phb_tlk *t, const double **grad) {
+	if (t->gradient == NULL || !(t->prepared_gradient & PHB_FLAG_TREE_MODEL)) {
+		if (phb_tlk_initialize_gradient(t, PHB_FLAG_TREE_MODEL) == 0) return PHB_ENOMEM;
+	}
+	if (t->update_upper || t->update) { /* treelikelihood.c:323 */
+		double lnl;
+		int rc = evaluate_once(t, 1, &lnl, t->gradient);
+		if (rc) return rc;
+		t->lk = lnl;
+		if (isnan(lnl) || isinf(lnl)) { /* :328-332 */
+			for (size_t i = 0; i < t->gradient_length; i++) t->gradient[i] = NAN;
+			if (isnan(lnl)) phb_tlk_update_all_nodes(t);
+		} else {
+			apply_unrooted(t, t->gradient);
+			memset(t->update_nodes, 0, t->N);
+			t->update = 0;
+			t->update_upper = 0;
+		}
+	}
+	*grad = t->gradient;
+	return PHB_OK;
+}
+
+int phb_tlk_cat_branch_gradient(phb_tlk *t, double *out) {
+	int rc = phbc_download_cat_grad(t->ctx, out);
+	if (rc) return dev_fail(rc);
+	for (int c = 0; c < t->C; c++) {
+		out[(size_t)t->root * t->C + c] = 0.0;
+		if (t->unrooted) out[(size_t)t->right[t->root] * t->C + c] = 0.0;
+	}
+	return PHB_OK;
+}
+
+int phb_tlk_get_partials(phb_tlk *t, int index, double *out) {
+	int rc = phbc_download_partials(t->ctx, index, out);
+	if (rc) return dev_fail(rc);
+	return PHB_OK;
+}
+
+int phb_tlk_get_matrices(phb_tlk *t, double *P, double *dP) {
+	int rc = phbc_download_matrices(t->ctx, P, dP);
+	if (rc) return dev_fail(rc);
+	return PHB_OK;
+}
+
+int phb_tlk_gradient_device(phb_tlk *t, double *out_device) {
+	int rc = check_ready(t);
+	if (rc) return rc;
+	if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+	phbc_eval_opts o;
+	fill_opts(t, &o, 1, 0);
+	if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
+	if ((rc = phbc_result_to_device(t->ctx, 0, out_device))) return dev_fail(rc);
+	/* the device copy holds raw per-shard sums; the caller applies the unrooted convention after the reduction */
+	memset(t->update_nodes, 0, t->N);
+	t->update = 1; /* lk is not known on the host: keep the object dirty */
+	t->update_upper = 1;
+	return PHB_OK;
+}
+
+void *phb_tlk_stream(phb_tlk *t) { return phbc_stream(t->ctx); }
+
+int phb_tlk_synchronize(phb_tlk *t) {
+	int rc = phbc_synchronize(t->ctx);
+	if (rc) return dev_fail(rc);
+	return PHB_OK;
+}
+
+int phb_tlk_gradient_batch(phb_tlk *t, int nbatch, const double *bl, double *lnl, double *grad) {
+	if (nbatch < 1) return fail(PHB_EINVAL, "nbatch must be >= 1");
+	/* inputs other than branch lengths must be in place */
+	t->have_bl = 1;
+	int rc = check_ready(t);
+	if (rc) return rc;
+	for (int b = 0; b < nbatch; b++)
+		for (int n = 0; n < t->N; n++)
+			if (n != t->root && bl[(size_t)b * t->N + n] < 0)
+				return fail(PHB_EINVAL, "calculate_partials: sample %d node %d branch length = %E", b, n, bl[(size_t)b * t->N + n]);
+	for (int attempt = 0; attempt < 2; attempt++) {
+		if ((rc = phbc_upload_branch_lengths(t->ctx, bl, nbatch))) return dev_fail(rc);
+		phbc_eval_opts o;
+		for (int b = 0; b < nbatch; b++) {
+			fill_opts(t, &o, grad != NULL, b);
+			if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
+		}
+		if ((rc = phbc_download_results(t->ctx, nbatch, lnl, grad))) return dev_fail(rc);
+		int any_inf = 0;
+		for (int b = 0; b < nbatch; b++) any_inf |= isinf(lnl[b]);
+		if (any_inf && !t->scale) {
+			fprintf(stdout, "_calculate: rescaling (batch)\n");
+			t->scale = 1;
+			continue;
+		}
+		break;
+	}
+	if (grad)
+		for (int b = 0; b < nbatch; b++) {
+			double *g = grad + (size_t)b * t->N;
+			if (isnan(lnl[b]) || isinf(lnl[b])) {
+				for (int n = 0; n < t->N; n++) g[n] = NAN;
+			} else {
+				apply_unrooted(t, g);
+			}
+		}
+	/* the single-sample state (t->bl, t->lk) is untouched but device partials now belong to the last sample */
+	phb_tlk_update_all_nodes(t);
+	return PHB_OK;
+}
+
+long long phb_tlk_launch_count(const phb_tlk *t) { return phbc_launch_count(t->ctx); }

@@ -1,0 +1,276 @@
+"""ctypes mirror of the reference's tree-likelihood interface over the C ABI (include/physher_b200.h).
+
+Method names follow the reference so that the parity tests read like its own tests:
+`calculate()` is `tlk->calculate(tlk)` (treelikelihood.c:1552), `update_all_nodes()` is
+`SingleTreeLikelihood_update_all_nodes` (:1737), `use_rescaling()` is
+`SingleTreeLikelihood_use_rescaling` (:164 of the header), `initialize_gradient(flags)` /
+`gradient()` are `TreeLikelihood_initialize_gradient` / `TreeLikelihood_gradient` (:237, :320).
+Every call goes through the shared library; a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libphysher_b200.so")
+
+FLAG_TREE_MODEL = 1 << 0
+OPT_INCLUDE_ROOT_FREQS = 1
+OPT_COMPAT_SCALED_GRADIENT = 2
+OPT_UNROOTED = 3
+OPT_KERNELS = 4
+OPT_SCALING_THRESHOLD_EXP = 5
+KERNELS_AUTO, KERNELS_GENERIC, KERNELS_FUSED = 0, 1, 2
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+_bp = C.POINTER(C.c_uint8)
+
+# every symbol include/physher_b200.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("phb_last_error", C.c_char_p, []),
+    ("phb_device_count", C.c_int, []),
+    ("phb_version", C.c_char_p, []),
+    ("phb_tlk_create", C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, C.c_int, C.c_int]),
+    ("phb_tlk_free", None, [C.c_void_p]),
+    ("phb_tlk_set_tip_states", C.c_int, [C.c_void_p, _bp]),
+    ("phb_tlk_set_tip_partials", C.c_int, [C.c_void_p, _dp]),
+    ("phb_tlk_set_pattern_weights", C.c_int, [C.c_void_p, _dp]),
+    ("phb_tlk_set_eigen", C.c_int, [C.c_void_p, _dp, _dp, _dp]),
+    ("phb_tlk_set_matrices", C.c_int, [C.c_void_p, _dp, _dp]),
+    ("phb_tlk_set_frequencies", C.c_int, [C.c_void_p, _dp]),
+    ("phb_tlk_set_site_model", C.c_int, [C.c_void_p, _dp, _dp]),
+    ("phb_tlk_set_branch_lengths", C.c_int, [C.c_void_p, _dp]),
+    ("phb_tlk_set_branch_length", C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    ("phb_tlk_update_all_nodes", None, [C.c_void_p]),
+    ("phb_tlk_update_one_node", C.c_int, [C.c_void_p, C.c_int]),
+    ("phb_tlk_use_rescaling", C.c_int, [C.c_void_p, C.c_int]),
+    ("phb_tlk_rescaling", C.c_int, [C.c_void_p]),
+    ("phb_tlk_set_option", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("phb_tlk_calculate", C.c_int, [C.c_void_p, _dp]),
+    ("phb_tlk_pattern_log_likelihoods", C.c_int, [C.c_void_p, _dp]),
+    ("phb_tlk_initialize_gradient", C.c_size_t, [C.c_void_p, C.c_int]),
+    ("phb_tlk_gradient", C.c_int, [C.c_void_p, C.POINTER(_dp)]),
+    ("phb_tlk_cat_branch_gradient", C.c_int, [C.c_void_p, _dp]),
+    ("phb_tlk_get_partials", C.c_int, [C.c_void_p, C.c_int, _dp]),
+    ("phb_tlk_get_matrices", C.c_int, [C.c_void_p, _dp, _dp]),
+    ("phb_tlk_gradient_device", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("phb_tlk_stream", C.c_void_p, [C.c_void_p]),
+    ("phb_tlk_synchronize", C.c_int, [C.c_void_p]),
+    ("phb_tlk_gradient_batch", C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp]),
+    ("phb_tlk_launch_count", C.c_longlong, [C.c_void_p]),
+]
+
+
+class PhysherB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Load the in-tree shared library; fail loudly when it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise PhysherB200Error(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). The tree-likelihood path has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, restype, argtypes in SYMBOLS:
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def device_count() -> int:
+    return int(load_library().phb_device_count())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class SingleTreeLikelihood:
+    """One tree likelihood on one GPU (mirrors `struct _SingleTreeLikelihood`, treelikelihood.h:46-124)."""
+
+    def __init__(self, left, right, root, nstate, ncat, npatterns, use_tip_states=True, device=0):
+        self.lib = load_library()
+        self.left = np.ascontiguousarray(left, dtype=np.int32)
+        self.right = np.ascontiguousarray(right, dtype=np.int32)
+        self.N = int(self.left.shape[0])
+        self.T = (self.N + 1) // 2
+        self.S, self.C, self.P = int(nstate), int(ncat), int(npatterns)
+        self.root = int(root)
+        self.h = self.lib.phb_tlk_create(self.T, self.S, self.C, self.P, self.left.ctypes.data_as(_ip),
+                                         self.right.ctypes.data_as(_ip), self.root, int(bool(use_tip_states)), int(device))
+        if not self.h:
+            raise PhysherB200Error(self._err())
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _err(self) -> str:
+        return (self.lib.phb_last_error() or b"").decode()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise PhysherB200Error(f"[{rc}] {self._err()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.phb_tlk_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @classmethod
+    def from_problem(cls, pb, device=0, kernels=KERNELS_AUTO):
+        """Build from a plain-array problem description (attributes left, right, root, nstate, ...) and push every input."""
+        tlk = cls(pb.left, pb.right, pb.root, pb.nstate, pb.ncat, pb.npatterns, use_tip_states=pb.use_tip_states, device=device)
+        if pb.use_tip_states:
+            tlk.set_tip_states(pb.tip_states)
+        else:
+            tlk.set_tip_partials(pb.tip_partials)
+        tlk.set_pattern_weights(pb.weights)
+        if pb.evec is not None:
+            tlk.set_eigen(pb.evec, pb.eval, pb.ivec)
+        else:
+            tlk.set_matrices(pb.P_override, pb.dP_override)
+        tlk.set_frequencies(pb.freqs)
+        tlk.set_site_model(pb.rates, pb.props)
+        tlk.set_branch_lengths(pb.bl)
+        tlk.set_option(OPT_UNROOTED, int(pb.unrooted))
+        tlk.set_option(OPT_INCLUDE_ROOT_FREQS, int(pb.include_root_freqs))
+        tlk.set_option(OPT_COMPAT_SCALED_GRADIENT, int(pb.compat_scaled_gradient))
+        tlk.set_option(OPT_KERNELS, kernels)
+        if pb.scale:
+            tlk.use_rescaling(True)
+        return tlk
+
+    # -- inputs -----------------------------------------------------------------------------
+    def set_tip_states(self, states):
+        a = np.ascontiguousarray(states, dtype=np.uint8)
+        assert a.shape == (self.T, self.P)
+        self._check(self.lib.phb_tlk_set_tip_states(self.h, a.ctypes.data_as(_bp)))
+
+    def set_tip_partials(self, partials):
+        a = _f64(partials)
+        assert a.shape == (self.T, self.P, self.S)
+        self._check(self.lib.phb_tlk_set_tip_partials(self.h, a.ctypes.data_as(_dp)))
+
+    def set_pattern_weights(self, w):
+        a = _f64(w)
+        assert a.shape == (self.P,)
+        self._check(self.lib.phb_tlk_set_pattern_weights(self.h, a.ctypes.data_as(_dp)))
+
+    def set_eigen(self, evec, eval_, ivec):
+        e, v, i = _f64(evec), _f64(eval_), _f64(ivec)
+        assert e.shape == (self.S, self.S) and v.shape == (self.S,) and i.shape == (self.S, self.S)
+        self._check(self.lib.phb_tlk_set_eigen(self.h, e.ctypes.data_as(_dp), v.ctypes.data_as(_dp), i.ctypes.data_as(_dp)))
+
+    def set_matrices(self, P, dP):
+        a, b = _f64(P), _f64(dP)
+        assert a.shape == (self.N, self.C, self.S, self.S) == b.shape
+        self._check(self.lib.phb_tlk_set_matrices(self.h, a.ctypes.data_as(_dp), b.ctypes.data_as(_dp)))
+
+    def set_frequencies(self, freqs):
+        a = _f64(freqs)
+        assert a.shape == (self.S,)
+        self._check(self.lib.phb_tlk_set_frequencies(self.h, a.ctypes.data_as(_dp)))
+
+    def set_site_model(self, rates, props):
+        r, p = _f64(rates), _f64(props)
+        assert r.shape == (self.C,) == p.shape
+        self._check(self.lib.phb_tlk_set_site_model(self.h, r.ctypes.data_as(_dp), p.ctypes.data_as(_dp)))
+
+    def set_branch_lengths(self, bl):
+        a = _f64(bl)
+        assert a.shape == (self.N,)
+        self._check(self.lib.phb_tlk_set_branch_lengths(self.h, a.ctypes.data_as(_dp)))
+
+    def set_branch_length(self, node, bl):
+        self._check(self.lib.phb_tlk_set_branch_length(self.h, int(node), float(bl)))
+
+    def set_option(self, option, value):
+        self._check(self.lib.phb_tlk_set_option(self.h, int(option), int(value)))
+
+    # -- reference-named operations -----------------------------------------------------------
+    def update_all_nodes(self):
+        self.lib.phb_tlk_update_all_nodes(self.h)
+
+    def update_one_node(self, node):
+        self._check(self.lib.phb_tlk_update_one_node(self.h, int(node)))
+
+    def use_rescaling(self, use: bool):
+        self._check(self.lib.phb_tlk_use_rescaling(self.h, int(use)))
+
+    def rescaling(self) -> bool:
+        return bool(self.lib.phb_tlk_rescaling(self.h))
+
+    def calculate(self) -> float:
+        out = C.c_double(0.0)
+        self._check(self.lib.phb_tlk_calculate(self.h, C.byref(out)))
+        return out.value
+
+    def pattern_log_likelihoods(self):
+        out = np.zeros(self.P)
+        self._check(self.lib.phb_tlk_pattern_log_likelihoods(self.h, out.ctypes.data_as(_dp)))
+        return out
+
+    def initialize_gradient(self, flags=FLAG_TREE_MODEL) -> int:
+        return int(self.lib.phb_tlk_initialize_gradient(self.h, int(flags)))
+
+    def gradient(self):
+        """TreeLikelihood_gradient: copy of the tlk-owned gradient buffer (branch lengths by node id)."""
+        ptr = _dp()
+        self._check(self.lib.phb_tlk_gradient(self.h, C.byref(ptr)))
+        return np.ctypeslib.as_array(ptr, shape=(self.N,)).copy()
+
+    def cat_branch_gradient(self):
+        out = np.zeros((self.N, self.C))
+        self._check(self.lib.phb_tlk_cat_branch_gradient(self.h, out.ctypes.data_as(_dp)))
+        return out
+
+    def get_partials(self, index):
+        out = np.zeros((self.C, self.P, self.S))
+        self._check(self.lib.phb_tlk_get_partials(self.h, int(index), out.ctypes.data_as(_dp)))
+        return out
+
+    def get_matrices(self):
+        Pm = np.zeros((self.N, self.C, self.S, self.S))
+        dPm = np.zeros_like(Pm)
+        self._check(self.lib.phb_tlk_get_matrices(self.h, Pm.ctypes.data_as(_dp), dPm.ctypes.data_as(_dp)))
+        return Pm, dPm
+
+    # -- multi-GPU / batched ------------------------------------------------------------------
+    def gradient_device(self, out_ptr: int):
+        """[lnL, grad[0..N)] of this shard into device memory at `out_ptr`, ordered on the tlk stream."""
+        self._check(self.lib.phb_tlk_gradient_device(self.h, C.c_void_p(out_ptr)))
+
+    def stream(self) -> int:
+        return int(self.lib.phb_tlk_stream(self.h) or 0)
+
+    def synchronize(self):
+        self._check(self.lib.phb_tlk_synchronize(self.h))
+
+    def gradient_batch(self, bl, want_gradient=True):
+        a = _f64(bl)
+        assert a.ndim == 2 and a.shape[1] == self.N
+        B = a.shape[0]
+        lnl = np.zeros(B)
+        grad = np.zeros((B, self.N)) if want_gradient else None
+        self._check(self.lib.phb_tlk_gradient_batch(self.h, B, a.ctypes.data_as(_dp), lnl.ctypes.data_as(_dp),
+                                                    grad.ctypes.data_as(_dp) if want_gradient else None))
+        return lnl, grad
+
+    def launch_count(self) -> int:
+        return int(self.lib.phb_tlk_launch_count(self.h))

@@ -1,0 +1,216 @@
+"""CUDA path vs the oracle and the reference's golden outputs, through the C ABI (-m gpu).
+
+Tolerances (north_star): lnL and every branch gradient within 1e-10 relative in FP64; gradient
+entries relative to max(|g|, |g|_inf * 1e-6).
+"""
+import numpy as np
+import pytest
+
+import physher_b200 as phb
+from oracle import oracle as O
+from physher_b200 import models, synthetic as syn
+from physher_b200.treelikelihood import OPT_COMPAT_SCALED_GRADIENT, OPT_INCLUDE_ROOT_FREQS
+from tests.util import RTOL, golden_names, grad_err, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = [phb.KERNELS_GENERIC, phb.KERNELS_AUTO]
+KIDS = ["generic", "auto"]
+
+
+@pytest.mark.parametrize("kernels", KERNELS, ids=KIDS)
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_lnl_and_gradient(name, kernels):
+    pb, z = load_golden(name)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=kernels)
+    lnl = tlk.calculate()
+    assert rel_err(lnl, float(z["ref_lnl"])) < RTOL
+    np.testing.assert_allclose(tlk.pattern_log_likelihoods(), z["ref_pattern_lnl"], rtol=1e-10, atol=0)
+    want = O.evaluate(pb)
+    g = tlk.gradient()
+    assert grad_err(g, want["grad"]) < RTOL
+    if "ref_grad_exact" in z:
+        assert grad_err(g, z["ref_grad_exact"]) < RTOL
+        # the reference's default request (include_root_freqs = true, SURVEY 0.4 iii)
+        tlk.set_option(OPT_INCLUDE_ROOT_FREQS, 1)
+        assert grad_err(tlk.gradient(), z["ref_grad_default"]) < RTOL
+        tlk.set_option(OPT_INCLUDE_ROOT_FREQS, 0)
+    cg = tlk.cat_branch_gradient()
+    assert grad_err(cg.ravel(), np.where(np.arange(pb.nnodes)[:, None] == pb.root, 0, want["cat_grad"]).ravel()) < RTOL
+    tlk.close()
+
+
+@pytest.mark.parametrize("kernels", KERNELS, ids=KIDS)
+def test_kat_jc69_fluA(kernels):
+    """tests/test_tree_likelihood.c:28-40: lnL and clock-rate gradient of the reference's own known-answer test."""
+    pb, z = load_golden("c1_jc69_fluA_tipstates")
+    pb.include_root_freqs = True
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=kernels)
+    lnl = tlk.calculate()
+    assert abs(lnl - float(z["kat_lnl"])) < 1e-8
+    assert rel_err(lnl, float(z["kat_lnl"])) < RTOL
+    clock = float((tlk.gradient() * z["time_elapsed"]).sum())
+    assert rel_err(clock, float(z["kat_clock_grad"])) < RTOL
+    tlk.close()
+
+
+@pytest.mark.parametrize("kernels", KERNELS, ids=KIDS)
+@pytest.mark.parametrize("name", [n for n in golden_names() if "deep_scaled" in n or n.startswith("synth_gtr_g4_tip")])
+def test_rescaling(name, kernels):
+    pb, z = load_golden(name)
+    base = O.evaluate(pb)
+    pb.scale = True
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=kernels)
+    assert tlk.rescaling()
+    lnl = tlk.calculate()
+    assert rel_err(lnl, float(z["ref_lnl_scaled"])) < RTOL
+    # exact form under rescaling reproduces the unscaled gradient
+    g = tlk.gradient()
+    assert grad_err(g, base["grad"]) < 1e-9
+    assert grad_err(g, O.evaluate(pb)["grad"]) < RTOL
+    # reference-compatible per-category normalisation (SURVEY 0.4 ii)
+    tlk.set_option(OPT_COMPAT_SCALED_GRADIENT, 1)
+    assert grad_err(tlk.gradient(), z["ref_grad_scaled_compat"]) < RTOL
+    tlk.close()
+
+
+@pytest.mark.parametrize("kernels", KERNELS, ids=KIDS)
+def test_transition_matrices_and_partials(kernels):
+    pb, z = load_golden("tiny_gtr_g4")
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=phb.KERNELS_GENERIC)
+    tlk.gradient()
+    Pm, dPm = tlk.get_matrices()
+    keep = np.arange(pb.nnodes) != pb.root
+    np.testing.assert_allclose(Pm[keep], z["ref_matrices"][keep], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(dPm[keep], z["ref_dmatrices"][keep], rtol=0, atol=1e-12)
+    for n in range(pb.ntips, pb.nnodes):
+        np.testing.assert_allclose(tlk.get_partials(n), z["ref_lower"][n], rtol=1e-11, atol=0)
+    for n in range(pb.nnodes):
+        if n != pb.root:
+            np.testing.assert_allclose(tlk.get_partials(pb.nnodes + n), z["ref_upper"][n], rtol=1e-11, atol=1e-300)
+    tlk.close()
+
+
+def _synthetic_problem(T, P, S, C, seed, topo=None, unknown=0.01):
+    topo = topo or syn.random_topology(T, seed)
+    if S == 4:
+        m = models.gtr([0.05, 0.3, 0.1, 0.15, 0.3, 0.1], [0.1, 0.2, 0.3, 0.4])
+    else:
+        m = models.random_reversible(S, seed + 5)
+    rates, props = models.discrete_gamma(0.5, C)
+    return O.Problem(left=topo.left, right=topo.right, parent=topo.parent, root=topo.root, nstate=S,
+                     tip_states=syn.random_patterns(T, P, S, 0.15, seed + 1, unknown_frac=unknown),
+                     weights=np.random.default_rng(seed + 2).integers(1, 5, P).astype(np.float64),
+                     freqs=m.freqs, rates=rates, props=props, bl=syn.random_branch_lengths(topo, seed + 3),
+                     evec=m.evec, eval=m.eval, ivec=m.ivec)
+
+
+@pytest.mark.parametrize("kernels", KERNELS, ids=KIDS)
+@pytest.mark.parametrize("shape", [(50, 1000, 4, 4), (33, 517, 4, 1), (64, 300, 4, 2), (20, 130, 4, 3), (17, 1, 4, 4),
+                                   (12, 333, 20, 4), (9, 200, 20, 1), (7, 150, 61, 1), (6, 90, 61, 2), (10, 100, 5, 2), (8, 64, 7, 1)])
+def test_synthetic_against_oracle(shape, kernels):
+    """Seeded synthetic inputs at sizes the oracle finishes in seconds; ragged pattern counts included."""
+    T, P, S, C = shape
+    pb = _synthetic_problem(T, P, S, C, seed=1000 + T + P)
+    want = O.evaluate(pb)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=kernels)
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), want["grad"]) < RTOL
+    tlk.close()
+
+
+@pytest.mark.parametrize("kernels", KERNELS, ids=KIDS)
+@pytest.mark.parametrize("topo_kind", ["caterpillar", "balanced"])
+def test_extreme_topologies(topo_kind, kernels):
+    T = 128
+    topo = syn.caterpillar_topology(T) if topo_kind == "caterpillar" else syn.balanced_topology(T)
+    pb = _synthetic_problem(T, 200, 4, 4, seed=77, topo=topo)
+    want = O.evaluate(pb)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=kernels)
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), want["grad"]) < RTOL
+    tlk.close()
+
+
+@pytest.mark.parametrize("kernels", KERNELS, ids=KIDS)
+def test_tip_partials_mode_matches_tip_states_for_known_states(kernels):
+    pb = _synthetic_problem(15, 256, 4, 4, seed=5, unknown=0.0)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=kernels)
+    a = tlk.calculate()
+    ga = tlk.gradient()
+    tlk.close()
+    pb.use_tip_states = False
+    pb.tip_partials = np.eye(4)[pb.tip_states]
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=kernels)
+    assert rel_err(tlk.calculate(), a) < 1e-13
+    assert grad_err(tlk.gradient(), ga) < 1e-12
+    tlk.close()
+
+
+def test_caching_semantics():
+    """cached lnL if nothing is dirty (treelikelihood.c:1458); gradient cached until something changes (:323,:336)."""
+    pb = _synthetic_problem(20, 128, 4, 4, seed=9)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    a = tlk.calculate()
+    n0 = tlk.launch_count()
+    assert tlk.calculate() == a and tlk.launch_count() == n0
+    g = tlk.gradient()
+    n1 = tlk.launch_count()
+    assert np.array_equal(tlk.gradient(), g) and tlk.launch_count() == n1
+    tlk.set_branch_length(3, pb.bl[3] * 1.5)
+    b = tlk.calculate()
+    assert b != a and tlk.launch_count() > n1
+    pb.bl[3] *= 1.5
+    assert rel_err(b, O.evaluate(pb, gradient=False)["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), O.evaluate(pb)["grad"]) < RTOL
+    tlk.close()
+
+
+def test_unrooted_convention_and_root_entries():
+    pb = _synthetic_problem(20, 128, 4, 4, seed=10)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    g = tlk.gradient()
+    assert g[pb.root] == 0.0 and g[pb.right[pb.root]] == 0.0  # treelikelihood.c:3249-3255
+    tlk.close()
+
+
+def test_underflow_switches_rescaling_on():
+    """-inf lnL => rescaling on and everything recomputed (treelikelihood.c:1496-1519)."""
+    T = 600
+    topo = syn.caterpillar_topology(T)
+    pb = _synthetic_problem(T, 40, 4, 1, seed=3, topo=topo, unknown=0.0)
+    pb.tip_states = syn.random_patterns(T, 40, 4, 0.75, 4)
+    pb.bl = syn.random_branch_lengths(topo, 6, 0.8, 1.6)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    assert not tlk.rescaling()
+    lnl = tlk.calculate()
+    assert tlk.rescaling() and np.isfinite(lnl)
+    pb.scale = True
+    assert rel_err(lnl, O.evaluate(pb, gradient=False)["lnl"]) < RTOL
+    tlk.close()
+
+
+def test_negative_branch_length_is_rejected():
+    pb = _synthetic_problem(8, 32, 4, 1, seed=2)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    bl = pb.bl.copy()
+    bl[1] = -0.1
+    with pytest.raises(phb.PhysherB200Error, match="branch length"):
+        tlk.set_branch_lengths(bl)
+    tlk.close()
+
+
+def test_batched_branch_length_samples():
+    """B samples sharing topology and patterns (BASELINE config 3 shape, scaled down)."""
+    pb = _synthetic_problem(30, 500, 4, 4, seed=21)
+    rng = np.random.default_rng(22)
+    B = 5
+    bls = pb.bl[None, :] * rng.lognormal(0, 0.1, size=(B, pb.nnodes))
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    lnl, grad = tlk.gradient_batch(bls)
+    for b in range(B):
+        pb.bl = bls[b]
+        want = O.evaluate(pb)
+        assert rel_err(lnl[b], want["lnl"]) < RTOL
+        assert grad_err(grad[b], want["grad"]) < RTOL
+    tlk.close()
