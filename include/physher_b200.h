@@ -51,6 +51,7 @@ extern "C" {
 #define PHB_OPT_UNROOTED 3               /* 1 (default): zero the root's right child gradient (treelikelihood.c:3249-3255) */
 #define PHB_OPT_KERNELS 4                /* PHB_KERNELS_* : force a kernel family (testing / profiling) */
 #define PHB_OPT_SCALING_THRESHOLD_EXP 5  /* tlk->scaling_threshold = 10^-value (default 40, treelikelihood.c:1121) */
+#define PHB_OPT_TIMING 6                 /* 1: bracket the dominant kernel of every evaluation with CUDA events */
 
 #define PHB_KERNELS_AUTO 0    /* by state count, like the function-pointer dispatch at treelikelihood.c:1067-1165 */
 #define PHB_KERNELS_GENERIC 1 /* node-at-a-time kernels, any state count, materialised upper partials */
@@ -140,6 +141,10 @@ int phb_tlk_synchronize(phb_tlk *tlk);
 /* B branch-length vectors sharing topology, patterns and models: lnl[b], grad[b][N]. */
 int phb_tlk_gradient_batch(phb_tlk *tlk, int nbatch, const double *bl /* [B][N] */, double *lnl /* [B] */,
                            double *grad /* [B][N] */);
+
+/* With PHB_OPT_TIMING on: device time (CUDA events on the tlk stream) and launch count of the dominant kernel
+ * (the fused walk kernel, or the sum of the node-at-a-time kernels) since the option was set. Synchronises. */
+int phb_tlk_kernel_time(phb_tlk *tlk, double *total_ms, long long *launches);
 
 /* number of kernel launches issued by this tlk since creation (bench.py's gpu_launches) */
 long long phb_tlk_launch_count(const phb_tlk *tlk);

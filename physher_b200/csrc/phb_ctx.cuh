@@ -43,6 +43,12 @@ struct phbc_ctx {
 	double *d_walk_lower;    // per-CTA lower-partial scratch
 	double *d_walk_gacc;     // per-CTA gradient accumulators
 	size_t walk_lower_bytes, walk_gacc_bytes, walk_mats_bytes;
+	uint8_t *d_nuc4_codes;   // [T][P] 5-bit tip codes
+	int *d_nuc4_bad;
+	bool nuc4_codes_valid, nuc4_codes_bad;
+	double *d_nuc4_cta_lnl;
+	int nuc4_grid;
+	double *h_freqs, *h_qmat;  // host copies of small model constants (kernel parameter bank)
 
 	// outputs
 	double *d_pattern_lnl;   // [P]
@@ -53,7 +59,17 @@ struct phbc_ctx {
 	size_t scratch_bytes;
 
 	long long launches;
+
+	// optional event timing of the dominant kernel(s)
+	bool timing;
+	cudaEvent_t *ev_beg, *ev_end;
+	int ev_count, ev_cap;
+	double timed_ms;
+	long long timed_launches;
 };
+
+int phbc_time_begin(phbc_ctx *ctx);
+int phbc_time_end(phbc_ctx *ctx);
 
 extern thread_local char phbc_errbuf[512];
 

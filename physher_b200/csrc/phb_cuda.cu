@@ -96,10 +96,21 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	void *bufs[] = {ctx->d_tip_states, ctx->d_tip_partials, ctx->d_weights, ctx->d_evec, ctx->d_eval, ctx->d_ivec, ctx->d_qmat,
 	                ctx->d_freqs, ctx->d_rates, ctx->d_props, ctx->d_bl, ctx->d_P, ctx->d_dP, ctx->d_lower, ctx->d_upper,
 	                ctx->d_sf, ctx->d_lower_ops, ctx->d_upper_ops, ctx->d_post_ops, ctx->d_pre_ops, ctx->d_walk_mats,
-	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch};
+	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch,
+	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl};
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		if (bufs[i]) cudaFree(bufs[i]);
+	if (ctx->ev_beg) {
+		for (int i = 0; i < ctx->ev_cap; i++) {
+			cudaEventDestroy(ctx->ev_beg[i]);
+			cudaEventDestroy(ctx->ev_end[i]);
+		}
+		free(ctx->ev_beg);
+		free(ctx->ev_end);
+	}
 	if (ctx->h_bl) cudaFreeHost(ctx->h_bl);
+	free(ctx->h_freqs);
+	free(ctx->h_qmat);
 	free(ctx->h_lower_level_off);
 	free(ctx->h_upper_level_off);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -163,11 +174,13 @@ extern "C" int phbc_set_schedule(phbc_ctx *ctx, const phbc_schedule *s) {
 
 extern "C" int phbc_upload_tip_states(phbc_ctx *ctx, const uint8_t *states) {
 	if (!ctx->d_tip_states) return -1;
+	ctx->nuc4_codes_valid = false;
 	UPLOAD(ctx->d_tip_states, states, (size_t)ctx->T * ctx->P);
 	return 0;
 }
 extern "C" int phbc_upload_tip_partials(phbc_ctx *ctx, const double *partials) {
 	if (!ctx->d_tip_partials) return -1;
+	ctx->nuc4_codes_valid = false;
 	UPLOAD(ctx->d_tip_partials, partials, (size_t)ctx->T * ctx->P * ctx->S);
 	return 0;
 }
@@ -190,13 +203,16 @@ extern "C" int phbc_upload_eigen(phbc_ctx *ctx, const double *evec, const double
 		}
 	cudaError_t e = cudaMemcpyAsync(ctx->d_qmat, q, sizeof(double) * S * S, cudaMemcpyHostToDevice, ctx->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-	free(q);
+	free(ctx->h_qmat);
+	ctx->h_qmat = q;
 	PHBC_CHECK(e);
 	ctx->have_eigen = true;
 	return 0;
 }
 extern "C" int phbc_upload_freqs(phbc_ctx *ctx, const double *freqs) {
 	UPLOAD(ctx->d_freqs, freqs, (size_t)ctx->S);
+	if (!ctx->h_freqs) ctx->h_freqs = (double *)malloc(sizeof(double) * ctx->S);
+	memcpy(ctx->h_freqs, freqs, sizeof(double) * ctx->S);
 	return 0;
 }
 extern "C" int phbc_upload_site_model(phbc_ctx *ctx, const double *rates, const double *props) {
@@ -274,10 +290,12 @@ __global__ void k_transition_matrices(int S, int C, int root, const double *__re
 	for (int e = threadIdx.x; e < S * S; e += blockDim.x) {
 		const int i = e / S, j = e % S;
 		double p = 0.0, d = 0.0;
+		// same operation order and rounding as substmodel.c:539-555 (no fused multiply-add):
+		// PP[k][j] = Invevec[k][j] * exp(.), P[i][j] = sum_k PP[k][j] * evec[i][k]
 		for (int k = 0; k < S; k++) {
-			const double vi = evec[i * S + k] * ivec[k * S + j];
-			p += vi * ex[k];
-			d += vi * lex[k];
+			const double iv = ivec[k * S + j], ev = evec[i * S + k];
+			p = __dadd_rn(p, __dmul_rn(__dmul_rn(iv, ex[k]), ev));
+			d = __dadd_rn(d, __dmul_rn(__dmul_rn(iv, lex[k]), ev));
 		}
 		Pm[base + e] = fabs(p);
 		dPm[base + e] = d;
@@ -574,6 +592,7 @@ int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		PHBC_CHECK(cudaFuncSetAttribute(k_generic_branch_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	}
 	const int ptiles = (int)((P + GEN_PBLK - 1) / GEN_PBLK);
+	if ((rc = phbc_time_begin(ctx))) return rc;
 	// post-order, one launch per level
 	for (int l = 0; l < ctx->n_lower_levels; l++) {
 		const int beg = ctx->h_lower_level_off[l], cnt = ctx->h_lower_level_off[l + 1] - beg;
@@ -633,6 +652,7 @@ int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		                                                                          ctx->d_rates, result);
 		ctx->launches += 2;
 	}
+	if ((rc = phbc_time_end(ctx))) return rc;
 	PHBC_CHECK(cudaGetLastError());
 	return 0;
 }
@@ -721,4 +741,59 @@ extern "C" int phbc_synchronize(phbc_ctx *ctx) {
 	return 0;
 }
 extern "C" void *phbc_stream(phbc_ctx *ctx) { return (void *)ctx->stream; }
+
+// --- optional event timing -------------------------------------------------------------------
+static int drain_events(phbc_ctx *ctx) {
+	if (ctx->ev_count == 0) return 0;
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+	for (int i = 0; i < ctx->ev_count; i++) {
+		float ms = 0.f;
+		PHBC_CHECK(cudaEventElapsedTime(&ms, ctx->ev_beg[i], ctx->ev_end[i]));
+		ctx->timed_ms += ms;
+		ctx->timed_launches++;
+	}
+	ctx->ev_count = 0;
+	return 0;
+}
+int phbc_time_begin(phbc_ctx *ctx) {
+	if (!ctx->timing) return 0;
+	if (ctx->ev_count == ctx->ev_cap) {
+		int rc = drain_events(ctx);
+		if (rc) return rc;
+	}
+	PHBC_CHECK(cudaEventRecord(ctx->ev_beg[ctx->ev_count], ctx->stream));
+	return 0;
+}
+int phbc_time_end(phbc_ctx *ctx) {
+	if (!ctx->timing) return 0;
+	PHBC_CHECK(cudaEventRecord(ctx->ev_end[ctx->ev_count], ctx->stream));
+	ctx->ev_count++;
+	return 0;
+}
+extern "C" int phbc_set_timing(phbc_ctx *ctx, int on) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	if (on && !ctx->ev_beg) {
+		ctx->ev_cap = 256;
+		ctx->ev_beg = (cudaEvent_t *)calloc(ctx->ev_cap, sizeof(cudaEvent_t));
+		ctx->ev_end = (cudaEvent_t *)calloc(ctx->ev_cap, sizeof(cudaEvent_t));
+		for (int i = 0; i < ctx->ev_cap; i++) {
+			PHBC_CHECK(cudaEventCreate(&ctx->ev_beg[i]));
+			PHBC_CHECK(cudaEventCreate(&ctx->ev_end[i]));
+		}
+	}
+	int rc = drain_events(ctx);
+	if (rc) return rc;
+	ctx->timing = on != 0;
+	ctx->timed_ms = 0.0;
+	ctx->timed_launches = 0;
+	return 0;
+}
+extern "C" int phbc_kernel_time(phbc_ctx *ctx, double *total_ms, long long *launches) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	int rc = drain_events(ctx);
+	if (rc) return rc;
+	if (total_ms) *total_ms = ctx->timed_ms;
+	if (launches) *launches = ctx->timed_launches;
+	return 0;
+}
 extern "C" long long phbc_launch_count(const phbc_ctx *ctx) { return ctx->launches; }

@@ -38,21 +38,26 @@ typedef struct phbc_op {
 #define PHBC_W_SLOT 1 /* idx = shared-memory slot                           */
 #define PHBC_W_ROOT 2 /* pre-order only: the parent is the root (W = 1 or pi) */
 
-typedef struct phbc_post_op { /* one internal node, DFS post-order                                */
+typedef struct phbc_post_op { /* one internal node, DFS post-order; 32 bytes (TMA bulk-copy granule)   */
 	int16_t a_kind, b_kind;
 	int a_idx, b_idx;        /* tip id or slot                                                    */
 	int a_node, b_node;      /* node ids of the children (matrix owners)                          */
 	int dst_slot;            /* slot receiving the result                                         */
-	int node;                /* node id of the result (row T.. of the lower scratch)               */
+	int node;                /* node id of the result; its lower-scratch row is the op's own index */
+	int pad;
 } phbc_post_op;
 
-typedef struct phbc_pre_op { /* one internal node acting as parent, DFS pre-order                 */
+typedef struct phbc_pre_op { /* one internal node acting as parent, DFS pre-order; 48 bytes         */
 	int16_t u_kind;          /* PHBC_W_SLOT or PHBC_W_ROOT                                        */
-	int16_t a_tip, b_tip;    /* 1 when the child is a tip                                         */
+	int16_t a_tip;           /* 1 when child a is a tip                                           */
+	int16_t b_tip;
+	int16_t pad0;
 	int u_slot;              /* slot holding U_parent                                             */
 	int node;                /* parent node id (matrix P_node when not the root)                  */
 	int a_node, b_node;      /* children node ids                                                 */
 	int a_slot, b_slot;      /* slots receiving U_a / U_b for internal children (-1: not kept)    */
+	int a_row, b_row;        /* lower-scratch rows (post-order op index) of internal children     */
+	int pad1, pad2;
 } phbc_pre_op;
 
 typedef struct phbc_schedule {
@@ -113,6 +118,8 @@ int phbc_download_matrices(phbc_ctx *ctx, double *P, double *dP);
 int phbc_synchronize(phbc_ctx *ctx);
 void *phbc_stream(phbc_ctx *ctx);
 long long phbc_launch_count(const phbc_ctx *ctx);
+int phbc_set_timing(phbc_ctx *ctx, int on);
+int phbc_kernel_time(phbc_ctx *ctx, double *total_ms, long long *launches);
 
 #ifdef __cplusplus
 }

@@ -188,7 +188,7 @@ static int build_level_schedules(phb_tlk *t) {
 static void compute_need(const phb_tlk *t, int *need, int *size) {
 	/* node ids are not guaranteed to be a post-order: iterate with an explicit stack */
 	const int N = t->N;
-	int *stack = (int *)malloc(sizeof(int) * 2 * N);
+	int *stack = (int *)malloc(sizeof(int) * (6 * (size_t)N + 8));
 	int sp = 0;
 	stack[sp++] = t->root;
 	stack[sp++] = 0;
@@ -238,14 +238,15 @@ static int build_walk_schedules(phb_tlk *t) {
 	int *need = (int *)malloc(sizeof(int) * N);
 	int *size = (int *)malloc(sizeof(int) * N);
 	int *slot_of = (int *)malloc(sizeof(int) * N);
-	int *stack = (int *)malloc(sizeof(int) * 2 * N);
+	int *row_of = (int *)malloc(sizeof(int) * N);
+	int *stack = (int *)malloc(sizeof(int) * (6 * (size_t)N + 8));
 	SlotPool pool;
 	pool.cap = N + 1;
 	pool.used = (unsigned char *)calloc(pool.cap, 1);
 	pool.high = 0;
 	t->post_ops = (phbc_post_op *)malloc(sizeof(phbc_post_op) * (nint > 0 ? nint : 1));
 	t->pre_ops = (phbc_pre_op *)malloc(sizeof(phbc_pre_op) * (nint > 0 ? nint : 1));
-	if (!need || !size || !slot_of || !stack || !pool.used || !t->post_ops || !t->pre_ops) return PHB_ENOMEM;
+	if (!need || !size || !slot_of || !row_of || !stack || !pool.used || !t->post_ops || !t->pre_ops) return PHB_ENOMEM;
 	compute_need(t, need, size);
 
 	/* post-order: visit the child with the larger need first so that at most need[root] results are live */
@@ -279,7 +280,9 @@ static int build_walk_schedules(phb_tlk *t) {
 			if (!is_tip(t, a)) pool.used[slot_of[a]] = 0;
 			if (!is_tip(t, b)) pool.used[slot_of[b]] = 0;
 			op->dst_slot = slot_alloc(&pool);
+			op->pad = 0;
 			slot_of[n] = op->dst_slot;
+			row_of[n] = nops - 1;
 		}
 	}
 	t->post_slots = pool.high;
@@ -327,6 +330,10 @@ static int build_walk_schedules(phb_tlk *t) {
 			pool.used[slot_of[n]] = 0; /* consumed by this op */
 		}
 		op->a_slot = op->b_slot = -1;
+		op->pad0 = 0;
+		op->pad1 = op->pad2 = 0;
+		op->a_row = op->a_tip ? -1 : row_of[a];
+		op->b_row = op->b_tip ? -1 : row_of[b];
 		if (!op->a_tip) slot_of[a] = op->a_slot = slot_alloc(&pool);
 		if (!op->b_tip) slot_of[b] = op->b_slot = slot_alloc(&pool);
 		/* push so that the smaller-need internal child is popped first */
@@ -347,6 +354,7 @@ static int build_walk_schedules(phb_tlk *t) {
 	free(need);
 	free(size);
 	free(slot_of);
+	free(row_of);
 	free(stack);
 	free(pool.used);
 	if (nops != nint || npre != nint) return fail(PHB_EINVAL, "walk schedule covers %d/%d of %d internal nodes", nops, npre, nint);
@@ -585,6 +593,11 @@ int phb_tlk_set_option(phb_tlk *t, int option, int value) {
 		t->kernels = value;
 		break;
 	case PHB_OPT_SCALING_THRESHOLD_EXP: t->scaling_threshold = pow(10.0, -(double)value); break;
+	case PHB_OPT_TIMING: {
+		int rc = phbc_set_timing(t->ctx, value);
+		if (rc) return dev_fail(rc);
+		return PHB_OK;
+	}
 	default: return fail(PHB_EINVAL, "unknown option %d", option);
 	}
 	t->update_upper = 1;
@@ -761,8 +774,10 @@ int phb_tlk_synchronize(phb_tlk *t) {
 int phb_tlk_gradient_batch(phb_tlk *t, int nbatch, const double *bl, double *lnl, double *grad) {
 	if (nbatch < 1) return fail(PHB_EINVAL, "nbatch must be >= 1");
 	/* inputs other than branch lengths must be in place */
+	const int had_bl = t->have_bl;
 	t->have_bl = 1;
 	int rc = check_ready(t);
+	t->have_bl = had_bl;
 	if (rc) return rc;
 	for (int b = 0; b < nbatch; b++)
 		for (int n = 0; n < t->N; n++)
@@ -796,6 +811,12 @@ int phb_tlk_gradient_batch(phb_tlk *t, int nbatch, const double *bl, double *lnl
 		}
 	/* the single-sample state (t->bl, t->lk) is untouched but device partials now belong to the last sample */
 	phb_tlk_update_all_nodes(t);
+	return PHB_OK;
+}
+
+int phb_tlk_kernel_time(phb_tlk *t, double *total_ms, long long *launches) {
+	int rc = phbc_kernel_time(t->ctx, total_ms, launches);
+	if (rc) return dev_fail(rc);
 	return PHB_OK;
 }
 

@@ -23,6 +23,7 @@ OPT_COMPAT_SCALED_GRADIENT = 2
 OPT_UNROOTED = 3
 OPT_KERNELS = 4
 OPT_SCALING_THRESHOLD_EXP = 5
+OPT_TIMING = 6
 KERNELS_AUTO, KERNELS_GENERIC, KERNELS_FUSED = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
@@ -61,6 +62,7 @@ SYMBOLS = [
     ("phb_tlk_stream", C.c_void_p, [C.c_void_p]),
     ("phb_tlk_synchronize", C.c_int, [C.c_void_p]),
     ("phb_tlk_gradient_batch", C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp]),
+    ("phb_tlk_kernel_time", C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_longlong)]),
     ("phb_tlk_launch_count", C.c_longlong, [C.c_void_p]),
 ]
 
@@ -271,6 +273,12 @@ class SingleTreeLikelihood:
         self._check(self.lib.phb_tlk_gradient_batch(self.h, B, a.ctypes.data_as(_dp), lnl.ctypes.data_as(_dp),
                                                     grad.ctypes.data_as(_dp) if want_gradient else None))
         return lnl, grad
+
+    def kernel_time(self):
+        """(total ms, launches) of the dominant kernel since OPT_TIMING was switched on."""
+        ms, n = C.c_double(0.0), C.c_longlong(0)
+        self._check(self.lib.phb_tlk_kernel_time(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
 
     def launch_count(self) -> int:
         return int(self.lib.phb_tlk_launch_count(self.h))
