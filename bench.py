@@ -54,7 +54,9 @@ def make_inputs(cfg: dict, rank: int, seed: int = 20261017):
     else:
         m = models.random_reversible(S, seed + 2)
     rates, props = models.discrete_gamma(0.5, C)
-    patterns = syn.random_patterns(T, P, S, cfg["mu"], seed + 100 + rank)
+    # data evolved down the same tree at 0.35x the evaluation branch lengths: all columns unique, per-pattern lnL
+    # around -240 (min > -400), so neither arm ever switches rescaling on (SURVEY.md 8c caveat 2)
+    patterns = syn.simulate_patterns(topo, bl * 0.35, P, S, seed + 100 + rank)
     weights = np.ones(P)
     return topo, bl, m, rates, props, patterns, weights
 

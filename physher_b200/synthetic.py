@@ -137,6 +137,30 @@ def random_patterns(ntips: int, npatterns: int, nstate: int, mu: float, seed: in
     return out
 
 
+def simulate_patterns(topo: Topology, bl: np.ndarray, npatterns: int, nstate: int, seed: int, unknown_frac: float = 0.0) -> np.ndarray:
+    """uint8 [T][P] tip states evolved DOWN the given tree (so the data fit the tree and per-pattern lnL stays
+    well above the double-precision underflow range): root state uniform; along a branch of length t a site keeps
+    its parent's state with probability exp(-t S/(S-1)) and is redrawn uniformly otherwise (a Jukes-Cantor-like
+    process on S states)."""
+    rng = np.random.default_rng(seed)
+    out = np.empty((topo.ntips, npatterns), np.uint8)
+    state = {topo.root: rng.integers(0, nstate, size=npatterns, dtype=np.uint8)}
+    stack = [topo.root]
+    while stack:
+        n = stack.pop()
+        cur = state.pop(n)
+        if topo.left[n] < 0:
+            out[n] = cur
+            continue
+        for ch in (int(topo.left[n]), int(topo.right[n])):
+            keep = rng.random(npatterns) < np.exp(-bl[ch] * nstate / (nstate - 1.0))
+            state[ch] = np.where(keep, cur, rng.integers(0, nstate, size=npatterns, dtype=np.uint8))
+            stack.append(ch)
+    if unknown_frac > 0:
+        out[rng.random(out.shape) < unknown_frac] = nstate
+    return out
+
+
 def to_newick(topo: Topology, bl: np.ndarray, names: list[str]) -> str:
     """Newick string whose physher parse reproduces `topo`'s ids (left child first)."""
     out = {}

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Summarise an .ncu-rep (read here, without a GPU) into the few numbers the roofline argument needs.
+
+    python tools/ncu_summary.py gpurun_out/prof.ncu-rep [--out profiles/name.md] [--title "..."]
+"""
+import argparse
+import csv
+import io
+import subprocess
+from collections import Counter
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+    "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_tma.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
+    "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "smsp__average_warp_latency_per_inst_issued.ratio",
+]
+
+
+def ncu_csv(rep, page):
+    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+    return list(csv.reader(io.StringIO(out)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("rep")
+    ap.add_argument("--out")
+    ap.add_argument("--title", default="")
+    a = ap.parse_args()
+    lines = [f"# {a.title or a.rep}", "", f"source: `{a.rep}` (ncu --set full --clock-control none --import-source on)", ""]
+    raw = ncu_csv(a.rep, "raw")
+    hdr, units = raw[0], raw[1]
+    for row in raw[2:]:
+        name = row[hdr.index("Kernel Name")] if "Kernel Name" in hdr else "?"
+        lines += [f"## {name}", "", "| metric | value | unit |", "|---|---|---|"]
+        for k in KEYS:
+            if k in hdr:
+                i = hdr.index(k)
+                lines.append(f"| {k} | {row[i]} | {units[i]} |")
+        stalls = [(h, float(row[i] or 0)) for i, h in enumerate(hdr) if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
+        stalls.sort(key=lambda x: -x[1])
+        lines += ["", "warp stall reasons (warps stalled per issue-active cycle): " +
+                  ", ".join(f"{h.split('stalled_')[1].split('_per_')[0]} {v:.2f}" for h, v in stalls[:8]), ""]
+    src = ncu_csv(a.rep, "source")
+    if len(src) > 2:
+        h = src[1]
+        ia, isrc = h.index("Instructions Executed"), h.index("Source")
+        c = Counter()
+        tot = 0
+        for r in src[2:]:
+            t = r[isrc].split()
+            if not t:
+                continue
+            op = (t[1] if t[0].startswith("@") and len(t) > 1 else t[0]).split(".")[0]
+            n = int(r[ia] or 0)
+            c[op] += n
+            tot += n
+        lines += ["SASS instruction mix (executed warp instructions): " + ", ".join(f"{op} {n/tot*100:.1f}%" for op, n in c.most_common(14)), ""]
+    text = "\n".join(lines)
+    if a.out:
+        open(a.out, "w").write(text + "\n")
+    print(text)
+
+
+if __name__ == "__main__":
+    main()
