@@ -39,11 +39,13 @@ struct phbc_ctx {
 	phbc_post_op *d_post_ops;
 	phbc_pre_op *d_pre_ops;
 	int n_post, n_pre, post_slots, pre_slots;
+	int *d_post_tip_order, *d_pre_tip_order;    // [T]
+	int post_first_tips, pre_first_tips;
 	double *d_walk_mats;     // schedule-ordered transition matrices
 	double *d_walk_lower;    // per-CTA lower-partial scratch
 	double *d_walk_gacc;     // per-CTA gradient accumulators
 	size_t walk_lower_bytes, walk_gacc_bytes, walk_mats_bytes;
-	uint8_t *d_nuc4_codes;   // [T][P] 5-bit tip codes
+	uint8_t *d_nuc4_codes;   // [2][tiles][T][PB] tip codes in post- and pre-order walk order
 	int *d_nuc4_bad;
 	bool nuc4_codes_valid, nuc4_codes_bad;
 	double *d_nuc4_cta_lnl;

@@ -97,7 +97,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	                ctx->d_freqs, ctx->d_rates, ctx->d_props, ctx->d_bl, ctx->d_P, ctx->d_dP, ctx->d_lower, ctx->d_upper,
 	                ctx->d_sf, ctx->d_lower_ops, ctx->d_upper_ops, ctx->d_post_ops, ctx->d_pre_ops, ctx->d_walk_mats,
 	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch,
-	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl};
+	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl, ctx->d_post_tip_order, ctx->d_pre_tip_order};
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		if (bufs[i]) cudaFree(bufs[i]);
 	if (ctx->ev_beg) {
@@ -148,6 +148,11 @@ extern "C" int phbc_set_schedule(phbc_ctx *ctx, const phbc_schedule *s) {
 	if ((rc = upload_array(ctx, &ctx->d_upper_ops, s->upper_ops, (size_t)s->n_upper_ops))) return rc;
 	if ((rc = upload_array(ctx, &ctx->d_post_ops, s->post_ops, (size_t)s->n_post))) return rc;
 	if ((rc = upload_array(ctx, &ctx->d_pre_ops, s->pre_ops, (size_t)s->n_pre))) return rc;
+	if ((rc = upload_array(ctx, &ctx->d_post_tip_order, s->post_tip_order, (size_t)ctx->T))) return rc;
+	if ((rc = upload_array(ctx, &ctx->d_pre_tip_order, s->pre_tip_order, (size_t)ctx->T))) return rc;
+	ctx->post_first_tips = s->post_first_tips;
+	ctx->pre_first_tips = s->pre_first_tips;
+	ctx->nuc4_codes_valid = false;
 	ctx->n_lower_ops = s->n_lower_ops;
 	ctx->n_upper_ops = s->n_upper_ops;
 	ctx->n_lower_levels = s->n_lower_levels;

@@ -33,31 +33,35 @@ typedef struct phbc_op {
 	int flags; /* bit 0: multiply the result by the root frequencies (treelikelihood.c:2148-2153) */
 } phbc_op;
 
-/* Whole-tree walk schedules of the fused 4-state kernels (see phb_nuc4.cu). Operand kinds: */
+/* Whole-tree walk schedules of the fused 4-state kernels (see phb_nuc4.cu). Ops are consumed in chunks of
+ * PHBC_WALK_CHUNK (one TMA stage); tip operands are numbered in walk order so that the tip codes a chunk
+ * needs are one contiguous range [chunk_tip0[ch], chunk_tip0[ch+1]) of a walk-ordered code array, and the
+ * descriptors carry indices local to that range.  Operand kinds: */
+#define PHBC_WALK_CHUNK 4
 #define PHBC_W_TIP 0  /* idx = tip node id                                  */
 #define PHBC_W_SLOT 1 /* idx = shared-memory slot                           */
 #define PHBC_W_ROOT 2 /* pre-order only: the parent is the root (W = 1 or pi) */
+#define PHBC_W_REG 3  /* the value is still in the registers of the preceding op   */
 
 typedef struct phbc_post_op { /* one internal node, DFS post-order; 32 bytes (TMA bulk-copy granule)   */
-	int16_t a_kind, b_kind;
-	int a_idx, b_idx;        /* tip id or slot                                                    */
+	int16_t a_kind, b_kind;  /* a tip child always comes first: kind = a_kind + b_kind in {0 tip-tip, 1 tip-internal, 2 internal-internal} */
+	int a_idx, b_idx;        /* slot, or chunk-local index of the tip operand's code row           */
 	int a_node, b_node;      /* node ids of the children (matrix owners)                          */
 	int dst_slot;            /* slot receiving the result                                         */
 	int node;                /* node id of the result; its lower-scratch row is the op's own index */
-	int pad;
+	int next_tips;           /* first op of a chunk: (first tip index << 5 | tip count) of the NEXT chunk */
 } phbc_post_op;
 
 typedef struct phbc_pre_op { /* one internal node acting as parent, DFS pre-order; 48 bytes         */
 	int16_t u_kind;          /* PHBC_W_SLOT or PHBC_W_ROOT                                        */
-	int16_t a_tip;           /* 1 when child a is a tip                                           */
-	int16_t b_tip;
-	int16_t pad0;
+	int16_t kind;            /* 0 tip-tip, 1 tip-internal (the tip is child a), 2 internal-internal */
+	int next_tips;           /* as in phbc_post_op                                                */
 	int u_slot;              /* slot holding U_parent                                             */
 	int node;                /* parent node id (matrix P_node when not the root)                  */
 	int a_node, b_node;      /* children node ids                                                 */
 	int a_slot, b_slot;      /* slots receiving U_a / U_b for internal children (-1: not kept)    */
 	int a_row, b_row;        /* lower-scratch rows (post-order op index) of internal children     */
-	int pad1, pad2;
+	int a_code, b_code;      /* chunk-local index of a tip child's code row                       */
 } phbc_pre_op;
 
 typedef struct phbc_schedule {
@@ -71,6 +75,9 @@ typedef struct phbc_schedule {
 	const phbc_post_op *post_ops;
 	const phbc_pre_op *pre_ops;
 	int post_slots, pre_slots;  /* shared-memory slots the walks need                             */
+	const int *post_tip_order;  /* [T] tip node ids in the order the post-order walk consumes them */
+	const int *pre_tip_order;   /* [T] same for the pre-order walk                                 */
+	int post_first_tips, pre_first_tips; /* tip count of chunk 0 of each walk (its first index is 0)  */
 } phbc_schedule;
 
 int phbc_device_count(void);

@@ -30,15 +30,16 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define NUC4_CHUNK 8  // ops per TMA chunk
+#define NUC4_CHUNK PHBC_WALK_CHUNK  // ops per TMA chunk
 #define NUC4_NT 256   // threads per CTA
 
 struct Nuc4Params {
 	int T, N, C, P, PB, root;
 	int n_post, n_pre, nslots, ntiles;
 	int include_root_freqs, compat;
+	int post_first_tips, pre_first_tips;  // tip count of chunk 0 of each walk
 	double threshold;
-	const uint8_t *tip_codes;  // [T][P]
+	const uint8_t *tip_codes;  // [2 walks][tiles][T][PB], rows in walk order
 	const double *weights;
 	const double *props;
 	const phbc_post_op *post_ops;
@@ -50,6 +51,8 @@ struct Nuc4Params {
 	double *cta_lnl;          // [grid]
 	double *pattern_lnl;      // [P]
 	double freqs[4];
+	double fq[4];     // weights of the gradient numerator: pi, or 1 when the root frequencies are folded into the uppers
+	double wroot[4];  // upper message entering the root's children: 1, or pi (tlk->include_root_freqs)
 	double Q[16];
 };
 
@@ -100,72 +103,98 @@ __device__ __forceinline__ void matvec_smem(const double *__restrict__ M, const 
 	}
 }
 
-// tip message: code bits 0-3 = set of compatible states, bit 4 = "missing, factor exactly 1"
-// (state tips with state >= 4, treelikelihood4.c:1107-1150).  One-hot codes gather a column.
+// Tip codes: 0..3 a known state (gather one column), 4 missing with factor exactly 1 (state tips with
+// state >= 4, treelikelihood4.c:1107-1150), 0x10 | mask an ambiguity set (tip partial vectors: sum of columns).
 __device__ __forceinline__ void tip_message(const double *__restrict__ M, unsigned code, double (&y)[4]) {
-	const bool simple = (code & 0x10u) || __popc(code & 0xfu) == 1;
-	if (__all_sync(0xffffffffu, simple)) {
-		const int s = (code & 0x10u) ? 0 : (__ffs(code) - 1);
+	if (__all_sync(0xffffffffu, code < 4u)) {
 #pragma unroll
-		for (int i = 0; i < 4; i++) {
-			const double v = M[4 * i + s];
-			y[i] = (code & 0x10u) ? 1.0 : v;
-		}
+		for (int i = 0; i < 4; i++) y[i] = M[4 * i + code];
 	} else {
 		double x[4];
 #pragma unroll
-		for (int j = 0; j < 4; j++) x[j] = ((code >> j) & 1u) ? 1.0 : 0.0;
-		if (code & 0x10u) x[0] = x[1] = x[2] = x[3] = 0.0;
+		for (int j = 0; j < 4; j++) x[j] = (code < 4u ? code == (unsigned)j : ((code >> j) & 1u)) ? 1.0 : 0.0;
 		matvec_smem(M, x, y);
-		if (code & 0x10u) y[0] = y[1] = y[2] = y[3] = 1.0;
+		if (code == 4u) y[0] = y[1] = y[2] = y[3] = 1.0;
 	}
 }
 
-struct Slots {
-	double2 *base;  // [slot][half][NT]
-	__device__ __forceinline__ void load(int slot, double (&x)[4]) const {
-		const double2 lo = base[(slot * 2 + 0) * NUC4_NT + threadIdx.x];
-		const double2 hi = base[(slot * 2 + 1) * NUC4_NT + threadIdx.x];
-		x[0] = lo.x, x[1] = lo.y, x[2] = hi.x, x[3] = hi.y;
-	}
-	__device__ __forceinline__ void store(int slot, const double (&x)[4]) const {
-		base[(slot * 2 + 0) * NUC4_NT + threadIdx.x] = make_double2(x[0], x[1]);
-		base[(slot * 2 + 1) * NUC4_NT + threadIdx.x] = make_double2(x[2], x[3]);
-	}
-};
+#define NUC4_SLOT_BYTES (2 * NUC4_NT * 16)  // one slot: two halves of NT double2
+#define NUC4_ROW_BYTES (NUC4_NT * 32)       // one lower-scratch row: same two-half layout
 
-__device__ __forceinline__ void load_lower(const double *__restrict__ p, double (&x)[4]) {
-	const double2 lo = __ldcs(reinterpret_cast<const double2 *>(p));
-	const double2 hi = __ldcs(reinterpret_cast<const double2 *>(p) + 1);
+// thread-private 32-byte cells inside a [half][NT] double2 tile (conflict-free 128-bit accesses)
+__device__ __forceinline__ void cell_load(const unsigned char *cell, double (&x)[4]) {
+	const double2 lo = *reinterpret_cast<const double2 *>(cell);
+	const double2 hi = *reinterpret_cast<const double2 *>(cell + NUC4_NT * 16);
 	x[0] = lo.x, x[1] = lo.y, x[2] = hi.x, x[3] = hi.y;
 }
-__device__ __forceinline__ void store_lower(double *__restrict__ p, const double (&x)[4]) {
-	__stcs(reinterpret_cast<double2 *>(p), make_double2(x[0], x[1]));
-	__stcs(reinterpret_cast<double2 *>(p) + 1, make_double2(x[2], x[3]));
+__device__ __forceinline__ void cell_store(unsigned char *cell, const double (&x)[4]) {
+	*reinterpret_cast<double2 *>(cell) = make_double2(x[0], x[1]);
+	*reinterpret_cast<double2 *>(cell + NUC4_NT * 16) = make_double2(x[2], x[3]);
+}
+// lower-scratch rows use the same layout in global memory (streaming loads / stores: touched once each way)
+__device__ __forceinline__ void row_load(const unsigned char *cell, double (&x)[4]) {
+	const double2 lo = __ldcs(reinterpret_cast<const double2 *>(cell));
+	const double2 hi = __ldcs(reinterpret_cast<const double2 *>(cell + NUC4_NT * 16));
+	x[0] = lo.x, x[1] = lo.y, x[2] = hi.x, x[3] = hi.y;
+}
+__device__ __forceinline__ void row_store(unsigned char *cell, const double (&x)[4]) {
+	__stcs(reinterpret_cast<double2 *>(cell), make_double2(x[0], x[1]));
+	__stcs(reinterpret_cast<double2 *>(cell + NUC4_NT * 16), make_double2(x[2], x[3]));
 }
 
 // ---------------------------------------------------------------------------------------------
 // the walk kernel
 // ---------------------------------------------------------------------------------------------
 // shared memory map (dynamic):
-//   [0, 16)                      two mbarriers
-//   stage[2]: each NUC4_CHUNK * (48 + 3*C*128) bytes (descriptors then matrices)
-//   slots:    nslots * 2 * NT * 16 bytes
+//   [0, 16)   two mbarriers
+//   stage[2]: each CHUNK * 48 B of descriptors, CHUNK * 3*C*128 B of matrices, 2*CHUNK * PB B of tip codes
+//   slots:    nslots * NUC4_SLOT_BYTES
 //   xch:      exchange area for cross-category sums (4 * C * PB doubles) + invLw[PB] + sfslot[nslots][NT]
-template <bool SCALE, bool GRAD>
-__global__ void __launch_bounds__(NUC4_NT, 2) k_nuc4_walk(const Nuc4Params prm) {
+struct Nuc4Stage {
+	uint32_t desc_off, mat_off, code_off, bytes;
+};
+__host__ __device__ constexpr Nuc4Stage nuc4_stage_layout(int C, int PB) {
+	return Nuc4Stage{0u, (uint32_t)(NUC4_CHUNK * 48), (uint32_t)(NUC4_CHUNK * 48 + NUC4_CHUNK * 3 * C * 128),
+	                 (uint32_t)((NUC4_CHUNK * 48 + NUC4_CHUNK * 3 * C * 128 + 2 * NUC4_CHUNK * PB + 127) & ~127)};
+}
+
+// 4 values per lane -> 4 warp totals in 6 shuffle rounds: lane 0 gets v0, lane 8 v2, lane 16 v1, lane 24 v3
+__device__ __forceinline__ double butterfly4(double v0, double v1, double v2, double v3, int lane) {
+	const bool h16 = lane & 16, h8 = lane & 8;
+	const double r01 = (h16 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, h16 ? v0 : v1, 16);
+	const double r23 = (h16 ? v3 : v2) + __shfl_xor_sync(0xffffffffu, h16 ? v2 : v3, 16);
+	double r = (h8 ? r23 : r01) + __shfl_xor_sync(0xffffffffu, h8 ? r01 : r23, 8);
+	r += __shfl_xor_sync(0xffffffffu, r, 4);
+	r += __shfl_xor_sync(0xffffffffu, r, 2);
+	r += __shfl_xor_sync(0xffffffffu, r, 1);
+	return r;
+}
+// 2 values per lane: lane 0 gets v0, lane 16 gets v1
+__device__ __forceinline__ double butterfly2(double v0, double v1, int lane) {
+	const bool h16 = lane & 16;
+	double r = (h16 ? v1 : v0) + __shfl_xor_sync(0xffffffffu, h16 ? v0 : v1, 16);
+	r += __shfl_xor_sync(0xffffffffu, r, 8);
+	r += __shfl_xor_sync(0xffffffffu, r, 4);
+	r += __shfl_xor_sync(0xffffffffu, r, 2);
+	r += __shfl_xor_sync(0xffffffffu, r, 1);
+	return r;
+}
+
+template <int C, bool SCALE, bool GRAD>
+__global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	const int C = prm.C, PB = prm.PB;
+	constexpr int PB = NUC4_NT / C;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int c = tid / PB, pl = tid - c * PB;
-	const size_t stage_bytes = (size_t)NUC4_CHUNK * (48 + 3 * C * 128);
+	constexpr Nuc4Stage lay = nuc4_stage_layout(C, PB);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
 	unsigned char *stage0 = smem_raw + 128;
-	Slots slots;
-	slots.base = reinterpret_cast<double2 *>(stage0 + 2 * stage_bytes);
-	double *xch = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(slots.base) + (size_t)prm.nslots * 2 * NUC4_NT * 16);
+	unsigned char *slot_cell = stage0 + 2 * lay.bytes + tid * 16;  // this thread's cell in slot 0
+	double *xch = reinterpret_cast<double *>(stage0 + 2 * lay.bytes + (size_t)prm.nslots * NUC4_SLOT_BYTES);
 	double *invLw = xch + 4 * C * PB;
 	double *sfslot = invLw + PB;  // [nslots][NT] thread-private copies (SCALE only)
+	const uint32_t my_mat = lay.mat_off + c * 128;  // this thread's category inside a staged matrix group
+	const uint32_t my_code = lay.code_off + pl;
 
 	if (tid == 0) {
 		mbar_init(&bars[0], 1);
@@ -174,69 +203,68 @@ __global__ void __launch_bounds__(NUC4_NT, 2) k_nuc4_walk(const Nuc4Params prm) 
 	}
 	__syncthreads();
 
-	uint32_t loads = 0;  // chunk loads consumed so far by this CTA (uniform): stage = loads & 1, parity = (loads >> 1) & 1
+	uint32_t loads = 0;  // chunk loads consumed so far (CTA-uniform): stage = loads & 1, parity = (loads >> 1) & 1
 	const double prop_c = (C == 1) ? 1.0 : prm.props[c];
 	double cta_lnl = 0.0;
-	double *my_lower = GRAD ? prm.lower + (size_t)blockIdx.x * prm.n_post * C * PB * 4 : nullptr;
+	unsigned char *row_cell = GRAD ? reinterpret_cast<unsigned char *>(prm.lower) + (size_t)blockIdx.x * prm.n_post * NUC4_ROW_BYTES + tid * 16 : nullptr;
 	double *my_gacc = GRAD ? prm.gacc + ((size_t)blockIdx.x * (NUC4_NT / 32) + warp) * prm.N : nullptr;
 
 	for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
 		const int p = tile * PB + pl;
 		const bool live = p < prm.P;
-		const int pc = live ? p : prm.P - 1;  // clamp loads of the ragged last tile
-		const uint8_t *codes = prm.tip_codes + pc;
+		const uint8_t *tile_codes_post = prm.tip_codes + (size_t)tile * prm.T * PB;
+		const uint8_t *tile_codes_pre = prm.tip_codes + ((size_t)prm.ntiles + tile) * prm.T * PB;
 
 		// ------------------------------------------------------------------ post-order
 		double out[4] = {1.0, 1.0, 1.0, 1.0};
 		double sf_acc = 0.0;  // SCALE: log scaling factor of the value currently in `out`
 		{
 			const int nchunks = (prm.n_post + NUC4_CHUNK - 1) / NUC4_CHUNK;
-			auto issue = [&](int ch, uint32_t ld) {
+			// one TMA stage: descriptors, walk-ordered matrices, walk-ordered tip codes of the chunk
+			auto issue = [&](int ch, uint32_t ld, int tips) {
 				const int first = ch * NUC4_CHUNK;
 				const int cnt = min(NUC4_CHUNK, prm.n_post - first);
-				unsigned char *dst = stage0 + (ld & 1) * stage_bytes;
+				unsigned char *dst = stage0 + (ld & 1) * lay.bytes;
 				const uint32_t dbytes = cnt * (uint32_t)sizeof(phbc_post_op), mbytes = cnt * 2 * C * 128;
-				mbar_expect_tx(&bars[ld & 1], dbytes + mbytes);
-				bulk_g2s(dst, prm.post_ops + first, dbytes, &bars[ld & 1]);
-				bulk_g2s(dst + NUC4_CHUNK * 48, prm.post_mats + (size_t)first * 2 * C * 16, mbytes, &bars[ld & 1]);
+				const uint32_t cbytes = (tips & 31) * PB;
+				mbar_expect_tx(&bars[ld & 1], dbytes + mbytes + cbytes);
+				bulk_g2s(dst + lay.desc_off, prm.post_ops + first, dbytes, &bars[ld & 1]);
+				bulk_g2s(dst + lay.mat_off, prm.post_mats + (size_t)first * 2 * C * 16, mbytes, &bars[ld & 1]);
+				if (cbytes) bulk_g2s(dst + lay.code_off, tile_codes_post + (size_t)(tips >> 5) * PB, cbytes, &bars[ld & 1]);
 			};
-			if (tid == 0) issue(0, loads);
+			if (tid == 0) issue(0, loads, prm.post_first_tips);
 			for (int ch = 0; ch < nchunks; ch++) {
-				if (tid == 0 && ch + 1 < nchunks) issue(ch + 1, loads + 1);
 				mbar_wait(&bars[loads & 1], (loads >> 1) & 1);
-				const unsigned char *st = stage0 + (loads & 1) * stage_bytes;
-				const phbc_post_op *desc = reinterpret_cast<const phbc_post_op *>(st);
-				const double *mats = reinterpret_cast<const double *>(st + NUC4_CHUNK * 48);
+				const unsigned char *st = stage0 + (loads & 1) * lay.bytes;
+				const phbc_post_op *desc = reinterpret_cast<const phbc_post_op *>(st + lay.desc_off);
+				if (tid == 0 && ch + 1 < nchunks) issue(ch + 1, loads + 1, desc[0].next_tips);
+				const unsigned char *mats = st + my_mat;
+				const uint8_t *cds = st + my_code;
 				const int first = ch * NUC4_CHUNK;
 				const int cnt = min(NUC4_CHUNK, prm.n_post - first);
-				// prefetch the tip codes of the first op of the chunk
-				unsigned codeA = 0, codeB = 0;
-				if (desc[0].a_kind == PHBC_W_TIP) codeA = codes[(size_t)desc[0].a_idx * prm.P];
-				if (desc[0].b_kind == PHBC_W_TIP) codeB = codes[(size_t)desc[0].b_idx * prm.P];
+#pragma unroll 1
 				for (int j = 0; j < cnt; j++) {
-					const phbc_post_op d = desc[j];
-					const unsigned curA = codeA, curB = codeB;
-					if (j + 1 < cnt) {  // software prefetch of the next op's tip codes
-						if (desc[j + 1].a_kind == PHBC_W_TIP) codeA = codes[(size_t)desc[j + 1].a_idx * prm.P];
-						if (desc[j + 1].b_kind == PHBC_W_TIP) codeB = codes[(size_t)desc[j + 1].b_idx * prm.P];
-					}
-					const double *MA = mats + ((size_t)(j * 2 + 0) * C + c) * 16;
-					const double *MB = mats + ((size_t)(j * 2 + 1) * C + c) * 16;
-					double ma[4], mb[4], x[4];
+					const int kind = desc[j].a_kind + desc[j].b_kind;
+					const int a_idx = desc[j].a_idx, b_idx = desc[j].b_idx, dst_slot = desc[j].dst_slot;
+					const double *MA = reinterpret_cast<const double *>(mats + j * 2 * C * 128);
+					const double *MB = reinterpret_cast<const double *>(mats + (j * 2 + 1) * C * 128);
+					double ma[4], mb[4];
 					double sf_in = 0.0;
-					if (d.a_kind == PHBC_W_TIP) {
-						tip_message(MA, curA, ma);
+					// operand b of kinds 1 and 2 is the previous op's result, still in `out`
+					if (kind == 0) {
+						tip_message(MA, cds[a_idx * PB], ma);
+						tip_message(MB, cds[b_idx * PB], mb);
 					} else {
-						slots.load(d.a_idx, x);
-						matvec_smem(MA, x, ma);
-						if (SCALE) sf_in += sfslot[d.a_idx * NUC4_NT + tid];
-					}
-					if (d.b_kind == PHBC_W_TIP) {
-						tip_message(MB, curB, mb);
-					} else {
-						slots.load(d.b_idx, x);
-						matvec_smem(MB, x, mb);
-						if (SCALE) sf_in += sfslot[d.b_idx * NUC4_NT + tid];
+						matvec_smem(MB, out, mb);
+						if (SCALE) sf_in = sf_acc;
+						if (kind == 1) {
+							tip_message(MA, cds[a_idx * PB], ma);
+						} else {
+							double x[4];
+							cell_load(slot_cell + a_idx * NUC4_SLOT_BYTES, x);
+							matvec_smem(MA, x, ma);
+							if (SCALE) sf_in += sfslot[a_idx * NUC4_NT + tid];
+						}
 					}
 #pragma unroll
 					for (int i = 0; i < 4; i++) out[i] = ma[i] * mb[i];
@@ -255,10 +283,10 @@ __global__ void __launch_bounds__(NUC4_NT, 2) k_nuc4_walk(const Nuc4Params prm) 
 							sf = log(m);
 						}
 						sf_acc = sf + sf_in;
-						sfslot[d.dst_slot * NUC4_NT + tid] = sf_acc;
+						if (dst_slot >= 0) sfslot[dst_slot * NUC4_NT + tid] = sf_acc;
 					}
-					slots.store(d.dst_slot, out);
-					if (GRAD) store_lower(my_lower + (((size_t)(first + j) * C + c) * PB + pl) * 4, out);
+					if (dst_slot >= 0) cell_store(slot_cell + dst_slot * NUC4_SLOT_BYTES, out);  // parked for a later kind-2 op
+					if (GRAD) row_store(row_cell + (size_t)(unsigned)(first + j) * NUC4_ROW_BYTES, out);
 				}
 				loads++;
 				__syncthreads();  // everyone is done with this stage before it is refilled
@@ -277,7 +305,7 @@ __global__ void __launch_bounds__(NUC4_NT, 2) k_nuc4_walk(const Nuc4Params prm) 
 				for (int cc = 1; cc < C; cc++) L += xch[cc * PB + pl];
 				double plk = log(L);
 				if (SCALE) plk += sf_acc;
-				const double w = live ? prm.weights[pc] : 0.0;
+				const double w = live ? prm.weights[p] : 0.0;
 				if (live) prm.pattern_lnl[p] = plk;
 				invLw[pl] = w / L;  // unscaled path: w_k / L_k; scaled paths use ratios instead
 				double v = live ? plk * w : 0.0;
@@ -290,133 +318,145 @@ __global__ void __launch_bounds__(NUC4_NT, 2) k_nuc4_walk(const Nuc4Params prm) 
 		// ------------------------------------------------------------------ pre-order + gradients
 		if (GRAD) {
 			const double sgrad = invLw[pl];
-			const double wk = live ? prm.weights[pc] : 0.0;
+			const double wk = live ? prm.weights[p] : 0.0;
 			const int nchunks = (prm.n_pre + NUC4_CHUNK - 1) / NUC4_CHUNK;
-			auto issue = [&](int ch, uint32_t ld) {
+			auto issue = [&](int ch, uint32_t ld, int tips) {
 				const int first = ch * NUC4_CHUNK;
 				const int cnt = min(NUC4_CHUNK, prm.n_pre - first);
-				unsigned char *dst = stage0 + (ld & 1) * stage_bytes;
+				unsigned char *dst = stage0 + (ld & 1) * lay.bytes;
 				const uint32_t dbytes = cnt * (uint32_t)sizeof(phbc_pre_op), mbytes = cnt * 3 * C * 128;
-				mbar_expect_tx(&bars[ld & 1], dbytes + mbytes);
-				bulk_g2s(dst, prm.pre_ops + first, dbytes, &bars[ld & 1]);
-				bulk_g2s(dst + NUC4_CHUNK * 48, prm.pre_mats + (size_t)first * 3 * C * 16, mbytes, &bars[ld & 1]);
+				const uint32_t cbytes = (tips & 31) * PB;
+				mbar_expect_tx(&bars[ld & 1], dbytes + mbytes + cbytes);
+				bulk_g2s(dst + lay.desc_off, prm.pre_ops + first, dbytes, &bars[ld & 1]);
+				bulk_g2s(dst + lay.mat_off, prm.pre_mats + (size_t)first * 3 * C * 16, mbytes, &bars[ld & 1]);
+				if (cbytes) bulk_g2s(dst + lay.code_off, tile_codes_pre + (size_t)(tips >> 5) * PB, cbytes, &bars[ld & 1]);
 			};
-			if (tid == 0) issue(0, loads);
+			// lower rows of the internal children of one op (kind: 0 tip-tip, 1 tip-internal, 2 internal-internal)
+			auto fetch = [&](const phbc_pre_op *d, double (&A)[4], double (&B)[4]) {
+				const int kind = d->kind;
+				if (kind == 2) row_load(row_cell + (size_t)(unsigned)d->a_row * NUC4_ROW_BYTES, A);
+				if (kind != 0) row_load(row_cell + (size_t)(unsigned)d->b_row * NUC4_ROW_BYTES, B);
+			};
+			// One op. Operands (lower rows of the children) are in xa / xb; as soon as they have been consumed the
+			// same registers receive the NEXT op's rows, a full op ahead of their use.  Returns the two gradient terms.
+			auto pre_op = [&](const phbc_pre_op *desc, const unsigned char *mats, const uint8_t *cds, int j, int cnt, bool more_chunks,
+			                  double (&xa)[4], double (&xb)[4], double (&ureg)[4], double &va, double &vb) {
+				const phbc_pre_op *d = desc + j;
+				const int kind = d->kind;
+				const double *MP = reinterpret_cast<const double *>(mats + (j * 3 + 0) * C * 128);
+				const double *MA = reinterpret_cast<const double *>(mats + (j * 3 + 1) * C * 128);
+				const double *MB = reinterpret_cast<const double *>(mats + (j * 3 + 2) * C * 128);
+				double W[4], ma[4], mb[4];
+				if (kind == 2) matvec_smem(MA, xa, ma);
+				else tip_message(MA, cds[d->a_code * PB], ma);
+				if (kind == 0) tip_message(MB, cds[d->b_code * PB], mb);
+				else matvec_smem(MB, xb, mb);
+				// xa / xb are dead: prefetch the next op's rows into them (across the chunk boundary too)
+				if (j + 1 < cnt) {
+					fetch(d + 1, xa, xb);
+				} else if (more_chunks) {
+					mbar_wait(&bars[(loads + 1) & 1], ((loads + 1) >> 1) & 1);
+					fetch(reinterpret_cast<const phbc_pre_op *>(stage0 + ((loads + 1) & 1) * lay.bytes + lay.desc_off), xa, xb);
+				}
+				if (d->u_kind == PHBC_W_ROOT) {
+					// children of the root: u = P_s L_s [o pi] (treelikelihood.c:2145-2154)
+#pragma unroll
+					for (int i = 0; i < 4; i++) W[i] = prm.wroot[i];
+				} else {
+					if (d->u_kind == PHBC_W_SLOT) cell_load(slot_cell + d->u_slot * NUC4_SLOT_BYTES, ureg);  // else: left by the preceding op
+					matvec_smem(MP, ureg, W);  // P_p u_p
+				}
+				double ua[4], ub[4];
+#pragma unroll
+				for (int i = 0; i < 4; i++) ua[i] = W[i] * mb[i], ub[i] = W[i] * ma[i];
+				// numerators: sum_i f_i u_n[i] (dP_n L_n)[i] with dP_n L_n = Q (P_n L_n)
+				double na = 0.0, nb = 0.0, da = 0.0, db = 0.0;
+#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					const double qa = fma(prm.Q[4 * i], ma[0], fma(prm.Q[4 * i + 1], ma[1], fma(prm.Q[4 * i + 2], ma[2], prm.Q[4 * i + 3] * ma[3])));
+					const double qb = fma(prm.Q[4 * i], mb[0], fma(prm.Q[4 * i + 1], mb[1], fma(prm.Q[4 * i + 2], mb[2], prm.Q[4 * i + 3] * mb[3])));
+					const double fa = prm.fq[i] * ua[i], fb = prm.fq[i] * ub[i];
+					na = fma(fa, qa, na);
+					nb = fma(fb, qb, nb);
+					if (SCALE) {
+						da = fma(fa, ma[i], da);
+						db = fma(fb, mb[i], db);
+					}
+				}
+				if (!SCALE) {
+					va = na * sgrad;
+					vb = nb * sgrad;
+				} else {
+					// rescale the upper partials like the reference (their scale cancels in the ratios below)
+					double *plane = xch;  // 4 planes: max_a, max_b, den_a, den_b
+					__syncthreads();      // previous op's readers are done
+					plane[0 * C * PB + c * PB + pl] = fmax(fmax(ua[0], ua[1]), fmax(ua[2], ua[3]));
+					plane[1 * C * PB + c * PB + pl] = fmax(fmax(ub[0], ub[1]), fmax(ub[2], ub[3]));
+					plane[2 * C * PB + c * PB + pl] = da * prop_c;
+					plane[3 * C * PB + c * PB + pl] = db * prop_c;
+					__syncthreads();
+					double mxa = 0.0, mxb = 0.0, dta = 0.0, dtb = 0.0;
+					for (int cc = 0; cc < C; cc++) {
+						mxa = fmax(mxa, plane[0 * C * PB + cc * PB + pl]);
+						mxb = fmax(mxb, plane[1 * C * PB + cc * PB + pl]);
+						dta += plane[2 * C * PB + cc * PB + pl];
+						dtb += plane[3 * C * PB + cc * PB + pl];
+					}
+					if (mxa < prm.threshold) {
+#pragma unroll
+						for (int i = 0; i < 4; i++) ua[i] /= mxa;
+					}
+					if (mxb < prm.threshold) {
+#pragma unroll
+						for (int i = 0; i < 4; i++) ub[i] /= mxb;
+					}
+					// exact: one site denominator shared by the categories; compat: per-category ratio
+					// (gradient_cat_branch_lengths_aux, treelikelihood.c:2721-2738)
+					va = prm.compat ? na / da * wk : na / dta * wk;
+					vb = prm.compat ? nb / db * wk : nb / dtb * wk;
+				}
+				if (kind == 2) cell_store(slot_cell + d->a_slot * NUC4_SLOT_BYTES, ua);  // parked until its own op comes up
+				if (kind != 0) {
+#pragma unroll
+					for (int i = 0; i < 4; i++) ureg[i] = ub[i];  // child b's op is the next one
+				}
+			};
+			if (tid == 0) issue(0, loads, prm.pre_first_tips);
+			mbar_wait(&bars[loads & 1], (loads >> 1) & 1);
+			double xa[4] = {0, 0, 0, 0}, xb[4] = {0, 0, 0, 0}, ureg[4] = {0, 0, 0, 0};
+			fetch(reinterpret_cast<const phbc_pre_op *>(stage0 + (loads & 1) * lay.bytes + lay.desc_off), xa, xb);
 			for (int ch = 0; ch < nchunks; ch++) {
-				if (tid == 0 && ch + 1 < nchunks) issue(ch + 1, loads + 1);
-				mbar_wait(&bars[loads & 1], (loads >> 1) & 1);
-				const unsigned char *st = stage0 + (loads & 1) * stage_bytes;
-				const phbc_pre_op *desc = reinterpret_cast<const phbc_pre_op *>(st);
-				const double *mats = reinterpret_cast<const double *>(st + NUC4_CHUNK * 48);
+				const unsigned char *st = stage0 + (loads & 1) * lay.bytes;
+				const phbc_pre_op *desc = reinterpret_cast<const phbc_pre_op *>(st + lay.desc_off);
+				if (tid == 0 && ch + 1 < nchunks) issue(ch + 1, loads + 1, desc[0].next_tips);
+				const unsigned char *mats = st + my_mat;
+				const uint8_t *cds = st + my_code;
 				const int first = ch * NUC4_CHUNK;
 				const int cnt = min(NUC4_CHUNK, prm.n_pre - first);
-				// operands of the first op of the chunk
-				double La[4], Lb[4];
-				unsigned codeA = 0, codeB = 0;
-				auto fetch = [&](const phbc_pre_op &d, double (&A)[4], double (&B)[4], unsigned &ca, unsigned &cb) {
-					if (d.a_tip) ca = codes[(size_t)d.a_node * prm.P];
-					else load_lower(my_lower + (((size_t)d.a_row * C + c) * PB + pl) * 4, A);
-					if (d.b_tip) cb = codes[(size_t)d.b_node * prm.P];
-					else load_lower(my_lower + (((size_t)d.b_row * C + c) * PB + pl) * 4, B);
-				};
-				fetch(desc[0], La, Lb, codeA, codeB);
-				for (int j = 0; j < cnt; j++) {
-					const phbc_pre_op d = desc[j];
-					double xa[4], xb[4];
-#pragma unroll
-					for (int i = 0; i < 4; i++) xa[i] = La[i], xb[i] = Lb[i];
-					const unsigned curA = codeA, curB = codeB;
-					if (j + 1 < cnt) fetch(desc[j + 1], La, Lb, codeA, codeB);  // prefetch next operands
-					const double *MP = mats + ((size_t)(j * 3 + 0) * C + c) * 16;
-					const double *MA = mats + ((size_t)(j * 3 + 1) * C + c) * 16;
-					const double *MB = mats + ((size_t)(j * 3 + 2) * C + c) * 16;
-					double W[4], ma[4], mb[4];
-					if (d.u_kind == PHBC_W_ROOT) {
-						// children of the root: u = P_s L_s [o pi] (treelikelihood.c:2145-2154)
-#pragma unroll
-						for (int i = 0; i < 4; i++) W[i] = prm.include_root_freqs ? prm.freqs[i] : 1.0;
+				const bool more = ch + 1 < nchunks;
+#pragma unroll 1
+				for (int j = 0; j < cnt; j += 2) {
+					// two ops (four branches) share one warp butterfly; partial sums go to warp-private rows
+					double v0, v1, v2 = 0.0, v3 = 0.0;
+					pre_op(desc, mats, cds, j, cnt, more, xa, xb, ureg, v0, v1);
+					if (j + 1 < cnt) {
+						pre_op(desc, mats, cds, j + 1, cnt, more, xa, xb, ureg, v2, v3);
+						const double r = butterfly4(v0, v1, v2, v3, lane);
+						if ((lane & 7) == 0) {
+							const phbc_pre_op *d = desc + j + ((lane >> 3) & 1);
+							red_add_f64(my_gacc + ((lane & 16) ? d->b_node : d->a_node), r);
+						}
 					} else {
-						double up[4];
-						slots.load(d.u_slot, up);
-						matvec_smem(MP, up, W);  // P_p u_p
+						const double r = butterfly2(v0, v1, lane);
+						if ((lane & 15) == 0) red_add_f64(my_gacc + ((lane & 16) ? desc[j].b_node : desc[j].a_node), r);
 					}
-					if (d.a_tip) tip_message(MA, curA, ma);
-					else matvec_smem(MA, xa, ma);
-					if (d.b_tip) tip_message(MB, curB, mb);
-					else matvec_smem(MB, xb, mb);
-					double ua[4], ub[4];
-#pragma unroll
-					for (int i = 0; i < 4; i++) ua[i] = W[i] * mb[i], ub[i] = W[i] * ma[i];
-					// numerators: sum_i f_i u_n[i] (dP_n L_n)[i] with dP_n L_n = Q (P_n L_n)
-					double na = 0.0, nb = 0.0, da = 0.0, db = 0.0;
-#pragma unroll
-					for (int i = 0; i < 4; i++) {
-						const double f = prm.include_root_freqs ? 1.0 : prm.freqs[i];
-						const double qa = fma(prm.Q[4 * i], ma[0], fma(prm.Q[4 * i + 1], ma[1], fma(prm.Q[4 * i + 2], ma[2], prm.Q[4 * i + 3] * ma[3])));
-						const double qb = fma(prm.Q[4 * i], mb[0], fma(prm.Q[4 * i + 1], mb[1], fma(prm.Q[4 * i + 2], mb[2], prm.Q[4 * i + 3] * mb[3])));
-						na = fma(f * ua[i], qa, na);
-						nb = fma(f * ub[i], qb, nb);
-						if (SCALE) {
-							da = fma(f * ua[i], ma[i], da);
-							db = fma(f * ub[i], mb[i], db);
-						}
-					}
-					double va, vb;
-					if (!SCALE) {
-						va = na * sgrad;
-						vb = nb * sgrad;
-					} else {
-						// rescale the upper partials like the reference (their scale cancels in the ratios below)
-						double *plane = xch;  // 4 planes: max_a, max_b, den_a, den_b
-						__syncthreads();      // previous op's readers are done
-						plane[0 * C * PB + c * PB + pl] = fmax(fmax(ua[0], ua[1]), fmax(ua[2], ua[3]));
-						plane[1 * C * PB + c * PB + pl] = fmax(fmax(ub[0], ub[1]), fmax(ub[2], ub[3]));
-						plane[2 * C * PB + c * PB + pl] = da * prop_c;
-						plane[3 * C * PB + c * PB + pl] = db * prop_c;
-						__syncthreads();
-						double mxa = 0.0, mxb = 0.0, dta = 0.0, dtb = 0.0;
-						for (int cc = 0; cc < C; cc++) {
-							mxa = fmax(mxa, plane[0 * C * PB + cc * PB + pl]);
-							mxb = fmax(mxb, plane[1 * C * PB + cc * PB + pl]);
-							dta += plane[2 * C * PB + cc * PB + pl];
-							dtb += plane[3 * C * PB + cc * PB + pl];
-						}
-						if (mxa < prm.threshold) {
-#pragma unroll
-							for (int i = 0; i < 4; i++) ua[i] /= mxa;
-						}
-						if (mxb < prm.threshold) {
-#pragma unroll
-							for (int i = 0; i < 4; i++) ub[i] /= mxb;
-						}
-						// exact: one site denominator shared by the categories; compat: per-category ratio
-						// (gradient_cat_branch_lengths_aux, treelikelihood.c:2721-2738)
-						va = prm.compat ? na / da * wk : na / dta * wk;
-						vb = prm.compat ? nb / db * wk : nb / dtb * wk;
-					}
-					if (d.a_slot >= 0) slots.store(d.a_slot, ua);
-					if (d.b_slot >= 0) slots.store(d.b_slot, ub);
-					// paired butterfly: lanes 0-15 end with branch a, lanes 16-31 with branch b
-					const bool hi = lane & 16;
-					double r = (hi ? vb : va) + __shfl_xor_sync(0xffffffffu, hi ? va : vb, 16);
-					r += __shfl_xor_sync(0xffffffffu, r, 8);
-					r += __shfl_xor_sync(0xffffffffu, r, 4);
-					r += __shfl_xor_sync(0xffffffffu, r, 2);
-					r += __shfl_xor_sync(0xffffffffu, r, 1);
-					if (lane == 0) red_add_f64(my_gacc + d.a_node, r);
-					if (lane == 16) red_add_f64(my_gacc + d.b_node, r);
 				}
 				loads++;
 				__syncthreads();
 			}
 		}
 	}
-	if (c == 0 && lane == 0) {
-		// one partial lnL per category-0 warp
-		prm.cta_lnl[(size_t)blockIdx.x * (NUC4_NT / 32) + warp] = cta_lnl;
-	} else if (lane == 0) {
-		prm.cta_lnl[(size_t)blockIdx.x * (NUC4_NT / 32) + warp] = 0.0;
-	}
+	if (lane == 0) prm.cta_lnl[(size_t)blockIdx.x * (NUC4_NT / 32) + warp] = (c == 0) ? cta_lnl : 0.0;  // one partial lnL per warp
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -465,44 +505,74 @@ __global__ void k_nuc4_matrices(int C, int root, int n_post, int n_pre, const ph
 		}
 }
 
-// tip encodings -> 5-bit codes.  states: s < 4 -> 1 << s, else 0x10 (missing).  partials: bit j set when
-// partial[j] == 1; anything that is not a 0/1 vector raises *bad (the fused path then declines).
-__global__ void k_nuc4_encode_states(size_t n, const uint8_t *__restrict__ states, uint8_t *__restrict__ codes) {
+// tip encodings -> codes (see tip_message), laid out [walk][tile][k][PB] with row k = the k-th tip the walk consumes.
+// states: s < 4 -> s, else 4 (missing).  partials: one-hot -> state, else 0x10 | mask with bit j set when partial[j] == 1;
+// anything that is not a 0/1 vector raises *bad (the fused path then declines).  Padding patterns get code 4.
+__global__ void k_nuc4_encode_tips(int T, int P, int PB, int ntiles, int tip_kind, const uint8_t *__restrict__ states,
+                                   const double *__restrict__ partials, const int *__restrict__ post_order,
+                                   const int *__restrict__ pre_order, uint8_t *__restrict__ codes, int *__restrict__ bad) {
+	const size_t per_walk = (size_t)ntiles * T * PB;
 	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	const unsigned s = states[i];
-	codes[i] = s < 4 ? (uint8_t)(1u << s) : (uint8_t)0x10;
-}
-__global__ void k_nuc4_encode_partials(size_t n, const double *__restrict__ partials, uint8_t *__restrict__ codes, int *__restrict__ bad) {
-	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	unsigned code = 0;
-	for (int j = 0; j < 4; j++) {
-		const double v = partials[i * 4 + j];
-		if (v == 1.0) code |= 1u << j;
-		else if (v != 0.0) *bad = 1;
+	if (i >= 2 * per_walk) return;
+	const int walk = i >= per_walk;
+	const size_t r = i - walk * per_walk;
+	const int pl = (int)(r % PB);
+	const int k = (int)((r / PB) % T);
+	const int tile = (int)(r / ((size_t)PB * T));
+	const int p = tile * PB + pl;
+	const int tip = walk ? pre_order[k] : post_order[k];
+	unsigned code = 4;
+	if (p < P) {
+		if (tip_kind == PHBC_TIP_STATES) {
+			const unsigned s = states[(size_t)tip * P + p];
+			code = s < 4 ? s : 4;
+		} else {
+			unsigned mask = 0;
+			for (int j = 0; j < 4; j++) {
+				const double v = partials[((size_t)tip * P + p) * 4 + j];
+				if (v == 1.0) mask |= 1u << j;
+				else if (v != 0.0) *bad = 1;
+			}
+			// one-hot vectors become plain states; anything else keeps its mask (row sums for all-ones, treelikelihood4.c:1019-1025)
+			code = __popc(mask) == 1 ? (unsigned)(__ffs(mask) - 1) : (0x10u | mask);
+		}
 	}
 	codes[i] = (uint8_t)code;
 }
 
-// fixed-order final sums: lnL and cat_grad[n][c] from the per-CTA / per-warp partials
+// fixed-order final sums: lnL and cat_grad[n][c] from the per-CTA / per-warp partials.
+// grid (ceil(N/32), C), block (32, 8): x = node, y strides over the CTAs of the walk launch.
 __global__ void k_nuc4_finalize(int N, int C, int PB, int grid, int root, const double *__restrict__ cta_lnl,
                                 const double *__restrict__ gacc, int want_grad, double *__restrict__ cat_grad,
                                 double *__restrict__ result) {
-	const int e = blockIdx.x * blockDim.x + threadIdx.x;
+	__shared__ double red[8][33];
 	const int warps = NUC4_NT / 32, wpc = PB / 32;
-	if (e == 0) {
+	const int tx = threadIdx.x, ty = threadIdx.y;
+	if (blockIdx.x == 0 && blockIdx.y == 0) {
 		double s = 0.0;
-		for (int i = 0; i < grid * warps; i++) s += cta_lnl[i];
-		result[0] = s;
+		for (int i = ty * 32 + tx; i < grid * warps; i += 256) s += cta_lnl[i];
+		s = phb_warp_sum(s);
+		if (tx == 0) red[ty][32] = s;
+		__syncthreads();
+		if (tx == 0 && ty == 0) {
+			double tot = 0.0;
+			for (int k = 0; k < 8; k++) tot += red[k][32];
+			result[0] = tot;
+		}
 	}
-	if (!want_grad || e >= N * C) return;
-	const int c = e / N, n = e % N;  // consecutive threads -> consecutive nodes (coalesced rows)
+	if (!want_grad) return;
+	const int n = blockIdx.x * 32 + tx, c = blockIdx.y;
 	double s = 0.0;
-	if (n != root)
-		for (int b = 0; b < grid; b++)
+	if (n < N && n != root)
+		for (int b = ty; b < grid; b += 8)
 			for (int w = 0; w < wpc; w++) s += gacc[((size_t)b * warps + c * wpc + w) * N + n];
-	cat_grad[(size_t)n * C + c] = s;
+	red[ty][tx] = s;
+	__syncthreads();
+	if (ty == 0 && n < N) {
+		double tot = 0.0;
+		for (int k = 0; k < 8; k++) tot += red[k][tx];
+		cat_grad[(size_t)n * C + c] = tot;
+	}
 }
 
 __global__ void k_collapse_categories_nuc4(int N, int C, const double *__restrict__ cat_grad, const double *__restrict__ props,
@@ -523,7 +593,7 @@ __global__ void k_collapse_categories_nuc4(int N, int C, const double *__restric
 // host side
 // ---------------------------------------------------------------------------------------------
 static size_t nuc4_smem_bytes(int C, int PB, int nslots, bool scale) {
-	return 128 + 2 * (size_t)NUC4_CHUNK * (48 + 3 * C * 128) + (size_t)nslots * 2 * NUC4_NT * 16 +
+	return 128 + 2 * (size_t)nuc4_stage_layout(C, PB).bytes + (size_t)nslots * NUC4_SLOT_BYTES +
 	       (size_t)(4 * C * PB + PB + (scale ? nslots * NUC4_NT : 0)) * sizeof(double);
 }
 
@@ -534,9 +604,8 @@ static int pattern_block(int C) {
 
 bool phbc_nuc4_supported(const phbc_ctx *ctx, const phbc_eval_opts *o) {
 	if (ctx->S != 4 || o->explicit_matrices || !ctx->have_eigen) return false;
-	if (ctx->C > NUC4_NT / 32) return false;
+	if (ctx->C != 1 && ctx->C != 2 && ctx->C != 4 && ctx->C != 8) return false;  // categories must tile the CTA exactly
 	const int PB = pattern_block(ctx->C);
-	if (PB < 32 || PB * ctx->C != NUC4_NT) return false;  // categories must tile the CTA exactly
 	const int nslots = ctx->post_slots > ctx->pre_slots ? ctx->post_slots : ctx->pre_slots;
 	if (nuc4_smem_bytes(ctx->C, PB, nslots, o->scale != 0) > ctx->smem_optin) return false;
 	return true;
@@ -550,18 +619,17 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	const int nslots = ctx->post_slots > ctx->pre_slots ? ctx->post_slots : ctx->pre_slots;
 	const size_t smem = nuc4_smem_bytes(C, PB, nslots, o->scale != 0);
 	const int ntiles = (P + PB - 1) / PB;
-	// tip codes (once per tip upload)
+	// tip codes in walk order (once per tip upload / schedule change)
 	if (!ctx->d_nuc4_codes) {
-		PHBC_CHECK(cudaMalloc((void **)&ctx->d_nuc4_codes, (size_t)T * P));
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_nuc4_codes, 2 * (size_t)ntiles * T * PB));
 		PHBC_CHECK(cudaMalloc((void **)&ctx->d_nuc4_bad, sizeof(int)));
 	}
 	if (!ctx->nuc4_codes_valid) {
-		const size_t n = (size_t)T * P;
+		const size_t n = 2 * (size_t)ntiles * T * PB;
 		PHBC_CHECK(cudaMemsetAsync(ctx->d_nuc4_bad, 0, sizeof(int), ctx->stream));
-		if (ctx->tip_kind == PHBC_TIP_STATES)
-			k_nuc4_encode_states<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->d_tip_states, ctx->d_nuc4_codes);
-		else
-			k_nuc4_encode_partials<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->d_tip_partials, ctx->d_nuc4_codes, ctx->d_nuc4_bad);
+		k_nuc4_encode_tips<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(T, P, PB, ntiles, ctx->tip_kind, ctx->d_tip_states, ctx->d_tip_partials,
+		                                                                       ctx->d_post_tip_order, ctx->d_pre_tip_order, ctx->d_nuc4_codes,
+		                                                                       ctx->d_nuc4_bad);
 		ctx->launches++;
 		int bad = 0;
 		PHBC_CHECK(cudaMemcpyAsync(&bad, ctx->d_nuc4_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -572,8 +640,15 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	if (ctx->nuc4_codes_bad) return phbc_generic_evaluate(ctx, o);  // non 0/1 tip partials: node-at-a-time kernels
 
 	// launch geometry: persistent CTAs, two per SM when shared memory allows
-	auto kern = o->scale ? (o->want_gradient ? k_nuc4_walk<true, true> : k_nuc4_walk<true, false>)
-	                     : (o->want_gradient ? k_nuc4_walk<false, true> : k_nuc4_walk<false, false>);
+	typedef void (*walk_fn)(const Nuc4Params);
+	static const walk_fn table[4][2][2] = {
+	    {{k_nuc4_walk<1, false, false>, k_nuc4_walk<1, false, true>}, {k_nuc4_walk<1, true, false>, k_nuc4_walk<1, true, true>}},
+	    {{k_nuc4_walk<2, false, false>, k_nuc4_walk<2, false, true>}, {k_nuc4_walk<2, true, false>, k_nuc4_walk<2, true, true>}},
+	    {{k_nuc4_walk<4, false, false>, k_nuc4_walk<4, false, true>}, {k_nuc4_walk<4, true, false>, k_nuc4_walk<4, true, true>}},
+	    {{k_nuc4_walk<8, false, false>, k_nuc4_walk<8, false, true>}, {k_nuc4_walk<8, true, false>, k_nuc4_walk<8, true, true>}},
+	};
+	const int ci = C == 1 ? 0 : (C == 2 ? 1 : (C == 4 ? 2 : 3));
+	walk_fn kern = table[ci][o->scale ? 1 : 0][o->want_gradient ? 1 : 0];
 	PHBC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;
 	PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NUC4_NT, smem));
@@ -594,7 +669,7 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		ctx->walk_mats_bytes = mats_bytes;
 	}
 	if (o->want_gradient) {
-		const size_t lower_bytes = (size_t)grid * ctx->n_post * C * PB * 4 * sizeof(double);
+		const size_t lower_bytes = (size_t)grid * ctx->n_post * NUC4_ROW_BYTES;
 		if (lower_bytes > ctx->walk_lower_bytes) {
 			PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 			if (ctx->d_walk_lower) cudaFree(ctx->d_walk_lower);
@@ -633,6 +708,7 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	prm.T = T, prm.N = N, prm.C = C, prm.P = P, prm.PB = PB, prm.root = ctx->root;
 	prm.n_post = ctx->n_post, prm.n_pre = ctx->n_pre, prm.nslots = nslots, prm.ntiles = ntiles;
 	prm.include_root_freqs = o->include_root_freqs, prm.compat = o->compat_scaled_gradient;
+	prm.post_first_tips = ctx->post_first_tips, prm.pre_first_tips = ctx->pre_first_tips;
 	prm.threshold = o->scaling_threshold;
 	prm.tip_codes = ctx->d_nuc4_codes;
 	prm.weights = ctx->d_weights;
@@ -647,13 +723,17 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	prm.pattern_lnl = ctx->d_pattern_lnl;
 	memcpy(prm.freqs, ctx->h_freqs, sizeof(prm.freqs));  // small model constants travel in the kernel parameter bank
 	memcpy(prm.Q, ctx->h_qmat, sizeof(prm.Q));
+	for (int i = 0; i < 4; i++) {
+		prm.fq[i] = o->include_root_freqs ? 1.0 : ctx->h_freqs[i];
+		prm.wroot[i] = o->include_root_freqs ? ctx->h_freqs[i] : 1.0;
+	}
 	int trc;
 	if ((trc = phbc_time_begin(ctx))) return trc;
 	kern<<<grid, NUC4_NT, smem, ctx->stream>>>(prm);
 	ctx->launches++;
 	if ((trc = phbc_time_end(ctx))) return trc;
 	double *result = ctx->d_result + (size_t)o->batch_index * (1 + N);
-	k_nuc4_finalize<<<(N * C + 127) / 128, 128, 0, ctx->stream>>>(N, C, PB, grid, ctx->root, ctx->d_nuc4_cta_lnl, ctx->d_walk_gacc,
+	k_nuc4_finalize<<<dim3((N + 31) / 32, C), dim3(32, 8), 0, ctx->stream>>>(N, C, PB, grid, ctx->root, ctx->d_nuc4_cta_lnl, ctx->d_walk_gacc,
 	                                                             o->want_gradient, ctx->d_cat_grad, result);
 	ctx->launches++;
 	if (o->want_gradient) {

@@ -53,6 +53,8 @@ struct phb_tlk {
 	phbc_post_op *post_ops;
 	phbc_pre_op *pre_ops;
 	int n_lower_levels, n_upper_levels, post_slots, pre_slots;
+	int *post_tip_order, *pre_tip_order, *post_chunk_tip0, *pre_chunk_tip0;
+	int post_first_tips, pre_first_tips;
 };
 
 static _Thread_local char g_err[512] = "";
@@ -231,7 +233,21 @@ static int slot_alloc(SlotPool *p) {
 	return -1;
 }
 
-/* whole-tree walks for the fused kernels */
+/*
+ * Whole-tree walks for the fused kernels.
+ *
+ * Post-order: children commute in the product, so every op is normalised to one of three kinds
+ *   0 tip-tip        (a tip, b tip)
+ *   1 tip-internal   (a tip, b = the result of the IMMEDIATELY preceding op, still in registers)
+ *   2 internal-int.  (a = an earlier result parked in a slot, b = the preceding op's result)
+ * A result is parked in a shared-memory slot only when it is the first-visited child of a kind-2 parent;
+ * visiting the child with the larger register need first keeps the number of live slots at the tree's
+ * Strahler number.
+ *
+ * Pre-order over internal nodes (each op turns U_parent into U for both children and their branch
+ * gradients): same three kinds; child b (when internal) is the node whose op comes NEXT, so its U stays in
+ * registers; child a of a kind-2 op is parked in a slot until its own op comes up.
+ */
 static int build_walk_schedules(phb_tlk *t) {
 	const int N = t->N, T = t->T;
 	const int nint = N - T;
@@ -239,6 +255,8 @@ static int build_walk_schedules(phb_tlk *t) {
 	int *size = (int *)malloc(sizeof(int) * N);
 	int *slot_of = (int *)malloc(sizeof(int) * N);
 	int *row_of = (int *)malloc(sizeof(int) * N);
+	int *parked = (int *)calloc(N, sizeof(int));
+	int *pneed = (int *)calloc(N, sizeof(int));
 	int *stack = (int *)malloc(sizeof(int) * (6 * (size_t)N + 8));
 	SlotPool pool;
 	pool.cap = N + 1;
@@ -246,11 +264,11 @@ static int build_walk_schedules(phb_tlk *t) {
 	pool.high = 0;
 	t->post_ops = (phbc_post_op *)malloc(sizeof(phbc_post_op) * (nint > 0 ? nint : 1));
 	t->pre_ops = (phbc_pre_op *)malloc(sizeof(phbc_pre_op) * (nint > 0 ? nint : 1));
-	if (!need || !size || !slot_of || !row_of || !stack || !pool.used || !t->post_ops || !t->pre_ops) return PHB_ENOMEM;
+	if (!need || !size || !slot_of || !row_of || !parked || !pneed || !stack || !pool.used || !t->post_ops || !t->pre_ops) return PHB_ENOMEM;
 	compute_need(t, need, size);
 
-	/* post-order: visit the child with the larger need first so that at most need[root] results are live */
-	int sp = 0, nops = 0;
+	/* ---- post-order: emit ops (larger-need child first), then assign slots in program order ---- */
+	int sp = 0, nops = 0, prev = -1;
 	stack[sp++] = t->root;
 	stack[sp++] = 0;
 	while (sp) {
@@ -268,89 +286,105 @@ static int build_walk_schedules(phb_tlk *t) {
 			stack[sp++] = first;
 			stack[sp++] = 0;
 		} else {
-			phbc_post_op *op = &t->post_ops[nops++];
+			phbc_post_op *op = &t->post_ops[nops];
+			if (!is_tip(t, a) && is_tip(t, b)) { /* a tip child comes first */
+				int tmp = a; a = b; b = tmp;
+			}
+			if (!is_tip(t, a) && !is_tip(t, b) && a == prev) { /* the just-computed child is operand b */
+				int tmp = a; a = b; b = tmp;
+			}
+			if (!is_tip(t, b) && b != prev) {
+				free(need); free(size); free(slot_of); free(row_of); free(parked); free(pneed); free(stack); free(pool.used);
+				return fail(PHB_EINVAL, "post-order walk: child %d of node %d was not computed by the preceding op", b, n);
+			}
 			op->node = n;
 			op->a_node = a;
 			op->b_node = b;
 			op->a_kind = is_tip(t, a) ? PHBC_W_TIP : PHBC_W_SLOT;
-			op->b_kind = is_tip(t, b) ? PHBC_W_TIP : PHBC_W_SLOT;
-			op->a_idx = is_tip(t, a) ? a : slot_of[a];
-			op->b_idx = is_tip(t, b) ? b : slot_of[b];
-			/* slots are thread-private in the kernel: operands may be released before the result is placed */
-			if (!is_tip(t, a)) pool.used[slot_of[a]] = 0;
-			if (!is_tip(t, b)) pool.used[slot_of[b]] = 0;
-			op->dst_slot = slot_alloc(&pool);
-			op->pad = 0;
-			slot_of[n] = op->dst_slot;
-			row_of[n] = nops - 1;
+			op->b_kind = is_tip(t, b) ? PHBC_W_TIP : PHBC_W_SLOT; /* SLOT here means "registers of the previous op" */
+			op->a_idx = op->b_idx = -1;
+			op->dst_slot = -1;
+			op->next_tips = 0;
+			if (op->a_kind == PHBC_W_SLOT) parked[a] = 1;
+			row_of[n] = nops;
+			prev = n;
+			nops++;
 		}
 	}
-	t->post_slots = pool.high;
+	for (int k = 0; k < nops; k++) {
+		phbc_post_op *op = &t->post_ops[k];
+		if (op->a_kind == PHBC_W_SLOT) {
+			op->a_idx = slot_of[op->a_node];
+			pool.used[slot_of[op->a_node]] = 0; /* slots are thread-private: release before placing the result */
+		}
+		if (parked[op->node]) slot_of[op->node] = op->dst_slot = slot_alloc(&pool);
+	}
+	t->post_slots = pool.high > 0 ? pool.high : 1;
 
-	/* pre-order over internal nodes: the parent's op yields U for both children; descend first into the
-	 * child whose subtree needs fewer slots, the other one waits in its slot */
+	/* ---- pre-order ---- */
 	memset(pool.used, 0, pool.cap);
 	pool.high = 0;
-	/* need over the tree of INTERNAL nodes only */
-	int *pneed = (int *)calloc(N, sizeof(int));
-	{
-		/* process nodes children-before-parents using the post-order op list */
-		for (int k = 0; k < nops; k++) {
-			int n = t->post_ops[k].node;
-			int a = t->left[n], b = t->right[n];
-			int ia = !is_tip(t, a), ib = !is_tip(t, b);
-			if (!ia && !ib) pneed[n] = 1;
-			else if (ia && !ib) pneed[n] = pneed[a] > 1 ? pneed[a] : 1;
-			else if (!ia && ib) pneed[n] = pneed[b] > 1 ? pneed[b] : 1;
-			else {
-				int lo = pneed[a] < pneed[b] ? pneed[a] : pneed[b];
-				int hi = pneed[a] < pneed[b] ? pneed[b] : pneed[a];
-				pneed[n] = lo + 1 > hi ? lo + 1 : hi;
-			}
+	for (int k = 0; k < nops; k++) { /* register need over the tree of INTERNAL nodes, children before parents */
+		int n = t->post_ops[k].node;
+		int a = t->left[n], b = t->right[n];
+		int ia = !is_tip(t, a), ib = !is_tip(t, b);
+		if (!ia && !ib) pneed[n] = 0;
+		else if (ia && !ib) pneed[n] = pneed[a];
+		else if (!ia && ib) pneed[n] = pneed[b];
+		else {
+			int lo = pneed[a] < pneed[b] ? pneed[a] : pneed[b];
+			int hi = pneed[a] < pneed[b] ? pneed[b] : pneed[a];
+			pneed[n] = lo + 1 > hi ? lo + 1 : hi;
 		}
 	}
 	int npre = 0;
 	sp = 0;
+	prev = -1;
 	stack[sp++] = t->root;
 	while (sp) {
 		int n = stack[--sp];
 		int a = t->left[n], b = t->right[n];
+		if (!is_tip(t, a) && is_tip(t, b)) { /* a tip child comes first */
+			int tmp = a; a = b; b = tmp;
+		}
+		if (!is_tip(t, a) && !is_tip(t, b) && pneed[a] < pneed[b]) { /* b = visited next = the smaller need */
+			int tmp = a; a = b; b = tmp;
+		}
 		phbc_pre_op *op = &t->pre_ops[npre++];
+		const int a_tip = is_tip(t, a), b_tip = is_tip(t, b);
 		op->node = n;
 		op->a_node = a;
 		op->b_node = b;
-		op->a_tip = (int16_t)is_tip(t, a);
-		op->b_tip = (int16_t)is_tip(t, b);
+		op->kind = (int16_t)((a_tip ? 0 : 1) + (b_tip ? 0 : 1));
+		op->next_tips = 0;
+		op->u_slot = -1;
 		if (n == t->root) {
 			op->u_kind = PHBC_W_ROOT;
-			op->u_slot = -1;
+		} else if (n == prev) {
+			op->u_kind = PHBC_W_REG; /* U_n is still in the registers of the preceding op */
 		} else {
 			op->u_kind = PHBC_W_SLOT;
 			op->u_slot = slot_of[n];
-			pool.used[slot_of[n]] = 0; /* consumed by this op */
+			pool.used[slot_of[n]] = 0;
 		}
 		op->a_slot = op->b_slot = -1;
-		op->pad0 = 0;
-		op->pad1 = op->pad2 = 0;
-		op->a_row = op->a_tip ? -1 : row_of[a];
-		op->b_row = op->b_tip ? -1 : row_of[b];
-		if (!op->a_tip) slot_of[a] = op->a_slot = slot_alloc(&pool);
-		if (!op->b_tip) slot_of[b] = op->b_slot = slot_alloc(&pool);
-		/* push so that the smaller-need internal child is popped first */
-		if (!op->a_tip && !op->b_tip) {
-			int first = pneed[a] <= pneed[b] ? a : b;
-			int second = first == a ? b : a;
-			stack[sp++] = second;
-			stack[sp++] = first;
-		} else if (!op->a_tip) {
-			stack[sp++] = a;
-		} else if (!op->b_tip) {
+		op->a_code = op->b_code = -1;
+		op->a_row = a_tip ? -1 : row_of[a];
+		op->b_row = b_tip ? -1 : row_of[b];
+		if (op->kind == 2) {
+			slot_of[a] = op->a_slot = slot_alloc(&pool);
+			stack[sp++] = a; /* parked, popped after b's whole subtree */
+		}
+		if (op->kind >= 1) {
 			stack[sp++] = b;
+			prev = b;
+		} else {
+			prev = -1;
 		}
 	}
 	t->pre_slots = pool.high > 0 ? pool.high : 1;
-	if (t->post_slots < 1) t->post_slots = 1;
 	free(pneed);
+	free(parked);
 	free(need);
 	free(size);
 	free(slot_of);
@@ -358,6 +392,50 @@ static int build_walk_schedules(phb_tlk *t) {
 	free(stack);
 	free(pool.used);
 	if (nops != nint || npre != nint) return fail(PHB_EINVAL, "walk schedule covers %d/%d of %d internal nodes", nops, npre, nint);
+
+	/* number the tip operands in walk order and make the descriptors' tip indices local to their chunk */
+	const int nch = (nint + PHBC_WALK_CHUNK - 1) / PHBC_WALK_CHUNK;
+	t->post_tip_order = (int *)malloc(sizeof(int) * T);
+	t->pre_tip_order = (int *)malloc(sizeof(int) * T);
+	t->post_chunk_tip0 = (int *)calloc(nch + 2, sizeof(int));
+	t->pre_chunk_tip0 = (int *)calloc(nch + 2, sizeof(int));
+	if (!t->post_tip_order || !t->pre_tip_order || !t->post_chunk_tip0 || !t->pre_chunk_tip0) return PHB_ENOMEM;
+	int k = 0, q = 0;
+	for (int i = 0; i < nint; i++) {
+		if (i % PHBC_WALK_CHUNK == 0) {
+			t->post_chunk_tip0[i / PHBC_WALK_CHUNK] = k;
+			t->pre_chunk_tip0[i / PHBC_WALK_CHUNK] = q;
+		}
+		phbc_post_op *po = &t->post_ops[i];
+		if (po->a_kind == PHBC_W_TIP) {
+			t->post_tip_order[k] = po->a_node;
+			po->a_idx = k++ - t->post_chunk_tip0[i / PHBC_WALK_CHUNK];
+		}
+		if (po->b_kind == PHBC_W_TIP) {
+			t->post_tip_order[k] = po->b_node;
+			po->b_idx = k++ - t->post_chunk_tip0[i / PHBC_WALK_CHUNK];
+		}
+		phbc_pre_op *qo = &t->pre_ops[i];
+		if (qo->kind != 2) { /* child a is a tip */
+			t->pre_tip_order[q] = qo->a_node;
+			qo->a_code = q++ - t->pre_chunk_tip0[i / PHBC_WALK_CHUNK];
+		}
+		if (qo->kind == 0) {
+			t->pre_tip_order[q] = qo->b_node;
+			qo->b_code = q++ - t->pre_chunk_tip0[i / PHBC_WALK_CHUNK];
+		}
+	}
+	t->post_chunk_tip0[nch] = k;
+	t->pre_chunk_tip0[nch] = q;
+	if (k != T || q != T) return fail(PHB_EINVAL, "walk schedule consumes %d/%d of %d tips", k, q, T);
+	/* the first op of chunk ch announces the tip range of chunk ch + 1 (the kernel issues that load while it works on ch) */
+	for (int ch = 0; ch + 1 < nch; ch++) {
+		const int i = ch * PHBC_WALK_CHUNK;
+		t->post_ops[i].next_tips = (t->post_chunk_tip0[ch + 1] << 5) | (t->post_chunk_tip0[ch + 2] - t->post_chunk_tip0[ch + 1]);
+		t->pre_ops[i].next_tips = (t->pre_chunk_tip0[ch + 1] << 5) | (t->pre_chunk_tip0[ch + 2] - t->pre_chunk_tip0[ch + 1]);
+	}
+	t->post_first_tips = nch > 0 ? t->post_chunk_tip0[1] : 0;
+	t->pre_first_tips = nch > 0 ? t->pre_chunk_tip0[1] : 0;
 	return PHB_OK;
 }
 
@@ -452,6 +530,10 @@ phb_tlk *phb_tlk_create(int ntips, int nstate, int ncat, int npatterns, const in
 	s.pre_ops = t->pre_ops;
 	s.post_slots = t->post_slots;
 	s.pre_slots = t->pre_slots;
+	s.post_tip_order = t->post_tip_order;
+	s.pre_tip_order = t->pre_tip_order;
+	s.post_first_tips = t->post_first_tips;
+	s.pre_first_tips = t->pre_first_tips;
 	if ((rc = phbc_set_schedule(t->ctx, &s))) {
 		dev_fail(rc);
 		phb_tlk_free(t);
@@ -475,6 +557,10 @@ void phb_tlk_free(phb_tlk *t) {
 	free(t->upper_level_off);
 	free(t->post_ops);
 	free(t->pre_ops);
+	free(t->post_tip_order);
+	free(t->pre_tip_order);
+	free(t->post_chunk_tip0);
+	free(t->pre_chunk_tip0);
 	free(t);
 }
 
