@@ -31,8 +31,9 @@ struct phbc_ctx {
 	double *d_upper;         // [N][C][P][S]   (lazy)
 	double *d_sf;            // [2N][P]        (lazy)
 	phbc_op *d_lower_ops, *d_upper_ops;
-	int n_lower_ops, n_upper_ops;
-	int *h_lower_level_off, *h_upper_level_off;
+	phbc_parent_op *d_parent_ops;
+	int n_lower_ops, n_upper_ops, n_parent_ops;
+	int *h_lower_level_off, *h_upper_level_off, *h_parent_level_off;
 	int n_lower_levels, n_upper_levels;
 
 	// fused walk state (phb_nuc4.cu)
@@ -89,6 +90,24 @@ int phbc_ensure_scratch(phbc_ctx *ctx, size_t bytes);
 
 // generic node-at-a-time path (phb_cuda.cu)
 int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
+// pieces of it shared with the tensor-core path (same buffers, same schedules)
+struct Bufs {
+	const uint8_t *tip_states;
+	const double *tip_partials;
+	double *lower;
+	double *upper;
+	double *sf;
+	int T, N, S, C, P, tip_kind;
+};
+Bufs phbc_make_bufs(phbc_ctx *ctx);
+int phbc_generic_prepare(phbc_ctx *ctx, const phbc_eval_opts *o);                       // buffers + transition matrices
+int phbc_generic_scale_ops(phbc_ctx *ctx, const phbc_op *d_ops, int count, double threshold);  // K5 on one level
+int phbc_generic_root(phbc_ctx *ctx, const phbc_eval_opts *o, double *result);           // K6, K7 -> result[0]
+int phbc_generic_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, double *result);       // K9, K10, A11 from materialised uppers
+int phbc_gradient_from_partials(phbc_ctx *ctx, int tiles, double *result);               // cat_grad = sum of [N][C][tiles] scratch, A11
+// FP64 tensor-core path, 20 / 61 states (phb_dmma.cu)
+int phbc_dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
+bool phbc_dmma_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);
 // fused 4-state walk path (phb_nuc4.cu)
 int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
 bool phbc_nuc4_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);

@@ -95,7 +95,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
 	void *bufs[] = {ctx->d_tip_states, ctx->d_tip_partials, ctx->d_weights, ctx->d_evec, ctx->d_eval, ctx->d_ivec, ctx->d_qmat,
 	                ctx->d_freqs, ctx->d_rates, ctx->d_props, ctx->d_bl, ctx->d_P, ctx->d_dP, ctx->d_lower, ctx->d_upper,
-	                ctx->d_sf, ctx->d_lower_ops, ctx->d_upper_ops, ctx->d_post_ops, ctx->d_pre_ops, ctx->d_walk_mats,
+	                ctx->d_sf, ctx->d_lower_ops, ctx->d_upper_ops, ctx->d_parent_ops, ctx->d_post_ops, ctx->d_pre_ops, ctx->d_walk_mats,
 	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch,
 	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl, ctx->d_post_tip_order, ctx->d_pre_tip_order};
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
@@ -113,6 +113,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	free(ctx->h_qmat);
 	free(ctx->h_lower_level_off);
 	free(ctx->h_upper_level_off);
+	free(ctx->h_parent_level_off);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	free(ctx);
 }
@@ -146,6 +147,8 @@ extern "C" int phbc_set_schedule(phbc_ctx *ctx, const phbc_schedule *s) {
 	int rc;
 	if ((rc = upload_array(ctx, &ctx->d_lower_ops, s->lower_ops, (size_t)s->n_lower_ops))) return rc;
 	if ((rc = upload_array(ctx, &ctx->d_upper_ops, s->upper_ops, (size_t)s->n_upper_ops))) return rc;
+	if ((rc = upload_array(ctx, &ctx->d_parent_ops, s->parent_ops, (size_t)s->n_parent_ops))) return rc;
+	ctx->n_parent_ops = s->n_parent_ops;
 	if ((rc = upload_array(ctx, &ctx->d_post_ops, s->post_ops, (size_t)s->n_post))) return rc;
 	if ((rc = upload_array(ctx, &ctx->d_pre_ops, s->pre_ops, (size_t)s->n_pre))) return rc;
 	if ((rc = upload_array(ctx, &ctx->d_post_tip_order, s->post_tip_order, (size_t)ctx->T))) return rc;
@@ -167,6 +170,9 @@ extern "C" int phbc_set_schedule(phbc_ctx *ctx, const phbc_schedule *s) {
 	ctx->h_upper_level_off = (int *)malloc(sizeof(int) * (s->n_upper_levels + 1));
 	memcpy(ctx->h_lower_level_off, s->lower_level_off, sizeof(int) * (s->n_lower_levels + 1));
 	memcpy(ctx->h_upper_level_off, s->upper_level_off, sizeof(int) * (s->n_upper_levels + 1));
+	free(ctx->h_parent_level_off);
+	ctx->h_parent_level_off = (int *)malloc(sizeof(int) * (s->n_upper_levels + 1));
+	memcpy(ctx->h_parent_level_off, s->parent_level_off, sizeof(int) * (s->n_upper_levels + 1));
 	return 0;
 }
 
@@ -310,15 +316,6 @@ __global__ void k_transition_matrices(int S, int C, int root, const double *__re
 // ---------------------------------------------------------------------------------------------
 // generic kernels
 // ---------------------------------------------------------------------------------------------
-
-struct Bufs {
-	const uint8_t *tip_states;
-	const double *tip_partials;
-	double *lower;
-	double *upper;
-	double *sf;
-	int T, N, S, C, P, tip_kind;
-};
 
 __device__ __forceinline__ const double *partial_ptr(const Bufs &b, int idx, int c) {
 	const size_t PS = (size_t)b.P * b.S;
@@ -535,7 +532,7 @@ __global__ void k_collapse_categories(int N, int C, const double *__restrict__ c
 	result[1 + n] = g;
 }
 
-static Bufs make_bufs(phbc_ctx *ctx) {
+Bufs phbc_make_bufs(phbc_ctx *ctx) {
 	Bufs b;
 	b.tip_states = ctx->d_tip_states;
 	b.tip_partials = ctx->d_tip_partials;
@@ -551,7 +548,7 @@ static Bufs make_bufs(phbc_ctx *ctx) {
 	return b;
 }
 
-int phbc_launch_transition_matrices(phbc_ctx *ctx, int batch_index) {
+static int phbc_launch_transition_matrices(phbc_ctx *ctx, int batch_index) {
 	int rc = ensure_node_matrices(ctx);
 	if (rc) return rc;
 	const int S = ctx->S;
@@ -565,13 +562,10 @@ int phbc_launch_transition_matrices(phbc_ctx *ctx, int batch_index) {
 	return 0;
 }
 
-int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
+// buffers of the node-at-a-time paths (lazy) and the per-node transition matrices
+int phbc_generic_prepare(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));
 	const size_t S = ctx->S, C = ctx->C, P = ctx->P, N = ctx->N, T = ctx->T;
-	if (C > GEN_MAXC) {
-		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "generic kernels support at most %d rate categories", GEN_MAXC);
-		return -1;
-	}
 	const size_t psize = C * P * S;
 	if (!ctx->d_lower) PHBC_CHECK(cudaMalloc((void **)&ctx->d_lower, (N - T) * psize * sizeof(double)));
 	if (o->want_gradient && !ctx->d_upper) PHBC_CHECK(cudaMalloc((void **)&ctx->d_upper, N * psize * sizeof(double)));
@@ -579,23 +573,84 @@ int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		PHBC_CHECK(cudaMalloc((void **)&ctx->d_sf, 2 * N * P * sizeof(double)));
 		PHBC_CHECK(cudaMemsetAsync(ctx->d_sf, 0, 2 * N * P * sizeof(double), ctx->stream));
 	}
-	int rc;
 	if (!o->explicit_matrices) {
 		if (!ctx->have_eigen) {
 			snprintf(phbc_errbuf, sizeof(phbc_errbuf), "no eigen system and no explicit matrices set");
 			return -4;
 		}
-		if ((rc = phbc_launch_transition_matrices(ctx, o->batch_index))) return rc;
-	} else if (!ctx->d_P) {
+		return phbc_launch_transition_matrices(ctx, o->batch_index);
+	}
+	if (!ctx->d_P) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "explicit matrices requested but not uploaded");
 		return -4;
 	}
-	Bufs b = make_bufs(ctx);
-	const size_t smem = 2 * S * S * sizeof(double);
-	if (smem > 48 * 1024) {
-		PHBC_CHECK(cudaFuncSetAttribute(k_generic_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		PHBC_CHECK(cudaFuncSetAttribute(k_generic_branch_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	return 0;
+}
+
+int phbc_generic_scale_ops(phbc_ctx *ctx, const phbc_op *d_ops, int count, double threshold) {
+	Bufs b = phbc_make_bufs(ctx);
+	for (int z0 = 0; z0 < count; z0 += 65535) {
+		const int zc = count - z0 < 65535 ? count - z0 : 65535;
+		k_generic_scale<<<dim3((unsigned)((ctx->P + 127) / 128), zc), 128, 0, ctx->stream>>>(b, d_ops + z0, threshold);
+		ctx->launches++;
 	}
+	PHBC_CHECK(cudaGetLastError());
+	return 0;
+}
+
+int phbc_generic_root(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
+	Bufs b = phbc_make_bufs(ctx);
+	const int rblocks = (ctx->P + 255) / 256;
+	int rc;
+	if ((rc = phbc_ensure_scratch(ctx, rblocks * sizeof(double)))) return rc;
+	k_generic_root<<<rblocks, 256, 0, ctx->stream>>>(b, ctx->root, ctx->d_freqs, ctx->d_props, ctx->d_weights, o->scale,
+	                                                  ctx->d_pattern_lnl, ctx->d_scratch);
+	k_sum_blocks<<<1, 256, 0, ctx->stream>>>(ctx->d_scratch, rblocks, result);
+	ctx->launches += 2;
+	PHBC_CHECK(cudaGetLastError());
+	return 0;
+}
+
+int phbc_gradient_from_partials(phbc_ctx *ctx, int tiles, double *result) {
+	const int N = ctx->N, C = ctx->C;
+	k_generic_gradient_reduce<<<(unsigned)((N * C + 127) / 128), 128, 0, ctx->stream>>>(N, C, ctx->root, tiles, ctx->d_scratch, ctx->d_cat_grad);
+	k_collapse_categories<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>(N, C, ctx->d_cat_grad, ctx->d_props, ctx->d_rates, result);
+	ctx->launches += 2;
+	PHBC_CHECK(cudaGetLastError());
+	return 0;
+}
+
+int phbc_generic_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
+	Bufs b = phbc_make_bufs(ctx);
+	const size_t S = ctx->S, C = ctx->C, P = ctx->P, N = ctx->N;
+	const size_t smem = 2 * S * S * sizeof(double);
+	if (smem > 48 * 1024) PHBC_CHECK(cudaFuncSetAttribute(k_generic_branch_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	const size_t gtiles = (P + GEN_PGRAD - 1) / GEN_PGRAD;
+	int rc;
+	if ((rc = phbc_ensure_scratch(ctx, N * C * gtiles * sizeof(double)))) return rc;
+	if (N - 1 > 65535) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "generic gradient kernel supports at most 65535 branches");
+		return -1;
+	}
+	// blockIdx.y enumerates the non-root nodes
+	k_generic_branch_gradient<<<dim3((unsigned)gtiles, (unsigned)(N - 1)), GEN_PGRAD, smem, ctx->stream>>>(
+	    b, ctx->root, ctx->d_P, ctx->d_dP, ctx->d_freqs, ctx->d_props, ctx->d_weights, ctx->d_pattern_lnl, o->scale,
+	    o->compat_scaled_gradient, o->include_root_freqs, ctx->d_scratch);
+	ctx->launches++;
+	return phbc_gradient_from_partials(ctx, (int)gtiles, result);
+}
+
+int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
+	const size_t S = ctx->S, C = ctx->C, P = ctx->P, N = ctx->N;
+	if (C > GEN_MAXC) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "generic kernels support at most %d rate categories", GEN_MAXC);
+		return -1;
+	}
+	int rc;
+	if ((rc = phbc_generic_prepare(ctx, o))) return rc;
+	Bufs b = phbc_make_bufs(ctx);
+	const size_t smem = 2 * S * S * sizeof(double);
+	if (smem > 48 * 1024) PHBC_CHECK(cudaFuncSetAttribute(k_generic_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	const int ptiles = (int)((P + GEN_PBLK - 1) / GEN_PBLK);
 	if ((rc = phbc_time_begin(ctx))) return rc;
 	// post-order, one launch per level
@@ -606,56 +661,25 @@ int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 			const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
 			k_generic_combine<<<dim3(ptiles, (unsigned)C, zc), 128, smem, ctx->stream>>>(b, ctx->d_lower_ops + beg + z0, ctx->d_P, ctx->d_freqs);
 			ctx->launches++;
-			if (o->scale) {
-				k_generic_scale<<<dim3((unsigned)((P + 127) / 128), zc), 128, 0, ctx->stream>>>(b, ctx->d_lower_ops + beg + z0, o->scaling_threshold);
-				ctx->launches++;
-			}
 		}
+		if (o->scale && (rc = phbc_generic_scale_ops(ctx, ctx->d_lower_ops + beg, cnt, o->scaling_threshold))) return rc;
 	}
-	// root
-	const int rblocks = (int)((P + 255) / 256);
-	const size_t gtiles = (P + GEN_PGRAD - 1) / GEN_PGRAD;
-	size_t need = rblocks * sizeof(double);
-	if (o->want_gradient && N * C * gtiles * sizeof(double) > need) need = N * C * gtiles * sizeof(double);
-	if ((rc = phbc_ensure_scratch(ctx, need))) return rc;
 	double *result = ctx->d_result + (size_t)o->batch_index * (1 + N);
-	k_generic_root<<<rblocks, 256, 0, ctx->stream>>>(b, ctx->root, ctx->d_freqs, ctx->d_props, ctx->d_weights, o->scale,
-	                                                  ctx->d_pattern_lnl, ctx->d_scratch);
-	k_sum_blocks<<<1, 256, 0, ctx->stream>>>(ctx->d_scratch, rblocks, result);
-	ctx->launches += 2;
+	if ((rc = phbc_generic_root(ctx, o, result))) return rc;
 	if (o->want_gradient) {
 		for (int l = 0; l < ctx->n_upper_levels; l++) {
 			const int beg = ctx->h_upper_level_off[l], cnt = ctx->h_upper_level_off[l + 1] - beg;
 			if (cnt <= 0) continue;
 			for (int z0 = 0; z0 < cnt; z0 += 65535) {
 				const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
-				// the include_root_freqs flag travels in op.flags, set by the host per evaluation option
+				// op.flags bit 0 asks for the root frequencies; they are applied only under include_root_freqs
 				k_generic_combine<<<dim3(ptiles, (unsigned)C, zc), 128, smem, ctx->stream>>>(b, ctx->d_upper_ops + beg + z0, ctx->d_P,
 				                                                                           o->include_root_freqs ? ctx->d_freqs : NULL);
 				ctx->launches++;
-				if (o->scale) {
-					k_generic_scale<<<dim3((unsigned)((P + 127) / 128), zc), 128, 0, ctx->stream>>>(b, ctx->d_upper_ops + beg + z0, o->scaling_threshold);
-					ctx->launches++;
-				}
 			}
+			if (o->scale && (rc = phbc_generic_scale_ops(ctx, ctx->d_upper_ops + beg, cnt, o->scaling_threshold))) return rc;
 		}
-		for (int y0 = 0; y0 < (int)N - 1; y0 += 65535) {
-			// blockIdx.y enumerates non-root nodes; chunks keep gridDim.y within limits
-			const int yc = (int)N - 1 - y0 < 65535 ? (int)N - 1 - y0 : 65535;
-			if (y0 != 0) {
-				snprintf(phbc_errbuf, sizeof(phbc_errbuf), "generic gradient kernel supports at most 65535 branches");
-				return -1;
-			}
-			k_generic_branch_gradient<<<dim3((unsigned)gtiles, yc), GEN_PGRAD, smem, ctx->stream>>>(
-			    b, ctx->root, ctx->d_P, ctx->d_dP, ctx->d_freqs, ctx->d_props, ctx->d_weights, ctx->d_pattern_lnl, o->scale,
-			    o->compat_scaled_gradient, o->include_root_freqs, ctx->d_scratch);
-			ctx->launches++;
-		}
-		k_generic_gradient_reduce<<<(unsigned)((N * C + 127) / 128), 128, 0, ctx->stream>>>((int)N, (int)C, ctx->root, (int)gtiles,
-		                                                                                 ctx->d_scratch, ctx->d_cat_grad);
-		k_collapse_categories<<<(unsigned)((N + 127) / 128), 128, 0, ctx->stream>>>((int)N, (int)C, ctx->d_cat_grad, ctx->d_props,
-		                                                                          ctx->d_rates, result);
-		ctx->launches += 2;
+		if ((rc = phbc_generic_gradient(ctx, o, result))) return rc;
 	}
 	if ((rc = phbc_time_end(ctx))) return rc;
 	PHBC_CHECK(cudaGetLastError());
@@ -668,6 +692,7 @@ extern "C" int phbc_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		return -1;
 	}
 	if (o->kernels != 1 /* PHB_KERNELS_GENERIC */ && phbc_nuc4_supported(ctx, o)) return phbc_nuc4_evaluate(ctx, o);
+	if (o->kernels != 1 /* PHB_KERNELS_GENERIC */ && phbc_dmma_supported(ctx, o)) return phbc_dmma_evaluate(ctx, o);
 	if (o->kernels == 2 /* PHB_KERNELS_FUSED */) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "fused kernels not available for this configuration (S=%d)", ctx->S);
 		return -1;

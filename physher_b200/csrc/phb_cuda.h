@@ -64,6 +64,13 @@ typedef struct phbc_pre_op { /* one internal node acting as parent, DFS pre-orde
 	int a_code, b_code;      /* chunk-local index of a tip child's code row                       */
 } phbc_pre_op;
 
+/* One pre-order op of the tensor-core kernels: internal node `node` with children a, b.  The kernel turns
+ * U_node (or the root message) into U_a, U_b and both branch-gradient terms.  Grouped by depth of `node`. */
+typedef struct phbc_parent_op {
+	int node, a, b;
+	int flags; /* bit 0: node is the root */
+} phbc_parent_op;
+
 typedef struct phbc_schedule {
 	int n_lower_ops, n_lower_levels;
 	const phbc_op *lower_ops;   /* grouped by level, children before parents                      */
@@ -71,6 +78,9 @@ typedef struct phbc_schedule {
 	int n_upper_ops, n_upper_levels;
 	const phbc_op *upper_ops;   /* grouped by depth, parents before children                      */
 	const int *upper_level_off;
+	int n_parent_ops;                 /* internal nodes grouped by their own depth (root first)  */
+	const phbc_parent_op *parent_ops;
+	const int *parent_level_off;      /* [n_upper_levels + 1]: level d = parents at depth d       */
 	int n_post, n_pre;
 	const phbc_post_op *post_ops;
 	const phbc_pre_op *pre_ops;

@@ -49,7 +49,8 @@ struct phb_tlk {
 
 	/* schedules (host copies kept for introspection) */
 	phbc_op *lower_ops, *upper_ops;
-	int *lower_level_off, *upper_level_off;
+	phbc_parent_op *parent_ops;
+	int *lower_level_off, *upper_level_off, *parent_level_off;
 	phbc_post_op *post_ops;
 	phbc_pre_op *pre_ops;
 	int n_lower_levels, n_upper_levels, post_slots, pre_slots;
@@ -177,6 +178,23 @@ static int build_level_schedules(phb_tlk *t) {
 			op->b_mat = -1;
 			op->flags = 1;
 		}
+	}
+	free(fill);
+	/* parent ops: internal nodes grouped by their own depth 0..maxdepth-1 (their children sit one level deeper) */
+	t->parent_level_off = (int *)calloc(maxdepth + 2, sizeof(int));
+	t->parent_ops = (phbc_parent_op *)malloc(sizeof(phbc_parent_op) * (N - T > 0 ? N - T : 1));
+	for (int n = 0; n < N; n++)
+		if (!is_tip(t, n)) t->parent_level_off[depth[n] + 1]++;
+	for (int d = 0; d < maxdepth; d++) t->parent_level_off[d + 1] += t->parent_level_off[d];
+	fill = (int *)calloc(maxdepth + 1, sizeof(int));
+	for (int n = 0; n < N; n++) {
+		if (is_tip(t, n)) continue;
+		const int d = depth[n];
+		phbc_parent_op *op = &t->parent_ops[t->parent_level_off[d] + fill[d]++];
+		op->node = n;
+		op->a = t->left[n];
+		op->b = t->right[n];
+		op->flags = n == t->root ? 1 : 0;
 	}
 	free(fill);
 	free(level);
@@ -524,6 +542,9 @@ phb_tlk *phb_tlk_create(int ntips, int nstate, int ncat, int npatterns, const in
 	s.n_upper_levels = t->n_upper_levels;
 	s.upper_ops = t->upper_ops;
 	s.upper_level_off = t->upper_level_off;
+	s.n_parent_ops = N - ntips;
+	s.parent_ops = t->parent_ops;
+	s.parent_level_off = t->parent_level_off;
 	s.n_post = N - ntips;
 	s.n_pre = N - ntips;
 	s.post_ops = t->post_ops;
@@ -555,6 +576,8 @@ void phb_tlk_free(phb_tlk *t) {
 	free(t->upper_ops);
 	free(t->lower_level_off);
 	free(t->upper_level_off);
+	free(t->parent_ops);
+	free(t->parent_level_off);
 	free(t->post_ops);
 	free(t->pre_ops);
 	free(t->post_tip_order);

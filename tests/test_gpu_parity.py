@@ -215,3 +215,80 @@ def test_batched_branch_length_samples():
         assert rel_err(lnl[b], want["lnl"]) < RTOL
         assert grad_err(grad[b], want["grad"]) < RTOL
     tlk.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# FP64 tensor-core path (20 / 61 states): KERNELS_AUTO routes there, KERNELS_GENERIC is the cross-check
+# ---------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("shape", [(24, 1000, 20, 4), (24, 63, 20, 4), (31, 65, 20, 1), (16, 257, 61, 1), (11, 31, 61, 2), (40, 129, 61, 1)])
+def test_tensor_core_path_against_oracle(shape):
+    """Ragged pattern counts around the 32 / 64-pattern tiles, deeper trees, unknown states."""
+    T, P, S, C = shape
+    pb = _synthetic_problem(T, P, S, C, seed=4000 + T + P, unknown=0.03)
+    want = O.evaluate(pb)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=phb.KERNELS_AUTO)
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
+    np.testing.assert_allclose(tlk.pattern_log_likelihoods(), want["pattern_lnl"], rtol=1e-11, atol=0)
+    assert grad_err(tlk.gradient(), want["grad"]) < RTOL
+    cg = tlk.cat_branch_gradient()
+    assert grad_err(cg.ravel(), np.where(np.arange(pb.nnodes)[:, None] == pb.root, 0, want["cat_grad"]).ravel()) < RTOL
+    # the reference's default request folds pi into the root's children (SURVEY 0.4 iii)
+    pb.include_root_freqs = True
+    tlk.set_option(OPT_INCLUDE_ROOT_FREQS, 1)
+    assert grad_err(tlk.gradient(), O.evaluate(pb)["grad"]) < RTOL
+    tlk.close()
+
+
+@pytest.mark.parametrize("S", [20, 61])
+def test_tensor_core_path_tip_partials(S):
+    pb = _synthetic_problem(13, 200, S, 2 if S == 20 else 1, seed=4100 + S, unknown=0.0)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    a, ga = tlk.calculate(), tlk.gradient()
+    tlk.close()
+    pb.use_tip_states = False
+    pb.tip_partials = np.eye(S)[pb.tip_states]
+    pb.tip_partials[3, 5, :] = 1.0  # one fully ambiguous entry
+    pb.tip_partials[7, 9, : S // 2] = 1.0  # and one ambiguity set
+    want = O.evaluate(pb)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), want["grad"]) < RTOL
+    assert abs(want["lnl"] - a) > 0  # the ambiguity really changed the model
+    tlk.close()
+
+
+@pytest.mark.parametrize("S,C", [(20, 4), (61, 1)])
+def test_tensor_core_path_rescaling(S, C):
+    """Deep caterpillar with long branches: partials underflow 1e-40, rescaling really triggers."""
+    T = 90
+    topo = syn.caterpillar_topology(T)
+    pb = _synthetic_problem(T, 70, S, C, seed=4200 + S, topo=topo, unknown=0.0)
+    pb.tip_states = syn.random_patterns(T, 70, S, 0.8, 4201)
+    pb.bl = syn.random_branch_lengths(topo, 4202, 0.6, 1.4)
+    base = O.evaluate(pb)
+    pb.scale = True
+    want = O.evaluate(pb, partials=True)
+    assert (want["scaling"][pb.root] < 0).any()
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
+    g = tlk.gradient()
+    assert grad_err(g, want["grad"]) < RTOL
+    assert grad_err(g, base["grad"]) < 1e-9
+    tlk.set_option(OPT_COMPAT_SCALED_GRADIENT, 1)
+    pb.compat_scaled_gradient = True
+    assert grad_err(tlk.gradient(), O.evaluate(pb)["grad"]) < RTOL
+    tlk.close()
+
+
+def test_tensor_core_path_matches_generic_partials():
+    """Lower and (internal-node) upper partials of the tensor-core path against the node-at-a-time kernels."""
+    pb = _synthetic_problem(10, 100, 20, 2, seed=4300)
+    out = O.evaluate(pb, partials=True)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    tlk.gradient()
+    for n in range(pb.ntips, pb.nnodes):
+        np.testing.assert_allclose(tlk.get_partials(n), out["lower"][n], rtol=1e-11, atol=0)
+        if n != pb.root:
+            np.testing.assert_allclose(tlk.get_partials(pb.nnodes + n), out["upper"][n], rtol=1e-11, atol=1e-300)
+    tlk.close()
