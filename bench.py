@@ -34,9 +34,14 @@ CONFIGS = {
     # name: (taxa, patterns per GPU, states, categories, model)
     "c2": dict(taxa=1000, patterns=100_000, states=4, cats=4, model="GTR+G4", mu=0.04),
     "c2_1m": dict(taxa=1000, patterns=1_000_000, states=4, cats=4, model="GTR+G4", mu=0.04),
-    "c4": dict(taxa=200, patterns=200_000, states=20, cats=4, model="LG-shaped REV20+G4", mu=0.08),
+    "c3": dict(taxa=500, patterns=50_000, states=4, cats=4, model="HKY+G4", mu=0.04),
+    "c4": dict(taxa=200, patterns=200_000, states=20, cats=4, model="LG+G4", mu=0.08),
     "c5": dict(taxa=100, patterns=1_000_000, states=61, cats=1, model="GY94", mu=0.1),
 }
+# FP64 tensor-core throughput measured on this pool's B200 with tools/dmma_peak.cu (profiles/r1_c_dmma_peak.md); nominal 40
+DMMA_PEAK_TFLOPS_FILE = os.path.join(ROOT, "profiles", "dmma_peak.json")
+CODON_BASES = "TCAG"
+CODON_AA = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
 METRIC = "lnL+gradient throughput (site patterns x tree nodes per second)"
 UNIT = "pattern*node/s"
 
@@ -47,10 +52,14 @@ def make_inputs(cfg: dict, rank: int, seed: int = 20261017):
     T, P, S, C = cfg["taxa"], cfg["patterns"], cfg["states"], cfg["cats"]
     topo = syn.random_topology(T, seed)
     bl = syn.random_branch_lengths(topo, seed + 1)
-    if S == 4:
+    if S == 4 and cfg["model"].startswith("HKY"):
+        m = models.hky(3.0, [0.1, 0.2, 0.3, 0.4])
+    elif S == 4:
         m = models.gtr([0.05, 0.3, 0.1, 0.15, 0.3, 0.1], [0.1, 0.2, 0.3, 0.4])
     elif S == 61:
         m = models.gy94(2.5, 0.3)
+    elif S == 20:
+        m = lg_model()
     else:
         m = models.random_reversible(S, seed + 2)
     rates, props = models.discrete_gamma(0.5, C)
@@ -59,6 +68,26 @@ def make_inputs(cfg: dict, rank: int, seed: int = 20261017):
     patterns = syn.simulate_patterns(topo, bl * 0.35, P, S, seed + 100 + rank)
     weights = np.ones(P)
     return topo, bl, m, rates, props, patterns, weights
+
+
+def lg_model():
+    """LG eigen system as the reference's host code produced it (lg.c + eigen.c), stored in the committed golden fixture."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "synth_lg_g4_tipstates.npz"))
+    return models.SubstitutionModel("LG", 20, z["freqs"], z["evec"], z["eval"], z["ivec"])
+
+
+def algorithmic_flops(cfg: dict) -> float:
+    """8 S^2 (T-2) flop per pattern per category (one S x S mat-vec per internal operand)."""
+    T, P, S, C = cfg["taxa"], cfg["patterns"], cfg["states"], cfg["cats"]
+    return 8.0 * S * S * (T - 2) * C * P
+
+
+def dmma_peak():
+    try:
+        d = json.load(open(DMMA_PEAK_TFLOPS_FILE))
+        return float(d["dmma_tflops"]), f"measured (tools/dmma_peak.cu, {d.get('shape', 'm8n8k4')}, profiles/dmma_peak.json)"
+    except Exception:
+        return 40.0, "nominal B200 FP64 tensor (no measured file)"
 
 
 def algorithmic_bytes(cfg: dict) -> float:
@@ -118,6 +147,18 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def measured_traffic(config_name, kernels):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
+    capture of this workload (profiles/traffic.json, written by tools/ncu_summary.py); None when there is no capture."""
+    if config_name is None:
+        return None
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return float(d[f"{config_name}:{kernels}"]["dram_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -147,12 +188,24 @@ def _reference_worker(args):
         S = sub["states"]
         if S == 4:
             seqs = dict(zip(names, syn.sequences_from_patterns(patterns, syn.NUCLEOTIDES)))
-            spec = O.treelikelihood_spec(syn.to_newick(topo, bl, names), seqs,
-                                         O.nucleotide_model_spec("gtr", [0.1, 0.2, 0.3, 0.4], [0.05, 0.3, 0.1, 0.15, 0.3, 0.1]),
-                                         categories=sub["cats"], alpha=0.5, tipstates=False)
+            mspec = (O.nucleotide_model_spec("hky", [0.1, 0.2, 0.3, 0.4], kappa=3.0) if sub["model"].startswith("HKY") else
+                     O.nucleotide_model_spec("gtr", [0.1, 0.2, 0.3, 0.4], [0.05, 0.3, 0.1, 0.15, 0.3, 0.1]))
+            spec = O.treelikelihood_spec(syn.to_newick(topo, bl, names), seqs, mspec, categories=sub["cats"], alpha=0.5, tipstates=False)
             ref = O.Reference(spec)
+        elif S == 20:
+            seqs = dict(zip(names, syn.sequences_from_patterns(patterns, syn.AMINO_ACIDS)))
+            lg = {"id": "sm", "type": "substitutionmodel", "model": "lg", "datatype": "aa",
+                  "frequencies": {"id": "freqs", "type": "Simplex", "values": [float(x) for x in m.freqs]}}
+            spec = O.treelikelihood_spec(syn.to_newick(topo, bl, names), seqs, lg, categories=sub["cats"], alpha=0.5, tipstates=False,
+                                         datatype="aa")
+            ref = O.Reference(spec)
+        elif S == 61:
+            codons = [a + b + c for a in CODON_BASES for b in CODON_BASES for c in CODON_BASES]
+            sense = [c for c, a in zip(codons, CODON_AA) if a != "*"]
+            seqs = {n: "".join(sense[s_] for s_ in row) for n, row in zip(names, patterns)}
+            ref = O.Reference(codon=dict(newick=syn.to_newick(topo, bl, names), sequences=seqs, kappa=2.5, omega=0.3))
         else:
-            raise NotImplementedError("reference arm is wired for the nucleotide headline config")
+            raise NotImplementedError(f"reference arm has no model for {S} states")
         # gradient request as in BASELINE.md §4.3: tree model flag, include_root_freqs = false
         ref.time_gradient(warm, O.FLAG_TREE_MODEL, 0)
         sec = ref.time_gradient(iters, O.FLAG_TREE_MODEL, 0)
@@ -191,7 +244,7 @@ def reference_main(args, cfg):
         return 0
     cores = os.cpu_count() or 1
     cores = min(cores, 32)
-    sample = 1000 * cores  # ~0.3 s per evaluation and core at 1000 taxa
+    sample = sample_per_core(cfg) * cores
     iters = max(1, min(args.steps, 10))
     t0 = time.perf_counter()
     r = run_reference(cfg, cores, sample, iters, warm=min(args.warmup, 1) or 1)
@@ -211,6 +264,11 @@ def reference_main(args, cfg):
     }
     print(json.dumps(line))
     return 0
+
+
+def sample_per_core(cfg) -> int:
+    """Patterns per reference process: a few seconds of CPU work per evaluation at each state count."""
+    return {4: 2000, 20: 1200, 61: 400}.get(cfg["states"], 200)
 
 
 def workload_name(cfg):
@@ -359,7 +417,30 @@ def main():
     kms = kern_ms / max(kern_n, 1)
     achieved = alg / (kms * 1e-3) / 1e9 if kms > 0 else None
     fused = args.kernels != "generic" and S == 4
-    fused_bytes = float(P) * (2 * (T - 1) * C * S * 8 + T)  # what the fused walk must move: lower rows out and back, tips in
+    tensor = args.kernels != "generic" and S in (20, 61)
+    traffic = measured_traffic(args.config if not args.patterns else None, args.kernels)
+    hbm = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+           "traffic": traffic, "peak_source": peak_src, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg}
+    if traffic and kms > 0:
+        hbm["traffic_GBs"] = traffic / (kms * 1e-3) / 1e9
+        hbm["traffic_frac"] = hbm["traffic_GBs"] / peak
+    if fused:
+        fused_bytes = float(P) * (2 * (T - 1) * C * S * 8 + 2 * T)  # what the fused walk must move: lower rows out and back, tip codes twice
+        hbm.update(kernel="k_nuc4_walk<C=%d,scale=0,grad=1>" % C, fused_min_bytes_per_launch=fused_bytes,
+                   note="achieved = SURVEY.md 8d streaming-model bytes / kernel time; the fused walk keeps upper partials on chip, so it moves "
+                        f"~{fused_bytes/1e9:.1f} GB per launch (traffic = ncu dram bytes) and frac can exceed 1; traffic_frac is the real DRAM utilisation")
+        roof = hbm
+    elif tensor:
+        flops = algorithmic_flops(cfg)
+        tpeak, tsrc = dmma_peak()
+        tf = flops / (kms * 1e-3) / 1e12 if kms > 0 else None
+        roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": (tf / tpeak) if tf else None, "traffic": traffic,
+                "peak_source": tsrc, "kernel": "k_dmma_lower + k_dmma_upper (FP64 mma.sync m8n8k4), all levels of one evaluation",
+                "kernel_ms": kms, "algorithmic_flops_per_launch": flops, "hbm": hbm,
+                "note": "launch = the level-batched kernel sequence of one evaluation; S=20 sits at the FP64 ridge so the HBM view is given too"}
+    else:
+        hbm.update(kernel="generic node-at-a-time kernels, all levels of one evaluation")
+        roof = hbm
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -371,25 +452,19 @@ def main():
                 "evals_per_s": 1e3 / e2e_ms},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-                     "traffic": None, "peak_source": peak_src, "kernel": "k_nuc4_walk<scale=0,grad=1>" if fused else "generic node-at-a-time kernels",
-                     "kernel_ms": kms, "algorithmic_bytes_per_launch": alg,
-                     "note": "achieved uses SURVEY.md 8d streaming-model bytes; the fused walk keeps upper partials on chip and moves "
-                             f"~{fused_bytes/1e9:.1f} GB per launch, so frac may exceed 1 (see DESIGN.md)" if fused else "node-at-a-time kernels"},
+        "roofline": roof,
     }
-    if fused and kms > 0:
-        line["roofline"]["fused_traffic_model_GBs"] = fused_bytes / (kms * 1e-3) / 1e9
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             from oracle import oracle as O
 
             if O.reference_available():
                 cores = min(os.cpu_count() or 1, 32)
-                r = run_reference(cfg, cores, 1000 * cores, iters=3)
+                r = run_reference(cfg, cores, sample_per_core(cfg) * cores, iters=3)
                 line["cpu_baseline"] = {
                     "value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference",
                     "sample": f"{cores} single-threaded reference processes x {r['per']} patterns each, 3 lnL+gradient evaluations each "
-                              f"(GTR+G4, {T} taxa, tip partials, SSE on), {r['wall']:.1f} s wall",
+                              f"({cfg['model']}, {T} taxa, tip partials, SSE on), {r['wall']:.1f} s wall",
                     "one_core_value": float(np.mean([p * r['nodes'] / s for s, p in zip(r['sec_per_eval'], r['patterns'])])),
                 }
             else:

@@ -50,12 +50,21 @@ __device__ __forceinline__ const double *dm_partial_ptr(const Bufs &b, int idx, 
 }
 __device__ __forceinline__ bool dm_state_tip(const Bufs &b, int idx) { return idx < b.T && b.tip_kind == PHBC_TIP_STATES; }
 
-// stage one S x S row-major matrix into shared memory as [NP][LD], zero padded; optional row sums (first NP entries of rs)
+// stage one S x S row-major matrix into shared memory, zero padded: as [NP][LD] (B-fragment layout) for operands that are
+// partials, or TRANSPOSED as [S][NP] for state tips so that one tip state selects a contiguous column of M (16-byte gathers);
+// optional row sums (first NP entries of rs)
 template <class Sh>
-__device__ __forceinline__ void stage_matrix(double *dst, const double *__restrict__ src, double *rs) {
-	for (int e = threadIdx.x; e < Sh::MAT; e += blockDim.x) {
-		const int i = e / Sh::LD, j = e - i * Sh::LD;
-		dst[e] = (i < Sh::S && j < Sh::S) ? __ldg(src + i * Sh::S + j) : 0.0;
+__device__ __forceinline__ void stage_matrix(double *dst, const double *__restrict__ src, double *rs, bool transposed) {
+	if (transposed) {
+		for (int e = threadIdx.x; e < Sh::S * Sh::NP; e += blockDim.x) {
+			const int s = e / Sh::NP, i = e - s * Sh::NP;
+			dst[e] = i < Sh::S ? __ldg(src + i * Sh::S + s) : 0.0;
+		}
+	} else {
+		for (int e = threadIdx.x; e < Sh::MAT; e += blockDim.x) {
+			const int i = e / Sh::LD, j = e - i * Sh::LD;
+			dst[e] = (i < Sh::S && j < Sh::S) ? __ldg(src + i * Sh::S + j) : 0.0;
+		}
 	}
 	if (rs) {
 		for (int i = threadIdx.x; i < Sh::NP; i += blockDim.x) {
@@ -115,8 +124,9 @@ __device__ __forceinline__ void tip_gather(const uint8_t *__restrict__ states, c
 		for (int j = 0; j < NTW; j++) {
 			const int i = (n0 + j) * 8 + 2 * q;
 			if (s < Sh::S) {
-				acc[m][j][0] = M[i * Sh::LD + s];
-				acc[m][j][1] = M[(i + 1) * Sh::LD + s];
+				const double2 v = *reinterpret_cast<const double2 *>(M + s * Sh::NP + i);  // transposed staging: M[s][i]
+				acc[m][j][0] = v.x;
+				acc[m][j][1] = v.y;
 			} else {
 				acc[m][j][0] = PROB ? 1.0 : rs[i];
 				acc[m][j][1] = PROB ? 1.0 : rs[i + 1];
@@ -138,33 +148,28 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const p
 	double *mA = sm, *mB = sm + Sh::MAT;
 	const phbc_op op = ops[blockIdx.z];
 	const int c = blockIdx.y;
-	stage_matrix<Sh>(mA, Pm + ((size_t)op.a_mat * b.C + c) * S * S, nullptr);
-	stage_matrix<Sh>(mB, Pm + ((size_t)op.b_mat * b.C + c) * S * S, nullptr);
+	const bool a_tip = dm_state_tip(b, op.a), b_tip = dm_state_tip(b, op.b);
+	stage_matrix<Sh>(mA, Pm + ((size_t)op.a_mat * b.C + c) * S * S, nullptr, a_tip);
+	stage_matrix<Sh>(mB, Pm + ((size_t)op.b_mat * b.C + c) * S * S, nullptr, b_tip);
 	__syncthreads();
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int wm = warp / NSPLIT, n0 = (warp % NSPLIT) * NTW;
 	const int r = lane >> 2, q = lane & 3;
 	constexpr int TP = WM * MT * 8;
 	double *out = (double *)dm_partial_ptr(b, op.out, c);
-	const bool a_tip = dm_state_tip(b, op.a), b_tip = dm_state_tip(b, op.b);
+	const double *xa = dm_partial_ptr(b, op.a, c), *xb = dm_partial_ptr(b, op.b, c);
 	const int ntiles = (b.P + TP - 1) / TP;
 	for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 		const int p0 = tile * TP + wm * MT * 8;
 		double acc[MT][NTW][2], acc2[MT][NTW][2];
-		if (a_tip) {
-			tip_gather<Sh, MT, NTW, true>(b.tip_states + (size_t)op.a * b.P, mA, nullptr, p0, b.P, n0, lane, acc);
-		} else {
-			double a[MT][Sh::KT];
-			load_a<Sh, MT>(dm_partial_ptr(b, op.a, c), p0, b.P, lane, a);
-			gemm<Sh, MT, NTW>(mA, n0, lane, a, acc);
-		}
-		if (b_tip) {
-			tip_gather<Sh, MT, NTW, true>(b.tip_states + (size_t)op.b * b.P, mB, nullptr, p0, b.P, n0, lane, acc2);
-		} else {
-			double a[MT][Sh::KT];
-			load_a<Sh, MT>(dm_partial_ptr(b, op.b, c), p0, b.P, lane, a);
-			gemm<Sh, MT, NTW>(mB, n0, lane, a, acc2);
-		}
+		double fa[MT][Sh::KT], fb[MT][Sh::KT];
+		// every global load of the tile is issued before the first product
+		if (!a_tip) load_a<Sh, MT>(xa, p0, b.P, lane, fa);
+		if (!b_tip) load_a<Sh, MT>(xb, p0, b.P, lane, fb);
+		if (a_tip) tip_gather<Sh, MT, NTW, true>(b.tip_states + (size_t)op.a * b.P, mA, nullptr, p0, b.P, n0, lane, acc);
+		else gemm<Sh, MT, NTW>(mA, n0, lane, fa, acc);
+		if (b_tip) tip_gather<Sh, MT, NTW, true>(b.tip_states + (size_t)op.b * b.P, mB, nullptr, p0, b.P, n0, lane, acc2);
+		else gemm<Sh, MT, NTW>(mB, n0, lane, fb, acc2);
 #pragma unroll
 		for (int m = 0; m < MT; m++) {
 			const int p = p0 + 8 * m + r;
@@ -207,12 +212,13 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 	const phbc_parent_op op = ops[blockIdx.z];
 	const int c = blockIdx.y;
 	const bool is_root = op.flags & 1;
-	if (!is_root) stage_matrix<Sh>(mP, Pm + ((size_t)op.node * b.C + c) * S * S, nullptr);
-	stage_matrix<Sh>(mA, Pm + ((size_t)op.a * b.C + c) * S * S, nullptr);
-	stage_matrix<Sh>(mB, Pm + ((size_t)op.b * b.C + c) * S * S, nullptr);
+	const bool a_tip = dm_state_tip(b, op.a), b_tip = dm_state_tip(b, op.b);
+	if (!is_root) stage_matrix<Sh>(mP, Pm + ((size_t)op.node * b.C + c) * S * S, nullptr, false);
+	stage_matrix<Sh>(mA, Pm + ((size_t)op.a * b.C + c) * S * S, nullptr, a_tip);
+	stage_matrix<Sh>(mB, Pm + ((size_t)op.b * b.C + c) * S * S, nullptr, b_tip);
 	if (GRAD) {
-		stage_matrix<Sh>(dA, dPm + ((size_t)op.a * b.C + c) * S * S, rsA);
-		stage_matrix<Sh>(dB, dPm + ((size_t)op.b * b.C + c) * S * S, rsB);
+		stage_matrix<Sh>(dA, dPm + ((size_t)op.a * b.C + c) * S * S, rsA, a_tip);
+		stage_matrix<Sh>(dB, dPm + ((size_t)op.b * b.C + c) * S * S, rsB, b_tip);
 	}
 	for (int i = threadIdx.x; i < Sh::NP; i += blockDim.x) {
 		const double f = i < S ? freqs[i] : 0.0;
@@ -224,8 +230,9 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 	const int wm = warp / NSPLIT, n0 = (warp % NSPLIT) * NTW;
 	const int r = lane >> 2, q = lane & 3;
 	constexpr int TP = WM * MT * 8;
-	const bool a_tip = dm_state_tip(b, op.a), b_tip = dm_state_tip(b, op.b);
 	const bool a_leaf = op.a < b.T, b_leaf = op.b < b.T;
+	const double *xw = b.upper + ((size_t)op.node * b.C + c) * (size_t)b.P * S;
+	const double *xa = dm_partial_ptr(b, op.a, c), *xb = dm_partial_ptr(b, op.b, c);
 	double *Ua = b.upper + ((size_t)op.a * b.C + c) * (size_t)b.P * S;
 	double *Ub = b.upper + ((size_t)op.b * b.C + c) * (size_t)b.P * S;
 	const int ntiles = (b.P + TP - 1) / TP;
@@ -253,6 +260,11 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 	for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 		const int p0 = tile * TP + wm * MT * 8;
 		double W[MT][NTW][2];
+		double fw[MT][Sh::KT], fa[MT][Sh::KT], fb[MT][Sh::KT];
+		// every global load of the tile is issued before the first product
+		if (!is_root) load_a<Sh, MT>(xw, p0, b.P, lane, fw);
+		if (!b_tip) load_a<Sh, MT>(xb, p0, b.P, lane, fb);
+		if (!a_tip) load_a<Sh, MT>(xa, p0, b.P, lane, fa);
 		if (is_root) {
 #pragma unroll
 			for (int m = 0; m < MT; m++)
@@ -262,9 +274,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 					W[m][j][0] = wroot[i], W[m][j][1] = wroot[i + 1];
 				}
 		} else {
-			double a[MT][Sh::KT];
-			load_a<Sh, MT>(b.upper + ((size_t)op.node * b.C + c) * (size_t)b.P * S, p0, b.P, lane, a);
-			gemm<Sh, MT, NTW>(mP, n0, lane, a, W);
+			gemm<Sh, MT, NTW>(mP, n0, lane, fw, W);
 		}
 		// child b: M_b, D_b  ->  U_a = W o M_b (stored), Y_b = f o W o D_b (kept for g_b = sum Y_b M_a)
 		double X[MT][NTW][2], Y[MT][NTW][2];
@@ -273,10 +283,8 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 			tip_gather<Sh, MT, NTW, true>(st, mB, nullptr, p0, b.P, n0, lane, X);
 			if (GRAD) tip_gather<Sh, MT, NTW, false>(st, dB, rsB, p0, b.P, n0, lane, Y);
 		} else {
-			double a[MT][Sh::KT];
-			load_a<Sh, MT>(dm_partial_ptr(b, op.b, c), p0, b.P, lane, a);
-			gemm<Sh, MT, NTW>(mB, n0, lane, a, X);
-			if (GRAD) gemm<Sh, MT, NTW>(dB, n0, lane, a, Y);
+			gemm<Sh, MT, NTW>(mB, n0, lane, fb, X);
+			if (GRAD) gemm<Sh, MT, NTW>(dB, n0, lane, fb, Y);
 		}
 #pragma unroll
 		for (int m = 0; m < MT; m++)
@@ -294,10 +302,8 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 			tip_gather<Sh, MT, NTW, true>(st, mA, nullptr, p0, b.P, n0, lane, Ma);
 			if (GRAD) tip_gather<Sh, MT, NTW, false>(st, dA, rsA, p0, b.P, n0, lane, Da);
 		} else {
-			double a[MT][Sh::KT];
-			load_a<Sh, MT>(dm_partial_ptr(b, op.a, c), p0, b.P, lane, a);
-			gemm<Sh, MT, NTW>(mA, n0, lane, a, Ma);
-			if (GRAD) gemm<Sh, MT, NTW>(dA, n0, lane, a, Da);
+			gemm<Sh, MT, NTW>(mA, n0, lane, fa, Ma);
+			if (GRAD) gemm<Sh, MT, NTW>(dA, n0, lane, fa, Da);
 		}
 		if (GRAD) {
 #pragma unroll
@@ -345,9 +351,9 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 template <int S>
 struct DmmaConfig;
 template <>
-struct DmmaConfig<20> {  // 128 threads, 64 patterns per tile
+struct DmmaConfig<20> {  // 128 threads; 64 patterns per tile in the lower pass, 32 in the upper pass
 	static constexpr int MT = 2, NSPLIT = 1, WM = 4;
-	static constexpr int UMT = 2, UNSPLIT = 1, UWM = 4;
+	static constexpr int UMT = 1, UNSPLIT = 1, UWM = 4;
 };
 template <>
 struct DmmaConfig<61> {  // 256 threads, 32 patterns per tile, n-tiles split over two warps

@@ -48,20 +48,31 @@ def main():
         lines += ["", "warp stall reasons (warps stalled per issue-active cycle): " +
                   ", ".join(f"{h.split('stalled_')[1].split('_per_')[0]} {v:.2f}" for h, v in stalls[:8]), ""]
     src = ncu_csv(a.rep, "source")
-    if len(src) > 2:
-        h = src[1]
+    # the source page repeats a (kernel title, header, rows...) block per profiled launch
+    c, tot, h, blocks = Counter(), 0, None, []
+    for r in src:
+        if "Instructions Executed" in r and "Source" in r:
+            if h is not None and tot:
+                blocks.append((c, tot))
+            h, c, tot = r, Counter(), 0
+            continue
+        if h is None or len(r) < len(h):
+            continue
         ia, isrc = h.index("Instructions Executed"), h.index("Source")
-        c = Counter()
-        tot = 0
-        for r in src[2:]:
-            t = r[isrc].split()
-            if not t:
-                continue
-            op = (t[1] if t[0].startswith("@") and len(t) > 1 else t[0]).split(".")[0]
+        t = r[isrc].split()
+        if not t:
+            continue
+        op = (t[1] if t[0].startswith("@") and len(t) > 1 else t[0]).split(".")[0]
+        try:
             n = int(r[ia] or 0)
-            c[op] += n
-            tot += n
-        lines += ["SASS instruction mix (executed warp instructions): " + ", ".join(f"{op} {n/tot*100:.1f}%" for op, n in c.most_common(14)), ""]
+        except ValueError:
+            continue
+        c[op] += n
+        tot += n
+    if h is not None and tot:
+        blocks.append((c, tot))
+    for k, (c, tot) in enumerate(blocks):
+        lines += [f"SASS instruction mix, launch {k} (executed warp instructions): " + ", ".join(f"{op} {n/tot*100:.1f}%" for op, n in c.most_common(14)), ""]
     text = "\n".join(lines)
     if a.out:
         open(a.out, "w").write(text + "\n")
