@@ -97,15 +97,45 @@ def algorithmic_bytes(cfg: dict) -> float:
 
 
 class ClockSampler:
-    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle-reason sampling DURING the timed region (B200_PROFILING.md clocks line): NVML polled from a
+    thread every few ms (the timed region of a short run is shorter than one `nvidia-smi -lms` period), with the
+    nvidia-smi loop as the fallback when the NVML binding is missing."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index: int, period_s: float = 0.004):
+        self.index, self.period = index, period_s
+        self.proc, self.lines, self.samples, self.stop = None, [], [], threading.Event()
+        self.nvml = None
+
+    def _nvml_loop(self):
+        n = self.nvml
+        h = n.nvmlDeviceGetHandleByIndex(self.index)
+        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        while not self.stop.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(sm), float(mx), [k for k, b in bits.items() if r & b]))
+            except Exception:
+                pass
+            self.stop.wait(self.period)
 
     def __enter__(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                                           "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -120,6 +150,9 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def __exit__(self, *exc):
+        self.stop.set()
+        if self.nvml is not None:
+            self.thread.join(timeout=2)
         if self.proc:
             self.proc.terminate()
             try:
@@ -129,7 +162,10 @@ class ClockSampler:
 
     def summary(self) -> dict:
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s_, m_, r_ in self.samples:
+            sm.append(s_)
+            mx.append(m_)
+            reasons.update(r_)
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
@@ -139,12 +175,13 @@ class ClockSampler:
                 mx.append(float(f[1]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[3:7]):
+            for name, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvml" if self.samples else "nvidia-smi"}
 
 
 def measured_traffic(config_name, kernels):

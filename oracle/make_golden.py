@@ -95,7 +95,60 @@ def synthetic_nucleotide(name, T, sites, model_spec, categories, seed, tipstates
     ref.close()
 
 
+def read_fasta(path):
+    seqs, name = {}, None
+    for line in open(path):
+        line = line.strip()
+        if line.startswith(">"):
+            name = line[1:].split()[0]
+            seqs[name] = ""
+        elif name:
+            seqs[name] += line
+    return seqs
+
+
+def write_c1_dropin_fixture():
+    """tests/golden/c1_jc69_time.json: the reference's own fixture tests/data/jc69-time.json with the alignment inlined (the GPU
+    box has no /root/reference), and tests/golden/c1_kat.json: the known answers of tests/test_tree_likelihood.c, parsed
+    from that file, plus the reference's own gradient vectors for the same requests."""
+    import re
+
+    doc = json.load(open(os.path.join(REF_DATA, "jc69-time.json")))
+    aln = doc["model"]["sitepattern"]["alignment"]
+    aln["sequences"] = read_fasta(os.path.join(REF_DATA, aln.pop("file")))
+    doc["model"]["tree"].pop("_file", None)
+    json.dump(doc, open(os.path.join(GOLDEN, "c1_jc69_time.json"), "w"), indent=0, separators=(",", ":"))
+    src = open("/root/reference/tests/test_tree_likelihood.c").read()
+
+    def scalar(name):
+        return float(re.search(r"double\s+" + name + r"\s*=\s*([-0-9.eE+]+)\s*;", src).group(1))
+
+    def vector(name):
+        body = re.search(r"double\s+" + name + r"\[\d+\]\s*=\s*\{(.*?)\}", src, re.S).group(1)
+        return [float(x) for x in body.replace("\n", " ").split(",") if x.strip()]
+
+    kat = {
+        "source": "tests/test_tree_likelihood.c:28-116 (test_treelikelihood_time)",
+        "logP": scalar("expected_logP"), "rate_grad": scalar("expected_rate_grad"),
+        "ratio_grad": vector("expected_ratio_grad"), "root_height_grad": scalar("expected_root_height_grad"),
+        "logP_jacobian": scalar("expected_logP_jacobian"), "ratio_jac_grad": vector("expected_ratios_jac_grad"),
+        "root_height_jac_grad": scalar("expected_root_height_jac_grad"),
+    }
+    # the reference's own TreeLikelihood_gradient output for the requests the drop-in test makes
+    ref = O.Reference(doc["model"])
+    ref.set_include_jacobian(False)
+    kat["ref_gradient_tree_branch"] = [float(x) for x in ref.gradient(O.FLAG_TREE_MODEL | O.FLAG_BRANCH_MODEL)]
+    kat["ref_logP"] = ref.logP()
+    ref.close()
+    json.dump(kat, open(os.path.join(GOLDEN, "c1_kat.json"), "w"), indent=1)
+    print("c1 drop-in fixture:", len(aln["sequences"]), "sequences,", len(kat["ratio_grad"]), "ratio gradients")
+
+
 def main():
+    if "--only-dropin" in sys.argv:
+        write_c1_dropin_fixture()
+        return
+    write_c1_dropin_fixture()
     cwd = os.getcwd()
     os.chdir(REF_DATA)  # fixtures reference fluA.fa / tiny.fa by relative path
 

@@ -347,3 +347,44 @@ double refh_time_gradient(void *vh, int flags, int include_root_freqs, int iters
 	double t1 = now_s();
 	return (t1 - t0) / iters;
 }
+
+/* ---- hooks for the drop-in test of integration/physher_glue.c (tests/test_glue_dropin.py) ---- */
+
+void *refh_model_handle(void *vh) { return ((RefH *)vh)->model; }
+
+size_t refh_initialize_gradient(void *vh, int flags, int include_root_freqs) {
+	RefH *h = (RefH *)vh;
+	size_t len = TreeLikelihood_initialize_gradient(h->model, flags);
+	if (include_root_freqs >= 0) h->tlk->include_root_freqs = include_root_freqs != 0;
+	return len;
+}
+
+void refh_mark_dirty(void *vh) {
+	RefH *h = (RefH *)vh;
+	SingleTreeLikelihood_update_all_nodes(h->tlk);
+	h->tlk->m->need_update = true;
+}
+
+/*
+ * The request sequence of the reference's own known-answer test (tests/test_tree_likelihood.c:33-77), through the
+ * Model vtable: prepare_gradient over {clock rate(s), ratios}, then dlogP per parameter.
+ * out[0] = d logP / d clock rate, out[1..] = d logP / d ratio_i (the last one is the root height).  Returns the count.
+ */
+int refh_kat_dlogP(void *vh, double *out, int cap) {
+	RefH *h = (RefH *)vh;
+	Model *model = h->model;
+	Model **models = (Model **)model->data;
+	Tree *tree = (Tree *)models[0]->obj;
+	BranchModel *bm = (BranchModel *)models[3]->obj;
+	Parameters *ps = new_Parameters(10);
+	for (size_t i = 0; i < Parameters_count(bm->rates); i++) Parameters_add(ps, Parameters_at(bm->rates, i));
+	Parameters *ratios = get_reparams(tree);
+	for (size_t i = 0; i < Parameters_count(ratios); i++) Parameters_add(ps, Parameters_at(ratios, i));
+	model->prepare_gradient(model, ps);
+	SingleTreeLikelihood_update_all_nodes(h->tlk);
+	int n = 0;
+	if (n < cap) out[n++] = model->dlogP(model, Parameters_at(ps, 0));
+	for (size_t i = 0; i < Parameters_count(ratios) && n < cap; i++) out[n++] = model->dlogP(model, Parameters_at(ratios, i));
+	free_Parameters(ps);
+	return n;
+}

@@ -694,11 +694,22 @@ int phb_tlk_rescaling(const phb_tlk *t) { return t->scale; }
 
 int phb_tlk_set_option(phb_tlk *t, int option, int value) {
 	switch (option) {
-	case PHB_OPT_INCLUDE_ROOT_FREQS: t->include_root_freqs = value != 0; break;
-	case PHB_OPT_COMPAT_SCALED_GRADIENT: t->compat_scaled_gradient = value != 0; break;
-	case PHB_OPT_UNROOTED: t->unrooted = value != 0; break;
+	/* an option set to the value it already has leaves the caches alone */
+	case PHB_OPT_INCLUDE_ROOT_FREQS:
+		if (t->include_root_freqs == (value != 0)) return PHB_OK;
+		t->include_root_freqs = value != 0;
+		break;
+	case PHB_OPT_COMPAT_SCALED_GRADIENT:
+		if (t->compat_scaled_gradient == (value != 0)) return PHB_OK;
+		t->compat_scaled_gradient = value != 0;
+		break;
+	case PHB_OPT_UNROOTED:
+		if (t->unrooted == (value != 0)) return PHB_OK;
+		t->unrooted = value != 0;
+		break;
 	case PHB_OPT_KERNELS:
 		if (value < PHB_KERNELS_AUTO || value > PHB_KERNELS_FUSED) return fail(PHB_EINVAL, "unknown kernel family %d", value);
+		if (t->kernels == value) return PHB_OK;
 		t->kernels = value;
 		break;
 	case PHB_OPT_SCALING_THRESHOLD_EXP: t->scaling_threshold = pow(10.0, -(double)value); break;

@@ -1,0 +1,133 @@
+"""Drop-in boundary: the UNMODIFIED reference runs its own JSON fixture with the tree likelihood
+re-pointed at libphysher_b200.so through integration/physher_glue.c, and must reproduce the known answers of its own
+test (tests/test_tree_likelihood.c:28-116: lnL, clock-rate gradient, 67 ratio gradients + root height, with and
+without the Jacobian) to the test's own tolerance (1e-8 absolute) and the north-star 1e-10 relative.
+
+Needs oracle/_ref (built where /root/reference exists; travels to the GPU box) and a GPU.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import GOLDEN, RTOL, grad_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+GLUE_SO = os.path.join(os.path.dirname(O.REF_SO), "libphysher_glue.so")
+
+
+@pytest.fixture(scope="module")
+def libs():
+    if not (O.reference_available() and os.path.exists(GLUE_SO)):
+        pytest.skip("oracle/_ref (compiled reference + glue) not present")
+    L = O._reflib()
+    L.refh_model_handle.argtypes = [C.c_void_p]
+    L.refh_model_handle.restype = C.c_void_p
+    L.refh_initialize_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    L.refh_initialize_gradient.restype = C.c_size_t
+    L.refh_mark_dirty.argtypes = [C.c_void_p]
+    L.refh_kat_dlogP.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.c_int]
+    L.refh_kat_dlogP.restype = C.c_int
+    G = C.CDLL(GLUE_SO)
+    G.phb_physher_attach.argtypes = [C.c_void_p, C.c_int]
+    G.phb_physher_attach.restype = C.c_int
+    G.phb_physher_detach.argtypes = [C.c_void_p]
+    G.phb_physher_gradient.argtypes = [C.c_void_p]
+    G.phb_physher_gradient.restype = C.POINTER(C.c_double)
+    G.phb_physher_evaluations.argtypes = [C.c_void_p]
+    G.phb_physher_evaluations.restype = C.c_longlong
+    return L, G
+
+
+def _spec(name="c1_jc69_time.json"):
+    return json.load(open(os.path.join(GOLDEN, name)))["model"]
+
+
+def test_reference_kat_through_the_glue(libs):
+    L, G = libs
+    kat = json.load(open(os.path.join(GOLDEN, "c1_kat.json")))
+    ref = O.Reference(_spec())
+    model = L.refh_model_handle(ref.h)
+    assert G.phb_physher_attach(model, 0) == 0
+    ref.set_include_jacobian(False)
+    # logP through the Model vtable -> tlk->calculate -> phb_tlk_calculate
+    lnl = ref.logP()
+    assert G.phb_physher_evaluations(model) == 1, "the likelihood did not run through libphysher_b200"
+    assert abs(lnl - kat["logP"]) < 1e-8 and rel_err(lnl, kat["logP"]) < RTOL
+    # the request sequence of the reference's own test through model->prepare_gradient / model->dlogP
+    out = np.zeros(80)
+    n = L.refh_kat_dlogP(ref.h, out.ctypes.data_as(C.POINTER(C.c_double)), 80)
+    assert n == 1 + 68
+    want = np.array([kat["rate_grad"]] + kat["ratio_grad"] + [kat["root_height_grad"]])
+    assert np.abs(out[:n] - want).max() < 1e-8 or grad_err(out[:n], want) < RTOL
+    assert grad_err(out[:n], want) < RTOL
+    assert G.phb_physher_evaluations(model) == 2, "one fused device evaluation per gradient request"
+    # with the Jacobian of the ratio transform (host chain, the reference's own code on top of device gradients)
+    ref.set_include_jacobian(True)
+    lnl = ref.logP()
+    assert abs(lnl - kat["logP_jacobian"]) < 1e-8
+    n = L.refh_kat_dlogP(ref.h, out.ctypes.data_as(C.POINTER(C.c_double)), 80)
+    want = np.array([kat["rate_grad"]] + kat["ratio_jac_grad"] + [kat["root_height_jac_grad"]])
+    assert grad_err(out[:n], want) < RTOL
+    G.phb_physher_detach(model)
+    ref.close()
+
+
+def test_gradient_vector_contract_and_caching(libs):
+    """TreeLikelihood_gradient's contract (treelikelihood.c:320-340): tlk-owned buffer, order (ratios | clock), cached."""
+    L, G = libs
+    kat = json.load(open(os.path.join(GOLDEN, "c1_kat.json")))
+    ref = O.Reference(_spec())
+    model = L.refh_model_handle(ref.h)
+    ref.set_include_jacobian(False)
+    G.phb_physher_attach(model, 0)
+    n = L.refh_initialize_gradient(ref.h, O.FLAG_TREE_MODEL | O.FLAG_BRANCH_MODEL, -1)
+    assert n == 69
+    L.refh_mark_dirty(ref.h)
+    p1 = G.phb_physher_gradient(model)
+    g = np.ctypeslib.as_array(p1, shape=(n,)).copy()
+    assert grad_err(g, np.array(kat["ref_gradient_tree_branch"])) < RTOL
+    evals = G.phb_physher_evaluations(model)
+    p2 = G.phb_physher_gradient(model)  # nothing changed: cached, same buffer, no device work
+    assert C.addressof(p1.contents) == C.addressof(p2.contents) and G.phb_physher_evaluations(model) == evals
+    assert abs(ref.L.refh_logP(ref.h) - kat["logP"]) < 1e-8  # marks dirty -> recomputed
+    assert G.phb_physher_evaluations(model) == evals + 1
+    # detach: the reference's own CPU path is back and agrees
+    G.phb_physher_detach(model)
+    assert abs(ref.logP() - kat["logP"]) < 1e-8
+    ref.close()
+
+
+@pytest.mark.parametrize("tipstates", [True, False])
+def test_unrooted_gtr_gamma_through_the_glue(libs, tipstates):
+    """Branch-length tree, GTR+G4 with non-uniform pi: eigen system path, unrooted convention, both gradient variants."""
+    from physher_b200 import synthetic as syn
+
+    L, G = libs
+    T, sites = 14, 500
+    topo = syn.random_topology(T, 41)
+    bl = syn.random_branch_lengths(topo, 42)
+    pat = syn.random_patterns(T, sites, 4, 0.3, 43, unknown_frac=0.02)
+    names = [f"t{i}" for i in range(T)]
+    seqs = dict(zip(names, syn.sequences_from_patterns(pat, syn.NUCLEOTIDES)))
+    gtr = O.nucleotide_model_spec("gtr", [0.1, 0.2, 0.3, 0.4], [0.05, 0.3, 0.1, 0.15, 0.3, 0.1])
+    spec = O.treelikelihood_spec(syn.to_newick(topo, bl, names), seqs, gtr, categories=4, alpha=0.5, tipstates=tipstates)
+    ref = O.Reference(spec)
+    lnl_cpu = ref.logP()
+    g_cpu_exact = ref.gradient(O.FLAG_TREE_MODEL, include_root_freqs=0)
+    g_cpu_default = ref.gradient(O.FLAG_TREE_MODEL, include_root_freqs=-1)
+    model = L.refh_model_handle(ref.h)
+    assert G.phb_physher_attach(model, 0) == 0
+    assert rel_err(ref.logP(), lnl_cpu) < RTOL
+    for irf, want in ((0, g_cpu_exact), (-1, g_cpu_default)):
+        n = L.refh_initialize_gradient(ref.h, O.FLAG_TREE_MODEL, irf)
+        L.refh_mark_dirty(ref.h)
+        g = np.ctypeslib.as_array(G.phb_physher_gradient(model), shape=(n,)).copy()
+        assert grad_err(g, want) < RTOL
+        assert g[ref.root] == 0.0 and g[ref.root_right] == 0.0
+    G.phb_physher_detach(model)
+    ref.close()
