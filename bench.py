@@ -34,7 +34,7 @@ CONFIGS = {
     # name: (taxa, patterns per GPU, states, categories, model)
     "c2": dict(taxa=1000, patterns=100_000, states=4, cats=4, model="GTR+G4", mu=0.04),
     "c2_1m": dict(taxa=1000, patterns=1_000_000, states=4, cats=4, model="GTR+G4", mu=0.04),
-    "c3": dict(taxa=500, patterns=50_000, states=4, cats=4, model="HKY+G4", mu=0.04),
+    "c3": dict(taxa=500, patterns=50_000, states=4, cats=4, model="HKY+G4", mu=0.04, batch=128),
     "c4": dict(taxa=200, patterns=200_000, states=20, cats=4, model="LG+G4", mu=0.08),
     "c5": dict(taxa=100, patterns=1_000_000, states=61, cats=1, model="GY94", mu=0.1),
 }
@@ -309,7 +309,8 @@ def sample_per_core(cfg) -> int:
 
 
 def workload_name(cfg):
-    return f"{cfg['model']} {cfg['taxa']} taxa x {cfg['patterns']} patterns per GPU, lnL + branch gradients"
+    batch = f" x {cfg['batch']} branch-length samples per step" if cfg.get("batch", 1) > 1 else ""
+    return f"{cfg['model']} {cfg['taxa']} taxa x {cfg['patterns']} patterns per GPU{batch}, lnL + branch gradients"
 
 
 # -------------------------------------------------------------------------------------------------
@@ -371,8 +372,26 @@ def main():
         b[topo.right[topo.root]] = 0.0
         return b
 
+    B = int(cfg.get("batch", 1))
+
+    def step_batch():
+        """BASELINE config 3: B branch-length samples (base x LogNormal(0, 0.1)) per step through phb_tlk_gradient_batch --
+        host buffers in ([B][N] doubles) and out (lnl[B], grad[B][N]); one fused launch for the whole batch."""
+        bls = bl[None, :] * rng.lognormal(0.0, 0.1, size=(B, N))
+        bls[:, topo.root] = 0.0
+        bls[:, topo.right[topo.root]] = 0.0
+        lnls, grads = tlk.gradient_batch(bls)
+        if world > 1:
+            t = torch.from_numpy(np.concatenate([lnls[:, None], grads], axis=1)).cuda()
+            dist.all_reduce(t)
+            h = t.cpu().numpy()
+            lnls, grads = h[:, 0], h[:, 1:]
+        return float(lnls[-1]), grads[-1]
+
     def step_e2e():
         """Public API, host in / host out: H2D of the branch lengths, full evaluation, D2H of lnL + gradient."""
+        if B > 1:
+            return step_batch()
         tlk.set_branch_lengths(new_bl())
         if world == 1:
             g = tlk.gradient()
@@ -388,6 +407,9 @@ def main():
 
     def step_device():
         """Device-resident step: inputs already in HBM, result left on the device."""
+        if B > 1:  # the batched entry point takes host buffers (2 x B x N doubles per step, ~1 MB each way at C3)
+            step_batch()
+            return
         tlk.gradient_device(out_dev.data_ptr())
         if world > 1:
             tlk.synchronize()
@@ -446,11 +468,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0])
 
-    total_pn = float(P) * world * N
+    total_pn = float(P) * world * N * B
     value = total_pn / (step_ms * 1e-3)
     e2e_value = total_pn / (e2e_ms * 1e-3)
     peak, peak_src = measured_peak_gbs()
-    alg = algorithmic_bytes(cfg)
+    alg = algorithmic_bytes(cfg) * B  # one launch processes the whole batch
     kms = kern_ms / max(kern_n, 1)
     achieved = alg / (kms * 1e-3) / 1e9 if kms > 0 else None
     fused = args.kernels != "generic" and S == 4
@@ -462,7 +484,7 @@ def main():
         hbm["traffic_GBs"] = traffic / (kms * 1e-3) / 1e9
         hbm["traffic_frac"] = hbm["traffic_GBs"] / peak
     if fused:
-        fused_bytes = float(P) * (2 * (T - 1) * C * S * 8 + 2 * T)  # what the fused walk must move: lower rows out and back, tip codes twice
+        fused_bytes = float(P) * B * (2 * (T - 1) * C * S * 8 + 2 * T)  # what the fused walk must move: lower rows out and back, tip codes twice
         hbm.update(kernel="k_nuc4_walk<C=%d,scale=0,grad=1>" % C, fused_min_bytes_per_launch=fused_bytes,
                    note="achieved = SURVEY.md 8d streaming-model bytes / kernel time; the fused walk keeps upper partials on chip, so it moves "
                         f"~{fused_bytes/1e9:.1f} GB per launch (traffic = ncu dram bytes) and frac can exceed 1; traffic_frac is the real DRAM utilisation")
@@ -483,10 +505,10 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(cfg), "taxa": T, "patterns_per_gpu": P, "states": S, "categories": C, "model": cfg["model"],
                    "kernels": args.kernels, "l2": "per-evaluation working set (>= 2 GB of partials) exceeds the 126 MB L2; no explicit flush",
-                   "sharding": f"patterns x{world}" if world > 1 else "single GPU"},
-        "evals_per_s": 1e3 / step_ms, "lnl": lnl,
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * (N + 1),
-                "evals_per_s": 1e3 / e2e_ms},
+                   "sharding": f"patterns x{world}" if world > 1 else "single GPU", "samples_per_step": B},
+        "evals_per_s": B * 1e3 / step_ms, "lnl": lnl,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * N * B, "d2h_bytes_per_step": 8 * (N + 1) * B,
+                "evals_per_s": B * 1e3 / e2e_ms},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": roof,

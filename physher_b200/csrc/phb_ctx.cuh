@@ -30,6 +30,8 @@ struct phbc_ctx {
 	double *d_lower;         // [N-T][C][P][S]
 	double *d_upper;         // [N][C][P][S]   (lazy)
 	double *d_sf;            // [2N][P]        (lazy)
+	double *d_dmma_img;      // packed matrix images of the tensor-core path [P | dP][N][C][IMG]
+	size_t dmma_img_bytes;
 	phbc_op *d_lower_ops, *d_upper_ops;
 	phbc_parent_op *d_parent_ops;
 	int n_lower_ops, n_upper_ops, n_parent_ops;
@@ -57,7 +59,8 @@ struct phbc_ctx {
 	double *d_pattern_lnl;   // [P]
 	double *d_result;        // [result_cap][1+N]
 	int result_cap;
-	double *d_cat_grad;      // [N][C]
+	double *d_cat_grad;      // [cat_grad_cap][N][C]
+	int cat_grad_cap;
 	double *d_scratch;       // reduction scratch
 	size_t scratch_bytes;
 
@@ -118,3 +121,38 @@ __device__ __forceinline__ double phb_warp_sum(double v) {
 	for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
 	return v;
 }
+
+// ---------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy (global -> shared)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+	             "l"(src), "r"(bytes), "r"(smem_u32(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	uint32_t done;
+	do {
+		asm volatile(
+		    "{\n"
+		    ".reg .pred p;\n"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+		    "selp.u32 %0, 1, 0, p;\n"
+		    "}\n"
+		    : "=r"(done)
+		    : "r"(smem_u32(bar)), "r"(parity)
+		    : "memory");
+	} while (!done);
+}
+__device__ __forceinline__ void red_add_f64(double *addr, double v) {
+	asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
+}
+

@@ -72,6 +72,7 @@ extern "C" phbc_ctx *phbc_create(int device, int ntips, int nstate, int ncat, in
 	ok = ok && dev_alloc(&ctx->d_freqs, S) == 0 && dev_alloc(&ctx->d_rates, C) == 0 && dev_alloc(&ctx->d_props, C) == 0;
 	ok = ok && dev_alloc(&ctx->d_pattern_lnl, P) == 0;
 	ok = ok && dev_alloc(&ctx->d_cat_grad, N * C) == 0;
+	ctx->cat_grad_cap = 1;
 	ctx->result_cap = 1;
 	ok = ok && dev_alloc(&ctx->d_result, (size_t)ctx->result_cap * (1 + N)) == 0;
 	ctx->bl_cap = 1;
@@ -97,7 +98,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	                ctx->d_freqs, ctx->d_rates, ctx->d_props, ctx->d_bl, ctx->d_P, ctx->d_dP, ctx->d_lower, ctx->d_upper,
 	                ctx->d_sf, ctx->d_lower_ops, ctx->d_upper_ops, ctx->d_parent_ops, ctx->d_post_ops, ctx->d_pre_ops, ctx->d_walk_mats,
 	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch,
-	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl, ctx->d_post_tip_order, ctx->d_pre_tip_order};
+	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl, ctx->d_post_tip_order, ctx->d_pre_tip_order, ctx->d_dmma_img};
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		if (bufs[i]) cudaFree(bufs[i]);
 	if (ctx->ev_beg) {
@@ -691,7 +692,22 @@ extern "C" int phbc_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "batch index %d out of range", o->batch_index);
 		return -1;
 	}
-	if (o->kernels != 1 /* PHB_KERNELS_GENERIC */ && phbc_nuc4_supported(ctx, o)) return phbc_nuc4_evaluate(ctx, o);
+	const int count = o->batch_count > 1 ? o->batch_count : 1;
+	if (o->batch_index + count > ctx->bl_cap || o->batch_index + count > ctx->result_cap) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "batch %d + %d out of range", o->batch_index, count);
+		return -1;
+	}
+	if (o->kernels != 1 /* PHB_KERNELS_GENERIC */ && phbc_nuc4_supported(ctx, o)) return phbc_nuc4_evaluate(ctx, o);  // one launch for the whole batch
+	if (count > 1) {  // node-at-a-time paths own one set of partials: samples run back to back
+		phbc_eval_opts one = *o;
+		one.batch_count = 1;
+		for (int b = 0; b < count; b++) {
+			one.batch_index = o->batch_index + b;
+			int rc = phbc_evaluate(ctx, &one);
+			if (rc) return rc;
+		}
+		return 0;
+	}
 	if (o->kernels != 1 /* PHB_KERNELS_GENERIC */ && phbc_dmma_supported(ctx, o)) return phbc_dmma_evaluate(ctx, o);
 	if (o->kernels == 2 /* PHB_KERNELS_FUSED */) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "fused kernels not available for this configuration (S=%d)", ctx->S);

@@ -114,7 +114,8 @@ typedef struct phbc_eval_opts {
 	int compat_scaled_gradient;
 	int want_gradient;
 	int explicit_matrices;       /* matrices were uploaded, do not rebuild them from the eigen system */
-	int batch_index;             /* which uploaded branch-length vector                            */
+	int batch_index;             /* which uploaded branch-length vector (the first one of a batch)  */
+	int batch_count;             /* > 1: evaluate batch_index .. batch_index + batch_count - 1 (results in the matching slots) */
 } phbc_eval_opts;
 
 /*

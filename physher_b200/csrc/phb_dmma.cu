@@ -36,6 +36,13 @@ struct DmmaShape {
 	static constexpr int KT = KP / 4, NT = NP / 8;
 	static constexpr int LD = (KP % 8 == 4) ? KP : KP + 4;  // leading dimension of a staged matrix, = 4 (mod 8)
 	static constexpr int MAT = NP * LD;                     // doubles per staged matrix
+	// the contraction runs in chunks of KCH k-steps; the A fragments of chunk i + 1 are fetched from HBM while the tensor
+	// pipe works on chunk i (register double buffering).  Short contractions are one chunk: the prefetch then spans tiles.
+	static constexpr int KCH = KT <= 6 ? KT : 4;
+	static constexpr int NCH = (KT + KCH - 1) / KCH;
+	// packed matrix image (one TMA bulk copy): [NP][LD] for partial operands, or TRANSPOSED [S][NP] + row sums [NP] for state tips
+	static constexpr int TIP_IMG = S * NP + NP;
+	static constexpr int IMG = ((MAT > TIP_IMG ? MAT : TIP_IMG) + 1) / 2 * 2;  // doubles, 16-byte multiple
 };
 
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
@@ -50,64 +57,71 @@ __device__ __forceinline__ const double *dm_partial_ptr(const Bufs &b, int idx, 
 }
 __device__ __forceinline__ bool dm_state_tip(const Bufs &b, int idx) { return idx < b.T && b.tip_kind == PHBC_TIP_STATES; }
 
-// stage one S x S row-major matrix into shared memory, zero padded: as [NP][LD] (B-fragment layout) for operands that are
-// partials, or TRANSPOSED as [S][NP] for state tips so that one tip state selects a contiguous column of M (16-byte gathers);
-// optional row sums (first NP entries of rs)
+// Packed shared-memory images of the transition matrices, written once per evaluation so that a CTA stages a matrix with ONE
+// TMA bulk copy instead of an element-wise gather: zero padded [NP][LD] (B-fragment layout) for nodes whose lower partials are
+// an operand, or TRANSPOSED [S][NP] followed by the row sums [NP] for state tips, so that one tip state selects a contiguous
+// column of M (16-byte gathers) and an unknown state selects the row sums (treelikelihoodX.c:878-1001).
+// grid (N, C, 2: P | dP), images laid out [which][node][category][IMG].
 template <class Sh>
-__device__ __forceinline__ void stage_matrix(double *dst, const double *__restrict__ src, double *rs, bool transposed) {
-	if (transposed) {
+__global__ void k_dmma_pack(int T, int N, int C, int tip_states, const double *__restrict__ Pm, const double *__restrict__ dPm,
+                            double *__restrict__ img) {
+	const int n = blockIdx.x, c = blockIdx.y, which = blockIdx.z;
+	const double *src = (which ? dPm : Pm) + ((size_t)n * C + c) * Sh::S * Sh::S;
+	double *dst = img + (((size_t)which * N + n) * C + c) * Sh::IMG;
+	if (n < T && tip_states) {
 		for (int e = threadIdx.x; e < Sh::S * Sh::NP; e += blockDim.x) {
 			const int s = e / Sh::NP, i = e - s * Sh::NP;
-			dst[e] = i < Sh::S ? __ldg(src + i * Sh::S + s) : 0.0;
+			dst[e] = i < Sh::S ? src[i * Sh::S + s] : 0.0;
 		}
-	} else {
-		for (int e = threadIdx.x; e < Sh::MAT; e += blockDim.x) {
-			const int i = e / Sh::LD, j = e - i * Sh::LD;
-			dst[e] = (i < Sh::S && j < Sh::S) ? __ldg(src + i * Sh::S + j) : 0.0;
-		}
-	}
-	if (rs) {
 		for (int i = threadIdx.x; i < Sh::NP; i += blockDim.x) {
 			double acc = 0.0;
 			if (i < Sh::S)
-				for (int j = 0; j < Sh::S; j++) acc += __ldg(src + i * Sh::S + j);
-			rs[i] = acc;
+				for (int j = 0; j < Sh::S; j++) acc += src[i * Sh::S + j];
+			dst[Sh::S * Sh::NP + i] = acc;
+		}
+		for (int e = Sh::TIP_IMG + threadIdx.x; e < Sh::IMG; e += blockDim.x) dst[e] = 0.0;
+	} else {
+		for (int e = threadIdx.x; e < Sh::IMG; e += blockDim.x) {
+			const int i = e / Sh::LD, j = e - i * Sh::LD;
+			dst[e] = (e < Sh::MAT && i < Sh::S && j < Sh::S) ? src[i * Sh::S + j] : 0.0;
 		}
 	}
 }
 
-// A fragments of MT m-tiles (8 patterns each) starting at pattern p0: a[m][t] = X[p0 + 8m + lane/4][4t + lane%4]
+// A fragments of chunk `ch` for MT m-tiles (8 patterns each) starting at pattern p0:
+// a[m][tt] = X[p0 + 8m + lane/4][4 (ch KCH + tt) + lane%4]  (a quad reads 32 contiguous bytes of one pattern's state vector)
 template <class Sh, int MT>
-__device__ __forceinline__ void load_a(const double *__restrict__ X, int p0, int P, int lane, double (&a)[MT][Sh::KT]) {
+__device__ __forceinline__ void load_chunk(const double *__restrict__ X, int p0, int P, int lane, int ch, double (&a)[MT][Sh::KCH]) {
 	const int r = lane >> 2, q = lane & 3;
 #pragma unroll
 	for (int m = 0; m < MT; m++) {
 		const int p = p0 + 8 * m + r;
 		const double *row = X + (size_t)p * Sh::S;
 #pragma unroll
-		for (int t = 0; t < Sh::KT; t++) {
-			const int k = 4 * t + q;
-			a[m][t] = (p < P && (Sh::KP == Sh::S || k < Sh::S)) ? __ldg(row + k) : 0.0;
+		for (int tt = 0; tt < Sh::KCH; tt++) {
+			const int t = ch * Sh::KCH + tt, k = 4 * t + q;
+			// volatile: the load is issued HERE, a whole chunk of tensor work ahead of its use (ptxas otherwise sinks it
+			// towards the consumer to shorten the live range, and the DMMA then waits out the full HBM latency)
+			a[m][tt] = 0.0;
+			if (t < Sh::KT && p < P && (Sh::KP == Sh::S || k < Sh::S)) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(a[m][tt]) : "l"(row + k));
 		}
 	}
 }
 
-// acc[m][j] (+)= A . M^T for the NTW n-tiles starting at n-tile n0
-template <class Sh, int MT, int NTW>
-__device__ __forceinline__ void gemm(const double *__restrict__ M, int n0, int lane, const double (&a)[MT][Sh::KT], double (&acc)[MT][NTW][2]) {
-	const int r = lane >> 2, q = lane & 3;
+template <int MT, int NTW>
+__device__ __forceinline__ void zero_acc(double (&acc)[MT][NTW][2]) {
 #pragma unroll
 	for (int m = 0; m < MT; m++)
 #pragma unroll
 		for (int j = 0; j < NTW; j++) acc[m][j][0] = acc[m][j][1] = 0.0;
+}
+
+template <class Sh, int MT>
+__device__ __forceinline__ void copy_chunk(double (&dst)[MT][Sh::KCH], const double (&src)[MT][Sh::KCH]) {
 #pragma unroll
-	for (int t = 0; t < Sh::KT; t++)
+	for (int m = 0; m < MT; m++)
 #pragma unroll
-		for (int j = 0; j < NTW; j++) {
-			const double bf = M[((n0 + j) * 8 + r) * Sh::LD + 4 * t + q];
-#pragma unroll
-			for (int m = 0; m < MT; m++) dmma_m8n8k4(acc[m][j][0], acc[m][j][1], a[m][t], bf);
-		}
+		for (int tt = 0; tt < Sh::KCH; tt++) dst[m][tt] = src[m][tt];
 }
 
 // message of a state tip: column s of M, or `unknown_value(i)` when s >= S (probability matrices: 1, treelikelihood20.c:125-131;
@@ -135,58 +149,122 @@ __device__ __forceinline__ void tip_gather(const uint8_t *__restrict__ states, c
 	}
 }
 
+template <class Sh, int MT, int NTW>
+__device__ __forceinline__ void store_tile(double *__restrict__ U, int p0, int P, int n0, int lane, const double (&v)[MT][NTW][2]) {
+	const int r = lane >> 2, q = lane & 3;
+#pragma unroll
+	for (int m = 0; m < MT; m++) {
+		const int p = p0 + 8 * m + r;
+		if (p >= P) continue;
+		double *row = U + (size_t)p * Sh::S;
+#pragma unroll
+		for (int j = 0; j < NTW; j++) {
+			const int i = (n0 + j) * 8 + 2 * q;
+			if (Sh::S % 2 == 0) {
+				if (i < Sh::S) *reinterpret_cast<double2 *>(row + i) = make_double2(v[m][j][0], v[m][j][1]);  // S even: 16-byte aligned
+			} else {
+				if (i < Sh::S) row[i] = v[m][j][0];
+				if (i + 1 < Sh::S) row[i + 1] = v[m][j][1];
+			}
+		}
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1-K4: out = (P_a x_a) o (P_b x_b);  grid (pattern chunks, C, ops of the level)
-// warps: WM m-groups x NSPLIT n-groups; a warp owns MT m-tiles and NT / NSPLIT n-tiles
+// warps: WM m-groups x NSPLIT n-groups; a warp owns MT m-tiles and NT / NSPLIT n-tiles.
+// Both products advance through ONE k-loop (2 MT NTW independent accumulator chains per warp keep the FP64 tensor pipe
+// busy across its latency) and the A fragments of the next chunk / next tile are in flight while it runs.
 // ---------------------------------------------------------------------------------------------
 template <int S, int MT, int NSPLIT, int WM>
-__global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ Pm) {
+__global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ img) {
 	using Sh = DmmaShape<S>;
 	constexpr int NTW = Sh::NT / NSPLIT;
 	static_assert(Sh::NT % NSPLIT == 0, "n-tiles must split evenly");
-	extern __shared__ double sm[];
-	double *mA = sm, *mB = sm + Sh::MAT;
+	extern __shared__ __align__(128) unsigned char smraw[];
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smraw);
+	double *sm = reinterpret_cast<double *>(smraw + 128);
+	double *mA = sm, *mB = sm + Sh::IMG;
 	const phbc_op op = ops[blockIdx.z];
 	const int c = blockIdx.y;
 	const bool a_tip = dm_state_tip(b, op.a), b_tip = dm_state_tip(b, op.b);
-	stage_matrix<Sh>(mA, Pm + ((size_t)op.a_mat * b.C + c) * S * S, nullptr, a_tip);
-	stage_matrix<Sh>(mB, Pm + ((size_t)op.b_mat * b.C + c) * S * S, nullptr, b_tip);
-	__syncthreads();
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		mbar_expect_tx(bar, 2 * Sh::IMG * 8);
+		bulk_g2s(mA, img + ((size_t)op.a_mat * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		bulk_g2s(mB, img + ((size_t)op.b_mat * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+	}
+	__syncthreads();  // the barrier is initialised before anyone polls it
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int wm = warp / NSPLIT, n0 = (warp % NSPLIT) * NTW;
 	const int r = lane >> 2, q = lane & 3;
 	constexpr int TP = WM * MT * 8;
 	double *out = (double *)dm_partial_ptr(b, op.out, c);
-	const double *xa = dm_partial_ptr(b, op.a, c), *xb = dm_partial_ptr(b, op.b, c);
+	// state tips have no partial operand: point the (fully predicated-off) loads at a valid address
+	const double *xa = a_tip ? nullptr : dm_partial_ptr(b, op.a, c), *xb = b_tip ? nullptr : dm_partial_ptr(b, op.b, c);
+	const int Pa = a_tip ? 0 : b.P, Pb = b_tip ? 0 : b.P;  // P = 0 switches the operand's loads off
 	const int ntiles = (b.P + TP - 1) / TP;
+	double ca[MT][Sh::KCH], cb[MT][Sh::KCH];
+	{
+		const int p0 = blockIdx.x * TP + wm * MT * 8;
+		load_chunk<Sh, MT>(xa, p0, Pa, lane, 0, ca);
+		load_chunk<Sh, MT>(xb, p0, Pb, lane, 0, cb);
+	}
+	mbar_wait(bar, 0);  // matrices have landed (the first A fragments are already in flight)
+	// B fragments run one (k-step, n-tile) ahead of the tensor pipe: the LDS of step u + 1 is issued before the DMMAs of step u
+	double bA = 0.0, bB = 0.0;
+	{
+		const int off = (n0 * 8 + r) * Sh::LD + q;
+		if (!a_tip) bA = mA[off];
+		if (!b_tip) bB = mB[off];
+	}
 	for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 		const int p0 = tile * TP + wm * MT * 8;
-		double acc[MT][NTW][2], acc2[MT][NTW][2];
-		double fa[MT][Sh::KT], fb[MT][Sh::KT];
-		// every global load of the tile is issued before the first product
-		if (!a_tip) load_a<Sh, MT>(xa, p0, b.P, lane, fa);
-		if (!b_tip) load_a<Sh, MT>(xb, p0, b.P, lane, fb);
-		if (a_tip) tip_gather<Sh, MT, NTW, true>(b.tip_states + (size_t)op.a * b.P, mA, nullptr, p0, b.P, n0, lane, acc);
-		else gemm<Sh, MT, NTW>(mA, n0, lane, fa, acc);
-		if (b_tip) tip_gather<Sh, MT, NTW, true>(b.tip_states + (size_t)op.b * b.P, mB, nullptr, p0, b.P, n0, lane, acc2);
-		else gemm<Sh, MT, NTW>(mB, n0, lane, fb, acc2);
+		double accA[MT][NTW][2], accB[MT][NTW][2];
+		zero_acc<MT, NTW>(accA);
+		zero_acc<MT, NTW>(accB);
 #pragma unroll
-		for (int m = 0; m < MT; m++) {
-			const int p = p0 + 8 * m + r;
-			if (p >= b.P) continue;
-			double *row = out + (size_t)p * S;
+		for (int ch = 0; ch < Sh::NCH; ch++) {
+			double na[MT][Sh::KCH], nb[MT][Sh::KCH];
+			const bool last = ch == Sh::NCH - 1;
+			const int np0 = last ? p0 + (int)gridDim.x * TP : p0;  // past the end => all loads predicated off
+			load_chunk<Sh, MT>(xa, np0, Pa, lane, last ? 0 : ch + 1, na);
+			load_chunk<Sh, MT>(xb, np0, Pb, lane, last ? 0 : ch + 1, nb);
+			__syncwarp();  // scheduling fence: keeps the prefetch loads above this chunk's tensor work
 #pragma unroll
-			for (int j = 0; j < NTW; j++) {
-				const int i = (n0 + j) * 8 + 2 * q;
-				const double v0 = acc[m][j][0] * acc2[m][j][0], v1 = acc[m][j][1] * acc2[m][j][1];
-				if (S % 2 == 0) {
-					if (i < S) *reinterpret_cast<double2 *>(row + i) = make_double2(v0, v1);  // S even: 16-byte aligned
-				} else {
-					if (i < S) row[i] = v0;
-					if (i + 1 < S) row[i + 1] = v1;
+			for (int tt = 0; tt < Sh::KCH; tt++) {
+				const int t = ch * Sh::KCH + tt;
+				if (t < Sh::KT) {
+#pragma unroll
+					for (int j = 0; j < NTW; j++) {
+						const int nj = j + 1 < NTW ? j + 1 : 0, nt = j + 1 < NTW ? t : (t + 1 < Sh::KT ? t + 1 : 0);  // wraps into the next tile
+						const int noff = ((n0 + nj) * 8 + r) * Sh::LD + 4 * nt + q;
+						double nA = 0.0, nB = 0.0;
+						if (!a_tip) nA = mA[noff];
+						if (!b_tip) nB = mB[noff];
+						if (!a_tip) {
+#pragma unroll
+							for (int m = 0; m < MT; m++) dmma_m8n8k4(accA[m][j][0], accA[m][j][1], ca[m][tt], bA);
+						}
+						if (!b_tip) {
+#pragma unroll
+							for (int m = 0; m < MT; m++) dmma_m8n8k4(accB[m][j][0], accB[m][j][1], cb[m][tt], bB);
+						}
+						bA = nA, bB = nB;
+					}
 				}
 			}
+			copy_chunk<Sh, MT>(ca, na);
+			copy_chunk<Sh, MT>(cb, nb);
 		}
+		if (a_tip) tip_gather<Sh, MT, NTW, true>(b.tip_states + (size_t)op.a * b.P, mA, nullptr, p0, b.P, n0, lane, accA);
+		if (b_tip) tip_gather<Sh, MT, NTW, true>(b.tip_states + (size_t)op.b * b.P, mB, nullptr, p0, b.P, n0, lane, accB);
+#pragma unroll
+		for (int m = 0; m < MT; m++)
+#pragma unroll
+			for (int j = 0; j < NTW; j++) accA[m][j][0] *= accB[m][j][0], accA[m][j][1] *= accB[m][j][1];
+		store_tile<Sh, MT, NTW>(out, p0, b.P, n0, lane, accA);
 	}
 }
 
@@ -195,30 +273,41 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const p
 // GRAD: reduce the branch-gradient terms (unscaled form, site likelihood from pattern_lnl);
 // !GRAD: only the upper partials, tips included (the caller reduces with the generic K9/K10 kernel).
 // partial: [N][C][gridDim.x] per-CTA sums of the children's gradient terms.
+// The five products W = P_n U_n, M_b = P_b L_b, D_b = dP_b L_b, M_a = P_a L_a, D_a = dP_a L_a share one k-loop
+// (5 MT NTW independent accumulator chains per warp) with the next chunk's A fragments in flight.
 // ---------------------------------------------------------------------------------------------
 template <int S, int MT, int NSPLIT, int WM, bool GRAD>
-__global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const phbc_parent_op *__restrict__ ops, const double *__restrict__ Pm,
-                                                               const double *__restrict__ dPm, const double *__restrict__ freqs,
-                                                               const double *__restrict__ weights, const double *__restrict__ pattern_lnl,
-                                                               int include_root_freqs, double *__restrict__ partial) {
+__global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const phbc_parent_op *__restrict__ ops, const double *__restrict__ img,
+                                                               const double *__restrict__ freqs, const double *__restrict__ weights,
+                                                               const double *__restrict__ pattern_lnl, int include_root_freqs, int pstride,
+                                                               double *__restrict__ partial) {
 	using Sh = DmmaShape<S>;
 	constexpr int NTW = Sh::NT / NSPLIT;
 	constexpr int NWARPS = WM * NSPLIT;
-	extern __shared__ double sm[];
-	double *mP = sm, *mA = sm + Sh::MAT, *mB = sm + 2 * Sh::MAT;
-	double *dA = GRAD ? sm + 3 * Sh::MAT : nullptr, *dB = GRAD ? sm + 4 * Sh::MAT : nullptr;
-	double *aux = sm + (GRAD ? 5 : 3) * Sh::MAT;  // rsA[NP], rsB[NP], fq[NP], wroot[NP], red[2 * NWARPS]
-	double *rsA = aux, *rsB = aux + Sh::NP, *fq = aux + 2 * Sh::NP, *wroot = aux + 3 * Sh::NP, *red = aux + 4 * Sh::NP;
+	extern __shared__ __align__(128) unsigned char smraw[];
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smraw);
+	double *sm = reinterpret_cast<double *>(smraw + 128);
+	double *mP = sm, *mA = sm + Sh::IMG, *mB = sm + 2 * Sh::IMG;
+	double *dA = GRAD ? sm + 3 * Sh::IMG : nullptr, *dB = GRAD ? sm + 4 * Sh::IMG : nullptr;
+	double *aux = sm + (GRAD ? 5 : 3) * Sh::IMG;  // fq[NP], wroot[NP], red[2 * NWARPS]
+	double *fq = aux, *wroot = aux + Sh::NP, *red = aux + 2 * Sh::NP;
 	const phbc_parent_op op = ops[blockIdx.z];
 	const int c = blockIdx.y;
 	const bool is_root = op.flags & 1;
 	const bool a_tip = dm_state_tip(b, op.a), b_tip = dm_state_tip(b, op.b);
-	if (!is_root) stage_matrix<Sh>(mP, Pm + ((size_t)op.node * b.C + c) * S * S, nullptr, false);
-	stage_matrix<Sh>(mA, Pm + ((size_t)op.a * b.C + c) * S * S, nullptr, a_tip);
-	stage_matrix<Sh>(mB, Pm + ((size_t)op.b * b.C + c) * S * S, nullptr, b_tip);
-	if (GRAD) {
-		stage_matrix<Sh>(dA, dPm + ((size_t)op.a * b.C + c) * S * S, rsA, a_tip);
-		stage_matrix<Sh>(dB, dPm + ((size_t)op.b * b.C + c) * S * S, rsB, b_tip);
+	const double *rsA = dA + Sh::S * Sh::NP, *rsB = dB + Sh::S * Sh::NP;  // row sums ride behind a tip's transposed image
+	if (threadIdx.x == 0) {
+		const size_t dimg = (size_t)b.N * b.C * Sh::IMG;  // offset of the dP images
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		mbar_expect_tx(bar, ((is_root ? 0 : 1) + (GRAD ? 4 : 2)) * Sh::IMG * 8);
+		if (!is_root) bulk_g2s(mP, img + ((size_t)op.node * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		bulk_g2s(mA, img + ((size_t)op.a * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		bulk_g2s(mB, img + ((size_t)op.b * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		if (GRAD) {
+			bulk_g2s(dA, img + dimg + ((size_t)op.a * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+			bulk_g2s(dB, img + dimg + ((size_t)op.b * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		}
 	}
 	for (int i = threadIdx.x; i < Sh::NP; i += blockDim.x) {
 		const double f = i < S ? freqs[i] : 0.0;
@@ -232,39 +321,111 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 	constexpr int TP = WM * MT * 8;
 	const bool a_leaf = op.a < b.T, b_leaf = op.b < b.T;
 	const double *xw = b.upper + ((size_t)op.node * b.C + c) * (size_t)b.P * S;
-	const double *xa = dm_partial_ptr(b, op.a, c), *xb = dm_partial_ptr(b, op.b, c);
+	const double *xa = a_tip ? nullptr : dm_partial_ptr(b, op.a, c), *xb = b_tip ? nullptr : dm_partial_ptr(b, op.b, c);
+	const int Pw = is_root ? 0 : b.P, Pa = a_tip ? 0 : b.P, Pb = b_tip ? 0 : b.P;  // P = 0 switches an operand's loads off
 	double *Ua = b.upper + ((size_t)op.a * b.C + c) * (size_t)b.P * S;
 	double *Ub = b.upper + ((size_t)op.b * b.C + c) * (size_t)b.P * S;
 	const int ntiles = (b.P + TP - 1) / TP;
 	double tot_a = 0.0, tot_b = 0.0;
-
-	auto store = [&](double *U, int p0, const double (&v)[MT][NTW][2]) {
-#pragma unroll
-		for (int m = 0; m < MT; m++) {
-			const int p = p0 + 8 * m + r;
-			if (p >= b.P) continue;
-			double *row = U + (size_t)p * S;
-#pragma unroll
-			for (int j = 0; j < NTW; j++) {
-				const int i = (n0 + j) * 8 + 2 * q;
-				if (S % 2 == 0) {
-					if (i < S) *reinterpret_cast<double2 *>(row + i) = make_double2(v[m][j][0], v[m][j][1]);
-				} else {
-					if (i < S) row[i] = v[m][j][0];
-					if (i + 1 < S) row[i + 1] = v[m][j][1];
-				}
-			}
+	double cw[MT][Sh::KCH], ca[MT][Sh::KCH], cb[MT][Sh::KCH];
+	{
+		const int p0 = blockIdx.x * TP + wm * MT * 8;
+		load_chunk<Sh, MT>(xw, p0, Pw, lane, 0, cw);
+		load_chunk<Sh, MT>(xb, p0, Pb, lane, 0, cb);
+		load_chunk<Sh, MT>(xa, p0, Pa, lane, 0, ca);
+	}
+	mbar_wait(bar, 0);  // matrices have landed (the first A fragments are already in flight)
+	// B fragments run one (k-step, n-tile) ahead of the tensor pipe: the LDS of step u + 1 is issued before the DMMAs of step u
+	double bP = 0.0, bA = 0.0, bB = 0.0, bdA = 0.0, bdB = 0.0;
+	{
+		const int off = (n0 * 8 + r) * Sh::LD + q;
+		if (!is_root) bP = mP[off];
+		if (!b_tip) {
+			bB = mB[off];
+			if (GRAD) bdB = dB[off];
 		}
-	};
-
+		if (!a_tip) {
+			bA = mA[off];
+			if (GRAD) bdA = dA[off];
+		}
+	}
 	for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 		const int p0 = tile * TP + wm * MT * 8;
-		double W[MT][NTW][2];
-		double fw[MT][Sh::KT], fa[MT][Sh::KT], fb[MT][Sh::KT];
-		// every global load of the tile is issued before the first product
-		if (!is_root) load_a<Sh, MT>(xw, p0, b.P, lane, fw);
-		if (!b_tip) load_a<Sh, MT>(xb, p0, b.P, lane, fb);
-		if (!a_tip) load_a<Sh, MT>(xa, p0, b.P, lane, fa);
+		// w_k and log L_k of this tile's patterns: requested now, consumed in the epilogue
+		double wk[MT], lk[MT];
+		if (GRAD) {
+#pragma unroll
+			for (int m = 0; m < MT; m++) {
+				const int p = p0 + 8 * m + r;
+				wk[m] = p < b.P ? __ldg(weights + p) : 0.0;
+				lk[m] = p < b.P ? __ldg(pattern_lnl + p) : 0.0;
+			}
+		}
+		double W[MT][NTW][2], Mb[MT][NTW][2], Db[MT][NTW][2], Ma[MT][NTW][2], Da[MT][NTW][2];
+		zero_acc<MT, NTW>(W);
+		zero_acc<MT, NTW>(Mb);
+		zero_acc<MT, NTW>(Ma);
+		if (GRAD) {
+			zero_acc<MT, NTW>(Db);
+			zero_acc<MT, NTW>(Da);
+		}
+#pragma unroll
+		for (int ch = 0; ch < Sh::NCH; ch++) {
+			double nw[MT][Sh::KCH], na[MT][Sh::KCH], nb[MT][Sh::KCH];
+			const bool last = ch == Sh::NCH - 1;
+			const int np0 = last ? p0 + (int)gridDim.x * TP : p0;  // past the end => all loads predicated off
+			const int nch = last ? 0 : ch + 1;
+			load_chunk<Sh, MT>(xw, np0, Pw, lane, nch, nw);
+			load_chunk<Sh, MT>(xb, np0, Pb, lane, nch, nb);
+			load_chunk<Sh, MT>(xa, np0, Pa, lane, nch, na);
+			__syncwarp();  // scheduling fence: keeps the prefetch loads above this chunk's tensor work
+#pragma unroll
+			for (int tt = 0; tt < Sh::KCH; tt++) {
+				const int t = ch * Sh::KCH + tt;
+				if (t < Sh::KT) {
+#pragma unroll
+					for (int j = 0; j < NTW; j++) {
+						// B fragments of the NEXT (k-step, n-tile) first, then this step's DMMAs (wraps into the next tile)
+						const int nj = j + 1 < NTW ? j + 1 : 0, nt = j + 1 < NTW ? t : (t + 1 < Sh::KT ? t + 1 : 0);
+						const int noff = ((n0 + nj) * 8 + r) * Sh::LD + 4 * nt + q;
+						double nP = 0.0, nA = 0.0, nB = 0.0, ndA = 0.0, ndB = 0.0;
+						if (!is_root) nP = mP[noff];
+						if (!b_tip) {
+							nB = mB[noff];
+							if (GRAD) ndB = dB[noff];
+						}
+						if (!a_tip) {
+							nA = mA[noff];
+							if (GRAD) ndA = dA[noff];
+						}
+						if (!is_root) {
+#pragma unroll
+							for (int m = 0; m < MT; m++) dmma_m8n8k4(W[m][j][0], W[m][j][1], cw[m][tt], bP);
+						}
+						if (!b_tip) {
+#pragma unroll
+							for (int m = 0; m < MT; m++) dmma_m8n8k4(Mb[m][j][0], Mb[m][j][1], cb[m][tt], bB);
+							if (GRAD) {
+#pragma unroll
+								for (int m = 0; m < MT; m++) dmma_m8n8k4(Db[m][j][0], Db[m][j][1], cb[m][tt], bdB);
+							}
+						}
+						if (!a_tip) {
+#pragma unroll
+							for (int m = 0; m < MT; m++) dmma_m8n8k4(Ma[m][j][0], Ma[m][j][1], ca[m][tt], bA);
+							if (GRAD) {
+#pragma unroll
+								for (int m = 0; m < MT; m++) dmma_m8n8k4(Da[m][j][0], Da[m][j][1], ca[m][tt], bdA);
+							}
+						}
+						bP = nP, bA = nA, bB = nB, bdA = ndA, bdB = ndB;
+					}
+				}
+			}
+			copy_chunk<Sh, MT>(cw, nw);
+			copy_chunk<Sh, MT>(cb, nb);
+			copy_chunk<Sh, MT>(ca, na);
+		}
 		if (is_root) {
 #pragma unroll
 			for (int m = 0; m < MT; m++)
@@ -273,38 +434,29 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 					const int i = (n0 + j) * 8 + 2 * q;
 					W[m][j][0] = wroot[i], W[m][j][1] = wroot[i + 1];
 				}
-		} else {
-			gemm<Sh, MT, NTW>(mP, n0, lane, fw, W);
 		}
-		// child b: M_b, D_b  ->  U_a = W o M_b (stored), Y_b = f o W o D_b (kept for g_b = sum Y_b M_a)
-		double X[MT][NTW][2], Y[MT][NTW][2];
 		if (b_tip) {
 			const uint8_t *st = b.tip_states + (size_t)op.b * b.P;
-			tip_gather<Sh, MT, NTW, true>(st, mB, nullptr, p0, b.P, n0, lane, X);
-			if (GRAD) tip_gather<Sh, MT, NTW, false>(st, dB, rsB, p0, b.P, n0, lane, Y);
-		} else {
-			gemm<Sh, MT, NTW>(mB, n0, lane, fb, X);
-			if (GRAD) gemm<Sh, MT, NTW>(dB, n0, lane, fb, Y);
+			tip_gather<Sh, MT, NTW, true>(st, mB, nullptr, p0, b.P, n0, lane, Mb);
+			if (GRAD) tip_gather<Sh, MT, NTW, false>(st, dB, rsB, p0, b.P, n0, lane, Db);
 		}
-#pragma unroll
-		for (int m = 0; m < MT; m++)
-#pragma unroll
-			for (int j = 0; j < NTW; j++) {
-				const int i = (n0 + j) * 8 + 2 * q;
-				X[m][j][0] *= W[m][j][0], X[m][j][1] *= W[m][j][1];  // X = U_a
-				if (GRAD) Y[m][j][0] *= fq[i] * W[m][j][0], Y[m][j][1] *= fq[i + 1] * W[m][j][1];
-			}
-		if (!a_leaf || !GRAD) store(Ua, p0, X);
-		// child a: M_a, D_a  ->  U_b = W o M_a (stored), g_a = sum f U_a D_a, g_b = sum Y_b M_a
-		double Ma[MT][NTW][2], Da[MT][NTW][2];
 		if (a_tip) {
 			const uint8_t *st = b.tip_states + (size_t)op.a * b.P;
 			tip_gather<Sh, MT, NTW, true>(st, mA, nullptr, p0, b.P, n0, lane, Ma);
 			if (GRAD) tip_gather<Sh, MT, NTW, false>(st, dA, rsA, p0, b.P, n0, lane, Da);
-		} else {
-			gemm<Sh, MT, NTW>(mA, n0, lane, fa, Ma);
-			if (GRAD) gemm<Sh, MT, NTW>(dA, n0, lane, fa, Da);
 		}
+		// U_a = W o M_b, U_b = W o M_a (in place), g_a = sum f U_a D_a, g_b = sum f U_b D_b
+#pragma unroll
+		for (int m = 0; m < MT; m++)
+#pragma unroll
+			for (int j = 0; j < NTW; j++) {
+				const double ua0 = W[m][j][0] * Mb[m][j][0], ua1 = W[m][j][1] * Mb[m][j][1];
+				const double ub0 = W[m][j][0] * Ma[m][j][0], ub1 = W[m][j][1] * Ma[m][j][1];
+				Mb[m][j][0] = ua0, Mb[m][j][1] = ua1;
+				Ma[m][j][0] = ub0, Ma[m][j][1] = ub1;
+			}
+		if (!a_leaf || !GRAD) store_tile<Sh, MT, NTW>(Ua, p0, b.P, n0, lane, Mb);
+		if (!b_leaf || !GRAD) store_tile<Sh, MT, NTW>(Ub, p0, b.P, n0, lane, Ma);
 		if (GRAD) {
 #pragma unroll
 			for (int m = 0; m < MT; m++) {
@@ -312,23 +464,17 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 #pragma unroll
 				for (int j = 0; j < NTW; j++) {
 					const int i = (n0 + j) * 8 + 2 * q;
-					ga = fma(fq[i] * X[m][j][0], Da[m][j][0], fma(fq[i + 1] * X[m][j][1], Da[m][j][1], ga));
-					gb = fma(Y[m][j][0], Ma[m][j][0], fma(Y[m][j][1], Ma[m][j][1], gb));
+					ga = fma(fq[i] * Mb[m][j][0], Da[m][j][0], fma(fq[i + 1] * Mb[m][j][1], Da[m][j][1], ga));
+					gb = fma(fq[i] * Ma[m][j][0], Db[m][j][0], fma(fq[i + 1] * Ma[m][j][1], Db[m][j][1], gb));
 				}
 				// the four lanes of a quad hold one pattern's columns
 				ga += __shfl_xor_sync(0xffffffffu, ga, 1), gb += __shfl_xor_sync(0xffffffffu, gb, 1);
 				ga += __shfl_xor_sync(0xffffffffu, ga, 2), gb += __shfl_xor_sync(0xffffffffu, gb, 2);
-				const int p = p0 + 8 * m + r;
-				const double wl = p < b.P ? weights[p] / exp(pattern_lnl[p]) : 0.0;  // w_k / L_k (treelikelihood.c:3207-3210)
+				const double wl = wk[m] / exp(lk[m]);  // w_k / L_k (treelikelihood.c:3207-3210); padding patterns carry w = 0
 				tot_a = fma(ga, wl, tot_a);
 				tot_b = fma(gb, wl, tot_b);
 			}
 		}
-#pragma unroll
-		for (int m = 0; m < MT; m++)
-#pragma unroll
-			for (int j = 0; j < NTW; j++) Ma[m][j][0] *= W[m][j][0], Ma[m][j][1] *= W[m][j][1];  // U_b
-		if (!b_leaf || !GRAD) store(Ub, p0, Ma);
 	}
 	if (GRAD) {
 		// every quad lane carries the same row value: sum lanes with q == 0 over the 8 rows, then across warps (fixed order)
@@ -339,8 +485,8 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 		if (threadIdx.x == 0) {
 			double sa = 0.0, sb = 0.0;
 			for (int w = 0; w < NWARPS; w++) sa += red[2 * w], sb += red[2 * w + 1];
-			partial[((size_t)op.a * b.C + c) * gridDim.x + blockIdx.x] = sa;
-			partial[((size_t)op.b * b.C + c) * gridDim.x + blockIdx.x] = sb;
+			partial[((size_t)op.a * b.C + c) * pstride + blockIdx.x] = sa;
+			partial[((size_t)op.b * b.C + c) * pstride + blockIdx.x] = sb;
 		}
 	}
 }
@@ -366,11 +512,21 @@ bool phbc_dmma_supported(const phbc_ctx *ctx, const phbc_eval_opts *o) {
 	return ctx->S == 20 || ctx->S == 61;
 }
 
-// pattern chunks per launch: enough CTAs for ~4 waves, never more than the tile count
-static int chunk_count(const phbc_ctx *ctx, int ntiles, int ctas_per_chunk) {
-	int want = (4 * ctx->num_sms + ctas_per_chunk - 1) / ctas_per_chunk;
-	if (want < 1) want = 1;
-	return want < ntiles ? want : ntiles;
+// Pattern chunks for one launch of `units` = C x ops (op, category) pairs on `slots` resident CTA slots: the chunk count whose
+// CTA total fills whole waves best, at most ~4 waves (every CTA pays the matrix staging once), never more than the tile count.
+static int pick_chunks(int slots, int units, int ntiles) {
+	int kmax = (4 * slots) / units;
+	if (kmax < 1) kmax = 1;
+	if (kmax > ntiles) kmax = ntiles;
+	int best = 1;
+	double best_eff = 0.0;
+	for (int k = 1; k <= kmax; k++) {
+		const long long ctas = (long long)units * k;
+		const long long waves = (ctas + slots - 1) / slots;
+		const double eff = (double)ctas / (double)(waves * slots);
+		if (eff > best_eff + 1e-9) best_eff = eff, best = k;
+	}
+	return best;
 }
 
 template <int S>
@@ -381,17 +537,33 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	int rc;
 	if ((rc = phbc_generic_prepare(ctx, o))) return rc;
 	Bufs b = phbc_make_bufs(ctx);
+	// packed matrix images [P | dP][node][category][IMG]
+	const size_t img_bytes = (size_t)2 * N * C * Sh::IMG * sizeof(double);
+	if (img_bytes > ctx->dmma_img_bytes) {
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		if (ctx->d_dmma_img) cudaFree(ctx->d_dmma_img);
+		ctx->d_dmma_img = NULL;
+		ctx->dmma_img_bytes = 0;
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_dmma_img, img_bytes));
+		ctx->dmma_img_bytes = img_bytes;
+	}
+	k_dmma_pack<Sh><<<dim3(N, C, 2), 128, 0, ctx->stream>>>(ctx->T, N, C, ctx->tip_kind == PHBC_TIP_STATES, ctx->d_P, ctx->d_dP, ctx->d_dmma_img);
+	ctx->launches++;
 	auto lower = k_dmma_lower<S, Cf::MT, Cf::NSPLIT, Cf::WM>;
-	const size_t lsmem = 2 * Sh::MAT * sizeof(double);
+	const size_t lsmem = 128 + 2 * Sh::IMG * sizeof(double);
 	PHBC_CHECK(cudaFuncSetAttribute(lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
 	const int lthreads = 32 * Cf::WM * Cf::NSPLIT, ltiles = (P + Cf::WM * Cf::MT * 8 - 1) / (Cf::WM * Cf::MT * 8);
+	int lper_sm = 1;
+	PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lper_sm, lower, lthreads, lsmem));
+	if (lper_sm < 1) lper_sm = 1;
 	if ((rc = phbc_time_begin(ctx))) return rc;
 	for (int l = 0; l < ctx->n_lower_levels; l++) {
 		const int beg = ctx->h_lower_level_off[l], cnt = ctx->h_lower_level_off[l + 1] - beg;
 		if (cnt <= 0) continue;
 		for (int z0 = 0; z0 < cnt; z0 += 65535) {
 			const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
-			lower<<<dim3(chunk_count(ctx, ltiles, C * zc), C, zc), lthreads, lsmem, ctx->stream>>>(b, ctx->d_lower_ops + beg + z0, ctx->d_P);
+			lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ltiles), C, zc), lthreads, lsmem, ctx->stream>>>(b, ctx->d_lower_ops + beg + z0,
+			                                                                                                     ctx->d_dmma_img);
 			ctx->launches++;
 		}
 		if (o->scale && (rc = phbc_generic_scale_ops(ctx, ctx->d_lower_ops + beg, cnt, o->scaling_threshold))) return rc;
@@ -400,22 +572,33 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	if ((rc = phbc_generic_root(ctx, o, result))) return rc;
 	if (o->want_gradient) {
 		const bool grad = !o->scale;  // fused reductions use the unscaled form
-		auto upper_g = k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, true>;
-		auto upper_u = k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, false>;
+		auto upper = grad ? k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, true> : k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, false>;
 		const int uwarps = Cf::UWM * Cf::UNSPLIT;
-		const size_t usmem = ((grad ? 5 : 3) * Sh::MAT + 4 * Sh::NP + 2 * uwarps) * sizeof(double);
-		PHBC_CHECK(cudaFuncSetAttribute(grad ? upper_g : upper_u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
+		const size_t usmem = 128 + ((grad ? 5 : 3) * Sh::IMG + 2 * Sh::NP + 2 * uwarps) * sizeof(double);
+		PHBC_CHECK(cudaFuncSetAttribute(upper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
 		const int uthreads = 32 * uwarps, utiles = (P + Cf::UWM * Cf::UMT * 8 - 1) / (Cf::UWM * Cf::UMT * 8);
-		// one chunk count for the whole pass: the per-CTA gradient partials are laid out [N][C][chunks]
-		int chunks = chunk_count(ctx, utiles, C);
-		if ((rc = phbc_ensure_scratch(ctx, (size_t)N * C * chunks * sizeof(double)))) return rc;
+		int uper_sm = 1;
+		PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&uper_sm, upper, uthreads, usmem));
+		if (uper_sm < 1) uper_sm = 1;
+		const int uslots = uper_sm * ctx->num_sms;
+		// per-CTA gradient partials are laid out [N][C][pstride]; levels launch different chunk counts, unused entries stay zero
+		int pstride = 1;
+		for (int l = 0; l < ctx->n_upper_levels; l++) {
+			const int cnt = ctx->h_parent_level_off[l + 1] - ctx->h_parent_level_off[l];
+			for (int z0 = 0; z0 < cnt; z0 += 65535) {
+				const int k = pick_chunks(uslots, C * (cnt - z0 < 65535 ? cnt - z0 : 65535), utiles);
+				if (k > pstride) pstride = k;
+			}
+		}
+		if ((rc = phbc_ensure_scratch(ctx, (size_t)N * C * pstride * sizeof(double)))) return rc;
+		if (grad) PHBC_CHECK(cudaMemsetAsync(ctx->d_scratch, 0, (size_t)N * C * pstride * sizeof(double), ctx->stream));
 		for (int l = 0; l < ctx->n_upper_levels; l++) {
 			const int beg = ctx->h_parent_level_off[l], cnt = ctx->h_parent_level_off[l + 1] - beg;
 			if (cnt > 0) {
 				for (int z0 = 0; z0 < cnt; z0 += 65535) {
 					const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
-					(grad ? upper_g : upper_u)<<<dim3(chunks, C, zc), uthreads, usmem, ctx->stream>>>(
-					    b, ctx->d_parent_ops + beg + z0, ctx->d_P, ctx->d_dP, ctx->d_freqs, ctx->d_weights, ctx->d_pattern_lnl, o->include_root_freqs,
+					upper<<<dim3(pick_chunks(uslots, C * zc, utiles), C, zc), uthreads, usmem, ctx->stream>>>(
+					    b, ctx->d_parent_ops + beg + z0, ctx->d_dmma_img, ctx->d_freqs, ctx->d_weights, ctx->d_pattern_lnl, o->include_root_freqs, pstride,
 					    ctx->d_scratch);
 					ctx->launches++;
 				}
@@ -425,7 +608,7 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 			if (o->scale && ucnt > 0 && (rc = phbc_generic_scale_ops(ctx, ctx->d_upper_ops + ubeg, ucnt, o->scaling_threshold))) return rc;
 		}
 		if (grad) {
-			if ((rc = phbc_gradient_from_partials(ctx, chunks, result))) return rc;
+			if ((rc = phbc_gradient_from_partials(ctx, pstride, result))) return rc;
 		} else {
 			if ((rc = phbc_generic_gradient(ctx, o, result))) return rc;
 		}

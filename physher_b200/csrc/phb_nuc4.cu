@@ -37,6 +37,8 @@ struct Nuc4Params {
 	int T, N, C, P, PB, root;
 	int n_post, n_pre, nslots, ntiles;
 	int include_root_freqs, compat;
+	int nbatch, phases;                   // branch-length samples sharing one launch; samples one CTA can touch
+	long long mats_stride;                // doubles between the walk matrices of consecutive samples
 	int post_first_tips, pre_first_tips;  // tip count of chunk 0 of each walk
 	double threshold;
 	const uint8_t *tip_codes;  // [2 walks][tiles][T][PB], rows in walk order
@@ -47,48 +49,14 @@ struct Nuc4Params {
 	const double *post_mats;  // [n_post][2][C][16]
 	const double *pre_mats;   // [n_pre][3][C][16]
 	double *lower;            // [grid][n_post][C][PB][4]
-	double *gacc;             // [grid][warps][N]
-	double *cta_lnl;          // [grid]
+	double *gacc;             // [grid][phases][warps][N]
+	double *cta_lnl;          // [grid][phases][warps]
 	double *pattern_lnl;      // [P]
 	double freqs[4];
 	double fq[4];     // weights of the gradient numerator: pi, or 1 when the root frequencies are folded into the uppers
 	double wroot[4];  // upper message entering the root's children: 1, or pi (tlk->include_root_freqs)
 	double Q[16];
 };
-
-// ---------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier + TMA bulk copy (global -> shared)
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-	             "l"(src), "r"(bytes), "r"(smem_u32(bar))
-	             : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-	uint32_t done;
-	do {
-		asm volatile(
-		    "{\n"
-		    ".reg .pred p;\n"
-		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-		    "selp.u32 %0, 1, 0, p;\n"
-		    "}\n"
-		    : "=r"(done)
-		    : "r"(smem_u32(bar)), "r"(parity)
-		    : "memory");
-	} while (!done);
-}
-__device__ __forceinline__ void red_add_f64(double *addr, double v) {
-	asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
-}
 
 // ---------------------------------------------------------------------------------------------
 // small dense helpers (everything in registers)
@@ -207,9 +175,31 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 	const double prop_c = (C == 1) ? 1.0 : prm.props[c];
 	double cta_lnl = 0.0;
 	unsigned char *row_cell = GRAD ? reinterpret_cast<unsigned char *>(prm.lower) + (size_t)blockIdx.x * prm.n_post * NUC4_ROW_BYTES + tid * 16 : nullptr;
-	double *my_gacc = GRAD ? prm.gacc + ((size_t)blockIdx.x * (NUC4_NT / 32) + warp) * prm.N : nullptr;
+	double *my_gacc = nullptr;
 
-	for (int tile = blockIdx.x; tile < prm.ntiles; tile += gridDim.x) {
+	// work items = (sample, pattern tile), sample-major; a CTA owns a CONTIGUOUS range, so it touches at most
+	// prm.phases consecutive samples and keeps one private accumulator row set per touched sample (deterministic sums)
+	const long long nitems = (long long)prm.ntiles * prm.nbatch;
+	// (a single sample keeps the strided assignment: tiles are few and coarse, and the strided order spreads the CTAs that
+	// get one tile more evenly over the SMs)
+	const bool strided = prm.nbatch == 1;
+	const int item0 = strided ? (int)blockIdx.x : (int)(blockIdx.x * nitems / gridDim.x);
+	const int item1 = strided ? (int)nitems : (int)((blockIdx.x + 1) * nitems / gridDim.x);
+	const int item_step = strided ? (int)gridDim.x : 1;
+	const int b_first = strided ? 0 : item0 / prm.ntiles;
+	int cur_b = -1;
+	auto flush_lnl = [&](int b) {
+		if (lane == 0) prm.cta_lnl[((size_t)blockIdx.x * prm.phases + (b - b_first)) * (NUC4_NT / 32) + warp] = (c == 0) ? cta_lnl : 0.0;  // one partial lnL per warp
+	};
+
+	for (int item = item0; item < item1; item += item_step) {
+		const int bsmp = item / prm.ntiles, tile = item - bsmp * prm.ntiles;
+		if (bsmp != cur_b) {
+			if (cur_b >= 0) flush_lnl(cur_b);
+			cur_b = bsmp;
+			cta_lnl = 0.0;
+			if (GRAD) my_gacc = prm.gacc + (((size_t)blockIdx.x * prm.phases + (bsmp - b_first)) * (NUC4_NT / 32) + warp) * prm.N;
+		}
 		const int p = tile * PB + pl;
 		const bool live = p < prm.P;
 		const uint8_t *tile_codes_post = prm.tip_codes + (size_t)tile * prm.T * PB;
@@ -229,7 +219,7 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 				const uint32_t cbytes = (tips & 31) * PB;
 				mbar_expect_tx(&bars[ld & 1], dbytes + mbytes + cbytes);
 				bulk_g2s(dst + lay.desc_off, prm.post_ops + first, dbytes, &bars[ld & 1]);
-				bulk_g2s(dst + lay.mat_off, prm.post_mats + (size_t)first * 2 * C * 16, mbytes, &bars[ld & 1]);
+				bulk_g2s(dst + lay.mat_off, prm.post_mats + (size_t)cur_b * prm.mats_stride + (size_t)first * 2 * C * 16, mbytes, &bars[ld & 1]);
 				if (cbytes) bulk_g2s(dst + lay.code_off, tile_codes_post + (size_t)(tips >> 5) * PB, cbytes, &bars[ld & 1]);
 			};
 			if (tid == 0) issue(0, loads, prm.post_first_tips);
@@ -306,7 +296,7 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 				double plk = log(L);
 				if (SCALE) plk += sf_acc;
 				const double w = live ? prm.weights[p] : 0.0;
-				if (live) prm.pattern_lnl[p] = plk;
+				if (live && prm.nbatch == 1) prm.pattern_lnl[p] = plk;
 				invLw[pl] = w / L;  // unscaled path: w_k / L_k; scaled paths use ratios instead
 				double v = live ? plk * w : 0.0;
 				v = phb_warp_sum(v);
@@ -328,7 +318,7 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 				const uint32_t cbytes = (tips & 31) * PB;
 				mbar_expect_tx(&bars[ld & 1], dbytes + mbytes + cbytes);
 				bulk_g2s(dst + lay.desc_off, prm.pre_ops + first, dbytes, &bars[ld & 1]);
-				bulk_g2s(dst + lay.mat_off, prm.pre_mats + (size_t)first * 3 * C * 16, mbytes, &bars[ld & 1]);
+				bulk_g2s(dst + lay.mat_off, prm.pre_mats + (size_t)cur_b * prm.mats_stride + (size_t)first * 3 * C * 16, mbytes, &bars[ld & 1]);
 				if (cbytes) bulk_g2s(dst + lay.code_off, tile_codes_pre + (size_t)(tips >> 5) * PB, cbytes, &bars[ld & 1]);
 			};
 			// lower rows of the internal children of one op (kind: 0 tip-tip, 1 tip-internal, 2 internal-internal)
@@ -456,7 +446,7 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 			}
 		}
 	}
-	if (lane == 0) prm.cta_lnl[(size_t)blockIdx.x * (NUC4_NT / 32) + warp] = (c == 0) ? cta_lnl : 0.0;  // one partial lnL per warp
+	if (cur_b >= 0) flush_lnl(cur_b);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -466,10 +456,14 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 __global__ void k_nuc4_matrices(int C, int root, int n_post, int n_pre, const phbc_post_op *__restrict__ post_ops,
                                 const phbc_pre_op *__restrict__ pre_ops, const double *__restrict__ evec,
                                 const double *__restrict__ eval, const double *__restrict__ ivec, const double *__restrict__ bl,
-                                const double *__restrict__ rates, double *__restrict__ post_mats, double *__restrict__ pre_mats) {
+                                const double *__restrict__ rates, double *__restrict__ post_mats, double *__restrict__ pre_mats, int N,
+                                long long mats_stride) {
 	const int e = blockIdx.x * blockDim.x + threadIdx.x;
 	const int total = (2 * n_post + 3 * n_pre) * C;
 	if (e >= total) return;
+	bl += (size_t)blockIdx.y * N;  // one branch-length vector and one matrix set per sample
+	post_mats += (size_t)blockIdx.y * mats_stride;
+	pre_mats += (size_t)blockIdx.y * mats_stride;
 	const int c = e % C;
 	const int m = e / C;
 	int node;
@@ -540,53 +534,86 @@ __global__ void k_nuc4_encode_tips(int T, int P, int PB, int ntiles, int tip_kin
 	codes[i] = (uint8_t)code;
 }
 
-// fixed-order final sums: lnL and cat_grad[n][c] from the per-CTA / per-warp partials.
-// grid (ceil(N/32), C), block (32, 8): x = node, y strides over the CTAs of the walk launch.
-__global__ void k_nuc4_finalize(int N, int C, int PB, int grid, int root, const double *__restrict__ cta_lnl,
-                                const double *__restrict__ gacc, int want_grad, double *__restrict__ cat_grad,
-                                double *__restrict__ result) {
-	__shared__ double red[8][33];
-	const int warps = NUC4_NT / 32, wpc = PB / 32;
+// fixed-order final sums per sample: lnL, cat_grad[n][c] and d lnL / d bl (A11, treelikelihood.c:3129-3143) from the per-CTA /
+// per-warp partials.  grid (ceil(N/32), nbatch), block (32, NUC4_FY): x = node, y strides over the CTAs of the walk launch
+// that touched the sample (all of them for a single sample; contiguous item ranges for a batch, see k_nuc4_walk).
+#define NUC4_FY 16
+__global__ void __launch_bounds__(32 * NUC4_FY) k_nuc4_finalize(int N, int C, int PB, int grid, int phases, int ntiles, int nbatch, int root,
+                                                                const double *__restrict__ cta_lnl, const double *__restrict__ gacc, int want_grad,
+                                                                const double *__restrict__ props, const double *__restrict__ rates,
+                                                                double *__restrict__ cat_grad, double *__restrict__ result) {
+	constexpr int warps = NUC4_NT / 32;
+	__shared__ double red[NUC4_FY][warps][33];
+	const int wpc = PB / 32;
 	const int tx = threadIdx.x, ty = threadIdx.y;
-	if (blockIdx.x == 0 && blockIdx.y == 0) {
+	const int b = blockIdx.y;
+	const long long nitems = (long long)ntiles * nbatch;
+	const long long lo = (long long)b * ntiles, hi = lo + ntiles;  // items of this sample
+	// CTAs whose item range [c * nitems / grid, (c + 1) * nitems / grid) intersects [lo, hi); one sample: every CTA, phase 0
+	int c_lo = 0, c_hi = grid;
+	if (nbatch > 1) {
+		c_lo = (int)(lo * grid / nitems);
+		c_hi = (int)((hi * grid + nitems - 1) / nitems) + 1;
+		while (c_lo > 0 && (long long)c_lo * nitems / grid > lo) c_lo--;
+		if (c_hi > grid) c_hi = grid;
+	}
+	result += (size_t)b * (1 + N);
+	cat_grad += (size_t)b * N * C;
+	auto phase_of = [&](int cta) -> int {  // -1 when the CTA did not touch this sample
+		if (nbatch == 1) return 0;
+		const long long i0 = (long long)cta * nitems / grid, i1 = (long long)(cta + 1) * nitems / grid;
+		if (i1 <= lo || i0 >= hi || i1 <= i0) return -1;
+		return b - (int)(i0 / ntiles);
+	};
+	if (blockIdx.x == 0) {
 		double s = 0.0;
-		for (int i = ty * 32 + tx; i < grid * warps; i += 256) s += cta_lnl[i];
+		for (int cta = c_lo + ty; cta < c_hi; cta += NUC4_FY) {
+			const int ph = phase_of(cta);
+			if (ph >= 0 && tx < warps) s += cta_lnl[((size_t)cta * phases + ph) * warps + tx];
+		}
 		s = phb_warp_sum(s);
-		if (tx == 0) red[ty][32] = s;
+		if (tx == 0) red[ty][0][32] = s;
 		__syncthreads();
 		if (tx == 0 && ty == 0) {
 			double tot = 0.0;
-			for (int k = 0; k < 8; k++) tot += red[k][32];
+			for (int k = 0; k < NUC4_FY; k++) tot += red[k][0][32];
 			result[0] = tot;
 		}
+		__syncthreads();
 	}
 	if (!want_grad) return;
-	const int n = blockIdx.x * 32 + tx, c = blockIdx.y;
-	double s = 0.0;
+	const int n = blockIdx.x * 32 + tx;
+	double s8[warps];
+#pragma unroll
+	for (int w = 0; w < warps; w++) s8[w] = 0.0;
 	if (n < N && n != root)
-		for (int b = ty; b < grid; b += 8)
-			for (int w = 0; w < wpc; w++) s += gacc[((size_t)b * warps + c * wpc + w) * N + n];
-	red[ty][tx] = s;
+		for (int cta = c_lo + ty; cta < c_hi; cta += NUC4_FY) {
+			const int ph = phase_of(cta);
+			if (ph < 0) continue;
+			const double *base = gacc + ((size_t)cta * phases + ph) * warps * N + n;
+#pragma unroll
+			for (int w = 0; w < warps; w++) s8[w] += base[(size_t)w * N];  // 8 independent loads in flight
+		}
+#pragma unroll
+	for (int w = 0; w < warps; w++) red[ty][w][tx] = s8[w];
+	__syncthreads();
+	if (ty < warps) {  // thread row w sums warp-row w over the CTA slices, fixed order
+		double tot = 0.0;
+		for (int k = 0; k < NUC4_FY; k++) tot += red[k][ty][tx];
+		red[0][ty][tx] = tot;  // slice 0 of row ty is read only by this thread above
+	}
 	__syncthreads();
 	if (ty == 0 && n < N) {
-		double tot = 0.0;
-		for (int k = 0; k < 8; k++) tot += red[k][tx];
-		cat_grad[(size_t)n * C + c] = tot;
+		double g = 0.0;
+		for (int c = 0; c < C; c++) {
+			double tot = 0.0;
+			for (int w = 0; w < wpc; w++) tot += red[0][c * wpc + w][tx];
+			cat_grad[(size_t)n * C + c] = tot;
+			if (C == 1) g = tot;
+			else g = c == 0 ? tot * props[0] * rates[0] : g + tot * props[c] * rates[c];
+		}
+		result[1 + n] = g;
 	}
-}
-
-__global__ void k_collapse_categories_nuc4(int N, int C, const double *__restrict__ cat_grad, const double *__restrict__ props,
-                                           const double *__restrict__ rates, double *__restrict__ result) {
-	const int n = blockIdx.x * blockDim.x + threadIdx.x;
-	if (n >= N) return;
-	double g;
-	if (C == 1) {
-		g = cat_grad[n];
-	} else {
-		g = cat_grad[(size_t)n * C] * props[0] * rates[0];
-		for (int c = 1; c < C; c++) g += cat_grad[(size_t)n * C + c] * props[c] * rates[c];
-	}
-	result[1 + n] = g;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -637,7 +664,16 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		ctx->nuc4_codes_bad = bad != 0;
 		ctx->nuc4_codes_valid = true;
 	}
-	if (ctx->nuc4_codes_bad) return phbc_generic_evaluate(ctx, o);  // non 0/1 tip partials: node-at-a-time kernels
+	if (ctx->nuc4_codes_bad) {  // non 0/1 tip partials: node-at-a-time kernels, one sample at a time
+		phbc_eval_opts one = *o;
+		one.batch_count = 1;
+		for (int b = 0; b < (o->batch_count > 1 ? o->batch_count : 1); b++) {
+			one.batch_index = o->batch_index + b;
+			const int rc = phbc_generic_evaluate(ctx, &one);
+			if (rc) return rc;
+		}
+		return 0;
+	}
 
 	// launch geometry: persistent CTAs, two per SM when shared memory allows
 	typedef void (*walk_fn)(const Nuc4Params);
@@ -656,15 +692,28 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "nuc4 walk kernel does not fit on an SM (smem %zu)", smem);
 		return -1;
 	}
+	const int nbatch = o->batch_count > 1 ? o->batch_count : 1;
+	const long long nitems = (long long)ntiles * nbatch;
 	int grid = per_sm * ctx->num_sms;
-	if (grid > ntiles) grid = ntiles;
+	if (grid > nitems) grid = (int)nitems;
+	// samples one CTA can touch: its contiguous item range [c * nitems / grid, (c + 1) * nitems / grid)
+	int phases = 1;
+	for (int cta = 0; cta < grid; cta++) {
+		const long long i0 = cta * nitems / grid, i1 = (cta + 1) * nitems / grid;
+		if (i1 > i0) {
+			const int ph = (int)((i1 - 1) / ntiles - i0 / ntiles) + 1;
+			if (ph > phases) phases = ph;
+		}
+	}
 	const int warps = NUC4_NT / 32;
-	// scratch: walk matrices, per-CTA lower rows, per-warp gradient rows, per-warp lnL
-	const size_t mats_bytes = (size_t)(2 * ctx->n_post + 3 * ctx->n_pre) * C * 16 * sizeof(double);
+	// scratch: walk matrices per sample, per-CTA lower rows, per-(CTA, sample phase, warp) gradient rows and lnL
+	const long long mats_stride = (long long)(2 * ctx->n_post + 3 * ctx->n_pre) * C * 16;
+	const size_t mats_bytes = (size_t)mats_stride * nbatch * sizeof(double);
 	if (mats_bytes > ctx->walk_mats_bytes) {
 		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 		if (ctx->d_walk_mats) cudaFree(ctx->d_walk_mats);
 		ctx->d_walk_mats = NULL;
+		ctx->walk_mats_bytes = 0;
 		PHBC_CHECK(cudaMalloc((void **)&ctx->d_walk_mats, mats_bytes));
 		ctx->walk_mats_bytes = mats_bytes;
 	}
@@ -674,33 +723,45 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 			PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 			if (ctx->d_walk_lower) cudaFree(ctx->d_walk_lower);
 			ctx->d_walk_lower = NULL;
+			ctx->walk_lower_bytes = 0;
 			PHBC_CHECK(cudaMalloc((void **)&ctx->d_walk_lower, lower_bytes));
 			ctx->walk_lower_bytes = lower_bytes;
 		}
-		const size_t gacc_bytes = (size_t)grid * warps * N * sizeof(double);
+		const size_t gacc_bytes = (size_t)grid * phases * warps * N * sizeof(double);
 		if (gacc_bytes > ctx->walk_gacc_bytes) {
 			PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 			if (ctx->d_walk_gacc) cudaFree(ctx->d_walk_gacc);
 			ctx->d_walk_gacc = NULL;
+			ctx->walk_gacc_bytes = 0;
 			PHBC_CHECK(cudaMalloc((void **)&ctx->d_walk_gacc, gacc_bytes));
 			ctx->walk_gacc_bytes = gacc_bytes;
 		}
 		PHBC_CHECK(cudaMemsetAsync(ctx->d_walk_gacc, 0, gacc_bytes, ctx->stream));
 	}
-	if (!ctx->d_nuc4_cta_lnl || ctx->nuc4_grid < grid) {
+	if (!ctx->d_nuc4_cta_lnl || ctx->nuc4_grid < grid * phases) {
 		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 		if (ctx->d_nuc4_cta_lnl) cudaFree(ctx->d_nuc4_cta_lnl);
 		ctx->d_nuc4_cta_lnl = NULL;
-		PHBC_CHECK(cudaMalloc((void **)&ctx->d_nuc4_cta_lnl, (size_t)grid * warps * sizeof(double)));
-		ctx->nuc4_grid = grid;
+		ctx->nuc4_grid = 0;
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_nuc4_cta_lnl, (size_t)grid * phases * warps * sizeof(double)));
+		ctx->nuc4_grid = grid * phases;
+	}
+	if (nbatch > ctx->cat_grad_cap) {  // cat_grad [sample][N][C]
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		cudaFree(ctx->d_cat_grad);
+		ctx->d_cat_grad = NULL;
+		ctx->cat_grad_cap = 0;
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_cat_grad, (size_t)nbatch * N * C * sizeof(double)));
+		ctx->cat_grad_cap = nbatch;
 	}
 	double *post_mats = ctx->d_walk_mats;
 	double *pre_mats = ctx->d_walk_mats + (size_t)2 * ctx->n_post * C * 16;
 	{
 		const int total = (2 * ctx->n_post + 3 * ctx->n_pre) * C;
-		k_nuc4_matrices<<<(total + 127) / 128, 128, 0, ctx->stream>>>(C, ctx->root, ctx->n_post, ctx->n_pre, ctx->d_post_ops, ctx->d_pre_ops,
-		                                                             ctx->d_evec, ctx->d_eval, ctx->d_ivec,
-		                                                             ctx->d_bl + (size_t)o->batch_index * N, ctx->d_rates, post_mats, pre_mats);
+		k_nuc4_matrices<<<dim3((total + 127) / 128, nbatch), 128, 0, ctx->stream>>>(C, ctx->root, ctx->n_post, ctx->n_pre, ctx->d_post_ops, ctx->d_pre_ops,
+		                                                                          ctx->d_evec, ctx->d_eval, ctx->d_ivec,
+		                                                                          ctx->d_bl + (size_t)o->batch_index * N, ctx->d_rates, post_mats, pre_mats,
+		                                                                          N, mats_stride);
 		ctx->launches++;
 	}
 	Nuc4Params prm;
@@ -708,6 +769,7 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	prm.T = T, prm.N = N, prm.C = C, prm.P = P, prm.PB = PB, prm.root = ctx->root;
 	prm.n_post = ctx->n_post, prm.n_pre = ctx->n_pre, prm.nslots = nslots, prm.ntiles = ntiles;
 	prm.include_root_freqs = o->include_root_freqs, prm.compat = o->compat_scaled_gradient;
+	prm.nbatch = nbatch, prm.phases = phases, prm.mats_stride = mats_stride;
 	prm.post_first_tips = ctx->post_first_tips, prm.pre_first_tips = ctx->pre_first_tips;
 	prm.threshold = o->scaling_threshold;
 	prm.tip_codes = ctx->d_nuc4_codes;
@@ -733,13 +795,10 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	ctx->launches++;
 	if ((trc = phbc_time_end(ctx))) return trc;
 	double *result = ctx->d_result + (size_t)o->batch_index * (1 + N);
-	k_nuc4_finalize<<<dim3((N + 31) / 32, C), dim3(32, 8), 0, ctx->stream>>>(N, C, PB, grid, ctx->root, ctx->d_nuc4_cta_lnl, ctx->d_walk_gacc,
-	                                                             o->want_gradient, ctx->d_cat_grad, result);
+	k_nuc4_finalize<<<dim3((N + 31) / 32, nbatch), dim3(32, NUC4_FY), 0, ctx->stream>>>(N, C, PB, grid, phases, ntiles, nbatch, ctx->root, ctx->d_nuc4_cta_lnl,
+	                                                                         ctx->d_walk_gacc, o->want_gradient, ctx->d_props, ctx->d_rates,
+	                                                                         ctx->d_cat_grad, result);
 	ctx->launches++;
-	if (o->want_gradient) {
-		k_collapse_categories_nuc4<<<(N + 127) / 128, 128, 0, ctx->stream>>>(N, C, ctx->d_cat_grad, ctx->d_props, ctx->d_rates, result);
-		ctx->launches++;
-	}
 	PHBC_CHECK(cudaGetLastError());
 	return 0;
 }

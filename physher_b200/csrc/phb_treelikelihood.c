@@ -906,10 +906,9 @@ int phb_tlk_gradient_batch(phb_tlk *t, int nbatch, const double *bl, double *lnl
 	for (int attempt = 0; attempt < 2; attempt++) {
 		if ((rc = phbc_upload_branch_lengths(t->ctx, bl, nbatch))) return dev_fail(rc);
 		phbc_eval_opts o;
-		for (int b = 0; b < nbatch; b++) {
-			fill_opts(t, &o, grad != NULL, b);
-			if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
-		}
+		fill_opts(t, &o, grad != NULL, 0);
+		o.batch_count = nbatch; /* the fused 4-state walk takes the whole batch in one launch */
+		if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
 		if ((rc = phbc_download_results(t->ctx, nbatch, lnl, grad))) return dev_fail(rc);
 		int any_inf = 0;
 		for (int b = 0; b < nbatch; b++) any_inf |= isinf(lnl[b]);

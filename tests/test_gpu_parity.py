@@ -217,6 +217,31 @@ def test_batched_branch_length_samples():
     tlk.close()
 
 
+@pytest.mark.parametrize("shape", [(12, 6400, 4, 7), (10, 100, 4, 600), (9, 70, 1, 500), (16, 1000, 2, 3)])
+def test_batched_samples_share_one_launch(shape):
+    """BASELINE config 3: many branch-length samples in ONE fused launch.  Work items are (sample, pattern tile) pairs in
+    contiguous per-CTA ranges, so these shapes make single CTAs span 2, 3 and more samples; every sample is checked."""
+    T, P, C, B = shape
+    pb = _synthetic_problem(T, P, 4, C, seed=600 + P)
+    rng = np.random.default_rng(601)
+    bls = pb.bl[None, :] * rng.lognormal(0, 0.1, size=(B, pb.nnodes))
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    n0 = tlk.launch_count()
+    lnl, grad = tlk.gradient_batch(bls)
+    assert tlk.launch_count() - n0 <= 4, "the batch must not be a loop of per-sample launches"
+    lnl2, grad2 = tlk.gradient_batch(bls)
+    assert np.array_equal(lnl, lnl2) and np.array_equal(grad, grad2), "fixed-order reductions: bit-identical reruns"
+    for b in range(B) if B <= 8 else list(range(0, B, 37)) + [B - 1]:
+        pb.bl = bls[b]
+        want = O.evaluate(pb)
+        assert rel_err(lnl[b], want["lnl"]) < RTOL
+        assert grad_err(grad[b], want["grad"]) < RTOL
+    # lnL only
+    lnl3, none = tlk.gradient_batch(bls, want_gradient=False)
+    assert none is None and np.allclose(lnl3, lnl, rtol=1e-13, atol=0)
+    tlk.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # FP64 tensor-core path (20 / 61 states): KERNELS_AUTO routes there, KERNELS_GENERIC is the cross-check
 # ---------------------------------------------------------------------------------------------
