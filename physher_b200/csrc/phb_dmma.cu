@@ -28,6 +28,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 template <int S_>
 struct DmmaShape {
 	static constexpr int S = S_;
@@ -47,6 +49,13 @@ struct DmmaShape {
 
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
 	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+// acc[m][j] (+)= A-fragments[m][tt] x bf for all MT m-tiles of one (k-step, n-tile).
+// (m16n8k4 on pairs of m-tiles was measured on B200: same results, 5-12 % SLOWER end to end than two m8n8k4 -- round 1, s16.)
+template <int MT, int NTW, int KCH>
+__device__ __forceinline__ void dmma_mtiles(double (&acc)[MT][NTW][2], const double (&a)[MT][KCH], int j, int tt, double bf) {
+#pragma unroll
+	for (int m = 0; m < MT; m++) dmma_m8n8k4(acc[m][j][0], acc[m][j][1], a[m][tt], bf);
 }
 
 __device__ __forceinline__ const double *dm_partial_ptr(const Bufs &b, int idx, int c) {
@@ -88,24 +97,86 @@ __global__ void k_dmma_pack(int T, int N, int C, int tip_states, const double *_
 	}
 }
 
-// A fragments of chunk `ch` for MT m-tiles (8 patterns each) starting at pattern p0:
-// a[m][tt] = X[p0 + 8m + lane/4][4 (ch KCH + tt) + lane%4]  (a quad reads 32 contiguous bytes of one pattern's state vector)
-template <class Sh, int MT>
-__device__ __forceinline__ void load_chunk(const double *__restrict__ X, int p0, int P, int lane, int ch, double (&a)[MT][Sh::KCH]) {
+// A operands (patterns x states slices of partials buffers) travel HBM -> shared memory by cp.async in k-chunks, a ring of
+// NSTAGE chunk buffers per m-group (the NSPLIT warps that share the same patterns), two chunks ahead of the tensor pipe:
+// no register is tied up by data in flight, so the prefetch distance does not depend on instruction scheduling.
+// One chunk buffer = NOPS operands x (MT * 8 patterns) rows x KC doubles, row stride RS = 4 (mod 8) doubles so that the
+// fragment reads (lane (r, q) -> row r, column 4 tt + q) are bank-conflict free.
+template <class Sh, int MT, int NOPS>
+struct AStage {
+	static constexpr int KC = Sh::KCH * 4;
+	static constexpr int RS = KC + ((4 - KC % 8) + 8) % 8;
+	static constexpr int OPB = MT * 8 * RS;
+	static constexpr int STG = NOPS * OPB;
+	static constexpr int NSTAGE = 3;
+};
+
+__device__ __forceinline__ void cp_async8(double *dst, const double *src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+	asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// one chunk of up to three operands for the group's MT * 8 patterns starting at p0; PX = 0 switches an operand off (zeros)
+template <class Sh, int MT, int NOPS, int GT>
+__device__ __forceinline__ void fill_chunk(double *stage, const double *__restrict__ x0, int P0, const double *__restrict__ x1, int P1,
+                                           const double *__restrict__ x2, int P2, int p0, int ch, int gl) {
+	using A = AStage<Sh, MT, NOPS>;
+	constexpr int PER = MT * 8 * A::KC;
+#pragma unroll
+	for (int e0 = 0; e0 < NOPS * PER; e0 += GT) {
+		const int e = e0 + gl;
+		if ((NOPS * PER) % GT != 0 && e >= NOPS * PER) break;
+		const int op = e / PER, rem = e - op * PER, row = rem / A::KC, col = rem - row * A::KC;
+		const int k = ch * A::KC + col, p = p0 + row;
+		const double *X = op == 0 ? x0 : (op == 1 ? x1 : x2);
+		const int PX = op == 0 ? P0 : (op == 1 ? P1 : P2);
+		double *dst = stage + op * A::OPB + row * A::RS + col;
+		if (p < PX && k < Sh::S) cp_async8(dst, X + (size_t)p * Sh::S + k);
+		else if (PX > 0) *dst = 0.0;  // padding of a live operand; a switched-off operand's buffer is never read
+	}
+}
+
+// fragments of one staged operand: a[m][tt] = chunk[8 m + lane / 4][4 tt + lane % 4]
+template <class Sh, int MT, int NOPS>
+__device__ __forceinline__ void read_frags(const double *opbuf, int lane, double (&a)[MT][Sh::KCH]) {
+	using A = AStage<Sh, MT, NOPS>;
 	const int r = lane >> 2, q = lane & 3;
 #pragma unroll
-	for (int m = 0; m < MT; m++) {
-		const int p = p0 + 8 * m + r;
-		const double *row = X + (size_t)p * Sh::S;
+	for (int m = 0; m < MT; m++)
 #pragma unroll
-		for (int tt = 0; tt < Sh::KCH; tt++) {
-			const int t = ch * Sh::KCH + tt, k = 4 * t + q;
-			// volatile: the load is issued HERE, a whole chunk of tensor work ahead of its use (ptxas otherwise sinks it
-			// towards the consumer to shorten the live range, and the DMMA then waits out the full HBM latency)
-			a[m][tt] = 0.0;
-			if (t < Sh::KT && p < P && (Sh::KP == Sh::S || k < Sh::S)) asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(a[m][tt]) : "l"(row + k));
-		}
+		for (int tt = 0; tt < Sh::KCH; tt++) a[m][tt] = opbuf[(8 * m + r) * A::RS + 4 * tt + q];
+}
+
+// CTA-uniform op properties (child is a state tip, parent is the root) become compile-time constants of the tile loop:
+// a predicated-off DMMA still occupies the FP64 tensor pipe, so the products an op does not need must not be in its code path.
+template <class F>
+__device__ __forceinline__ void dispatch2(bool x, bool y, F &&f) {
+	using T = std::true_type;
+	using N = std::false_type;
+	if (x) {
+		if (y) f(T{}, T{});
+		else f(T{}, N{});
+	} else {
+		if (y) f(N{}, T{});
+		else f(N{}, N{});
 	}
+}
+template <class F>
+__device__ __forceinline__ void dispatch3(bool x, bool y, bool z, F &&f) {
+	using T = std::true_type;
+	using N = std::false_type;
+	if (x) dispatch2(y, z, [&](auto Y, auto Z) { f(T{}, Y, Z); });
+	else dispatch2(y, z, [&](auto Y, auto Z) { f(N{}, Y, Z); });
+}
+
+template <int NSPLIT>
+__device__ __forceinline__ void group_sync(int wm) {
+	if (NSPLIT == 1) __syncwarp();
+	else asm volatile("bar.sync %0, %1;" ::"r"(1 + wm), "n"(32 * NSPLIT) : "memory");
 }
 
 template <int MT, int NTW>
@@ -114,14 +185,6 @@ __device__ __forceinline__ void zero_acc(double (&acc)[MT][NTW][2]) {
 	for (int m = 0; m < MT; m++)
 #pragma unroll
 		for (int j = 0; j < NTW; j++) acc[m][j][0] = acc[m][j][1] = 0.0;
-}
-
-template <class Sh, int MT>
-__device__ __forceinline__ void copy_chunk(double (&dst)[MT][Sh::KCH], const double (&src)[MT][Sh::KCH]) {
-#pragma unroll
-	for (int m = 0; m < MT; m++)
-#pragma unroll
-		for (int tt = 0; tt < Sh::KCH; tt++) dst[m][tt] = src[m][tt];
 }
 
 // message of a state tip: column s of M, or `unknown_value(i)` when s >= S (probability matrices: 1, treelikelihood20.c:125-131;
@@ -187,7 +250,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const p
 	double *mA = sm, *mB = sm + Sh::IMG;
 	const phbc_op op = ops[blockIdx.z];
 	const int c = blockIdx.y;
-	const bool a_tip = dm_state_tip(b, op.a), b_tip = dm_state_tip(b, op.b);
+	const bool a_tip_rt = dm_state_tip(b, op.a), b_tip_rt = dm_state_tip(b, op.b);
 	if (threadIdx.x == 0) {
 		mbar_init(bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -202,16 +265,26 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const p
 	constexpr int TP = WM * MT * 8;
 	double *out = (double *)dm_partial_ptr(b, op.out, c);
 	// state tips have no partial operand: point the (fully predicated-off) loads at a valid address
-	const double *xa = a_tip ? nullptr : dm_partial_ptr(b, op.a, c), *xb = b_tip ? nullptr : dm_partial_ptr(b, op.b, c);
-	const int Pa = a_tip ? 0 : b.P, Pb = b_tip ? 0 : b.P;  // P = 0 switches the operand's loads off
+	const double *xa = a_tip_rt ? nullptr : dm_partial_ptr(b, op.a, c), *xb = b_tip_rt ? nullptr : dm_partial_ptr(b, op.b, c);
+	const int Pa = a_tip_rt ? 0 : b.P, Pb = b_tip_rt ? 0 : b.P;  // P = 0 switches the operand's loads off
 	const int ntiles = (b.P + TP - 1) / TP;
-	double ca[MT][Sh::KCH], cb[MT][Sh::KCH];
-	{
-		const int p0 = blockIdx.x * TP + wm * MT * 8;
-		load_chunk<Sh, MT>(xa, p0, Pa, lane, 0, ca);
-		load_chunk<Sh, MT>(xb, p0, Pb, lane, 0, cb);
-	}
-	mbar_wait(bar, 0);  // matrices have landed (the first A fragments are already in flight)
+	using AS = AStage<Sh, MT, 2>;
+	constexpr int GT = 32 * NSPLIT;
+	double *abuf = sm + 2 * Sh::IMG + wm * AS::NSTAGE * AS::STG;  // this m-group's ring
+	const int gl = (warp % NSPLIT) * 32 + lane;
+	int f_tile = blockIdx.x, f_ch = 0, f_stage = 0;
+	auto fill_next = [&]() {  // stage the next chunk of the (tile, chunk) sequence; always commits, so group counts stay uniform
+		if (f_tile < ntiles) fill_chunk<Sh, MT, 2, GT>(abuf + f_stage * AS::STG, xa, Pa, xb, Pb, nullptr, 0, f_tile * TP + wm * MT * 8, f_ch, gl);
+		cp_async_commit();
+		f_stage = f_stage + 1 == AS::NSTAGE ? 0 : f_stage + 1;
+		if (++f_ch == Sh::NCH) f_ch = 0, f_tile += gridDim.x;
+	};
+	fill_next();
+	fill_next();
+	int c_stage = 0;
+	mbar_wait(bar, 0);  // matrices have landed (the first A chunks are already in flight)
+	dispatch2(a_tip_rt, b_tip_rt, [&](auto ATIP, auto BTIP) {
+	constexpr bool a_tip = decltype(ATIP)::value, b_tip = decltype(BTIP)::value;
 	// B fragments run one (k-step, n-tile) ahead of the tensor pipe: the LDS of step u + 1 is issued before the DMMAs of step u
 	double bA = 0.0, bB = 0.0;
 	{
@@ -224,14 +297,17 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const p
 		double accA[MT][NTW][2], accB[MT][NTW][2];
 		zero_acc<MT, NTW>(accA);
 		zero_acc<MT, NTW>(accB);
+		if (!(a_tip && b_tip))  // a cherry is two gathers: no contraction, no staged operand
 #pragma unroll
 		for (int ch = 0; ch < Sh::NCH; ch++) {
-			double na[MT][Sh::KCH], nb[MT][Sh::KCH];
-			const bool last = ch == Sh::NCH - 1;
-			const int np0 = last ? p0 + (int)gridDim.x * TP : p0;  // past the end => all loads predicated off
-			load_chunk<Sh, MT>(xa, np0, Pa, lane, last ? 0 : ch + 1, na);
-			load_chunk<Sh, MT>(xb, np0, Pb, lane, last ? 0 : ch + 1, nb);
-			__syncwarp();  // scheduling fence: keeps the prefetch loads above this chunk's tensor work
+			cp_async_wait<1>();      // this chunk has landed (the newest group may still be in flight)
+			group_sync<NSPLIT>(wm);  // ... for every thread of the group, and the buffer refilled below is no longer read
+			fill_next();
+			const double *st = abuf + c_stage * AS::STG;
+			c_stage = c_stage + 1 == AS::NSTAGE ? 0 : c_stage + 1;
+			double ca[MT][Sh::KCH], cb[MT][Sh::KCH];
+			if (!a_tip) read_frags<Sh, MT, 2>(st, lane, ca);
+			if (!b_tip) read_frags<Sh, MT, 2>(st + AS::OPB, lane, cb);
 #pragma unroll
 			for (int tt = 0; tt < Sh::KCH; tt++) {
 				const int t = ch * Sh::KCH + tt;
@@ -244,19 +320,15 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const p
 						if (!a_tip) nA = mA[noff];
 						if (!b_tip) nB = mB[noff];
 						if (!a_tip) {
-#pragma unroll
-							for (int m = 0; m < MT; m++) dmma_m8n8k4(accA[m][j][0], accA[m][j][1], ca[m][tt], bA);
+dmma_mtiles<MT, NTW, Sh::KCH>(accA, ca, j, tt, bA);
 						}
 						if (!b_tip) {
-#pragma unroll
-							for (int m = 0; m < MT; m++) dmma_m8n8k4(accB[m][j][0], accB[m][j][1], cb[m][tt], bB);
+dmma_mtiles<MT, NTW, Sh::KCH>(accB, cb, j, tt, bB);
 						}
 						bA = nA, bB = nB;
 					}
 				}
 			}
-			copy_chunk<Sh, MT>(ca, na);
-			copy_chunk<Sh, MT>(cb, nb);
 		}
 		if (a_tip) tip_gather<Sh, MT, NTW, true>(b.tip_states + (size_t)op.a * b.P, mA, nullptr, p0, b.P, n0, lane, accA);
 		if (b_tip) tip_gather<Sh, MT, NTW, true>(b.tip_states + (size_t)op.b * b.P, mB, nullptr, p0, b.P, n0, lane, accB);
@@ -266,6 +338,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const p
 			for (int j = 0; j < NTW; j++) accA[m][j][0] *= accB[m][j][0], accA[m][j][1] *= accB[m][j][1];
 		store_tile<Sh, MT, NTW>(out, p0, b.P, n0, lane, accA);
 	}
+	});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -293,15 +366,15 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 	double *fq = aux, *wroot = aux + Sh::NP, *red = aux + 2 * Sh::NP;
 	const phbc_parent_op op = ops[blockIdx.z];
 	const int c = blockIdx.y;
-	const bool is_root = op.flags & 1;
-	const bool a_tip = dm_state_tip(b, op.a), b_tip = dm_state_tip(b, op.b);
+	const bool is_root_rt = op.flags & 1;
+	const bool a_tip_rt = dm_state_tip(b, op.a), b_tip_rt = dm_state_tip(b, op.b);
 	const double *rsA = dA + Sh::S * Sh::NP, *rsB = dB + Sh::S * Sh::NP;  // row sums ride behind a tip's transposed image
 	if (threadIdx.x == 0) {
 		const size_t dimg = (size_t)b.N * b.C * Sh::IMG;  // offset of the dP images
 		mbar_init(bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		mbar_expect_tx(bar, ((is_root ? 0 : 1) + (GRAD ? 4 : 2)) * Sh::IMG * 8);
-		if (!is_root) bulk_g2s(mP, img + ((size_t)op.node * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		mbar_expect_tx(bar, ((is_root_rt ? 0 : 1) + (GRAD ? 4 : 2)) * Sh::IMG * 8);
+		if (!is_root_rt) bulk_g2s(mP, img + ((size_t)op.node * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
 		bulk_g2s(mA, img + ((size_t)op.a * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
 		bulk_g2s(mB, img + ((size_t)op.b * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
 		if (GRAD) {
@@ -321,20 +394,29 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 	constexpr int TP = WM * MT * 8;
 	const bool a_leaf = op.a < b.T, b_leaf = op.b < b.T;
 	const double *xw = b.upper + ((size_t)op.node * b.C + c) * (size_t)b.P * S;
-	const double *xa = a_tip ? nullptr : dm_partial_ptr(b, op.a, c), *xb = b_tip ? nullptr : dm_partial_ptr(b, op.b, c);
-	const int Pw = is_root ? 0 : b.P, Pa = a_tip ? 0 : b.P, Pb = b_tip ? 0 : b.P;  // P = 0 switches an operand's loads off
+	const double *xa = a_tip_rt ? nullptr : dm_partial_ptr(b, op.a, c), *xb = b_tip_rt ? nullptr : dm_partial_ptr(b, op.b, c);
+	const int Pw = is_root_rt ? 0 : b.P, Pa = a_tip_rt ? 0 : b.P, Pb = b_tip_rt ? 0 : b.P;  // P = 0 switches an operand's loads off
 	double *Ua = b.upper + ((size_t)op.a * b.C + c) * (size_t)b.P * S;
 	double *Ub = b.upper + ((size_t)op.b * b.C + c) * (size_t)b.P * S;
 	const int ntiles = (b.P + TP - 1) / TP;
 	double tot_a = 0.0, tot_b = 0.0;
-	double cw[MT][Sh::KCH], ca[MT][Sh::KCH], cb[MT][Sh::KCH];
-	{
-		const int p0 = blockIdx.x * TP + wm * MT * 8;
-		load_chunk<Sh, MT>(xw, p0, Pw, lane, 0, cw);
-		load_chunk<Sh, MT>(xb, p0, Pb, lane, 0, cb);
-		load_chunk<Sh, MT>(xa, p0, Pa, lane, 0, ca);
-	}
-	mbar_wait(bar, 0);  // matrices have landed (the first A fragments are already in flight)
+	using AS = AStage<Sh, MT, 3>;
+	constexpr int GT = 32 * NSPLIT;
+	double *abuf = red + 2 * NWARPS + wm * AS::NSTAGE * AS::STG;  // this m-group's ring: operands U_n | L_b | L_a
+	const int gl = (warp % NSPLIT) * 32 + lane;
+	int f_tile = blockIdx.x, f_ch = 0, f_stage = 0;
+	auto fill_next = [&]() {  // stage the next chunk of the (tile, chunk) sequence; always commits, so group counts stay uniform
+		if (f_tile < ntiles) fill_chunk<Sh, MT, 3, GT>(abuf + f_stage * AS::STG, xw, Pw, xb, Pb, xa, Pa, f_tile * TP + wm * MT * 8, f_ch, gl);
+		cp_async_commit();
+		f_stage = f_stage + 1 == AS::NSTAGE ? 0 : f_stage + 1;
+		if (++f_ch == Sh::NCH) f_ch = 0, f_tile += gridDim.x;
+	};
+	fill_next();
+	fill_next();
+	int c_stage = 0;
+	mbar_wait(bar, 0);  // matrices have landed (the first A chunks are already in flight)
+	dispatch3(is_root_rt, a_tip_rt, b_tip_rt, [&](auto ROOT, auto ATIP, auto BTIP) {
+	constexpr bool is_root = decltype(ROOT)::value, a_tip = decltype(ATIP)::value, b_tip = decltype(BTIP)::value;
 	// B fragments run one (k-step, n-tile) ahead of the tensor pipe: the LDS of step u + 1 is issued before the DMMAs of step u
 	double bP = 0.0, bA = 0.0, bB = 0.0, bdA = 0.0, bdB = 0.0;
 	{
@@ -371,14 +453,15 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 		}
 #pragma unroll
 		for (int ch = 0; ch < Sh::NCH; ch++) {
-			double nw[MT][Sh::KCH], na[MT][Sh::KCH], nb[MT][Sh::KCH];
-			const bool last = ch == Sh::NCH - 1;
-			const int np0 = last ? p0 + (int)gridDim.x * TP : p0;  // past the end => all loads predicated off
-			const int nch = last ? 0 : ch + 1;
-			load_chunk<Sh, MT>(xw, np0, Pw, lane, nch, nw);
-			load_chunk<Sh, MT>(xb, np0, Pb, lane, nch, nb);
-			load_chunk<Sh, MT>(xa, np0, Pa, lane, nch, na);
-			__syncwarp();  // scheduling fence: keeps the prefetch loads above this chunk's tensor work
+			cp_async_wait<1>();      // this chunk has landed (the newest group may still be in flight)
+			group_sync<NSPLIT>(wm);  // ... for every thread of the group, and the buffer refilled below is no longer read
+			fill_next();
+			const double *st = abuf + c_stage * AS::STG;
+			c_stage = c_stage + 1 == AS::NSTAGE ? 0 : c_stage + 1;
+			double cw[MT][Sh::KCH], cb[MT][Sh::KCH], ca[MT][Sh::KCH];
+			if (!is_root) read_frags<Sh, MT, 3>(st, lane, cw);
+			if (!b_tip) read_frags<Sh, MT, 3>(st + AS::OPB, lane, cb);
+			if (!a_tip) read_frags<Sh, MT, 3>(st + 2 * AS::OPB, lane, ca);
 #pragma unroll
 			for (int tt = 0; tt < Sh::KCH; tt++) {
 				const int t = ch * Sh::KCH + tt;
@@ -399,32 +482,24 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 							if (GRAD) ndA = dA[noff];
 						}
 						if (!is_root) {
-#pragma unroll
-							for (int m = 0; m < MT; m++) dmma_m8n8k4(W[m][j][0], W[m][j][1], cw[m][tt], bP);
+dmma_mtiles<MT, NTW, Sh::KCH>(W, cw, j, tt, bP);
 						}
 						if (!b_tip) {
-#pragma unroll
-							for (int m = 0; m < MT; m++) dmma_m8n8k4(Mb[m][j][0], Mb[m][j][1], cb[m][tt], bB);
+dmma_mtiles<MT, NTW, Sh::KCH>(Mb, cb, j, tt, bB);
 							if (GRAD) {
-#pragma unroll
-								for (int m = 0; m < MT; m++) dmma_m8n8k4(Db[m][j][0], Db[m][j][1], cb[m][tt], bdB);
+dmma_mtiles<MT, NTW, Sh::KCH>(Db, cb, j, tt, bdB);
 							}
 						}
 						if (!a_tip) {
-#pragma unroll
-							for (int m = 0; m < MT; m++) dmma_m8n8k4(Ma[m][j][0], Ma[m][j][1], ca[m][tt], bA);
+dmma_mtiles<MT, NTW, Sh::KCH>(Ma, ca, j, tt, bA);
 							if (GRAD) {
-#pragma unroll
-								for (int m = 0; m < MT; m++) dmma_m8n8k4(Da[m][j][0], Da[m][j][1], ca[m][tt], bdA);
+dmma_mtiles<MT, NTW, Sh::KCH>(Da, ca, j, tt, bdA);
 							}
 						}
 						bP = nP, bA = nA, bB = nB, bdA = ndA, bdB = ndB;
 					}
 				}
 			}
-			copy_chunk<Sh, MT>(cw, nw);
-			copy_chunk<Sh, MT>(cb, nb);
-			copy_chunk<Sh, MT>(ca, na);
 		}
 		if (is_root) {
 #pragma unroll
@@ -476,6 +551,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 			}
 		}
 	}
+	});
 	if (GRAD) {
 		// every quad lane carries the same row value: sum lanes with q == 0 over the 8 rows, then across warps (fixed order)
 		tot_a = q == 0 ? tot_a : 0.0, tot_b = q == 0 ? tot_b : 0.0;
@@ -550,7 +626,7 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	k_dmma_pack<Sh><<<dim3(N, C, 2), 128, 0, ctx->stream>>>(ctx->T, N, C, ctx->tip_kind == PHBC_TIP_STATES, ctx->d_P, ctx->d_dP, ctx->d_dmma_img);
 	ctx->launches++;
 	auto lower = k_dmma_lower<S, Cf::MT, Cf::NSPLIT, Cf::WM>;
-	const size_t lsmem = 128 + 2 * Sh::IMG * sizeof(double);
+	const size_t lsmem = 128 + (2 * Sh::IMG + Cf::WM * AStage<Sh, Cf::MT, 2>::NSTAGE * AStage<Sh, Cf::MT, 2>::STG) * sizeof(double);
 	PHBC_CHECK(cudaFuncSetAttribute(lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
 	const int lthreads = 32 * Cf::WM * Cf::NSPLIT, ltiles = (P + Cf::WM * Cf::MT * 8 - 1) / (Cf::WM * Cf::MT * 8);
 	int lper_sm = 1;
@@ -574,7 +650,7 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		const bool grad = !o->scale;  // fused reductions use the unscaled form
 		auto upper = grad ? k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, true> : k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, false>;
 		const int uwarps = Cf::UWM * Cf::UNSPLIT;
-		const size_t usmem = 128 + ((grad ? 5 : 3) * Sh::IMG + 2 * Sh::NP + 2 * uwarps) * sizeof(double);
+		const size_t usmem = 128 + ((grad ? 5 : 3) * Sh::IMG + 2 * Sh::NP + 2 * uwarps + Cf::UWM * AStage<Sh, Cf::UMT, 3>::NSTAGE * AStage<Sh, Cf::UMT, 3>::STG) * sizeof(double);
 		PHBC_CHECK(cudaFuncSetAttribute(upper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
 		const int uthreads = 32 * uwarps, utiles = (P + Cf::UWM * Cf::UMT * 8 - 1) / (Cf::UWM * Cf::UMT * 8);
 		int uper_sm = 1;
