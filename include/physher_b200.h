@@ -142,6 +142,28 @@ int phb_tlk_synchronize(phb_tlk *tlk);
 int phb_tlk_gradient_batch(phb_tlk *tlk, int nbatch, const double *bl /* [B][N] */, double *lnl /* [B] */,
                            double *grad /* [B][N] */);
 
+/*
+ * Time trees, batched (the reference runs these O(N) recursions on the host around every evaluation).
+ *
+ * phb_tlk_set_time_tree: sampling dates of the tips as heights [T] by tip node id; the lower bounds of the ratio transform
+ * are derived from them (tree_transform_collect_lowers, treetransform.c:239-252).
+ *
+ * phb_tlk_gradient_batch_time: B samples of the reparameterised tree -- ratios[b][class id] with the root height in the
+ * root's entry (class id = node id - T, tree.c:183-199; TreeTransform parameters, treetransform.c:224-237) and clock rates
+ * (nrates = 1: strict clock, nrates = N: one rate per node id, BranchModel.get) -- are turned into node heights and branch
+ * lengths rate * (h_parent - h_node) (treelikelihood.c:1652-1663) on the device, evaluated in one fused launch, and the branch
+ * gradients are chained back on the device to
+ *   grad_ratios[b][T-1]  gradient_ratios (treelikelihood.c:3161-3171: gradient_heights + Tree_node_transform_jvp, plus the
+ *                        gradient of the log Jacobian when include_jacobian, treetransform.c:95-120)
+ *   grad_rates[b][nrates] gradient_clock (treelikelihood.c:3054-3075)
+ * lnl[b] excludes the Jacobian (like tlk->calculate); log_jacobian[b] is TreeTransform.log_jacobian (treetransform.c:215-222),
+ * what _singleTreeLikelihood_logP adds when tlk->include_jacobian (treelikelihood.c:163-172).  Any output pointer may be NULL.
+ */
+int phb_tlk_set_time_tree(phb_tlk *tlk, const double *tip_heights /* [T] */);
+int phb_tlk_gradient_batch_time(phb_tlk *tlk, int nbatch, const double *ratios /* [B][T-1] */, const double *rates /* [B][nrates] */,
+                                int nrates, int include_jacobian, double *lnl /* [B] */, double *log_jacobian /* [B] */,
+                                double *grad_ratios /* [B][T-1] */, double *grad_rates /* [B][nrates] */);
+
 /* With PHB_OPT_TIMING on: device time (CUDA events on the tlk stream) and launch count of the dominant kernel
  * (the fused walk kernel, or the sum of the node-at-a-time kernels) since the option was set. Synchronises. */
 int phb_tlk_kernel_time(phb_tlk *tlk, double *total_ms, long long *launches);

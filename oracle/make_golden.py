@@ -144,11 +144,42 @@ def write_c1_dropin_fixture():
     print("c1 drop-in fixture:", len(aln["sequences"]), "sequences,", len(kat["ratio_grad"]), "ratio gradients")
 
 
+def write_c1_time_tree_fixture():
+    """tests/golden/c1_time_tree.npz: inputs of the time-tree chain of the reference's own fixture (tip dates as heights, ratios,
+    root height, clock rate) and the reference's outputs for the fixture's own values and for perturbed samples."""
+    doc = json.load(open(os.path.join(GOLDEN, "c1_jc69_time.json")))
+    ref = O.Reference(doc["model"])
+    pb = ref.problem()
+    th, ratios, rates = ref.time_tree()
+    rng = np.random.default_rng(20261017)
+    B = 6
+    samples = np.tile(ratios, (B, 1))
+    samples[1:, :-1] = np.clip(ratios[None, :-1] * rng.lognormal(0, 0.15, size=(B - 1, ratios.shape[0] - 1)), 0.02, 0.98)
+    samples[1:, -1] = ratios[-1] * rng.lognormal(0, 0.05, size=B - 1)
+    rate_samples = rates[0] * np.concatenate([[1.0], rng.lognormal(0, 0.2, size=B - 1)])
+    out = dict(tip_heights=th, ratios=samples, rates=rate_samples, ref_lnl=np.zeros(B), ref_lnl_jacobian=np.zeros(B),
+               ref_grad=np.zeros((B, ref.T)), ref_grad_jacobian=np.zeros((B, ref.T)))
+    for b in range(B):
+        ref.set_ratios(samples[b])
+        ref.set_clock_rate(rate_samples[b])
+        ref.set_include_jacobian(False)
+        out["ref_lnl"][b] = ref.logP()
+        out["ref_grad"][b] = ref.gradient(O.FLAG_TREE_MODEL | O.FLAG_BRANCH_MODEL)
+        ref.set_include_jacobian(True)
+        out["ref_lnl_jacobian"][b] = ref.logP()
+        out["ref_grad_jacobian"][b] = ref.gradient(O.FLAG_TREE_MODEL | O.FLAG_BRANCH_MODEL)
+    ref.close()
+    np.savez_compressed(os.path.join(GOLDEN, "c1_time_tree.npz"), **out)
+    print("c1 time tree fixture:", B, "samples, lnL", out["ref_lnl"])
+
+
 def main():
     if "--only-dropin" in sys.argv:
         write_c1_dropin_fixture()
+        write_c1_time_tree_fixture()
         return
     write_c1_dropin_fixture()
+    write_c1_time_tree_fixture()
     cwd = os.getcwd()
     os.chdir(REF_DATA)  # fixtures reference fluA.fa / tiny.fa by relative path
 

@@ -187,6 +187,31 @@ def evaluate(pb: Problem, gradient: bool = True, partials: bool = False, matrice
     return out
 
 
+def time_evaluate(pb: Problem, tip_heights, ratios, rates, include_jacobian=False) -> dict:
+    """Time-tree chain around `evaluate` (naive reference forms): ratios [T-1] (root entry = root height), rates [1] or [N]
+    -> dict(lnl, log_jacobian, heights, bl, grad_ratios, grad_rates)."""
+    import copy
+
+    lib = _oracle()
+    T, N = pb.ntips, pb.nnodes
+    left, right, parent = (np.ascontiguousarray(a, dtype=np.int32) for a in (pb.left, pb.right, pb.parent))
+    th = np.ascontiguousarray(tip_heights, dtype=np.float64)
+    r = np.ascontiguousarray(ratios, dtype=np.float64)
+    c = np.ascontiguousarray(rates, dtype=np.float64)
+    lowers, heights, bl, lj = np.zeros(N), np.zeros(N), np.zeros(N), C.c_double(0)
+    lib.oracle_time_forward.argtypes = [C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _dp, _dp, _dp, C.c_int, _dp, _dp, _dp, C.POINTER(C.c_double)]
+    lib.oracle_time_backward.argtypes = [C.c_int, C.c_int, C.c_int, _ip, _ip, _ip, _dp, _dp, C.c_int, _dp, _dp, _dp, C.c_int, _dp, _dp]
+    lib.oracle_time_forward(T, N, int(pb.root), _i(left), _i(right), _i(parent), _d(th), _d(r), _d(c), c.shape[0], _d(lowers), _d(heights),
+                            _d(bl), C.byref(lj))
+    q = copy.copy(pb)
+    q.bl, q.unrooted = bl, False
+    out = evaluate(q)
+    gr, gc = np.zeros(T - 1), np.zeros(c.shape[0])
+    lib.oracle_time_backward(T, N, int(pb.root), _i(left), _i(right), _i(parent), _d(r), _d(c), c.shape[0], _d(lowers), _d(heights),
+                             _d(np.ascontiguousarray(out["grad"])), int(include_jacobian), _d(gr), _d(gc))
+    return dict(lnl=out["lnl"], log_jacobian=lj.value, heights=heights, bl=bl, lowers=lowers, grad_ratios=gr, grad_rates=gc, grad=out["grad"])
+
+
 # ---------------------------------------------------------------------------------------------
 # compiled reference (oracle/_ref)
 # ---------------------------------------------------------------------------------------------
@@ -244,6 +269,10 @@ def _reflib():
         L.refh_time_logP.restype = C.c_double
         L.refh_time_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.refh_time_gradient.restype = C.c_double
+        L.refh_time_tree.argtypes = [C.c_void_p, _dp, _dp, _dp]
+        L.refh_time_tree.restype = C.c_int
+        L.refh_set_ratios.argtypes = [C.c_void_p, _dp]
+        L.refh_set_clock_rate.argtypes = [C.c_void_p, C.c_double]
         _ref = L
     return _ref
 
@@ -321,6 +350,18 @@ class Reference:
 
     def time_gradient(self, iters, flags=FLAG_TREE_MODEL, include_root_freqs=-1):
         return float(self.L.refh_time_gradient(self.h, flags, include_root_freqs, iters))
+
+    def time_tree(self):
+        """(tip_heights[T], ratios[T-1] with the root height in the root's entry, rates[1 or N]) as the reference holds them."""
+        th, ratios, rates = np.zeros(self.T), np.zeros(self.T - 1), np.zeros(self.N)
+        nr = self.L.refh_time_tree(self.h, _d(th), _d(ratios), _d(rates))
+        return th, ratios, rates[:nr].copy() if nr == 1 else rates
+
+    def set_ratios(self, ratios):
+        self.L.refh_set_ratios(self.h, _d(np.ascontiguousarray(ratios, dtype=np.float64)))
+
+    def set_clock_rate(self, rate):
+        self.L.refh_set_clock_rate(self.h, float(rate))
 
     def problem(self, **kw) -> Problem:
         """Export every input of the hot path as plain arrays (ids and pattern order as the reference has them)."""

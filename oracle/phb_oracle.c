@@ -350,3 +350,106 @@ int oracle_evaluate(const OracleProblem *pb, OracleResult *res) {
 	free(w.sf);
 	return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Time-tree chain.  Deliberately the reference's NAIVE forms (recursive products of ratios),
+ * so that the device implementation (an adjoint sweep) is checked against an independent formulation.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* tree_transform_collect_lowers (treetransform.c:239-252) */
+static double tt_collect_lowers(const int *left, const int *right, const double *tip_heights, int n, double *lowers) {
+	if (left[n] < 0) return lowers[n] = tip_heights[n];
+	const double a = tt_collect_lowers(left, right, tip_heights, left[n], lowers);
+	const double b = tt_collect_lowers(left, right, tip_heights, right[n], lowers);
+	return lowers[n] = a > b ? a : b;
+}
+
+/* tree_transform_update_heights (treetransform.c:224-237) */
+static void tt_update_heights(const int *left, const int *right, const int *parent, int T, int n, const double *ratios, const double *lowers,
+                              double *heights) {
+	if (left[n] < 0) {
+		heights[n] = lowers[n];
+		return;
+	}
+	const double s = ratios[n - T];
+	if (parent[n] < 0) heights[n] = s;
+	else heights[n] = lowers[n] + (heights[parent[n]] - lowers[n]) * s;
+	tt_update_heights(left, right, parent, T, left[n], ratios, lowers, heights);
+	tt_update_heights(left, right, parent, T, right[n], ratios, lowers, heights);
+}
+
+/* heights, branch lengths rate * (h_parent - h) (treelikelihood.c:1652-1663), log Jacobian (_node_transform_log_jacobian,
+ * treetransform.c:215-222).  ratios by class id = node id - T, root entry = root height; nrates = 1 or N. */
+void oracle_time_forward(int T, int N, int root, const int *left, const int *right, const int *parent, const double *tip_heights,
+                         const double *ratios, const double *rates, int nrates, double *lowers, double *heights, double *bl, double *logjac) {
+	tt_collect_lowers(left, right, tip_heights, root, lowers);
+	tt_update_heights(left, right, parent, T, root, ratios, lowers, heights);
+	double lj = 0.0;
+	for (int n = 0; n < N; n++) {
+		if (n == root) {
+			bl[n] = 0.0;
+			continue;
+		}
+		bl[n] = (nrates == 1 ? rates[0] : rates[n]) * (heights[parent[n]] - heights[n]);
+		if (n >= T) lj += log(heights[parent[n]] - lowers[n]);
+	}
+	*logjac = lj;
+}
+
+/* product_of_ratios (treetransform.c:311-318) */
+static void tt_product_of_ratios(const int *left, const int *right, int T, int n, const double *grad, const double *ratios, double prod,
+                                 double *out) {
+	if (left[n] < 0) return;
+	const double p = ratios[n - T] * prod;
+	*out += grad[n - T] * p;
+	tt_product_of_ratios(left, right, T, left[n], grad, ratios, p, out);
+	tt_product_of_ratios(left, right, T, right[n], grad, ratios, p, out);
+}
+
+/* _node_transform_dlog_jacobian_aux (treetransform.c:268-285) */
+static void tt_dlog_jacobian_aux(const int *left, const int *right, const int *parent, int T, int ref, int n, const double *ratios,
+                                 const double *lowers, const double *heights, double *dlogP, double *descendant) {
+	if (left[n] < 0) return;
+	if (parent[n] >= 0 && n != ref) descendant[n] = descendant[parent[n]] * ratios[n - T];
+	else if (parent[n] >= 0) descendant[n] = heights[parent[n]] - lowers[n];
+	else descendant[n] = 1;
+	tt_dlog_jacobian_aux(left, right, parent, T, ref, left[n], ratios, lowers, heights, dlogP, descendant);
+	tt_dlog_jacobian_aux(left, right, parent, T, ref, right[n], ratios, lowers, heights, dlogP, descendant);
+	if (parent[n] >= 0 && n != ref) *dlogP += descendant[parent[n]] / (heights[parent[n]] - lowers[n]);
+}
+
+/* branch gradient -> gradient_heights (treelikelihood.c:3145-3156) -> node_transform_jvp (treetransform.c:320-337)
+ * [+ _node_transform_log_jacobian_gradient (treetransform.c:297-309)], and gradient_clock (treelikelihood.c:3054-3075) */
+void oracle_time_backward(int T, int N, int root, const int *left, const int *right, const int *parent, const double *ratios,
+                          const double *rates, int nrates, const double *lowers, const double *heights, const double *branch_grad,
+                          int include_jacobian, double *grad_ratios, double *grad_rates) {
+	double *hg = (double *)calloc(T - 1, sizeof(double));
+	double *descendant = (double *)calloc(N, sizeof(double));
+	for (int n = 0; n < N; n++) {
+		if (n == root) continue;
+		const double g = branch_grad[n] * (nrates == 1 ? rates[0] : rates[n]);
+		if (n >= T) hg[n - T] += -g;
+		hg[parent[n] - T] += g;
+	}
+	for (int n = T; n < N; n++) {
+		const double dh = n == root ? 1.0 : heights[parent[n]] - lowers[n];
+		double acc = hg[n - T];
+		tt_product_of_ratios(left, right, T, left[n], hg, ratios, 1.0, &acc);
+		tt_product_of_ratios(left, right, T, right[n], hg, ratios, 1.0, &acc);
+		grad_ratios[n - T] = acc * dh;
+		if (include_jacobian) {
+			double adj = 0.0;
+			tt_dlog_jacobian_aux(left, right, parent, T, n, n, ratios, lowers, heights, &adj, descendant);
+			grad_ratios[n - T] += adj;
+		}
+	}
+	if (nrates == 1) {
+		grad_rates[0] = 0.0;
+		for (int n = 0; n < N; n++)
+			if (n != root) grad_rates[0] += branch_grad[n] * (heights[parent[n]] - heights[n]);
+	} else {
+		for (int n = 0; n < N; n++) grad_rates[n] = n == root ? 0.0 : branch_grad[n] * (heights[parent[n]] - heights[n]);
+	}
+	free(hg);
+	free(descendant);
+}

@@ -388,3 +388,46 @@ int refh_kat_dlogP(void *vh, double *out, int cap) {
 	free_Parameters(ps);
 	return n;
 }
+
+/* inputs of the time-tree chain as the reference holds them: tip heights [T] by node id, reparameterisation values [T-1] by
+ * class id (root entry = root height), clock rates (returns their count: 1 strict, else one per node by node id) */
+int refh_time_tree(void *vh, double *tip_heights, double *ratios, double *rates) {
+	RefH *h = (RefH *)vh;
+	Model **models = (Model **)h->model->data;
+	Tree *tree = (Tree *)models[0]->obj;
+	BranchModel *bm = (BranchModel *)models[3]->obj;
+	Tree_update_heights(tree);
+	int N = Tree_node_count(tree);
+	for (int i = 0; i < N; i++) {
+		Node *n = Tree_node(tree, i);
+		if (Node_isleaf(n)) tip_heights[Node_id(n)] = Node_height(n);
+	}
+	Parameters *rp = get_reparams(tree);
+	for (size_t i = 0; i < Parameters_count(rp); i++) ratios[i] = Parameters_value(rp, i);
+	int nr = (int)Parameters_count(bm->rates);
+	if (nr == 1) rates[0] = Parameters_value(bm->rates, 0);
+	else
+		for (int i = 0; i < N; i++) {
+			Node *n = Tree_node(tree, i);
+			if (!Node_isroot(n)) rates[Node_id(n)] = bm->get(bm, n);
+		}
+	return nr;
+}
+
+void refh_set_ratios(void *vh, const double *ratios) {
+	RefH *h = (RefH *)vh;
+	Model **models = (Model **)h->model->data;
+	Tree *tree = (Tree *)models[0]->obj;
+	Parameters *rp = get_reparams(tree);
+	for (size_t i = 0; i < Parameters_count(rp); i++) Parameters_set_value(rp, i, ratios[i]);
+	Tree_update_heights(tree);
+	SingleTreeLikelihood_update_all_nodes(h->tlk);
+}
+
+void refh_set_clock_rate(void *vh, double rate) {
+	RefH *h = (RefH *)vh;
+	Model **models = (Model **)h->model->data;
+	BranchModel *bm = (BranchModel *)models[3]->obj;
+	Parameters_set_value(bm->rates, 0, rate);
+	SingleTreeLikelihood_update_all_nodes(h->tlk);
+}

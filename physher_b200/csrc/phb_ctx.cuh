@@ -64,6 +64,14 @@ struct phbc_ctx {
 	double *d_scratch;       // reduction scratch
 	size_t scratch_bytes;
 
+	// time-tree chain (phb_timetree.cu)
+	double *d_tt_lowers;     // [N]
+	int *d_tt_topo;          // parent[N] | preorder[N] | postorder[N]
+	int *d_tt_bad;
+	double *d_tt_ratios, *d_tt_rates, *d_tt_heights, *d_tt_adj, *d_tt_out;
+	double *h_tt;            // pinned staging
+	int tt_cap;
+
 	long long launches;
 
 	// optional event timing of the dominant kernel(s)

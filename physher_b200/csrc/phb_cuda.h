@@ -133,6 +133,11 @@ int phbc_download_cat_grad(phbc_ctx *ctx, double *out);
 int phbc_download_pattern_lnl(phbc_ctx *ctx, double *out);
 int phbc_download_partials(phbc_ctx *ctx, int index, double *out);
 int phbc_download_matrices(phbc_ctx *ctx, double *P, double *dP);
+/* time-tree chain, batched (phb_timetree.cu) */
+int phbc_set_time_tree(phbc_ctx *ctx, const double *lowers, const int *parent, const int *preorder, const int *postorder);
+int phbc_time_forward(phbc_ctx *ctx, int nbatch, const double *ratios, const double *rates, int nrates); /* 1: negative branch length */
+int phbc_time_backward(phbc_ctx *ctx, int nbatch, int nrates, int include_jacobian, int want_gradient, double *lnl, double *logjac,
+                       double *grad_ratios, double *grad_rates);
 int phbc_synchronize(phbc_ctx *ctx);
 void *phbc_stream(phbc_ctx *ctx);
 long long phbc_launch_count(const phbc_ctx *ctx);

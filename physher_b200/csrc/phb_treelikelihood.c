@@ -56,6 +56,7 @@ struct phb_tlk {
 	int n_lower_levels, n_upper_levels, post_slots, pre_slots;
 	int *post_tip_order, *pre_tip_order, *post_chunk_tip0, *pre_chunk_tip0;
 	int post_first_tips, pre_first_tips;
+	int have_time_tree;
 };
 
 static _Thread_local char g_err[512] = "";
@@ -930,6 +931,84 @@ int phb_tlk_gradient_batch(phb_tlk *t, int nbatch, const double *bl, double *lnl
 		}
 	/* the single-sample state (t->bl, t->lk) is untouched but device partials now belong to the last sample */
 	phb_tlk_update_all_nodes(t);
+	return PHB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* time trees (batched chain on the device, phb_timetree.cu)                                   */
+/* ------------------------------------------------------------------------------------------- */
+
+int phb_tlk_set_time_tree(phb_tlk *t, const double *tip_heights) {
+	const int N = t->N, T = t->T;
+	double *lowers = (double *)malloc(sizeof(double) * N);
+	int *pre = (int *)malloc(sizeof(int) * N), *post = (int *)malloc(sizeof(int) * N), *stack = (int *)malloc(sizeof(int) * N);
+	if (!lowers || !pre || !post || !stack) {
+		free(lowers), free(pre), free(post), free(stack);
+		return fail(PHB_ENOMEM, "out of memory");
+	}
+	int sp = 0, cnt = 0;
+	stack[sp++] = t->root;
+	while (sp) { /* pre-order: parents before children */
+		const int n = stack[--sp];
+		pre[cnt++] = n;
+		if (!is_tip(t, n)) {
+			stack[sp++] = t->right[n];
+			stack[sp++] = t->left[n];
+		}
+	}
+	for (int k = 0; k < N; k++) post[k] = pre[N - 1 - k]; /* reversed pre-order: children before parents */
+	/* lower bound of a node = the oldest sampling date below it (tree_transform_collect_lowers, treetransform.c:239-252) */
+	for (int k = 0; k < N; k++) {
+		const int n = post[k];
+		if (is_tip(t, n)) lowers[n] = tip_heights[n];
+		else lowers[n] = lowers[t->left[n]] > lowers[t->right[n]] ? lowers[t->left[n]] : lowers[t->right[n]];
+	}
+	(void)T;
+	int rc = phbc_set_time_tree(t->ctx, lowers, t->parent, pre, post);
+	free(lowers), free(pre), free(post), free(stack);
+	if (rc) return dev_fail(rc);
+	t->have_time_tree = 1;
+	return PHB_OK;
+}
+
+int phb_tlk_gradient_batch_time(phb_tlk *t, int nbatch, const double *ratios, const double *rates, int nrates, int include_jacobian,
+                                double *lnl, double *log_jacobian, double *grad_ratios, double *grad_rates) {
+	if (nbatch < 1 || !ratios || !rates || !lnl) return fail(PHB_EINVAL, "nbatch >= 1, ratios, rates and lnl are required");
+	if (nrates != 1 && nrates != t->N) return fail(PHB_EINVAL, "nrates must be 1 (strict clock) or N = %d (one rate per node)", t->N);
+	if (!t->have_time_tree) return fail(PHB_ESTATE, "phb_tlk_set_time_tree has not been called");
+	const int had_bl = t->have_bl;
+	t->have_bl = 1;
+	int rc = check_ready(t);
+	t->have_bl = had_bl;
+	if (rc) return rc;
+	const int want_gradient = grad_ratios != NULL || grad_rates != NULL;
+	rc = phbc_time_forward(t->ctx, nbatch, ratios, rates, nrates);
+	if (rc == 1) return fail(PHB_EINVAL, "calculate_partials: a sample has a negative branch length (node older than its parent)");
+	if (rc) return dev_fail(rc);
+	for (int attempt = 0; attempt < 2; attempt++) {
+		phbc_eval_opts o;
+		fill_opts(t, &o, want_gradient, 0);
+		o.batch_count = nbatch;
+		if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
+		if ((rc = phbc_time_backward(t->ctx, nbatch, nrates, include_jacobian, want_gradient, lnl, log_jacobian, grad_ratios, grad_rates)))
+			return dev_fail(rc);
+		int any_inf = 0;
+		for (int b = 0; b < nbatch; b++) any_inf |= isinf(lnl[b]);
+		if (any_inf && !t->scale) { /* treelikelihood.c:1496-1519 */
+			fprintf(stdout, "_calculate: rescaling (batch)\n");
+			t->scale = 1;
+			continue;
+		}
+		break;
+	}
+	for (int b = 0; b < nbatch; b++) /* treelikelihood.c:328-332 */
+		if (isnan(lnl[b]) || isinf(lnl[b])) {
+			if (grad_ratios)
+				for (int i = 0; i < t->T - 1; i++) grad_ratios[(size_t)b * (t->T - 1) + i] = NAN;
+			if (grad_rates)
+				for (int i = 0; i < nrates; i++) grad_rates[(size_t)b * nrates + i] = NAN;
+		}
+	phb_tlk_update_all_nodes(t); /* device partials now belong to the last sample */
 	return PHB_OK;
 }
 

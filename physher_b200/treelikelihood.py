@@ -62,6 +62,8 @@ SYMBOLS = [
     ("phb_tlk_stream", C.c_void_p, [C.c_void_p]),
     ("phb_tlk_synchronize", C.c_int, [C.c_void_p]),
     ("phb_tlk_gradient_batch", C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp]),
+    ("phb_tlk_set_time_tree", C.c_int, [C.c_void_p, _dp]),
+    ("phb_tlk_gradient_batch_time", C.c_int, [C.c_void_p, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
     ("phb_tlk_kernel_time", C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_longlong)]),
     ("phb_tlk_launch_count", C.c_longlong, [C.c_void_p]),
 ]
@@ -273,6 +275,25 @@ class SingleTreeLikelihood:
         self._check(self.lib.phb_tlk_gradient_batch(self.h, B, a.ctypes.data_as(_dp), lnl.ctypes.data_as(_dp),
                                                     grad.ctypes.data_as(_dp) if want_gradient else None))
         return lnl, grad
+
+    # -- time trees ---------------------------------------------------------------------------
+    def set_time_tree(self, tip_heights):
+        a = _f64(tip_heights)
+        assert a.shape == (self.T,)
+        self._check(self.lib.phb_tlk_set_time_tree(self.h, a.ctypes.data_as(_dp)))
+
+    def gradient_batch_time(self, ratios, rates, include_jacobian=False, want_gradient=True):
+        """B samples of (ratios | root height)[T-1] and clock rates -> lnl[B], log_jacobian[B], grad_ratios[B][T-1], grad_rates[B][R]."""
+        r, c = _f64(ratios), _f64(rates)
+        assert r.ndim == 2 and r.shape[1] == self.T - 1 and c.ndim == 2 and c.shape[0] == r.shape[0] and c.shape[1] in (1, self.N)
+        B, R = r.shape[0], c.shape[1]
+        lnl, lj = np.zeros(B), np.zeros(B)
+        gr = np.zeros((B, self.T - 1)) if want_gradient else None
+        gc = np.zeros((B, R)) if want_gradient else None
+        self._check(self.lib.phb_tlk_gradient_batch_time(
+            self.h, B, r.ctypes.data_as(_dp), c.ctypes.data_as(_dp), R, int(bool(include_jacobian)), lnl.ctypes.data_as(_dp),
+            lj.ctypes.data_as(_dp), gr.ctypes.data_as(_dp) if want_gradient else None, gc.ctypes.data_as(_dp) if want_gradient else None))
+        return lnl, lj, gr, gc
 
     def kernel_time(self):
         """(total ms, launches) of the dominant kernel since OPT_TIMING was switched on."""
