@@ -37,6 +37,7 @@
 /* non-static helpers of treelikelihood.c that its header does not list */
 extern void gradient_ratios(SingleTreeLikelihood *tlk, const double *branch_gradient, double *gradient);
 extern void gradient_clock(SingleTreeLikelihood *tlk, const double *branch_gradient, double *gradient);
+extern void gradient_discrete_sitemodel(SingleTreeLikelihood *tlk, const double *branch_gradient, const double *branch_lengths, double *gradient);
 extern void update_eigen_system(SubstitutionModel *m);
 
 typedef struct Backend {
@@ -48,7 +49,7 @@ typedef struct Backend {
 	double (*ref_dlogP)(Model *, const Parameter *);
 	void (*ref_free)(Model *);
 	int N, S, C;
-	double *bl, *rates, *props, *freqs, *evec, *eval, *ivec, *P, *dP, *branch_gradient;
+	double *bl, *rates, *props, *freqs, *evec, *eval, *ivec, *P, *dP, *branch_gradient, *cat_gradient, *site_bl;
 	int have_model; /* the substitution model has been pushed at least once */
 	long long evaluations;
 } Backend;
@@ -196,8 +197,13 @@ double *phb_physher_gradient(Model *self) {
 	Backend *b = backend_of_tlk(tlk);
 	if (!b) return TreeLikelihood_gradient(self);
 	const int flags = tlk->prepared_gradient;
-	if (flags & ~((TREELIKELIHOOD_FLAG_TREE_MODEL) | (TREELIKELIHOOD_FLAG_BRANCH_MODEL))) {
-		fprintf(stderr, "physher_b200: gradient flags 0x%x include site/substitution-model parameters: not on the device path\n", flags);
+	if (flags & ~((TREELIKELIHOOD_FLAG_TREE_MODEL) | (TREELIKELIHOOD_FLAG_BRANCH_MODEL) | (TREELIKELIHOOD_FLAG_SITE_MODEL))) {
+		fprintf(stderr, "physher_b200: gradient flags 0x%x include substitution-model parameters: not on the device path\n", flags);
+		exit(2);
+	}
+	if ((flags & (TREELIKELIHOOD_FLAG_SITE_MODEL)) && (tlk->sm->proportions != NULL || tlk->sm->mu != NULL)) {
+		/* gradient_pinv_sitemodel reads the CPU root partials (treelikelihood.c:2943-2975); mu rescales rates and lengths (:3245-3249) */
+		fprintf(stderr, "physher_b200: invariant-site proportion and mu gradients are not on the device path\n");
 		exit(2);
 	}
 	if (tlk->update_upper) {
@@ -229,6 +235,24 @@ double *phb_physher_gradient(Model *self) {
 				memcpy(tlk->gradient, b->branch_gradient, sizeof(double) * b->N);
 				offset += b->N;
 			}
+		}
+		if (flags & (TREELIKELIHOOD_FLAG_SITE_MODEL)) {
+			/* the device hands over cat_branch_gradient [N][C] (gradient_cat_branch_lengths, :2793); the chain through the rate
+			 * quantiles is the reference's own gradient_discrete_sitemodel / sm->derivative (:3034-3052, sitemodel.c:258-434) */
+			const int N = b->N, C = b->C;
+			if (!b->cat_gradient) {
+				b->cat_gradient = (double *)calloc((size_t)N * C, sizeof(double));
+				b->site_bl = (double *)calloc(N, sizeof(double));
+			}
+			if (phb_tlk_cat_branch_gradient(b->h, b->cat_gradient)) die("cat_branch_gradient");
+			for (int i = 0; i < N; i++) { /* branch lengths as :3228-3243 builds them; b->bl already carries rate * dt or the distance */
+				Node *n = Tree_node(tlk->tree, i);
+				b->site_bl[Node_id(n)] = Node_isroot(n) ? 0.0 : b->bl[Node_id(n)];
+			}
+			if (!time_mode) b->site_bl[Node_id(Tree_root(tlk->tree)->right)] = 0.0; /* :3249-3255 */
+			double grad_sitemodel[2] = {0.0, 0.0};
+			if (C > 1) gradient_discrete_sitemodel(tlk, b->cat_gradient, b->site_bl, grad_sitemodel);
+			if (Parameters_count(tlk->sm->rates) == 1) tlk->gradient[offset++] = grad_sitemodel[0];
 		}
 		if ((flags & (TREELIKELIHOOD_FLAG_BRANCH_MODEL)) && time_mode) gradient_clock(tlk, b->branch_gradient, tlk->gradient + offset);
 		tlk->update_upper = false;
@@ -337,7 +361,7 @@ int phb_physher_detach(Model *model) {
 	SingleTreeLikelihood_update_all_nodes(tlk);
 	phb_tlk_free(b->h);
 	free(b->bl), free(b->branch_gradient), free(b->rates), free(b->props), free(b->freqs);
-	free(b->evec), free(b->ivec), free(b->eval), free(b->P), free(b->dP);
+	free(b->evec), free(b->ivec), free(b->eval), free(b->P), free(b->dP), free(b->cat_gradient), free(b->site_bl);
 	free(b);
 	return 0;
 }

@@ -120,7 +120,16 @@ def test_unrooted_gtr_gamma_through_the_glue(libs, tipstates):
     lnl_cpu = ref.logP()
     g_cpu_exact = ref.gradient(O.FLAG_TREE_MODEL, include_root_freqs=0)
     g_cpu_default = ref.gradient(O.FLAG_TREE_MODEL, include_root_freqs=-1)
+    g_cpu_site = ref.gradient(O.FLAG_TREE_MODEL | O.FLAG_SITE_MODEL, include_root_freqs=0)  # [branches | d lnL / d gamma shape]
+    assert g_cpu_site.shape[0] == ref.N + 1
     model = L.refh_model_handle(ref.h)
+    assert G.phb_physher_attach(model, 0) == 0
+    n = L.refh_initialize_gradient(ref.h, O.FLAG_TREE_MODEL | O.FLAG_SITE_MODEL, 0)
+    L.refh_mark_dirty(ref.h)
+    g = np.ctypeslib.as_array(G.phb_physher_gradient(model), shape=(n,)).copy()
+    assert grad_err(g[:-1], g_cpu_site[:-1]) < RTOL
+    assert rel_err(g[-1], g_cpu_site[-1]) < 1e-9, "site-model (shape) gradient: device cat_branch_gradient + the reference's own chain"
+    G.phb_physher_detach(model)
     assert G.phb_physher_attach(model, 0) == 0
     assert rel_err(ref.logP(), lnl_cpu) < RTOL
     for irf, want in ((0, g_cpu_exact), (-1, g_cpu_default)):
