@@ -164,6 +164,18 @@ int phb_tlk_gradient_batch_time(phb_tlk *tlk, int nbatch, const double *ratios /
                                 int nrates, int include_jacobian, double *lnl /* [B] */, double *log_jacobian /* [B] */,
                                 double *grad_ratios /* [B][T-1] */, double *grad_rates /* [B][nrates] */);
 
+/*
+ * Site-pattern compression (SitePattern, sitepattern.h:68-82; new_SitePattern2 / _make_patterns, sitepattern.c:186-251, 731-754).
+ * alignment: encoded states [ntaxa][nsites] (DataType.encoding, datatype.c:74-91), taxa in alignment order.
+ * Out (malloc'd, release with phb_free): patterns [ntaxa][P] and weights [P] (multiplicities) in EXACTLY the order the
+ * reference's hash table yields them (hashtable.c:199-312, 414-451; hashtable_size = its initial size request, 100 at
+ * sitepattern.c:197), and optionally the pattern index of every site.  Integer work, bit-exact.
+ */
+int phb_compress_patterns(int device, int ntaxa, size_t nsites, const uint8_t *alignment, int hashtable_size, size_t *npatterns,
+                          uint8_t **patterns, double **weights, int **site_to_pattern /* may be NULL */);
+void phb_free(void *p);
+const char *phb_patterns_last_error(void);
+
 /* With PHB_OPT_TIMING on: device time (CUDA events on the tlk stream) and launch count of the dominant kernel
  * (the fused walk kernel, or the sum of the node-at-a-time kernels) since the option was set. Synchronises. */
 int phb_tlk_kernel_time(phb_tlk *tlk, double *total_ms, long long *launches);

@@ -173,13 +173,43 @@ def write_c1_time_tree_fixture():
     print("c1 time tree fixture:", B, "samples, lnL", out["ref_lnl"])
 
 
+def write_sitepattern_fixture():
+    """tests/golden/sitepatterns.npz: encoded alignments and the reference's SitePattern (patterns in ITS order, weights) for the
+    reference's own fluA alignment and for a synthetic alignment with ambiguity codes that makes its hash table grow five times."""
+    out = {}
+    doc = json.load(open(os.path.join(GOLDEN, "c1_jc69_time.json")))
+    ref = O.Reference(doc["model"])
+    pat, w, names = ref.patterns_raw()
+    seqs = doc["model"]["sitepattern"]["alignment"]["sequences"]
+    out.update(fluA_alignment=O.encode_nucleotides([seqs[n] for n in names]), fluA_patterns=pat, fluA_weights=w)
+    ref.close()
+    rng = np.random.default_rng(5)
+    T, n = 11, 30000
+    chars = np.array(list("ACGTRYN-?"))
+    base = rng.integers(0, 4, size=(1, n))
+    alnc = np.where(rng.random((T, n)) < 0.08, rng.integers(0, 9, size=(T, n)), base)
+    seqs = {f"t{i}": "".join(chars[alnc[i]]) for i in range(T)}
+    topo = syn.random_topology(T, 1)
+    spec = O.treelikelihood_spec(syn.to_newick(topo, syn.random_branch_lengths(topo, 2), list(seqs)), seqs, O.nucleotide_model_spec("jc69"))
+    ref = O.Reference(spec)
+    pat, w, names = ref.patterns_raw()
+    out.update(synth_alignment=O.encode_nucleotides([seqs[n_] for n_ in names]), synth_patterns=pat, synth_weights=w)
+    ref.close()
+    np.savez_compressed(os.path.join(GOLDEN, "sitepatterns.npz"), **out)
+    print("sitepattern fixture:", out["fluA_patterns"].shape, out["synth_patterns"].shape)
+
+
 def main():
+    if "--only-patterns" in sys.argv:
+        write_sitepattern_fixture()
+        return
     if "--only-dropin" in sys.argv:
         write_c1_dropin_fixture()
         write_c1_time_tree_fixture()
         return
     write_c1_dropin_fixture()
     write_c1_time_tree_fixture()
+    write_sitepattern_fixture()
     cwd = os.getcwd()
     os.chdir(REF_DATA)  # fixtures reference fluA.fa / tiny.fa by relative path
 

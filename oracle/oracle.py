@@ -187,6 +187,37 @@ def evaluate(pb: Problem, gradient: bool = True, partials: bool = False, matrice
     return out
 
 
+# DataType.encoding of the nucleotide data type: the NUCLEOTIDE_STATES table (datatype.c:74-91), case-insensitive;
+# letters without a meaning and '?' -> 16, every other character (gaps included) -> 17
+NUCLEOTIDE_CODES = dict(A=0, C=1, G=2, T=3, U=3, R=5, Y=6, M=7, W=8, S=9, K=10, B=11, D=12, H=13, V=14, N=15)
+
+
+def encode_nucleotides(sequences) -> np.ndarray:
+    def code(ch):
+        u = ch.upper()
+        if u in NUCLEOTIDE_CODES:
+            return NUCLEOTIDE_CODES[u]
+        return 16 if (u.isalpha() and u.isascii()) or ch == "?" else 17
+
+    return np.array([[code(ch) for ch in s] for s in sequences], dtype=np.uint8)
+
+
+def compress_patterns(alignment, hashtable_size=100):
+    """new_SitePattern2 restated (incl. the reference's pattern order): uint8 [T][nsites] -> (patterns [T][P], weights [P], site_to_pattern)."""
+    lib = _oracle()
+    a = np.ascontiguousarray(alignment, dtype=np.uint8)
+    T, n = a.shape
+    pat = np.zeros(T * n, np.uint8)
+    w = np.zeros(n)
+    smap = np.zeros(n, np.int32)
+    lib.oracle_compress_patterns.argtypes = [C.c_int, C.c_size_t, _bp, C.c_uint, _bp, _dp, _ip]
+    lib.oracle_compress_patterns.restype = C.c_long
+    P = lib.oracle_compress_patterns(T, n, a.ctypes.data_as(_bp), hashtable_size, pat.ctypes.data_as(_bp), _d(w), _i(smap))
+    if P < 0:
+        raise MemoryError("oracle_compress_patterns failed")
+    return pat[: T * P].reshape(T, P).copy(), w[:P].copy(), smap
+
+
 def time_evaluate(pb: Problem, tip_heights, ratios, rates, include_jacobian=False) -> dict:
     """Time-tree chain around `evaluate` (naive reference forms): ratios [T-1] (root entry = root height), rates [1] or [N]
     -> dict(lnl, log_jacobian, heights, bl, grad_ratios, grad_rates)."""
@@ -269,6 +300,10 @@ def _reflib():
         L.refh_time_logP.restype = C.c_double
         L.refh_time_gradient.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.refh_time_gradient.restype = C.c_double
+        L.refh_patterns_raw.argtypes = [C.c_void_p, _bp, _dp]
+        L.refh_patterns_raw.restype = C.c_int
+        L.refh_pattern_name.argtypes = [C.c_void_p, C.c_int]
+        L.refh_pattern_name.restype = C.c_char_p
         L.refh_time_tree.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.refh_time_tree.restype = C.c_int
         L.refh_set_ratios.argtypes = [C.c_void_p, _dp]
@@ -350,6 +385,14 @@ class Reference:
 
     def time_gradient(self, iters, flags=FLAG_TREE_MODEL, include_root_freqs=-1):
         return float(self.L.refh_time_gradient(self.h, flags, include_root_freqs, iters))
+
+    def patterns_raw(self):
+        """sp->patterns [sequences][P] in ALIGNMENT order, sp->weights and sp->names exactly as new_SitePattern2 left them."""
+        pat = np.zeros((self.T, self.P), np.uint8)
+        w = np.zeros(self.P)
+        n = self.L.refh_patterns_raw(self.h, pat.ctypes.data_as(_bp), _d(w))
+        names = [self.L.refh_pattern_name(self.h, i).decode() for i in range(n)]
+        return pat, w, names
 
     def time_tree(self):
         """(tip_heights[T], ratios[T-1] with the root height in the root's entry, rates[1 or N]) as the reference holds them."""

@@ -453,3 +453,101 @@ void oracle_time_backward(int T, int N, int root, const int *left, const int *ri
 	free(hg);
 	free(descendant);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Site-pattern compression (row A3): new_SitePattern2 / _make_patterns (sitepattern.c:186-251, 731-754) on top of the
+ * reference's chained hash table (hashtable.c), restated with whole-column keys: insertion at the bucket head (:262-312),
+ * growth through the prime list at load factor 0.65 with the list-reversing transfer (:199-249), iteration over buckets
+ * in index order (:414-451).  alignment [T][nsites] encoded states; returns the pattern count, fills patterns [T][P] (the
+ * caller provides room for P = nsites), weights [P] and site_to_pattern [nsites].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct PatEntry {
+	unsigned hash;
+	int first_site; /* key: the column at this site */
+	int count;
+	int next;
+} PatEntry;
+
+static unsigned pat_hash(const uint8_t *aln, int T, size_t nsites, size_t s) {
+	unsigned hash = aln[s]; /* hashtable_hash_uint8_t, sitepattern.c:71-79 */
+	for (int i = 1; i < T; i++) hash ^= aln[(size_t)i * nsites + s] + 0x9e3779b9 + (hash << 6) + (hash >> 2);
+	unsigned i = hash; /* hashfn, hashtable.c:188-197 */
+	i += ~(i << 9);
+	i ^= ((i >> 14) | (i << 18));
+	i += (i << 4);
+	i ^= ((i >> 10) | (i << 22));
+	return i;
+}
+
+static int pat_same(const uint8_t *aln, int T, size_t nsites, size_t a, size_t b) {
+	for (int i = 0; i < T; i++)
+		if (aln[(size_t)i * nsites + a] != aln[(size_t)i * nsites + b]) return 0;
+	return 1;
+}
+
+long oracle_compress_patterns(int T, size_t nsites, const uint8_t *aln, unsigned initial_size, uint8_t *patterns, double *weights,
+                              int *site_to_pattern) {
+	static const unsigned primes[] = {5,        53,       97,       193,      389,       769,       1543,      3079,      6151,
+	                                  12289,    24593,    49157,    98317,    196613,    393241,    786433,    1572869,   3145739,
+	                                  6291469,  12582917, 25165843, 50331653, 100663319, 201326611, 402653189, 805306457, 1610612741};
+	int pindex = 0;
+	for (pindex = 0; primes[pindex] < initial_size; pindex++) {
+	}
+	unsigned size = primes[pindex];
+	unsigned loadlimit = (unsigned)ceil(size * 0.65);
+	int *table = (int *)malloc(sizeof(int) * size);
+	PatEntry *entries = (PatEntry *)malloc(sizeof(PatEntry) * nsites);
+	int *entry_of_site = (int *)malloc(sizeof(int) * nsites);
+	if (!table || !entries || !entry_of_site) return -1;
+	for (unsigned i = 0; i < size; i++) table[i] = -1;
+	int length = 0;
+	for (size_t site = 0; site < nsites; site++) { /* _make_patterns */
+		const unsigned hv = pat_hash(aln, T, nsites, site);
+		int e;
+		for (e = table[hv % size]; e >= 0; e = entries[e].next) /* Hashtable_get_entry */
+			if (entries[e].hash == hv && pat_same(aln, T, nsites, site, (size_t)entries[e].first_site)) break;
+		if (e >= 0) {
+			entries[e].count++;
+			entry_of_site[site] = e;
+			continue;
+		}
+		if ((unsigned)length == loadlimit) { /* Hashtable_add -> Hashtable_expand */
+			const unsigned newsize = primes[++pindex];
+			int *nt = (int *)malloc(sizeof(int) * newsize);
+			for (unsigned i = 0; i < newsize; i++) nt[i] = -1;
+			for (unsigned i = 0; i < size; i++) {
+				int x;
+				while ((x = table[i]) >= 0) {
+					table[i] = entries[x].next;
+					const unsigned idx = entries[x].hash % newsize;
+					entries[x].next = nt[idx];
+					nt[idx] = x;
+				}
+			}
+			free(table);
+			table = nt;
+			size = newsize;
+			loadlimit = (unsigned)ceil(size * 0.65);
+		}
+		e = length++;
+		entries[e].hash = hv;
+		entries[e].first_site = (int)site;
+		entries[e].count = 1;
+		entries[e].next = table[hv % size];
+		table[hv % size] = e;
+		entry_of_site[site] = e;
+	}
+	int *pos = (int *)malloc(sizeof(int) * (length ? length : 1));
+	long index = 0;
+	for (unsigned i = 0; i < size; i++) /* Hashtable_init_iterator / Hashtable_next, then sitepattern.c:229-240 */
+		for (int e = table[i]; e >= 0; e = entries[e].next) {
+			weights[index] = entries[e].count;
+			for (int t = 0; t < T; t++) patterns[(size_t)t * length + index] = aln[(size_t)t * nsites + entries[e].first_site];
+			pos[e] = (int)index;
+			index++;
+		}
+	if (site_to_pattern)
+		for (size_t site = 0; site < nsites; site++) site_to_pattern[site] = pos[entry_of_site[site]];
+	free(pos), free(table), free(entries), free(entry_of_site);
+	return index;
+}

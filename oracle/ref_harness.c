@@ -431,3 +431,13 @@ void refh_set_clock_rate(void *vh, double rate) {
 	Parameters_set_value(bm->rates, 0, rate);
 	SingleTreeLikelihood_update_all_nodes(h->tlk);
 }
+
+/* sp->patterns [size][count] in alignment order (NOT re-mapped to node ids), sp->weights; returns sp->size */
+int refh_patterns_raw(void *vh, uint8_t *patterns, double *weights) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	SitePattern *sp = tlk->sp;
+	for (int i = 0; i < sp->size; i++) memcpy(patterns + (size_t)i * sp->count, sp->patterns[i], sp->count);
+	memcpy(weights, sp->weights, sizeof(double) * sp->count);
+	return sp->size;
+}
+const char *refh_pattern_name(void *vh, int i) { return ((RefH *)vh)->tlk->sp->names[i]; }

@@ -11,11 +11,12 @@ from .treelikelihood import (  # noqa: F401
     KERNELS_GENERIC,
     PhysherB200Error,
     SingleTreeLikelihood,
+    compress_patterns,
     device_count,
     load_library,
 )
 
 __all__ = [
-    "SingleTreeLikelihood", "PhysherB200Error", "load_library", "device_count",
+    "SingleTreeLikelihood", "PhysherB200Error", "load_library", "device_count", "compress_patterns",
     "FLAG_TREE_MODEL", "KERNELS_AUTO", "KERNELS_GENERIC", "KERNELS_FUSED",
 ]

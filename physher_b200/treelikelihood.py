@@ -64,6 +64,10 @@ SYMBOLS = [
     ("phb_tlk_gradient_batch", C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp]),
     ("phb_tlk_set_time_tree", C.c_int, [C.c_void_p, _dp]),
     ("phb_tlk_gradient_batch_time", C.c_int, [C.c_void_p, C.c_int, _dp, _dp, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
+    ("phb_compress_patterns", C.c_int, [C.c_int, C.c_int, C.c_size_t, _bp, C.c_int, C.POINTER(C.c_size_t), C.POINTER(_bp), C.POINTER(_dp),
+                                        C.POINTER(_ip)]),
+    ("phb_free", None, [C.c_void_p]),
+    ("phb_patterns_last_error", C.c_char_p, []),
     ("phb_tlk_kernel_time", C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_longlong)]),
     ("phb_tlk_launch_count", C.c_longlong, [C.c_void_p]),
 ]
@@ -99,6 +103,33 @@ def device_count() -> int:
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def compress_patterns(alignment, device=0, hashtable_size=100, want_site_map=True):
+    """SitePattern construction (new_SitePattern2, sitepattern.c:186-251) on the device.
+    alignment: uint8 [ntaxa][nsites] encoded states.  Returns (patterns uint8 [ntaxa][P], weights float64 [P], site_to_pattern int32 [nsites])
+    with the patterns in the reference's own order."""
+    lib = load_library()
+    a = np.ascontiguousarray(alignment, dtype=np.uint8)
+    assert a.ndim == 2
+    T, n = a.shape
+    npat = C.c_size_t(0)
+    pat, w, smap = _bp(), _dp(), _ip()
+    rc = lib.phb_compress_patterns(int(device), T, n, a.ctypes.data_as(_bp), int(hashtable_size), C.byref(npat), C.byref(pat), C.byref(w),
+                                   C.byref(smap) if want_site_map else None)
+    if rc != 0:
+        raise PhysherB200Error(f"[{rc}] {(lib.phb_patterns_last_error() or b'').decode()}")
+    try:
+        P = npat.value
+        patterns = np.ctypeslib.as_array(pat, shape=(T, P)).copy()
+        weights = np.ctypeslib.as_array(w, shape=(P,)).copy()
+        site_map = np.ctypeslib.as_array(smap, shape=(n,)).copy() if want_site_map else None
+    finally:
+        lib.phb_free(pat)
+        lib.phb_free(w)
+        if want_site_map:
+            lib.phb_free(smap)
+    return patterns, weights, site_map
 
 
 class SingleTreeLikelihood:
