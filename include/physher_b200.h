@@ -96,6 +96,11 @@ int phb_tlk_set_branch_length(phb_tlk *tlk, int node, double bl); /* + SingleTre
 void phb_tlk_update_all_nodes(phb_tlk *tlk);
 int phb_tlk_update_one_node(phb_tlk *tlk, int node);
 
+/* Model.store / Model.restore of the tree likelihood (_singleTreeLikelihood_store / _restore, treelikelihood.c:116-161):
+ * restore returns to the stored inputs and the stored lnL without recomputation (MCMC reject). */
+int phb_tlk_store(phb_tlk *tlk);
+int phb_tlk_restore(phb_tlk *tlk);
+
 /* SingleTreeLikelihood_use_rescaling / _rescaling (treelikelihood.h:163-164) */
 int phb_tlk_use_rescaling(phb_tlk *tlk, int use);
 int phb_tlk_rescaling(const phb_tlk *tlk);

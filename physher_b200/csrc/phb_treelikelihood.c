@@ -57,6 +57,14 @@ struct phb_tlk {
 	int *post_tip_order, *pre_tip_order, *post_chunk_tip0, *pre_chunk_tip0;
 	int post_first_tips, pre_first_tips;
 	int have_time_tree;
+
+	/* host mirrors of the small model inputs + the stored state of store / restore (MCMC, treelikelihood.c:116-161) */
+	double *h_evec, *h_eval, *h_ivec, *h_freqs, *h_rates, *h_props;
+	int has_store;
+	double *st_bl, *st_evec, *st_eval, *st_ivec, *st_freqs, *st_rates, *st_props;
+	double st_lk;
+	int st_update, st_scale, st_have_eigen;
+	int eigen_changed, freqs_changed, site_changed, bl_changed; /* since the last store */
 };
 
 static _Thread_local char g_err[512] = "";
@@ -585,6 +593,8 @@ void phb_tlk_free(phb_tlk *t) {
 	free(t->pre_tip_order);
 	free(t->post_chunk_tip0);
 	free(t->pre_chunk_tip0);
+	free(t->h_evec), free(t->h_eval), free(t->h_ivec), free(t->h_freqs), free(t->h_rates), free(t->h_props);
+	free(t->st_bl), free(t->st_evec), free(t->st_eval), free(t->st_ivec), free(t->st_freqs), free(t->st_rates), free(t->st_props);
 	free(t);
 }
 
@@ -635,6 +645,17 @@ int phb_tlk_set_pattern_weights(phb_tlk *t, const double *w) {
 int phb_tlk_set_eigen(phb_tlk *t, const double *evec, const double *eval, const double *ivec) {
 	int rc = phbc_upload_eigen(t->ctx, evec, eval, ivec);
 	if (rc) return dev_fail(rc);
+	if (!t->h_evec) {
+		t->h_evec = (double *)malloc(sizeof(double) * t->S * t->S);
+		t->h_ivec = (double *)malloc(sizeof(double) * t->S * t->S);
+		t->h_eval = (double *)malloc(sizeof(double) * t->S);
+	}
+	if (evec != t->h_evec) {
+		memcpy(t->h_evec, evec, sizeof(double) * t->S * t->S);
+		memcpy(t->h_ivec, ivec, sizeof(double) * t->S * t->S);
+		memcpy(t->h_eval, eval, sizeof(double) * t->S);
+	}
+	t->eigen_changed = 1;
 	t->have_eigen = 1;
 	t->have_matrices = 0;
 	phb_tlk_update_all_nodes(t); /* substitution model changed: _treelikelihood_handle_change, :73-114 */
@@ -652,6 +673,9 @@ int phb_tlk_set_matrices(phb_tlk *t, const double *P, const double *dP) {
 int phb_tlk_set_frequencies(phb_tlk *t, const double *freqs) {
 	int rc = phbc_upload_freqs(t->ctx, freqs);
 	if (rc) return dev_fail(rc);
+	if (!t->h_freqs) t->h_freqs = (double *)malloc(sizeof(double) * t->S);
+	if (freqs != t->h_freqs) memcpy(t->h_freqs, freqs, sizeof(double) * t->S);
+	t->freqs_changed = 1;
 	t->have_freqs = 1;
 	phb_tlk_update_all_nodes(t);
 	return PHB_OK;
@@ -660,6 +684,15 @@ int phb_tlk_set_frequencies(phb_tlk *t, const double *freqs) {
 int phb_tlk_set_site_model(phb_tlk *t, const double *rates, const double *props) {
 	int rc = phbc_upload_site_model(t->ctx, rates, props);
 	if (rc) return dev_fail(rc);
+	if (!t->h_rates) {
+		t->h_rates = (double *)malloc(sizeof(double) * t->C);
+		t->h_props = (double *)malloc(sizeof(double) * t->C);
+	}
+	if (rates != t->h_rates) {
+		memcpy(t->h_rates, rates, sizeof(double) * t->C);
+		memcpy(t->h_props, props, sizeof(double) * t->C);
+	}
+	t->site_changed = 1;
 	t->have_site = 1;
 	phb_tlk_update_all_nodes(t);
 	return PHB_OK;
@@ -670,9 +703,10 @@ int phb_tlk_set_branch_lengths(phb_tlk *t, const double *bl) {
 		if (n != t->root && bl[n] < 0) /* treelikelihood.c:1659-1662 exits on a negative length */
 			return fail(PHB_EINVAL, "calculate_partials: node %d branch length = %E", n, bl[n]);
 	}
-	memcpy(t->bl, bl, sizeof(double) * t->N);
+	if (bl != t->bl) memcpy(t->bl, bl, sizeof(double) * t->N);
 	t->have_bl = 1;
 	t->bl_dirty = 1;
+	t->bl_changed = 1;
 	phb_tlk_update_all_nodes(t);
 	return PHB_OK;
 }
@@ -682,6 +716,7 @@ int phb_tlk_set_branch_length(phb_tlk *t, int node, double bl) {
 	if (bl < 0) return fail(PHB_EINVAL, "calculate_partials: node %d branch length = %E", node, bl);
 	t->bl[node] = bl;
 	t->bl_dirty = 1;
+	t->bl_changed = 1;
 	return phb_tlk_update_one_node(t, node);
 }
 
@@ -931,6 +966,73 @@ int phb_tlk_gradient_batch(phb_tlk *t, int nbatch, const double *bl, double *lnl
 		}
 	/* the single-sample state (t->bl, t->lk) is untouched but device partials now belong to the last sample */
 	phb_tlk_update_all_nodes(t);
+	return PHB_OK;
+}
+
+/* ------------------------------------------------------------------------------------------- */
+/* store / restore (MCMC accept / reject)                                                      */
+/* ------------------------------------------------------------------------------------------- */
+
+/*
+ * _singleTreeLikelihood_store (treelikelihood.c:126-150): remember the state a rejected proposal returns to.  The reference
+ * flips between two sets of partials and matrices; this backend recomputes every node per evaluation and keeps no partials
+ * across calls (the fused walk has none), so the stored state is the inputs the likelihood is a function of -- branch
+ * lengths, eigen system, frequencies, site model, rescaling flag -- and the cached lnL with its dirty flag.
+ */
+int phb_tlk_store(phb_tlk *t) {
+	const size_t S = t->S, C = t->C, N = t->N;
+	if (!t->st_bl) {
+		t->st_bl = (double *)malloc(sizeof(double) * N);
+		t->st_evec = (double *)malloc(sizeof(double) * S * S);
+		t->st_ivec = (double *)malloc(sizeof(double) * S * S);
+		t->st_eval = (double *)malloc(sizeof(double) * S);
+		t->st_freqs = (double *)malloc(sizeof(double) * S);
+		t->st_rates = (double *)malloc(sizeof(double) * C);
+		t->st_props = (double *)malloc(sizeof(double) * C);
+		if (!t->st_bl || !t->st_evec || !t->st_ivec || !t->st_eval || !t->st_freqs || !t->st_rates || !t->st_props) return fail(PHB_ENOMEM, "out of memory");
+	}
+	memcpy(t->st_bl, t->bl, sizeof(double) * N);
+	t->st_have_eigen = t->have_eigen && t->h_evec != NULL;
+	if (t->st_have_eigen) {
+		memcpy(t->st_evec, t->h_evec, sizeof(double) * S * S);
+		memcpy(t->st_ivec, t->h_ivec, sizeof(double) * S * S);
+		memcpy(t->st_eval, t->h_eval, sizeof(double) * S);
+	}
+	if (t->h_freqs) memcpy(t->st_freqs, t->h_freqs, sizeof(double) * S);
+	if (t->h_rates) {
+		memcpy(t->st_rates, t->h_rates, sizeof(double) * C);
+		memcpy(t->st_props, t->h_props, sizeof(double) * C);
+	}
+	t->st_lk = t->lk; /* tlk->stored_lk */
+	t->st_update = t->update;
+	t->st_scale = t->scale;
+	t->eigen_changed = t->freqs_changed = t->site_changed = t->bl_changed = 0;
+	t->has_store = 1;
+	return PHB_OK;
+}
+
+/*
+ * _singleTreeLikelihood_restore + _treelikelihood_handle_restore (treelikelihood.c:116-124, 152-161): back to the stored
+ * state WITHOUT recomputation -- tlk->lk = tlk->stored_lk, and a following calculate() returns it from the cache.  Only the
+ * inputs that changed since the store travel to the device again.  Models given as explicit matrices are not stored: after a
+ * restore the caller sets them again (which marks the object dirty).
+ */
+int phb_tlk_restore(phb_tlk *t) {
+	if (!t->has_store) return fail(PHB_ESTATE, "phb_tlk_restore without phb_tlk_store");
+	int rc;
+	if (t->bl_changed) {
+		memcpy(t->bl, t->st_bl, sizeof(double) * t->N);
+		t->bl_dirty = 1;
+	}
+	if (t->eigen_changed && t->st_have_eigen && (rc = phb_tlk_set_eigen(t, t->st_evec, t->st_eval, t->st_ivec))) return rc;
+	if (t->freqs_changed && t->h_freqs && (rc = phb_tlk_set_frequencies(t, t->st_freqs))) return rc;
+	if (t->site_changed && t->h_rates && (rc = phb_tlk_set_site_model(t, t->st_rates, t->st_props))) return rc;
+	t->scale = t->st_scale;
+	t->lk = t->st_lk;
+	t->update = t->st_update || (t->eigen_changed && !t->st_have_eigen); /* explicit matrices were not stored */
+	if (!t->update) memset(t->update_nodes, 0, t->N);
+	t->update_upper = 1; /* the gradient buffer belongs to the rejected state */
+	t->eigen_changed = t->freqs_changed = t->site_changed = t->bl_changed = 0;
 	return PHB_OK;
 }
 

@@ -48,6 +48,8 @@ SYMBOLS = [
     ("phb_tlk_set_branch_length", C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     ("phb_tlk_update_all_nodes", None, [C.c_void_p]),
     ("phb_tlk_update_one_node", C.c_int, [C.c_void_p, C.c_int]),
+    ("phb_tlk_store", C.c_int, [C.c_void_p]),
+    ("phb_tlk_restore", C.c_int, [C.c_void_p]),
     ("phb_tlk_use_rescaling", C.c_int, [C.c_void_p, C.c_int]),
     ("phb_tlk_rescaling", C.c_int, [C.c_void_p]),
     ("phb_tlk_set_option", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
@@ -244,6 +246,12 @@ class SingleTreeLikelihood:
 
     def update_one_node(self, node):
         self._check(self.lib.phb_tlk_update_one_node(self.h, int(node)))
+
+    def store(self):
+        self._check(self.lib.phb_tlk_store(self.h))
+
+    def restore(self):
+        self._check(self.lib.phb_tlk_restore(self.h))
 
     def use_rescaling(self, use: bool):
         self._check(self.lib.phb_tlk_use_rescaling(self.h, int(use)))

@@ -167,6 +167,44 @@ def test_caching_semantics():
     tlk.close()
 
 
+def test_store_restore_mcmc_reject():
+    """Model.store / restore (treelikelihood.c:116-161): a rejected proposal returns to the stored lnL WITHOUT recomputation."""
+    pb = _synthetic_problem(25, 300, 4, 4, seed=12)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    lnl0, g0 = tlk.calculate(), tlk.gradient()
+    tlk.store()
+    # proposal: new branch lengths, a new substitution model and a new site model
+    m2 = models.gtr([0.2, 0.1, 0.3, 0.1, 0.2, 0.1], [0.3, 0.2, 0.2, 0.3])
+    r2, p2 = models.discrete_gamma(1.7, 4)
+    tlk.set_branch_lengths(pb.bl * 1.3)
+    tlk.set_eigen(m2.evec, m2.eval, m2.ivec)
+    tlk.set_frequencies(m2.freqs)
+    tlk.set_site_model(r2, p2)
+    lnl1 = tlk.calculate()
+    assert lnl1 != lnl0
+    n0 = tlk.launch_count()
+    tlk.restore()
+    assert tlk.calculate() == lnl0 and tlk.launch_count() == n0, "restore must not recompute"
+    g = tlk.gradient()  # the gradient buffer belonged to the rejected state: recomputed from the restored inputs
+    assert tlk.launch_count() > n0 and grad_err(g, g0) < 1e-13 and tlk.calculate() == lnl0
+    # accept path: store after a move, then a second reject comes back to the moved state
+    tlk.set_branch_length(5, pb.bl[5] * 2.0)
+    lnl2 = tlk.calculate()
+    tlk.store()
+    tlk.set_branch_length(7, pb.bl[7] * 0.5)
+    assert tlk.calculate() != lnl2
+    tlk.restore()
+    assert tlk.calculate() == lnl2
+    pb.bl[5] *= 2.0
+    assert rel_err(lnl2, O.evaluate(pb, gradient=False)["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), O.evaluate(pb)["grad"]) < RTOL
+    tlk.close()
+    fresh = phb.SingleTreeLikelihood.from_problem(pb)
+    with pytest.raises(phb.PhysherB200Error, match="without phb_tlk_store"):
+        fresh.restore()
+    fresh.close()
+
+
 def test_unrooted_convention_and_root_entries():
     pb = _synthetic_problem(20, 128, 4, 4, seed=10)
     tlk = phb.SingleTreeLikelihood.from_problem(pb)
