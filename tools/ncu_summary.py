@@ -32,6 +32,8 @@ def main():
     ap.add_argument("rep")
     ap.add_argument("--out")
     ap.add_argument("--title", default="")
+    ap.add_argument("--traffic", default="", help="KEY: record dram bytes per launch (mean over the captured launches) in profiles/traffic.json "
+                                                    "under KEY, e.g. c2:auto -- bench.py reads it for roofline.traffic")
     a = ap.parse_args()
     lines = [f"# {a.title or a.rep}", "", f"source: `{a.rep}` (ncu --set full --clock-control none --import-source on)", ""]
     raw = ncu_csv(a.rep, "raw")
@@ -73,6 +75,23 @@ def main():
         blocks.append((c, tot))
     for k, (c, tot) in enumerate(blocks):
         lines += [f"SASS instruction mix, launch {k} (executed warp instructions): " + ", ".join(f"{op} {n/tot*100:.1f}%" for op, n in c.most_common(14)), ""]
+    if a.traffic:
+        import json
+        import os
+
+        def num(row, key):
+            i = hdr.index(key)
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[units[i]]
+            return float(row[i].replace(",", "")) * scale
+
+        per = [num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum") for r in raw[2:]]
+        ms = [float(r[hdr.index("gpu__time_duration.sum")].replace(",", "")) * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}[units[hdr.index("gpu__time_duration.sum")]]
+              for r in raw[2:]]
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+        d = json.load(open(path)) if os.path.exists(path) else {}
+        d[a.traffic] = {"dram_bytes_per_launch": sum(per) / len(per), "launches": len(per), "kernel": raw[2][hdr.index("Kernel Name")][:80],
+                        "ncu_ms_per_launch": sum(ms) / len(ms), "source": os.path.basename(a.rep)}
+        json.dump(d, open(path, "w"), indent=1, sort_keys=True)
     text = "\n".join(lines)
     if a.out:
         open(a.out, "w").write(text + "\n")
