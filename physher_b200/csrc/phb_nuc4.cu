@@ -148,21 +148,40 @@ __device__ __forceinline__ double butterfly2(double v0, double v1, int lane) {
 	return r;
 }
 
-template <int C, bool SCALE, bool GRAD>
-__global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) {
+// y[u] = M x[u] for the PPT patterns of a thread: every matrix element is read from shared memory ONCE and feeds PPT
+// independent FMA chains (half the LDS traffic and twice the instruction-level parallelism per pattern at PPT = 2)
+template <int PPT>
+__device__ __forceinline__ void matvec_smem_n(const double *__restrict__ M, const double (&x)[PPT][4], double (&y)[PPT][4]) {
+	const double2 *M2 = reinterpret_cast<const double2 *>(M);
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const double2 a = M2[2 * i], b = M2[2 * i + 1];
+#pragma unroll
+		for (int u = 0; u < PPT; u++) y[u][i] = fma(a.x, x[u][0], fma(a.y, x[u][1], fma(b.x, x[u][2], b.y * x[u][3])));
+	}
+}
+
+// A thread owns PPT (pattern, category) cells of the tile: category c and patterns pl0 + u * PBT (PBT = PB / PPT), i.e. cell
+// index c * PB + pl0 + u * PBT in every [half][NUC4_NT] cell array (slots, lower rows) -- the layouts do not depend on PPT.
+template <int C, bool SCALE, bool GRAD, int PPT>
+__global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params prm) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
-	constexpr int PB = NUC4_NT / C;
+	constexpr int PB = NUC4_NT / C;      // patterns per tile
+	constexpr int NTHR = NUC4_NT / PPT;  // threads per CTA
+	constexpr int PBT = PB / PPT;        // patterns per u-plane
+	static_assert(PBT % 32 == 0 || PPT == 1, "a warp must not mix categories");
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const int c = tid / PB, pl = tid - c * PB;
+	const int c = tid / PBT, pl0 = tid - c * PBT;
+	const int cell0 = c * PB + pl0;  // cell index of u = 0; u adds u * PBT
 	constexpr Nuc4Stage lay = nuc4_stage_layout(C, PB);
 	uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
 	unsigned char *stage0 = smem_raw + 128;
-	unsigned char *slot_cell = stage0 + 2 * lay.bytes + tid * 16;  // this thread's cell in slot 0
+	unsigned char *slot_cell = stage0 + 2 * lay.bytes + cell0 * 16;  // this thread's first cell in slot 0
 	double *xch = reinterpret_cast<double *>(stage0 + 2 * lay.bytes + (size_t)prm.nslots * NUC4_SLOT_BYTES);
 	double *invLw = xch + 4 * C * PB;
 	double *sfslot = invLw + PB;  // [nslots][NT] thread-private copies (SCALE only)
 	const uint32_t my_mat = lay.mat_off + c * 128;  // this thread's category inside a staged matrix group
-	const uint32_t my_code = lay.code_off + pl;
+	const uint32_t my_code = lay.code_off + pl0;
 
 	if (tid == 0) {
 		mbar_init(&bars[0], 1);
@@ -174,14 +193,14 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 	uint32_t loads = 0;  // chunk loads consumed so far (CTA-uniform): stage = loads & 1, parity = (loads >> 1) & 1
 	const double prop_c = (C == 1) ? 1.0 : prm.props[c];
 	double cta_lnl = 0.0;
-	unsigned char *row_cell = GRAD ? reinterpret_cast<unsigned char *>(prm.lower) + (size_t)blockIdx.x * prm.n_post * NUC4_ROW_BYTES + tid * 16 : nullptr;
+	unsigned char *row_cell = GRAD ? reinterpret_cast<unsigned char *>(prm.lower) + (size_t)blockIdx.x * prm.n_post * NUC4_ROW_BYTES + cell0 * 16 : nullptr;
 	double *my_gacc = nullptr;
 
 	// work items = (sample, pattern tile), sample-major; a CTA owns a CONTIGUOUS range, so it touches at most
 	// prm.phases consecutive samples and keeps one private accumulator row set per touched sample (deterministic sums)
-	const long long nitems = (long long)prm.ntiles * prm.nbatch;
 	// (a single sample keeps the strided assignment: tiles are few and coarse, and the strided order spreads the CTAs that
 	// get one tile more evenly over the SMs)
+	const long long nitems = (long long)prm.ntiles * prm.nbatch;
 	const bool strided = prm.nbatch == 1;
 	const int item0 = strided ? (int)blockIdx.x : (int)(blockIdx.x * nitems / gridDim.x);
 	const int item1 = strided ? (int)nitems : (int)((blockIdx.x + 1) * nitems / gridDim.x);
@@ -189,7 +208,7 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 	const int b_first = strided ? 0 : item0 / prm.ntiles;
 	int cur_b = -1;
 	auto flush_lnl = [&](int b) {
-		if (lane == 0) prm.cta_lnl[((size_t)blockIdx.x * prm.phases + (b - b_first)) * (NUC4_NT / 32) + warp] = (c == 0) ? cta_lnl : 0.0;  // one partial lnL per warp
+		if (lane == 0) prm.cta_lnl[((size_t)blockIdx.x * prm.phases + (b - b_first)) * (NTHR / 32) + warp] = (c == 0) ? cta_lnl : 0.0;  // one partial lnL per warp
 	};
 
 	for (int item = item0; item < item1; item += item_step) {
@@ -198,16 +217,16 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 			if (cur_b >= 0) flush_lnl(cur_b);
 			cur_b = bsmp;
 			cta_lnl = 0.0;
-			if (GRAD) my_gacc = prm.gacc + (((size_t)blockIdx.x * prm.phases + (bsmp - b_first)) * (NUC4_NT / 32) + warp) * prm.N;
+			if (GRAD) my_gacc = prm.gacc + (((size_t)blockIdx.x * prm.phases + (bsmp - b_first)) * (NTHR / 32) + warp) * prm.N;
 		}
-		const int p = tile * PB + pl;
-		const bool live = p < prm.P;
 		const uint8_t *tile_codes_post = prm.tip_codes + (size_t)tile * prm.T * PB;
 		const uint8_t *tile_codes_pre = prm.tip_codes + ((size_t)prm.ntiles + tile) * prm.T * PB;
 
 		// ------------------------------------------------------------------ post-order
-		double out[4] = {1.0, 1.0, 1.0, 1.0};
-		double sf_acc = 0.0;  // SCALE: log scaling factor of the value currently in `out`
+		double out[PPT][4];
+		double sf_acc[PPT];  // SCALE: log scaling factor of the value currently in `out`
+#pragma unroll
+		for (int u = 0; u < PPT; u++) out[u][0] = out[u][1] = out[u][2] = out[u][3] = 1.0, sf_acc[u] = 0.0;
 		{
 			const int nchunks = (prm.n_post + NUC4_CHUNK - 1) / NUC4_CHUNK;
 			// one TMA stage: descriptors, walk-ordered matrices, walk-ordered tip codes of the chunk
@@ -238,45 +257,66 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 					const int a_idx = desc[j].a_idx, b_idx = desc[j].b_idx, dst_slot = desc[j].dst_slot;
 					const double *MA = reinterpret_cast<const double *>(mats + j * 2 * C * 128);
 					const double *MB = reinterpret_cast<const double *>(mats + (j * 2 + 1) * C * 128);
-					double ma[4], mb[4];
-					double sf_in = 0.0;
+					double ma[PPT][4], mb[PPT][4];
+					double sf_in[PPT];
+#pragma unroll
+					for (int u = 0; u < PPT; u++) sf_in[u] = 0.0;
 					// operand b of kinds 1 and 2 is the previous op's result, still in `out`
 					if (kind == 0) {
-						tip_message(MA, cds[a_idx * PB], ma);
-						tip_message(MB, cds[b_idx * PB], mb);
+#pragma unroll
+						for (int u = 0; u < PPT; u++) {
+							tip_message(MA, cds[a_idx * PB + u * PBT], ma[u]);
+							tip_message(MB, cds[b_idx * PB + u * PBT], mb[u]);
+						}
 					} else {
-						matvec_smem(MB, out, mb);
-						if (SCALE) sf_in = sf_acc;
+						matvec_smem_n<PPT>(MB, out, mb);
+						if (SCALE) {
+#pragma unroll
+							for (int u = 0; u < PPT; u++) sf_in[u] = sf_acc[u];
+						}
 						if (kind == 1) {
-							tip_message(MA, cds[a_idx * PB], ma);
+#pragma unroll
+							for (int u = 0; u < PPT; u++) tip_message(MA, cds[a_idx * PB + u * PBT], ma[u]);
 						} else {
-							double x[4];
-							cell_load(slot_cell + a_idx * NUC4_SLOT_BYTES, x);
-							matvec_smem(MA, x, ma);
-							if (SCALE) sf_in += sfslot[a_idx * NUC4_NT + tid];
+							double x[PPT][4];
+#pragma unroll
+							for (int u = 0; u < PPT; u++) {
+								cell_load(slot_cell + a_idx * NUC4_SLOT_BYTES + u * PBT * 16, x[u]);
+								if (SCALE) sf_in[u] += sfslot[a_idx * NUC4_NT + cell0 + u * PBT];
+							}
+							matvec_smem_n<PPT>(MA, x, ma);
 						}
 					}
 #pragma unroll
-					for (int i = 0; i < 4; i++) out[i] = ma[i] * mb[i];
+					for (int u = 0; u < PPT; u++)
+#pragma unroll
+						for (int i = 0; i < 4; i++) out[u][i] = ma[u][i] * mb[u][i];
 					if (SCALE) {
 						// SingleTreeLikelihood_scalePartials (treelikelihood.c:1790-1836): max over categories and states
-						double m = fmax(fmax(out[0], out[1]), fmax(out[2], out[3]));
 						double *mx = xch + ((first + j) & 1) * C * PB;
-						mx[c * PB + pl] = m;
-						__syncthreads();
-						m = mx[pl];
-						for (int cc = 1; cc < C; cc++) m = fmax(m, mx[cc * PB + pl]);
-						double sf = 0.0;
-						if (m < prm.threshold) {
 #pragma unroll
-							for (int i = 0; i < 4; i++) out[i] /= m;
-							sf = log(m);
+						for (int u = 0; u < PPT; u++) mx[cell0 + u * PBT] = fmax(fmax(out[u][0], out[u][1]), fmax(out[u][2], out[u][3]));
+						__syncthreads();
+#pragma unroll
+						for (int u = 0; u < PPT; u++) {
+							const int pl = pl0 + u * PBT;
+							double m = mx[pl];
+							for (int cc = 1; cc < C; cc++) m = fmax(m, mx[cc * PB + pl]);
+							double sf = 0.0;
+							if (m < prm.threshold) {
+#pragma unroll
+								for (int i = 0; i < 4; i++) out[u][i] /= m;
+								sf = log(m);
+							}
+							sf_acc[u] = sf + sf_in[u];
+							if (dst_slot >= 0) sfslot[dst_slot * NUC4_NT + cell0 + u * PBT] = sf_acc[u];
 						}
-						sf_acc = sf + sf_in;
-						if (dst_slot >= 0) sfslot[dst_slot * NUC4_NT + tid] = sf_acc;
 					}
-					if (dst_slot >= 0) cell_store(slot_cell + dst_slot * NUC4_SLOT_BYTES, out);  // parked for a later kind-2 op
-					if (GRAD) row_store(row_cell + (size_t)(unsigned)(first + j) * NUC4_ROW_BYTES, out);
+#pragma unroll
+					for (int u = 0; u < PPT; u++) {
+						if (dst_slot >= 0) cell_store(slot_cell + dst_slot * NUC4_SLOT_BYTES + u * PBT * 16, out[u]);  // parked for a later kind-2 op
+						if (GRAD) row_store(row_cell + (size_t)(unsigned)(first + j) * NUC4_ROW_BYTES + u * PBT * 16, out[u]);
+					}
 				}
 				loads++;
 				__syncthreads();  // everyone is done with this stage before it is refilled
@@ -286,19 +326,28 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 		// ------------------------------------------------------------------ root integration
 		// integrate_partials_4_SSE + node_log_likelihoods_4_SSE + weighted sum
 		{
-			double site = prm.freqs[0] * out[0] + prm.freqs[1] * out[1] + prm.freqs[2] * out[2] + prm.freqs[3] * out[3];
-			site *= prop_c;
-			xch[c * PB + pl] = site;
+#pragma unroll
+			for (int u = 0; u < PPT; u++) {
+				double site = prm.freqs[0] * out[u][0] + prm.freqs[1] * out[u][1] + prm.freqs[2] * out[u][2] + prm.freqs[3] * out[u][3];
+				xch[cell0 + u * PBT] = site * prop_c;
+			}
 			__syncthreads();
 			if (c == 0) {
-				double L = xch[pl];
-				for (int cc = 1; cc < C; cc++) L += xch[cc * PB + pl];
-				double plk = log(L);
-				if (SCALE) plk += sf_acc;
-				const double w = live ? prm.weights[p] : 0.0;
-				if (live && prm.nbatch == 1) prm.pattern_lnl[p] = plk;
-				invLw[pl] = w / L;  // unscaled path: w_k / L_k; scaled paths use ratios instead
-				double v = live ? plk * w : 0.0;
+				double v = 0.0;
+#pragma unroll
+				for (int u = 0; u < PPT; u++) {
+					const int pl = pl0 + u * PBT;
+					const int p = tile * PB + pl;
+					const bool live = p < prm.P;
+					double L = xch[pl];
+					for (int cc = 1; cc < C; cc++) L += xch[cc * PB + pl];
+					double plk = log(L);
+					if (SCALE) plk += sf_acc[u];
+					const double w = live ? prm.weights[p] : 0.0;
+					if (live && prm.nbatch == 1) prm.pattern_lnl[p] = plk;
+					invLw[pl] = w / L;  // unscaled path: w_k / L_k; scaled paths use ratios instead
+					v += live ? plk * w : 0.0;
+				}
 				v = phb_warp_sum(v);
 				if (lane == 0) cta_lnl += v;  // warps of category 0 only; summed below
 			}
@@ -307,8 +356,14 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 
 		// ------------------------------------------------------------------ pre-order + gradients
 		if (GRAD) {
-			const double sgrad = invLw[pl];
-			const double wk = live ? prm.weights[p] : 0.0;
+			double sgrad[PPT], wk[PPT];
+#pragma unroll
+			for (int u = 0; u < PPT; u++) {
+				const int pl = pl0 + u * PBT;
+				const int p = tile * PB + pl;
+				sgrad[u] = invLw[pl];
+				wk[u] = p < prm.P ? prm.weights[p] : 0.0;
+			}
 			const int nchunks = (prm.n_pre + NUC4_CHUNK - 1) / NUC4_CHUNK;
 			auto issue = [&](int ch, uint32_t ld, int tips) {
 				const int first = ch * NUC4_CHUNK;
@@ -322,25 +377,33 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 				if (cbytes) bulk_g2s(dst + lay.code_off, tile_codes_pre + (size_t)(tips >> 5) * PB, cbytes, &bars[ld & 1]);
 			};
 			// lower rows of the internal children of one op (kind: 0 tip-tip, 1 tip-internal, 2 internal-internal)
-			auto fetch = [&](const phbc_pre_op *d, double (&A)[4], double (&B)[4]) {
+			auto fetch = [&](const phbc_pre_op *d, double (&A)[PPT][4], double (&B)[PPT][4]) {
 				const int kind = d->kind;
-				if (kind == 2) row_load(row_cell + (size_t)(unsigned)d->a_row * NUC4_ROW_BYTES, A);
-				if (kind != 0) row_load(row_cell + (size_t)(unsigned)d->b_row * NUC4_ROW_BYTES, B);
+#pragma unroll
+				for (int u = 0; u < PPT; u++) {
+					if (kind == 2) row_load(row_cell + (size_t)(unsigned)d->a_row * NUC4_ROW_BYTES + u * PBT * 16, A[u]);
+					if (kind != 0) row_load(row_cell + (size_t)(unsigned)d->b_row * NUC4_ROW_BYTES + u * PBT * 16, B[u]);
+				}
 			};
 			// One op. Operands (lower rows of the children) are in xa / xb; as soon as they have been consumed the
 			// same registers receive the NEXT op's rows, a full op ahead of their use.  Returns the two gradient terms.
 			auto pre_op = [&](const phbc_pre_op *desc, const unsigned char *mats, const uint8_t *cds, int j, int cnt, bool more_chunks,
-			                  double (&xa)[4], double (&xb)[4], double (&ureg)[4], double &va, double &vb) {
+			                  double (&xa)[PPT][4], double (&xb)[PPT][4], double (&ureg)[PPT][4], double &va, double &vb) {
 				const phbc_pre_op *d = desc + j;
 				const int kind = d->kind;
 				const double *MP = reinterpret_cast<const double *>(mats + (j * 3 + 0) * C * 128);
 				const double *MA = reinterpret_cast<const double *>(mats + (j * 3 + 1) * C * 128);
 				const double *MB = reinterpret_cast<const double *>(mats + (j * 3 + 2) * C * 128);
-				double W[4], ma[4], mb[4];
-				if (kind == 2) matvec_smem(MA, xa, ma);
-				else tip_message(MA, cds[d->a_code * PB], ma);
-				if (kind == 0) tip_message(MB, cds[d->b_code * PB], mb);
-				else matvec_smem(MB, xb, mb);
+				double W[PPT][4], ma[PPT][4], mb[PPT][4];
+				if (kind == 2) matvec_smem_n<PPT>(MA, xa, ma);
+				else {
+#pragma unroll
+					for (int u = 0; u < PPT; u++) tip_message(MA, cds[d->a_code * PB + u * PBT], ma[u]);
+				}
+				if (kind == 0) {
+#pragma unroll
+					for (int u = 0; u < PPT; u++) tip_message(MB, cds[d->b_code * PB + u * PBT], mb[u]);
+				} else matvec_smem_n<PPT>(MB, xb, mb);
 				// xa / xb are dead: prefetch the next op's rows into them (across the chunk boundary too)
 				if (j + 1 < cnt) {
 					fetch(d + 1, xa, xb);
@@ -351,69 +414,97 @@ __global__ void __launch_bounds__(NUC4_NT, 3) k_nuc4_walk(const Nuc4Params prm) 
 				if (d->u_kind == PHBC_W_ROOT) {
 					// children of the root: u = P_s L_s [o pi] (treelikelihood.c:2145-2154)
 #pragma unroll
-					for (int i = 0; i < 4; i++) W[i] = prm.wroot[i];
-				} else {
-					if (d->u_kind == PHBC_W_SLOT) cell_load(slot_cell + d->u_slot * NUC4_SLOT_BYTES, ureg);  // else: left by the preceding op
-					matvec_smem(MP, ureg, W);  // P_p u_p
-				}
-				double ua[4], ub[4];
+					for (int u = 0; u < PPT; u++)
 #pragma unroll
-				for (int i = 0; i < 4; i++) ua[i] = W[i] * mb[i], ub[i] = W[i] * ma[i];
+						for (int i = 0; i < 4; i++) W[u][i] = prm.wroot[i];
+				} else {
+					if (d->u_kind == PHBC_W_SLOT) {
+#pragma unroll
+						for (int u = 0; u < PPT; u++) cell_load(slot_cell + d->u_slot * NUC4_SLOT_BYTES + u * PBT * 16, ureg[u]);  // else: left by the preceding op
+					}
+					matvec_smem_n<PPT>(MP, ureg, W);  // P_p u_p
+				}
+				double ua[PPT][4], ub[PPT][4];
+#pragma unroll
+				for (int u = 0; u < PPT; u++)
+#pragma unroll
+					for (int i = 0; i < 4; i++) ua[u][i] = W[u][i] * mb[u][i], ub[u][i] = W[u][i] * ma[u][i];
 				// numerators: sum_i f_i u_n[i] (dP_n L_n)[i] with dP_n L_n = Q (P_n L_n)
-				double na = 0.0, nb = 0.0, da = 0.0, db = 0.0;
+				double na[PPT], nb[PPT], da[PPT], db[PPT];
+#pragma unroll
+				for (int u = 0; u < PPT; u++) na[u] = nb[u] = da[u] = db[u] = 0.0;
 #pragma unroll
 				for (int i = 0; i < 4; i++) {
-					const double qa = fma(prm.Q[4 * i], ma[0], fma(prm.Q[4 * i + 1], ma[1], fma(prm.Q[4 * i + 2], ma[2], prm.Q[4 * i + 3] * ma[3])));
-					const double qb = fma(prm.Q[4 * i], mb[0], fma(prm.Q[4 * i + 1], mb[1], fma(prm.Q[4 * i + 2], mb[2], prm.Q[4 * i + 3] * mb[3])));
-					const double fa = prm.fq[i] * ua[i], fb = prm.fq[i] * ub[i];
-					na = fma(fa, qa, na);
-					nb = fma(fb, qb, nb);
-					if (SCALE) {
-						da = fma(fa, ma[i], da);
-						db = fma(fb, mb[i], db);
+#pragma unroll
+					for (int u = 0; u < PPT; u++) {
+						const double qa = fma(prm.Q[4 * i], ma[u][0], fma(prm.Q[4 * i + 1], ma[u][1], fma(prm.Q[4 * i + 2], ma[u][2], prm.Q[4 * i + 3] * ma[u][3])));
+						const double qb = fma(prm.Q[4 * i], mb[u][0], fma(prm.Q[4 * i + 1], mb[u][1], fma(prm.Q[4 * i + 2], mb[u][2], prm.Q[4 * i + 3] * mb[u][3])));
+						const double fa = prm.fq[i] * ua[u][i], fb = prm.fq[i] * ub[u][i];
+						na[u] = fma(fa, qa, na[u]);
+						nb[u] = fma(fb, qb, nb[u]);
+						if (SCALE) {
+							da[u] = fma(fa, ma[u][i], da[u]);
+							db[u] = fma(fb, mb[u][i], db[u]);
+						}
 					}
 				}
+				va = vb = 0.0;
 				if (!SCALE) {
-					va = na * sgrad;
-					vb = nb * sgrad;
+#pragma unroll
+					for (int u = 0; u < PPT; u++) va = fma(na[u], sgrad[u], va), vb = fma(nb[u], sgrad[u], vb);
 				} else {
 					// rescale the upper partials like the reference (their scale cancels in the ratios below)
 					double *plane = xch;  // 4 planes: max_a, max_b, den_a, den_b
 					__syncthreads();      // previous op's readers are done
-					plane[0 * C * PB + c * PB + pl] = fmax(fmax(ua[0], ua[1]), fmax(ua[2], ua[3]));
-					plane[1 * C * PB + c * PB + pl] = fmax(fmax(ub[0], ub[1]), fmax(ub[2], ub[3]));
-					plane[2 * C * PB + c * PB + pl] = da * prop_c;
-					plane[3 * C * PB + c * PB + pl] = db * prop_c;
+#pragma unroll
+					for (int u = 0; u < PPT; u++) {
+						const int ci = cell0 + u * PBT;
+						plane[0 * C * PB + ci] = fmax(fmax(ua[u][0], ua[u][1]), fmax(ua[u][2], ua[u][3]));
+						plane[1 * C * PB + ci] = fmax(fmax(ub[u][0], ub[u][1]), fmax(ub[u][2], ub[u][3]));
+						plane[2 * C * PB + ci] = da[u] * prop_c;
+						plane[3 * C * PB + ci] = db[u] * prop_c;
+					}
 					__syncthreads();
-					double mxa = 0.0, mxb = 0.0, dta = 0.0, dtb = 0.0;
-					for (int cc = 0; cc < C; cc++) {
-						mxa = fmax(mxa, plane[0 * C * PB + cc * PB + pl]);
-						mxb = fmax(mxb, plane[1 * C * PB + cc * PB + pl]);
-						dta += plane[2 * C * PB + cc * PB + pl];
-						dtb += plane[3 * C * PB + cc * PB + pl];
-					}
-					if (mxa < prm.threshold) {
 #pragma unroll
-						for (int i = 0; i < 4; i++) ua[i] /= mxa;
-					}
-					if (mxb < prm.threshold) {
+					for (int u = 0; u < PPT; u++) {
+						const int pl = pl0 + u * PBT;
+						double mxa = 0.0, mxb = 0.0, dta = 0.0, dtb = 0.0;
+						for (int cc = 0; cc < C; cc++) {
+							mxa = fmax(mxa, plane[0 * C * PB + cc * PB + pl]);
+							mxb = fmax(mxb, plane[1 * C * PB + cc * PB + pl]);
+							dta += plane[2 * C * PB + cc * PB + pl];
+							dtb += plane[3 * C * PB + cc * PB + pl];
+						}
+						if (mxa < prm.threshold) {
 #pragma unroll
-						for (int i = 0; i < 4; i++) ub[i] /= mxb;
+							for (int i = 0; i < 4; i++) ua[u][i] /= mxa;
+						}
+						if (mxb < prm.threshold) {
+#pragma unroll
+							for (int i = 0; i < 4; i++) ub[u][i] /= mxb;
+						}
+						// exact: one site denominator shared by the categories; compat: per-category ratio
+						// (gradient_cat_branch_lengths_aux, treelikelihood.c:2721-2738)
+						va += prm.compat ? na[u] / da[u] * wk[u] : na[u] / dta * wk[u];
+						vb += prm.compat ? nb[u] / db[u] * wk[u] : nb[u] / dtb * wk[u];
 					}
-					// exact: one site denominator shared by the categories; compat: per-category ratio
-					// (gradient_cat_branch_lengths_aux, treelikelihood.c:2721-2738)
-					va = prm.compat ? na / da * wk : na / dta * wk;
-					vb = prm.compat ? nb / db * wk : nb / dtb * wk;
 				}
-				if (kind == 2) cell_store(slot_cell + d->a_slot * NUC4_SLOT_BYTES, ua);  // parked until its own op comes up
-				if (kind != 0) {
 #pragma unroll
-					for (int i = 0; i < 4; i++) ureg[i] = ub[i];  // child b's op is the next one
+				for (int u = 0; u < PPT; u++) {
+					if (kind == 2) cell_store(slot_cell + d->a_slot * NUC4_SLOT_BYTES + u * PBT * 16, ua[u]);  // parked until its own op comes up
+					if (kind != 0) {
+#pragma unroll
+						for (int i = 0; i < 4; i++) ureg[u][i] = ub[u][i];  // child b's op is the next one
+					}
 				}
 			};
 			if (tid == 0) issue(0, loads, prm.pre_first_tips);
 			mbar_wait(&bars[loads & 1], (loads >> 1) & 1);
-			double xa[4] = {0, 0, 0, 0}, xb[4] = {0, 0, 0, 0}, ureg[4] = {0, 0, 0, 0};
+			double xa[PPT][4], xb[PPT][4], ureg[PPT][4];
+#pragma unroll
+			for (int u = 0; u < PPT; u++)
+#pragma unroll
+				for (int i = 0; i < 4; i++) xa[u][i] = xb[u][i] = ureg[u][i] = 0.0;
 			fetch(reinterpret_cast<const phbc_pre_op *>(stage0 + (loads & 1) * lay.bytes + lay.desc_off), xa, xb);
 			for (int ch = 0; ch < nchunks; ch++) {
 				const unsigned char *st = stage0 + (loads & 1) * lay.bytes;
@@ -538,13 +629,13 @@ __global__ void k_nuc4_encode_tips(int T, int P, int PB, int ntiles, int tip_kin
 // per-warp partials.  grid (ceil(N/32), nbatch), block (32, NUC4_FY): x = node, y strides over the CTAs of the walk launch
 // that touched the sample (all of them for a single sample; contiguous item ranges for a batch, see k_nuc4_walk).
 #define NUC4_FY 16
-__global__ void __launch_bounds__(32 * NUC4_FY) k_nuc4_finalize(int N, int C, int PB, int grid, int phases, int ntiles, int nbatch, int root,
+__global__ void __launch_bounds__(32 * NUC4_FY) k_nuc4_finalize(int N, int C, int nw /* warps per walk CTA */, int grid, int phases, int ntiles, int nbatch, int root,
                                                                 const double *__restrict__ cta_lnl, const double *__restrict__ gacc, int want_grad,
                                                                 const double *__restrict__ props, const double *__restrict__ rates,
                                                                 double *__restrict__ cat_grad, double *__restrict__ result) {
-	constexpr int warps = NUC4_NT / 32;
+	constexpr int warps = NUC4_NT / 32;  // upper bound of nw
 	__shared__ double red[NUC4_FY][warps][33];
-	const int wpc = PB / 32;
+	const int wpc = nw / C;  // warps per category
 	const int tx = threadIdx.x, ty = threadIdx.y;
 	const int b = blockIdx.y;
 	const long long nitems = (long long)ntiles * nbatch;
@@ -569,7 +660,7 @@ __global__ void __launch_bounds__(32 * NUC4_FY) k_nuc4_finalize(int N, int C, in
 		double s = 0.0;
 		for (int cta = c_lo + ty; cta < c_hi; cta += NUC4_FY) {
 			const int ph = phase_of(cta);
-			if (ph >= 0 && tx < warps) s += cta_lnl[((size_t)cta * phases + ph) * warps + tx];
+			if (ph >= 0 && tx < nw) s += cta_lnl[((size_t)cta * phases + ph) * nw + tx];
 		}
 		s = phb_warp_sum(s);
 		if (tx == 0) red[ty][0][32] = s;
@@ -590,14 +681,15 @@ __global__ void __launch_bounds__(32 * NUC4_FY) k_nuc4_finalize(int N, int C, in
 		for (int cta = c_lo + ty; cta < c_hi; cta += NUC4_FY) {
 			const int ph = phase_of(cta);
 			if (ph < 0) continue;
-			const double *base = gacc + ((size_t)cta * phases + ph) * warps * N + n;
+			const double *base = gacc + ((size_t)cta * phases + ph) * nw * N + n;
 #pragma unroll
-			for (int w = 0; w < warps; w++) s8[w] += base[(size_t)w * N];  // 8 independent loads in flight
+			for (int w = 0; w < warps; w++)
+				if (w < nw) s8[w] += base[(size_t)w * N];  // independent loads in flight
 		}
 #pragma unroll
 	for (int w = 0; w < warps; w++) red[ty][w][tx] = s8[w];
 	__syncthreads();
-	if (ty < warps) {  // thread row w sums warp-row w over the CTA slices, fixed order
+	if (ty < nw) {  // thread row w sums warp-row w over the CTA slices, fixed order
 		double tot = 0.0;
 		for (int k = 0; k < NUC4_FY; k++) tot += red[k][ty][tx];
 		red[0][ty][tx] = tot;  // slice 0 of row ty is read only by this thread above
@@ -676,18 +768,20 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	}
 
 	// launch geometry: persistent CTAs, two per SM when shared memory allows
+	// two patterns per thread (every matrix element read once feeds two FMA chains) wherever a warp still holds one category
 	typedef void (*walk_fn)(const Nuc4Params);
 	static const walk_fn table[4][2][2] = {
-	    {{k_nuc4_walk<1, false, false>, k_nuc4_walk<1, false, true>}, {k_nuc4_walk<1, true, false>, k_nuc4_walk<1, true, true>}},
-	    {{k_nuc4_walk<2, false, false>, k_nuc4_walk<2, false, true>}, {k_nuc4_walk<2, true, false>, k_nuc4_walk<2, true, true>}},
-	    {{k_nuc4_walk<4, false, false>, k_nuc4_walk<4, false, true>}, {k_nuc4_walk<4, true, false>, k_nuc4_walk<4, true, true>}},
-	    {{k_nuc4_walk<8, false, false>, k_nuc4_walk<8, false, true>}, {k_nuc4_walk<8, true, false>, k_nuc4_walk<8, true, true>}},
+	    {{k_nuc4_walk<1, false, false, 2>, k_nuc4_walk<1, false, true, 2>}, {k_nuc4_walk<1, true, false, 2>, k_nuc4_walk<1, true, true, 2>}},
+	    {{k_nuc4_walk<2, false, false, 2>, k_nuc4_walk<2, false, true, 2>}, {k_nuc4_walk<2, true, false, 2>, k_nuc4_walk<2, true, true, 2>}},
+	    {{k_nuc4_walk<4, false, false, 2>, k_nuc4_walk<4, false, true, 2>}, {k_nuc4_walk<4, true, false, 2>, k_nuc4_walk<4, true, true, 2>}},
+	    {{k_nuc4_walk<8, false, false, 1>, k_nuc4_walk<8, false, true, 1>}, {k_nuc4_walk<8, true, false, 1>, k_nuc4_walk<8, true, true, 1>}},
 	};
+	const int ppt = C == 8 ? 1 : 2, nthr = NUC4_NT / ppt;
 	const int ci = C == 1 ? 0 : (C == 2 ? 1 : (C == 4 ? 2 : 3));
 	walk_fn kern = table[ci][o->scale ? 1 : 0][o->want_gradient ? 1 : 0];
 	PHBC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;
-	PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NUC4_NT, smem));
+	PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthr, smem));
 	if (per_sm < 1) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "nuc4 walk kernel does not fit on an SM (smem %zu)", smem);
 		return -1;
@@ -705,7 +799,7 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 			if (ph > phases) phases = ph;
 		}
 	}
-	const int warps = NUC4_NT / 32;
+	const int warps = nthr / 32;
 	// scratch: walk matrices per sample, per-CTA lower rows, per-(CTA, sample phase, warp) gradient rows and lnL
 	const long long mats_stride = (long long)(2 * ctx->n_post + 3 * ctx->n_pre) * C * 16;
 	const size_t mats_bytes = (size_t)mats_stride * nbatch * sizeof(double);
@@ -791,11 +885,11 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	}
 	int trc;
 	if ((trc = phbc_time_begin(ctx))) return trc;
-	kern<<<grid, NUC4_NT, smem, ctx->stream>>>(prm);
+	kern<<<grid, nthr, smem, ctx->stream>>>(prm);
 	ctx->launches++;
 	if ((trc = phbc_time_end(ctx))) return trc;
 	double *result = ctx->d_result + (size_t)o->batch_index * (1 + N);
-	k_nuc4_finalize<<<dim3((N + 31) / 32, nbatch), dim3(32, NUC4_FY), 0, ctx->stream>>>(N, C, PB, grid, phases, ntiles, nbatch, ctx->root, ctx->d_nuc4_cta_lnl,
+	k_nuc4_finalize<<<dim3((N + 31) / 32, nbatch), dim3(32, NUC4_FY), 0, ctx->stream>>>(N, C, warps, grid, phases, ntiles, nbatch, ctx->root, ctx->d_nuc4_cta_lnl,
 	                                                                         ctx->d_walk_gacc, o->want_gradient, ctx->d_props, ctx->d_rates,
 	                                                                         ctx->d_cat_grad, result);
 	ctx->launches++;
