@@ -124,6 +124,13 @@ int phb_tlk_gradient(phb_tlk *tlk, const double **grad);
 /* cat_branch_gradient [N][C] of the last gradient call (gradient_cat_branch_lengths, treelikelihood.c:2793) */
 int phb_tlk_cat_branch_gradient(phb_tlk *tlk, double *out /* [N][C] */);
 
+/* Substitution-model parameter gradients: the node sweep of calculate_dlnl_dQ (treelikelihood.c:2337-2583).  M holds `nsets` sets of
+ * per-node matrices [nsets][N][C][S][S] (row-major like P), e.g. dP/d theta_k from m->dPdp(m, k, mat, bl * rate_c)
+ * (substmodel.c:469-489, :2421); out[k] = sum over non-root nodes (not the root's right child when unrooted, :2408) and patterns of
+ * w_p / L_p * sum_c prop_c sum_i f_i U_n[c,p,i] (M_k[n,c] L_n[c,p])_i.  Honours PHB_OPT_INCLUDE_ROOT_FREQS and rescaling.
+ * Runs on the node-at-a-time kernels (materialised upper partials). */
+int phb_tlk_matrix_gradient(phb_tlk *tlk, int nsets, const double *M, double *out /* [nsets] */);
+
 /* Copy of one partials buffer [C][P][S]: index < N lower partials of that node, >= N upper partials of node
  * index-N (tlk->partials[..][index], treelikelihood.h:62; used by asr.c:60).  Generic kernels only. */
 int phb_tlk_get_partials(phb_tlk *tlk, int index, double *out);

@@ -199,7 +199,35 @@ def write_sitepattern_fixture():
     print("sitepattern fixture:", out["fluA_patterns"].shape, out["synth_patterns"].shape)
 
 
+def write_dlnl_dq_fixture():
+    """tests/golden/dlnl_dq_gtr_g4.npz: a GTR+G4 problem, the reference's dP/d theta matrices (m->dPdp) for its five free rate
+    parameters and the reference's own calculate_dlnl_dQ values (include_root_freqs false / true)."""
+    T, sites = 12, 400
+    topo = syn.random_topology(T, 100)
+    bl = syn.random_branch_lengths(topo, 101)
+    pat = syn.random_patterns(T, sites, 4, 0.3, 102, unknown_frac=0.02)
+    names = [f"t{i}" for i in range(T)]
+    seqs = dict(zip(names, syn.sequences_from_patterns(pat, syn.NUCLEOTIDES)))
+    gtr = O.nucleotide_model_spec("gtr", [0.1, 0.2, 0.3, 0.4], [0.05, 0.3, 0.1, 0.15, 0.3, 0.1])
+    ref = O.Reference(O.treelikelihood_spec(syn.to_newick(topo, bl, names), seqs, gtr, categories=4, alpha=0.5, tipstates=True))
+    pb = ref.problem()
+    K = 5
+    d = dict(left=pb.left, right=pb.right, parent=pb.parent, root=np.int32(pb.root), nstate=np.int32(4), tip_states=pb.tip_states,
+             weights=pb.weights, freqs=pb.freqs, rates=pb.rates, props=pb.props, bl=pb.bl, evec=pb.evec, eval=pb.eval, ivec=pb.ivec,
+             use_tip_states=np.int32(1), unrooted=np.int32(1), time_elapsed=pb.meta["time_elapsed"],
+             dPdp=np.stack([ref.dPdp(k) for k in range(K)]),
+             ref_dlnl_dq=np.array([ref.dlnl_dQ(k, 0) for k in range(K)]),
+             ref_dlnl_dq_root_freqs=np.array([ref.dlnl_dQ(k, 1) for k in range(K)]),
+             ref_lnl=np.float64(ref.logP()))
+    ref.close()
+    np.savez_compressed(os.path.join(GOLDEN, "dlnl_dq_gtr_g4.npz"), **d)
+    print("dlnl_dQ fixture:", d["dPdp"].shape, d["ref_dlnl_dq"])
+
+
 def main():
+    if "--only-dq" in sys.argv:
+        write_dlnl_dq_fixture()
+        return
     if "--only-patterns" in sys.argv:
         write_sitepattern_fixture()
         return
@@ -210,6 +238,7 @@ def main():
     write_c1_dropin_fixture()
     write_c1_time_tree_fixture()
     write_sitepattern_fixture()
+    write_dlnl_dq_fixture()
     cwd = os.getcwd()
     os.chdir(REF_DATA)  # fixtures reference fluA.fa / tiny.fa by relative path
 

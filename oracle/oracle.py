@@ -218,6 +218,36 @@ def compress_patterns(alignment, hashtable_size=100):
     return pat[: T * P].reshape(T, P).copy(), w[:P].copy(), smap
 
 
+def matrix_gradient(pb: Problem, M) -> np.ndarray:
+    """Node sweep of calculate_dlnl_dQ (treelikelihood.c:2337-2583) from the restatement's own lower / upper partials:
+    out[k] = sum_n sum_p w_p / L_p sum_c prop_c sum_i f_i U_n[c,p,i] (M_k[n,c] L_n[c,p])_i, unscaled form."""
+    assert not pb.scale
+    res = evaluate(pb, partials=True)
+    N, Cc, P, S, T = pb.nnodes, pb.ncat, pb.npatterns, pb.nstate, pb.ntips
+    lower = res["lower"].copy()
+    for t in range(T):  # tips: indicator vectors, ones for unknown states
+        if pb.use_tip_states:
+            tp = np.ones((P, S))
+            known = pb.tip_states[t] < S
+            tp[known] = np.eye(S)[pb.tip_states[t][known]]
+        else:
+            tp = pb.tip_partials[t]
+        lower[t] = tp[None]
+    fq = np.ones(S) if pb.include_root_freqs else pb.freqs
+    wl = pb.weights / np.exp(res["pattern_lnl"])
+    skip = {int(pb.root)} | ({int(pb.right[pb.root])} if pb.unrooted else set())
+    out = np.zeros(len(M))
+    for k, Mk in enumerate(M):
+        tot = 0.0
+        for n in range(N):
+            if n in skip:
+                continue
+            ml = np.einsum("cij,cpj->cpi", Mk[n], lower[n])
+            tot += float(np.einsum("c,p,i,cpi,cpi->", pb.props, wl, fq, res["upper"][n], ml))
+        out[k] = tot
+    return out
+
+
 def time_evaluate(pb: Problem, tip_heights, ratios, rates, include_jacobian=False) -> dict:
     """Time-tree chain around `evaluate` (naive reference forms): ratios [T-1] (root entry = root height), rates [1] or [N]
     -> dict(lnl, log_jacobian, heights, bl, grad_ratios, grad_rates)."""
@@ -304,6 +334,9 @@ def _reflib():
         L.refh_patterns_raw.restype = C.c_int
         L.refh_pattern_name.argtypes = [C.c_void_p, C.c_int]
         L.refh_pattern_name.restype = C.c_char_p
+        L.refh_dPdp.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.refh_dlnl_dQ.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.refh_dlnl_dQ.restype = C.c_double
         L.refh_time_tree.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.refh_time_tree.restype = C.c_int
         L.refh_set_ratios.argtypes = [C.c_void_p, _dp]
@@ -393,6 +426,14 @@ class Reference:
         n = self.L.refh_patterns_raw(self.h, pat.ctypes.data_as(_bp), _d(w))
         names = [self.L.refh_pattern_name(self.h, i).decode() for i in range(n)]
         return pat, w, names
+
+    def dPdp(self, index):
+        out = np.zeros((self.N, self.C, self.S, self.S))
+        self.L.refh_dPdp(self.h, int(index), _d(out))
+        return out
+
+    def dlnl_dQ(self, index, include_root_freqs=0):
+        return float(self.L.refh_dlnl_dQ(self.h, int(index), int(include_root_freqs)))
 
     def time_tree(self):
         """(tip_heights[T], ratios[T-1] with the root height in the root's entry, rates[1 or N]) as the reference holds them."""

@@ -441,3 +441,30 @@ int refh_patterns_raw(void *vh, uint8_t *patterns, double *weights) {
 	return sp->size;
 }
 const char *refh_pattern_name(void *vh, int i) { return ((RefH *)vh)->tlk->sp->names[i]; }
+
+/* ---- substitution-model parameter gradients (calculate_dlnl_dQ, treelikelihood.c:2337-2583) ---- */
+
+/* dP/d theta_index per (node, category) straight from m->dPdp at t = bl * rate_c (what :2421 builds), [N][C][S][S] */
+void refh_dPdp(void *vh, int index, double *out) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	int N = Tree_node_count(tlk->tree), S = tlk->m->nstate, C = tlk->cat_count;
+	double *bl = (double *)malloc(sizeof(double) * N);
+	refh_branch_lengths(vh, bl, NULL);
+	tlk->m->dQ_need_update = true;
+	for (int id = 0; id < N; id++)
+		for (int c = 0; c < C; c++) {
+			size_t off = ((size_t)id * C + c) * S * S;
+			if (id == Node_id(Tree_root(tlk->tree))) memset(out + off, 0, sizeof(double) * S * S);
+			else tlk->m->dPdp(tlk->m, index, out + off, bl[id] * tlk->sm->get_rate(tlk->sm, c));
+		}
+	free(bl);
+}
+
+/* the reference's own value for parameter `index`: lnL + upper partials through TreeLikelihood_gradient (tree flags,
+ * include_root_freqs as given), then calculate_dlnl_dQ on its pattern likelihoods */
+double refh_dlnl_dQ(void *vh, int index, int include_root_freqs) {
+	RefH *h = (RefH *)vh;
+	double tmp[8];
+	refh_gradient(vh, TREELIKELIHOOD_FLAG_TREE_MODEL, include_root_freqs, tmp, 8);
+	return calculate_dlnl_dQ(h->tlk, index, h->tlk->pattern_lk + h->tlk->sp->count);
+}

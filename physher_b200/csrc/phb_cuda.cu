@@ -689,6 +689,81 @@ int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	return 0;
 }
 
+// out[k] = sum over nodes n (not the root, not `skip`) and categories of props[c] * cat[k][n][c]  -- one block per set, fixed order
+__global__ void k_matrix_gradient_sum(int N, int C, int root, int skip, const double *__restrict__ cat /* [nsets][N][C] */,
+                                      const double *__restrict__ props, double *__restrict__ out) {
+	__shared__ double red[256];
+	const double *g = cat + (size_t)blockIdx.x * N * C;
+	double s = 0.0;
+	for (int e = threadIdx.x; e < N * C; e += blockDim.x) {
+		const int n = e / C, c = e - n * C;
+		if (n != root && n != skip) s += g[e] * (C == 1 ? 1.0 : props[c]);
+	}
+	red[threadIdx.x] = s;
+	__syncthreads();
+	for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+		if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
+/*
+ * Node sweep of calculate_dlnl_dQ (treelikelihood.c:2337-2583): for each of `nsets` per-node matrix sets M (e.g. dP/d theta from
+ * m->dPdp), out[k] = sum_n sum_p w_p / L_p sum_c prop_c sum_i f_i U_n[c,p,i] (M_k[n,c] L_n[c,p])_i over the non-root nodes
+ * (and not `skip_node`: the root's right child of an unrooted tree, :2408).  Needs materialised upper partials, so the
+ * evaluation runs on the node-at-a-time kernels (tensor-core lower / upper kernels for 20 / 61 states).
+ */
+extern "C" int phbc_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int nsets, const double *M_host, int skip_node, double *lnl,
+                                    double *out_host) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	const size_t S = ctx->S, C = ctx->C, P = ctx->P, N = ctx->N;
+	if (C > GEN_MAXC) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "generic kernels support at most %d rate categories", GEN_MAXC);
+		return -1;
+	}
+	phbc_eval_opts e = *o;
+	e.want_gradient = 1;
+	e.materialize_uppers = 1;
+	e.batch_count = 1;
+	int rc = phbc_dmma_supported(ctx, &e) && e.kernels != 1 ? phbc_dmma_evaluate(ctx, &e) : phbc_generic_evaluate(ctx, &e);
+	if (rc) return rc;
+	const size_t set = N * C * S * S;
+	double *d_M = NULL, *d_cat = NULL, *d_out = NULL;
+	cudaError_t err = cudaMalloc((void **)&d_M, (size_t)nsets * set * sizeof(double));
+	if (err == cudaSuccess) err = cudaMalloc((void **)&d_cat, (size_t)nsets * N * C * sizeof(double));
+	if (err == cudaSuccess) err = cudaMalloc((void **)&d_out, (size_t)nsets * sizeof(double));
+	if (err == cudaSuccess) err = cudaMemcpyAsync(d_M, M_host, (size_t)nsets * set * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+	const size_t gtiles = (P + GEN_PGRAD - 1) / GEN_PGRAD;
+	if (err == cudaSuccess) {
+		rc = phbc_ensure_scratch(ctx, N * C * gtiles * sizeof(double));
+		const size_t smem = 2 * S * S * sizeof(double);
+		if (!rc && smem > 48 * 1024) err = cudaFuncSetAttribute(k_generic_branch_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		Bufs b = phbc_make_bufs(ctx);
+		for (int k = 0; k < nsets && !rc && err == cudaSuccess; k++) {
+			k_generic_branch_gradient<<<dim3((unsigned)gtiles, (unsigned)(N - 1)), GEN_PGRAD, smem, ctx->stream>>>(
+			    b, ctx->root, ctx->d_P, d_M + (size_t)k * set, ctx->d_freqs, ctx->d_props, ctx->d_weights, ctx->d_pattern_lnl, e.scale,
+			    0 /* one site denominator: dlikelihood / likelihood, :2464-2474 */, e.include_root_freqs, ctx->d_scratch);
+			k_generic_gradient_reduce<<<(unsigned)((N * C + 127) / 128), 128, 0, ctx->stream>>>((int)N, (int)C, ctx->root, (int)gtiles, ctx->d_scratch,
+			                                                                                 d_cat + (size_t)k * N * C);
+			ctx->launches += 2;
+		}
+		if (!rc && err == cudaSuccess) {
+			k_matrix_gradient_sum<<<nsets, 256, 0, ctx->stream>>>((int)N, (int)C, ctx->root, skip_node, d_cat, ctx->d_props, d_out);
+			ctx->launches++;
+			err = cudaMemcpyAsync(out_host, d_out, (size_t)nsets * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+			if (err == cudaSuccess && lnl)
+				err = cudaMemcpyAsync(lnl, ctx->d_result + (size_t)e.batch_index * (1 + N), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+		}
+	}
+	if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+	if (err == cudaSuccess) err = cudaGetLastError();
+	cudaFree(d_M), cudaFree(d_cat), cudaFree(d_out);
+	if (rc) return rc;
+	PHBC_CHECK(err);
+	return 0;
+}
+
 extern "C" int phbc_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	if (o->batch_index < 0 || o->batch_index >= ctx->bl_cap || o->batch_index >= ctx->result_cap) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "batch index %d out of range", o->batch_index);

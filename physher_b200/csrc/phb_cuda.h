@@ -115,6 +115,7 @@ typedef struct phbc_eval_opts {
 	int want_gradient;
 	int explicit_matrices;       /* matrices were uploaded, do not rebuild them from the eigen system */
 	int batch_index;             /* which uploaded branch-length vector (the first one of a batch)  */
+	int materialize_uppers;      /* tensor-core path: store every upper partial (tips included) and reduce with the generic K9/K10 */
 	int batch_count;             /* > 1: evaluate batch_index .. batch_index + batch_count - 1 (results in the matching slots) */
 } phbc_eval_opts;
 
@@ -133,6 +134,7 @@ int phbc_download_cat_grad(phbc_ctx *ctx, double *out);
 int phbc_download_pattern_lnl(phbc_ctx *ctx, double *out);
 int phbc_download_partials(phbc_ctx *ctx, int index, double *out);
 int phbc_download_matrices(phbc_ctx *ctx, double *P, double *dP);
+int phbc_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int nsets, const double *M_host, int skip_node, double *lnl, double *out_host);
 /* time-tree chain, batched (phb_timetree.cu) */
 int phbc_set_time_tree(phbc_ctx *ctx, const double *lowers, const int *parent, const int *preorder, const int *postorder);
 int phbc_time_forward(phbc_ctx *ctx, int nbatch, const double *ratios, const double *rates, int nrates); /* 1: negative branch length */

@@ -647,7 +647,7 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	double *result = ctx->d_result + (size_t)o->batch_index * (1 + N);
 	if ((rc = phbc_generic_root(ctx, o, result))) return rc;
 	if (o->want_gradient) {
-		const bool grad = !o->scale;  // fused reductions use the unscaled form
+		const bool grad = !o->scale && !o->materialize_uppers;  // fused reductions use the unscaled form and skip the tips' uppers
 		auto upper = grad ? k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, true> : k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, false>;
 		const int uwarps = Cf::UWM * Cf::UNSPLIT;
 		const size_t usmem = 128 + ((grad ? 5 : 3) * Sh::IMG + 2 * Sh::NP + 2 * uwarps + Cf::UWM * AStage<Sh, Cf::UMT, 3>::NSTAGE * AStage<Sh, Cf::UMT, 3>::STG) * sizeof(double);

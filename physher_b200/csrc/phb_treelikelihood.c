@@ -969,6 +969,33 @@ int phb_tlk_gradient_batch(phb_tlk *t, int nbatch, const double *bl, double *lnl
 	return PHB_OK;
 }
 
+/* node sweep of calculate_dlnl_dQ (treelikelihood.c:2337-2583) for `nsets` sets of per-node matrices, e.g. dP/d theta from m->dPdp */
+int phb_tlk_matrix_gradient(phb_tlk *t, int nsets, const double *M, double *out) {
+	if (nsets < 1 || !M || !out) return fail(PHB_EINVAL, "nsets >= 1, M and out are required");
+	int rc = check_ready(t);
+	if (rc) return rc;
+	if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+	t->bl_dirty = 0;
+	for (int attempt = 0; attempt < 2; attempt++) {
+		phbc_eval_opts o;
+		fill_opts(t, &o, 1, 0);
+		double lnl = 0.0;
+		if ((rc = phbc_matrix_gradient(t->ctx, &o, nsets, M, t->unrooted ? t->right[t->root] : -1, &lnl, out))) return dev_fail(rc);
+		t->lk = lnl;
+		if (isinf(lnl) && !t->scale) { /* treelikelihood.c:1496-1519 */
+			fprintf(stdout, "_calculate: rescaling %f\n", lnl);
+			t->scale = 1;
+			continue;
+		}
+		break;
+	}
+	if (isnan(t->lk) || isinf(t->lk))
+		for (int k = 0; k < nsets; k++) out[k] = NAN;
+	t->update = isnan(t->lk) ? 1 : 0;
+	t->update_upper = 1; /* the gradient buffer was not refreshed */
+	return PHB_OK;
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* store / restore (MCMC accept / reject)                                                      */
 /* ------------------------------------------------------------------------------------------- */

@@ -58,6 +58,7 @@ SYMBOLS = [
     ("phb_tlk_initialize_gradient", C.c_size_t, [C.c_void_p, C.c_int]),
     ("phb_tlk_gradient", C.c_int, [C.c_void_p, C.POINTER(_dp)]),
     ("phb_tlk_cat_branch_gradient", C.c_int, [C.c_void_p, _dp]),
+    ("phb_tlk_matrix_gradient", C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
     ("phb_tlk_get_partials", C.c_int, [C.c_void_p, C.c_int, _dp]),
     ("phb_tlk_get_matrices", C.c_int, [C.c_void_p, _dp, _dp]),
     ("phb_tlk_gradient_device", C.c_int, [C.c_void_p, C.c_void_p]),
@@ -281,6 +282,14 @@ class SingleTreeLikelihood:
     def cat_branch_gradient(self):
         out = np.zeros((self.N, self.C))
         self._check(self.lib.phb_tlk_cat_branch_gradient(self.h, out.ctypes.data_as(_dp)))
+        return out
+
+    def matrix_gradient(self, M):
+        """calculate_dlnl_dQ's node sweep for sets of per-node matrices M [nsets][N][C][S][S] (e.g. dP/d theta)."""
+        a = _f64(M)
+        assert a.ndim == 5 and a.shape[1:] == (self.N, self.C, self.S, self.S)
+        out = np.zeros(a.shape[0])
+        self._check(self.lib.phb_tlk_matrix_gradient(self.h, a.shape[0], a.ctypes.data_as(_dp), out.ctypes.data_as(_dp)))
         return out
 
     def get_partials(self, index):

@@ -1,0 +1,70 @@
+"""Substitution-model parameter gradients: the node sweep of calculate_dlnl_dQ (treelikelihood.c:2337-2583)
+with per-node matrices dP/d theta supplied by the caller (m->dPdp).
+
+Golden: tests/golden/dlnl_dq_gtr_g4.npz -- the reference's own dPdp matrices for the five free GTR rate parameters and its own
+calculate_dlnl_dQ values, with include_root_freqs false and true.  CPU: the oracle's restatement (from its own lower / upper
+partials) against them.  GPU: phb_tlk_matrix_gradient against both, plus the tensor-core state counts against the oracle.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests.util import RTOL, grad_err, load_golden, rel_err
+
+
+def _case():
+    pb, z = load_golden("dlnl_dq_gtr_g4")
+    return pb, z
+
+
+@pytest.mark.parametrize("irf,key", [(False, "ref_dlnl_dq"), (True, "ref_dlnl_dq_root_freqs")])
+def test_oracle_reproduces_reference_dlnl_dq(irf, key):
+    pb, z = _case()
+    pb.include_root_freqs = irf
+    got = O.matrix_gradient(pb, z["dPdp"])
+    assert grad_err(got, z[key]) < RTOL
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernels", ["generic", "auto"])
+@pytest.mark.parametrize("irf,key", [(False, "ref_dlnl_dq"), (True, "ref_dlnl_dq_root_freqs")])
+def test_gpu_reproduces_reference_dlnl_dq(irf, key, kernels):
+    import physher_b200 as phb
+    from physher_b200.treelikelihood import OPT_INCLUDE_ROOT_FREQS
+
+    pb, z = _case()
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=phb.KERNELS_GENERIC if kernels == "generic" else phb.KERNELS_AUTO)
+    tlk.set_option(OPT_INCLUDE_ROOT_FREQS, int(irf))
+    got = tlk.matrix_gradient(z["dPdp"])
+    assert grad_err(got, z[key]) < RTOL
+    assert rel_err(tlk.calculate(), float(z["ref_lnl"])) < RTOL  # the sweep leaves lnL cached
+    pb.include_root_freqs = irf
+    if not irf:
+        # rescaling on: the dlikelihood / likelihood form (:2464-2474) is the same derivative.  (With include_root_freqs and a
+        # non-uniform pi the reference's per-node denominators are not the site likelihood -- SURVEY.md 0.4 iii -- so that
+        # combination has no exact value to agree with.)
+        tlk.use_rescaling(True)
+        assert grad_err(tlk.matrix_gradient(z["dPdp"]), z[key]) < 1e-9
+        pb.scale = True
+    # the branch gradient still works afterwards
+    assert grad_err(tlk.gradient(), O.evaluate(pb)["grad"]) < RTOL
+    tlk.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(9, 130, 20, 2), (7, 70, 61, 1), (10, 90, 5, 3)])
+def test_gpu_matrix_gradient_other_state_counts(shape):
+    """20 / 61 states go through the tensor-core lower / upper kernels with every upper partial materialised; 5 states generic."""
+    import physher_b200 as phb
+    from tests.test_gpu_parity import _synthetic_problem
+
+    T, P, S, C = shape
+    pb = _synthetic_problem(T, P, S, C, seed=5000 + S, unknown=0.03)
+    rng = np.random.default_rng(5001)
+    M = rng.normal(size=(3, pb.nnodes, C, S, S))
+    want = O.matrix_gradient(pb, M)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    got = tlk.matrix_gradient(M)
+    assert grad_err(got, want) < RTOL
+    assert grad_err(tlk.gradient(), O.evaluate(pb)["grad"]) < RTOL
+    tlk.close()
