@@ -81,7 +81,8 @@ extern "C" phbc_ctx *phbc_create(int device, int ntips, int nstate, int ncat, in
 	if (tip_kind == PHBC_TIP_STATES)
 		ok = ok && dev_alloc(&ctx->d_tip_states, T * P) == 0;
 	else
-		ok = ok && dev_alloc(&ctx->d_tip_partials, T * P * S) == 0;
+		ok = ok && dev_alloc(&ctx->d_tip_partials, T * P * S + 64) == 0 &&
+		     cudaMemset(ctx->d_tip_partials, 0, (T * P * S + 64) * sizeof(double)) == cudaSuccess;  // zeroed tail, see phbc_generic_prepare
 	if (!ok) {
 		if (!phbc_errbuf[0]) snprintf(phbc_errbuf, sizeof(phbc_errbuf), "device allocation failed");
 		phbc_destroy(ctx);
@@ -570,8 +571,17 @@ int phbc_generic_prepare(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));
 	const size_t S = ctx->S, C = ctx->C, P = ctx->P, N = ctx->N, T = ctx->T;
 	const size_t psize = C * P * S;
-	if (!ctx->d_lower) PHBC_CHECK(cudaMalloc((void **)&ctx->d_lower, (N - T) * psize * sizeof(double)));
-	if (o->want_gradient && !ctx->d_upper) PHBC_CHECK(cudaMalloc((void **)&ctx->d_upper, N * psize * sizeof(double)));
+	// zero-initialised, with a zeroed tail: the tensor-core kernels stage whole k-chunks without predicates and may read a few
+	// doubles past a row (into the next row / block) -- always finite values that meet zero-padded matrix columns
+	const size_t tail = 64;
+	if (!ctx->d_lower) {
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_lower, ((N - T) * psize + tail) * sizeof(double)));
+		PHBC_CHECK(cudaMemsetAsync(ctx->d_lower, 0, ((N - T) * psize + tail) * sizeof(double), ctx->stream));
+	}
+	if (o->want_gradient && !ctx->d_upper) {
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_upper, (N * psize + tail) * sizeof(double)));
+		PHBC_CHECK(cudaMemsetAsync(ctx->d_upper, 0, (N * psize + tail) * sizeof(double), ctx->stream));
+	}
 	if (o->scale && !ctx->d_sf) {
 		PHBC_CHECK(cudaMalloc((void **)&ctx->d_sf, 2 * N * P * sizeof(double)));
 		PHBC_CHECK(cudaMemsetAsync(ctx->d_sf, 0, 2 * N * P * sizeof(double), ctx->stream));

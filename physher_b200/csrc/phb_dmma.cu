@@ -120,25 +120,36 @@ __device__ __forceinline__ void cp_async_wait() {
 	asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// one chunk of up to three operands for the group's MT * 8 patterns starting at p0; PX = 0 switches an operand off (zeros)
+// Per-thread plan of the cp.async granules of one operand chunk: thread gl of the m-group copies elements e = j * GT + gl of the
+// [MT * 8 rows][KC doubles] chunk.  Row / column / shared-memory offsets are computed ONCE per kernel; a fill is then one min, one
+// multiply-add and one cp.async per granule.  No predicates: rows past the pattern count read the last pattern again (their
+// results are never stored and carry weight 0), columns past S read the first doubles of the NEXT row / block -- finite values
+// that meet zero-padded matrix columns (the partials buffers are zero-initialised with a zeroed tail for exactly this reason).
 template <class Sh, int MT, int NOPS, int GT>
-__device__ __forceinline__ void fill_chunk(double *stage, const double *__restrict__ x0, int P0, const double *__restrict__ x1, int P1,
-                                           const double *__restrict__ x2, int P2, int p0, int ch, int gl) {
+struct AFill {
 	using A = AStage<Sh, MT, NOPS>;
-	constexpr int PER = MT * 8 * A::KC;
+	static constexpr int PER = MT * 8 * A::KC;
+	static constexpr int NE = (PER + GT - 1) / GT;
+	int row[NE], col[NE], soff[NE];
+	__device__ __forceinline__ void init(int gl) {
 #pragma unroll
-	for (int e0 = 0; e0 < NOPS * PER; e0 += GT) {
-		const int e = e0 + gl;
-		if ((NOPS * PER) % GT != 0 && e >= NOPS * PER) break;
-		const int op = e / PER, rem = e - op * PER, row = rem / A::KC, col = rem - row * A::KC;
-		const int k = ch * A::KC + col, p = p0 + row;
-		const double *X = op == 0 ? x0 : (op == 1 ? x1 : x2);
-		const int PX = op == 0 ? P0 : (op == 1 ? P1 : P2);
-		double *dst = stage + op * A::OPB + row * A::RS + col;
-		if (p < PX && k < Sh::S) cp_async8(dst, X + (size_t)p * Sh::S + k);
-		else if (PX > 0) *dst = 0.0;  // padding of a live operand; a switched-off operand's buffer is never read
+		for (int j = 0; j < NE; j++) {
+			const int e = j * GT + gl;
+			row[j] = e / A::KC;
+			col[j] = e - row[j] * A::KC;
+			soff[j] = row[j] * A::RS + col[j];
+			if (PER % GT != 0 && e >= PER) row[j] = -1;  // this thread has no granule j
+		}
 	}
-}
+	__device__ __forceinline__ void fill(double *opbuf, const double *__restrict__ X, int p0, int P, int ch) const {
+#pragma unroll
+		for (int j = 0; j < NE; j++) {
+			if (PER % GT != 0 && row[j] < 0) continue;
+			const int p = min(p0 + row[j], P - 1);
+			cp_async8(opbuf + soff[j], X + (size_t)p * Sh::S + (ch * A::KC + col[j]));
+		}
+	}
+};
 
 // fragments of one staged operand: a[m][tt] = chunk[8 m + lane / 4][4 tt + lane % 4]
 template <class Sh, int MT, int NOPS>
@@ -272,9 +283,19 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const p
 	constexpr int GT = 32 * NSPLIT;
 	double *abuf = sm + 2 * Sh::IMG + wm * AS::NSTAGE * AS::STG;  // this m-group's ring
 	const int gl = (warp % NSPLIT) * 32 + lane;
+	mbar_wait(bar, 0);  // matrices have landed (the first A chunks are already in flight)
+	dispatch2(a_tip_rt, b_tip_rt, [&](auto ATIP, auto BTIP) {
+	constexpr bool a_tip = decltype(ATIP)::value, b_tip = decltype(BTIP)::value;
+	AFill<Sh, MT, 2, GT> plan;
+	plan.init(gl);
 	int f_tile = blockIdx.x, f_ch = 0, f_stage = 0;
 	auto fill_next = [&]() {  // stage the next chunk of the (tile, chunk) sequence; always commits, so group counts stay uniform
-		if (f_tile < ntiles) fill_chunk<Sh, MT, 2, GT>(abuf + f_stage * AS::STG, xa, Pa, xb, Pb, nullptr, 0, f_tile * TP + wm * MT * 8, f_ch, gl);
+		if (f_tile < ntiles) {
+			double *stg = abuf + f_stage * AS::STG;
+			const int fp0 = f_tile * TP + wm * MT * 8;
+			if (!a_tip) plan.fill(stg, xa, fp0, b.P, f_ch);
+			if (!b_tip) plan.fill(stg + AS::OPB, xb, fp0, b.P, f_ch);
+		}
 		cp_async_commit();
 		f_stage = f_stage + 1 == AS::NSTAGE ? 0 : f_stage + 1;
 		if (++f_ch == Sh::NCH) f_ch = 0, f_tile += gridDim.x;
@@ -282,9 +303,6 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const p
 	fill_next();
 	fill_next();
 	int c_stage = 0;
-	mbar_wait(bar, 0);  // matrices have landed (the first A chunks are already in flight)
-	dispatch2(a_tip_rt, b_tip_rt, [&](auto ATIP, auto BTIP) {
-	constexpr bool a_tip = decltype(ATIP)::value, b_tip = decltype(BTIP)::value;
 	// B fragments run one (k-step, n-tile) ahead of the tensor pipe: the LDS of step u + 1 is issued before the DMMAs of step u
 	double bA = 0.0, bB = 0.0;
 	{
@@ -404,9 +422,20 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 	constexpr int GT = 32 * NSPLIT;
 	double *abuf = red + 2 * NWARPS + wm * AS::NSTAGE * AS::STG;  // this m-group's ring: operands U_n | L_b | L_a
 	const int gl = (warp % NSPLIT) * 32 + lane;
+	mbar_wait(bar, 0);  // matrices have landed (the first A chunks are already in flight)
+	dispatch3(is_root_rt, a_tip_rt, b_tip_rt, [&](auto ROOT, auto ATIP, auto BTIP) {
+	constexpr bool is_root = decltype(ROOT)::value, a_tip = decltype(ATIP)::value, b_tip = decltype(BTIP)::value;
+	AFill<Sh, MT, 3, GT> plan;
+	plan.init(gl);
 	int f_tile = blockIdx.x, f_ch = 0, f_stage = 0;
 	auto fill_next = [&]() {  // stage the next chunk of the (tile, chunk) sequence; always commits, so group counts stay uniform
-		if (f_tile < ntiles) fill_chunk<Sh, MT, 3, GT>(abuf + f_stage * AS::STG, xw, Pw, xb, Pb, xa, Pa, f_tile * TP + wm * MT * 8, f_ch, gl);
+		if (f_tile < ntiles) {
+			double *stg = abuf + f_stage * AS::STG;
+			const int fp0 = f_tile * TP + wm * MT * 8;
+			if (!is_root) plan.fill(stg, xw, fp0, b.P, f_ch);
+			if (!b_tip) plan.fill(stg + AS::OPB, xb, fp0, b.P, f_ch);
+			if (!a_tip) plan.fill(stg + 2 * AS::OPB, xa, fp0, b.P, f_ch);
+		}
 		cp_async_commit();
 		f_stage = f_stage + 1 == AS::NSTAGE ? 0 : f_stage + 1;
 		if (++f_ch == Sh::NCH) f_ch = 0, f_tile += gridDim.x;
@@ -414,9 +443,6 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 	fill_next();
 	fill_next();
 	int c_stage = 0;
-	mbar_wait(bar, 0);  // matrices have landed (the first A chunks are already in flight)
-	dispatch3(is_root_rt, a_tip_rt, b_tip_rt, [&](auto ROOT, auto ATIP, auto BTIP) {
-	constexpr bool is_root = decltype(ROOT)::value, a_tip = decltype(ATIP)::value, b_tip = decltype(BTIP)::value;
 	// B fragments run one (k-step, n-tile) ahead of the tensor pipe: the LDS of step u + 1 is issued before the DMMAs of step u
 	double bP = 0.0, bA = 0.0, bB = 0.0, bdA = 0.0, bdB = 0.0;
 	{
