@@ -304,8 +304,9 @@ def reference_main(args, cfg):
 
 
 def sample_per_core(cfg) -> int:
-    """Patterns per reference process: a few seconds of CPU work per evaluation at each state count."""
-    return {4: 2000, 20: 1200, 61: 400}.get(cfg["states"], 200)
+    """Patterns per reference process: ~1 s of CPU work per evaluation and process at each state count, i.e. 10-30 core-seconds
+    per core over the warm-up + timed evaluations (the reference allocates every node's partials: ~1.3 GB per process at C2)."""
+    return {4: 5000, 20: 2400, 61: 800}.get(cfg["states"], 200)
 
 
 def workload_name(cfg):
