@@ -10,7 +10,11 @@
 //     lower partials, root integration, then pre-order for upper partials and branch gradients;
 //   * intermediate partials live in thread-private shared-memory slots; the host orders the walks so
 //     that the number of live slots is the tree's Strahler number (<= log2(T) + 1);
-//   * lower partials of internal nodes are streamed once to a CTA-private HBM scratch row (32 B per
+//   * what travels between ops is the MESSAGE M_n = P_n L_n a node sends to its parent (L_n = M_a o M_b is formed and, if
+//     needed, rescaled in registers): the post-order op of n multiplies by n's OWN matrix once, and that product is reused
+//     three times -- by the parent's lower partial, by the sibling's upper partial and by n's own branch gradient
+//     (4 mat-vecs per internal node and evaluation instead of the 7 a node-at-a-time formulation spends);
+//   * the messages of internal nodes are streamed once to a CTA-private HBM scratch row (32 B per
 //     thread per node, coalesced 1 KB per warp) and read back once by the pre-order pass; upper
 //     partials never leave the SM.  HBM traffic is ~2(T-1)*C*32 B per pattern instead of the
 //     ~(5T-9)*C*32 B of node-at-a-time streaming;
@@ -46,9 +50,9 @@ struct Nuc4Params {
 	const double *props;
 	const phbc_post_op *post_ops;
 	const phbc_pre_op *pre_ops;
-	const double *post_mats;  // [n_post][2][C][16]
+	const double *post_mats;  // [n_post][3][C][16]: own (identity at the root) | child a | child b (tips only)
 	const double *pre_mats;   // [n_pre][3][C][16]
-	double *lower;            // [grid][n_post][C][PB][4]
+	double *lower;            // [grid][n_post][C][PB][4]: messages P_n L_n
 	double *gacc;             // [grid][phases][warps][N]
 	double *cta_lnl;          // [grid][phases][warps]
 	double *pattern_lnl;      // [P]
@@ -114,16 +118,18 @@ __device__ __forceinline__ void row_store(unsigned char *cell, const double (&x)
 // the walk kernel
 // ---------------------------------------------------------------------------------------------
 // shared memory map (dynamic):
-//   [0, 16)   two mbarriers
-//   stage[2]: each CHUNK * 48 B of descriptors, CHUNK * 3*C*128 B of matrices, 2*CHUNK * PB B of tip codes
+//   stage[2]: each 64 B (the two mbarriers live in stage 0's), CHUNK * 48 B of descriptors, CHUNK * 3*C*128 B of matrices,
+//             2*CHUNK * PB B of tip codes
 //   slots:    nslots * NUC4_SLOT_BYTES
-//   xch:      exchange area for cross-category sums (4 * C * PB doubles) + invLw[PB] + sfslot[nslots][NT]
+//   xch:      exchange area for cross-category sums (C * PB doubles; 4 * C * PB under rescaling) + invLw[PB] + sfslot[nslots][NT]
+// (C2's shape, Gamma-4 and 5 slots: 57,344 B.  Four CTAs per SM at a 128-register budget were measured SLOWER than three at 160:
+// 6.62 against 6.29 ms on the same box, round 1 h2.)
 struct Nuc4Stage {
 	uint32_t desc_off, mat_off, code_off, bytes;
 };
 __host__ __device__ constexpr Nuc4Stage nuc4_stage_layout(int C, int PB) {
-	return Nuc4Stage{0u, (uint32_t)(NUC4_CHUNK * 48), (uint32_t)(NUC4_CHUNK * 48 + NUC4_CHUNK * 3 * C * 128),
-	                 (uint32_t)((NUC4_CHUNK * 48 + NUC4_CHUNK * 3 * C * 128 + 2 * NUC4_CHUNK * PB + 127) & ~127)};
+	return Nuc4Stage{64u, (uint32_t)(64 + NUC4_CHUNK * 48), (uint32_t)(64 + NUC4_CHUNK * 48 + NUC4_CHUNK * 3 * C * 128),
+	                 (uint32_t)((64 + NUC4_CHUNK * 48 + NUC4_CHUNK * 3 * C * 128 + 2 * NUC4_CHUNK * PB + 127) & ~127)};
 }
 
 // 4 values per lane -> 4 warp totals in 6 shuffle rounds: lane 0 gets v0, lane 8 v2, lane 16 v1, lane 24 v3
@@ -174,11 +180,11 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 	const int c = tid / PBT, pl0 = tid - c * PBT;
 	const int cell0 = c * PB + pl0;  // cell index of u = 0; u adds u * PBT
 	constexpr Nuc4Stage lay = nuc4_stage_layout(C, PB);
-	uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
-	unsigned char *stage0 = smem_raw + 128;
+	uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);  // inside stage 0's leading 64 bytes
+	unsigned char *stage0 = smem_raw;
 	unsigned char *slot_cell = stage0 + 2 * lay.bytes + cell0 * 16;  // this thread's first cell in slot 0
 	double *xch = reinterpret_cast<double *>(stage0 + 2 * lay.bytes + (size_t)prm.nslots * NUC4_SLOT_BYTES);
-	double *invLw = xch + 4 * C * PB;
+	double *invLw = xch + (SCALE ? 4 : 1) * C * PB;
 	double *sfslot = invLw + PB;  // [nslots][NT] thread-private copies (SCALE only)
 	const uint32_t my_mat = lay.mat_off + c * 128;  // this thread's category inside a staged matrix group
 	const uint32_t my_code = lay.code_off + pl0;
@@ -234,11 +240,11 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 				const int first = ch * NUC4_CHUNK;
 				const int cnt = min(NUC4_CHUNK, prm.n_post - first);
 				unsigned char *dst = stage0 + (ld & 1) * lay.bytes;
-				const uint32_t dbytes = cnt * (uint32_t)sizeof(phbc_post_op), mbytes = cnt * 2 * C * 128;
+				const uint32_t dbytes = cnt * (uint32_t)sizeof(phbc_post_op), mbytes = cnt * 3 * C * 128;
 				const uint32_t cbytes = (tips & 31) * PB;
 				mbar_expect_tx(&bars[ld & 1], dbytes + mbytes + cbytes);
 				bulk_g2s(dst + lay.desc_off, prm.post_ops + first, dbytes, &bars[ld & 1]);
-				bulk_g2s(dst + lay.mat_off, prm.post_mats + (size_t)cur_b * prm.mats_stride + (size_t)first * 2 * C * 16, mbytes, &bars[ld & 1]);
+				bulk_g2s(dst + lay.mat_off, prm.post_mats + (size_t)cur_b * prm.mats_stride + (size_t)first * 3 * C * 16, mbytes, &bars[ld & 1]);
 				if (cbytes) bulk_g2s(dst + lay.code_off, tile_codes_post + (size_t)(tips >> 5) * PB, cbytes, &bars[ld & 1]);
 			};
 			if (tid == 0) issue(0, loads, prm.post_first_tips);
@@ -255,21 +261,22 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 				for (int j = 0; j < cnt; j++) {
 					const int kind = desc[j].a_kind + desc[j].b_kind;
 					const int a_idx = desc[j].a_idx, b_idx = desc[j].b_idx, dst_slot = desc[j].dst_slot;
-					const double *MA = reinterpret_cast<const double *>(mats + j * 2 * C * 128);
-					const double *MB = reinterpret_cast<const double *>(mats + (j * 2 + 1) * C * 128);
-					double ma[PPT][4], mb[PPT][4];
+					const double *MN = reinterpret_cast<const double *>(mats + (j * 3 + 0) * C * 128);
+					const double *MA = reinterpret_cast<const double *>(mats + (j * 3 + 1) * C * 128);
+					const double *MB = reinterpret_cast<const double *>(mats + (j * 3 + 2) * C * 128);
+					double ma[PPT][4], lw[PPT][4];
 					double sf_in[PPT];
 #pragma unroll
 					for (int u = 0; u < PPT; u++) sf_in[u] = 0.0;
-					// operand b of kinds 1 and 2 is the previous op's result, still in `out`
+					// messages of the children: a tip's is a column (or column sum) of its matrix, an internal child's was formed by
+					// its own op -- child b of kinds 1 and 2 is the previous op's result, still in `out`
 					if (kind == 0) {
 #pragma unroll
 						for (int u = 0; u < PPT; u++) {
 							tip_message(MA, cds[a_idx * PB + u * PBT], ma[u]);
-							tip_message(MB, cds[b_idx * PB + u * PBT], mb[u]);
+							tip_message(MB, cds[b_idx * PB + u * PBT], out[u]);
 						}
 					} else {
-						matvec_smem_n<PPT>(MB, out, mb);
 						if (SCALE) {
 #pragma unroll
 							for (int u = 0; u < PPT; u++) sf_in[u] = sf_acc[u];
@@ -278,24 +285,22 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 #pragma unroll
 							for (int u = 0; u < PPT; u++) tip_message(MA, cds[a_idx * PB + u * PBT], ma[u]);
 						} else {
-							double x[PPT][4];
 #pragma unroll
 							for (int u = 0; u < PPT; u++) {
-								cell_load(slot_cell + a_idx * NUC4_SLOT_BYTES + u * PBT * 16, x[u]);
+								cell_load(slot_cell + a_idx * NUC4_SLOT_BYTES + u * PBT * 16, ma[u]);
 								if (SCALE) sf_in[u] += sfslot[a_idx * NUC4_NT + cell0 + u * PBT];
 							}
-							matvec_smem_n<PPT>(MA, x, ma);
 						}
 					}
 #pragma unroll
 					for (int u = 0; u < PPT; u++)
 #pragma unroll
-						for (int i = 0; i < 4; i++) out[u][i] = ma[u][i] * mb[u][i];
+						for (int i = 0; i < 4; i++) lw[u][i] = ma[u][i] * out[u][i];  // lower partial L_n
 					if (SCALE) {
 						// SingleTreeLikelihood_scalePartials (treelikelihood.c:1790-1836): max over categories and states
 						double *mx = xch + ((first + j) & 1) * C * PB;
 #pragma unroll
-						for (int u = 0; u < PPT; u++) mx[cell0 + u * PBT] = fmax(fmax(out[u][0], out[u][1]), fmax(out[u][2], out[u][3]));
+						for (int u = 0; u < PPT; u++) mx[cell0 + u * PBT] = fmax(fmax(lw[u][0], lw[u][1]), fmax(lw[u][2], lw[u][3]));
 						__syncthreads();
 #pragma unroll
 						for (int u = 0; u < PPT; u++) {
@@ -305,13 +310,15 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 							double sf = 0.0;
 							if (m < prm.threshold) {
 #pragma unroll
-								for (int i = 0; i < 4; i++) out[u][i] /= m;
+								for (int i = 0; i < 4; i++) lw[u][i] /= m;
 								sf = log(m);
 							}
 							sf_acc[u] = sf + sf_in[u];
 							if (dst_slot >= 0) sfslot[dst_slot * NUC4_NT + cell0 + u * PBT] = sf_acc[u];
 						}
 					}
+					// the message to the parent: the node's OWN matrix (identity at the root, whose `out` feeds the root integration)
+					matvec_smem_n<PPT>(MN, lw, out);
 #pragma unroll
 					for (int u = 0; u < PPT; u++) {
 						if (dst_slot >= 0) cell_store(slot_cell + dst_slot * NUC4_SLOT_BYTES + u * PBT * 16, out[u]);  // parked for a later kind-2 op
@@ -376,7 +383,7 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 				bulk_g2s(dst + lay.mat_off, prm.pre_mats + (size_t)cur_b * prm.mats_stride + (size_t)first * 3 * C * 16, mbytes, &bars[ld & 1]);
 				if (cbytes) bulk_g2s(dst + lay.code_off, tile_codes_pre + (size_t)(tips >> 5) * PB, cbytes, &bars[ld & 1]);
 			};
-			// lower rows of the internal children of one op (kind: 0 tip-tip, 1 tip-internal, 2 internal-internal)
+			// message rows of the internal children of one op (kind: 0 tip-tip, 1 tip-internal, 2 internal-internal)
 			auto fetch = [&](const phbc_pre_op *d, double (&A)[PPT][4], double (&B)[PPT][4]) {
 				const int kind = d->kind;
 #pragma unroll
@@ -395,15 +402,19 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 				const double *MA = reinterpret_cast<const double *>(mats + (j * 3 + 1) * C * 128);
 				const double *MB = reinterpret_cast<const double *>(mats + (j * 3 + 2) * C * 128);
 				double W[PPT][4], ma[PPT][4], mb[PPT][4];
-				if (kind == 2) matvec_smem_n<PPT>(MA, xa, ma);
-				else {
+				// messages P_x L_x of the children: stored rows for internal children, matrix columns for tips
 #pragma unroll
-					for (int u = 0; u < PPT; u++) tip_message(MA, cds[d->a_code * PB + u * PBT], ma[u]);
+				for (int u = 0; u < PPT; u++) {
+					if (kind == 2) {
+#pragma unroll
+						for (int i = 0; i < 4; i++) ma[u][i] = xa[u][i];
+					} else tip_message(MA, cds[d->a_code * PB + u * PBT], ma[u]);
+					if (kind == 0) tip_message(MB, cds[d->b_code * PB + u * PBT], mb[u]);
+					else {
+#pragma unroll
+						for (int i = 0; i < 4; i++) mb[u][i] = xb[u][i];
+					}
 				}
-				if (kind == 0) {
-#pragma unroll
-					for (int u = 0; u < PPT; u++) tip_message(MB, cds[d->b_code * PB + u * PBT], mb[u]);
-				} else matvec_smem_n<PPT>(MB, xb, mb);
 				// xa / xb are dead: prefetch the next op's rows into them (across the chunk boundary too)
 				if (j + 1 < cnt) {
 					fetch(d + 1, xa, xb);
@@ -542,37 +553,41 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 
 // ---------------------------------------------------------------------------------------------
 // walk-ordered transition matrices: P(t) = |V exp(L t) V^-1| (substmodel.c:518-557), one thread per
-// (matrix, category).  post entries: [op][a|b]; pre entries: [op][parent|a|b].
+// (matrix, category).  post entries: [op][own|a|b] (own = identity at the root); pre entries: [op][parent|a|b].
+// Only tip children need their matrix at the parent's op; entries of internal children are left untouched.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_nuc4_matrices(int C, int root, int n_post, int n_pre, const phbc_post_op *__restrict__ post_ops,
+__global__ void k_nuc4_matrices(int T, int C, int root, int n_post, int n_pre, const phbc_post_op *__restrict__ post_ops,
                                 const phbc_pre_op *__restrict__ pre_ops, const double *__restrict__ evec,
                                 const double *__restrict__ eval, const double *__restrict__ ivec, const double *__restrict__ bl,
                                 const double *__restrict__ rates, double *__restrict__ post_mats, double *__restrict__ pre_mats, int N,
                                 long long mats_stride) {
 	const int e = blockIdx.x * blockDim.x + threadIdx.x;
-	const int total = (2 * n_post + 3 * n_pre) * C;
+	const int total = (3 * n_post + 3 * n_pre) * C;
 	if (e >= total) return;
 	bl += (size_t)blockIdx.y * N;  // one branch-length vector and one matrix set per sample
 	post_mats += (size_t)blockIdx.y * mats_stride;
 	pre_mats += (size_t)blockIdx.y * mats_stride;
 	const int c = e % C;
 	const int m = e / C;
-	int node;
+	int node, which;
 	double *dst;
-	if (m < 2 * n_post) {
-		const phbc_post_op op = post_ops[m >> 1];
-		node = (m & 1) ? op.b_node : op.a_node;
+	if (m < 3 * n_post) {
+		const phbc_post_op op = post_ops[m / 3];
+		which = m % 3;
+		node = which == 0 ? op.node : (which == 1 ? op.a_node : op.b_node);
 		dst = post_mats + (size_t)e * 16;
 	} else {
-		const int mm = m - 2 * n_post;
+		const int mm = m - 3 * n_post;
 		const phbc_pre_op op = pre_ops[mm / 3];
-		const int which = mm % 3;
+		which = mm % 3;
 		node = which == 0 ? op.node : (which == 1 ? op.a_node : op.b_node);
 		dst = pre_mats + ((size_t)mm * C + c) * 16;
 	}
+	if (which != 0 && node >= T) return;  // internal children bring their message along: no matrix needed here
 	if (node == root) {
+		const double diag = m < 3 * n_post ? 1.0 : 0.0;  // post-order: L_root passes through unchanged
 #pragma unroll
-		for (int k = 0; k < 16; k++) dst[k] = 0.0;
+		for (int k = 0; k < 16; k++) dst[k] = (k % 5 == 0) ? diag : 0.0;
 		return;
 	}
 	const double t = bl[node] * rates[c];
@@ -712,8 +727,8 @@ __global__ void __launch_bounds__(32 * NUC4_FY) k_nuc4_finalize(int N, int C, in
 // host side
 // ---------------------------------------------------------------------------------------------
 static size_t nuc4_smem_bytes(int C, int PB, int nslots, bool scale) {
-	return 128 + 2 * (size_t)nuc4_stage_layout(C, PB).bytes + (size_t)nslots * NUC4_SLOT_BYTES +
-	       (size_t)(4 * C * PB + PB + (scale ? nslots * NUC4_NT : 0)) * sizeof(double);
+	return 2 * (size_t)nuc4_stage_layout(C, PB).bytes + (size_t)nslots * NUC4_SLOT_BYTES +
+	       (size_t)((scale ? 4 : 1) * C * PB + PB + (scale ? nslots * NUC4_NT : 0)) * sizeof(double);
 }
 
 static int pattern_block(int C) {
@@ -801,7 +816,7 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	}
 	const int warps = nthr / 32;
 	// scratch: walk matrices per sample, per-CTA lower rows, per-(CTA, sample phase, warp) gradient rows and lnL
-	const long long mats_stride = (long long)(2 * ctx->n_post + 3 * ctx->n_pre) * C * 16;
+	const long long mats_stride = (long long)(3 * ctx->n_post + 3 * ctx->n_pre) * C * 16;
 	const size_t mats_bytes = (size_t)mats_stride * nbatch * sizeof(double);
 	if (mats_bytes > ctx->walk_mats_bytes) {
 		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -849,10 +864,10 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		ctx->cat_grad_cap = nbatch;
 	}
 	double *post_mats = ctx->d_walk_mats;
-	double *pre_mats = ctx->d_walk_mats + (size_t)2 * ctx->n_post * C * 16;
+	double *pre_mats = ctx->d_walk_mats + (size_t)3 * ctx->n_post * C * 16;
 	{
-		const int total = (2 * ctx->n_post + 3 * ctx->n_pre) * C;
-		k_nuc4_matrices<<<dim3((total + 127) / 128, nbatch), 128, 0, ctx->stream>>>(C, ctx->root, ctx->n_post, ctx->n_pre, ctx->d_post_ops, ctx->d_pre_ops,
+		const int total = (3 * ctx->n_post + 3 * ctx->n_pre) * C;
+		k_nuc4_matrices<<<dim3((total + 127) / 128, nbatch), 128, 0, ctx->stream>>>(T, C, ctx->root, ctx->n_post, ctx->n_pre, ctx->d_post_ops, ctx->d_pre_ops,
 		                                                                          ctx->d_evec, ctx->d_eval, ctx->d_ivec,
 		                                                                          ctx->d_bl + (size_t)o->batch_index * N, ctx->d_rates, post_mats, pre_mats,
 		                                                                          N, mats_stride);
