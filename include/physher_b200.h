@@ -52,6 +52,8 @@ extern "C" {
 #define PHB_OPT_KERNELS 4                /* PHB_KERNELS_* : force a kernel family (testing / profiling) */
 #define PHB_OPT_SCALING_THRESHOLD_EXP 5  /* tlk->scaling_threshold = 10^-value (default 40, treelikelihood.c:1121) */
 #define PHB_OPT_TIMING 6                 /* 1: bracket the dominant kernel of every evaluation with CUDA events */
+#define PHB_OPT_INCREMENTAL 7            /* 1: keep all partials resident between calls (like tlk->partials) and recompute only what
+                                            update_one_node / set_branch_length dirtied (_calculate_partials, treelikelihood.c:1645-1734) */
 
 #define PHB_KERNELS_AUTO 0    /* by state count, like the function-pointer dispatch at treelikelihood.c:1067-1165 */
 #define PHB_KERNELS_GENERIC 1 /* node-at-a-time kernels, any state count, materialised upper partials */
@@ -130,6 +132,23 @@ int phb_tlk_cat_branch_gradient(phb_tlk *tlk, double *out /* [N][C] */);
  * w_p / L_p * sum_c prop_c sum_i f_i U_n[c,p,i] (M_k[n,c] L_n[c,p])_i.  Honours PHB_OPT_INCLUDE_ROOT_FREQS and rescaling.
  * Runs on the node-at-a-time kernels (materialised upper partials). */
 int phb_tlk_matrix_gradient(phb_tlk *tlk, int nsets, const double *M, double *out /* [nsets] */);
+
+/*
+ * Single-branch fast path (tlk->use_upper: serial_brent_optimize_tree optimizer.c:111-152, NNI / SPR nniopt.c:301-334,
+ * spropt.c:1548-1615, Model.d2logP treelikelihood.c:470-527).
+ *
+ * phb_tlk_update_uppers == SingleTreeLikelihood_update_uppers (treelikelihood.c:1530-1538): lnL, then every upper partial
+ * (root frequencies not folded in), all kept on the device.  Switches PHB_OPT_INCREMENTAL on.
+ *
+ * phb_tlk_calculate_branch == _calculate_uppper (treelikelihood.c:2592-2686) + calculate_dldt_uppper (:2195-2262) +
+ * d2lnldt2_uppper (:2267-2335): lnL and its first and second derivative with respect to the length of the branch above `node`,
+ * at `nbl` candidate lengths in ONE launch, from the upper partial of `node`, its lower partial and fresh P, P', P" -- every other
+ * branch at its current length (pending set_branch_length changes are applied first, recomputing only the partials they reach).
+ * The object's own branch lengths are not changed; the caller keeps the length it chooses with phb_tlk_set_branch_length.
+ * Output pointers may be NULL.
+ */
+int phb_tlk_update_uppers(phb_tlk *tlk);
+int phb_tlk_calculate_branch(phb_tlk *tlk, int node, int nbl, const double *bl, double *lnl, double *dlnl, double *d2lnl);
 
 /* Copy of one partials buffer [C][P][S]: index < N lower partials of that node, >= N upper partials of node
  * index-N (tlk->partials[..][index], treelikelihood.h:62; used by asr.c:60).  Generic kernels only. */

@@ -224,7 +224,43 @@ def write_dlnl_dq_fixture():
     print("dlnl_dQ fixture:", d["dPdp"].shape, d["ref_dlnl_dq"])
 
 
+def write_branch_fixture():
+    """tests/golden/branch_gtr_g4.npz: a GTR+G4 problem and the reference's own single-branch lnL, d lnL/dt, d2 lnL/dt2
+    (_calculate_uppper, calculate_dldt_uppper, d2lnldt2_uppper) for a tip, two internal nodes and the root's left child at
+    0.5x, 1x and 2.5x their branch length; the same for an HKY problem with one rate category and tip partials."""
+    out = {}
+    for tag, model, cats, tipstates, seed in (("g4", O.nucleotide_model_spec("gtr", [0.1, 0.2, 0.3, 0.4], [0.05, 0.3, 0.1, 0.15, 0.3, 0.1]), 4, True, 300),
+                                              ("c1", O.nucleotide_model_spec("hky", [0.3, 0.2, 0.2, 0.3], kappa=3.0), 1, False, 310)):
+        T, sites = 10, 300
+        topo = syn.random_topology(T, seed)
+        bl = syn.random_branch_lengths(topo, seed + 1)
+        pat = syn.random_patterns(T, sites, 4, 0.3, seed + 2, unknown_frac=0.03)
+        names = [f"t{i}" for i in range(T)]
+        seqs = dict(zip(names, syn.sequences_from_patterns(pat, syn.NUCLEOTIDES)))
+        ref = O.Reference(O.treelikelihood_spec(syn.to_newick(topo, bl, names), seqs, model, categories=cats, alpha=0.5, tipstates=tipstates))
+        pb = ref.problem()
+        root = int(pb.root)
+        nodes = [0, 3, T, T + 3, int(pb.left[root])]
+        nodes = [n for n in dict.fromkeys(nodes) if n != root and n != int(pb.right[root])]
+        factors = np.array([0.5, 1.0, 2.5])
+        vals = np.array([[ref.branch_derivatives(n, pb.bl[n] * f) for f in factors] for n in nodes])
+        d = dict(left=pb.left, right=pb.right, parent=pb.parent, root=np.int32(root), nstate=np.int32(4), weights=pb.weights, freqs=pb.freqs,
+                 rates=pb.rates, props=pb.props, bl=pb.bl, evec=pb.evec, eval=pb.eval, ivec=pb.ivec, use_tip_states=np.int32(tipstates),
+                 nodes=np.array(nodes, dtype=np.int32), factors=factors, ref_branch=vals, ref_lnl=np.float64(ref.logP()))
+        if tipstates:
+            d["tip_states"] = pb.tip_states
+        else:
+            d["tip_partials"] = pb.tip_partials
+        out.update({f"{tag}_{k}": v for k, v in d.items()})
+        print("branch fixture", tag, "nodes", nodes, "lnL", d["ref_lnl"], "first", vals[0, 1])
+        ref.close()
+    np.savez_compressed(os.path.join(GOLDEN, "branch_derivatives.npz"), **out)
+
+
 def main():
+    if "--only-branch" in sys.argv:
+        write_branch_fixture()
+        return
     if "--only-dq" in sys.argv:
         write_dlnl_dq_fixture()
         return
@@ -239,6 +275,7 @@ def main():
     write_c1_time_tree_fixture()
     write_sitepattern_fixture()
     write_dlnl_dq_fixture()
+    write_branch_fixture()
     cwd = os.getcwd()
     os.chdir(REF_DATA)  # fixtures reference fluA.fa / tiny.fa by relative path
 

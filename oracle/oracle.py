@@ -248,6 +248,46 @@ def matrix_gradient(pb: Problem, M) -> np.ndarray:
     return out
 
 
+def branch_derivatives(pb: Problem, node: int, bls) -> np.ndarray:
+    """lnL, d lnL/dt and d2 lnL/dt2 [len(bls)][3] of the branch above `node` at candidate lengths, every other branch as in pb.
+
+    Restates _calculate_uppper (treelikelihood.c:2662-2677: calculate_branch_partials + integrate_partials +
+    node_log_likelihoods on the upper partial of `node`, its lower partial and a fresh P(t)), calculate_dldt_uppper (:2195-2262,
+    matrix r dP/dt) and d2lnldt2_uppper (:2267-2335, matrix r^2 d2P/dt2, :2331 for the second derivative of the log).  Upper and
+    lower partials come from the C restatement (oracle_evaluate, update_upper_partials with include_root_freqs = false as
+    SingleTreeLikelihood_update_uppers does, :1535).  Unscaled problems only."""
+    from dataclasses import replace
+    assert not pb.scale and pb.evec is not None
+    res = evaluate(replace(pb, include_root_freqs=False), gradient=True, partials=True)
+    S, Cc, P, T = pb.nstate, pb.ncat, pb.npatterns, pb.ntips
+    U = res["upper"][node]  # [C][P][S]
+    if node >= T:
+        L = res["lower"][node]
+    elif pb.use_tip_states:  # a known state selects a column, an unknown one the row sum (treelikelihoodX.c:878-1001)
+        st = pb.tip_states[node].astype(int)
+        one = np.where(st[:, None] < S, np.eye(S + 1)[np.minimum(st, S)][:, :S], 1.0)
+        L = np.broadcast_to(one, (Cc, P, S))
+    else:
+        L = np.broadcast_to(pb.tip_partials[node], (Cc, P, S))
+    lib = _oracle()
+    ev, la, iv = (np.ascontiguousarray(a, dtype=np.float64) for a in (pb.evec, pb.eval, pb.ivec))
+    out = np.zeros((len(bls), 3))
+    for k, t in enumerate(bls):
+        lk = np.zeros(P), np.zeros(P), np.zeros(P)
+        for c in range(Cc):
+            r = float(pb.rates[c])
+            M0, M1 = np.zeros((S, S)), np.zeros((S, S))
+            lib.oracle_p_t(S, _d(ev), _d(la), _d(iv), float(t) * r, _d(M0))
+            lib.oracle_dp_dt(S, _d(ev), _d(la), _d(iv), float(t) * r, _d(M1))
+            M2 = (ev * (la * la * np.exp(la * float(t) * r))[None, :]) @ iv  # d2p_d2t, substmodel.c:801-828
+            prop = 1.0 if Cc == 1 else float(pb.props[c])
+            for q, M in enumerate((M0, M1 * r, M2 * r * r)):
+                lk[q][:] += prop * np.einsum("pi,ij,pj->p", U[c] * pb.freqs[None, :], M, L[c])
+        w = pb.weights
+        out[k] = [np.sum(w * np.log(lk[0])), np.sum(w * lk[1] / lk[0]), np.sum(w * (lk[2] * lk[0] - lk[1] ** 2) / lk[0] ** 2)]
+    return out
+
+
 def time_evaluate(pb: Problem, tip_heights, ratios, rates, include_jacobian=False) -> dict:
     """Time-tree chain around `evaluate` (naive reference forms): ratios [T-1] (root entry = root height), rates [1] or [N]
     -> dict(lnl, log_jacobian, heights, bl, grad_ratios, grad_rates)."""
@@ -337,6 +377,8 @@ def _reflib():
         L.refh_dPdp.argtypes = [C.c_void_p, C.c_int, _dp]
         L.refh_dlnl_dQ.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.refh_dlnl_dQ.restype = C.c_double
+        L.refh_branch_derivatives.argtypes = [C.c_void_p, C.c_int, C.c_double, _dp]
+        L.refh_branch_derivatives.restype = C.c_int
         L.refh_time_tree.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.refh_time_tree.restype = C.c_int
         L.refh_set_ratios.argtypes = [C.c_void_p, _dp]
@@ -434,6 +476,14 @@ class Reference:
 
     def dlnl_dQ(self, index, include_root_freqs=0):
         return float(self.L.refh_dlnl_dQ(self.h, int(index), int(include_root_freqs)))
+
+    def branch_derivatives(self, node, bl):
+        """(lnL, d lnL/dt, d2 lnL/dt2) of the branch above `node` at length `bl` from the reference's own _calculate_uppper,
+        calculate_dldt_uppper and d2lnldt2_uppper (treelikelihood.c:2592-2686, 2195-2335)."""
+        out = np.zeros(3)
+        if _reflib().refh_branch_derivatives(self.h, int(node), float(bl), _d(out)) != 0:
+            raise ValueError(f"node {node}: the reference's upper-likelihood functions exclude the root and its right child")
+        return out
 
     def time_tree(self):
         """(tip_heights[T], ratios[T-1] with the root height in the root's entry, rates[1 or N]) as the reference holds them."""

@@ -468,3 +468,36 @@ double refh_dlnl_dQ(void *vh, int index, int include_root_freqs) {
 	refh_gradient(vh, TREELIKELIHOOD_FLAG_TREE_MODEL, include_root_freqs, tmp, 8);
 	return calculate_dlnl_dQ(h->tlk, index, h->tlk->pattern_lk + h->tlk->sp->count);
 }
+
+/* ---- single-branch "upper likelihood" functions (treelikelihood.c:2195-2335, 2592-2686) ---- */
+
+/* The reference's own lnL, d lnL/dt and d2 lnL/dt2 for the branch above node `id` at length `bl`, exactly as its Brent / Newton
+ * drivers obtain them: tlk->calculate_upper (= _calculate_uppper; node_upper == NULL => _calculate_simple + update_upper_partials),
+ * then calculate_dldt_uppper and d2lnldt2_uppper on exp(pattern_lk) (the protocol of _singleTreeLikelihood_d2logP, :470-527).
+ * The branch length is put back afterwards.  Not for the root or the root's right child (:2202-2205).  Returns 0 on success. */
+int refh_branch_derivatives(void *vh, int id, double bl, double *out) {
+	RefH *h = (RefH *)vh;
+	SingleTreeLikelihood *tlk = h->tlk;
+	Node *node = Tree_node(tlk->tree, id);
+	if (Node_isroot(node) || Tree_root(tlk->tree)->right == node) return 1;
+	const int P = tlk->sp->count;
+	const double old = Node_distance(node);
+	Node_set_distance(node, bl);
+	SingleTreeLikelihood_update_all_nodes(tlk); /* node_upper = NULL */
+	tlk->m->need_update = true;
+	out[0] = tlk->calculate_upper(tlk, node);
+	double *lk = (double *)malloc(sizeof(double) * P), *dlk = (double *)malloc(sizeof(double) * P);
+	for (int k = 0; k < P; k++) lk[k] = exp(tlk->pattern_lk[k]);
+	calculate_dldt_uppper(tlk, node, dlk);
+	double d1 = 0;
+	for (int k = 0; k < P; k++) d1 += dlk[k] / lk[k] * tlk->sp->weights[k];
+	out[1] = d1;
+	out[2] = d2lnldt2_uppper(tlk, node, lk, dlk);
+	free(lk);
+	free(dlk);
+	Node_set_distance(node, old);
+	SingleTreeLikelihood_update_all_nodes(tlk);
+	tlk->m->need_update = true;
+	tlk->use_upper = false;
+	return 0;
+}

@@ -9,6 +9,7 @@ from .treelikelihood import (  # noqa: F401
     KERNELS_AUTO,
     KERNELS_FUSED,
     KERNELS_GENERIC,
+    OPT_INCREMENTAL,
     PhysherB200Error,
     SingleTreeLikelihood,
     compress_patterns,
@@ -18,5 +19,5 @@ from .treelikelihood import (  # noqa: F401
 
 __all__ = [
     "SingleTreeLikelihood", "PhysherB200Error", "load_library", "device_count", "compress_patterns",
-    "FLAG_TREE_MODEL", "KERNELS_AUTO", "KERNELS_GENERIC", "KERNELS_FUSED",
+    "FLAG_TREE_MODEL", "KERNELS_AUTO", "KERNELS_GENERIC", "KERNELS_FUSED", "OPT_INCREMENTAL",
 ]

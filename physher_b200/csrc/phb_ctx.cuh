@@ -33,6 +33,10 @@ struct phbc_ctx {
 	double *d_dmma_img;      // packed matrix images of the tensor-core path [P | dP][N][C][IMG]
 	size_t dmma_img_bytes;
 	phbc_op *d_lower_ops, *d_upper_ops;
+	phbc_op *d_sub_ops;      // op list of a partial re-evaluation (phbc_run_ops)
+	int sub_ops_cap;
+	double *d_branch;        // single-branch scratch: candidate lengths, matrices, per-CTA sums, results (phb_branch.cu)
+	size_t branch_bytes;
 	phbc_parent_op *d_parent_ops;
 	int n_lower_ops, n_upper_ops, n_parent_ops;
 	int *h_lower_level_off, *h_upper_level_off, *h_parent_level_off;
@@ -112,6 +116,7 @@ struct Bufs {
 };
 Bufs phbc_make_bufs(phbc_ctx *ctx);
 int phbc_generic_prepare(phbc_ctx *ctx, const phbc_eval_opts *o);                       // buffers + transition matrices
+int phbc_generic_buffers(phbc_ctx *ctx, const phbc_eval_opts *o);                       // buffers only (lazy)
 int phbc_generic_scale_ops(phbc_ctx *ctx, const phbc_op *d_ops, int count, double threshold);  // K5 on one level
 int phbc_generic_root(phbc_ctx *ctx, const phbc_eval_opts *o, double *result);           // K6, K7 -> result[0]
 int phbc_generic_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, double *result);       // K9, K10, A11 from materialised uppers
@@ -119,6 +124,8 @@ int phbc_gradient_from_partials(phbc_ctx *ctx, int tiles, double *result);      
 // FP64 tensor-core path, 20 / 61 states (phb_dmma.cu)
 int phbc_dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
 bool phbc_dmma_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);
+int phbc_dmma_pack(phbc_ctx *ctx);                                   // packed matrix images from d_P / d_dP
+int phbc_dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt);  // out = (P_a x_a) o (P_b x_b) for a device op list (one level)
 // fused 4-state walk path (phb_nuc4.cu)
 int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
 bool phbc_nuc4_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);
@@ -128,6 +135,34 @@ __device__ __forceinline__ double phb_warp_sum(double v) {
 #pragma unroll
 	for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
 	return v;
+}
+
+// generic partials addressing (node-at-a-time kernels)
+__device__ __forceinline__ const double *partial_ptr(const Bufs &b, int idx, int c) {
+	const size_t PS = (size_t)b.P * b.S;
+	if (idx < b.T) return b.tip_partials + (size_t)idx * PS;
+	if (idx < b.N) return b.lower + ((size_t)(idx - b.T) * b.C + c) * PS;
+	return b.upper + ((size_t)(idx - b.N) * b.C + c) * PS;
+}
+
+__device__ __forceinline__ bool is_state_tip(const Bufs &b, int idx) { return idx < b.T && b.tip_kind == PHBC_TIP_STATES; }
+
+// message_i = sum_j M[i][j] x[j]; state tips gather a column, unknown states give 1 for probability
+// matrices and the real row sum for derivative matrices (treelikelihoodX.c:166-289, 878-1001).
+__device__ __forceinline__ double message(const Bufs &b, int idx, int c, const double *M, int p, int i, bool prob) {
+	const int S = b.S;
+	if (is_state_tip(b, idx)) {
+		const int s = b.tip_states[(size_t)idx * b.P + p];
+		if (s < S) return M[i * S + s];
+		if (prob) return 1.0;
+		double acc = 0.0;
+		for (int j = 0; j < S; j++) acc += M[i * S + j];
+		return acc;
+	}
+	const double *x = partial_ptr(b, idx, c) + (size_t)p * S;
+	double acc = 0.0;
+	for (int j = 0; j < S; j++) acc += M[i * S + j] * x[j];
+	return acc;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -95,7 +95,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-	void *bufs[] = {ctx->d_tip_states, ctx->d_tip_partials, ctx->d_weights, ctx->d_evec, ctx->d_eval, ctx->d_ivec, ctx->d_qmat,
+	void *bufs[] = {ctx->d_sub_ops, ctx->d_branch, ctx->d_tip_states, ctx->d_tip_partials, ctx->d_weights, ctx->d_evec, ctx->d_eval, ctx->d_ivec, ctx->d_qmat,
 	                ctx->d_freqs, ctx->d_rates, ctx->d_props, ctx->d_bl, ctx->d_P, ctx->d_dP, ctx->d_lower, ctx->d_upper,
 	                ctx->d_sf, ctx->d_lower_ops, ctx->d_upper_ops, ctx->d_parent_ops, ctx->d_post_ops, ctx->d_pre_ops, ctx->d_walk_mats,
 	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch,
@@ -321,33 +321,6 @@ __global__ void k_transition_matrices(int S, int C, int root, const double *__re
 // generic kernels
 // ---------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ const double *partial_ptr(const Bufs &b, int idx, int c) {
-	const size_t PS = (size_t)b.P * b.S;
-	if (idx < b.T) return b.tip_partials + (size_t)idx * PS;
-	if (idx < b.N) return b.lower + ((size_t)(idx - b.T) * b.C + c) * PS;
-	return b.upper + ((size_t)(idx - b.N) * b.C + c) * PS;
-}
-
-__device__ __forceinline__ bool is_state_tip(const Bufs &b, int idx) { return idx < b.T && b.tip_kind == PHBC_TIP_STATES; }
-
-// message_i = sum_j M[i][j] x[j]; state tips gather a column, unknown states give 1 for probability
-// matrices and the real row sum for derivative matrices (treelikelihoodX.c:166-289, 878-1001).
-__device__ __forceinline__ double message(const Bufs &b, int idx, int c, const double *M, int p, int i, bool prob) {
-	const int S = b.S;
-	if (is_state_tip(b, idx)) {
-		const int s = b.tip_states[(size_t)idx * b.P + p];
-		if (s < S) return M[i * S + s];
-		if (prob) return 1.0;
-		double acc = 0.0;
-		for (int j = 0; j < S; j++) acc += M[i * S + j];
-		return acc;
-	}
-	const double *x = partial_ptr(b, idx, c) + (size_t)p * S;
-	double acc = 0.0;
-	for (int j = 0; j < S; j++) acc += M[i * S + j] * x[j];
-	return acc;
-}
-
 #define GEN_PBLK 32
 
 // out = (M_a x_a) o (M_b x_b) [o pi]; grid (ceil(P/32), C, ops in level)   -- K1-K4, K8
@@ -567,7 +540,7 @@ static int phbc_launch_transition_matrices(phbc_ctx *ctx, int batch_index) {
 }
 
 // buffers of the node-at-a-time paths (lazy) and the per-node transition matrices
-int phbc_generic_prepare(phbc_ctx *ctx, const phbc_eval_opts *o) {
+int phbc_generic_buffers(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));
 	const size_t S = ctx->S, C = ctx->C, P = ctx->P, N = ctx->N, T = ctx->T;
 	const size_t psize = C * P * S;
@@ -586,6 +559,12 @@ int phbc_generic_prepare(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		PHBC_CHECK(cudaMalloc((void **)&ctx->d_sf, 2 * N * P * sizeof(double)));
 		PHBC_CHECK(cudaMemsetAsync(ctx->d_sf, 0, 2 * N * P * sizeof(double), ctx->stream));
 	}
+	return 0;
+}
+
+int phbc_generic_prepare(phbc_ctx *ctx, const phbc_eval_opts *o) {
+	int brc = phbc_generic_buffers(ctx, o);
+	if (brc) return brc;
 	if (!o->explicit_matrices) {
 		if (!ctx->have_eigen) {
 			snprintf(phbc_errbuf, sizeof(phbc_errbuf), "no eigen system and no explicit matrices set");
@@ -772,6 +751,116 @@ extern "C" int phbc_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int 
 	if (rc) return rc;
 	PHBC_CHECK(err);
 	return 0;
+}
+
+
+/*
+ * Partial re-evaluation on the resident node-at-a-time buffers: the dirty-flag traversal of _calculate_partials
+ * (treelikelihood.c:1645-1734) and update_upper_partials2 (:2164-2190) as explicit op lists.  `ops` (host) is grouped by level
+ * (level_off[nlevels + 1]); ops of one level are independent, levels run in order.  Lower ops (out < N) are followed by the root
+ * integration when do_root; upper ops (out >= N) leave their results in the upper buffers.  Transition matrices of ALL nodes are
+ * rebuilt from the uploaded branch lengths first when rebuild_matrices (N x C tiny CTAs: cheaper than tracking a subset).
+ */
+extern "C" int phbc_run_ops(phbc_ctx *ctx, const phbc_eval_opts *o, int nops, const phbc_op *ops, int nlevels, const int *level_off,
+                            int rebuild_matrices, int do_root, double *lnl_host) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	const size_t S = ctx->S, C = ctx->C, P = ctx->P, N = ctx->N;
+	int rc;
+	phbc_eval_opts e = *o;
+	e.batch_index = 0;
+	e.batch_count = 1;
+	for (int k = 0; k < nops; k++)
+		if (ops[k].out >= (int)N) e.want_gradient = 1;  // upper buffers are needed
+	if ((rc = phbc_generic_buffers(ctx, &e))) return rc;
+	const bool dmma = e.kernels != 1 && phbc_dmma_supported(ctx, &e);
+	if (rebuild_matrices) {
+		if (!e.explicit_matrices) {
+			if (!ctx->have_eigen) {
+				snprintf(phbc_errbuf, sizeof(phbc_errbuf), "no eigen system and no explicit matrices set");
+				return -4;
+			}
+			if ((rc = phbc_launch_transition_matrices(ctx, 0))) return rc;
+		}
+		if (dmma && (rc = phbc_dmma_pack(ctx))) return rc;
+	}
+	if (nops > 0) {
+		// within a level: ops the tensor-core kernel takes (two operands, no frequency factor) first, the rest after them
+		phbc_op *sorted = (phbc_op *)malloc(sizeof(phbc_op) * nops);
+		int *split = (int *)malloc(sizeof(int) * (nlevels > 0 ? nlevels : 1));
+		if (!sorted || !split) {
+			free(sorted), free(split);
+			return -3;
+		}
+		for (int l = 0; l < nlevels; l++) {
+			int w = level_off[l];
+			for (int pass = 0; pass < 2; pass++)
+				for (int k = level_off[l]; k < level_off[l + 1]; k++) {
+					const bool fast = dmma && ops[k].b >= 0 && !((ops[k].flags & 1) && e.include_root_freqs);
+					if (fast == (pass == 0)) sorted[w++] = ops[k];
+				}
+			split[l] = level_off[l];
+			for (int k = level_off[l]; k < level_off[l + 1]; k++)
+				if (dmma && sorted[k].b >= 0 && !((sorted[k].flags & 1) && e.include_root_freqs)) split[l] = k + 1;
+		}
+		if (nops > ctx->sub_ops_cap) {
+			PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+			if (ctx->d_sub_ops) cudaFree(ctx->d_sub_ops);
+			ctx->d_sub_ops = NULL;
+			ctx->sub_ops_cap = 0;
+			const int cap = nops > 2 * (int)N ? nops : 2 * (int)N;
+			cudaError_t err = cudaMalloc((void **)&ctx->d_sub_ops, sizeof(phbc_op) * cap);
+			if (err != cudaSuccess) {
+				free(sorted), free(split);
+				PHBC_CHECK(err);
+			}
+			ctx->sub_ops_cap = cap;
+		}
+		cudaError_t err = cudaMemcpyAsync(ctx->d_sub_ops, sorted, sizeof(phbc_op) * nops, cudaMemcpyHostToDevice, ctx->stream);
+		if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);  // `sorted` is pageable and freed below
+		free(sorted);
+		if (err != cudaSuccess) {
+			free(split);
+			PHBC_CHECK(err);
+		}
+		Bufs b = phbc_make_bufs(ctx);
+		const size_t smem = 2 * S * S * sizeof(double);
+		if (smem > 48 * 1024) PHBC_CHECK(cudaFuncSetAttribute(k_generic_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		const int ptiles = (int)((P + GEN_PBLK - 1) / GEN_PBLK);
+		rc = 0;
+		for (int l = 0; l < nlevels && !rc; l++) {
+			const int beg = level_off[l], end = level_off[l + 1], mid = split[l];
+			if (end <= beg) continue;
+			if (mid > beg) rc = phbc_dmma_lower_ops(ctx, ctx->d_sub_ops + beg, mid - beg);
+			for (int z0 = mid; z0 < end && !rc; z0 += 65535) {
+				const int zc = end - z0 < 65535 ? end - z0 : 65535;
+				k_generic_combine<<<dim3(ptiles, (unsigned)C, zc), 128, smem, ctx->stream>>>(b, ctx->d_sub_ops + z0, ctx->d_P,
+				                                                                           e.include_root_freqs ? ctx->d_freqs : NULL);
+				ctx->launches++;
+			}
+			if (!rc && e.scale) rc = phbc_generic_scale_ops(ctx, ctx->d_sub_ops + beg, end - beg, e.scaling_threshold);
+		}
+		free(split);
+		if (rc) return rc;
+	}
+	if (do_root) {
+		if ((rc = phbc_generic_root(ctx, &e, ctx->d_result))) return rc;
+		if (lnl_host) {
+			PHBC_CHECK(cudaMemcpyAsync(lnl_host, ctx->d_result, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+			PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		}
+	}
+	PHBC_CHECK(cudaGetLastError());
+	return 0;
+}
+
+// K9 / K10 / A11 over every branch from the resident upper and lower partials: result[1..N], cat_grad (lnL slot untouched)
+extern "C" int phbc_resident_gradient(phbc_ctx *ctx, const phbc_eval_opts *o) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	if (!ctx->d_upper || !ctx->d_lower) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "upper / lower partials are not resident");
+		return -4;
+	}
+	return phbc_generic_gradient(ctx, o, ctx->d_result);
 }
 
 extern "C" int phbc_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {

@@ -134,6 +134,14 @@ int phbc_download_cat_grad(phbc_ctx *ctx, double *out);
 int phbc_download_pattern_lnl(phbc_ctx *ctx, double *out);
 int phbc_download_partials(phbc_ctx *ctx, int index, double *out);
 int phbc_download_matrices(phbc_ctx *ctx, double *P, double *dP);
+/* Partial re-evaluation on the resident node-at-a-time buffers (dirty-flag traversal, treelikelihood.c:1645-1734, 2164-2190):
+ * host op list grouped by level; lower ops are followed by the root integration when do_root (lnl_host may be NULL). */
+int phbc_run_ops(phbc_ctx *ctx, const phbc_eval_opts *o, int nops, const phbc_op *ops, int nlevels, const int *level_off, int rebuild_matrices,
+                 int do_root, double *lnl_host);
+/* K9 / K10 / A11 over every branch from resident upper and lower partials (results in slot 0; lnL slot untouched) */
+int phbc_resident_gradient(phbc_ctx *ctx, const phbc_eval_opts *o);
+/* single-branch fast path (phb_branch.cu): out [nbl][3] = lnL, d lnL/dt, d2 lnL/dt2 at each candidate length of the branch above node */
+int phbc_branch_lnl(phbc_ctx *ctx, const phbc_eval_opts *o, int node, int nbl, const double *bl, double *out);
 int phbc_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int nsets, const double *M_host, int skip_node, double *lnl, double *out_host);
 /* time-tree chain, batched (phb_timetree.cu) */
 int phbc_set_time_tree(phbc_ctx *ctx, const double *lowers, const int *parent, const int *preorder, const int *postorder);

@@ -631,15 +631,12 @@ static int pick_chunks(int slots, int units, int ntiles) {
 	return best;
 }
 
+
+// packed matrix images [P | dP][node][category][IMG] from the per-node matrices
 template <int S>
-static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
+static int dmma_pack(phbc_ctx *ctx) {
 	using Sh = DmmaShape<S>;
-	using Cf = DmmaConfig<S>;
-	const int C = ctx->C, P = ctx->P, N = ctx->N;
-	int rc;
-	if ((rc = phbc_generic_prepare(ctx, o))) return rc;
-	Bufs b = phbc_make_bufs(ctx);
-	// packed matrix images [P | dP][node][category][IMG]
+	const int C = ctx->C, N = ctx->N;
 	const size_t img_bytes = (size_t)2 * N * C * Sh::IMG * sizeof(double);
 	if (img_bytes > ctx->dmma_img_bytes) {
 		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -651,6 +648,17 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	}
 	k_dmma_pack<Sh><<<dim3(N, C, 2), 128, 0, ctx->stream>>>(ctx->T, N, C, ctx->tip_kind == PHBC_TIP_STATES, ctx->d_P, ctx->d_dP, ctx->d_dmma_img);
 	ctx->launches++;
+	PHBC_CHECK(cudaGetLastError());
+	return 0;
+}
+
+// one level of K1-K4 ops (device list): wave-filling launch geometry, every CTA stages its two matrices once
+template <int S>
+static int dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
+	using Sh = DmmaShape<S>;
+	using Cf = DmmaConfig<S>;
+	const int C = ctx->C, P = ctx->P;
+	Bufs b = phbc_make_bufs(ctx);
 	auto lower = k_dmma_lower<S, Cf::MT, Cf::NSPLIT, Cf::WM>;
 	const size_t lsmem = 128 + (2 * Sh::IMG + Cf::WM * AStage<Sh, Cf::MT, 2>::NSTAGE * AStage<Sh, Cf::MT, 2>::STG) * sizeof(double);
 	PHBC_CHECK(cudaFuncSetAttribute(lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
@@ -658,16 +666,40 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	int lper_sm = 1;
 	PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lper_sm, lower, lthreads, lsmem));
 	if (lper_sm < 1) lper_sm = 1;
+	for (int z0 = 0; z0 < cnt; z0 += 65535) {
+		const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
+		lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ltiles), C, zc), lthreads, lsmem, ctx->stream>>>(b, d_ops + z0, ctx->d_dmma_img);
+		ctx->launches++;
+	}
+	PHBC_CHECK(cudaGetLastError());
+	return 0;
+}
+
+int phbc_dmma_pack(phbc_ctx *ctx) {
+	if (ctx->S == 20) return dmma_pack<20>(ctx);
+	if (ctx->S == 61) return dmma_pack<61>(ctx);
+	return -1;
+}
+int phbc_dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
+	if (ctx->S == 20) return dmma_lower_ops<20>(ctx, d_ops, cnt);
+	if (ctx->S == 61) return dmma_lower_ops<61>(ctx, d_ops, cnt);
+	return -1;
+}
+
+template <int S>
+static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
+	using Sh = DmmaShape<S>;
+	using Cf = DmmaConfig<S>;
+	const int C = ctx->C, P = ctx->P, N = ctx->N;
+	int rc;
+	if ((rc = phbc_generic_prepare(ctx, o))) return rc;
+	Bufs b = phbc_make_bufs(ctx);
+	if ((rc = dmma_pack<S>(ctx))) return rc;
 	if ((rc = phbc_time_begin(ctx))) return rc;
 	for (int l = 0; l < ctx->n_lower_levels; l++) {
 		const int beg = ctx->h_lower_level_off[l], cnt = ctx->h_lower_level_off[l + 1] - beg;
 		if (cnt <= 0) continue;
-		for (int z0 = 0; z0 < cnt; z0 += 65535) {
-			const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
-			lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ltiles), C, zc), lthreads, lsmem, ctx->stream>>>(b, ctx->d_lower_ops + beg + z0,
-			                                                                                                     ctx->d_dmma_img);
-			ctx->launches++;
-		}
+		if ((rc = dmma_lower_ops<S>(ctx, ctx->d_lower_ops + beg, cnt))) return rc;
 		if (o->scale && (rc = phbc_generic_scale_ops(ctx, ctx->d_lower_ops + beg, cnt, o->scaling_threshold))) return rc;
 	}
 	double *result = ctx->d_result + (size_t)o->batch_index * (1 + N);

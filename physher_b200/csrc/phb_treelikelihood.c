@@ -58,6 +58,15 @@ struct phb_tlk {
 	int post_first_tips, pre_first_tips;
 	int have_time_tree;
 
+	/* resident node-at-a-time partials (PHB_OPT_INCREMENTAL): which device buffers hold values of the CURRENT inputs */
+	int incremental, resident, all_dirty;
+	unsigned char *lower_ok, *upper_ok; /* [N] */
+	int upper_irf;                      /* include_root_freqs value the valid uppers were built with */
+	int *upper_op_of;                   /* [N] index into upper_ops */
+	phbc_op *sub_ops;                   /* [2N] scratch op list */
+	int *sub_level_off;                 /* [N + 2] */
+	int *path;                          /* [N] scratch */
+
 	/* host mirrors of the small model inputs + the stored state of store / restore (MCMC, treelikelihood.c:116-161) */
 	double *h_evec, *h_eval, *h_ivec, *h_freqs, *h_rates, *h_props;
 	int has_store;
@@ -500,7 +509,15 @@ phb_tlk *phb_tlk_create(int ntips, int nstate, int ncat, int npatterns, const in
 	t->parent = (int *)malloc(sizeof(int) * N);
 	t->bl = (double *)calloc(N, sizeof(double));
 	t->update_nodes = (unsigned char *)malloc(N);
-	if (!t->left || !t->right || !t->parent || !t->bl || !t->update_nodes) {
+	t->lower_ok = (unsigned char *)calloc(N, 1);
+	t->upper_ok = (unsigned char *)calloc(N, 1);
+	t->upper_op_of = (int *)malloc(sizeof(int) * N);
+	t->sub_ops = (phbc_op *)malloc(sizeof(phbc_op) * 2 * (size_t)N);
+	t->sub_level_off = (int *)malloc(sizeof(int) * ((size_t)N + 2));
+	t->path = (int *)malloc(sizeof(int) * N);
+	t->all_dirty = 1;
+	if (!t->left || !t->right || !t->parent || !t->bl || !t->update_nodes || !t->lower_ok || !t->upper_ok || !t->upper_op_of || !t->sub_ops ||
+	    !t->sub_level_off || !t->path) {
 		phb_tlk_free(t);
 		fail(PHB_ENOMEM, "phb_tlk_create: out of memory");
 		return NULL;
@@ -531,6 +548,10 @@ phb_tlk *phb_tlk_create(int ntips, int nstate, int ncat, int npatterns, const in
 	t->kernels = PHB_KERNELS_AUTO;
 	int rc = build_level_schedules(t);
 	if (rc == PHB_OK) rc = build_walk_schedules(t);
+	if (rc == PHB_OK) {
+		for (int n = 0; n < N; n++) t->upper_op_of[n] = -1;
+		for (int k = 0; k < N - 1; k++) t->upper_op_of[t->upper_ops[k].out - N] = k;
+	}
 	if (rc != PHB_OK) {
 		phb_tlk_free(t);
 		return NULL;
@@ -593,6 +614,7 @@ void phb_tlk_free(phb_tlk *t) {
 	free(t->pre_tip_order);
 	free(t->post_chunk_tip0);
 	free(t->pre_chunk_tip0);
+	free(t->lower_ok), free(t->upper_ok), free(t->upper_op_of), free(t->sub_ops), free(t->sub_level_off), free(t->path);
 	free(t->h_evec), free(t->h_eval), free(t->h_ivec), free(t->h_freqs), free(t->h_rates), free(t->h_props);
 	free(t->st_bl), free(t->st_evec), free(t->st_eval), free(t->st_ivec), free(t->st_freqs), free(t->st_rates), free(t->st_props);
 	free(t);
@@ -606,6 +628,7 @@ void phb_tlk_update_all_nodes(phb_tlk *t) { /* treelikelihood.c:1737-1744 */
 	memset(t->update_nodes, 1, t->N);
 	t->update = 1;
 	t->update_upper = 1;
+	t->all_dirty = 1; /* resident partials (if any) are stale as a whole */
 }
 
 int phb_tlk_update_one_node(phb_tlk *t, int node) { /* treelikelihood.c:1747-1751 */
@@ -703,6 +726,19 @@ int phb_tlk_set_branch_lengths(phb_tlk *t, const double *bl) {
 		if (n != t->root && bl[n] < 0) /* treelikelihood.c:1659-1662 exits on a negative length */
 			return fail(PHB_EINVAL, "calculate_partials: node %d branch length = %E", n, bl[n]);
 	}
+	if (t->incremental && t->resident && !t->all_dirty && t->have_bl && bl != t->bl) {
+		/* resident partials: only the branches whose length differs are dirty (what the reference's per-node listener reports) */
+		for (int n = 0; n < t->N; n++)
+			if (n != t->root && bl[n] != t->bl[n]) {
+				t->bl[n] = bl[n];
+				t->update_nodes[n] = 1;
+				t->update = 1;
+				t->update_upper = 1;
+			}
+		t->bl_dirty = 1;
+		t->bl_changed = 1;
+		return PHB_OK;
+	}
 	if (bl != t->bl) memcpy(t->bl, bl, sizeof(double) * t->N);
 	t->have_bl = 1;
 	t->bl_dirty = 1;
@@ -747,8 +783,18 @@ int phb_tlk_set_option(phb_tlk *t, int option, int value) {
 		if (value < PHB_KERNELS_AUTO || value > PHB_KERNELS_FUSED) return fail(PHB_EINVAL, "unknown kernel family %d", value);
 		if (t->kernels == value) return PHB_OK;
 		t->kernels = value;
+		t->all_dirty = 1;
 		break;
-	case PHB_OPT_SCALING_THRESHOLD_EXP: t->scaling_threshold = pow(10.0, -(double)value); break;
+	case PHB_OPT_SCALING_THRESHOLD_EXP:
+		t->scaling_threshold = pow(10.0, -(double)value);
+		t->all_dirty = 1;
+		break;
+	case PHB_OPT_INCREMENTAL:
+		if (t->incremental == (value != 0)) return PHB_OK;
+		t->incremental = value != 0;
+		t->resident = 0;
+		phb_tlk_update_all_nodes(t);
+		return PHB_OK;
 	case PHB_OPT_TIMING: {
 		int rc = phbc_set_timing(t->ctx, value);
 		if (rc) return dev_fail(rc);
@@ -810,11 +856,233 @@ static int evaluate_once(phb_tlk *t, int want_gradient, double *lnl, double *gra
 	return PHB_OK;
 }
 
+
+/* ------------------------------------------------------------------------------------------- */
+/* resident partials: incremental evaluation and the single-branch fast path                   */
+/* ------------------------------------------------------------------------------------------- */
+
+/*
+ * With PHB_OPT_INCREMENTAL the object keeps every lower (and, once asked for, upper) partial on the device between calls, like the
+ * reference's tlk->partials, and an evaluation recomputes only what the dirty flags reach:
+ *   lower partials   the proper ancestors of every node marked by update_one_node / set_branch_length -- the traversal of
+ *                    _calculate_partials (treelikelihood.c:1645-1734), as per-level op lists;
+ *   upper partials   U_x stays valid iff x lies on the root path of EVERY changed branch (U_x depends on everything outside the
+ *                    subtree of x, and on the length of x's own branch not at all); the others are rebuilt lazily, top-down, for the
+ *                    nodes a caller needs (update_upper_partials2, :2164-2190; the node-change logic of _calculate_uppper, :2592-2636).
+ * Any other change (model, site model, tips, weights, options) marks the whole object dirty and the next evaluation is a full one.
+ * These evaluations run on the node-at-a-time kernels (tensor-core kernels for 20 / 61 states); the fused 4-state walk keeps no
+ * partials and is used only when the option is off.
+ */
+static void fill_opts_resident(const phb_tlk *t, phbc_eval_opts *o, int want_gradient) {
+	fill_opts(t, o, want_gradient, 0);
+	o->kernels = ((t->S == 20 || t->S == 61) && t->kernels != PHB_KERNELS_GENERIC) ? PHB_KERNELS_AUTO : PHB_KERNELS_GENERIC;
+	o->materialize_uppers = 1;
+}
+
+static void mark_clean(phb_tlk *t) {
+	memset(t->update_nodes, 0, t->N);
+	t->update = 0;
+}
+
+/* full evaluation that leaves all lower partials (and with want_gradient all upper partials) resident */
+static int resident_full(phb_tlk *t, int want_gradient, double *lnl, double *grad_out) {
+	int rc = check_ready(t);
+	if (rc) return rc;
+	if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+	t->bl_dirty = 0;
+	t->resident = 0;
+	for (int attempt = 0; attempt < 2; attempt++) {
+		phbc_eval_opts o;
+		fill_opts_resident(t, &o, want_gradient);
+		if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
+		if ((rc = phbc_download_results(t->ctx, 1, lnl, want_gradient ? grad_out : NULL))) return dev_fail(rc);
+		if (isinf(*lnl) && !t->scale) {
+			fprintf(stdout, "_calculate: rescaling %f\n", *lnl); /* treelikelihood.c:1497 */
+			t->scale = 1;
+			continue;
+		}
+		break;
+	}
+	if (isnan(*lnl) || isinf(*lnl)) return PHB_OK; /* nothing is marked valid */
+	for (int n = 0; n < t->N; n++) {
+		t->lower_ok[n] = 1;
+		t->upper_ok[n] = want_gradient != 0;
+	}
+	t->upper_irf = t->include_root_freqs;
+	t->resident = 1;
+	t->all_dirty = 0;
+	return PHB_OK;
+}
+
+/* make lnL and every lower partial current; recomputes only the ancestors of changed branches when it can */
+static int resident_calculate(phb_tlk *t, double *lnl) {
+	if (!t->update && t->resident && !t->all_dirty) {
+		*lnl = t->lk;
+		return PHB_OK;
+	}
+	int rc;
+	if (!t->resident || t->all_dirty) {
+		if ((rc = resident_full(t, 0, &t->lk, NULL))) return rc;
+	} else {
+		if ((rc = check_ready(t))) return rc;
+		const int N = t->N;
+		/* lowers: every proper ancestor of a changed branch; uppers: valid only on the root path of every changed branch */
+		int ndirty = 0;
+		int *cnt = t->path;
+		memset(cnt, 0, sizeof(int) * N);
+		for (int n = 0; n < N; n++) {
+			if (!t->update_nodes[n] || n == t->root) continue;
+			ndirty++;
+			cnt[n]++;
+			for (int a = t->parent[n]; a >= 0; a = t->parent[a]) {
+				t->lower_ok[a] = 0;
+				cnt[a]++;
+			}
+		}
+		if (ndirty)
+			for (int n = 0; n < N; n++)
+				if (cnt[n] != ndirty) t->upper_ok[n] = 0;
+		int nops = 0;
+		for (int l = 0; l < t->n_lower_levels; l++) {
+			t->sub_level_off[l] = nops;
+			for (int k = t->lower_level_off[l]; k < t->lower_level_off[l + 1]; k++)
+				if (!t->lower_ok[t->lower_ops[k].out]) t->sub_ops[nops++] = t->lower_ops[k];
+		}
+		t->sub_level_off[t->n_lower_levels] = nops;
+		if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+		t->bl_dirty = 0;
+		phbc_eval_opts o;
+		fill_opts_resident(t, &o, 0);
+		if ((rc = phbc_run_ops(t->ctx, &o, nops, t->sub_ops, t->n_lower_levels, t->sub_level_off, 1, 1, &t->lk))) return dev_fail(rc);
+		if (isinf(t->lk) && !t->scale) { /* treelikelihood.c:1496-1519: switch rescaling on and recompute everything */
+			fprintf(stdout, "_calculate: rescaling %f\n", t->lk);
+			t->scale = 1;
+			if ((rc = resident_full(t, 0, &t->lk, NULL))) return rc;
+		} else if (!isnan(t->lk) && !isinf(t->lk)) {
+			for (int n = 0; n < N; n++) t->lower_ok[n] = 1;
+		}
+	}
+	*lnl = t->lk;
+	if (isnan(t->lk) || isinf(t->lk)) {
+		if (isnan(t->lk)) phb_tlk_update_all_nodes(t); /* :1489-1495 */
+		t->resident = 0;
+		return PHB_OK;
+	}
+	mark_clean(t);
+	t->update_upper = 1;
+	return PHB_OK;
+}
+
+/* make U_node (node >= 0) or every upper partial (node < 0) current; lowers and matrices must be current */
+static int resident_uppers(phb_tlk *t, int node, int irf) {
+	const int N = t->N;
+	if (t->upper_irf != irf) {
+		memset(t->upper_ok, 0, N);
+		t->upper_irf = irf;
+	}
+	int nops = 0, nlevels = 0;
+	if (node >= 0) {
+		int len = 0;
+		for (int x = node; x != t->root; x = t->parent[x]) t->path[len++] = x;
+		for (int k = len - 1; k >= 0; k--) { /* top-down: each op needs the one before it */
+			const int x = t->path[k];
+			if (t->upper_ok[x]) continue;
+			t->sub_level_off[nlevels++] = nops;
+			t->sub_ops[nops++] = t->upper_ops[t->upper_op_of[x]];
+		}
+		t->sub_level_off[nlevels] = nops;
+	} else {
+		for (int l = 0; l < t->n_upper_levels; l++) {
+			t->sub_level_off[l] = nops;
+			for (int k = t->upper_level_off[l]; k < t->upper_level_off[l + 1]; k++)
+				if (!t->upper_ok[t->upper_ops[k].out - N]) t->sub_ops[nops++] = t->upper_ops[k];
+		}
+		nlevels = t->n_upper_levels;
+		t->sub_level_off[nlevels] = nops;
+	}
+	if (nops == 0) return PHB_OK;
+	phbc_eval_opts o;
+	fill_opts_resident(t, &o, 1);
+	o.include_root_freqs = irf;
+	int rc = phbc_run_ops(t->ctx, &o, nops, t->sub_ops, nlevels, t->sub_level_off, 0, 0, NULL);
+	if (rc) return dev_fail(rc);
+	for (int k = 0; k < nops; k++) t->upper_ok[t->sub_ops[k].out - N] = 1;
+	return PHB_OK;
+}
+
+/* SingleTreeLikelihood_update_uppers (treelikelihood.c:1530-1538): lnL, then every upper partial (root frequencies not folded in) */
+int phb_tlk_update_uppers(phb_tlk *t) {
+	if (!t->incremental) {
+		t->incremental = 1;
+		t->resident = 0;
+	}
+	double lnl;
+	int rc = resident_calculate(t, &lnl);
+	if (rc) return rc;
+	if (isnan(lnl) || isinf(lnl)) return fail(PHB_ESTATE, "update_uppers: lnL = %f", lnl);
+	return resident_uppers(t, -1, 0);
+}
+
+/* _calculate_uppper + calculate_dldt_uppper + d2lnldt2_uppper (treelikelihood.c:2592-2686, 2195-2335) at nbl candidate lengths */
+int phb_tlk_calculate_branch(phb_tlk *t, int node, int nbl, const double *bl, double *lnl, double *dlnl, double *d2lnl) {
+	if (node < 0 || node >= t->N || node == t->root) return fail(PHB_EINVAL, "calculate_branch: node %d is not a branch (root %d)", node, t->root);
+	if (nbl < 1 || !bl) return fail(PHB_EINVAL, "calculate_branch: nbl >= 1 and bl are required");
+	if (t->have_matrices) return fail(PHB_ESTATE, "calculate_branch needs the eigen system: explicit matrices cannot be re-evaluated at a new length");
+	for (int k = 0; k < nbl; k++)
+		if (bl[k] < 0) return fail(PHB_EINVAL, "calculate_partials: node %d branch length = %E", node, bl[k]);
+	if (!t->incremental) {
+		t->incremental = 1;
+		t->resident = 0;
+	}
+	double cur;
+	int rc = resident_calculate(t, &cur);
+	if (rc) return rc;
+	if (isnan(cur) || isinf(cur)) {
+		for (int k = 0; k < nbl; k++) {
+			if (lnl) lnl[k] = cur;
+			if (dlnl) dlnl[k] = NAN;
+			if (d2lnl) d2lnl[k] = NAN;
+		}
+		return PHB_OK;
+	}
+	if ((rc = resident_uppers(t, node, 0))) return rc;
+	double *out = (double *)malloc(sizeof(double) * 3 * (size_t)nbl);
+	if (!out) return fail(PHB_ENOMEM, "out of memory");
+	phbc_eval_opts o;
+	fill_opts_resident(t, &o, 1);
+	rc = phbc_branch_lnl(t->ctx, &o, node, nbl, bl, out);
+	if (!rc)
+		for (int k = 0; k < nbl; k++) {
+			if (lnl) lnl[k] = out[3 * k];
+			if (dlnl) dlnl[k] = out[3 * k + 1];
+			if (d2lnl) d2lnl[k] = out[3 * k + 2];
+		}
+	free(out);
+	if (rc) return dev_fail(rc);
+	return PHB_OK;
+}
+
+/* lnL + gradient from resident partials: incremental lowers, the missing uppers, then the K9 / K10 reductions over all branches */
+static int resident_gradient(phb_tlk *t, double *lnl, double *grad_out) {
+	int rc;
+	if (!t->resident || t->all_dirty) return resident_full(t, 1, lnl, grad_out);
+	if ((rc = resident_calculate(t, lnl))) return rc;
+	if (isnan(*lnl) || isinf(*lnl)) return PHB_OK;
+	if ((rc = resident_uppers(t, -1, t->include_root_freqs))) return rc;
+	phbc_eval_opts o;
+	fill_opts_resident(t, &o, 1);
+	if ((rc = phbc_resident_gradient(t->ctx, &o))) return dev_fail(rc);
+	double dummy;
+	if ((rc = phbc_download_results(t->ctx, 1, &dummy, grad_out))) return dev_fail(rc);
+	return PHB_OK;
+}
+
 int phb_tlk_calculate(phb_tlk *t, double *lnl) {
 	if (!t->update) { /* cached, treelikelihood.c:1458-1460 */
 		*lnl = t->lk;
 		return PHB_OK;
 	}
+	if (t->incremental) return resident_calculate(t, lnl);
 	int rc = evaluate_once(t, 0, &t->lk, NULL);
 	if (rc) return rc;
 	*lnl = t->lk;
@@ -865,7 +1133,7 @@ int phb_tlk_gradient(phb_tlk *t, const double **grad) {
 	}
 	if (t->update_upper || t->update) { /* treelikelihood.c:323 */
 		double lnl;
-		int rc = evaluate_once(t, 1, &lnl, t->gradient);
+		int rc = t->incremental ? resident_gradient(t, &lnl, t->gradient) : evaluate_once(t, 1, &lnl, t->gradient);
 		if (rc) return rc;
 		t->lk = lnl;
 		if (isnan(lnl) || isinf(lnl)) { /* :328-332 */
@@ -910,6 +1178,7 @@ int phb_tlk_gradient_device(phb_tlk *t, double *out_device) {
 	if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
 	phbc_eval_opts o;
 	fill_opts(t, &o, 1, 0);
+	t->resident = 0;
 	if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
 	if ((rc = phbc_result_to_device(t->ctx, 0, out_device))) return dev_fail(rc);
 	/* the device copy holds raw per-shard sums; the caller applies the unrooted convention after the reduction */
@@ -980,6 +1249,7 @@ int phb_tlk_matrix_gradient(phb_tlk *t, int nsets, const double *M, double *out)
 		phbc_eval_opts o;
 		fill_opts(t, &o, 1, 0);
 		double lnl = 0.0;
+		t->resident = 0; /* the sweep rebuilds every partial with its own options */
 		if ((rc = phbc_matrix_gradient(t->ctx, &o, nsets, M, t->unrooted ? t->right[t->root] : -1, &lnl, out))) return dev_fail(rc);
 		t->lk = lnl;
 		if (isinf(lnl) && !t->scale) { /* treelikelihood.c:1496-1519 */
@@ -1059,6 +1329,7 @@ int phb_tlk_restore(phb_tlk *t) {
 	t->update = t->st_update || (t->eigen_changed && !t->st_have_eigen); /* explicit matrices were not stored */
 	if (!t->update) memset(t->update_nodes, 0, t->N);
 	t->update_upper = 1; /* the gradient buffer belongs to the rejected state */
+	if (t->eigen_changed || t->freqs_changed || t->site_changed || t->bl_changed) t->all_dirty = 1; /* so do resident partials */
 	t->eigen_changed = t->freqs_changed = t->site_changed = t->bl_changed = 0;
 	return PHB_OK;
 }

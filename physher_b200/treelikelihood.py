@@ -24,6 +24,7 @@ OPT_UNROOTED = 3
 OPT_KERNELS = 4
 OPT_SCALING_THRESHOLD_EXP = 5
 OPT_TIMING = 6
+OPT_INCREMENTAL = 7
 KERNELS_AUTO, KERNELS_GENERIC, KERNELS_FUSED = 0, 1, 2
 
 _dp = C.POINTER(C.c_double)
@@ -59,6 +60,8 @@ SYMBOLS = [
     ("phb_tlk_gradient", C.c_int, [C.c_void_p, C.POINTER(_dp)]),
     ("phb_tlk_cat_branch_gradient", C.c_int, [C.c_void_p, _dp]),
     ("phb_tlk_matrix_gradient", C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    ("phb_tlk_update_uppers", C.c_int, [C.c_void_p]),
+    ("phb_tlk_calculate_branch", C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
     ("phb_tlk_get_partials", C.c_int, [C.c_void_p, C.c_int, _dp]),
     ("phb_tlk_get_matrices", C.c_int, [C.c_void_p, _dp, _dp]),
     ("phb_tlk_gradient_device", C.c_int, [C.c_void_p, C.c_void_p]),
@@ -291,6 +294,19 @@ class SingleTreeLikelihood:
         out = np.zeros(a.shape[0])
         self._check(self.lib.phb_tlk_matrix_gradient(self.h, a.shape[0], a.ctypes.data_as(_dp), out.ctypes.data_as(_dp)))
         return out
+
+    def update_uppers(self):
+        """SingleTreeLikelihood_update_uppers (treelikelihood.c:1530-1538): lnL, then every upper partial, kept on the device."""
+        self._check(self.lib.phb_tlk_update_uppers(self.h))
+
+    def calculate_branch(self, node, bl):
+        """_calculate_uppper + calculate_dldt_uppper + d2lnldt2_uppper (treelikelihood.c:2592-2686, 2195-2335) for candidate
+        lengths `bl` of the branch above `node`: arrays lnL, d lnL/dt, d2 lnL/dt2."""
+        a = np.atleast_1d(_f64(bl))
+        lnl, d1, d2 = np.zeros(a.size), np.zeros(a.size), np.zeros(a.size)
+        self._check(self.lib.phb_tlk_calculate_branch(self.h, int(node), int(a.size), a.ctypes.data_as(_dp), lnl.ctypes.data_as(_dp),
+                                                      d1.ctypes.data_as(_dp), d2.ctypes.data_as(_dp)))
+        return lnl, d1, d2
 
     def get_partials(self, index):
         out = np.zeros((self.C, self.P, self.S))

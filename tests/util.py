@@ -15,7 +15,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RTOL = 1e-10
 
 
-AUX_FIXTURES = {"c1_time_tree", "sitepatterns", "dlnl_dq_gtr_g4"}  # inputs / outputs of other rows (tests/test_time_tree.py), not tree-likelihood problems
+AUX_FIXTURES = {"c1_time_tree", "sitepatterns", "dlnl_dq_gtr_g4", "branch_derivatives"}  # inputs / outputs of other rows (tests/test_time_tree.py), not tree-likelihood problems
 
 
 def golden_names():
