@@ -51,6 +51,8 @@ typedef struct Backend {
 	int N, S, C;
 	double *bl, *rates, *props, *freqs, *evec, *eval, *ivec, *P, *dP, *branch_gradient, *cat_gradient, *site_bl;
 	int have_model; /* the substitution model has been pushed at least once */
+	int incremental; /* the device object keeps its partials resident (single-branch fast path in use) */
+	double (*ref_d2logP)(Model *, const Parameter *);
 	long long evaluations;
 } Backend;
 
@@ -161,7 +163,7 @@ static int prepare(Backend *b) {
 	if (Tree_is_time_mode(tlk->tree)) Tree_update_heights(tlk->tree); /* :1468 */
 	sync_inputs(b);
 	if (phb_tlk_rescaling(b->h) != (int)tlk->scale) phb_tlk_use_rescaling(b->h, tlk->scale);
-	phb_tlk_update_all_nodes(b->h);
+	if (!b->incremental) phb_tlk_update_all_nodes(b->h); /* resident partials: the setters above marked exactly what moved */
 	return 1;
 }
 
@@ -178,9 +180,51 @@ static double finish(Backend *b, double lnl) {
 	return lnl;
 }
 
+/*
+ * tlk->calculate while tlk->use_upper is set: the control flow of _calculate (treelikelihood.c:1552-1607).  The optimiser has
+ * changed the length of ONE branch (Brent on that branch) or has just moved on to the next branch (two nodes flagged: the
+ * previous one, whose final length is now pushed to the device object, and the new one).  The branch under optimisation is
+ * evaluated from its upper and lower partials at its candidate length (phb_tlk_calculate_branch == _calculate_uppper, :2592-2686);
+ * the device object recomputes only the partials the pushed change reaches.
+ */
+static double calculate_upper_mode(Backend *b) {
+	SingleTreeLikelihood *tlk = b->tlk;
+	if (!tlk->update) return tlk->lk; /* "no update", :1582-1587 */
+	if (Tree_is_time_mode(tlk->tree)) {
+		fprintf(stderr, "physher_b200: use_upper on a time tree is not on the device path\n");
+		exit(2);
+	}
+	const int prev = tlk->node_upper ? Node_id(tlk->node_upper) : -1;
+	int count = 0, cur = -1;
+	for (int i = 0; i < b->N; i++)
+		if (tlk->update_nodes[i]) {
+			count++;
+			if (count == 1 || i != prev) cur = i; /* one flagged node: that one; more: the one that is not node_upper (:1591-1599) */
+		}
+	if (cur < 0) return tlk->lk;
+	for (int i = 0; i < b->N; i++) { /* every other flagged branch takes its current length for good */
+		if (!tlk->update_nodes[i] || i == cur) continue;
+		Node *n = Tree_node(tlk->tree, i);
+		const int id = Node_id(n);
+		if (!Node_isroot(n) && Node_distance(n) != b->bl[id]) {
+			if (phb_tlk_set_branch_length(b->h, id, Node_distance(n))) die("set_branch_length");
+			b->bl[id] = Node_distance(n);
+		}
+		tlk->update_nodes[i] = false;
+	}
+	Node *node = Tree_node(tlk->tree, cur);
+	const double t = Node_distance(node);
+	double lnl = NAN;
+	if (phb_tlk_calculate_branch(b->h, Node_id(node), 1, &t, &lnl, NULL, NULL)) die("calculate_branch");
+	b->evaluations++;
+	tlk->node_upper = node;
+	return tlk->lk = lnl;
+}
+
 /* == tlk->calculate: control flow of _calculate_simple (treelikelihood.c:1454-1526), numerics on the device */
 static double phb_physher_calculate(SingleTreeLikelihood *tlk) {
 	Backend *b = backend_of_tlk(tlk);
+	if (tlk->use_upper && b->incremental) return calculate_upper_mode(b);
 	if (!tlk->update) return tlk->lk; /* :1458 */
 	if (!prepare(b)) return tlk->lk = NAN;
 	double lnl = NAN;
@@ -273,6 +317,62 @@ static double phb_physher_dlogP(Model *self, const Parameter *p) {
 	return b->ref_dlogP(self, p);
 }
 
+/* == SingleTreeLikelihood_update_uppers (treelikelihood.c:1530-1538), the call that opens serial_brent_optimize_tree
+ * (optimizer.c:125), NNI and SPR: lnL, every upper partial, use_upper on.  A non-virtual function in the reference, so a drop-in
+ * build forwards it here when a backend is attached. */
+void phb_physher_update_uppers(Model *model) {
+	SingleTreeLikelihood *tlk = (SingleTreeLikelihood *)model->obj;
+	Backend *b = backend_of_tlk(tlk);
+	if (!b) {
+		SingleTreeLikelihood_update_uppers(tlk);
+		return;
+	}
+	if (!b->incremental) {
+		b->incremental = 1;
+		if (phb_tlk_set_option(b->h, PHB_OPT_INCREMENTAL, 1)) die("set_option");
+	}
+	double lnl = NAN;
+	if (!prepare(b)) die("update_uppers: site model");
+	if (phb_tlk_update_uppers(b->h)) die("update_uppers");
+	if (phb_tlk_calculate(b->h, &lnl)) die("calculate"); /* cached */
+	finish(b, lnl);
+	tlk->update_upper = false;
+	tlk->use_upper = true;
+	tlk->node_upper = NULL;
+}
+
+/* == model->d2logP for a branch length (_singleTreeLikelihood_d2logP, treelikelihood.c:470-527): calculate_dldt_uppper +
+ * d2lnldt2_uppper at the current length, from the device's upper / lower partials of that branch */
+static double phb_physher_d2logP(Model *self, const Parameter *p) {
+	SingleTreeLikelihood *tlk = (SingleTreeLikelihood *)self->obj;
+	Backend *b = backend_of_tlk(tlk);
+	Node *node = NULL;
+	for (int i = 0; i < b->N; i++) {
+		Node *n = Tree_node(tlk->tree, i);
+		if (n->distance && strcmp(n->distance->name, Parameter_name(p)) == 0) {
+			node = n;
+			break;
+		}
+	}
+	if (!node || Node_isroot(node) || Tree_is_time_mode(tlk->tree)) return b->ref_d2logP(self, p); /* finite differences (:485-487) */
+	if (!b->incremental) {
+		b->incremental = 1;
+		if (phb_tlk_set_option(b->h, PHB_OPT_INCREMENTAL, 1)) die("set_option");
+	}
+	if (tlk->update) {
+		double lnl = NAN;
+		if (!prepare(b)) return NAN;
+		if (phb_tlk_calculate(b->h, &lnl)) die("calculate");
+		finish(b, lnl);
+		if (isnan(lnl) || isinf(lnl)) return lnl; /* :501-503 */
+	}
+	const double t = Node_distance(node);
+	double lnl, d1, d2;
+	if (phb_tlk_calculate_branch(b->h, Node_id(node), 1, &t, &lnl, &d1, &d2)) die("calculate_branch");
+	if (isnan(d2)) SingleTreeLikelihood_update_all_nodes(tlk); /* :520-522 */
+	return d2;
+}
+
 int phb_physher_detach(Model *model);
 
 static void phb_physher_free(Model *self) {
@@ -338,9 +438,11 @@ int phb_physher_attach(Model *model, int device) {
 	b->eval = (double *)calloc(S, sizeof(double));
 	b->ref_calculate = tlk->calculate;
 	b->ref_dlogP = model->dlogP;
+	b->ref_d2logP = model->d2logP;
 	b->ref_free = model->free;
 	tlk->calculate = phb_physher_calculate;
 	model->dlogP = phb_physher_dlogP;
+	model->d2logP = phb_physher_d2logP;
 	model->free = phb_physher_free;
 	b->next = g_backends;
 	g_backends = b;
@@ -357,7 +459,9 @@ int phb_physher_detach(Model *model) {
 	*pp = b->next;
 	tlk->calculate = b->ref_calculate;
 	model->dlogP = b->ref_dlogP;
+	model->d2logP = b->ref_d2logP;
 	model->free = b->ref_free;
+	tlk->use_upper = false;
 	SingleTreeLikelihood_update_all_nodes(tlk);
 	phb_tlk_free(b->h);
 	free(b->bl), free(b->branch_gradient), free(b->rates), free(b->props), free(b->freqs);

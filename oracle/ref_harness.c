@@ -501,3 +501,45 @@ int refh_branch_derivatives(void *vh, int id, double bl, double *out) {
 	tlk->use_upper = false;
 	return 0;
 }
+
+/*
+ * The access pattern of serial_brent_optimize_tree (optimizer.c:111-152) with fixed candidate lengths instead of Brent's: open
+ * with update_uppers (the reference's own, or the one passed in -- a drop-in backend's), then visit the branches in post-order
+ * (not the root, not the root's right child) and evaluate tlk->calculate at d0 * factors[k] for each; the last factor stays.
+ * out receives one lnL per (branch, factor); ids (optional) the node id of each visit.  Returns the number of values.
+ */
+int refh_upper_walk(void *vh, void (*update_uppers)(Model *), const double *factors, int nf, double *out, int *ids, int cap) {
+	RefH *h = (RefH *)vh;
+	SingleTreeLikelihood *tlk = h->tlk;
+	Tree *tree = tlk->tree;
+	Node **nodes = Tree_get_nodes(tree, POSTORDER);
+	tlk->node_upper = NULL;
+	tlk->use_upper = true;
+	tlk->update_upper = true;
+	if (update_uppers) update_uppers(h->model);
+	else SingleTreeLikelihood_update_uppers(tlk);
+	int k = 0;
+	for (int i = 0; i < Tree_node_count(tree); i++) {
+		Node *node = nodes[i];
+		if (Node_isroot(node) || (Node_isroot(Node_parent(node)) && Node_right(Node_parent(node)) == node)) continue;
+		if (tlk->node_upper == NULL) tlk->node_upper = node;
+		const double d0 = Node_distance(node);
+		for (int f = 0; f < nf && k < cap; f++) {
+			Node_set_distance(node, d0 * factors[f]);
+			SingleTreeLikelihood_update_one_node(tlk, node);
+			if (ids) ids[k] = Node_id(node);
+			out[k++] = tlk->calculate(tlk);
+		}
+	}
+	tlk->use_upper = false;
+	SingleTreeLikelihood_update_all_nodes(tlk);
+	return k;
+}
+
+/* model->d2logP for the branch-length parameter of node `id` (Model vtable; _singleTreeLikelihood_d2logP, treelikelihood.c:470-527) */
+double refh_d2logP_branch(void *vh, int id) {
+	RefH *h = (RefH *)vh;
+	Node *node = Tree_node(h->tlk->tree, id);
+	SingleTreeLikelihood_update_all_nodes(h->tlk);
+	return h->model->d2logP(h->model, node->distance);
+}

@@ -40,6 +40,11 @@ def libs():
     G.phb_physher_gradient.restype = C.POINTER(C.c_double)
     G.phb_physher_evaluations.argtypes = [C.c_void_p]
     G.phb_physher_evaluations.restype = C.c_longlong
+    G.phb_physher_update_uppers.argtypes = [C.c_void_p]
+    L.refh_upper_walk.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_int]
+    L.refh_upper_walk.restype = C.c_int
+    L.refh_d2logP_branch.argtypes = [C.c_void_p, C.c_int]
+    L.refh_d2logP_branch.restype = C.c_double
     return L, G
 
 
@@ -140,3 +145,45 @@ def test_unrooted_gtr_gamma_through_the_glue(libs, tipstates):
         assert g[ref.root] == 0.0 and g[ref.root_right] == 0.0
     G.phb_physher_detach(model)
     ref.close()
+
+
+def test_single_branch_fast_path_through_the_glue(libs):
+    """tlk->use_upper: the access pattern of serial_brent_optimize_tree (optimizer.c:111-152) driven through tlk->calculate, once on
+    the reference's CPU path and once with the likelihood on the device; model->d2logP of a branch length the same way."""
+    from physher_b200 import synthetic as syn
+
+    L, G = libs
+    T, sites = 11, 400
+    topo = syn.random_topology(T, 61)
+    bl = syn.random_branch_lengths(topo, 62)
+    pat = syn.random_patterns(T, sites, 4, 0.3, 63, unknown_frac=0.02)
+    names = [f"t{i}" for i in range(T)]
+    seqs = dict(zip(names, syn.sequences_from_patterns(pat, syn.NUCLEOTIDES)))
+    gtr = O.nucleotide_model_spec("gtr", [0.1, 0.2, 0.3, 0.4], [0.05, 0.3, 0.1, 0.15, 0.3, 0.1])
+    spec = O.treelikelihood_spec(syn.to_newick(topo, bl, names), seqs, gtr, categories=4, alpha=0.5, tipstates=True)
+    factors = np.array([0.5, 2.0, 1.3])
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+
+    def walk(ref, update_uppers):
+        out, ids = np.zeros(3 * 2 * T), np.zeros(3 * 2 * T, dtype=np.int32)
+        n = L.refh_upper_walk(ref.h, update_uppers, factors.ctypes.data_as(dp), 3, out.ctypes.data_as(dp), ids.ctypes.data_as(ip), out.size)
+        return out[:n], ids[:n]
+
+    cpu = O.Reference(spec)
+    want, want_ids = walk(cpu, None)
+    d2_cpu = [L.refh_d2logP_branch(cpu.h, n) for n in (0, 5, T + 2)]
+    lnl_cpu_end = cpu.logP()
+    cpu.close()
+
+    dev = O.Reference(spec)
+    model = L.refh_model_handle(dev.h)
+    assert G.phb_physher_attach(model, 0) == 0
+    got, got_ids = walk(dev, C.cast(G.phb_physher_update_uppers, C.c_void_p))
+    assert got.size == want.size == 3 * (2 * T - 3) and (got_ids == want_ids).all()
+    assert np.max(np.abs(got - want) / np.abs(want)) < RTOL
+    assert G.phb_physher_evaluations(model) >= got.size, "the single-branch evaluations did not run through libphysher_b200"
+    d2_dev = [L.refh_d2logP_branch(dev.h, n) for n in (0, 5, T + 2)]
+    assert grad_err(np.array(d2_dev), np.array(d2_cpu)) < RTOL
+    assert rel_err(dev.logP(), lnl_cpu_end) < RTOL  # all kept lengths reached the device object
+    G.phb_physher_detach(model)
+    dev.close()
