@@ -132,6 +132,10 @@ int phb_tlk_cat_branch_gradient(phb_tlk *tlk, double *out /* [N][C] */);
  * w_p / L_p * sum_c prop_c sum_i f_i U_n[c,p,i] (M_k[n,c] L_n[c,p])_i.  Honours PHB_OPT_INCLUDE_ROOT_FREQS and rescaling.
  * Runs on the node-at-a-time kernels (materialised upper partials). */
 int phb_tlk_matrix_gradient(phb_tlk *tlk, int nsets, const double *M, double *out /* [nsets] */);
+/* The root term of the frequency parameters in calculate_dlnl_dQ (treelikelihood.c:2371-2404): out[i] = d lnL / d pi_i with the partials
+ * held fixed = sum_p w_p R[p,i] / L_p, R the category-integrated root partials; the caller contracts it with d pi / d theta
+ * (simplex->gradient, or a unit vector).  Reuses the partials phb_tlk_matrix_gradient left on the device when nothing changed since. */
+int phb_tlk_root_frequency_gradient(phb_tlk *tlk, double *out /* [S] */);
 
 /*
  * Single-branch fast path (tlk->use_upper: serial_brent_optimize_tree optimizer.c:111-152, NNI / SPR nniopt.c:301-334,

@@ -232,6 +232,55 @@ static double phb_physher_calculate(SingleTreeLikelihood *tlk) {
 	return finish(b, lnl);
 }
 
+/*
+ * calculate_dlnl_dQ (treelikelihood.c:2337-2583) for the parameter indices [first, first + count): the per-node matrices dP/d theta
+ * come from the reference's own m->dPdp (:2421, :2484), the node sweep over upper partials, lower partials and pattern likelihoods
+ * runs on the device for all indices in one call (phb_tlk_matrix_gradient), and a frequency parameter adds its root term
+ * sum_i (d pi_i / d theta) * d lnL / d pi_i (:2371-2404) from phb_tlk_root_frequency_gradient.
+ */
+static void device_dlnl_dQ(Backend *b, int first, int count, double *out) {
+	SingleTreeLikelihood *tlk = b->tlk;
+	SubstitutionModel *m = tlk->m;
+	const int N = b->N, S = b->S, C = b->C;
+	if (count <= 0) return;
+	const size_t msz = (size_t)S * S, set = (size_t)N * C * msz;
+	double *M = (double *)calloc((size_t)count * set, sizeof(double));
+	if (!M) die("out of memory");
+	for (int k = 0; k < count; k++) {
+		m->dQ_need_update = true; /* :2360 */
+		for (int i = 0; i < N; i++) {
+			Node *n = Tree_node(tlk->tree, i);
+			const int id = Node_id(n);
+			if (Node_isroot(n)) continue;
+			for (int c = 0; c < C; c++) m->dPdp(m, first + k, M + (size_t)k * set + ((size_t)id * C + c) * msz, b->bl[id] * b->rates[c]);
+		}
+	}
+	if (phb_tlk_matrix_gradient(b->h, count, M, out)) die("matrix_gradient");
+	free(M);
+	/* frequency parameters: indices >= rateCount (:2362-2369) */
+	size_t rate_count = m->rates_simplex == NULL ? Parameters_count(m->rates) : m->rates_simplex->K - 1;
+	if (m->rates_simplex != NULL && !m->grad_wrt_reparam) rate_count++;
+	double *G = NULL, *dphi = NULL;
+	for (int k = 0; k < count; k++) {
+		if ((size_t)(first + k) < rate_count) continue;
+		if (tlk->get_root_frequencies(tlk) == tlk->root_frequencies) continue; /* fixed root frequencies: no root term (:2372) */
+		if (!G) {
+			G = (double *)calloc(S, sizeof(double));
+			dphi = (double *)calloc(S, sizeof(double));
+			if (phb_tlk_root_frequency_gradient(b->h, G)) die("root_frequency_gradient");
+		}
+		const size_t fi = (size_t)(first + k) - rate_count;
+		memset(dphi, 0, sizeof(double) * S);
+		if (m->grad_wrt_reparam) m->simplex->gradient(m->simplex, fi, dphi);
+		else dphi[fi] = 1.0;
+		double root_term = 0.0;
+		for (int i = 0; i < S; i++) root_term += dphi[i] * G[i];
+		out[k] += root_term;
+	}
+	free(G);
+	free(dphi);
+}
+
 /* == TreeLikelihood_gradient (treelikelihood.c:320-340).  Supported requests: TREE_MODEL and BRANCH_MODEL (what the
  * hot path produces: branch-length gradients and everything the reference derives from them on the host).  When the
  * lower pass is stale too, lnL and the gradient come out of ONE device evaluation (the reference runs calculate() and
@@ -241,9 +290,17 @@ double *phb_physher_gradient(Model *self) {
 	Backend *b = backend_of_tlk(tlk);
 	if (!b) return TreeLikelihood_gradient(self);
 	const int flags = tlk->prepared_gradient;
-	if (flags & ~((TREELIKELIHOOD_FLAG_TREE_MODEL) | (TREELIKELIHOOD_FLAG_BRANCH_MODEL) | (TREELIKELIHOOD_FLAG_SITE_MODEL))) {
-		fprintf(stderr, "physher_b200: gradient flags 0x%x include substitution-model parameters: not on the device path\n", flags);
-		exit(2);
+	const int subst_all = (flags & (TREELIKELIHOOD_FLAG_SUBSTITUTION_MODEL)) || (flags & (TREELIKELIHOOD_FLAG_SUBSTITUTION_MODEL_UNCONSTRAINED));
+	const int subst_rates = subst_all || (flags & (TREELIKELIHOOD_FLAG_SUBSTITUTION_MODEL_RATES));
+	const int subst_freqs = subst_all || (flags & (TREELIKELIHOOD_FLAG_SUBSTITUTION_MODEL_FREQUENCIES));
+	if (subst_rates || subst_freqs) {
+		/* the analytic route of the reference (calculate_dlnl_dQ on m->dPdp); its finite-difference routes (:3318-3334, :3344-3351)
+		 * re-evaluate logP and would run on the device through tlk->calculate, but are not wired here */
+		Model **models = (Model **)self->data;
+		if (tlk->m->dPdp == NULL || tlk->m->modeltype == NONREVERSIBLE || (!subst_all && models[1]->epsilon > 0.0)) {
+			fprintf(stderr, "physher_b200: substitution-model gradient by finite differences is not on the device path\n");
+			exit(2);
+		}
 	}
 	if ((flags & (TREELIKELIHOOD_FLAG_SITE_MODEL)) && (tlk->sm->proportions != NULL || tlk->sm->mu != NULL)) {
 		/* gradient_pinv_sitemodel reads the CPU root partials (treelikelihood.c:2943-2975); mu rescales rates and lengths (:3245-3249) */
@@ -298,7 +355,25 @@ double *phb_physher_gradient(Model *self) {
 			if (C > 1) gradient_discrete_sitemodel(tlk, b->cat_gradient, b->site_bl, grad_sitemodel);
 			if (Parameters_count(tlk->sm->rates) == 1) tlk->gradient[offset++] = grad_sitemodel[0];
 		}
-		if ((flags & (TREELIKELIHOOD_FLAG_BRANCH_MODEL)) && time_mode) gradient_clock(tlk, b->branch_gradient, tlk->gradient + offset);
+		if ((flags & (TREELIKELIHOOD_FLAG_BRANCH_MODEL)) && time_mode) {
+			gradient_clock(tlk, b->branch_gradient, tlk->gradient + offset);
+			offset += Parameters_count(tlk->bm->rates);
+		}
+		if (subst_rates || subst_freqs) {
+			/* index ranges of gradient_PMatrix / _rates / _frequencies (treelikelihood.c:3077-3113) */
+			SubstitutionModel *m = tlk->m;
+			size_t nrate = m->rates_simplex == NULL ? Parameters_count(m->rates) : m->rates_simplex->K;
+			if (m->rates_simplex != NULL && m->grad_wrt_reparam) nrate--;
+			size_t nfreq = 0;
+			if (m->simplex != NULL) {
+				nfreq = m->simplex->K;
+				if (m->grad_wrt_reparam) nfreq--;
+			}
+			const size_t first = subst_rates ? 0 : nrate;
+			const size_t count = (subst_rates ? nrate : 0) + (subst_freqs ? nfreq : 0);
+			device_dlnl_dQ(b, (int)first, (int)count, tlk->gradient + offset);
+			offset += count;
+		}
 		tlk->update_upper = false;
 	}
 	return tlk->gradient;

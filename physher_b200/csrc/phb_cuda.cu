@@ -853,6 +853,73 @@ extern "C" int phbc_run_ops(phbc_ctx *ctx, const phbc_eval_opts *o, int nops, co
 	return 0;
 }
 
+// d lnL / d pi_i at fixed partials: G_i = sum_k w_k R[k,i] / L_k with R the category-integrated root partials -- the "root term" of the
+// frequency parameters in calculate_dlnl_dQ (treelikelihood.c:2371-2404); under rescaling R and L_k carry the same factor (:2384-2392).
+// grid (pattern tiles, S); partial [S][tiles]
+__global__ void k_root_freq_gradient(Bufs b, int root, const double *__restrict__ freqs, const double *__restrict__ props,
+                                     const double *__restrict__ weights, double *__restrict__ partial) {
+	__shared__ double red[8];
+	const int S = b.S, i = blockIdx.y;
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	double v = 0.0;
+	if (p < b.P) {
+		double L = 0.0, Ri = 0.0;
+		for (int j = 0; j < S; j++) {
+			double r = 0.0;
+			for (int c = 0; c < b.C; c++) {
+				const double x = partial_ptr(b, root, c)[(size_t)p * S + j];
+				r += (b.C == 1) ? x : x * props[c];
+			}
+			L += freqs[j] * r;
+			if (j == i) Ri = r;
+		}
+		v = weights[p] * Ri / L;
+	}
+	v = phb_warp_sum(v);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double s = 0.0;
+		for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w];
+		partial[(size_t)i * gridDim.x + blockIdx.x] = s;
+	}
+}
+__global__ void k_sum_rows(const double *__restrict__ partial, int n, double *__restrict__ out) {
+	__shared__ double red[8];
+	const double *in = partial + (size_t)blockIdx.x * n;
+	double v = 0.0;
+	for (int k = threadIdx.x; k < n; k += blockDim.x) v += in[k];
+	v = phb_warp_sum(v);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double s = 0.0;
+		for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w];
+		out[blockIdx.x] = s;
+	}
+}
+
+// the root's lower partial must be resident (any node-at-a-time evaluation of the current inputs)
+extern "C" int phbc_root_frequency_gradient(phbc_ctx *ctx, double *out_host) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	if (!ctx->d_lower) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "lower partials are not resident");
+		return -4;
+	}
+	const size_t S = ctx->S, P = ctx->P;
+	const size_t tiles = (P + 255) / 256;
+	int rc;
+	if ((rc = phbc_ensure_scratch(ctx, (S * tiles + S) * sizeof(double)))) return rc;
+	Bufs b = phbc_make_bufs(ctx);
+	k_root_freq_gradient<<<dim3((unsigned)tiles, (unsigned)S), 256, 0, ctx->stream>>>(b, ctx->root, ctx->d_freqs, ctx->d_props, ctx->d_weights, ctx->d_scratch);
+	k_sum_rows<<<(unsigned)S, 256, 0, ctx->stream>>>(ctx->d_scratch, (int)tiles, ctx->d_scratch + S * tiles);
+	ctx->launches += 2;
+	PHBC_CHECK(cudaGetLastError());
+	PHBC_CHECK(cudaMemcpyAsync(out_host, ctx->d_scratch + S * tiles, S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
 // K9 / K10 / A11 over every branch from the resident upper and lower partials: result[1..N], cat_grad (lnL slot untouched)
 extern "C" int phbc_resident_gradient(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));

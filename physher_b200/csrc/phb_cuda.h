@@ -138,6 +138,8 @@ int phbc_download_matrices(phbc_ctx *ctx, double *P, double *dP);
  * host op list grouped by level; lower ops are followed by the root integration when do_root (lnl_host may be NULL). */
 int phbc_run_ops(phbc_ctx *ctx, const phbc_eval_opts *o, int nops, const phbc_op *ops, int nlevels, const int *level_off, int rebuild_matrices,
                  int do_root, double *lnl_host);
+/* d lnL / d pi_i at fixed partials from the resident root partial (root term of calculate_dlnl_dQ, treelikelihood.c:2371-2404) */
+int phbc_root_frequency_gradient(phbc_ctx *ctx, double *out /* [S] */);
 /* K9 / K10 / A11 over every branch from resident upper and lower partials (results in slot 0; lnL slot untouched) */
 int phbc_resident_gradient(phbc_ctx *ctx, const phbc_eval_opts *o);
 /* single-branch fast path (phb_branch.cu): out [nbl][3] = lnL, d lnL/dt, d2 lnL/dt2 at each candidate length of the branch above node */

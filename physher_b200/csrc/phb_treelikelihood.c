@@ -57,6 +57,7 @@ struct phb_tlk {
 	int *post_tip_order, *pre_tip_order, *post_chunk_tip0, *pre_chunk_tip0;
 	int post_first_tips, pre_first_tips;
 	int have_time_tree;
+	int sweep_valid; /* the node-at-a-time buffers hold a full evaluation of the current inputs (phb_tlk_matrix_gradient) */
 
 	/* resident node-at-a-time partials (PHB_OPT_INCREMENTAL): which device buffers hold values of the CURRENT inputs */
 	int incremental, resident, all_dirty;
@@ -629,6 +630,7 @@ void phb_tlk_update_all_nodes(phb_tlk *t) { /* treelikelihood.c:1737-1744 */
 	t->update = 1;
 	t->update_upper = 1;
 	t->all_dirty = 1; /* resident partials (if any) are stale as a whole */
+	t->sweep_valid = 0;
 }
 
 int phb_tlk_update_one_node(phb_tlk *t, int node) { /* treelikelihood.c:1747-1751 */
@@ -636,6 +638,7 @@ int phb_tlk_update_one_node(phb_tlk *t, int node) { /* treelikelihood.c:1747-175
 	t->update_nodes[node] = 1;
 	t->update = 1;
 	t->update_upper = 1;
+	t->sweep_valid = 0;
 	return PHB_OK;
 }
 
@@ -1263,6 +1266,40 @@ int phb_tlk_matrix_gradient(phb_tlk *t, int nsets, const double *M, double *out)
 		for (int k = 0; k < nsets; k++) out[k] = NAN;
 	t->update = isnan(t->lk) ? 1 : 0;
 	t->update_upper = 1; /* the gradient buffer was not refreshed */
+	t->sweep_valid = !(isnan(t->lk) || isinf(t->lk));
+	return PHB_OK;
+}
+
+/* root term of the frequency parameters in calculate_dlnl_dQ (treelikelihood.c:2371-2404): out[i] = d lnL / d pi_i at fixed partials */
+int phb_tlk_root_frequency_gradient(phb_tlk *t, double *out) {
+	if (!out) return fail(PHB_EINVAL, "out is required");
+	int rc = check_ready(t);
+	if (rc) return rc;
+	const int resident_ok = t->incremental && t->resident && !t->all_dirty && !t->update;
+	if (!resident_ok && (t->update || !t->sweep_valid)) { /* a node-at-a-time evaluation leaves the root partial on the device */
+		if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+		t->bl_dirty = 0;
+		t->resident = 0;
+		for (int attempt = 0; attempt < 2; attempt++) {
+			phbc_eval_opts o;
+			fill_opts_resident(t, &o, 0);
+			if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
+			if ((rc = phbc_download_results(t->ctx, 1, &t->lk, NULL))) return dev_fail(rc);
+			if (isinf(t->lk) && !t->scale) {
+				fprintf(stdout, "_calculate: rescaling %f\n", t->lk);
+				t->scale = 1;
+				continue;
+			}
+			break;
+		}
+		t->update = isnan(t->lk) ? 1 : 0;
+		t->sweep_valid = !(isnan(t->lk) || isinf(t->lk));
+		if (!t->sweep_valid) {
+			for (int i = 0; i < t->S; i++) out[i] = NAN;
+			return PHB_OK;
+		}
+	}
+	if ((rc = phbc_root_frequency_gradient(t->ctx, out))) return dev_fail(rc);
 	return PHB_OK;
 }
 

@@ -60,6 +60,7 @@ SYMBOLS = [
     ("phb_tlk_gradient", C.c_int, [C.c_void_p, C.POINTER(_dp)]),
     ("phb_tlk_cat_branch_gradient", C.c_int, [C.c_void_p, _dp]),
     ("phb_tlk_matrix_gradient", C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
+    ("phb_tlk_root_frequency_gradient", C.c_int, [C.c_void_p, _dp]),
     ("phb_tlk_update_uppers", C.c_int, [C.c_void_p]),
     ("phb_tlk_calculate_branch", C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
     ("phb_tlk_get_partials", C.c_int, [C.c_void_p, C.c_int, _dp]),
@@ -293,6 +294,12 @@ class SingleTreeLikelihood:
         assert a.ndim == 5 and a.shape[1:] == (self.N, self.C, self.S, self.S)
         out = np.zeros(a.shape[0])
         self._check(self.lib.phb_tlk_matrix_gradient(self.h, a.shape[0], a.ctypes.data_as(_dp), out.ctypes.data_as(_dp)))
+        return out
+
+    def root_frequency_gradient(self):
+        """d lnL / d pi_i at fixed partials: the root term of the frequency parameters in calculate_dlnl_dQ (treelikelihood.c:2371-2404)."""
+        out = np.zeros(self.S)
+        self._check(self.lib.phb_tlk_root_frequency_gradient(self.h, out.ctypes.data_as(_dp)))
         return out
 
     def update_uppers(self):

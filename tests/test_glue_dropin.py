@@ -187,3 +187,36 @@ def test_single_branch_fast_path_through_the_glue(libs):
     assert rel_err(dev.logP(), lnl_cpu_end) < RTOL  # all kept lengths reached the device object
     G.phb_physher_detach(model)
     dev.close()
+
+
+@pytest.mark.parametrize("name,kw", [("gtr", dict(freqs=[0.1, 0.2, 0.3, 0.4], rates=[0.05, 0.3, 0.1, 0.15, 0.3, 0.1])),
+                                     ("hky", dict(freqs=[0.3, 0.2, 0.2, 0.3], kappa=3.0))])
+def test_substitution_model_gradient_through_the_glue(libs, name, kw):
+    """TREELIKELIHOOD_FLAG_SUBSTITUTION_MODEL[_RATES|_FREQUENCIES] (what torchtree-physher requests, physher.hpp:27-34): the reference's
+    calculate_dlnl_dQ values (rates, then frequencies with their root term) from the device sweep over the reference's own dPdp matrices."""
+    from physher_b200 import synthetic as syn
+
+    L, G = libs
+    T, sites = 10, 300
+    topo = syn.random_topology(T, 71)
+    bl = syn.random_branch_lengths(topo, 72)
+    pat = syn.random_patterns(T, sites, 4, 0.3, 73, unknown_frac=0.02)
+    names = [f"t{i}" for i in range(T)]
+    seqs = dict(zip(names, syn.sequences_from_patterns(pat, syn.NUCLEOTIDES)))
+    spec = O.treelikelihood_spec(syn.to_newick(topo, bl, names), seqs, O.nucleotide_model_spec(name, **kw), categories=4, alpha=0.5, tipstates=True)
+    SUBST, RATES, FREQS = 1 << 2, 1 << 3, 1 << 4
+    cpu = O.Reference(spec)
+    want = {f: cpu.gradient(O.FLAG_TREE_MODEL | f, include_root_freqs=-1) for f in (SUBST, RATES, FREQS)}
+    cpu.close()
+    dev = O.Reference(spec)
+    model = L.refh_model_handle(dev.h)
+    assert G.phb_physher_attach(model, 0) == 0
+    for f in (SUBST, RATES, FREQS):
+        n = L.refh_initialize_gradient(dev.h, O.FLAG_TREE_MODEL | f, -1)
+        assert n == want[f].size
+        L.refh_mark_dirty(dev.h)
+        g = np.ctypeslib.as_array(G.phb_physher_gradient(model), shape=(n,)).copy()
+        assert grad_err(g[:dev.N], want[f][:dev.N]) < RTOL
+        assert grad_err(g[dev.N:], want[f][dev.N:]) < RTOL, (f, g[dev.N:], want[f][dev.N:])
+    G.phb_physher_detach(model)
+    dev.close()

@@ -8,6 +8,7 @@ partials) against them.  GPU: phb_tlk_matrix_gradient against both, plus the ten
 import numpy as np
 import pytest
 
+import physher_b200 as phb
 from oracle import oracle as O
 from tests.util import RTOL, grad_err, load_golden, rel_err
 
@@ -67,4 +68,31 @@ def test_gpu_matrix_gradient_other_state_counts(shape):
     got = tlk.matrix_gradient(M)
     assert grad_err(got, want) < RTOL
     assert grad_err(tlk.gradient(), O.evaluate(pb)["grad"]) < RTOL
+    tlk.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,C,scale", [(4, 4, False), (4, 4, True), (20, 2, False), (61, 1, False)], ids=["nuc4", "nuc4-scaled", "aa20", "codon61"])
+def test_root_frequency_gradient(S, C, scale):
+    """d lnL / d pi_i at fixed partials (root term of calculate_dlnl_dQ, treelikelihood.c:2371-2404) against the oracle's root partials"""
+    from physher_b200 import models, synthetic as syn
+
+    T, P = 8, 211
+    topo = syn.random_topology(T, 5)
+    m = models.gtr([0.05, 0.3, 0.1, 0.15, 0.3, 0.1], [0.1, 0.2, 0.3, 0.4]) if S == 4 else models.random_reversible(S, 9)
+    rates, props = models.discrete_gamma(0.5, C) if C > 1 else (np.ones(1), np.ones(1))
+    pb = O.Problem(left=topo.left, right=topo.right, parent=topo.parent, root=topo.root, nstate=S,
+                   tip_states=syn.random_patterns(T, P, S, 0.25, 6, unknown_frac=0.02), weights=np.random.default_rng(7).integers(1, 4, P).astype(np.float64),
+                   freqs=m.freqs, rates=rates, props=props, bl=syn.random_branch_lengths(topo, 8), evec=m.evec, eval=m.eval, ivec=m.ivec)
+    res = O.evaluate(pb, gradient=False, partials=True)
+    R = np.einsum("c,cpi->pi", props, res["lower"][pb.root])
+    want = (pb.weights[:, None] * R / (R @ pb.freqs)[:, None]).sum(0)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    if scale:
+        tlk.set_option(phb.treelikelihood.OPT_SCALING_THRESHOLD_EXP, 2)
+        tlk.use_rescaling(True)
+    got = tlk.root_frequency_gradient()
+    assert grad_err(got, want) < (1e-9 if scale else RTOL)
+    # sum_i pi_i G_i = sum_k w_k exactly
+    assert abs(got @ pb.freqs - pb.weights.sum()) < 1e-9 * pb.weights.sum()
     tlk.close()
