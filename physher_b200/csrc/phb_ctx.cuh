@@ -30,6 +30,7 @@ struct phbc_ctx {
 	double *d_lower;         // [N-T][C][P][S]
 	double *d_upper;         // [N][C][P][S]   (lazy)
 	double *d_sf;            // [2N][P]        (lazy)
+	bool lower_is_message;   // d_lower holds M_n = P_n L_n instead of L_n (tensor-core message form; the root's entry is L_root either way)
 	double *d_dmma_img;      // packed matrix images of the tensor-core path [P | dP][N][C][IMG]
 	size_t dmma_img_bytes;
 	phbc_op *d_lower_ops, *d_upper_ops;

@@ -640,6 +640,7 @@ int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	}
 	int rc;
 	if ((rc = phbc_generic_prepare(ctx, o))) return rc;
+	ctx->lower_is_message = false;
 	Bufs b = phbc_make_bufs(ctx);
 	const size_t smem = 2 * S * S * sizeof(double);
 	if (smem > 48 * 1024) PHBC_CHECK(cudaFuncSetAttribute(k_generic_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1010,6 +1011,10 @@ extern "C" int phbc_download_partials(phbc_ctx *ctx, int index, double *out) {
 	}
 	if (index < ctx->N) {
 		if (!ctx->d_lower) return -4;
+		if (ctx->lower_is_message && index != ctx->root) {
+			snprintf(phbc_errbuf, sizeof(phbc_errbuf), "the last evaluation kept messages P L, not lower partials, on the device");
+			return -4;
+		}
 		DOWNLOAD(out, ctx->d_lower + (size_t)(index - ctx->T) * psize, psize);
 		return 0;
 	}

@@ -70,13 +70,20 @@ __device__ __forceinline__ bool dm_state_tip(const Bufs &b, int idx) { return id
 // TMA bulk copy instead of an element-wise gather: zero padded [NP][LD] (B-fragment layout) for nodes whose lower partials are
 // an operand, or TRANSPOSED [S][NP] followed by the row sums [NP] for state tips, so that one tip state selects a contiguous
 // column of M (16-byte gathers) and an unknown state selects the row sums (treelikelihoodX.c:878-1001).
-// grid (N, C, 2: P | dP), images laid out [which][node][category][IMG].
+// grid (N, C, 2: P | dP), images laid out [which][node][category][IMG]; one more image behind them: the rate matrix Q (k_dmma_pack_q).
 template <class Sh>
-__global__ void k_dmma_pack(int T, int N, int C, int tip_states, const double *__restrict__ Pm, const double *__restrict__ dPm,
+__global__ void k_dmma_pack(int T, int N, int C, int root, int tip_states, const double *__restrict__ Pm, const double *__restrict__ dPm,
                             double *__restrict__ img) {
 	const int n = blockIdx.x, c = blockIdx.y, which = blockIdx.z;
 	const double *src = (which ? dPm : Pm) + ((size_t)n * C + c) * Sh::S * Sh::S;
 	double *dst = img + (((size_t)which * N + n) * C + c) * Sh::IMG;
+	if (n == root) {  // the root has no branch: its "matrix" is the identity (message form: L_root passes through unchanged)
+		for (int e = threadIdx.x; e < Sh::IMG; e += blockDim.x) {
+			const int i = e / Sh::LD, j = e - i * Sh::LD;
+			dst[e] = (e < Sh::MAT && i < Sh::S && i == j && which == 0) ? 1.0 : 0.0;
+		}
+		return;
+	}
 	if (n < T && tip_states) {
 		for (int e = threadIdx.x; e < Sh::S * Sh::NP; e += blockDim.x) {
 			const int s = e / Sh::NP, i = e - s * Sh::NP;
@@ -94,6 +101,15 @@ __global__ void k_dmma_pack(int T, int N, int C, int tip_states, const double *_
 			const int i = e / Sh::LD, j = e - i * Sh::LD;
 			dst[e] = (e < Sh::MAT && i < Sh::S && j < Sh::S) ? src[i * Sh::S + j] : 0.0;
 		}
+	}
+}
+
+// Q in the B-fragment layout [NP][LD], zero padded: dP/dt L = Q (P L) for every node and category (message form)
+template <class Sh>
+__global__ void k_dmma_pack_q(const double *__restrict__ Q, double *__restrict__ dst) {
+	for (int e = threadIdx.x; e < Sh::IMG; e += blockDim.x) {
+		const int i = e / Sh::LD, j = e - i * Sh::LD;
+		dst[e] = (e < Sh::MAT && i < Sh::S && j < Sh::S) ? Q[i * Sh::S + j] : 0.0;
 	}
 }
 
@@ -594,6 +610,352 @@ dmma_mtiles<MT, NTW, Sh::KCH>(Da, ca, j, tt, bdA);
 }
 
 // ---------------------------------------------------------------------------------------------
+// Message form (unscaled evaluations with state tips -- the fast path).  What a node hands to its parent is stored instead of its
+// lower partial: M_n = P_n L_n with L_n = M_a o M_b.  The product P_n L_n is needed three times -- by the parent's lower partial,
+// by the sibling's upper partial and by n's own branch gradient (dP_n L_n = Q M_n) -- and the node-at-a-time formulation above
+// computes it twice (lower pass and upper pass); here it is computed once, so an evaluation runs 3 instead of 4 dense products
+// per internal node, and the derivative matrices of internal nodes are never staged (one Q image serves every node and category).
+// HBM traffic is unchanged: M_n takes the place of L_n in the lower buffers.
+//
+// k_dmma_lower_msg: A fragments are formed on the fly as products of the children's messages (staged rows for internal children,
+// columns of the transposed matrix image for state tips), B is the node's OWN matrix (the identity at the root, whose L then feeds
+// the root integration unchanged).
+// ---------------------------------------------------------------------------------------------
+template <class Sh>
+__device__ __forceinline__ double tip_value(const double *__restrict__ MT, int s, int col) {
+	return s < Sh::S ? MT[s * Sh::NP + col] : 1.0;  // unknown state: factor 1 (treelikelihood20.c:125-131)
+}
+
+template <int S, int MT, int NSPLIT, int WM>
+__global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ img) {
+	using Sh = DmmaShape<S>;
+	constexpr int NTW = Sh::NT / NSPLIT;
+	static_assert(Sh::NT % NSPLIT == 0, "n-tiles must split evenly");
+	extern __shared__ __align__(128) unsigned char smraw[];
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smraw);
+	double *sm = reinterpret_cast<double *>(smraw + 128);
+	double *mN = sm, *mA = sm + Sh::IMG, *mB = sm + 2 * Sh::IMG;
+	const phbc_op op = ops[blockIdx.z];
+	const int c = blockIdx.y;
+	const bool a_tip_rt = op.a < b.T, b_tip_rt = op.b < b.T;
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		mbar_expect_tx(bar, (1 + (a_tip_rt ? 1 : 0) + (b_tip_rt ? 1 : 0)) * Sh::IMG * 8);
+		bulk_g2s(mN, img + ((size_t)op.out * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		if (a_tip_rt) bulk_g2s(mA, img + ((size_t)op.a_mat * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		if (b_tip_rt) bulk_g2s(mB, img + ((size_t)op.b_mat * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+	}
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int wm = warp / NSPLIT, n0 = (warp % NSPLIT) * NTW;
+	const int r = lane >> 2, q = lane & 3;
+	constexpr int TP = WM * MT * 8;
+	double *out = (double *)dm_partial_ptr(b, op.out, c);
+	const double *xa = a_tip_rt ? nullptr : dm_partial_ptr(b, op.a, c), *xb = b_tip_rt ? nullptr : dm_partial_ptr(b, op.b, c);
+	const int ntiles = (b.P + TP - 1) / TP;
+	using AS = AStage<Sh, MT, 2>;
+	constexpr int GT = 32 * NSPLIT;
+	double *abuf = sm + 3 * Sh::IMG + wm * AS::NSTAGE * AS::STG;
+	const int gl = (warp % NSPLIT) * 32 + lane;
+	mbar_wait(bar, 0);
+	dispatch2(a_tip_rt, b_tip_rt, [&](auto ATIP, auto BTIP) {
+	constexpr bool a_tip = decltype(ATIP)::value, b_tip = decltype(BTIP)::value;
+	AFill<Sh, MT, 2, GT> plan;
+	plan.init(gl);
+	int f_tile = blockIdx.x, f_ch = 0, f_stage = 0;
+	auto fill_next = [&]() {
+		if (f_tile < ntiles) {
+			double *stg = abuf + f_stage * AS::STG;
+			const int fp0 = f_tile * TP + wm * MT * 8;
+			if (!a_tip) plan.fill(stg, xa, fp0, b.P, f_ch);
+			if (!b_tip) plan.fill(stg + AS::OPB, xb, fp0, b.P, f_ch);
+		}
+		cp_async_commit();
+		f_stage = f_stage + 1 == AS::NSTAGE ? 0 : f_stage + 1;
+		if (++f_ch == Sh::NCH) f_ch = 0, f_tile += gridDim.x;
+	};
+	fill_next();
+	fill_next();
+	int c_stage = 0;
+	double bN = mN[(n0 * 8 + r) * Sh::LD + q];
+	const uint8_t *sta = b.tip_states + (size_t)(a_tip ? op.a : 0) * b.P, *stb = b.tip_states + (size_t)(b_tip ? op.b : 0) * b.P;
+	for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		const int p0 = tile * TP + wm * MT * 8;
+		int sa[MT], sb[MT];
+#pragma unroll
+		for (int m = 0; m < MT; m++) {
+			const int p = p0 + 8 * m + r;
+			sa[m] = (a_tip && p < b.P) ? sta[p] : Sh::S;
+			sb[m] = (b_tip && p < b.P) ? stb[p] : Sh::S;
+		}
+		double acc[MT][NTW][2];
+		zero_acc<MT, NTW>(acc);
+#pragma unroll
+		for (int ch = 0; ch < Sh::NCH; ch++) {
+			cp_async_wait<1>();
+			group_sync<NSPLIT>(wm);
+			fill_next();
+			const double *st = abuf + c_stage * AS::STG;
+			c_stage = c_stage + 1 == AS::NSTAGE ? 0 : c_stage + 1;
+			double ca[MT][Sh::KCH], cb[MT][Sh::KCH];
+			if (!a_tip) read_frags<Sh, MT, 2>(st, lane, ca);
+			if (!b_tip) read_frags<Sh, MT, 2>(st + AS::OPB, lane, cb);
+#pragma unroll
+			for (int m = 0; m < MT; m++)
+#pragma unroll
+				for (int tt = 0; tt < Sh::KCH; tt++) {
+					const int col = ch * AS::KC + 4 * tt + q;
+					if (ch * Sh::KCH + tt < Sh::KT) {
+						if (a_tip) ca[m][tt] = tip_value<Sh>(mA, sa[m], col);
+						if (b_tip) cb[m][tt] = tip_value<Sh>(mB, sb[m], col);
+						ca[m][tt] *= cb[m][tt];  // L_n = M_a o M_b, straight into the A fragment
+					} else ca[m][tt] = 0.0;
+				}
+#pragma unroll
+			for (int tt = 0; tt < Sh::KCH; tt++) {
+				const int t = ch * Sh::KCH + tt;
+				if (t < Sh::KT) {
+#pragma unroll
+					for (int j = 0; j < NTW; j++) {
+						const int nj = j + 1 < NTW ? j + 1 : 0, nt = j + 1 < NTW ? t : (t + 1 < Sh::KT ? t + 1 : 0);
+						const double nN = mN[((n0 + nj) * 8 + r) * Sh::LD + 4 * nt + q];
+						dmma_mtiles<MT, NTW, Sh::KCH>(acc, ca, j, tt, bN);
+						bN = nN;
+					}
+				}
+			}
+		}
+		store_tile<Sh, MT, NTW>(out, p0, b.P, n0, lane, acc);
+	}
+	});
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_dmma_upper_msg: per PARENT n with children a, b.  W = P_n U_n (DMMA), the children's messages M_a, M_b come straight from
+// the lower buffers (or the tips' matrix columns), U_a = W o M_b and U_b = W o M_a are stored for internal children, and the branch
+// gradient terms are sum_i f_i U_x[i] (Q M_x)[i] w_k / L_k with Q M_x one more DMMA product per INTERNAL child (a tip's derivative
+// column is gathered from its transposed dP image).  Three products share one k-loop; the D-fragment copies of M_a, M_b are picked
+// out of the staged chunks as they pass, so each message is read from HBM once.
+// Shared-memory image slots: 0 P_n | 1 a: tip image, else Q | 2 a: tip dP image | 3 b: tip image, else Q when a is a tip | 4 b: tip dP image.
+// ---------------------------------------------------------------------------------------------
+template <int S, int MT, int NSPLIT, int WM>
+__global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, const phbc_parent_op *__restrict__ ops, const double *__restrict__ img,
+                                                                   const double *__restrict__ freqs, const double *__restrict__ weights,
+                                                                   const double *__restrict__ pattern_lnl, int include_root_freqs, int pstride,
+                                                                   double *__restrict__ partial) {
+	using Sh = DmmaShape<S>;
+	constexpr int NTW = Sh::NT / NSPLIT;
+	constexpr int NWARPS = WM * NSPLIT;
+	extern __shared__ __align__(128) unsigned char smraw[];
+	uint64_t *bar = reinterpret_cast<uint64_t *>(smraw);
+	double *sm = reinterpret_cast<double *>(smraw + 128);
+	const phbc_parent_op op = ops[blockIdx.z];
+	const int c = blockIdx.y;
+	const bool is_root_rt = op.flags & 1;
+	const bool a_tip_rt = op.a < b.T, b_tip_rt = op.b < b.T;
+	double *mP = sm, *mA = sm + Sh::IMG, *dA = sm + 2 * Sh::IMG, *mB = sm + 3 * Sh::IMG, *dB = sm + 4 * Sh::IMG;
+	const double *mQ = !a_tip_rt ? mA : mB;  // only read when a child is internal
+	double *aux = sm + 5 * Sh::IMG;
+	double *fq = aux, *wroot = aux + Sh::NP, *red = aux + 2 * Sh::NP;
+	const double *rsA = dA + Sh::S * Sh::NP, *rsB = dB + Sh::S * Sh::NP;
+	if (threadIdx.x == 0) {
+		const size_t dimg = (size_t)b.N * b.C * Sh::IMG;
+		const double *qimg = img + 2 * dimg;
+		mbar_init(bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		const int nimg = (is_root_rt ? 0 : 1) + (a_tip_rt ? 2 : 0) + (b_tip_rt ? 2 : 0) + ((!a_tip_rt || !b_tip_rt) ? 1 : 0);
+		mbar_expect_tx(bar, nimg * Sh::IMG * 8);
+		if (!is_root_rt) bulk_g2s(mP, img + ((size_t)op.node * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		if (a_tip_rt) {
+			bulk_g2s(mA, img + ((size_t)op.a * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+			bulk_g2s(dA, img + dimg + ((size_t)op.a * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		}
+		if (b_tip_rt) {
+			bulk_g2s(mB, img + ((size_t)op.b * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+			bulk_g2s(dB, img + dimg + ((size_t)op.b * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		}
+		if (!a_tip_rt) bulk_g2s(mA, qimg, Sh::IMG * 8, bar);
+		else if (!b_tip_rt) bulk_g2s(mB, qimg, Sh::IMG * 8, bar);
+	}
+	for (int i = threadIdx.x; i < Sh::NP; i += blockDim.x) {
+		const double f = i < S ? freqs[i] : 0.0;
+		fq[i] = i < S ? (include_root_freqs ? 1.0 : f) : 0.0;
+		wroot[i] = i < S ? (include_root_freqs ? f : 1.0) : 0.0;
+	}
+	__syncthreads();
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int wm = warp / NSPLIT, n0 = (warp % NSPLIT) * NTW;
+	const int r = lane >> 2, q = lane & 3;
+	constexpr int TP = WM * MT * 8;
+	const double *xw = b.upper + ((size_t)op.node * b.C + c) * (size_t)b.P * S;
+	const double *xa = a_tip_rt ? nullptr : dm_partial_ptr(b, op.a, c), *xb = b_tip_rt ? nullptr : dm_partial_ptr(b, op.b, c);
+	double *Ua = b.upper + ((size_t)op.a * b.C + c) * (size_t)b.P * S;
+	double *Ub = b.upper + ((size_t)op.b * b.C + c) * (size_t)b.P * S;
+	const int ntiles = (b.P + TP - 1) / TP;
+	double tot_a = 0.0, tot_b = 0.0;
+	using AS = AStage<Sh, MT, 3>;
+	constexpr int GT = 32 * NSPLIT;
+	double *abuf = red + 2 * NWARPS + wm * AS::NSTAGE * AS::STG;  // ring operands: U_n | M_b | M_a
+	const int gl = (warp % NSPLIT) * 32 + lane;
+	mbar_wait(bar, 0);
+	dispatch3(is_root_rt, a_tip_rt, b_tip_rt, [&](auto ROOT, auto ATIP, auto BTIP) {
+	constexpr bool is_root = decltype(ROOT)::value, a_tip = decltype(ATIP)::value, b_tip = decltype(BTIP)::value;
+	constexpr bool need_q = !a_tip || !b_tip;
+	AFill<Sh, MT, 3, GT> plan;
+	plan.init(gl);
+	int f_tile = blockIdx.x, f_ch = 0, f_stage = 0;
+	auto fill_next = [&]() {
+		if (f_tile < ntiles) {
+			double *stg = abuf + f_stage * AS::STG;
+			const int fp0 = f_tile * TP + wm * MT * 8;
+			if (!is_root) plan.fill(stg, xw, fp0, b.P, f_ch);
+			if (!b_tip) plan.fill(stg + AS::OPB, xb, fp0, b.P, f_ch);
+			if (!a_tip) plan.fill(stg + 2 * AS::OPB, xa, fp0, b.P, f_ch);
+		}
+		cp_async_commit();
+		f_stage = f_stage + 1 == AS::NSTAGE ? 0 : f_stage + 1;
+		if (++f_ch == Sh::NCH) f_ch = 0, f_tile += gridDim.x;
+	};
+	fill_next();
+	fill_next();
+	int c_stage = 0;
+	double bP = 0.0, bQ = 0.0;
+	{
+		const int off = (n0 * 8 + r) * Sh::LD + q;
+		if (!is_root) bP = mP[off];
+		if (need_q) bQ = mQ[off];
+	}
+	for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		const int p0 = tile * TP + wm * MT * 8;
+		double wk[MT], lk[MT];
+#pragma unroll
+		for (int m = 0; m < MT; m++) {
+			const int p = p0 + 8 * m + r;
+			wk[m] = p < b.P ? __ldg(weights + p) : 0.0;
+			lk[m] = p < b.P ? __ldg(pattern_lnl + p) : 0.0;
+		}
+		double W[MT][NTW][2], Mb[MT][NTW][2], Db[MT][NTW][2], Ma[MT][NTW][2], Da[MT][NTW][2];
+		zero_acc<MT, NTW>(W);
+		zero_acc<MT, NTW>(Mb);
+		zero_acc<MT, NTW>(Ma);
+		zero_acc<MT, NTW>(Db);
+		zero_acc<MT, NTW>(Da);
+		if (!(is_root && a_tip && b_tip))
+#pragma unroll
+		for (int ch = 0; ch < Sh::NCH; ch++) {
+			cp_async_wait<1>();
+			group_sync<NSPLIT>(wm);
+			fill_next();
+			const double *st = abuf + c_stage * AS::STG;
+			c_stage = c_stage + 1 == AS::NSTAGE ? 0 : c_stage + 1;
+			double cw[MT][Sh::KCH], cb[MT][Sh::KCH], ca[MT][Sh::KCH];
+			if (!is_root) read_frags<Sh, MT, 3>(st, lane, cw);
+			if (!b_tip) read_frags<Sh, MT, 3>(st + AS::OPB, lane, cb);
+			if (!a_tip) read_frags<Sh, MT, 3>(st + 2 * AS::OPB, lane, ca);
+			// the messages again in accumulator layout (row 8 m + r, columns (n0 + j) 8 + 2 q, + 1) while their chunk is staged
+#pragma unroll
+			for (int j = 0; j < NTW; j++) {
+				const int col = (n0 + j) * 8 + 2 * q, lc = col - ch * AS::KC;
+				if (lc >= 0 && lc < AS::KC && col < S) {
+#pragma unroll
+					for (int m = 0; m < MT; m++) {
+						if (!b_tip) {
+							const double2 v = *reinterpret_cast<const double2 *>(st + AS::OPB + (8 * m + r) * AS::RS + lc);
+							Mb[m][j][0] = v.x, Mb[m][j][1] = v.y;
+						}
+						if (!a_tip) {
+							const double2 v = *reinterpret_cast<const double2 *>(st + 2 * AS::OPB + (8 * m + r) * AS::RS + lc);
+							Ma[m][j][0] = v.x, Ma[m][j][1] = v.y;
+						}
+					}
+				}
+			}
+#pragma unroll
+			for (int tt = 0; tt < Sh::KCH; tt++) {
+				const int t = ch * Sh::KCH + tt;
+				if (t < Sh::KT) {
+#pragma unroll
+					for (int j = 0; j < NTW; j++) {
+						const int nj = j + 1 < NTW ? j + 1 : 0, nt = j + 1 < NTW ? t : (t + 1 < Sh::KT ? t + 1 : 0);
+						const int noff = ((n0 + nj) * 8 + r) * Sh::LD + 4 * nt + q;
+						double nP = 0.0, nQ = 0.0;
+						if (!is_root) nP = mP[noff];
+						if (need_q) nQ = mQ[noff];
+						if (!is_root) {
+dmma_mtiles<MT, NTW, Sh::KCH>(W, cw, j, tt, bP);
+						}
+						if (!b_tip) {
+dmma_mtiles<MT, NTW, Sh::KCH>(Db, cb, j, tt, bQ);
+						}
+						if (!a_tip) {
+dmma_mtiles<MT, NTW, Sh::KCH>(Da, ca, j, tt, bQ);
+						}
+						bP = nP, bQ = nQ;
+					}
+				}
+			}
+		}
+		if (is_root) {
+#pragma unroll
+			for (int m = 0; m < MT; m++)
+#pragma unroll
+				for (int j = 0; j < NTW; j++) {
+					const int i = (n0 + j) * 8 + 2 * q;
+					W[m][j][0] = wroot[i], W[m][j][1] = wroot[i + 1];
+				}
+		}
+		if (b_tip) {
+			const uint8_t *st = b.tip_states + (size_t)op.b * b.P;
+			tip_gather<Sh, MT, NTW, true>(st, mB, nullptr, p0, b.P, n0, lane, Mb);
+			tip_gather<Sh, MT, NTW, false>(st, dB, rsB, p0, b.P, n0, lane, Db);
+		}
+		if (a_tip) {
+			const uint8_t *st = b.tip_states + (size_t)op.a * b.P;
+			tip_gather<Sh, MT, NTW, true>(st, mA, nullptr, p0, b.P, n0, lane, Ma);
+			tip_gather<Sh, MT, NTW, false>(st, dA, rsA, p0, b.P, n0, lane, Da);
+		}
+#pragma unroll
+		for (int m = 0; m < MT; m++)
+#pragma unroll
+			for (int j = 0; j < NTW; j++) {
+				const double ua0 = W[m][j][0] * Mb[m][j][0], ua1 = W[m][j][1] * Mb[m][j][1];
+				const double ub0 = W[m][j][0] * Ma[m][j][0], ub1 = W[m][j][1] * Ma[m][j][1];
+				Mb[m][j][0] = ua0, Mb[m][j][1] = ua1;
+				Ma[m][j][0] = ub0, Ma[m][j][1] = ub1;
+			}
+		if (!a_tip) store_tile<Sh, MT, NTW>(Ua, p0, b.P, n0, lane, Mb);
+		if (!b_tip) store_tile<Sh, MT, NTW>(Ub, p0, b.P, n0, lane, Ma);
+#pragma unroll
+		for (int m = 0; m < MT; m++) {
+			double ga = 0.0, gb = 0.0;
+#pragma unroll
+			for (int j = 0; j < NTW; j++) {
+				const int i = (n0 + j) * 8 + 2 * q;
+				ga = fma(fq[i] * Mb[m][j][0], Da[m][j][0], fma(fq[i + 1] * Mb[m][j][1], Da[m][j][1], ga));
+				gb = fma(fq[i] * Ma[m][j][0], Db[m][j][0], fma(fq[i + 1] * Ma[m][j][1], Db[m][j][1], gb));
+			}
+			ga += __shfl_xor_sync(0xffffffffu, ga, 1), gb += __shfl_xor_sync(0xffffffffu, gb, 1);
+			ga += __shfl_xor_sync(0xffffffffu, ga, 2), gb += __shfl_xor_sync(0xffffffffu, gb, 2);
+			const double wl = wk[m] / exp(lk[m]);
+			tot_a = fma(ga, wl, tot_a);
+			tot_b = fma(gb, wl, tot_b);
+		}
+	}
+	});
+	tot_a = q == 0 ? tot_a : 0.0, tot_b = q == 0 ? tot_b : 0.0;
+	tot_a = phb_warp_sum(tot_a), tot_b = phb_warp_sum(tot_b);
+	if (lane == 0) red[2 * warp] = tot_a, red[2 * warp + 1] = tot_b;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double sa = 0.0, sb = 0.0;
+		for (int w = 0; w < NWARPS; w++) sa += red[2 * w], sb += red[2 * w + 1];
+		partial[((size_t)op.a * b.C + c) * pstride + blockIdx.x] = sa;
+		partial[((size_t)op.b * b.C + c) * pstride + blockIdx.x] = sb;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 template <int S>
@@ -637,7 +999,7 @@ template <int S>
 static int dmma_pack(phbc_ctx *ctx) {
 	using Sh = DmmaShape<S>;
 	const int C = ctx->C, N = ctx->N;
-	const size_t img_bytes = (size_t)2 * N * C * Sh::IMG * sizeof(double);
+	const size_t img_bytes = ((size_t)2 * N * C + 1) * Sh::IMG * sizeof(double);
 	if (img_bytes > ctx->dmma_img_bytes) {
 		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 		if (ctx->d_dmma_img) cudaFree(ctx->d_dmma_img);
@@ -646,8 +1008,12 @@ static int dmma_pack(phbc_ctx *ctx) {
 		PHBC_CHECK(cudaMalloc((void **)&ctx->d_dmma_img, img_bytes));
 		ctx->dmma_img_bytes = img_bytes;
 	}
-	k_dmma_pack<Sh><<<dim3(N, C, 2), 128, 0, ctx->stream>>>(ctx->T, N, C, ctx->tip_kind == PHBC_TIP_STATES, ctx->d_P, ctx->d_dP, ctx->d_dmma_img);
+	k_dmma_pack<Sh><<<dim3(N, C, 2), 128, 0, ctx->stream>>>(ctx->T, N, C, ctx->root, ctx->tip_kind == PHBC_TIP_STATES, ctx->d_P, ctx->d_dP, ctx->d_dmma_img);
 	ctx->launches++;
+	if (ctx->have_eigen) {
+		k_dmma_pack_q<Sh><<<1, 128, 0, ctx->stream>>>(ctx->d_qmat, ctx->d_dmma_img + (size_t)2 * N * C * Sh::IMG);
+		ctx->launches++;
+	}
 	PHBC_CHECK(cudaGetLastError());
 	return 0;
 }
@@ -661,6 +1027,29 @@ static int dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
 	Bufs b = phbc_make_bufs(ctx);
 	auto lower = k_dmma_lower<S, Cf::MT, Cf::NSPLIT, Cf::WM>;
 	const size_t lsmem = 128 + (2 * Sh::IMG + Cf::WM * AStage<Sh, Cf::MT, 2>::NSTAGE * AStage<Sh, Cf::MT, 2>::STG) * sizeof(double);
+	PHBC_CHECK(cudaFuncSetAttribute(lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+	const int lthreads = 32 * Cf::WM * Cf::NSPLIT, ltiles = (P + Cf::WM * Cf::MT * 8 - 1) / (Cf::WM * Cf::MT * 8);
+	int lper_sm = 1;
+	PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lper_sm, lower, lthreads, lsmem));
+	if (lper_sm < 1) lper_sm = 1;
+	for (int z0 = 0; z0 < cnt; z0 += 65535) {
+		const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
+		lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ltiles), C, zc), lthreads, lsmem, ctx->stream>>>(b, d_ops + z0, ctx->d_dmma_img);
+		ctx->launches++;
+	}
+	PHBC_CHECK(cudaGetLastError());
+	return 0;
+}
+
+// one level of message-form lower ops
+template <int S>
+static int dmma_lower_msg_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
+	using Sh = DmmaShape<S>;
+	using Cf = DmmaConfig<S>;
+	const int C = ctx->C, P = ctx->P;
+	Bufs b = phbc_make_bufs(ctx);
+	auto lower = k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM>;
+	const size_t lsmem = 128 + (3 * Sh::IMG + Cf::WM * AStage<Sh, Cf::MT, 2>::NSTAGE * AStage<Sh, Cf::MT, 2>::STG) * sizeof(double);
 	PHBC_CHECK(cudaFuncSetAttribute(lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
 	const int lthreads = 32 * Cf::WM * Cf::NSPLIT, ltiles = (P + Cf::WM * Cf::MT * 8 - 1) / (Cf::WM * Cf::MT * 8);
 	int lper_sm = 1;
@@ -695,18 +1084,23 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	if ((rc = phbc_generic_prepare(ctx, o))) return rc;
 	Bufs b = phbc_make_bufs(ctx);
 	if ((rc = dmma_pack<S>(ctx))) return rc;
+	// message form: the fast path (unscaled, state tips, eigen system, upper partials not needed as such afterwards)
+	const bool msg = !o->scale && !o->materialize_uppers && ctx->tip_kind == PHBC_TIP_STATES && ctx->have_eigen && !o->explicit_matrices &&
+	                 getenv("PHB_DMMA_LEGACY") == NULL;
+	ctx->lower_is_message = msg;
 	if ((rc = phbc_time_begin(ctx))) return rc;
 	for (int l = 0; l < ctx->n_lower_levels; l++) {
 		const int beg = ctx->h_lower_level_off[l], cnt = ctx->h_lower_level_off[l + 1] - beg;
 		if (cnt <= 0) continue;
-		if ((rc = dmma_lower_ops<S>(ctx, ctx->d_lower_ops + beg, cnt))) return rc;
+		if ((rc = msg ? dmma_lower_msg_ops<S>(ctx, ctx->d_lower_ops + beg, cnt) : dmma_lower_ops<S>(ctx, ctx->d_lower_ops + beg, cnt))) return rc;
 		if (o->scale && (rc = phbc_generic_scale_ops(ctx, ctx->d_lower_ops + beg, cnt, o->scaling_threshold))) return rc;
 	}
 	double *result = ctx->d_result + (size_t)o->batch_index * (1 + N);
 	if ((rc = phbc_generic_root(ctx, o, result))) return rc;
 	if (o->want_gradient) {
 		const bool grad = !o->scale && !o->materialize_uppers;  // fused reductions use the unscaled form and skip the tips' uppers
-		auto upper = grad ? k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, true> : k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, false>;
+		auto upper = msg ? k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM>
+		                 : (grad ? k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, true> : k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, false>);
 		const int uwarps = Cf::UWM * Cf::UNSPLIT;
 		const size_t usmem = 128 + ((grad ? 5 : 3) * Sh::IMG + 2 * Sh::NP + 2 * uwarps + Cf::UWM * AStage<Sh, Cf::UMT, 3>::NSTAGE * AStage<Sh, Cf::UMT, 3>::STG) * sizeof(double);
 		PHBC_CHECK(cudaFuncSetAttribute(upper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));

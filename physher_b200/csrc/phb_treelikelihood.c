@@ -1164,7 +1164,21 @@ int phb_tlk_cat_branch_gradient(phb_tlk *t, double *out) {
 }
 
 int phb_tlk_get_partials(phb_tlk *t, int index, double *out) {
-	int rc = phbc_download_partials(t->ctx, index, out);
+	int rc;
+	if (index >= t->T && !(t->incremental && t->resident && !t->all_dirty && !t->update)) {
+		/* tlk->partials as the reference holds them: a node-at-a-time evaluation with every upper partial materialised (the fused paths
+		 * keep no partials, or keep messages P L in their place) */
+		if ((rc = check_ready(t))) return rc;
+		if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+		phbc_eval_opts o;
+		fill_opts_resident(t, &o, 1);
+		t->resident = 0;
+		t->sweep_valid = 0;
+		if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
+	} else if (index >= t->N && t->incremental) {
+		if ((rc = resident_uppers(t, index - t->N, t->upper_irf))) return rc;
+	}
+	rc = phbc_download_partials(t->ctx, index, out);
 	if (rc) return dev_fail(rc);
 	return PHB_OK;
 }
