@@ -41,6 +41,7 @@ struct phbc_ctx {
 	phbc_parent_op *d_parent_ops;
 	int n_lower_ops, n_upper_ops, n_parent_ops;
 	int *h_lower_level_off, *h_upper_level_off, *h_parent_level_off;
+	int *h_lower_kind_off, *h_parent_kind_off;  // [levels][4]: within a level the device op lists are sorted by the number of tip children (0, 1, 2)
 	int n_lower_levels, n_upper_levels;
 
 	// fused walk state (phb_nuc4.cu)

@@ -118,6 +118,8 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	free(ctx->h_lower_level_off);
 	free(ctx->h_upper_level_off);
 	free(ctx->h_parent_level_off);
+	free(ctx->h_lower_kind_off);
+	free(ctx->h_parent_kind_off);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	free(ctx);
 }
@@ -147,11 +149,43 @@ static int upload_array(phbc_ctx *ctx, T **dst, const T *src, size_t count) {
 	return 0;
 }
 
+// stable sort of each level's ops by the number of tip children; kind_off [levels][4] = absolute offsets of the kind groups
+template <typename OP, typename F>
+static OP *sort_levels_by_kind(const OP *ops, int nops, int nlevels, const int *level_off, int *kind_off, F tips_of) {
+	OP *out = (OP *)malloc(sizeof(OP) * (nops > 0 ? nops : 1));
+	if (!out) return NULL;
+	for (int l = 0; l < nlevels; l++) {
+		int w = level_off[l];
+		for (int kind = 0; kind < 3; kind++) {
+			kind_off[4 * l + kind] = w;
+			for (int k = level_off[l]; k < level_off[l + 1]; k++)
+				if (tips_of(ops[k]) == kind) out[w++] = ops[k];
+		}
+		kind_off[4 * l + 3] = w;
+	}
+	return out;
+}
+
 extern "C" int phbc_set_schedule(phbc_ctx *ctx, const phbc_schedule *s) {
 	int rc;
-	if ((rc = upload_array(ctx, &ctx->d_lower_ops, s->lower_ops, (size_t)s->n_lower_ops))) return rc;
+	const int T = ctx->T;
+	free(ctx->h_lower_kind_off);
+	free(ctx->h_parent_kind_off);
+	ctx->h_lower_kind_off = (int *)malloc(sizeof(int) * 4 * (s->n_lower_levels + 1));
+	ctx->h_parent_kind_off = (int *)malloc(sizeof(int) * 4 * (s->n_upper_levels + 1));
+	phbc_op *lsorted = sort_levels_by_kind(s->lower_ops, s->n_lower_ops, s->n_lower_levels, s->lower_level_off, ctx->h_lower_kind_off,
+	                                       [T](const phbc_op &o) { return (o.a < T ? 1 : 0) + (o.b >= 0 && o.b < T ? 1 : 0); });
+	phbc_parent_op *psorted = sort_levels_by_kind(s->parent_ops, s->n_parent_ops, s->n_upper_levels, s->parent_level_off, ctx->h_parent_kind_off,
+	                                              [T](const phbc_parent_op &o) { return (o.a < T ? 1 : 0) + (o.b < T ? 1 : 0); });
+	if (!lsorted || !psorted || !ctx->h_lower_kind_off || !ctx->h_parent_kind_off) {
+		free(lsorted), free(psorted);
+		return -3;
+	}
+	rc = upload_array(ctx, &ctx->d_lower_ops, lsorted, (size_t)s->n_lower_ops);
+	if (!rc) rc = upload_array(ctx, &ctx->d_parent_ops, psorted, (size_t)s->n_parent_ops);
+	free(lsorted), free(psorted);
+	if (rc) return rc;
 	if ((rc = upload_array(ctx, &ctx->d_upper_ops, s->upper_ops, (size_t)s->n_upper_ops))) return rc;
-	if ((rc = upload_array(ctx, &ctx->d_parent_ops, s->parent_ops, (size_t)s->n_parent_ops))) return rc;
 	ctx->n_parent_ops = s->n_parent_ops;
 	if ((rc = upload_array(ctx, &ctx->d_post_ops, s->post_ops, (size_t)s->n_post))) return rc;
 	if ((rc = upload_array(ctx, &ctx->d_pre_ops, s->pre_ops, (size_t)s->n_pre))) return rc;

@@ -627,17 +627,18 @@ __device__ __forceinline__ double tip_value(const double *__restrict__ MT, int s
 }
 
 template <int S, int MT, int NSPLIT, int WM>
-__global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ img) {
+__global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ img, int nimg) {
 	using Sh = DmmaShape<S>;
 	constexpr int NTW = Sh::NT / NSPLIT;
 	static_assert(Sh::NT % NSPLIT == 0, "n-tiles must split evenly");
 	extern __shared__ __align__(128) unsigned char smraw[];
 	uint64_t *bar = reinterpret_cast<uint64_t *>(smraw);
 	double *sm = reinterpret_cast<double *>(smraw + 128);
-	double *mN = sm, *mA = sm + Sh::IMG, *mB = sm + 2 * Sh::IMG;
 	const phbc_op op = ops[blockIdx.z];
 	const int c = blockIdx.y;
 	const bool a_tip_rt = op.a < b.T, b_tip_rt = op.b < b.T;
+	// image slots: own matrix, then one transposed image per tip child; the launch provides nimg >= 1 + tip children slots
+	double *mN = sm, *mA = sm + Sh::IMG, *mB = sm + (a_tip_rt ? 2 : 1) * Sh::IMG;
 	if (threadIdx.x == 0) {
 		mbar_init(bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -656,7 +657,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 	const int ntiles = (b.P + TP - 1) / TP;
 	using AS = AStage<Sh, MT, 2>;
 	constexpr int GT = 32 * NSPLIT;
-	double *abuf = sm + 3 * Sh::IMG + wm * AS::NSTAGE * AS::STG;
+	double *abuf = sm + nimg * Sh::IMG + wm * AS::NSTAGE * AS::STG;
 	const int gl = (warp % NSPLIT) * 32 + lane;
 	mbar_wait(bar, 0);
 	dispatch2(a_tip_rt, b_tip_rt, [&](auto ATIP, auto BTIP) {
@@ -743,7 +744,7 @@ template <int S, int MT, int NSPLIT, int WM>
 __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, const phbc_parent_op *__restrict__ ops, const double *__restrict__ img,
                                                                    const double *__restrict__ freqs, const double *__restrict__ weights,
                                                                    const double *__restrict__ pattern_lnl, int include_root_freqs, int pstride,
-                                                                   double *__restrict__ partial) {
+                                                                   double *__restrict__ partial, int nslots) {
 	using Sh = DmmaShape<S>;
 	constexpr int NTW = Sh::NT / NSPLIT;
 	constexpr int NWARPS = WM * NSPLIT;
@@ -756,7 +757,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 	const bool a_tip_rt = op.a < b.T, b_tip_rt = op.b < b.T;
 	double *mP = sm, *mA = sm + Sh::IMG, *dA = sm + 2 * Sh::IMG, *mB = sm + 3 * Sh::IMG, *dB = sm + 4 * Sh::IMG;
 	const double *mQ = !a_tip_rt ? mA : mB;  // only read when a child is internal
-	double *aux = sm + 5 * Sh::IMG;
+	double *aux = sm + nslots * Sh::IMG;  // 2 slots when both children are internal (P_n, Q), else 5
 	double *fq = aux, *wroot = aux + Sh::NP, *red = aux + 2 * Sh::NP;
 	const double *rsA = dA + Sh::S * Sh::NP, *rsB = dB + Sh::S * Sh::NP;
 	if (threadIdx.x == 0) {
@@ -964,11 +965,13 @@ template <>
 struct DmmaConfig<20> {  // 128 threads; 64 patterns per tile in the lower pass, 32 in the upper pass
 	static constexpr int MT = 2, NSPLIT = 1, WM = 4;
 	static constexpr int UMT = 1, UNSPLIT = 1, UWM = 4;
+	static constexpr int UWM_II = 4;  // message-form upper kernel, parents without tip children
 };
 template <>
 struct DmmaConfig<61> {  // 256 threads, 32 patterns per tile, n-tiles split over two warps
 	static constexpr int MT = 1, NSPLIT = 2, WM = 4;
 	static constexpr int UMT = 1, UNSPLIT = 2, UWM = 4;
+	static constexpr int UWM_II = 8;  // two image slots instead of five leave room for a 16-warp CTA sharing them
 };
 
 bool phbc_dmma_supported(const phbc_ctx *ctx, const phbc_eval_opts *o) {
@@ -1041,24 +1044,37 @@ static int dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
 	return 0;
 }
 
-// one level of message-form lower ops
+// one level of message-form lower ops: three launches by the number of tip children (the device op list is sorted that way), so
+// that ops without tip children do not pay shared memory for tip images (61 states: 3 CTAs per SM instead of 1)
 template <int S>
-static int dmma_lower_msg_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
+static int dmma_lower_msg_level(phbc_ctx *ctx, int level) {
 	using Sh = DmmaShape<S>;
 	using Cf = DmmaConfig<S>;
 	const int C = ctx->C, P = ctx->P;
 	Bufs b = phbc_make_bufs(ctx);
 	auto lower = k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM>;
-	const size_t lsmem = 128 + (3 * Sh::IMG + Cf::WM * AStage<Sh, Cf::MT, 2>::NSTAGE * AStage<Sh, Cf::MT, 2>::STG) * sizeof(double);
-	PHBC_CHECK(cudaFuncSetAttribute(lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsmem));
+	const size_t ring = (size_t)Cf::WM * AStage<Sh, Cf::MT, 2>::NSTAGE * AStage<Sh, Cf::MT, 2>::STG;
 	const int lthreads = 32 * Cf::WM * Cf::NSPLIT, ltiles = (P + Cf::WM * Cf::MT * 8 - 1) / (Cf::WM * Cf::MT * 8);
-	int lper_sm = 1;
-	PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lper_sm, lower, lthreads, lsmem));
-	if (lper_sm < 1) lper_sm = 1;
-	for (int z0 = 0; z0 < cnt; z0 += 65535) {
-		const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
-		lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ltiles), C, zc), lthreads, lsmem, ctx->stream>>>(b, d_ops + z0, ctx->d_dmma_img);
-		ctx->launches++;
+	PHBC_CHECK(cudaFuncSetAttribute(lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 + (3 * Sh::IMG + ring) * sizeof(double))));
+	const bool split = getenv("PHB_DMMA_NOSPLIT") == NULL;
+	for (int kind = 0; kind < 3; kind++) {
+		int beg = ctx->h_lower_kind_off[4 * level + kind], end = ctx->h_lower_kind_off[4 * level + kind + 1];
+		int nimg = 1 + kind;
+		if (!split) {
+			if (kind) break;
+			end = ctx->h_lower_kind_off[4 * level + 3];
+			nimg = 3;
+		}
+		if (end <= beg) continue;
+		const size_t lsmem = 128 + (nimg * Sh::IMG + ring) * sizeof(double);
+		int lper_sm = 1;
+		PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lper_sm, lower, lthreads, lsmem));
+		if (lper_sm < 1) lper_sm = 1;
+		for (int z0 = beg; z0 < end; z0 += 65535) {
+			const int zc = end - z0 < 65535 ? end - z0 : 65535;
+			lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ltiles), C, zc), lthreads, lsmem, ctx->stream>>>(b, ctx->d_lower_ops + z0, ctx->d_dmma_img, nimg);
+			ctx->launches++;
+		}
 	}
 	PHBC_CHECK(cudaGetLastError());
 	return 0;
@@ -1073,6 +1089,80 @@ int phbc_dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
 	if (ctx->S == 20) return dmma_lower_ops<20>(ctx, d_ops, cnt);
 	if (ctx->S == 61) return dmma_lower_ops<61>(ctx, d_ops, cnt);
 	return -1;
+}
+
+// message-form pre-order pass: per depth, one launch per kind of parent (0, 1, 2 tip children; the device op list is sorted that
+// way).  Parents without tip children need two image slots (P_n, Q) and run as wider CTAs where that pays (DmmaConfig::UWM_II).
+template <int S>
+static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
+	using Sh = DmmaShape<S>;
+	using Cf = DmmaConfig<S>;
+	const int C = ctx->C, P = ctx->P, N = ctx->N;
+	int rc;
+	Bufs b = phbc_make_bufs(ctx);
+	const bool split = getenv("PHB_DMMA_NOSPLIT") == NULL;
+	typedef void (*upper_fn)(Bufs, const phbc_parent_op *, const double *, const double *, const double *, const double *, int, int, double *, int);
+	struct Variant {
+		upper_fn fn;
+		int wm, nslots, threads, tiles, slots;
+		size_t smem;
+	} var[3];
+	for (int kind = 0; kind < 3; kind++) {
+		Variant &v = var[kind];
+		const bool wide = split && kind == 0 && Cf::UWM_II != Cf::UWM;
+		v.fn = wide ? (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM_II> : (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM>;
+		v.wm = wide ? Cf::UWM_II : Cf::UWM;
+		v.nslots = (split && kind == 0) ? 2 : 5;
+		const int warps = v.wm * Cf::UNSPLIT;
+		v.threads = 32 * warps;
+		v.tiles = (P + v.wm * Cf::UMT * 8 - 1) / (v.wm * Cf::UMT * 8);
+		v.smem = 128 + ((size_t)v.nslots * Sh::IMG + 2 * Sh::NP + 2 * warps + (size_t)v.wm * AStage<Sh, Cf::UMT, 3>::NSTAGE * AStage<Sh, Cf::UMT, 3>::STG) * sizeof(double);
+	}
+	for (int kind = 0; kind < 3; kind++) {
+		Variant &v = var[kind];
+		size_t mx = 0;
+		for (int k2 = 0; k2 < 3; k2++)
+			if (var[k2].fn == v.fn && var[k2].smem > mx) mx = var[k2].smem;
+		PHBC_CHECK(cudaFuncSetAttribute(v.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mx));
+		int per_sm = 1;
+		PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, v.fn, v.threads, v.smem));
+		v.slots = (per_sm < 1 ? 1 : per_sm) * ctx->num_sms;
+	}
+	// group [beg, end) of (level, kind); without the split one group per level takes every op with the five-slot variant
+	auto group = [&](int l, int kind, int &beg, int &end) {
+		beg = ctx->h_parent_kind_off[4 * l + kind], end = ctx->h_parent_kind_off[4 * l + kind + 1];
+		if (!split) {
+			if (kind) end = beg;
+			else end = ctx->h_parent_kind_off[4 * l + 3];
+		}
+	};
+	int pstride = 1;
+	for (int l = 0; l < ctx->n_upper_levels; l++)
+		for (int kind = 0; kind < 3; kind++) {
+			int beg, end;
+			group(l, kind, beg, end);
+			for (int z0 = beg; z0 < end; z0 += 65535) {
+				const int k = pick_chunks(var[kind].slots, C * (end - z0 < 65535 ? end - z0 : 65535), var[kind].tiles);
+				if (k > pstride) pstride = k;
+			}
+		}
+	if ((rc = phbc_ensure_scratch(ctx, (size_t)N * C * pstride * sizeof(double)))) return rc;
+	PHBC_CHECK(cudaMemsetAsync(ctx->d_scratch, 0, (size_t)N * C * pstride * sizeof(double), ctx->stream));
+	for (int l = 0; l < ctx->n_upper_levels; l++)
+		for (int kind = 0; kind < 3; kind++) {
+			int beg, end;
+			group(l, kind, beg, end);
+			const Variant &v = var[kind];
+			for (int z0 = beg; z0 < end; z0 += 65535) {
+				const int zc = end - z0 < 65535 ? end - z0 : 65535;
+				v.fn<<<dim3(pick_chunks(v.slots, C * zc, v.tiles), C, zc), v.threads, v.smem, ctx->stream>>>(
+				    b, ctx->d_parent_ops + z0, ctx->d_dmma_img, ctx->d_freqs, ctx->d_weights, ctx->d_pattern_lnl, o->include_root_freqs, pstride, ctx->d_scratch,
+				    v.nslots);
+				ctx->launches++;
+			}
+		}
+	PHBC_CHECK(cudaGetLastError());
+	return phbc_gradient_from_partials(ctx, pstride, result);
 }
 
 template <int S>
@@ -1092,15 +1182,20 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	for (int l = 0; l < ctx->n_lower_levels; l++) {
 		const int beg = ctx->h_lower_level_off[l], cnt = ctx->h_lower_level_off[l + 1] - beg;
 		if (cnt <= 0) continue;
-		if ((rc = msg ? dmma_lower_msg_ops<S>(ctx, ctx->d_lower_ops + beg, cnt) : dmma_lower_ops<S>(ctx, ctx->d_lower_ops + beg, cnt))) return rc;
+		if ((rc = msg ? dmma_lower_msg_level<S>(ctx, l) : dmma_lower_ops<S>(ctx, ctx->d_lower_ops + beg, cnt))) return rc;
 		if (o->scale && (rc = phbc_generic_scale_ops(ctx, ctx->d_lower_ops + beg, cnt, o->scaling_threshold))) return rc;
 	}
 	double *result = ctx->d_result + (size_t)o->batch_index * (1 + N);
 	if ((rc = phbc_generic_root(ctx, o, result))) return rc;
 	if (o->want_gradient) {
 		const bool grad = !o->scale && !o->materialize_uppers;  // fused reductions use the unscaled form and skip the tips' uppers
-		auto upper = msg ? k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM>
-		                 : (grad ? k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, true> : k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, false>);
+		if (msg) {
+			if ((rc = dmma_upper_msg<S>(ctx, o, result))) return rc;
+			if ((rc = phbc_time_end(ctx))) return rc;
+			PHBC_CHECK(cudaGetLastError());
+			return 0;
+		}
+		auto upper = grad ? k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, true> : k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, false>;
 		const int uwarps = Cf::UWM * Cf::UNSPLIT;
 		const size_t usmem = 128 + ((grad ? 5 : 3) * Sh::IMG + 2 * Sh::NP + 2 * uwarps + Cf::UWM * AStage<Sh, Cf::UMT, 3>::NSTAGE * AStage<Sh, Cf::UMT, 3>::STG) * sizeof(double);
 		PHBC_CHECK(cudaFuncSetAttribute(upper, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)usmem));
