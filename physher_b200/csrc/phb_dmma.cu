@@ -124,7 +124,9 @@ struct AStage {
 	static constexpr int RS = KC + ((4 - KC % 8) + 8) % 8;
 	static constexpr int OPB = MT * 8 * RS;
 	static constexpr int STG = NOPS * OPB;
-	static constexpr int NSTAGE = 3;
+	// ring depth: the fills run NSTAGE - 1 chunks ahead of the tensor pipe.  A contraction that is ONE chunk (20 states) stages whole tiles:
+	// one tile ahead is enough there and the smaller ring buys a fourth resident CTA per SM (round 1, h4 profile: 12 -> 16 warps per SM)
+	static constexpr int NSTAGE = Sh::NCH == 1 ? 2 : 3;
 };
 
 __device__ __forceinline__ void cp_async8(double *dst, const double *src) {
@@ -316,8 +318,8 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const p
 		f_stage = f_stage + 1 == AS::NSTAGE ? 0 : f_stage + 1;
 		if (++f_ch == Sh::NCH) f_ch = 0, f_tile += gridDim.x;
 	};
-	fill_next();
-	fill_next();
+#pragma unroll
+	for (int pf = 0; pf < AS::NSTAGE - 1; pf++) fill_next();
 	int c_stage = 0;
 	// B fragments run one (k-step, n-tile) ahead of the tensor pipe: the LDS of step u + 1 is issued before the DMMAs of step u
 	double bA = 0.0, bB = 0.0;
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const p
 		if (!(a_tip && b_tip))  // a cherry is two gathers: no contraction, no staged operand
 #pragma unroll
 		for (int ch = 0; ch < Sh::NCH; ch++) {
-			cp_async_wait<1>();      // this chunk has landed (the newest group may still be in flight)
+			cp_async_wait<AS::NSTAGE - 2>();      // this chunk has landed (the newest group may still be in flight)
 			group_sync<NSPLIT>(wm);  // ... for every thread of the group, and the buffer refilled below is no longer read
 			fill_next();
 			const double *st = abuf + c_stage * AS::STG;
@@ -456,8 +458,8 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 		f_stage = f_stage + 1 == AS::NSTAGE ? 0 : f_stage + 1;
 		if (++f_ch == Sh::NCH) f_ch = 0, f_tile += gridDim.x;
 	};
-	fill_next();
-	fill_next();
+#pragma unroll
+	for (int pf = 0; pf < AS::NSTAGE - 1; pf++) fill_next();
 	int c_stage = 0;
 	// B fragments run one (k-step, n-tile) ahead of the tensor pipe: the LDS of step u + 1 is issued before the DMMAs of step u
 	double bP = 0.0, bA = 0.0, bB = 0.0, bdA = 0.0, bdB = 0.0;
@@ -495,7 +497,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 		}
 #pragma unroll
 		for (int ch = 0; ch < Sh::NCH; ch++) {
-			cp_async_wait<1>();      // this chunk has landed (the newest group may still be in flight)
+			cp_async_wait<AS::NSTAGE - 2>();      // this chunk has landed (the newest group may still be in flight)
 			group_sync<NSPLIT>(wm);  // ... for every thread of the group, and the buffer refilled below is no longer read
 			fill_next();
 			const double *st = abuf + c_stage * AS::STG;
@@ -676,8 +678,8 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 		f_stage = f_stage + 1 == AS::NSTAGE ? 0 : f_stage + 1;
 		if (++f_ch == Sh::NCH) f_ch = 0, f_tile += gridDim.x;
 	};
-	fill_next();
-	fill_next();
+#pragma unroll
+	for (int pf = 0; pf < AS::NSTAGE - 1; pf++) fill_next();
 	int c_stage = 0;
 	double bN = mN[(n0 * 8 + r) * Sh::LD + q];
 	const uint8_t *sta = b.tip_states + (size_t)(a_tip ? op.a : 0) * b.P, *stb = b.tip_states + (size_t)(b_tip ? op.b : 0) * b.P;
@@ -694,7 +696,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 		zero_acc<MT, NTW>(acc);
 #pragma unroll
 		for (int ch = 0; ch < Sh::NCH; ch++) {
-			cp_async_wait<1>();
+			cp_async_wait<AS::NSTAGE - 2>();
 			group_sync<NSPLIT>(wm);
 			fill_next();
 			const double *st = abuf + c_stage * AS::STG;
@@ -818,8 +820,8 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 		f_stage = f_stage + 1 == AS::NSTAGE ? 0 : f_stage + 1;
 		if (++f_ch == Sh::NCH) f_ch = 0, f_tile += gridDim.x;
 	};
-	fill_next();
-	fill_next();
+#pragma unroll
+	for (int pf = 0; pf < AS::NSTAGE - 1; pf++) fill_next();
 	int c_stage = 0;
 	double bP = 0.0, bQ = 0.0;
 	{
@@ -845,7 +847,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 		if (!(is_root && a_tip && b_tip))
 #pragma unroll
 		for (int ch = 0; ch < Sh::NCH; ch++) {
-			cp_async_wait<1>();
+			cp_async_wait<AS::NSTAGE - 2>();
 			group_sync<NSPLIT>(wm);
 			fill_next();
 			const double *st = abuf + c_stage * AS::STG;
