@@ -79,6 +79,7 @@ struct phbc_ctx {
 	int tt_cap;
 
 	long long launches;
+	long long node_evals;    // full evaluations that rewrote the node-at-a-time buffers (generic / tensor-core paths)
 
 	// optional event timing of the dominant kernel(s)
 	bool timing;

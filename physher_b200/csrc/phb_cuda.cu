@@ -355,11 +355,12 @@ __global__ void k_transition_matrices(int S, int C, int root, const double *__re
 // generic kernels
 // ---------------------------------------------------------------------------------------------
 
-#define GEN_PBLK 32
+// patterns per CTA of k_generic_combine: few states => many patterns, so that a CTA amortises its matrix staging over ~2k outputs
+static inline int gen_pblk(int S) { return S <= 8 ? 512 : (S <= 32 ? 128 : 32); }
 
-// out = (M_a x_a) o (M_b x_b) [o pi]; grid (ceil(P/32), C, ops in level)   -- K1-K4, K8
+// out = (M_a x_a) o (M_b x_b) [o pi]; grid (ceil(P/pblk), C, ops in level)   -- K1-K4, K8
 __global__ void k_generic_combine(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ Pm,
-                                  const double *__restrict__ freqs) {
+                                  const double *__restrict__ freqs, int pblk) {
 	extern __shared__ double sm[];
 	const int S = b.S, SS = S * S;
 	double *mA = sm, *mB = sm + SS;
@@ -371,8 +372,8 @@ __global__ void k_generic_combine(Bufs b, const phbc_op *__restrict__ ops, const
 	}
 	__syncthreads();
 	double *out = (double *)partial_ptr(b, op.out, c);
-	const int p0 = blockIdx.x * GEN_PBLK;
-	for (int e = threadIdx.x; e < GEN_PBLK * S; e += blockDim.x) {
+	const int p0 = blockIdx.x * pblk;
+	for (int e = threadIdx.x; e < pblk * S; e += blockDim.x) {
 		const int p = p0 + e / S, i = e % S;
 		if (p >= b.P) break;
 		double v = message(b, op.a, c, mA, p, i, true);
@@ -675,10 +676,11 @@ int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	int rc;
 	if ((rc = phbc_generic_prepare(ctx, o))) return rc;
 	ctx->lower_is_message = false;
+	ctx->node_evals++;
 	Bufs b = phbc_make_bufs(ctx);
 	const size_t smem = 2 * S * S * sizeof(double);
 	if (smem > 48 * 1024) PHBC_CHECK(cudaFuncSetAttribute(k_generic_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	const int ptiles = (int)((P + GEN_PBLK - 1) / GEN_PBLK);
+	const int pblk = gen_pblk((int)S), ptiles = (int)((P + pblk - 1) / pblk);
 	if ((rc = phbc_time_begin(ctx))) return rc;
 	// post-order, one launch per level
 	for (int l = 0; l < ctx->n_lower_levels; l++) {
@@ -686,7 +688,7 @@ int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		if (cnt <= 0) continue;
 		for (int z0 = 0; z0 < cnt; z0 += 65535) {
 			const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
-			k_generic_combine<<<dim3(ptiles, (unsigned)C, zc), 128, smem, ctx->stream>>>(b, ctx->d_lower_ops + beg + z0, ctx->d_P, ctx->d_freqs);
+			k_generic_combine<<<dim3(ptiles, (unsigned)C, zc), 128, smem, ctx->stream>>>(b, ctx->d_lower_ops + beg + z0, ctx->d_P, ctx->d_freqs, pblk);
 			ctx->launches++;
 		}
 		if (o->scale && (rc = phbc_generic_scale_ops(ctx, ctx->d_lower_ops + beg, cnt, o->scaling_threshold))) return rc;
@@ -701,7 +703,7 @@ int phbc_generic_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 				const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
 				// op.flags bit 0 asks for the root frequencies; they are applied only under include_root_freqs
 				k_generic_combine<<<dim3(ptiles, (unsigned)C, zc), 128, smem, ctx->stream>>>(b, ctx->d_upper_ops + beg + z0, ctx->d_P,
-				                                                                           o->include_root_freqs ? ctx->d_freqs : NULL);
+				                                                                           o->include_root_freqs ? ctx->d_freqs : NULL, pblk);
 				ctx->launches++;
 			}
 			if (o->scale && (rc = phbc_generic_scale_ops(ctx, ctx->d_upper_ops + beg, cnt, o->scaling_threshold))) return rc;
@@ -860,7 +862,7 @@ extern "C" int phbc_run_ops(phbc_ctx *ctx, const phbc_eval_opts *o, int nops, co
 		Bufs b = phbc_make_bufs(ctx);
 		const size_t smem = 2 * S * S * sizeof(double);
 		if (smem > 48 * 1024) PHBC_CHECK(cudaFuncSetAttribute(k_generic_combine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		const int ptiles = (int)((P + GEN_PBLK - 1) / GEN_PBLK);
+		const int pblk = gen_pblk((int)S), ptiles = (int)((P + pblk - 1) / pblk);
 		rc = 0;
 		for (int l = 0; l < nlevels && !rc; l++) {
 			const int beg = level_off[l], end = level_off[l + 1], mid = split[l];
@@ -869,7 +871,7 @@ extern "C" int phbc_run_ops(phbc_ctx *ctx, const phbc_eval_opts *o, int nops, co
 			for (int z0 = mid; z0 < end && !rc; z0 += 65535) {
 				const int zc = end - z0 < 65535 ? end - z0 : 65535;
 				k_generic_combine<<<dim3(ptiles, (unsigned)C, zc), 128, smem, ctx->stream>>>(b, ctx->d_sub_ops + z0, ctx->d_P,
-				                                                                           e.include_root_freqs ? ctx->d_freqs : NULL);
+				                                                                           e.include_root_freqs ? ctx->d_freqs : NULL, pblk);
 				ctx->launches++;
 			}
 			if (!rc && e.scale) rc = phbc_generic_scale_ops(ctx, ctx->d_sub_ops + beg, end - beg, e.scaling_threshold);
@@ -1125,3 +1127,4 @@ extern "C" int phbc_kernel_time(phbc_ctx *ctx, double *total_ms, long long *laun
 	return 0;
 }
 extern "C" long long phbc_launch_count(const phbc_ctx *ctx) { return ctx->launches; }
+extern "C" long long phbc_node_eval_count(const phbc_ctx *ctx) { return ctx->node_evals; }

@@ -153,6 +153,7 @@ int phbc_time_backward(phbc_ctx *ctx, int nbatch, int nrates, int include_jacobi
 int phbc_synchronize(phbc_ctx *ctx);
 void *phbc_stream(phbc_ctx *ctx);
 long long phbc_launch_count(const phbc_ctx *ctx);
+long long phbc_node_eval_count(const phbc_ctx *ctx); /* full evaluations that rewrote the node-at-a-time partials buffers */
 int phbc_set_timing(phbc_ctx *ctx, int on);
 int phbc_kernel_time(phbc_ctx *ctx, double *total_ms, long long *launches);
 

@@ -1180,6 +1180,7 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	const bool msg = !o->scale && !o->materialize_uppers && ctx->tip_kind == PHBC_TIP_STATES && ctx->have_eigen && !o->explicit_matrices &&
 	                 getenv("PHB_DMMA_LEGACY") == NULL;
 	ctx->lower_is_message = msg;
+	ctx->node_evals++;
 	if ((rc = phbc_time_begin(ctx))) return rc;
 	for (int l = 0; l < ctx->n_lower_levels; l++) {
 		const int beg = ctx->h_lower_level_off[l], cnt = ctx->h_lower_level_off[l + 1] - beg;
