@@ -59,6 +59,10 @@ struct phbc_ctx {
 	bool nuc4_codes_valid, nuc4_codes_bad;
 	double *d_nuc4_cta_lnl;
 	int nuc4_grid;
+	double *d_walk_gstat;    // per-(CTA, warp) expected-transition statistics [grid][warps][N][16] (GRAD = 2 walks)
+	size_t walk_gstat_bytes;
+	double *d_nuc4_G;        // [N][C][16] summed statistics; the root's entry holds the root term of the frequency gradient
+	bool nuc4_G_valid;       // d_nuc4_G belongs to the current inputs (cleared by every other evaluation)
 	double *h_freqs, *h_qmat;  // host copies of small model constants (kernel parameter bank)
 
 	// outputs
@@ -132,6 +136,8 @@ int phbc_dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt);  // out =
 // fused 4-state walk path (phb_nuc4.cu)
 int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
 bool phbc_nuc4_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);
+int phbc_nuc4_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int nsets, const double *M_host, int skip_node, double *lnl, double *out_host);  // 1 = declined
+int phbc_nuc4_root_frequency_gradient(phbc_ctx *ctx, double *out_host);
 
 // shared device helpers
 __device__ __forceinline__ double phb_warp_sum(double v) {

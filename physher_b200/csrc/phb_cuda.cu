@@ -99,7 +99,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	                ctx->d_freqs, ctx->d_rates, ctx->d_props, ctx->d_bl, ctx->d_P, ctx->d_dP, ctx->d_lower, ctx->d_upper,
 	                ctx->d_sf, ctx->d_lower_ops, ctx->d_upper_ops, ctx->d_parent_ops, ctx->d_post_ops, ctx->d_pre_ops, ctx->d_walk_mats,
 	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch,
-	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl, ctx->d_post_tip_order, ctx->d_pre_tip_order, ctx->d_dmma_img, ctx->d_tt_lowers, ctx->d_tt_topo, ctx->d_tt_bad,
+	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl, ctx->d_walk_gstat, ctx->d_nuc4_G, ctx->d_post_tip_order, ctx->d_pre_tip_order, ctx->d_dmma_img, ctx->d_tt_lowers, ctx->d_tt_topo, ctx->d_tt_bad,
 	                ctx->d_tt_ratios, ctx->d_tt_rates, ctx->d_tt_heights, ctx->d_tt_adj, ctx->d_tt_out};
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		if (bufs[i]) cudaFree(bufs[i]);
@@ -752,6 +752,12 @@ extern "C" int phbc_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int 
 	e.want_gradient = 1;
 	e.materialize_uppers = 1;
 	e.batch_count = 1;
+	// 4 states, unscaled: the fused walk accumulates the per-branch statistics every set contracts with -- no materialised uppers
+	ctx->nuc4_G_valid = false;
+	{
+		const int frc = phbc_nuc4_matrix_gradient(ctx, &e, nsets, M_host, skip_node, lnl, out_host);
+		if (frc != 1) return frc;
+	}
 	int rc = phbc_dmma_supported(ctx, &e) && e.kernels != 1 ? phbc_dmma_evaluate(ctx, &e) : phbc_generic_evaluate(ctx, &e);
 	if (rc) return rc;
 	const size_t set = N * C * S * S;
@@ -806,6 +812,7 @@ extern "C" int phbc_run_ops(phbc_ctx *ctx, const phbc_eval_opts *o, int nops, co
 	phbc_eval_opts e = *o;
 	e.batch_index = 0;
 	e.batch_count = 1;
+	ctx->nuc4_G_valid = false;
 	for (int k = 0; k < nops; k++)
 		if (ops[k].out >= (int)N) e.want_gradient = 1;  // upper buffers are needed
 	if ((rc = phbc_generic_buffers(ctx, &e))) return rc;
@@ -939,6 +946,7 @@ __global__ void k_sum_rows(const double *__restrict__ partial, int n, double *__
 // the root's lower partial must be resident (any node-at-a-time evaluation of the current inputs)
 extern "C" int phbc_root_frequency_gradient(phbc_ctx *ctx, double *out_host) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));
+	if (ctx->nuc4_G_valid) return phbc_nuc4_root_frequency_gradient(ctx, out_host);
 	if (!ctx->d_lower) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "lower partials are not resident");
 		return -4;
@@ -972,6 +980,7 @@ extern "C" int phbc_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "batch index %d out of range", o->batch_index);
 		return -1;
 	}
+	ctx->nuc4_G_valid = false;
 	const int count = o->batch_count > 1 ? o->batch_count : 1;
 	if (o->batch_index + count > ctx->bl_cap || o->batch_index + count > ctx->result_cap) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "batch %d + %d out of range", o->batch_index, count);

@@ -54,6 +54,7 @@ struct Nuc4Params {
 	const double *pre_mats;   // [n_pre][3][C][16]
 	double *lower;            // [grid][n_post][C][PB][4]: messages P_n L_n
 	double *gacc;             // [grid][phases][warps][N]
+	double *gstat;            // GRAD == 2: [grid][warps][N][16] expected-transition statistics (see gstat_add)
 	double *cta_lnl;          // [grid][phases][warps]
 	double *pattern_lnl;      // [P]
 	double freqs[4];
@@ -154,6 +155,43 @@ __device__ __forceinline__ double butterfly2(double v0, double v1, int lane) {
 	return r;
 }
 
+// indicator vector of a tip code = the tip's L_n: a known state is one-hot, a missing state all ones (derivative matrices see their
+// real row sums, treelikelihoodX.c:878-1001), an ambiguity set its mask
+__device__ __forceinline__ void tip_vector(unsigned code, double (&x)[4]) {
+#pragma unroll
+	for (int j = 0; j < 4; j++) x[j] = (code < 4u ? code == (unsigned)j : (code == 4u || ((code >> j) & 1u))) ? 1.0 : 0.0;
+}
+
+// Expected-transition statistics of one branch: row[4 i + j] += sum over the warp's patterns of t[i] * x[j], with
+// t = (w_k / L_k) f_i U_n[k, i] and x = L_n[k, .].  Any per-branch matrix M then contracts as sum_ij G[i][j] M[i][j] =
+// sum_k w_k / L_k sum_i f_i U_n[k,i] (M L_n[k])_i -- the node sweep of calculate_dlnl_dQ (treelikelihood.c:2408-2478) for EVERY
+// parameter at once, and without materialised upper partials.  16 values are reduced across 32 lanes by a transposing
+// butterfly (8 + 4 + 2 + 1 + 1 shuffles); lane l ends up with element l >> 1.
+template <int PPT>
+__device__ __forceinline__ void gstat_add(const double (&t)[PPT][4], const double (&x)[PPT][4], double *row, int lane) {
+	double v[16];
+#pragma unroll
+	for (int i = 0; i < 4; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			double a = t[0][i] * x[0][j];
+#pragma unroll
+			for (int u = 1; u < PPT; u++) a = fma(t[u][i], x[u][j], a);
+			v[4 * i + j] = a;
+		}
+#pragma unroll
+	for (int w = 8, off = 16; w >= 1; w >>= 1, off >>= 1) {
+		const bool h = lane & off;
+#pragma unroll
+		for (int k = 0; k < w; k++) {
+			const double keep = h ? v[w + k] : v[k], send = h ? v[k] : v[w + k];
+			v[k] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+		}
+	}
+	v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+	if (!(lane & 1)) red_add_f64(row + (lane >> 1), v[0]);
+}
+
 // y[u] = M x[u] for the PPT patterns of a thread: every matrix element is read from shared memory ONCE and feeds PPT
 // independent FMA chains (half the LDS traffic and twice the instruction-level parallelism per pattern at PPT = 2)
 template <int PPT>
@@ -169,7 +207,8 @@ __device__ __forceinline__ void matvec_smem_n(const double *__restrict__ M, cons
 
 // A thread owns PPT (pattern, category) cells of the tile: category c and patterns pl0 + u * PBT (PBT = PB / PPT), i.e. cell
 // index c * PB + pl0 + u * PBT in every [half][NUC4_NT] cell array (slots, lower rows) -- the layouts do not depend on PPT.
-template <int C, bool SCALE, bool GRAD, int PPT>
+// GRAD: 0 lnL only, 1 + branch gradients, 2 + expected-transition statistics per branch (substitution-model gradients)
+template <int C, bool SCALE, int GRAD, int PPT>
 __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params prm) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	constexpr int PB = NUC4_NT / C;      // patterns per tile
@@ -201,6 +240,7 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 	double cta_lnl = 0.0;
 	unsigned char *row_cell = GRAD ? reinterpret_cast<unsigned char *>(prm.lower) + (size_t)blockIdx.x * prm.n_post * NUC4_ROW_BYTES + cell0 * 16 : nullptr;
 	double *my_gacc = nullptr;
+	double *my_gstat = GRAD == 2 ? prm.gstat + ((size_t)blockIdx.x * (NTHR / 32) + warp) * prm.N * 16 : nullptr;  // single sample only
 
 	// work items = (sample, pattern tile), sample-major; a CTA owns a CONTIGUOUS range, so it touches at most
 	// prm.phases consecutive samples and keeps one private accumulator row set per touched sample (deterministic sums)
@@ -371,6 +411,19 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 				sgrad[u] = invLw[pl];
 				wk[u] = p < prm.P ? prm.weights[p] : 0.0;
 			}
+			if (GRAD == 2) {
+				// root entry of the statistics: sum_k w_k / L_k L_root[c, k, i] (the root term of the frequency parameters,
+				// treelikelihood.c:2371-2404); `out` still holds the root op's result
+				double r[4];
+#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					r[i] = sgrad[0] * out[0][i];
+#pragma unroll
+					for (int u = 1; u < PPT; u++) r[i] = fma(sgrad[u], out[u][i], r[i]);
+				}
+				const double tot = butterfly4(r[0], r[1], r[2], r[3], lane);  // lane 0: r0, lane 8: r2, lane 16: r1, lane 24: r3
+				if ((lane & 7) == 0) red_add_f64(my_gstat + (size_t)prm.root * 16 + (((lane >> 4) & 1) | ((lane >> 2) & 2)), tot);
+			}
 			const int nchunks = (prm.n_pre + NUC4_CHUNK - 1) / NUC4_CHUNK;
 			auto issue = [&](int ch, uint32_t ld, int tips) {
 				const int first = ch * NUC4_CHUNK;
@@ -434,6 +487,14 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 						for (int u = 0; u < PPT; u++) cell_load(slot_cell + d->u_slot * NUC4_SLOT_BYTES + u * PBT * 16, ureg[u]);  // else: left by the preceding op
 					}
 					matvec_smem_n<PPT>(MP, ureg, W);  // P_p u_p
+					if (GRAD == 2) {  // the branch above this op's node: U_p is in ureg, L_p = M_a o M_b
+						double tp[PPT][4], xp[PPT][4];
+#pragma unroll
+						for (int u = 0; u < PPT; u++)
+#pragma unroll
+							for (int i = 0; i < 4; i++) tp[u][i] = sgrad[u] * prm.fq[i] * ureg[u][i], xp[u][i] = ma[u][i] * mb[u][i];
+						gstat_add<PPT>(tp, xp, my_gstat + (size_t)d->node * 16, lane);
+					}
 				}
 				double ua[PPT][4], ub[PPT][4];
 #pragma unroll
@@ -498,6 +559,25 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 						// (gradient_cat_branch_lengths_aux, treelikelihood.c:2721-2738)
 						va += prm.compat ? na[u] / da[u] * wk[u] : na[u] / dta * wk[u];
 						vb += prm.compat ? nb[u] / db[u] * wk[u] : nb[u] / dtb * wk[u];
+					}
+				}
+				if (GRAD == 2 && kind != 2) {  // tip branches: L_n is the tip's indicator vector
+					double tt[PPT][4], xt[PPT][4];
+#pragma unroll
+					for (int u = 0; u < PPT; u++) {
+						tip_vector(cds[d->a_code * PB + u * PBT], xt[u]);
+#pragma unroll
+						for (int i = 0; i < 4; i++) tt[u][i] = sgrad[u] * prm.fq[i] * ua[u][i];
+					}
+					gstat_add<PPT>(tt, xt, my_gstat + (size_t)d->a_node * 16, lane);
+					if (kind == 0) {
+#pragma unroll
+						for (int u = 0; u < PPT; u++) {
+							tip_vector(cds[d->b_code * PB + u * PBT], xt[u]);
+#pragma unroll
+							for (int i = 0; i < 4; i++) tt[u][i] = sgrad[u] * prm.fq[i] * ub[u][i];
+						}
+						gstat_add<PPT>(tt, xt, my_gstat + (size_t)d->b_node * 16, lane);
 					}
 				}
 #pragma unroll
@@ -723,6 +803,61 @@ __global__ void __launch_bounds__(32 * NUC4_FY) k_nuc4_finalize(int N, int C, in
 	}
 }
 
+// G[n][c][e] = fixed-order sum of the per-(CTA, warp) statistics rows; warp w of a walk CTA works on category w / (nw / C).
+// block (64, NUC4_GY): x = element of the [N][C][16] result, y strides over the (CTA, warp-of-category) rows
+#define NUC4_GY 8
+__global__ void __launch_bounds__(64 * NUC4_GY) k_nuc4_gstat_sum(int N, int C, int nw, int grid, const double *__restrict__ gstat, double *__restrict__ G) {
+	__shared__ double red[NUC4_GY][64];
+	const int idx = blockIdx.x * 64 + threadIdx.x;
+	const bool live = idx < N * C * 16;
+	const int e = idx & 15, c = live ? (idx >> 4) % C : 0, n = live ? (idx >> 4) / C : 0;
+	const int wpc = nw / C, rows = grid * wpc;
+	double s[4] = {0.0, 0.0, 0.0, 0.0};
+	if (live) {
+		const double *base = gstat + (size_t)n * 16 + e;
+		int r = threadIdx.y;
+		for (; r + 3 * NUC4_GY < rows; r += 4 * NUC4_GY) {
+#pragma unroll
+			for (int q = 0; q < 4; q++) {
+				const int rr = r + q * NUC4_GY;
+				s[q] += base[((size_t)(rr / wpc) * nw + c * wpc + rr % wpc) * N * 16];
+			}
+		}
+		for (; r < rows; r += NUC4_GY) s[0] += base[((size_t)(r / wpc) * nw + c * wpc + r % wpc) * N * 16];
+	}
+	red[threadIdx.y][threadIdx.x] = (s[0] + s[1]) + (s[2] + s[3]);
+	__syncthreads();
+	if (threadIdx.y == 0 && live) {
+		double tot = 0.0;
+#pragma unroll
+		for (int k = 0; k < NUC4_GY; k++) tot += red[k][threadIdx.x];
+		G[idx] = tot;
+	}
+}
+
+// out[k] = sum over nodes n (not the root, not `skip`), categories and matrix entries of props[c] * G[n][c][e] * M[k][n][c][e]
+__global__ void k_nuc4_gstat_contract(int N, int C, int root, int skip, const double *__restrict__ G, const double *__restrict__ M /* [nsets][N][C][16] */,
+                                      const double *__restrict__ props, double *__restrict__ out) {
+	__shared__ double red[256];
+	const double *Mk = M + (size_t)blockIdx.x * N * C * 16;
+	double s = 0.0;
+	for (int nc = threadIdx.x; nc < N * C; nc += blockDim.x) {
+		const int n = nc / C, c = nc - n * C;
+		if (n == root || n == skip) continue;
+		double a = 0.0;
+#pragma unroll
+		for (int e = 0; e < 16; e++) a = fma(G[(size_t)nc * 16 + e], Mk[(size_t)nc * 16 + e], a);
+		s += a * (C == 1 ? 1.0 : props[c]);
+	}
+	red[threadIdx.x] = s;
+	__syncthreads();
+	for (int w = blockDim.x / 2; w > 0; w >>= 1) {
+		if (threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -746,6 +881,8 @@ bool phbc_nuc4_supported(const phbc_ctx *ctx, const phbc_eval_opts *o) {
 }
 
 
+static int nuc4_prepare_codes(phbc_ctx *ctx, int *usable);
+
 int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));
 	const int C = ctx->C, N = ctx->N, T = ctx->T, P = ctx->P;
@@ -754,22 +891,10 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	const size_t smem = nuc4_smem_bytes(C, PB, nslots, o->scale != 0);
 	const int ntiles = (P + PB - 1) / PB;
 	// tip codes in walk order (once per tip upload / schedule change)
-	if (!ctx->d_nuc4_codes) {
-		PHBC_CHECK(cudaMalloc((void **)&ctx->d_nuc4_codes, 2 * (size_t)ntiles * T * PB));
-		PHBC_CHECK(cudaMalloc((void **)&ctx->d_nuc4_bad, sizeof(int)));
-	}
-	if (!ctx->nuc4_codes_valid) {
-		const size_t n = 2 * (size_t)ntiles * T * PB;
-		PHBC_CHECK(cudaMemsetAsync(ctx->d_nuc4_bad, 0, sizeof(int), ctx->stream));
-		k_nuc4_encode_tips<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(T, P, PB, ntiles, ctx->tip_kind, ctx->d_tip_states, ctx->d_tip_partials,
-		                                                                       ctx->d_post_tip_order, ctx->d_pre_tip_order, ctx->d_nuc4_codes,
-		                                                                       ctx->d_nuc4_bad);
-		ctx->launches++;
-		int bad = 0;
-		PHBC_CHECK(cudaMemcpyAsync(&bad, ctx->d_nuc4_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
-		ctx->nuc4_codes_bad = bad != 0;
-		ctx->nuc4_codes_valid = true;
+	{
+		int usable = 0;
+		const int prc = nuc4_prepare_codes(ctx, &usable);
+		if (prc) return prc;
 	}
 	if (ctx->nuc4_codes_bad) {  // non 0/1 tip partials: node-at-a-time kernels, one sample at a time
 		phbc_eval_opts one = *o;
@@ -786,14 +911,22 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	// two patterns per thread (every matrix element read once feeds two FMA chains) wherever a warp still holds one category
 	typedef void (*walk_fn)(const Nuc4Params);
 	static const walk_fn table[4][2][2] = {
-	    {{k_nuc4_walk<1, false, false, 2>, k_nuc4_walk<1, false, true, 2>}, {k_nuc4_walk<1, true, false, 2>, k_nuc4_walk<1, true, true, 2>}},
-	    {{k_nuc4_walk<2, false, false, 2>, k_nuc4_walk<2, false, true, 2>}, {k_nuc4_walk<2, true, false, 2>, k_nuc4_walk<2, true, true, 2>}},
-	    {{k_nuc4_walk<4, false, false, 2>, k_nuc4_walk<4, false, true, 2>}, {k_nuc4_walk<4, true, false, 2>, k_nuc4_walk<4, true, true, 2>}},
-	    {{k_nuc4_walk<8, false, false, 1>, k_nuc4_walk<8, false, true, 1>}, {k_nuc4_walk<8, true, false, 1>, k_nuc4_walk<8, true, true, 1>}},
+	    {{k_nuc4_walk<1, false, 0, 2>, k_nuc4_walk<1, false, 1, 2>}, {k_nuc4_walk<1, true, 0, 2>, k_nuc4_walk<1, true, 1, 2>}},
+	    {{k_nuc4_walk<2, false, 0, 2>, k_nuc4_walk<2, false, 1, 2>}, {k_nuc4_walk<2, true, 0, 2>, k_nuc4_walk<2, true, 1, 2>}},
+	    {{k_nuc4_walk<4, false, 0, 2>, k_nuc4_walk<4, false, 1, 2>}, {k_nuc4_walk<4, true, 0, 2>, k_nuc4_walk<4, true, 1, 2>}},
+	    {{k_nuc4_walk<8, false, 0, 1>, k_nuc4_walk<8, false, 1, 1>}, {k_nuc4_walk<8, true, 0, 1>, k_nuc4_walk<8, true, 1, 1>}},
 	};
+	// unscaled walks that also accumulate the expected-transition statistics (phbc_nuc4_matrix_gradient)
+	static const walk_fn table_stat[4] = {k_nuc4_walk<1, false, 2, 2>, k_nuc4_walk<2, false, 2, 2>, k_nuc4_walk<4, false, 2, 2>, k_nuc4_walk<8, false, 2, 1>};
 	const int ppt = C == 8 ? 1 : 2, nthr = NUC4_NT / ppt;
 	const int ci = C == 1 ? 0 : (C == 2 ? 1 : (C == 4 ? 2 : 3));
-	walk_fn kern = table[ci][o->scale ? 1 : 0][o->want_gradient ? 1 : 0];
+	const bool want_stat = o->want_gradient == 2;
+	if (want_stat && (o->scale || (o->batch_count > 1))) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "nuc4 walk: transition statistics need an unscaled single-sample evaluation");
+		return -1;
+	}
+	walk_fn kern = want_stat ? table_stat[ci] : table[ci][o->scale ? 1 : 0][o->want_gradient ? 1 : 0];
+	ctx->nuc4_G_valid = false;
 	PHBC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;
 	PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthr, smem));
@@ -847,6 +980,19 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		}
 		PHBC_CHECK(cudaMemsetAsync(ctx->d_walk_gacc, 0, gacc_bytes, ctx->stream));
 	}
+	if (want_stat) {
+		const size_t gstat_bytes = (size_t)grid * warps * N * 16 * sizeof(double);
+		if (gstat_bytes > ctx->walk_gstat_bytes) {
+			PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+			if (ctx->d_walk_gstat) cudaFree(ctx->d_walk_gstat);
+			ctx->d_walk_gstat = NULL;
+			ctx->walk_gstat_bytes = 0;
+			PHBC_CHECK(cudaMalloc((void **)&ctx->d_walk_gstat, gstat_bytes));
+			ctx->walk_gstat_bytes = gstat_bytes;
+		}
+		if (!ctx->d_nuc4_G) PHBC_CHECK(cudaMalloc((void **)&ctx->d_nuc4_G, (size_t)N * C * 16 * sizeof(double)));
+		PHBC_CHECK(cudaMemsetAsync(ctx->d_walk_gstat, 0, gstat_bytes, ctx->stream));
+	}
 	if (!ctx->d_nuc4_cta_lnl || ctx->nuc4_grid < grid * phases) {
 		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 		if (ctx->d_nuc4_cta_lnl) cudaFree(ctx->d_nuc4_cta_lnl);
@@ -890,6 +1036,7 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	prm.pre_mats = pre_mats;
 	prm.lower = ctx->d_walk_lower;
 	prm.gacc = ctx->d_walk_gacc;
+	prm.gstat = ctx->d_walk_gstat;
 	prm.cta_lnl = ctx->d_nuc4_cta_lnl;
 	prm.pattern_lnl = ctx->d_pattern_lnl;
 	memcpy(prm.freqs, ctx->h_freqs, sizeof(prm.freqs));  // small model constants travel in the kernel parameter bank
@@ -908,6 +1055,89 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	                                                                         ctx->d_walk_gacc, o->want_gradient, ctx->d_props, ctx->d_rates,
 	                                                                         ctx->d_cat_grad, result);
 	ctx->launches++;
+	if (want_stat) {
+		k_nuc4_gstat_sum<<<(N * C * 16 + 63) / 64, dim3(64, NUC4_GY), 0, ctx->stream>>>(N, C, warps, grid, ctx->d_walk_gstat, ctx->d_nuc4_G);
+		ctx->launches++;
+		ctx->nuc4_G_valid = true;
+	}
 	PHBC_CHECK(cudaGetLastError());
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// substitution-model parameter gradients on the fused walk
+// ---------------------------------------------------------------------------------------------
+// makes sure the walk-ordered tip codes exist; *usable = 0 when the tips are not 0/1 vectors (the walk then declines)
+static int nuc4_prepare_codes(phbc_ctx *ctx, int *usable) {
+	const int C = ctx->C, T = ctx->T, P = ctx->P;
+	const int PB = pattern_block(C);
+	const int ntiles = (P + PB - 1) / PB;
+	if (!ctx->d_nuc4_codes) {
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_nuc4_codes, 2 * (size_t)ntiles * T * PB));
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_nuc4_bad, sizeof(int)));
+	}
+	if (!ctx->nuc4_codes_valid) {
+		const size_t n = 2 * (size_t)ntiles * T * PB;
+		PHBC_CHECK(cudaMemsetAsync(ctx->d_nuc4_bad, 0, sizeof(int), ctx->stream));
+		k_nuc4_encode_tips<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(T, P, PB, ntiles, ctx->tip_kind, ctx->d_tip_states, ctx->d_tip_partials,
+		                                                                       ctx->d_post_tip_order, ctx->d_pre_tip_order, ctx->d_nuc4_codes,
+		                                                                       ctx->d_nuc4_bad);
+		ctx->launches++;
+		int bad = 0;
+		PHBC_CHECK(cudaMemcpyAsync(&bad, ctx->d_nuc4_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		ctx->nuc4_codes_bad = bad != 0;
+		ctx->nuc4_codes_valid = true;
+	}
+	*usable = !ctx->nuc4_codes_bad;
+	return 0;
+}
+
+/*
+ * phbc_matrix_gradient on the fused walk: one GRAD = 2 launch leaves G[n][c][i][j] on the device, every matrix set is then a
+ * 16-element contraction per (node, category).  Returns 1 (declined, nothing done) when the walk cannot serve the request:
+ * rescaling on, tips that are not 0/1 vectors, or a shape phbc_nuc4_supported refuses.
+ */
+int phbc_nuc4_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int nsets, const double *M_host, int skip_node, double *lnl, double *out_host) {
+	if (o->scale || o->kernels == 1 || !phbc_nuc4_supported(ctx, o)) return 1;
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	int usable = 0, rc;
+	if ((rc = nuc4_prepare_codes(ctx, &usable))) return rc;
+	if (!usable) return 1;
+	phbc_eval_opts e = *o;
+	e.want_gradient = 2;
+	e.batch_count = 1;
+	if ((rc = phbc_nuc4_evaluate(ctx, &e))) return rc;
+	const size_t N = ctx->N, C = ctx->C, set = N * C * 16;
+	// matrix sets and results travel through the grow-only reduction scratch (no allocation per request)
+	if ((rc = phbc_ensure_scratch(ctx, ((size_t)nsets * set + nsets) * sizeof(double)))) return rc;
+	double *d_M = ctx->d_scratch, *d_out = ctx->d_scratch + (size_t)nsets * set;
+	PHBC_CHECK(cudaMemcpyAsync(d_M, M_host, (size_t)nsets * set * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	k_nuc4_gstat_contract<<<nsets, 256, 0, ctx->stream>>>((int)N, (int)C, ctx->root, skip_node, ctx->d_nuc4_G, d_M, ctx->d_props, d_out);
+	ctx->launches++;
+	PHBC_CHECK(cudaMemcpyAsync(out_host, d_out, (size_t)nsets * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	if (lnl) PHBC_CHECK(cudaMemcpyAsync(lnl, ctx->d_result + (size_t)e.batch_index * (1 + N), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+	PHBC_CHECK(cudaGetLastError());
+	return 0;
+}
+
+// d lnL / d pi_i at fixed partials from the root entry of the statistics: sum_c prop_c G[root][c][i]
+int phbc_nuc4_root_frequency_gradient(phbc_ctx *ctx, double *out_host) {
+	if (!ctx->nuc4_G_valid) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "transition statistics are not resident");
+		return -4;
+	}
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	double g[8 * 16], props[8];
+	const int C = ctx->C;
+	PHBC_CHECK(cudaMemcpyAsync(g, ctx->d_nuc4_G + (size_t)ctx->root * C * 16, (size_t)C * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	PHBC_CHECK(cudaMemcpyAsync(props, ctx->d_props, (size_t)C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+	for (int i = 0; i < 4; i++) {
+		double s = 0.0;
+		for (int c = 0; c < C; c++) s += (C == 1 ? 1.0 : props[c]) * g[c * 16 + i];
+		out_host[i] = s;
+	}
 	return 0;
 }

@@ -96,3 +96,58 @@ def test_root_frequency_gradient(S, C, scale):
     # sum_i pi_i G_i = sum_k w_k exactly
     assert abs(got @ pb.freqs - pb.weights.sum()) < 1e-9 * pb.weights.sum()
     tlk.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tips", ["states", "partials"])
+@pytest.mark.parametrize("shape", [(37, 1500, 4), (21, 333, 1), (18, 257, 2), (26, 65, 8), (128, 900, 4)], ids=lambda s: "T%d-P%d-C%d" % s)
+def test_gpu_fused_walk_transition_statistics(shape, tips):
+    """4 states, unscaled: ONE launch of the fused walk accumulates the per-branch statistics G[n][c][i][j] every matrix set
+    contracts with (no materialised upper partials); arbitrary matrices, unknown states / ambiguity sets at the tips, and the
+    root term of the frequency gradient from the statistics' root entry.  Checked against the oracle's node sweep and against
+    the node-at-a-time kernels."""
+    import physher_b200 as phb
+    from physher_b200 import synthetic as syn
+    from tests.test_gpu_parity import _synthetic_problem
+
+    T, P, C = shape
+    topo = syn.caterpillar_topology(T) if T == 128 else None
+    pb = _synthetic_problem(T, P, 4, C, seed=7000 + T + C, topo=topo, unknown=0.04)
+    if tips == "partials":
+        rng = np.random.default_rng(7100 + T)
+        tp = np.zeros((T, P, 4))
+        known = pb.tip_states < 4
+        tp[known, pb.tip_states[known]] = 1.0
+        tp[~known] = 1.0
+        amb = rng.random((T, P)) < 0.05  # ambiguity sets (R, Y, ...): two or three states set
+        tp[amb] = (rng.random((int(amb.sum()), 4)) < 0.5).astype(np.float64)
+        tp[tp.sum(-1) == 0] = 1.0
+        pb.tip_partials = tp
+        pb.use_tip_states = False
+    rng = np.random.default_rng(7200 + C)
+    M = rng.normal(size=(6, pb.nnodes, C, 4, 4))
+    want = O.matrix_gradient(pb, M)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    before = tlk.launch_count()
+    got = tlk.matrix_gradient(M)
+    assert tlk.launch_count() - before <= 7, "the fused walk serves the request in a handful of launches"
+    assert grad_err(got, want) < RTOL
+    res = O.evaluate(pb, gradient=False, partials=True)
+    R = np.einsum("c,cpi->pi", pb.props, res["lower"][pb.root])
+    want_root = (pb.weights[:, None] * R / (R @ pb.freqs)[:, None]).sum(0)
+    before = tlk.launch_count()
+    assert grad_err(tlk.root_frequency_gradient(), want_root) < RTOL
+    assert tlk.launch_count() == before, "served from the statistics' root entry"
+    assert rel_err(tlk.calculate(), res["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), O.evaluate(pb)["grad"]) < RTOL
+    # same request on the node-at-a-time kernels
+    gen = phb.SingleTreeLikelihood.from_problem(pb, kernels=phb.KERNELS_GENERIC)
+    assert grad_err(gen.matrix_gradient(M), want) < RTOL
+    gen.close()
+    # include_root_freqs (the reference's default request) on the fused path
+    from physher_b200.treelikelihood import OPT_INCLUDE_ROOT_FREQS
+
+    tlk.set_option(OPT_INCLUDE_ROOT_FREQS, 1)
+    pb.include_root_freqs = True
+    assert grad_err(tlk.matrix_gradient(M), O.matrix_gradient(pb, M)) < RTOL
+    tlk.close()
