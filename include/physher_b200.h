@@ -75,6 +75,17 @@ phb_tlk *phb_tlk_create(int ntips, int nstate, int ncat, int npatterns, const in
 /* free_SingleTreeLikelihood (treelikelihood.c:1187-1230) */
 void phb_tlk_free(phb_tlk *tlk);
 
+/* clone_SingleTreeLikelihood (treelikelihood.c:1241-1395; what Model.clone builds per worker, gradascent.c:166-170): an independent
+ * object on `device` (may differ from the source's) with the same topology, data (copied device to device), model inputs,
+ * options, rescaling state and gradient request.  Partials are not copied: the clone starts with every node dirty. */
+phb_tlk *phb_tlk_clone(phb_tlk *tlk, int device);
+
+/* Topology moves (NNI / SPR: nniopt.c:301-334, spropt.c:1548-1615).  The reference re-reads its Tree on every traversal; here the
+ * traversal is compiled into schedules, so a changed tree (same taxa, same node-id convention) is handed over explicitly.  Data,
+ * model inputs, options and branch lengths (by node id) are kept; every partial is dirty; phb_tlk_set_time_tree must be called
+ * again.  On failure the previous topology stays in place. */
+int phb_tlk_set_topology(phb_tlk *tlk, const int *left, const int *right, int root);
+
 /* SitePattern inputs (sitepattern.h:68-82): patterns[taxon][pattern] by TIP NODE ID and weights[pattern] */
 int phb_tlk_set_tip_states(phb_tlk *tlk, const uint8_t *states /* [T][P] */);
 int phb_tlk_set_tip_partials(phb_tlk *tlk, const double *partials /* [T][P][S], sp->get_partials */);
@@ -97,6 +108,8 @@ int phb_tlk_set_branch_length(phb_tlk *tlk, int node, double bl); /* + SingleTre
 /* SingleTreeLikelihood_update_all_nodes / _update_one_node (treelikelihood.c:1737-1751) */
 void phb_tlk_update_all_nodes(phb_tlk *tlk);
 int phb_tlk_update_one_node(phb_tlk *tlk, int node);
+/* SingleTreeLikelihood_update_three_nodes (treelikelihood.c:1754-1771): the node and both its children */
+int phb_tlk_update_three_nodes(phb_tlk *tlk, int node);
 
 /* Model.store / Model.restore of the tree likelihood (_singleTreeLikelihood_store / _restore, treelikelihood.c:116-161):
  * restore returns to the stored inputs and the stored lnL without recomputation (MCMC reject). */
@@ -130,7 +143,9 @@ int phb_tlk_cat_branch_gradient(phb_tlk *tlk, double *out /* [N][C] */);
  * per-node matrices [nsets][N][C][S][S] (row-major like P), e.g. dP/d theta_k from m->dPdp(m, k, mat, bl * rate_c)
  * (substmodel.c:469-489, :2421); out[k] = sum over non-root nodes (not the root's right child when unrooted, :2408) and patterns of
  * w_p / L_p * sum_c prop_c sum_i f_i U_n[c,p,i] (M_k[n,c] L_n[c,p])_i.  Honours PHB_OPT_INCLUDE_ROOT_FREQS and rescaling.
- * Runs on the node-at-a-time kernels (materialised upper partials). */
+ * 4 states without rescaling: ONE launch of the fused walk accumulates the per-branch statistics G[n][c][i][j] =
+ * sum_p w_p / L_p f_i U_n[c,p,i] L_n[c,p,j] and every set is a 16-element contraction per (node, category) -- no materialised upper
+ * partials, cost independent of nsets.  Otherwise the node-at-a-time kernels (materialised upper partials, one sweep per set). */
 int phb_tlk_matrix_gradient(phb_tlk *tlk, int nsets, const double *M, double *out /* [nsets] */);
 /* The root term of the frequency parameters in calculate_dlnl_dQ (treelikelihood.c:2371-2404): out[i] = d lnL / d pi_i with the partials
  * held fixed = sum_p w_p R[p,i] / L_p, R the category-integrated root partials; the caller contracts it with d pi / d theta

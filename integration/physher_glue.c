@@ -53,6 +53,8 @@ typedef struct Backend {
 	int have_model; /* the substitution model has been pushed at least once */
 	int incremental; /* the device object keeps its partials resident (single-branch fast path in use) */
 	double (*ref_d2logP)(Model *, const Parameter *);
+	Model *(*ref_clone)(Model *, Hashtable *);
+	int device;
 	long long evaluations;
 } Backend;
 
@@ -457,6 +459,25 @@ static void phb_physher_free(Model *self) {
 	ref_free(self);
 }
 
+static int attach_with(Model *model, int device, phb_tlk *h);
+
+/*
+ * Model.clone of the tree likelihood (_treeLikelihood_model_clone, treelikelihood.c:715-790): the reference clones its model graph
+ * and copies the function pointers of the source object (clone_SingleTreeLikelihood_with, :1310), so a clone of an attached model
+ * must get a device object of its own -- phb_tlk_clone copies the data device to device -- before anybody evaluates it.
+ */
+static Model *phb_physher_clone(Model *self, Hashtable *hash) {
+	Backend *b = backend_of_tlk((SingleTreeLikelihood *)self->obj);
+	Model *c = b->ref_clone(self, hash);
+	SingleTreeLikelihood *ctlk = (SingleTreeLikelihood *)c->obj;
+	ctlk->calculate = b->ref_calculate; /* what attach_with records as the reference's own function */
+	ctlk->use_upper = false;
+	phb_tlk *h = phb_tlk_clone(b->h, b->device);
+	if (!h) die("phb_tlk_clone");
+	if (attach_with(c, b->device, h)) die("attach clone");
+	return c;
+}
+
 int phb_physher_attach(Model *model, int device) {
 	SingleTreeLikelihood *tlk = (SingleTreeLikelihood *)model->obj;
 	if (backend_of_tlk(tlk)) return 0;
@@ -497,6 +518,14 @@ int phb_physher_attach(Model *model, int device) {
 		free(partials);
 	}
 	if (phb_tlk_set_pattern_weights(h, tlk->sp->weights)) die("set_pattern_weights");
+	return attach_with(model, device, h);
+}
+
+/* common part of attach and clone: the backend record and the re-pointed slots */
+static int attach_with(Model *model, int device, phb_tlk *h) {
+	SingleTreeLikelihood *tlk = (SingleTreeLikelihood *)model->obj;
+	const int N = Tree_node_count(tlk->tree);
+	const int S = tlk->m->nstate, C = tlk->cat_count;
 
 	Backend *b = (Backend *)calloc(1, sizeof(Backend));
 	b->model = model;
@@ -515,6 +544,9 @@ int phb_physher_attach(Model *model, int device) {
 	b->ref_dlogP = model->dlogP;
 	b->ref_d2logP = model->d2logP;
 	b->ref_free = model->free;
+	b->ref_clone = model->clone;
+	b->device = device;
+	model->clone = phb_physher_clone;
 	tlk->calculate = phb_physher_calculate;
 	model->dlogP = phb_physher_dlogP;
 	model->d2logP = phb_physher_d2logP;
@@ -536,6 +568,7 @@ int phb_physher_detach(Model *model) {
 	model->dlogP = b->ref_dlogP;
 	model->d2logP = b->ref_d2logP;
 	model->free = b->ref_free;
+	model->clone = b->ref_clone;
 	tlk->use_upper = false;
 	SingleTreeLikelihood_update_all_nodes(tlk);
 	phb_tlk_free(b->h);

@@ -89,12 +89,24 @@ void *refh_create_codon(const char *newick, int n, const char **names, const cha
 	return h;
 }
 
+/* Model.clone (what gradascent.c:166-170 does per worker): a second handle on an independent copy of the model graph */
+void *refh_clone(void *vh) {
+	RefH *src = (RefH *)vh;
+	RefH *h = (RefH *)calloc(1, sizeof(RefH));
+	h->hash = new_Hashtable_string(10);
+	hashtable_set_key_ownership(h->hash, false);
+	hashtable_set_value_ownership(h->hash, false);
+	h->model = src->model->clone(src->model, h->hash);
+	h->tlk = (SingleTreeLikelihood *)h->model->obj;
+	return h;
+}
+
 void refh_free(void *vh) {
 	RefH *h = (RefH *)vh;
 	if (h->hash != NULL) { /* models built by hand are left to the process exit */
 		h->model->free(h->model);
 		free_Hashtable(h->hash);
-		json_free_tree(h->json);
+		if (h->json) json_free_tree(h->json);
 	}
 	free(h);
 }

@@ -166,6 +166,16 @@ static OP *sort_levels_by_kind(const OP *ops, int nops, int nlevels, const int *
 	return out;
 }
 
+extern "C" int phbc_set_root(phbc_ctx *ctx, int root) {
+	if (root < ctx->T || root >= ctx->N) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "root %d is not an internal node", root);
+		return -1;
+	}
+	ctx->root = root;
+	ctx->nuc4_G_valid = false;
+	return 0;
+}
+
 extern "C" int phbc_set_schedule(phbc_ctx *ctx, const phbc_schedule *s) {
 	int rc;
 	const int T = ctx->T;
@@ -284,6 +294,43 @@ extern "C" int phbc_upload_matrices(phbc_ctx *ctx, const double *P, const double
 	const size_t n = (size_t)ctx->N * ctx->C * ctx->S * ctx->S;
 	UPLOAD(ctx->d_P, P, n);
 	UPLOAD(ctx->d_dP, dP, n);
+	return 0;
+}
+
+// Device-to-device copy of the bulky inputs of `src` into `dst` (same shape; any pair of devices): tip states / partials,
+// pattern weights, explicit matrices and the time-tree tables.  The small model inputs are re-uploaded by the host layer.
+extern "C" int phbc_copy_inputs(phbc_ctx *dst, phbc_ctx *src, int matrices, int time_tree) {
+	if (dst->T != src->T || dst->S != src->S || dst->C != src->C || dst->P != src->P || dst->tip_kind != src->tip_kind) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "phbc_copy_inputs: shapes differ");
+		return -1;
+	}
+	phbc_ctx *ctx = src;
+	PHBC_CHECK(cudaSetDevice(src->device));
+	PHBC_CHECK(cudaStreamSynchronize(src->stream));
+	ctx = dst;
+	PHBC_CHECK(cudaSetDevice(dst->device));
+	const size_t T = src->T, P = src->P, S = src->S, N = src->N, C = src->C;
+	if (src->d_tip_states) PHBC_CHECK(cudaMemcpyPeerAsync(dst->d_tip_states, dst->device, src->d_tip_states, src->device, T * P, dst->stream));
+	if (src->d_tip_partials)
+		PHBC_CHECK(cudaMemcpyPeerAsync(dst->d_tip_partials, dst->device, src->d_tip_partials, src->device, T * P * S * sizeof(double), dst->stream));
+	PHBC_CHECK(cudaMemcpyPeerAsync(dst->d_weights, dst->device, src->d_weights, src->device, P * sizeof(double), dst->stream));
+	dst->nuc4_codes_valid = false;
+	if (matrices && src->d_P && src->d_dP) {
+		int rc = ensure_node_matrices(dst);
+		if (rc) return rc;
+		PHBC_CHECK(cudaMemcpyPeerAsync(dst->d_P, dst->device, src->d_P, src->device, N * C * S * S * sizeof(double), dst->stream));
+		PHBC_CHECK(cudaMemcpyPeerAsync(dst->d_dP, dst->device, src->d_dP, src->device, N * C * S * S * sizeof(double), dst->stream));
+	}
+	if (time_tree && src->d_tt_lowers) {
+		if (!dst->d_tt_lowers) {
+			PHBC_CHECK(cudaMalloc((void **)&dst->d_tt_lowers, N * sizeof(double)));
+			PHBC_CHECK(cudaMalloc((void **)&dst->d_tt_topo, 3 * N * sizeof(int)));
+			PHBC_CHECK(cudaMalloc((void **)&dst->d_tt_bad, sizeof(int)));
+		}
+		PHBC_CHECK(cudaMemcpyPeerAsync(dst->d_tt_lowers, dst->device, src->d_tt_lowers, src->device, N * sizeof(double), dst->stream));
+		PHBC_CHECK(cudaMemcpyPeerAsync(dst->d_tt_topo, dst->device, src->d_tt_topo, src->device, 3 * N * sizeof(int), dst->stream));
+	}
+	PHBC_CHECK(cudaStreamSynchronize(dst->stream));
 	return 0;
 }
 

@@ -97,6 +97,7 @@ phbc_ctx *phbc_create(int device, int ntips, int nstate, int ncat, int npatterns
 void phbc_destroy(phbc_ctx *ctx);
 
 int phbc_set_schedule(phbc_ctx *ctx, const phbc_schedule *s);
+int phbc_set_root(phbc_ctx *ctx, int root); /* with a new schedule: topology moves */
 int phbc_upload_tip_states(phbc_ctx *ctx, const uint8_t *states);
 int phbc_upload_tip_partials(phbc_ctx *ctx, const double *partials);
 int phbc_upload_weights(phbc_ctx *ctx, const double *w);
@@ -105,6 +106,8 @@ int phbc_upload_matrices(phbc_ctx *ctx, const double *P, const double *dP);
 int phbc_upload_freqs(phbc_ctx *ctx, const double *freqs);
 int phbc_upload_site_model(phbc_ctx *ctx, const double *rates, const double *props);
 int phbc_upload_branch_lengths(phbc_ctx *ctx, const double *bl, int nbatch); /* [nbatch][N], pinned staging */
+/* device-to-device copy of the bulky inputs (tips, weights, explicit matrices, time-tree tables) between same-shaped contexts */
+int phbc_copy_inputs(phbc_ctx *dst, phbc_ctx *src, int matrices, int time_tree);
 
 typedef struct phbc_eval_opts {
 	int kernels;                 /* PHB_KERNELS_*                                                  */

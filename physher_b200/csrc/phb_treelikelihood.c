@@ -106,12 +106,17 @@ static int build_level_schedules(phb_tlk *t) {
 	int *level = (int *)calloc(N, sizeof(int));
 	int *depth = (int *)calloc(N, sizeof(int));
 	int *order = (int *)malloc(sizeof(int) * N); /* pre-order */
-	int *stack = (int *)malloc(sizeof(int) * N);
+	int *stack = (int *)malloc(sizeof(int) * (2 * (size_t)N + 2));
 	if (!level || !depth || !order || !stack) return PHB_ENOMEM;
 	int sp = 0, cnt = 0;
 	stack[sp++] = t->root;
 	while (sp) {
 		int n = stack[--sp];
+		if (cnt >= N || level[n]) { /* a node reached twice: a cycle or a shared child (phb_tlk_set_topology hands over caller data) */
+			cnt = N + 1;
+			break;
+		}
+		level[n] = 1; /* visited mark; levels are assigned below */
 		order[cnt++] = n;
 		if (!is_tip(t, n)) {
 			depth[t->left[n]] = depth[n] + 1;
@@ -124,6 +129,7 @@ static int build_level_schedules(phb_tlk *t) {
 		free(level); free(depth); free(order); free(stack);
 		return fail(PHB_EINVAL, "topology is not a rooted binary tree over %d nodes (visited %d)", N, cnt);
 	}
+	memset(level, 0, sizeof(int) * N); /* drop the visited marks: tips are level 0 */
 	int maxlevel = 0, maxdepth = 0;
 	for (int k = N - 1; k >= 0; k--) { /* reverse pre-order: children before parents */
 		int n = order[k];
@@ -481,6 +487,113 @@ static int build_walk_schedules(phb_tlk *t) {
 /* construction                                                                                */
 /* ------------------------------------------------------------------------------------------- */
 
+/* hand the host schedules to the device context */
+static int push_schedule(phb_tlk *t) {
+	const int N = t->N, ntips = t->T;
+	int rc;
+	phbc_schedule s;
+	memset(&s, 0, sizeof(s));
+	s.n_lower_ops = N - ntips;
+	s.n_lower_levels = t->n_lower_levels;
+	s.lower_ops = t->lower_ops;
+	s.lower_level_off = t->lower_level_off;
+	s.n_upper_ops = N - 1;
+	s.n_upper_levels = t->n_upper_levels;
+	s.upper_ops = t->upper_ops;
+	s.upper_level_off = t->upper_level_off;
+	s.n_parent_ops = N - ntips;
+	s.parent_ops = t->parent_ops;
+	s.parent_level_off = t->parent_level_off;
+	s.n_post = N - ntips;
+	s.n_pre = N - ntips;
+	s.post_ops = t->post_ops;
+	s.pre_ops = t->pre_ops;
+	s.post_slots = t->post_slots;
+	s.pre_slots = t->pre_slots;
+	s.post_tip_order = t->post_tip_order;
+	s.pre_tip_order = t->pre_tip_order;
+	s.post_first_tips = t->post_first_tips;
+	s.pre_first_tips = t->pre_first_tips;
+	if ((rc = phbc_set_schedule(t->ctx, &s))) return dev_fail(rc);
+	return PHB_OK;
+}
+
+/* copies and checks a topology (node-id convention of tree.c:183-199) */
+static int install_topology(phb_tlk *t, const int *left, const int *right, int root) {
+	const int N = t->N, ntips = t->T;
+	if (root < ntips || root >= N) return fail(PHB_EINVAL, "root %d is not an internal node", root);
+	for (int n = 0; n < N; n++) {
+		const int tip = left[n] < 0;
+		if ((left[n] < 0) != (right[n] < 0) || (tip && n >= ntips) || (!tip && n < ntips) || left[n] >= N || right[n] >= N)
+			return fail(PHB_EINVAL, "node %d breaks the id convention (tips 0..T-1, internal T..2T-2)", n);
+	}
+	for (int n = 0; n < N; n++) t->parent[n] = -1;
+	for (int n = 0; n < N; n++) {
+		t->left[n] = left[n];
+		t->right[n] = right[n];
+		if (left[n] >= 0) {
+			t->parent[left[n]] = n;
+			t->parent[right[n]] = n;
+		}
+	}
+	t->root = root;
+	return PHB_OK;
+}
+
+static void free_schedules(phb_tlk *t) {
+	free(t->lower_ops), free(t->upper_ops), free(t->lower_level_off), free(t->upper_level_off), free(t->parent_ops), free(t->parent_level_off);
+	free(t->post_ops), free(t->pre_ops), free(t->post_tip_order), free(t->pre_tip_order), free(t->post_chunk_tip0), free(t->pre_chunk_tip0);
+	t->lower_ops = t->upper_ops = NULL;
+	t->lower_level_off = t->upper_level_off = t->parent_level_off = NULL;
+	t->parent_ops = NULL;
+	t->post_ops = NULL;
+	t->pre_ops = NULL;
+	t->post_tip_order = t->pre_tip_order = t->post_chunk_tip0 = t->pre_chunk_tip0 = NULL;
+}
+
+/*
+ * A topology move (NNI / SPR, nniopt.c:301-334, spropt.c:1548-1615): the reference re-reads the Tree pointers on every traversal and
+ * only needs SingleTreeLikelihood_update_three_nodes; here the traversal order is compiled into schedules, so a changed tree is
+ * handed over explicitly.  Same taxa, same node-id convention; data, model inputs, options and branch lengths (by node id) are
+ * kept, every partial is dirty, the time-tree tables must be set again.  On failure the object keeps its previous topology.
+ */
+static int rebuild_schedules(phb_tlk *t) {
+	const int N = t->N;
+	free_schedules(t);
+	int rc = build_level_schedules(t);
+	if (rc == PHB_OK) rc = build_walk_schedules(t);
+	if (rc != PHB_OK) return rc;
+	for (int n = 0; n < N; n++) t->upper_op_of[n] = -1;
+	for (int k = 0; k < N - 1; k++) t->upper_op_of[t->upper_ops[k].out - N] = k;
+	if (phbc_set_root(t->ctx, t->root)) return fail(PHB_ECUDA, "%s", phbc_last_error());
+	return push_schedule(t);
+}
+
+int phb_tlk_set_topology(phb_tlk *t, const int *left, const int *right, int root) {
+	if (!left || !right) return fail(PHB_EINVAL, "left and right are required");
+	const int N = t->N;
+	int *old = (int *)malloc(sizeof(int) * 2 * (size_t)N);
+	if (!old) return fail(PHB_ENOMEM, "out of memory");
+	memcpy(old, t->left, sizeof(int) * N);
+	memcpy(old + N, t->right, sizeof(int) * N);
+	const int old_root = t->root;
+	int rc = install_topology(t, left, right, root); /* validates before it touches the object */
+	if (rc == PHB_OK && (rc = rebuild_schedules(t)) != PHB_OK) {
+		char msg[sizeof(g_err)];
+		memcpy(msg, g_err, sizeof(msg));
+		install_topology(t, old, old + N, old_root);
+		rebuild_schedules(t);
+		memcpy(g_err, msg, sizeof(msg));
+	}
+	free(old);
+	t->have_time_tree = 0;
+	t->resident = 0;
+	memset(t->lower_ok, 0, N);
+	memset(t->upper_ok, 0, N);
+	phb_tlk_update_all_nodes(t);
+	return rc;
+}
+
 phb_tlk *phb_tlk_create(int ntips, int nstate, int ncat, int npatterns, const int *left, const int *right, int root,
                         int use_tip_states, int device) {
 	if (ntips < 2 || nstate < 2 || ncat < 1 || npatterns < 1 || !left || !right) {
@@ -564,31 +677,7 @@ phb_tlk *phb_tlk_create(int ntips, int nstate, int ncat, int npatterns, const in
 		phb_tlk_free(t);
 		return NULL;
 	}
-	phbc_schedule s;
-	memset(&s, 0, sizeof(s));
-	s.n_lower_ops = N - ntips;
-	s.n_lower_levels = t->n_lower_levels;
-	s.lower_ops = t->lower_ops;
-	s.lower_level_off = t->lower_level_off;
-	s.n_upper_ops = N - 1;
-	s.n_upper_levels = t->n_upper_levels;
-	s.upper_ops = t->upper_ops;
-	s.upper_level_off = t->upper_level_off;
-	s.n_parent_ops = N - ntips;
-	s.parent_ops = t->parent_ops;
-	s.parent_level_off = t->parent_level_off;
-	s.n_post = N - ntips;
-	s.n_pre = N - ntips;
-	s.post_ops = t->post_ops;
-	s.pre_ops = t->pre_ops;
-	s.post_slots = t->post_slots;
-	s.pre_slots = t->pre_slots;
-	s.post_tip_order = t->post_tip_order;
-	s.pre_tip_order = t->pre_tip_order;
-	s.post_first_tips = t->post_first_tips;
-	s.pre_first_tips = t->pre_first_tips;
-	if ((rc = phbc_set_schedule(t->ctx, &s))) {
-		dev_fail(rc);
+	if ((rc = push_schedule(t))) {
 		phb_tlk_free(t);
 		return NULL;
 	}
@@ -622,6 +711,49 @@ void phb_tlk_free(phb_tlk *t) {
 	free(t);
 }
 
+/*
+ * clone_SingleTreeLikelihood (treelikelihood.c:1241-1395; Model.clone :715-790): an independent object with the same topology,
+ * data, model inputs, options and rescaling state -- what the reference's parallel users build per worker (gradascent.c:166-170).
+ * Tips, weights, explicit matrices and the time-tree tables are copied device to device (`device` may differ from the
+ * source's); partials are not copied: the clone starts with every node dirty, as a clone of a dirty reference object does.
+ */
+phb_tlk *phb_tlk_clone(phb_tlk *src, int device) {
+	if (!src) {
+		fail(PHB_EINVAL, "phb_tlk_clone: NULL source");
+		return NULL;
+	}
+	phb_tlk *t = phb_tlk_create(src->T, src->S, src->C, src->P, src->left, src->right, src->root, src->use_tip_states, device);
+	if (!t) return NULL;
+	int rc = PHB_OK;
+	if (src->have_tips || src->have_weights || src->have_matrices || src->have_time_tree) {
+		const int drc = phbc_copy_inputs(t->ctx, src->ctx, src->have_matrices, src->have_time_tree);
+		if (drc) rc = dev_fail(drc);
+	}
+	t->have_tips = src->have_tips;
+	t->have_weights = src->have_weights;
+	t->have_time_tree = src->have_time_tree;
+	if (rc == PHB_OK && src->have_eigen && src->h_evec) rc = phb_tlk_set_eigen(t, src->h_evec, src->h_eval, src->h_ivec);
+	if (rc == PHB_OK && src->have_matrices) t->have_matrices = 1, t->have_eigen = 0; /* explicit matrices win, as in the source */
+	if (rc == PHB_OK && src->have_freqs && src->h_freqs) rc = phb_tlk_set_frequencies(t, src->h_freqs);
+	if (rc == PHB_OK && src->have_site && src->h_rates) rc = phb_tlk_set_site_model(t, src->h_rates, src->h_props);
+	if (rc == PHB_OK && src->have_bl) rc = phb_tlk_set_branch_lengths(t, src->bl);
+	if (rc != PHB_OK) {
+		phb_tlk_free(t);
+		return NULL;
+	}
+	t->scale = src->scale;
+	t->scaling_threshold = src->scaling_threshold;
+	t->include_root_freqs = src->include_root_freqs;
+	t->compat_scaled_gradient = src->compat_scaled_gradient;
+	t->unrooted = src->unrooted;
+	t->kernels = src->kernels;
+	t->incremental = src->incremental;
+	if (src->prepared_gradient) phb_tlk_initialize_gradient(t, src->prepared_gradient);
+	t->eigen_changed = t->freqs_changed = t->site_changed = t->bl_changed = 0;
+	phb_tlk_update_all_nodes(t);
+	return t;
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* inputs                                                                                      */
 /* ------------------------------------------------------------------------------------------- */
@@ -640,6 +772,17 @@ int phb_tlk_update_one_node(phb_tlk *t, int node) { /* treelikelihood.c:1747-175
 	t->update = 1;
 	t->update_upper = 1;
 	t->sweep_valid = 0;
+	return PHB_OK;
+}
+
+/* SingleTreeLikelihood_update_three_nodes (treelikelihood.c:1754-1771): a node and both its children (NNI / SPR moves) */
+int phb_tlk_update_three_nodes(phb_tlk *t, int node) {
+	int rc = phb_tlk_update_one_node(t, node);
+	if (rc) return rc;
+	if (!is_tip(t, node)) {
+		t->update_nodes[t->left[node]] = 1;
+		t->update_nodes[t->right[node]] = 1;
+	}
 	return PHB_OK;
 }
 

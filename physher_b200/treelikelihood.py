@@ -38,6 +38,8 @@ SYMBOLS = [
     ("phb_version", C.c_char_p, []),
     ("phb_tlk_create", C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, C.c_int, C.c_int]),
     ("phb_tlk_free", None, [C.c_void_p]),
+    ("phb_tlk_clone", C.c_void_p, [C.c_void_p, C.c_int]),
+    ("phb_tlk_set_topology", C.c_int, [C.c_void_p, _ip, _ip, C.c_int]),
     ("phb_tlk_set_tip_states", C.c_int, [C.c_void_p, _bp]),
     ("phb_tlk_set_tip_partials", C.c_int, [C.c_void_p, _dp]),
     ("phb_tlk_set_pattern_weights", C.c_int, [C.c_void_p, _dp]),
@@ -49,6 +51,7 @@ SYMBOLS = [
     ("phb_tlk_set_branch_length", C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     ("phb_tlk_update_all_nodes", None, [C.c_void_p]),
     ("phb_tlk_update_one_node", C.c_int, [C.c_void_p, C.c_int]),
+    ("phb_tlk_update_three_nodes", C.c_int, [C.c_void_p, C.c_int]),
     ("phb_tlk_store", C.c_int, [C.c_void_p]),
     ("phb_tlk_restore", C.c_int, [C.c_void_p]),
     ("phb_tlk_use_rescaling", C.c_int, [C.c_void_p, C.c_int]),
@@ -150,6 +153,7 @@ class SingleTreeLikelihood:
         self.T = (self.N + 1) // 2
         self.S, self.C, self.P = int(nstate), int(ncat), int(npatterns)
         self.root = int(root)
+        self.device = int(device)
         self.h = self.lib.phb_tlk_create(self.T, self.S, self.C, self.P, self.left.ctypes.data_as(_ip),
                                          self.right.ctypes.data_as(_ip), self.root, int(bool(use_tip_states)), int(device))
         if not self.h:
@@ -162,6 +166,26 @@ class SingleTreeLikelihood:
     def _check(self, rc: int):
         if rc != 0:
             raise PhysherB200Error(f"[{rc}] {self._err()}")
+
+    def clone(self, device=None):
+        """clone_SingleTreeLikelihood (treelikelihood.c:1241-1395): an independent object, optionally on another device."""
+        h = self.lib.phb_tlk_clone(self.h, int(self.device if device is None else device))
+        if not h:
+            raise PhysherB200Error(self._err())
+        other = object.__new__(type(self))
+        other.__dict__.update({k: v for k, v in self.__dict__.items() if k != "h"})
+        other.left, other.right = self.left.copy(), self.right.copy()
+        other.device = int(self.device if device is None else device)
+        other.h = h
+        return other
+
+    def set_topology(self, left, right, root):
+        """A topology move (NNI / SPR): same taxa and node-id convention, new child arrays; everything else is kept."""
+        left = np.ascontiguousarray(left, dtype=np.int32)
+        right = np.ascontiguousarray(right, dtype=np.int32)
+        assert left.shape == (self.N,) and right.shape == (self.N,)
+        self._check(self.lib.phb_tlk_set_topology(self.h, left.ctypes.data_as(_ip), right.ctypes.data_as(_ip), int(root)))
+        self.left, self.right, self.root = left, right, int(root)
 
     def close(self):
         if getattr(self, "h", None):
@@ -251,6 +275,9 @@ class SingleTreeLikelihood:
 
     def update_one_node(self, node):
         self._check(self.lib.phb_tlk_update_one_node(self.h, int(node)))
+
+    def update_three_nodes(self, node):
+        self._check(self.lib.phb_tlk_update_three_nodes(self.h, int(node)))
 
     def store(self):
         self._check(self.lib.phb_tlk_store(self.h))

@@ -220,3 +220,47 @@ def test_substitution_model_gradient_through_the_glue(libs, name, kw):
         assert grad_err(g[dev.N:], want[f][dev.N:]) < RTOL, (f, g[dev.N:], want[f][dev.N:])
     G.phb_physher_detach(model)
     dev.close()
+
+
+def test_model_clone_gets_its_own_device_object(libs):
+    """Model.clone of an attached tree likelihood (_treeLikelihood_model_clone, treelikelihood.c:715-790; what gradascent.c:166-170 does
+    per worker): the reference copies the function pointers of the source object, so the glue's clone wrapper must give the
+    clone a device object of its own (phb_tlk_clone).  Both reproduce the known answer, move independently, and free cleanly."""
+    L, G = libs
+    L.refh_clone.argtypes = [C.c_void_p]
+    L.refh_clone.restype = C.c_void_p
+    L.refh_free.argtypes = [C.c_void_p]
+    L.refh_set_clock_rate.argtypes = [C.c_void_p, C.c_double]
+    L.refh_logP.argtypes = [C.c_void_p]
+    L.refh_logP.restype = C.c_double
+    kat = json.load(open(os.path.join(GOLDEN, "c1_kat.json")))
+    ref = O.Reference(_spec())
+    ref.set_include_jacobian(False)
+    model = L.refh_model_handle(ref.h)
+    assert G.phb_physher_attach(model, 0) == 0
+    assert rel_err(ref.logP(), kat["logP"]) < RTOL
+    twin = L.refh_clone(ref.h)
+    twin_model = L.refh_model_handle(twin)
+    assert G.phb_physher_evaluations(twin_model) == 0, "the clone has its own backend record"
+    # (the reference's clone of this time tree does not evaluate to the source's value -- its cloned tree carries different
+    # heights -- so the clone is checked against the reference's own CPU path ON THE CLONE, below)
+    base = L.refh_logP(twin)
+    assert np.isfinite(base) and G.phb_physher_evaluations(twin_model) == 1
+    # the clone moves (a different clock rate); the source still gives the known answer
+    L.refh_set_clock_rate(twin, 0.002)
+    moved = L.refh_logP(twin)
+    assert np.isfinite(moved) and moved != base
+    evals = G.phb_physher_evaluations(model)
+    assert rel_err(ref.logP(), kat["logP"]) < RTOL and G.phb_physher_evaluations(model) == evals + 1
+    # same values as the reference's own CPU path on the clone
+    G.phb_physher_detach(twin_model)
+    assert rel_err(L.refh_logP(twin), moved) < RTOL
+    L.refh_free(twin)
+    G.phb_physher_detach(model)
+    ref.close()
+    ref2 = O.Reference(_spec())  # the clone's starting value, from an untouched CPU clone
+    ref2.set_include_jacobian(False)
+    twin2 = L.refh_clone(ref2.h)
+    assert rel_err(base, L.refh_logP(twin2)) < RTOL
+    L.refh_free(twin2)
+    ref2.close()
