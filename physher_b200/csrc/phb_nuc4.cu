@@ -445,36 +445,31 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 					if (kind != 0) row_load(row_cell + (size_t)(unsigned)d->b_row * NUC4_ROW_BYTES + u * PBT * 16, B[u]);
 				}
 			};
-			// One op. Operands (lower rows of the children) are in xa / xb; as soon as they have been consumed the
-			// same registers receive the NEXT op's rows, a full op ahead of their use.  Returns the two gradient terms.
+			// One op.  Its operands (message rows of the internal children) were loaded into xa / xb by the PREVIOUS op.  ALT: the first
+			// thing this op does is to issue the loads of the NEXT op's rows into the other register set (na / nb), a full op ahead
+			// of their use -- the two sets alternate between consecutive ops, no copies, and nothing tempts ptxas to sink the loads
+			// towards their consumer.  The statistics variant (GRAD = 2) has no registers to spare for a second set: it copies its
+			// operands out and refills the same set (na / nb alias xa / xb).  Returns the two gradient terms.
+			constexpr bool ALT = GRAD != 2;
 			auto pre_op = [&](const phbc_pre_op *desc, const unsigned char *mats, const uint8_t *cds, int j, int cnt, bool more_chunks,
-			                  double (&xa)[PPT][4], double (&xb)[PPT][4], double (&ureg)[PPT][4], double &va, double &vb) {
+			                  double (&xa)[PPT][4], double (&xb)[PPT][4], double (&na_)[PPT][4], double (&nb_)[PPT][4], double (&ureg)[PPT][4],
+			                  double &va, double &vb) {
 				const phbc_pre_op *d = desc + j;
 				const int kind = d->kind;
+				auto prefetch = [&]() {
+					if (j + 1 < cnt) {
+						fetch(d + 1, na_, nb_);
+					} else if (more_chunks) {
+						mbar_wait(&bars[(loads + 1) & 1], ((loads + 1) >> 1) & 1);
+						fetch(reinterpret_cast<const phbc_pre_op *>(stage0 + ((loads + 1) & 1) * lay.bytes + lay.desc_off), na_, nb_);
+					}
+				};
 				const double *MP = reinterpret_cast<const double *>(mats + (j * 3 + 0) * C * 128);
 				const double *MA = reinterpret_cast<const double *>(mats + (j * 3 + 1) * C * 128);
 				const double *MB = reinterpret_cast<const double *>(mats + (j * 3 + 2) * C * 128);
-				double W[PPT][4], ma[PPT][4], mb[PPT][4];
-				// messages P_x L_x of the children: stored rows for internal children, matrix columns for tips
-#pragma unroll
-				for (int u = 0; u < PPT; u++) {
-					if (kind == 2) {
-#pragma unroll
-						for (int i = 0; i < 4; i++) ma[u][i] = xa[u][i];
-					} else tip_message(MA, cds[d->a_code * PB + u * PBT], ma[u]);
-					if (kind == 0) tip_message(MB, cds[d->b_code * PB + u * PBT], mb[u]);
-					else {
-#pragma unroll
-						for (int i = 0; i < 4; i++) mb[u][i] = xb[u][i];
-					}
-				}
-				// xa / xb are dead: prefetch the next op's rows into them (across the chunk boundary too)
-				if (j + 1 < cnt) {
-					fetch(d + 1, xa, xb);
-				} else if (more_chunks) {
-					mbar_wait(&bars[(loads + 1) & 1], ((loads + 1) >> 1) & 1);
-					fetch(reinterpret_cast<const phbc_pre_op *>(stage0 + ((loads + 1) & 1) * lay.bytes + lay.desc_off), xa, xb);
-				}
+				// the op proper, on the messages P_x L_x of the children (ma, mb)
+				auto body = [&](double (&ma)[PPT][4], double (&mb)[PPT][4]) {
+				double W[PPT][4];
 				if (d->u_kind == PHBC_W_ROOT) {
 					// children of the root: u = P_s L_s [o pi] (treelikelihood.c:2145-2154)
 #pragma unroll
@@ -588,14 +583,42 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 						for (int i = 0; i < 4; i++) ureg[u][i] = ub[u][i];  // child b's op is the next one
 					}
 				}
+				};
+				// messages of the children: the prefetched rows for internal children, matrix columns (or column sums) for tips
+				if (ALT) {
+					prefetch();
+#pragma unroll
+					for (int u = 0; u < PPT; u++) {
+						if (kind != 2) tip_message(MA, cds[d->a_code * PB + u * PBT], xa[u]);
+						if (kind == 0) tip_message(MB, cds[d->b_code * PB + u * PBT], xb[u]);
+					}
+					body(xa, xb);
+				} else {
+					double la[PPT][4], lb[PPT][4];
+#pragma unroll
+					for (int u = 0; u < PPT; u++) {
+						if (kind == 2) {
+#pragma unroll
+							for (int i = 0; i < 4; i++) la[u][i] = xa[u][i];
+						} else tip_message(MA, cds[d->a_code * PB + u * PBT], la[u]);
+						if (kind == 0) tip_message(MB, cds[d->b_code * PB + u * PBT], lb[u]);
+						else {
+#pragma unroll
+							for (int i = 0; i < 4; i++) lb[u][i] = xb[u][i];
+						}
+					}
+					prefetch();
+					body(la, lb);
+				}
 			};
 			if (tid == 0) issue(0, loads, prm.pre_first_tips);
 			mbar_wait(&bars[loads & 1], (loads >> 1) & 1);
-			double xa[PPT][4], xb[PPT][4], ureg[PPT][4];
+			static_assert(NUC4_CHUNK % 2 == 0, "the two operand register sets alternate in pairs of ops");
+			double xa[PPT][4], xb[PPT][4], ya[PPT][4], yb[PPT][4], ureg[PPT][4];
 #pragma unroll
 			for (int u = 0; u < PPT; u++)
 #pragma unroll
-				for (int i = 0; i < 4; i++) xa[u][i] = xb[u][i] = ureg[u][i] = 0.0;
+				for (int i = 0; i < 4; i++) xa[u][i] = xb[u][i] = ya[u][i] = yb[u][i] = ureg[u][i] = 0.0;
 			fetch(reinterpret_cast<const phbc_pre_op *>(stage0 + (loads & 1) * lay.bytes + lay.desc_off), xa, xb);
 			for (int ch = 0; ch < nchunks; ch++) {
 				const unsigned char *st = stage0 + (loads & 1) * lay.bytes;
@@ -610,9 +633,11 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 				for (int j = 0; j < cnt; j += 2) {
 					// two ops (four branches) share one warp butterfly; partial sums go to warp-private rows
 					double v0, v1, v2 = 0.0, v3 = 0.0;
-					pre_op(desc, mats, cds, j, cnt, more, xa, xb, ureg, v0, v1);
+					if (ALT) pre_op(desc, mats, cds, j, cnt, more, xa, xb, ya, yb, ureg, v0, v1);
+					else pre_op(desc, mats, cds, j, cnt, more, xa, xb, xa, xb, ureg, v0, v1);
 					if (j + 1 < cnt) {
-						pre_op(desc, mats, cds, j + 1, cnt, more, xa, xb, ureg, v2, v3);
+						if (ALT) pre_op(desc, mats, cds, j + 1, cnt, more, ya, yb, xa, xb, ureg, v2, v3);
+						else pre_op(desc, mats, cds, j + 1, cnt, more, xa, xb, xa, xb, ureg, v2, v3);
 						const double r = butterfly4(v0, v1, v2, v3, lane);
 						if ((lane & 7) == 0) {
 							const phbc_pre_op *d = desc + j + ((lane >> 3) & 1);
