@@ -52,16 +52,19 @@ typedef struct phbc_post_op { /* one internal node, DFS post-order; 32 bytes (TM
 	int next_tips;           /* first op of a chunk: (first tip index << 5 | tip count) of the NEXT chunk */
 } phbc_post_op;
 
+#define PHBC_PF_DIST 3 /* L2 prefetch distance of the pre-order walk, in ops */
 typedef struct phbc_pre_op { /* one internal node acting as parent, DFS pre-order; 48 bytes         */
-	int16_t u_kind;          /* PHBC_W_SLOT or PHBC_W_ROOT                                        */
+	int16_t u_kind;          /* PHBC_W_SLOT, PHBC_W_REG or PHBC_W_ROOT                            */
 	int16_t kind;            /* 0 tip-tip, 1 tip-internal (the tip is child a), 2 internal-internal */
 	int next_tips;           /* as in phbc_post_op                                                */
-	int u_slot;              /* slot holding U_parent                                             */
+	int16_t u_slot;          /* slot holding U_parent                                             */
+	int16_t a_slot, b_slot;  /* slots receiving U_a / U_b for internal children (-1: not kept)    */
+	int16_t a_code, b_code;  /* chunk-local index of a tip child's code row                       */
+	int16_t pad_;
 	int node;                /* parent node id (matrix P_node when not the root)                  */
 	int a_node, b_node;      /* children node ids                                                 */
-	int a_slot, b_slot;      /* slots receiving U_a / U_b for internal children (-1: not kept)    */
 	int a_row, b_row;        /* lower-scratch rows (post-order op index) of internal children     */
-	int a_code, b_code;      /* chunk-local index of a tip child's code row                       */
+	int pf_a_row, pf_b_row;  /* a_row / b_row of the op PHBC_PF_DIST positions later (-1: none): L2 prefetch targets */
 } phbc_pre_op;
 
 /* One pre-order op of the tensor-core kernels: internal node `node` with children a, b.  The kernel turns

@@ -36,6 +36,9 @@
 
 #define NUC4_CHUNK PHBC_WALK_CHUNK  // ops per TMA chunk
 #define NUC4_NT 256   // threads per CTA
+#ifndef NUC4_L2PF
+#define NUC4_L2PF 1    // L2 prefetch hints two pre-order ops ahead
+#endif
 
 struct Nuc4Params {
 	int T, N, C, P, PB, root;
@@ -241,6 +244,12 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 	unsigned char *row_cell = GRAD ? reinterpret_cast<unsigned char *>(prm.lower) + (size_t)blockIdx.x * prm.n_post * NUC4_ROW_BYTES + cell0 * 16 : nullptr;
 	double *my_gacc = nullptr;
 	double *my_gstat = GRAD == 2 ? prm.gstat + ((size_t)blockIdx.x * (NTHR / 32) + warp) * prm.N * 16 : nullptr;  // single sample only
+
+	// L2 prefetch lanes of the pre-order pass (see pre_op): lane -> (row a | b, plane, half, 128-byte line)
+	constexpr int PF_LPR = PPT * 2 * 4;  // lines per message row and warp
+	const int pf_row = (lane / PF_LPR) & 1, pf_q = lane % PF_LPR;
+	const bool pf_on = GRAD && lane < 2 * PF_LPR;
+	const unsigned char *pf_base = GRAD ? row_cell - lane * 16 + ((pf_q >> 3) * PBT) * 16 + ((pf_q >> 2) & 1) * (NUC4_NT * 16) + (pf_q & 3) * 128 : nullptr;
 
 	// work items = (sample, pattern tile), sample-major; a CTA owns a CONTIGUOUS range, so it touches at most
 	// prm.phases consecutive samples and keeps one private accumulator row set per touched sample (deterministic sums)
@@ -451,6 +460,7 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 			// towards their consumer.  The statistics variant (GRAD = 2) has no registers to spare for a second set: it copies its
 			// operands out and refills the same set (na / nb alias xa / xb).  Returns the two gradient terms.
 			constexpr bool ALT = GRAD != 2;
+			constexpr bool L2PF = NUC4_L2PF && GRAD != 2;  // the statistics variant is issue-bound: the hints cost it more than they return
 			auto pre_op = [&](const phbc_pre_op *desc, const unsigned char *mats, const uint8_t *cds, int j, int cnt, bool more_chunks,
 			                  double (&xa)[PPT][4], double (&xb)[PPT][4], double (&na_)[PPT][4], double (&nb_)[PPT][4], double (&ureg)[PPT][4],
 			                  double &va, double &vb) {
@@ -464,6 +474,14 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 						fetch(reinterpret_cast<const phbc_pre_op *>(stage0 + ((loads + 1) & 1) * lay.bytes + lay.desc_off), na_, nb_);
 					}
 				};
+				if (L2PF) {
+					// the rows the op PHBC_PF_DIST positions later will read go to L2 now (the host put their indices into THIS op's
+					// descriptor): the register prefetch above is one op -- about the loaded HBM latency -- ahead of its use, the hint
+					// turns that load into an L2 hit.  One instruction per warp: lane l takes one 128-byte line of the warp's share
+					// (2 rows x PPT planes x 2 halves x 512 bytes).
+					const int r = reinterpret_cast<const int *>(&d->pf_a_row)[pf_row];
+					if (pf_on && r >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + (size_t)(unsigned)r * NUC4_ROW_BYTES));
+				}
 				const double *MP = reinterpret_cast<const double *>(mats + (j * 3 + 0) * C * 128);
 				const double *MA = reinterpret_cast<const double *>(mats + (j * 3 + 1) * C * 128);
 				const double *MB = reinterpret_cast<const double *>(mats + (j * 3 + 2) * C * 128);

@@ -402,13 +402,14 @@ static int build_walk_schedules(phb_tlk *t) {
 		op->kind = (int16_t)((a_tip ? 0 : 1) + (b_tip ? 0 : 1));
 		op->next_tips = 0;
 		op->u_slot = -1;
+		op->pf_a_row = op->pf_b_row = -1;
 		if (n == t->root) {
 			op->u_kind = PHBC_W_ROOT;
 		} else if (n == prev) {
 			op->u_kind = PHBC_W_REG; /* U_n is still in the registers of the preceding op */
 		} else {
 			op->u_kind = PHBC_W_SLOT;
-			op->u_slot = slot_of[n];
+			op->u_slot = (int16_t)slot_of[n];
 			pool.used[slot_of[n]] = 0;
 		}
 		op->a_slot = op->b_slot = -1;
@@ -416,7 +417,8 @@ static int build_walk_schedules(phb_tlk *t) {
 		op->a_row = a_tip ? -1 : row_of[a];
 		op->b_row = b_tip ? -1 : row_of[b];
 		if (op->kind == 2) {
-			slot_of[a] = op->a_slot = slot_alloc(&pool);
+			slot_of[a] = slot_alloc(&pool);
+			op->a_slot = (int16_t)slot_of[a];
 			stack[sp++] = a; /* parked, popped after b's whole subtree */
 		}
 		if (op->kind >= 1) {
@@ -462,11 +464,11 @@ static int build_walk_schedules(phb_tlk *t) {
 		phbc_pre_op *qo = &t->pre_ops[i];
 		if (qo->kind != 2) { /* child a is a tip */
 			t->pre_tip_order[q] = qo->a_node;
-			qo->a_code = q++ - t->pre_chunk_tip0[i / PHBC_WALK_CHUNK];
+			qo->a_code = (int16_t)(q++ - t->pre_chunk_tip0[i / PHBC_WALK_CHUNK]);
 		}
 		if (qo->kind == 0) {
 			t->pre_tip_order[q] = qo->b_node;
-			qo->b_code = q++ - t->pre_chunk_tip0[i / PHBC_WALK_CHUNK];
+			qo->b_code = (int16_t)(q++ - t->pre_chunk_tip0[i / PHBC_WALK_CHUNK]);
 		}
 	}
 	t->post_chunk_tip0[nch] = k;
@@ -477,6 +479,12 @@ static int build_walk_schedules(phb_tlk *t) {
 		const int i = ch * PHBC_WALK_CHUNK;
 		t->post_ops[i].next_tips = (t->post_chunk_tip0[ch + 1] << 5) | (t->post_chunk_tip0[ch + 2] - t->post_chunk_tip0[ch + 1]);
 		t->pre_ops[i].next_tips = (t->pre_chunk_tip0[ch + 1] << 5) | (t->pre_chunk_tip0[ch + 2] - t->pre_chunk_tip0[ch + 1]);
+	}
+	for (int i = 0; i < nint; i++) { /* what the op PHBC_PF_DIST positions later will read: requested into L2 at this op */
+		const int k2 = i + PHBC_PF_DIST;
+		t->pre_ops[i].pf_a_row = k2 < nint ? t->pre_ops[k2].a_row : -1;
+		t->pre_ops[i].pf_b_row = k2 < nint ? t->pre_ops[k2].b_row : -1;
+		t->pre_ops[i].pad_ = 0;
 	}
 	t->post_first_tips = nch > 0 ? t->post_chunk_tip0[1] : 0;
 	t->pre_first_tips = nch > 0 ? t->pre_chunk_tip0[1] : 0;
