@@ -63,7 +63,7 @@ struct Nuc4Params {
 	double freqs[4];
 	double fq[4];     // weights of the gradient numerator: pi, or 1 when the root frequencies are folded into the uppers
 	double wroot[4];  // upper message entering the root's children: 1, or pi (tlk->include_root_freqs)
-	double Q[16];
+	double FQ[16];    // diag(fq) Q: row i of the rate matrix times the weight of state i in the gradient numerator
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -522,14 +522,14 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 				for (int i = 0; i < 4; i++) {
 #pragma unroll
 					for (int u = 0; u < PPT; u++) {
-						const double qa = fma(prm.Q[4 * i], ma[u][0], fma(prm.Q[4 * i + 1], ma[u][1], fma(prm.Q[4 * i + 2], ma[u][2], prm.Q[4 * i + 3] * ma[u][3])));
-						const double qb = fma(prm.Q[4 * i], mb[u][0], fma(prm.Q[4 * i + 1], mb[u][1], fma(prm.Q[4 * i + 2], mb[u][2], prm.Q[4 * i + 3] * mb[u][3])));
-						const double fa = prm.fq[i] * ua[u][i], fb = prm.fq[i] * ub[u][i];
-						na[u] = fma(fa, qa, na[u]);
-						nb[u] = fma(fb, qb, nb[u]);
+						// prm.FQ = diag(f) Q: the frequency weights ride on the rows of the rate matrix
+						const double qa = fma(prm.FQ[4 * i], ma[u][0], fma(prm.FQ[4 * i + 1], ma[u][1], fma(prm.FQ[4 * i + 2], ma[u][2], prm.FQ[4 * i + 3] * ma[u][3])));
+						const double qb = fma(prm.FQ[4 * i], mb[u][0], fma(prm.FQ[4 * i + 1], mb[u][1], fma(prm.FQ[4 * i + 2], mb[u][2], prm.FQ[4 * i + 3] * mb[u][3])));
+						na[u] = fma(ua[u][i], qa, na[u]);
+						nb[u] = fma(ub[u][i], qb, nb[u]);
 						if (SCALE) {
-							da[u] = fma(fa, ma[u][i], da[u]);
-							db[u] = fma(fb, mb[u][i], db[u]);
+							da[u] = fma(prm.fq[i] * ua[u][i], ma[u][i], da[u]);
+							db[u] = fma(prm.fq[i] * ub[u][i], mb[u][i], db[u]);
 						}
 					}
 				}
@@ -1083,10 +1083,10 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	prm.cta_lnl = ctx->d_nuc4_cta_lnl;
 	prm.pattern_lnl = ctx->d_pattern_lnl;
 	memcpy(prm.freqs, ctx->h_freqs, sizeof(prm.freqs));  // small model constants travel in the kernel parameter bank
-	memcpy(prm.Q, ctx->h_qmat, sizeof(prm.Q));
 	for (int i = 0; i < 4; i++) {
 		prm.fq[i] = o->include_root_freqs ? 1.0 : ctx->h_freqs[i];
 		prm.wroot[i] = o->include_root_freqs ? ctx->h_freqs[i] : 1.0;
+		for (int j = 0; j < 4; j++) prm.FQ[4 * i + j] = prm.fq[i] * ctx->h_qmat[4 * i + j];
 	}
 	int trc;
 	if ((trc = phbc_time_begin(ctx))) return trc;
