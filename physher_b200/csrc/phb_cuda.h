@@ -37,7 +37,7 @@ typedef struct phbc_op {
  * PHBC_WALK_CHUNK (one TMA stage); tip operands are numbered in walk order so that the tip codes a chunk
  * needs are one contiguous range [chunk_tip0[ch], chunk_tip0[ch+1]) of a walk-ordered code array, and the
  * descriptors carry indices local to that range.  Operand kinds: */
-#define PHBC_WALK_CHUNK 4
+#define PHBC_WALK_CHUNK 6
 #define PHBC_W_TIP 0  /* idx = tip node id                                  */
 #define PHBC_W_SLOT 1 /* idx = shared-memory slot                           */
 #define PHBC_W_ROOT 2 /* pre-order only: the parent is the root (W = 1 or pi) */
