@@ -596,10 +596,10 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 #pragma unroll
 				for (int u = 0; u < PPT; u++) {
 					if (kind == 2) cell_store(slot_cell + d->a_slot * NUC4_SLOT_BYTES + u * PBT * 16, ua[u]);  // parked until its own op comes up
-					if (kind != 0) {
+					// child b's op is the next one when b is internal; unconditional, so that ub is formed in ureg's registers (a
+					// conditional hand-over costs 16 register moves per op) -- after a tip-tip op the next op reloads ureg from its slot
 #pragma unroll
-						for (int i = 0; i < 4; i++) ureg[u][i] = ub[u][i];  // child b's op is the next one
-					}
+					for (int i = 0; i < 4; i++) ureg[u][i] = ub[u][i];
 				}
 				};
 				// messages of the children: the prefetched rows for internal children, matrix columns (or column sums) for tips
