@@ -143,7 +143,7 @@ int phb_tlk_cat_branch_gradient(phb_tlk *tlk, double *out /* [N][C] */);
  * per-node matrices [nsets][N][C][S][S] (row-major like P), e.g. dP/d theta_k from m->dPdp(m, k, mat, bl * rate_c)
  * (substmodel.c:469-489, :2421); out[k] = sum over non-root nodes (not the root's right child when unrooted, :2408) and patterns of
  * w_p / L_p * sum_c prop_c sum_i f_i U_n[c,p,i] (M_k[n,c] L_n[c,p])_i.  Honours PHB_OPT_INCLUDE_ROOT_FREQS and rescaling.
- * 4 states without rescaling: ONE launch of the fused walk accumulates the per-branch statistics G[n][c][i][j] =
+ * 4 states (under rescaling: exact weights and a reversible model): ONE launch of the fused walk accumulates the per-branch statistics G[n][c][i][j] =
  * sum_p w_p / L_p f_i U_n[c,p,i] L_n[c,p,j] and every set is a 16-element contraction per (node, category) -- no materialised upper
  * partials, cost independent of nsets.  Otherwise the node-at-a-time kernels (materialised upper partials, one sweep per set). */
 int phb_tlk_matrix_gradient(phb_tlk *tlk, int nsets, const double *M, double *out /* [nsets] */);

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 	unsigned char *stage0 = smem_raw;
 	unsigned char *slot_cell = stage0 + 2 * lay.bytes + cell0 * 16;  // this thread's first cell in slot 0
 	double *xch = reinterpret_cast<double *>(stage0 + 2 * lay.bytes + (size_t)prm.nslots * NUC4_SLOT_BYTES);
-	double *invLw = xch + (SCALE ? 4 : 1) * C * PB;
+	double *invLw = xch + (SCALE ? (GRAD == 2 ? 5 : 4) : 1) * C * PB;
 	double *sfslot = invLw + PB;  // [nslots][NT] thread-private copies (SCALE only)
 	const uint32_t my_mat = lay.mat_off + c * 128;  // this thread's category inside a staged matrix group
 	const uint32_t my_code = lay.code_off + pl0;
@@ -504,14 +504,6 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 				}
 				// the op proper, on the messages P_x L_x of the children (ma, mb)
 				auto body = [&](double (&ma)[PPT][4], double (&mb)[PPT][4]) {
-				if (GRAD == 2 && d->u_kind != PHBC_W_ROOT) {  // the branch above this op's node: U_p is in ureg, L_p = M_a o M_b
-					double tp[PPT][4], xp[PPT][4];
-#pragma unroll
-					for (int u = 0; u < PPT; u++)
-#pragma unroll
-						for (int i = 0; i < 4; i++) tp[u][i] = sgrad[u] * prm.fq[i] * ureg[u][i], xp[u][i] = ma[u][i] * mb[u][i];
-					gstat_add<PPT>(tp, xp, my_gstat + (size_t)d->node * 16, lane);
-				}
 				double ua[PPT][4], ub[PPT][4];
 #pragma unroll
 				for (int u = 0; u < PPT; u++)
@@ -537,12 +529,17 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 					}
 				}
 				va = vb = 0.0;
+				// GRAD == 2: what multiplies f_i U[i] L[j] in the statistics of the three branches this op serves -- w_k / L_k, with
+				// the site likelihood L_k taken in each branch's own scale under rescaling
+				double coefa[PPT], coefb[PPT], coefp[PPT];
+#pragma unroll
+				for (int u = 0; u < PPT; u++) coefa[u] = coefb[u] = coefp[u] = sgrad[u];
 				if (!SCALE) {
 #pragma unroll
 					for (int u = 0; u < PPT; u++) va = fma(na[u], sgrad[u], va), vb = fma(nb[u], sgrad[u], vb);
 				} else {
 					// rescale the upper partials like the reference (their scale cancels in the ratios below)
-					double *plane = xch;  // 4 planes: max_a, max_b, den_a, den_b
+					double *plane = xch;  // planes: max_a, max_b, den_a, den_b [, den_p]
 					__syncthreads();      // previous op's readers are done
 #pragma unroll
 					for (int u = 0; u < PPT; u++) {
@@ -551,6 +548,15 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 						plane[1 * C * PB + ci] = fmax(fmax(ub[u][0], ub[u][1]), fmax(ub[u][2], ub[u][3]));
 						plane[2 * C * PB + ci] = da[u] * prop_c;
 						plane[3 * C * PB + ci] = db[u] * prop_c;
+						if (GRAD == 2) {
+							// site likelihood seen from the branch above this op's node, in the scale of (U_p, L_p = M_a o M_b):
+							// sum_i f_i U_p[i] (P_p L_p)[i] = sum_j f_j L_p[j] (P_p U_p)[j] for a reversible model with f = pi, and
+							// P_p U_p is W (the host sends a request here only then)
+							double dp = 0.0;
+#pragma unroll
+							for (int i = 0; i < 4; i++) dp = fma(prm.fq[i] * W[u][i], ma[u][i] * mb[u][i], dp);
+							plane[4 * C * PB + ci] = dp * prop_c;
+						}
 					}
 					__syncthreads();
 #pragma unroll
@@ -575,7 +581,23 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 						// (gradient_cat_branch_lengths_aux, treelikelihood.c:2721-2738)
 						va += prm.compat ? na[u] / da[u] * wk[u] : na[u] / dta * wk[u];
 						vb += prm.compat ? nb[u] / db[u] * wk[u] : nb[u] / dtb * wk[u];
+						if (GRAD == 2) {
+							double dtp = 0.0;
+							for (int cc = 0; cc < C; cc++) dtp += plane[4 * C * PB + cc * PB + pl];
+							// ua / ub have just been divided by their maxima: the denominators belong to the undivided values
+							coefa[u] = wk[u] / dta * (mxa < prm.threshold ? mxa : 1.0);
+							coefb[u] = wk[u] / dtb * (mxb < prm.threshold ? mxb : 1.0);
+							coefp[u] = wk[u] / dtp;
+						}
 					}
+				}
+				if (GRAD == 2 && d->u_kind != PHBC_W_ROOT) {  // the branch above this op's node: U_p is in ureg, L_p = M_a o M_b
+					double tp[PPT][4], xp[PPT][4];
+#pragma unroll
+					for (int u = 0; u < PPT; u++)
+#pragma unroll
+						for (int i = 0; i < 4; i++) tp[u][i] = coefp[u] * prm.fq[i] * ureg[u][i], xp[u][i] = ma[u][i] * mb[u][i];
+					gstat_add<PPT>(tp, xp, my_gstat + (size_t)d->node * 16, lane);
 				}
 				if (GRAD == 2 && kind != 2) {  // tip branches: L_n is the tip's indicator vector
 					double tt[PPT][4], xt[PPT][4];
@@ -583,7 +605,7 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 					for (int u = 0; u < PPT; u++) {
 						tip_vector(cds[d->a_code * PB + u * PBT], xt[u]);
 #pragma unroll
-						for (int i = 0; i < 4; i++) tt[u][i] = sgrad[u] * prm.fq[i] * ua[u][i];
+						for (int i = 0; i < 4; i++) tt[u][i] = coefa[u] * prm.fq[i] * ua[u][i];
 					}
 					gstat_add<PPT>(tt, xt, my_gstat + (size_t)d->a_node * 16, lane);
 					if (kind == 0) {
@@ -591,7 +613,7 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 						for (int u = 0; u < PPT; u++) {
 							tip_vector(cds[d->b_code * PB + u * PBT], xt[u]);
 #pragma unroll
-							for (int i = 0; i < 4; i++) tt[u][i] = sgrad[u] * prm.fq[i] * ub[u][i];
+							for (int i = 0; i < 4; i++) tt[u][i] = coefb[u] * prm.fq[i] * ub[u][i];
 						}
 						gstat_add<PPT>(tt, xt, my_gstat + (size_t)d->b_node * 16, lane);
 					}
@@ -906,9 +928,9 @@ __global__ void k_nuc4_gstat_contract(int N, int C, int root, int skip, const do
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static size_t nuc4_smem_bytes(int C, int PB, int nslots, bool scale) {
+static size_t nuc4_smem_bytes(int C, int PB, int nslots, bool scale, bool stat) {
 	return 2 * (size_t)nuc4_stage_layout(C, PB).bytes + (size_t)nslots * NUC4_SLOT_BYTES +
-	       (size_t)((scale ? 4 : 1) * C * PB + PB + (scale ? nslots * NUC4_NT : 0)) * sizeof(double);
+	       (size_t)((scale ? (stat ? 5 : 4) : 1) * C * PB + PB + (scale ? nslots * NUC4_NT : 0)) * sizeof(double);
 }
 
 static int pattern_block(int C) {
@@ -921,7 +943,7 @@ bool phbc_nuc4_supported(const phbc_ctx *ctx, const phbc_eval_opts *o) {
 	if (ctx->C != 1 && ctx->C != 2 && ctx->C != 4 && ctx->C != 8) return false;  // categories must tile the CTA exactly
 	const int PB = pattern_block(ctx->C);
 	const int nslots = ctx->post_slots > ctx->pre_slots ? ctx->post_slots : ctx->pre_slots;
-	if (nuc4_smem_bytes(ctx->C, PB, nslots, o->scale != 0) > ctx->smem_optin) return false;
+	if (nuc4_smem_bytes(ctx->C, PB, nslots, o->scale != 0, o->want_gradient == 2) > ctx->smem_optin) return false;
 	return true;
 }
 
@@ -933,7 +955,7 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	const int C = ctx->C, N = ctx->N, T = ctx->T, P = ctx->P;
 	const int PB = pattern_block(C);
 	const int nslots = ctx->post_slots > ctx->pre_slots ? ctx->post_slots : ctx->pre_slots;
-	const size_t smem = nuc4_smem_bytes(C, PB, nslots, o->scale != 0);
+	const size_t smem = nuc4_smem_bytes(C, PB, nslots, o->scale != 0, o->want_gradient == 2);
 	const int ntiles = (P + PB - 1) / PB;
 	// tip codes in walk order (once per tip upload / schedule change)
 	{
@@ -962,15 +984,18 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	    {{k_nuc4_walk<8, false, 0, 1>, k_nuc4_walk<8, false, 1, 1>}, {k_nuc4_walk<8, true, 0, 1>, k_nuc4_walk<8, true, 1, 1>}},
 	};
 	// unscaled walks that also accumulate the expected-transition statistics (phbc_nuc4_matrix_gradient)
-	static const walk_fn table_stat[4] = {k_nuc4_walk<1, false, 2, 2>, k_nuc4_walk<2, false, 2, 2>, k_nuc4_walk<4, false, 2, 2>, k_nuc4_walk<8, false, 2, 1>};
+	static const walk_fn table_stat[4][2] = {{k_nuc4_walk<1, false, 2, 2>, k_nuc4_walk<1, true, 2, 2>},
+	                                         {k_nuc4_walk<2, false, 2, 2>, k_nuc4_walk<2, true, 2, 2>},
+	                                         {k_nuc4_walk<4, false, 2, 2>, k_nuc4_walk<4, true, 2, 2>},
+	                                         {k_nuc4_walk<8, false, 2, 1>, k_nuc4_walk<8, true, 2, 1>}};
 	const int ppt = C == 8 ? 1 : 2, nthr = NUC4_NT / ppt;
 	const int ci = C == 1 ? 0 : (C == 2 ? 1 : (C == 4 ? 2 : 3));
 	const bool want_stat = o->want_gradient == 2;
-	if (want_stat && (o->scale || (o->batch_count > 1))) {
-		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "nuc4 walk: transition statistics need an unscaled single-sample evaluation");
+	if (want_stat && o->batch_count > 1) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "nuc4 walk: transition statistics need a single-sample evaluation");
 		return -1;
 	}
-	walk_fn kern = want_stat ? table_stat[ci] : table[ci][o->scale ? 1 : 0][o->want_gradient ? 1 : 0];
+	walk_fn kern = want_stat ? table_stat[ci][o->scale ? 1 : 0] : table[ci][o->scale ? 1 : 0][o->want_gradient ? 1 : 0];
 	ctx->nuc4_G_valid = false;
 	PHBC_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int per_sm = 0;
@@ -1141,17 +1166,30 @@ static int nuc4_prepare_codes(phbc_ctx *ctx, int *usable) {
 /*
  * phbc_matrix_gradient on the fused walk: one GRAD = 2 launch leaves G[n][c][i][j] on the device, every matrix set is then a
  * 16-element contraction per (node, category).  Returns 1 (declined, nothing done) when the walk cannot serve the request:
- * rescaling on, tips that are not 0/1 vectors, or a shape phbc_nuc4_supported refuses.
+ * tips that are not 0/1 vectors, a shape phbc_nuc4_supported refuses, or rescaling together with include_root_freqs, the
+ * reference-compatible normalisation or a non-reversible model.
  */
 int phbc_nuc4_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int nsets, const double *M_host, int skip_node, double *lnl, double *out_host) {
-	if (o->scale || o->kernels == 1 || !phbc_nuc4_supported(ctx, o)) return 1;
+	phbc_eval_opts e = *o;
+	e.want_gradient = 2;
+	e.batch_count = 1;
+	if (o->kernels == 1 || !phbc_nuc4_supported(ctx, &e)) return 1;
+	if (o->scale) {
+		// the scaled form takes each branch's site likelihood from P_p U_p (see the kernel): exact weights and a reversible model
+		if (o->include_root_freqs || o->compat_scaled_gradient) return 1;
+		double worst = 0.0, big = 0.0;
+		for (int i = 0; i < 4; i++)
+			for (int j = 0; j < 4; j++) {
+				const double a = ctx->h_freqs[i] * ctx->h_qmat[4 * i + j], b = ctx->h_freqs[j] * ctx->h_qmat[4 * j + i];
+				worst = fmax(worst, fabs(a - b));
+				big = fmax(big, fabs(a));
+			}
+		if (!(worst <= 1e-12 * big)) return 1;
+	}
 	PHBC_CHECK(cudaSetDevice(ctx->device));
 	int usable = 0, rc;
 	if ((rc = nuc4_prepare_codes(ctx, &usable))) return rc;
 	if (!usable) return 1;
-	phbc_eval_opts e = *o;
-	e.want_gradient = 2;
-	e.batch_count = 1;
 	if ((rc = phbc_nuc4_evaluate(ctx, &e))) return rc;
 	const size_t N = ctx->N, C = ctx->C, set = N * C * 16;
 	// matrix sets and results travel through the grow-only reduction scratch (no allocation per request)

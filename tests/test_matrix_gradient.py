@@ -151,3 +151,50 @@ def test_gpu_fused_walk_transition_statistics(shape, tips):
     pb.include_root_freqs = True
     assert grad_err(tlk.matrix_gradient(M), O.matrix_gradient(pb, M)) < RTOL
     tlk.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(37, 1500, 4), (21, 333, 1), (26, 65, 8), (128, 900, 4)], ids=lambda s: "T%d-P%d-C%d" % s)
+def test_gpu_fused_walk_transition_statistics_rescaled(shape):
+    """The same request with rescaling on and a threshold that makes nearly every node rescale (1e-2): each branch's statistics are
+    normalised by the site likelihood in that branch's own scale (dlikelihood / likelihood, treelikelihood.c:2464-2474), still ONE fused
+    launch; the values are the unscaled derivative.  Requests the walk cannot serve exactly (include_root_freqs, the reference-compatible
+    per-category normalisation) go to the node-at-a-time kernels and must agree as well."""
+    import physher_b200 as phb
+    from physher_b200 import synthetic as syn
+    from physher_b200.treelikelihood import OPT_COMPAT_SCALED_GRADIENT, OPT_SCALING_THRESHOLD_EXP
+    from tests.test_gpu_parity import _synthetic_problem
+
+    T, P, C = shape
+    topo = syn.caterpillar_topology(T) if T == 128 else None
+    pb = _synthetic_problem(T, P, 4, C, seed=7300 + T + C, topo=topo, unknown=0.04)
+    rng = np.random.default_rng(7400 + C)
+    M = rng.normal(size=(5, pb.nnodes, C, 4, 4))
+    want = O.matrix_gradient(pb, M)
+    res = O.evaluate(pb, gradient=True, partials=True)
+    R = np.einsum("c,cpi->pi", pb.props, res["lower"][pb.root])
+    want_root = (pb.weights[:, None] * R / (R @ pb.freqs)[:, None]).sum(0)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    tlk.set_option(OPT_SCALING_THRESHOLD_EXP, 2)
+    tlk.use_rescaling(True)
+    before = tlk.launch_count()
+    got = tlk.matrix_gradient(M)
+    assert tlk.launch_count() - before <= 7, "served by the fused walk"
+    assert grad_err(got, want) < 1e-9
+    before = tlk.launch_count()
+    assert grad_err(tlk.root_frequency_gradient(), want_root) < 1e-9
+    assert tlk.launch_count() == before
+    assert rel_err(tlk.calculate(), res["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), res["grad"]) < 1e-9
+    # node-at-a-time kernels on the same scaled request
+    gen = phb.SingleTreeLikelihood.from_problem(pb, kernels=phb.KERNELS_GENERIC)
+    gen.set_option(OPT_SCALING_THRESHOLD_EXP, 2)
+    gen.use_rescaling(True)
+    assert grad_err(gen.matrix_gradient(M), want) < 1e-9
+    gen.close()
+    # the reference-compatible normalisation is not something the walk's statistics can express: declined, served by the sweep
+    tlk.set_option(OPT_COMPAT_SCALED_GRADIENT, 1)
+    before = tlk.launch_count()
+    assert grad_err(tlk.matrix_gradient(M), want) < 1e-9  # the sweep always uses dlikelihood / likelihood
+    assert tlk.launch_count() - before > 7
+    tlk.close()
