@@ -355,3 +355,21 @@ def test_tensor_core_path_matches_generic_partials():
         if n != pb.root:
             np.testing.assert_allclose(tlk.get_partials(pb.nnodes + n), out["upper"][n], rtol=1e-11, atol=1e-300)
     tlk.close()
+
+
+@pytest.mark.parametrize("kernels", KERNELS, ids=KIDS)
+@pytest.mark.parametrize("shape", [(2, 50, 4, 4), (3, 70, 4, 1), (2, 33, 20, 2), (3, 40, 61, 1), (2, 10, 5, 2), (4, 1, 4, 8)], ids=lambda s: "T%d-S%d-C%d" % (s[0], s[2], s[3]))
+def test_smallest_trees(shape, kernels):
+    """two and three taxa (the root's children are tips; one internal node besides the root at most), a single pattern, 8 categories"""
+    T, P, S, C = shape
+    pb = _synthetic_problem(T, P, S, C, seed=3000 + T * 7 + S, unknown=0.05)
+    want = O.evaluate(pb)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=kernels)
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), want["grad"]) < RTOL
+    M = np.random.default_rng(3100 + T).normal(size=(2, pb.nnodes, C, S, S))
+    assert grad_err(tlk.matrix_gradient(M), O.matrix_gradient(pb, M)) < RTOL
+    tlk.use_rescaling(True)
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), want["grad"]) < 1e-9
+    tlk.close()
