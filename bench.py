@@ -70,6 +70,24 @@ def make_inputs(cfg: dict, rank: int, seed: int = 20261017):
     return topo, bl, m, rates, props, patterns, weights
 
 
+def inputs_sha256(topo, bl, m, rates, props, patterns=None, weights=None):
+    """SHA-256 of the workload as both arms see it (recorded next to every result).  `tree_model` covers topology,
+    branch lengths, eigen system, frequencies and the site model -- identical in both arms and on every rank; `patterns` covers the
+    pattern shard of rank 0 (our arm; the reference arm times bounded shards of the same generator, see cpu_baseline.sample)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    for a in (topo.left, topo.right, [topo.root], bl, m.evec, m.eval, m.ivec, m.freqs, rates, props):
+        h.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    out = {"tree_model": h.hexdigest()}
+    if patterns is not None:
+        g = hashlib.sha256()
+        g.update(np.ascontiguousarray(patterns, dtype=np.uint8).tobytes())
+        g.update(np.ascontiguousarray(weights, dtype=np.float64).tobytes())
+        out["patterns_rank0"] = g.hexdigest()
+    return out
+
+
 def lg_model():
     """LG eigen system as the reference's host code produced it (lg.c + eigen.c), stored in the committed golden fixture."""
     z = np.load(os.path.join(ROOT, "tests", "golden", "synth_lg_g4_tipstates.npz"))
@@ -283,6 +301,7 @@ def reference_main(args, cfg):
     cores = min(cores, 32)
     sample = sample_per_core(cfg) * cores
     iters = max(1, min(args.steps, 10))
+    topo_, bl_, m_, rates_, props_, _, _ = make_inputs(dict(cfg, patterns=64), 0)
     t0 = time.perf_counter()
     r = run_reference(cfg, cores, sample, iters, warm=min(args.warmup, 1) or 1)
     total_patterns = sum(r["patterns"])
@@ -291,7 +310,7 @@ def reference_main(args, cfg):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": iters, "warmup": 1,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(cfg), "taxa": cfg["taxa"], "patterns_per_gpu": cfg["patterns"], "states": cfg["states"],
-                   "categories": cfg["cats"], "model": cfg["model"]},
+                   "categories": cfg["cats"], "model": cfg["model"], "inputs_sha256": inputs_sha256(topo_, bl_, m_, rates_, props_)},
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference",
                          "sample": f"{cores} single-threaded processes x {r['per']} patterns each ({total_patterns} unique patterns total) of the same "
                                    f"{cfg['taxa']}-taxon workload, {iters} lnL+gradient evaluations each, protocol examples/benchmarking.c:498-503"},
@@ -352,6 +371,7 @@ def main():
     W, K = max(args.warmup, 3), args.steps
 
     topo, bl, m, rates, props, patterns, weights = make_inputs(cfg, rank)
+    sha = inputs_sha256(topo, bl, m, rates, props, patterns, weights) if rank == 0 else None
     T, P, S, C = cfg["taxa"], cfg["patterns"], cfg["states"], cfg["cats"]
     N = 2 * T - 1
     tlk = phb.SingleTreeLikelihood(topo.left, topo.right, topo.root, S, C, P, use_tip_states=True, device=local_rank)
@@ -506,7 +526,7 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(cfg), "taxa": T, "patterns_per_gpu": P, "states": S, "categories": C, "model": cfg["model"],
                    "kernels": args.kernels, "l2": "per-evaluation working set (>= 2 GB of partials) exceeds the 126 MB L2; no explicit flush",
-                   "sharding": f"patterns x{world}" if world > 1 else "single GPU", "samples_per_step": B},
+                   "sharding": f"patterns x{world}" if world > 1 else "single GPU", "samples_per_step": B, "inputs_sha256": sha},
         "evals_per_s": B * 1e3 / step_ms, "lnl": lnl,
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * N * B, "d2h_bytes_per_step": 8 * (N + 1) * B,
                 "evals_per_s": B * 1e3 / e2e_ms},
