@@ -13,6 +13,10 @@ single-GPU host code in csrc/phb_treelikelihood.c:
   * NaN / inf lnL       => NaN-filled gradient (treelikelihood.c:328-332);
   * unrooted convention => root's right child gradient forced to 0 (treelikelihood.c:3249-3255).
 
+Substitution-model parameter gradients shard the same way: the node sweep of calculate_dlnl_dQ
+(treelikelihood.c:2337-2583) is a sum over patterns of w_k / L_k (...) with L_k local to the pattern, so
+the per-shard values of `phb_tlk_matrix_gradient` add up -- one more SUM all-reduce of [lnL, out[nsets]].
+
 The shard evaluator is the `phb_tlk_gradient_device` entry point of the C ABI; tests inject a
 different evaluator to exercise this host logic with the gloo backend on CPU.
 """
@@ -46,7 +50,7 @@ class ShardedTreeLikelihood:
     """
 
     def __init__(self, nnodes: int, root: int, root_right: int, tlk=None, evaluate_shard: Optional[Callable] = None,
-                 unrooted: bool = True, group=None, device=None):
+                 unrooted: bool = True, group=None, device=None, evaluate_matrix_shard: Optional[Callable] = None):
         import torch
         import torch.distributed as dist
 
@@ -59,6 +63,7 @@ class ShardedTreeLikelihood:
         self.tlk = tlk
         self.rescaling = bool(tlk.rescaling()) if tlk is not None else False
         self.evaluations = 0
+        self._evaluate_matrix = evaluate_matrix_shard if tlk is None else self._evaluate_matrix_tlk
         if tlk is not None:
             self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
             self.out = torch.zeros(1 + self.N, dtype=torch.float64, device=self.device)
@@ -79,6 +84,13 @@ class ShardedTreeLikelihood:
         # the collective runs on torch's current stream: order it after the tlk's stream
         self.torch.cuda.current_stream(self.device).wait_stream(self.stream)
         return self.out
+
+    def _evaluate_matrix_tlk(self, M, rescaling):
+        if rescaling != self.tlk.rescaling():
+            self.tlk.use_rescaling(rescaling)
+        out = self.tlk.matrix_gradient(M)  # host values of this shard (the C ABI returns them to the host)
+        lnl = self.tlk.calculate()          # cached by the sweep
+        return self.torch.from_numpy(np.concatenate([[lnl], out])).to(self.device)
 
     # -- reduction + post-reduction policy ------------------------------------------------------
     def reduce_device(self, bl=None):
@@ -106,3 +118,25 @@ class ShardedTreeLikelihood:
             if self.unrooted:
                 g[self.root_right] = 0.0  # treelikelihood.c:3249-3255
         return lnl, g
+
+    def matrix_gradient(self, M) -> Tuple[float, np.ndarray]:
+        """(lnL, out[nsets]) of phb_tlk_matrix_gradient over ALL shards for per-node matrix sets M [nsets][N][C][S][S] (the same on
+        every rank): per-shard sweeps, one SUM all-reduce, then the reference's inf / NaN policy on the reduced lnL."""
+        if self._evaluate_matrix is None:
+            raise ValueError("no matrix-gradient evaluator (give tlk or evaluate_matrix_shard)")
+
+        def once():
+            t = self._evaluate_matrix(M, self.rescaling)
+            if self.dist.is_available() and self.dist.is_initialized() and self.dist.get_world_size(self.group) > 1:
+                self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
+            self.evaluations += 1
+            return t.detach().cpu().numpy().copy()
+
+        h = once()
+        if math.isinf(float(h[0])) and not self.rescaling:
+            self.rescaling = True  # every rank sees the same reduced lnL (treelikelihood.c:1496-1519)
+            h = once()
+        lnl, out = float(h[0]), h[1:]
+        if math.isnan(lnl) or math.isinf(lnl):
+            out[:] = np.nan
+        return lnl, out

@@ -80,8 +80,21 @@ def _worker(rank, world, port, case, q):
                 out["lnl"] = float("nan")
             return torch.from_numpy(np.concatenate([[out["lnl"]], out["grad"]]))
 
-        st = sharded.ShardedTreeLikelihood(pb.nnodes, pb.root, int(pb.right[pb.root]), evaluate_shard=evaluate_shard)
-        lnl, g = st.gradient(pb.bl)
+        def evaluate_matrix_shard(M, rescaling):
+            # stands in for phb_tlk_matrix_gradient + the cached lnL of the shard
+            calls.append(bool(rescaling))
+            pb.scale = bool(rescaling)
+            pb.unrooted = True  # the sweep skips the root's right child itself (treelikelihood.c:2408)
+            lnl_shard = O.evaluate(pb, gradient=False)["lnl"]
+            return torch.from_numpy(np.concatenate([[lnl_shard], O.matrix_gradient(pb, M)]))
+
+        st = sharded.ShardedTreeLikelihood(pb.nnodes, pb.root, int(pb.right[pb.root]), evaluate_shard=evaluate_shard,
+                                           evaluate_matrix_shard=evaluate_matrix_shard)
+        if case.get("matrix_sets"):
+            M = np.random.default_rng(case["matrix_seed"]).normal(size=(case["matrix_sets"], pb.nnodes, pb.ncat, pb.nstate, pb.nstate))
+            lnl, g = st.matrix_gradient(M)
+        else:
+            lnl, g = st.gradient(pb.bl)
         q.put((rank, lnl, g, calls, st.rescaling, st.evaluations))
     finally:
         dist.destroy_process_group()
@@ -140,6 +153,20 @@ def test_two_rank_nan_fills_the_gradient_on_every_rank():
         assert np.isnan(lnl) and np.isnan(g).all() and not rescaling  # treelikelihood.c:328-332
 
 
+@pytest.mark.timeout(300)
+def test_two_rank_matrix_gradient_matches_unsharded():
+    """substitution-model parameter gradients are sums over patterns too: per-shard sweeps + one all-reduce of [lnL, out[nsets]]"""
+    case = {"problem": dict(T=12, P=151, C=4, seed=41), "matrix_sets": 4, "matrix_seed": 42}
+    res = _run(case)
+    pb = _problem(**case["problem"])
+    M = np.random.default_rng(42).normal(size=(4, pb.nnodes, pb.ncat, pb.nstate, pb.nstate))
+    want, want_lnl = O.matrix_gradient(pb, M), O.evaluate(pb, gradient=False)["lnl"]
+    for rank, lnl, out, calls, rescaling, evals in res:
+        assert rel_err(lnl, want_lnl) < RTOL and grad_err(out, want) < RTOL
+        assert calls == [False] and evals == 1
+    assert np.array_equal(res[0][2], res[1][2])
+
+
 # -------------------------------------------------------------------------------------------------
 # the real thing: C-ABI shards on GPUs (single process drives both shards when one GPU is visible)
 # -------------------------------------------------------------------------------------------------
@@ -171,3 +198,24 @@ def test_gpu_shards_sum_to_the_unsharded_result():
     g[pb.right[pb.root]] = 0.0
     assert rel_err(float(h[0]), want["lnl"]) < RTOL and rel_err(float(h[0]), lnl_full) < 1e-12
     assert grad_err(g, want["grad"]) < RTOL and grad_err(g, g_full) < 1e-11
+
+
+@pytest.mark.gpu
+def test_gpu_matrix_gradient_shards_sum_to_the_unsharded_result():
+    import physher_b200 as phb
+
+    pb = _problem(T=33, P=777, C=4, seed=91)
+    M = np.random.default_rng(92).normal(size=(3, pb.nnodes, pb.ncat, 4, 4))
+    want = O.matrix_gradient(pb, M)
+    world, acc, lnl = 3, np.zeros(3), 0.0
+    for rank in range(world):
+        states, w = sharded.shard_inputs(pb.tip_states, pb.weights, rank, world)
+        sub = O.Problem(**{**pb.__dict__, "tip_states": states, "weights": w})
+        tlk = phb.SingleTreeLikelihood.from_problem(sub)
+        st = sharded.ShardedTreeLikelihood(pb.nnodes, pb.root, int(pb.right[pb.root]), tlk=tlk, device="cuda:0")
+        shard_lnl, out = st.matrix_gradient(M)  # no process group: the shard's own values
+        acc += out
+        lnl += shard_lnl
+        tlk.close()
+    assert grad_err(acc, want) < RTOL
+    assert rel_err(lnl, O.evaluate(pb, gradient=False)["lnl"]) < RTOL
