@@ -6,7 +6,7 @@
 // calculate_branch_partials_4_SSE treelikelihood4.c:1752, gradient_cat_branch_lengths
 // treelikelihood.c:2793) by ONE kernel per evaluation:
 //
-//   * a thread owns one (pattern, rate category) pair and walks the WHOLE tree: post-order for the
+//   * a thread owns PPT (pattern, rate category) pairs and walks the WHOLE tree: post-order for the
 //     lower partials, root integration, then pre-order for upper partials and branch gradients;
 //   * intermediate partials live in thread-private shared-memory slots; the host orders the walks so
 //     that the number of live slots is the tree's Strahler number (<= log2(T) + 1);
@@ -15,16 +15,18 @@
 //     three times -- by the parent's lower partial, by the sibling's upper partial and by n's own branch gradient
 //     (4 mat-vecs per internal node and evaluation instead of the 7 a node-at-a-time formulation spends);
 //   * the messages of internal nodes are streamed once to a CTA-private HBM scratch row (32 B per
-//     thread per node, coalesced 1 KB per warp) and read back once by the pre-order pass; upper
-//     partials never leave the SM.  HBM traffic is ~2(T-1)*C*32 B per pattern instead of the
+//     (pattern, category) and node, coalesced 1 KB per warp) and read back once by the pre-order pass -- requested one op
+//     ahead into alternating register sets and hinted into L2 three ops ahead; upper partials never leave the SM.  HBM traffic is ~2(T-1)*C*32 B per pattern instead of the
 //     ~(5T-9)*C*32 B of node-at-a-time streaming;
 //   * transition matrices arrive in walk order through TMA bulk copies (cp.async.bulk + mbarrier,
-//     double-buffered chunks of 8 ops) and are read as warp-uniform broadcasts;
+//     double-buffered chunks of PHBC_WALK_CHUNK ops) and are read as warp-uniform broadcasts;
 //   * dP/dt L is evaluated as Q (P L): dP/dt = Q P(t) for any rate matrix, so derivative matrices are
-//     never built or staged; Q sits in the kernel parameter (constant) bank;
-//   * per-branch gradient terms are reduced with a paired warp butterfly (two branches per 5
-//     shuffles) and accumulated with no-return reductions into warp-private rows, which a second
-//     tiny kernel sums in a fixed order (deterministic).
+//     never built or staged; diag(f) Q sits in the kernel parameter (constant) bank;
+//   * per-branch gradient terms are reduced with a paired warp butterfly (four branches per 6
+//     shuffle rounds) and accumulated with no-return reductions into warp-private rows, which a second
+//     tiny kernel sums in a fixed order (deterministic);
+//   * GRAD = 2 additionally accumulates the 4 x 4 transition statistics of every branch (gstat_add), from which the
+//     substitution-model parameter gradients of calculate_dlnl_dQ (treelikelihood.c:2337-2583) are 16-element contractions.
 //
 // CTAs are persistent: grid = min(tiles, resident CTAs), each CTA loops over pattern tiles and owns
 // its scratch, so device memory is independent of the pattern count.
