@@ -188,6 +188,42 @@ int phb_tlk_gradient_device(phb_tlk *tlk, double *out_device /* [1+N] */);
 void *phb_tlk_stream(phb_tlk *tlk);
 int phb_tlk_synchronize(phb_tlk *tlk);
 
+/*
+ * The same for ONE host process driving several devices (physher itself is a single process): launch queues one evaluation of the
+ * current inputs on the tlk's stream and returns, collect blocks on that stream and hands back the RAW sums of this object's
+ * patterns (lnL and d lnL / d bl by node id; grad may be NULL) -- no inf / NaN / unrooted policy.
+ */
+int phb_tlk_evaluate_launch(phb_tlk *tlk, int want_gradient);
+int phb_tlk_evaluate_collect(phb_tlk *tlk, double *lnl, double *grad /* [N] */);
+
+/*
+ * phb_group: one tree likelihood sharded over several GPUs from one host thread.  Shard g owns the contiguous
+ * pattern range [P g / G, P (g + 1) / G) on devices[g] (a device may appear more than once); pattern-indexed inputs are given
+ * for the WHOLE alignment and sliced, model inputs are broadcast, an evaluation is launched on every shard before any result is
+ * collected, and the G vectors [lnL, grad[N]] are summed on the host in shard order.  The reference's conventions are applied to
+ * the REDUCED values: +-inf lnL switches rescaling on on every shard and recomputes (treelikelihood.c:1496-1519), a NaN / inf lnL
+ * NaN-fills the gradient (:328-332), PHB_OPT_UNROOTED zeroes the root's right child (:3249-3255).  *grad is owned by the group.
+ */
+typedef struct phb_group phb_group;
+phb_group *phb_group_create(int nshards, const int *devices, int ntips, int nstate, int ncat, int npatterns, const int *left,
+                            const int *right, int root, int use_tip_states);
+void phb_group_free(phb_group *g);
+int phb_group_size(const phb_group *g);
+phb_tlk *phb_group_shard(phb_group *g, int shard); /* borrowed: per-shard introspection */
+int phb_group_shard_range(const phb_group *g, int shard, int *begin, int *end);
+int phb_group_set_tip_states(phb_group *g, const uint8_t *states /* [T][P] */);
+int phb_group_set_tip_partials(phb_group *g, const double *partials /* [T][P][S] */);
+int phb_group_set_pattern_weights(phb_group *g, const double *weights /* [P] */);
+int phb_group_set_eigen(phb_group *g, const double *evec, const double *eval, const double *ivec);
+int phb_group_set_frequencies(phb_group *g, const double *freqs);
+int phb_group_set_site_model(phb_group *g, const double *rates, const double *proportions);
+int phb_group_set_branch_lengths(phb_group *g, const double *bl);
+int phb_group_set_option(phb_group *g, int option, int value);
+int phb_group_use_rescaling(phb_group *g, int use);
+int phb_group_rescaling(const phb_group *g);
+int phb_group_calculate(phb_group *g, double *lnl);
+int phb_group_gradient(phb_group *g, double *lnl, const double **grad);
+
 /* B branch-length vectors sharing topology, patterns and models: lnl[b], grad[b][N]. */
 int phb_tlk_gradient_batch(phb_tlk *tlk, int nbatch, const double *bl /* [B][N] */, double *lnl /* [B] */,
                            double *grad /* [B][N] */);

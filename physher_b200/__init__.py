@@ -12,12 +12,13 @@ from .treelikelihood import (  # noqa: F401
     OPT_INCREMENTAL,
     PhysherB200Error,
     SingleTreeLikelihood,
+    TreeLikelihoodGroup,
     compress_patterns,
     device_count,
     load_library,
 )
 
 __all__ = [
-    "SingleTreeLikelihood", "PhysherB200Error", "load_library", "device_count", "compress_patterns",
+    "SingleTreeLikelihood", "TreeLikelihoodGroup", "PhysherB200Error", "load_library", "device_count", "compress_patterns",
     "FLAG_TREE_MODEL", "KERNELS_AUTO", "KERNELS_GENERIC", "KERNELS_FUSED", "OPT_INCREMENTAL",
 ]

@@ -1371,6 +1371,33 @@ int phb_tlk_gradient_device(phb_tlk *t, double *out_device) {
 	return PHB_OK;
 }
 
+/*
+ * Split evaluation for single-process multi-GPU hosts (phb_group.c): launch queues one evaluation of the current inputs on the
+ * tlk's stream and returns; collect blocks on that stream and returns the RAW sums of this object's patterns -- no inf / NaN /
+ * unrooted policy, that belongs to whoever adds the shards up.  The object stays dirty (its lnL is not known here).
+ */
+int phb_tlk_evaluate_launch(phb_tlk *t, int want_gradient) {
+	int rc = check_ready(t);
+	if (rc) return rc;
+	if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+	t->bl_dirty = 0;
+	phbc_eval_opts o;
+	fill_opts(t, &o, want_gradient != 0, 0);
+	t->resident = 0;
+	t->sweep_valid = 0;
+	if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
+	memset(t->update_nodes, 0, t->N);
+	t->update = 1;
+	t->update_upper = 1;
+	return PHB_OK;
+}
+
+int phb_tlk_evaluate_collect(phb_tlk *t, double *lnl, double *grad) {
+	int rc = phbc_download_results(t->ctx, 1, lnl, grad);
+	if (rc) return dev_fail(rc);
+	return PHB_OK;
+}
+
 void *phb_tlk_stream(phb_tlk *t) { return phbc_stream(t->ctx); }
 
 int phb_tlk_synchronize(phb_tlk *t) {

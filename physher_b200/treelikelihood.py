@@ -69,6 +69,25 @@ SYMBOLS = [
     ("phb_tlk_get_partials", C.c_int, [C.c_void_p, C.c_int, _dp]),
     ("phb_tlk_get_matrices", C.c_int, [C.c_void_p, _dp, _dp]),
     ("phb_tlk_gradient_device", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("phb_tlk_evaluate_launch", C.c_int, [C.c_void_p, C.c_int]),
+    ("phb_tlk_evaluate_collect", C.c_int, [C.c_void_p, _dp, _dp]),
+    ("phb_group_create", C.c_void_p, [C.c_int, _ip, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, C.c_int]),
+    ("phb_group_free", None, [C.c_void_p]),
+    ("phb_group_size", C.c_int, [C.c_void_p]),
+    ("phb_group_shard", C.c_void_p, [C.c_void_p, C.c_int]),
+    ("phb_group_shard_range", C.c_int, [C.c_void_p, C.c_int, _ip, _ip]),
+    ("phb_group_set_tip_states", C.c_int, [C.c_void_p, _bp]),
+    ("phb_group_set_tip_partials", C.c_int, [C.c_void_p, _dp]),
+    ("phb_group_set_pattern_weights", C.c_int, [C.c_void_p, _dp]),
+    ("phb_group_set_eigen", C.c_int, [C.c_void_p, _dp, _dp, _dp]),
+    ("phb_group_set_frequencies", C.c_int, [C.c_void_p, _dp]),
+    ("phb_group_set_site_model", C.c_int, [C.c_void_p, _dp, _dp]),
+    ("phb_group_set_branch_lengths", C.c_int, [C.c_void_p, _dp]),
+    ("phb_group_set_option", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("phb_group_use_rescaling", C.c_int, [C.c_void_p, C.c_int]),
+    ("phb_group_rescaling", C.c_int, [C.c_void_p]),
+    ("phb_group_calculate", C.c_int, [C.c_void_p, _dp]),
+    ("phb_group_gradient", C.c_int, [C.c_void_p, _dp, C.POINTER(_dp)]),
     ("phb_tlk_stream", C.c_void_p, [C.c_void_p]),
     ("phb_tlk_synchronize", C.c_int, [C.c_void_p]),
     ("phb_tlk_gradient_batch", C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp]),
@@ -401,3 +420,86 @@ class SingleTreeLikelihood:
 
     def launch_count(self) -> int:
         return int(self.lib.phb_tlk_launch_count(self.h))
+
+
+class TreeLikelihoodGroup:
+    """One tree likelihood sharded over several GPUs from one host thread (phb_group, csrc/phb_group.c): pattern-indexed inputs for the
+    whole alignment, model inputs broadcast, every evaluation launched on all shards before any result is collected."""
+
+    def __init__(self, devices, left, right, root, nstate, ncat, npatterns, use_tip_states=True):
+        self.lib = load_library()
+        self.left = np.ascontiguousarray(left, dtype=np.int32)
+        self.right = np.ascontiguousarray(right, dtype=np.int32)
+        self.N = int(self.left.shape[0])
+        self.T = (self.N + 1) // 2
+        self.S, self.C, self.P = int(nstate), int(ncat), int(npatterns)
+        dev = np.ascontiguousarray(devices, dtype=np.int32)
+        self.h = self.lib.phb_group_create(int(dev.size), dev.ctypes.data_as(_ip), self.T, self.S, self.C, self.P, self.left.ctypes.data_as(_ip),
+                                           self.right.ctypes.data_as(_ip), int(root), int(bool(use_tip_states)))
+        if not self.h:
+            raise PhysherB200Error((self.lib.phb_last_error() or b"").decode() or "phb_group_create failed")
+
+    @classmethod
+    def from_problem(cls, pb, devices):
+        g = cls(devices, pb.left, pb.right, pb.root, pb.nstate, pb.ncat, pb.npatterns, use_tip_states=pb.use_tip_states)
+        if pb.use_tip_states:
+            a = np.ascontiguousarray(pb.tip_states, dtype=np.uint8)
+            g._check(g.lib.phb_group_set_tip_states(g.h, a.ctypes.data_as(_bp)))
+        else:
+            g._check(g.lib.phb_group_set_tip_partials(g.h, _f64(pb.tip_partials).ctypes.data_as(_dp)))
+        g._check(g.lib.phb_group_set_pattern_weights(g.h, _f64(pb.weights).ctypes.data_as(_dp)))
+        g._check(g.lib.phb_group_set_eigen(g.h, _f64(pb.evec).ctypes.data_as(_dp), _f64(pb.eval).ctypes.data_as(_dp), _f64(pb.ivec).ctypes.data_as(_dp)))
+        g._check(g.lib.phb_group_set_frequencies(g.h, _f64(pb.freqs).ctypes.data_as(_dp)))
+        g._check(g.lib.phb_group_set_site_model(g.h, _f64(pb.rates).ctypes.data_as(_dp), _f64(pb.props).ctypes.data_as(_dp)))
+        g.set_branch_lengths(pb.bl)
+        g.set_option(OPT_UNROOTED, int(pb.unrooted))
+        if getattr(pb, "scale", False):
+            g.use_rescaling(True)
+        return g
+
+    def _check(self, rc):
+        if rc != 0:
+            raise PhysherB200Error(f"[{rc}] {(self.lib.phb_last_error() or b'').decode()}")
+
+    def size(self):
+        return int(self.lib.phb_group_size(self.h))
+
+    def shard_range(self, shard):
+        b, e = C.c_int(0), C.c_int(0)
+        self._check(self.lib.phb_group_shard_range(self.h, int(shard), C.byref(b), C.byref(e)))
+        return b.value, e.value
+
+    def set_branch_lengths(self, bl):
+        a = _f64(bl)
+        assert a.shape == (self.N,)
+        self._check(self.lib.phb_group_set_branch_lengths(self.h, a.ctypes.data_as(_dp)))
+
+    def set_option(self, option, value):
+        self._check(self.lib.phb_group_set_option(self.h, int(option), int(value)))
+
+    def use_rescaling(self, use):
+        self._check(self.lib.phb_group_use_rescaling(self.h, int(bool(use))))
+
+    def rescaling(self):
+        return bool(self.lib.phb_group_rescaling(self.h))
+
+    def calculate(self):
+        v = C.c_double(0.0)
+        self._check(self.lib.phb_group_calculate(self.h, C.byref(v)))
+        return v.value
+
+    def gradient(self):
+        v, p = C.c_double(0.0), _dp()
+        self._check(self.lib.phb_group_gradient(self.h, C.byref(v), C.byref(p)))
+        return v.value, np.ctypeslib.as_array(p, shape=(self.N,)).copy()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.phb_group_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
