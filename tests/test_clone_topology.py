@@ -152,3 +152,16 @@ def test_topology_move_with_resident_partials_and_three_node_updates():
     tlk.update_three_nodes(node)
     assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
     tlk.close()
+
+
+def test_clone_to_another_device():
+    """with two visible GPUs: the clone lives on the other device (data travels device to device) and agrees bit for bit"""
+    if phb.device_count() < 2:
+        pytest.skip("one GPU visible")
+    pb = _synthetic_problem(30, 900, 4, 4, seed=8400)
+    src = phb.SingleTreeLikelihood.from_problem(pb, device=0)
+    lnl, g = src.calculate(), src.gradient().copy()
+    twin = src.clone(device=1)
+    src.close()
+    assert twin.calculate() == lnl and np.array_equal(twin.gradient(), g)
+    twin.close()
