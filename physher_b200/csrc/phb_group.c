@@ -29,14 +29,16 @@ struct phb_group {
 	int prepared;
 };
 
-static int group_fail(const char *what) {
-	(void)what;
-	return PHB_EINVAL;
-}
+int phb_internal_fail(int code, const char *msg); /* phb_treelikelihood.c: sets phb_last_error() */
+
+static int group_fail(const char *what) { return phb_internal_fail(PHB_EINVAL, what); }
 
 phb_group *phb_group_create(int nshards, const int *devices, int ntips, int nstate, int ncat, int npatterns, const int *left, const int *right,
                             int root, int use_tip_states) {
-	if (nshards < 1 || !devices || npatterns < nshards) return NULL;
+	if (nshards < 1 || !devices || npatterns < nshards || !left || !right) {
+		group_fail("phb_group_create: need nshards >= 1, a device list, a topology and at least one pattern per shard");
+		return NULL;
+	}
 	phb_group *g = (phb_group *)calloc(1, sizeof(phb_group));
 	if (!g) return NULL;
 	g->G = nshards, g->T = ntips, g->N = 2 * ntips - 1, g->S = nstate, g->C = ncat, g->P = npatterns, g->root = root;
@@ -47,8 +49,9 @@ phb_group *phb_group_create(int nshards, const int *devices, int ntips, int nsta
 	g->begin = (int *)malloc(sizeof(int) * (nshards + 1));
 	g->gradient = (double *)calloc(g->N, sizeof(double));
 	g->scratch = (double *)calloc(g->N, sizeof(double));
-	if (!g->shard || !g->begin || !g->gradient || !g->scratch || root < 0 || root >= g->N || !right) {
+	if (!g->shard || !g->begin || !g->gradient || !g->scratch || root < 0 || root >= g->N) {
 		phb_group_free(g);
+		phb_internal_fail(root < 0 || root >= 2 * ntips - 1 ? PHB_EINVAL : PHB_ENOMEM, "phb_group_create: bad root or out of memory");
 		return NULL;
 	}
 	g->root_right = right[root];
@@ -77,7 +80,7 @@ int phb_group_size(const phb_group *g) { return g->G; }
 phb_tlk *phb_group_shard(phb_group *g, int shard) { return (shard >= 0 && shard < g->G) ? g->shard[shard] : NULL; }
 
 int phb_group_shard_range(const phb_group *g, int shard, int *begin, int *end) {
-	if (shard < 0 || shard >= g->G) return group_fail("shard");
+	if (shard < 0 || shard >= g->G) return group_fail("phb_group_shard_range: shard out of range");
 	if (begin) *begin = g->begin[shard];
 	if (end) *end = g->begin[shard + 1];
 	return PHB_OK;
@@ -140,7 +143,7 @@ int phb_group_set_option(phb_group *g, int option, int value) {
 		g->unrooted = value != 0;
 		return PHB_OK;
 	}
-	if (option == PHB_OPT_INCREMENTAL && value) return group_fail("resident partials are a single-device mode");
+	if (option == PHB_OPT_INCREMENTAL && value) return group_fail("phb_group_set_option: resident partials (PHB_OPT_INCREMENTAL) are a single-device mode");
 	BROADCAST(phb_tlk_set_option(t, option, value));
 }
 
@@ -180,14 +183,14 @@ static int group_evaluate(phb_group *g, int want_gradient, double *lnl) {
 }
 
 int phb_group_calculate(phb_group *g, double *lnl) {
-	if (!lnl) return group_fail("lnl");
+	if (!lnl) return group_fail("phb_group_calculate: lnl is required");
 	const int rc = group_evaluate(g, 0, &g->lk);
 	*lnl = g->lk;
 	return rc;
 }
 
 int phb_group_gradient(phb_group *g, double *lnl, const double **grad) {
-	if (!grad) return group_fail("grad");
+	if (!grad) return group_fail("phb_group_gradient: grad is required");
 	const int rc = group_evaluate(g, 1, &g->lk);
 	if (rc) return rc;
 	if (isnan(g->lk) || isinf(g->lk)) {

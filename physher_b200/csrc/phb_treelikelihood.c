@@ -91,6 +91,9 @@ static int fail(int code, const char *fmt, ...) {
 static int dev_fail(int rc) { return fail(rc == -3 ? PHB_ENOMEM : (rc == -1 ? PHB_EINVAL : (rc == -4 ? PHB_ESTATE : PHB_ECUDA)), "%s", phbc_last_error()); }
 
 const char *phb_last_error(void) { return g_err; }
+
+/* for the other host translation unit of the library (phb_group.c); not part of the ABI */
+int phb_internal_fail(int code, const char *msg) { return fail(code, "%s", msg); }
 int phb_device_count(void) { return phbc_device_count(); }
 const char *phb_version(void) { return "physher_b200 0.1 (sm_100a)"; }
 
