@@ -55,6 +55,11 @@ extern "C" {
 #define PHB_OPT_INCREMENTAL 7            /* 1: keep all partials resident between calls (like tlk->partials) and recompute only what
                                             update_one_node / set_branch_length dirtied (_calculate_partials, treelikelihood.c:1645-1734) */
 
+#define PHB_OPT_HOST_EXPONENTIALS 8      /* 1: exp(eval * t) of the transition matrices comes from the host's libm -- the exp the reference calls
+                                            (substmodel.c:539) -- instead of the device's: 61-state models have probabilities of order t^2, t^3
+                                            that a one-ulp difference in an exponential moves by 1e-9.  Default 1 for >= 60 states, else 0; node-at-a-time
+                                            and tensor-core paths, single evaluations (batches build their matrices on the device) */
+
 #define PHB_KERNELS_AUTO 0    /* by state count, like the function-pointer dispatch at treelikelihood.c:1067-1165 */
 #define PHB_KERNELS_GENERIC 1 /* node-at-a-time kernels, any state count, materialised upper partials */
 #define PHB_KERNELS_FUSED 2   /* whole-tree walk kernels (4 states) / tensor-core kernels (20, 61 states) */

@@ -24,6 +24,8 @@ struct phbc_ctx {
 	double *h_bl;            // pinned staging
 	int bl_cap;
 	bool have_eigen;
+	double *d_ex, *h_ex;     // [N][C][S] host-computed exp(eval * t) of the branch lengths uploaded last (61-state parity), pinned staging
+	bool ex_valid;
 
 	// node-at-a-time state
 	double *d_P, *d_dP;      // [N][C][S*S]

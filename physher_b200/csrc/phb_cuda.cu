@@ -99,7 +99,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	                ctx->d_freqs, ctx->d_rates, ctx->d_props, ctx->d_bl, ctx->d_P, ctx->d_dP, ctx->d_lower, ctx->d_upper,
 	                ctx->d_sf, ctx->d_lower_ops, ctx->d_upper_ops, ctx->d_parent_ops, ctx->d_post_ops, ctx->d_pre_ops, ctx->d_walk_mats,
 	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch,
-	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl, ctx->d_walk_gstat, ctx->d_nuc4_G, ctx->d_post_tip_order, ctx->d_pre_tip_order, ctx->d_dmma_img, ctx->d_tt_lowers, ctx->d_tt_topo, ctx->d_tt_bad,
+	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl, ctx->d_walk_gstat, ctx->d_nuc4_G, ctx->d_ex, ctx->d_post_tip_order, ctx->d_pre_tip_order, ctx->d_dmma_img, ctx->d_tt_lowers, ctx->d_tt_topo, ctx->d_tt_bad,
 	                ctx->d_tt_ratios, ctx->d_tt_rates, ctx->d_tt_heights, ctx->d_tt_adj, ctx->d_tt_out};
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		if (bufs[i]) cudaFree(bufs[i]);
@@ -112,6 +112,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 		free(ctx->ev_end);
 	}
 	if (ctx->h_bl) cudaFreeHost(ctx->h_bl);
+	if (ctx->h_ex) cudaFreeHost(ctx->h_ex);
 	if (ctx->h_tt) cudaFreeHost(ctx->h_tt);
 	free(ctx->h_freqs);
 	free(ctx->h_qmat);
@@ -334,9 +335,26 @@ extern "C" int phbc_copy_inputs(phbc_ctx *dst, phbc_ctx *src, int matrices, int 
 	return 0;
 }
 
+// exp(eval[k] * bl[n] * rates[c]) for the branch lengths uploaded LAST, [N][C][S], computed by the host (see k_transition_matrices);
+// valid until the next branch-length upload
+extern "C" int phbc_upload_exponentials(phbc_ctx *ctx, const double *ex) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	const size_t n = (size_t)ctx->N * ctx->C * ctx->S;
+	if (!ctx->d_ex) {
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_ex, n * sizeof(double)));
+		PHBC_CHECK(cudaMallocHost((void **)&ctx->h_ex, n * sizeof(double)));
+	}
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));  // the previous copy out of the pinned staging buffer
+	memcpy(ctx->h_ex, ex, n * sizeof(double));
+	PHBC_CHECK(cudaMemcpyAsync(ctx->d_ex, ctx->h_ex, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	ctx->ex_valid = true;
+	return 0;
+}
+
 extern "C" int phbc_upload_branch_lengths(phbc_ctx *ctx, const double *bl, int nbatch) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));
 	const size_t N = ctx->N;
+	ctx->ex_valid = false;
 	if (nbatch > ctx->bl_cap) {
 		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 		cudaFree(ctx->d_bl);
@@ -368,7 +386,8 @@ extern "C" int phbc_upload_branch_lengths(phbc_ctx *ctx, const double *bl, int n
 
 __global__ void k_transition_matrices(int S, int C, int root, const double *__restrict__ evec, const double *__restrict__ eval,
                                       const double *__restrict__ ivec, const double *__restrict__ bl,
-                                      const double *__restrict__ rates, double *__restrict__ Pm, double *__restrict__ dPm) {
+                                      const double *__restrict__ rates, double *__restrict__ Pm, double *__restrict__ dPm,
+                                      const double *__restrict__ ex_host /* [N][C][S] exp(eval * t) from the host's libm, or NULL */) {
 	extern __shared__ double sm[];
 	double *ex = sm;       // exp(lambda_k t)
 	double *lex = sm + S;  // lambda_k exp(lambda_k t)
@@ -377,7 +396,10 @@ __global__ void k_transition_matrices(int S, int C, int root, const double *__re
 	const double t = bl[node] * rates[c];
 	for (int k = threadIdx.x; k < S; k += blockDim.x) {
 		const double l = eval[k];
-		const double e = exp(l * t);
+		// 61-state models have transition probabilities of order t^2, t^3 (codons two or three changes apart) that come out of this sum
+		// by cancellation: one ulp in an exponential moves them by 1e-9 relative, so parity with the reference at 1e-10 needs ITS exp
+		// (the host's libm, phb_treelikelihood.c:upload_bl), not just an equally good one
+		const double e = ex_host ? ex_host[((size_t)node * C + c) * S + k] : exp(l * t);
 		ex[k] = e;
 		lex[k] = l * e;
 	}
@@ -615,7 +637,7 @@ static int phbc_launch_transition_matrices(phbc_ctx *ctx, int batch_index) {
 	const int threads = S * S >= 256 ? 256 : (S * S >= 64 ? 64 : 32);
 	k_transition_matrices<<<grid, threads, 2 * S * sizeof(double), ctx->stream>>>(
 	    S, ctx->C, ctx->root, ctx->d_evec, ctx->d_eval, ctx->d_ivec, ctx->d_bl + (size_t)batch_index * ctx->N, ctx->d_rates,
-	    ctx->d_P, ctx->d_dP);
+	    ctx->d_P, ctx->d_dP, (ctx->ex_valid && batch_index == 0) ? ctx->d_ex : NULL);
 	ctx->launches++;
 	PHBC_CHECK(cudaGetLastError());
 	return 0;

@@ -109,6 +109,7 @@ int phbc_upload_matrices(phbc_ctx *ctx, const double *P, const double *dP);
 int phbc_upload_freqs(phbc_ctx *ctx, const double *freqs);
 int phbc_upload_site_model(phbc_ctx *ctx, const double *rates, const double *props);
 int phbc_upload_branch_lengths(phbc_ctx *ctx, const double *bl, int nbatch); /* [nbatch][N], pinned staging */
+int phbc_upload_exponentials(phbc_ctx *ctx, const double *ex); /* [N][C][S] exp(eval * bl * rate) from the host's libm, for the vector uploaded last */
 /* device-to-device copy of the bulky inputs (tips, weights, explicit matrices, time-tree tables) between same-shaped contexts */
 int phbc_copy_inputs(phbc_ctx *dst, phbc_ctx *src, int matrices, int time_tree);
 

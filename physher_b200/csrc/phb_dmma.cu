@@ -71,9 +71,11 @@ __device__ __forceinline__ bool dm_state_tip(const Bufs &b, int idx) { return id
 // an operand, or TRANSPOSED [S][NP] followed by the row sums [NP] for state tips, so that one tip state selects a contiguous
 // column of M (16-byte gathers) and an unknown state selects the row sums (treelikelihoodX.c:878-1001).
 // grid (N, C, 2: P | dP), images laid out [which][node][category][IMG]; one more image behind them: the rate matrix Q (k_dmma_pack_q).
+// adjoint (message form): the dP image of an INTERNAL node is stored transposed and weighted, [j][i] = f_i dP[i][j], the B operand of
+// Z[j] = sum_i U[i] f_i dP[i][j] -- the node's own branch gradient is then sum_j L[j] Z[j] with the reference's dP entries themselves.
 template <class Sh>
 __global__ void k_dmma_pack(int T, int N, int C, int root, int tip_states, const double *__restrict__ Pm, const double *__restrict__ dPm,
-                            double *__restrict__ img) {
+                            double *__restrict__ img, int adjoint, const double *__restrict__ freqs, int include_root_freqs) {
 	const int n = blockIdx.x, c = blockIdx.y, which = blockIdx.z;
 	const double *src = (which ? dPm : Pm) + ((size_t)n * C + c) * Sh::S * Sh::S;
 	double *dst = img + (((size_t)which * N + n) * C + c) * Sh::IMG;
@@ -96,6 +98,11 @@ __global__ void k_dmma_pack(int T, int N, int C, int root, int tip_states, const
 			dst[Sh::S * Sh::NP + i] = acc;
 		}
 		for (int e = Sh::TIP_IMG + threadIdx.x; e < Sh::IMG; e += blockDim.x) dst[e] = 0.0;
+	} else if (which == 1 && adjoint && n >= T) {
+		for (int e = threadIdx.x; e < Sh::IMG; e += blockDim.x) {
+			const int j = e / Sh::LD, i = e - j * Sh::LD;
+			dst[e] = (e < Sh::MAT && i < Sh::S && j < Sh::S) ? (include_root_freqs ? 1.0 : freqs[i]) * src[i * Sh::S + j] : 0.0;
+		}
 	} else {
 		for (int e = threadIdx.x; e < Sh::IMG; e += blockDim.x) {
 			const int i = e / Sh::LD, j = e - i * Sh::LD;
@@ -736,11 +743,15 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 
 // ---------------------------------------------------------------------------------------------
 // k_dmma_upper_msg: per PARENT n with children a, b.  W = P_n U_n (DMMA), the children's messages M_a, M_b come straight from
-// the lower buffers (or the tips' matrix columns), U_a = W o M_b and U_b = W o M_a are stored for internal children, and the branch
-// gradient terms are sum_i f_i U_x[i] (Q M_x)[i] w_k / L_k with Q M_x one more DMMA product per INTERNAL child (a tip's derivative
-// column is gathered from its transposed dP image).  Three products share one k-loop; the D-fragment copies of M_a, M_b are picked
-// out of the staged chunks as they pass, so each message is read from HBM once.
-// Shared-memory image slots: 0 P_n | 1 a: tip image, else Q | 2 a: tip dP image | 3 b: tip image, else Q when a is a tip | 4 b: tip dP image.
+// the lower buffers (or the tips' matrix columns), U_a = W o M_b and U_b = W o M_a are stored for internal children.  Branch gradients
+// in ADJOINT form: the op of n reduces n's OWN branch, sum_i f_i U_n[i] (dP_n L_n)[i] = sum_j L_n[j] Z[j] with L_n = M_a o M_b and
+// Z = U_n (f o dP_n) -- a second DMMA product that shares the A fragments of W -- so an internal branch sees the reference's dP
+// entries themselves (Q (P L) differs from dP L by 1e-9 relative where codon probabilities of order t^3 dominate a pattern) at two
+// products per op instead of up to three; the branches of TIP children are reduced here too, from the tips' transposed dP images.
+// The accumulator-layout copies of M_a, M_b are picked out of the staged chunks as they pass, so each message is read from HBM once.
+// Shared-memory image slots: 0 P_n | 1 a: tip image | 2 a: tip dP image | 3 b: tip image | 4 b: tip dP image; the adjoint image of n
+// sits in slot 1 when a is internal, else in slot 3 when b is internal, else (both tips) in a sixth slot at 20 states and in slot 1 at
+// 61 states, where five images are all an SM can hold -- a's tip image is then read from global memory (one L2-resident column per pattern).
 // ---------------------------------------------------------------------------------------------
 template <int S, int MT, int NSPLIT, int WM>
 __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, const phbc_parent_op *__restrict__ ops, const double *__restrict__ img,
@@ -758,28 +769,32 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 	const bool is_root_rt = op.flags & 1;
 	const bool a_tip_rt = op.a < b.T, b_tip_rt = op.b < b.T;
 	double *mP = sm, *mA = sm + Sh::IMG, *dA = sm + 2 * Sh::IMG, *mB = sm + 3 * Sh::IMG, *dB = sm + 4 * Sh::IMG;
-	const double *mQ = !a_tip_rt ? mA : mB;  // only read when a child is internal
+	const bool cherry_rt = a_tip_rt && b_tip_rt;
+	const bool sixth = nslots >= 6;  // room for a slot of its own (20 states); at 61 states five images are all an SM can hold
+	const double *mZ = !a_tip_rt ? mA : (!b_tip_rt ? mB : (sixth ? sm + 5 * Sh::IMG : mA));  // adjoint image (f o dP_n) transposed; not staged at the root
+	const double *tipA = (cherry_rt && !is_root_rt && !sixth) ? img + ((size_t)op.a * b.C + c) * Sh::IMG : mA;  // a's transposed P image
 	double *aux = sm + nslots * Sh::IMG;  // 2 slots when both children are internal (P_n, Q), else 5
 	double *fq = aux, *wroot = aux + Sh::NP, *red = aux + 2 * Sh::NP;
 	const double *rsA = dA + Sh::S * Sh::NP, *rsB = dB + Sh::S * Sh::NP;
 	if (threadIdx.x == 0) {
 		const size_t dimg = (size_t)b.N * b.C * Sh::IMG;
-		const double *qimg = img + 2 * dimg;
 		mbar_init(bar, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-		const int nimg = (is_root_rt ? 0 : 1) + (a_tip_rt ? 2 : 0) + (b_tip_rt ? 2 : 0) + ((!a_tip_rt || !b_tip_rt) ? 1 : 0);
+		const bool a_img = a_tip_rt && tipA == mA;  // a's tip image goes to shared memory unless the adjoint image needs its slot
+		const int nimg = (is_root_rt ? 0 : 2) + (a_tip_rt ? 1 : 0) + (a_img ? 1 : 0) + (b_tip_rt ? 2 : 0);
 		mbar_expect_tx(bar, nimg * Sh::IMG * 8);
-		if (!is_root_rt) bulk_g2s(mP, img + ((size_t)op.node * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		if (!is_root_rt) {
+			bulk_g2s(mP, img + ((size_t)op.node * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+			bulk_g2s(const_cast<double *>(mZ), img + dimg + ((size_t)op.node * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+		}
 		if (a_tip_rt) {
-			bulk_g2s(mA, img + ((size_t)op.a * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
+			if (a_img) bulk_g2s(mA, img + ((size_t)op.a * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
 			bulk_g2s(dA, img + dimg + ((size_t)op.a * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
 		}
 		if (b_tip_rt) {
 			bulk_g2s(mB, img + ((size_t)op.b * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
 			bulk_g2s(dB, img + dimg + ((size_t)op.b * b.C + c) * Sh::IMG, Sh::IMG * 8, bar);
 		}
-		if (!a_tip_rt) bulk_g2s(mA, qimg, Sh::IMG * 8, bar);
-		else if (!b_tip_rt) bulk_g2s(mB, qimg, Sh::IMG * 8, bar);
 	}
 	for (int i = threadIdx.x; i < Sh::NP; i += blockDim.x) {
 		const double f = i < S ? freqs[i] : 0.0;
@@ -796,15 +811,14 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 	double *Ua = b.upper + ((size_t)op.a * b.C + c) * (size_t)b.P * S;
 	double *Ub = b.upper + ((size_t)op.b * b.C + c) * (size_t)b.P * S;
 	const int ntiles = (b.P + TP - 1) / TP;
-	double tot_a = 0.0, tot_b = 0.0;
+	double tot_a = 0.0, tot_b = 0.0, tot_n = 0.0;
 	using AS = AStage<Sh, MT, 3>;
 	constexpr int GT = 32 * NSPLIT;
-	double *abuf = red + 2 * NWARPS + wm * AS::NSTAGE * AS::STG;  // ring operands: U_n | M_b | M_a
+	double *abuf = red + 4 * NWARPS + wm * AS::NSTAGE * AS::STG;  // ring operands: U_n | M_b | M_a
 	const int gl = (warp % NSPLIT) * 32 + lane;
 	mbar_wait(bar, 0);
 	dispatch3(is_root_rt, a_tip_rt, b_tip_rt, [&](auto ROOT, auto ATIP, auto BTIP) {
 	constexpr bool is_root = decltype(ROOT)::value, a_tip = decltype(ATIP)::value, b_tip = decltype(BTIP)::value;
-	constexpr bool need_q = !a_tip || !b_tip;
 	AFill<Sh, MT, 3, GT> plan;
 	plan.init(gl);
 	int f_tile = blockIdx.x, f_ch = 0, f_stage = 0;
@@ -823,11 +837,10 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 #pragma unroll
 	for (int pf = 0; pf < AS::NSTAGE - 1; pf++) fill_next();
 	int c_stage = 0;
-	double bP = 0.0, bQ = 0.0;
+	double bP = 0.0, bZ = 0.0;
 	{
 		const int off = (n0 * 8 + r) * Sh::LD + q;
-		if (!is_root) bP = mP[off];
-		if (need_q) bQ = mQ[off];
+		if (!is_root) bP = mP[off], bZ = mZ[off];
 	}
 	for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
 		const int p0 = tile * TP + wm * MT * 8;
@@ -838,12 +851,11 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 			wk[m] = p < b.P ? __ldg(weights + p) : 0.0;
 			lk[m] = p < b.P ? __ldg(pattern_lnl + p) : 0.0;
 		}
-		double W[MT][NTW][2], Mb[MT][NTW][2], Db[MT][NTW][2], Ma[MT][NTW][2], Da[MT][NTW][2];
+		double W[MT][NTW][2], Z[MT][NTW][2], Mb[MT][NTW][2], Ma[MT][NTW][2];
 		zero_acc<MT, NTW>(W);
+		zero_acc<MT, NTW>(Z);
 		zero_acc<MT, NTW>(Mb);
 		zero_acc<MT, NTW>(Ma);
-		zero_acc<MT, NTW>(Db);
-		zero_acc<MT, NTW>(Da);
 		if (!(is_root && a_tip && b_tip))
 #pragma unroll
 		for (int ch = 0; ch < Sh::NCH; ch++) {
@@ -852,10 +864,8 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 			fill_next();
 			const double *st = abuf + c_stage * AS::STG;
 			c_stage = c_stage + 1 == AS::NSTAGE ? 0 : c_stage + 1;
-			double cw[MT][Sh::KCH], cb[MT][Sh::KCH], ca[MT][Sh::KCH];
+			double cw[MT][Sh::KCH];
 			if (!is_root) read_frags<Sh, MT, 3>(st, lane, cw);
-			if (!b_tip) read_frags<Sh, MT, 3>(st + AS::OPB, lane, cb);
-			if (!a_tip) read_frags<Sh, MT, 3>(st + 2 * AS::OPB, lane, ca);
 			// the messages again in accumulator layout (row 8 m + r, columns (n0 + j) 8 + 2 q, + 1) while their chunk is staged
 #pragma unroll
 			for (int j = 0; j < NTW; j++) {
@@ -882,19 +892,13 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 					for (int j = 0; j < NTW; j++) {
 						const int nj = j + 1 < NTW ? j + 1 : 0, nt = j + 1 < NTW ? t : (t + 1 < Sh::KT ? t + 1 : 0);
 						const int noff = ((n0 + nj) * 8 + r) * Sh::LD + 4 * nt + q;
-						double nP = 0.0, nQ = 0.0;
-						if (!is_root) nP = mP[noff];
-						if (need_q) nQ = mQ[noff];
+						double nP = 0.0, nZ = 0.0;
 						if (!is_root) {
+							nP = mP[noff], nZ = mZ[noff];
 dmma_mtiles<MT, NTW, Sh::KCH>(W, cw, j, tt, bP);
+dmma_mtiles<MT, NTW, Sh::KCH>(Z, cw, j, tt, bZ);
 						}
-						if (!b_tip) {
-dmma_mtiles<MT, NTW, Sh::KCH>(Db, cb, j, tt, bQ);
-						}
-						if (!a_tip) {
-dmma_mtiles<MT, NTW, Sh::KCH>(Da, ca, j, tt, bQ);
-						}
-						bP = nP, bQ = nQ;
+						bP = nP, bZ = nZ;
 					}
 				}
 			}
@@ -908,6 +912,7 @@ dmma_mtiles<MT, NTW, Sh::KCH>(Da, ca, j, tt, bQ);
 					W[m][j][0] = wroot[i], W[m][j][1] = wroot[i + 1];
 				}
 		}
+		double Da[MT][NTW][2], Db[MT][NTW][2];  // dP columns of the TIP children (dead code for internal children)
 		if (b_tip) {
 			const uint8_t *st = b.tip_states + (size_t)op.b * b.P;
 			tip_gather<Sh, MT, NTW, true>(st, mB, nullptr, p0, b.P, n0, lane, Mb);
@@ -915,46 +920,54 @@ dmma_mtiles<MT, NTW, Sh::KCH>(Da, ca, j, tt, bQ);
 		}
 		if (a_tip) {
 			const uint8_t *st = b.tip_states + (size_t)op.a * b.P;
-			tip_gather<Sh, MT, NTW, true>(st, mA, nullptr, p0, b.P, n0, lane, Ma);
+			tip_gather<Sh, MT, NTW, true>(st, tipA, nullptr, p0, b.P, n0, lane, Ma);
 			tip_gather<Sh, MT, NTW, false>(st, dA, rsA, p0, b.P, n0, lane, Da);
 		}
+		double gn[MT];
 #pragma unroll
-		for (int m = 0; m < MT; m++)
+		for (int m = 0; m < MT; m++) {
+			gn[m] = 0.0;
 #pragma unroll
 			for (int j = 0; j < NTW; j++) {
+				// n's own branch: sum_j L_n[j] Z[j], L_n = M_a o M_b (the weights f sit in the adjoint image; padding columns are zero)
+				if (!is_root) gn[m] = fma(Ma[m][j][0] * Mb[m][j][0], Z[m][j][0], fma(Ma[m][j][1] * Mb[m][j][1], Z[m][j][1], gn[m]));
 				const double ua0 = W[m][j][0] * Mb[m][j][0], ua1 = W[m][j][1] * Mb[m][j][1];
 				const double ub0 = W[m][j][0] * Ma[m][j][0], ub1 = W[m][j][1] * Ma[m][j][1];
 				Mb[m][j][0] = ua0, Mb[m][j][1] = ua1;
 				Ma[m][j][0] = ub0, Ma[m][j][1] = ub1;
 			}
+		}
 		if (!a_tip) store_tile<Sh, MT, NTW>(Ua, p0, b.P, n0, lane, Mb);
 		if (!b_tip) store_tile<Sh, MT, NTW>(Ub, p0, b.P, n0, lane, Ma);
 #pragma unroll
 		for (int m = 0; m < MT; m++) {
-			double ga = 0.0, gb = 0.0;
+			double ga = 0.0, gb = 0.0, g0 = gn[m];
 #pragma unroll
 			for (int j = 0; j < NTW; j++) {
 				const int i = (n0 + j) * 8 + 2 * q;
-				ga = fma(fq[i] * Mb[m][j][0], Da[m][j][0], fma(fq[i + 1] * Mb[m][j][1], Da[m][j][1], ga));
-				gb = fma(fq[i] * Ma[m][j][0], Db[m][j][0], fma(fq[i + 1] * Ma[m][j][1], Db[m][j][1], gb));
+				if (a_tip) ga = fma(fq[i] * Mb[m][j][0], Da[m][j][0], fma(fq[i + 1] * Mb[m][j][1], Da[m][j][1], ga));
+				if (b_tip) gb = fma(fq[i] * Ma[m][j][0], Db[m][j][0], fma(fq[i + 1] * Ma[m][j][1], Db[m][j][1], gb));
 			}
-			ga += __shfl_xor_sync(0xffffffffu, ga, 1), gb += __shfl_xor_sync(0xffffffffu, gb, 1);
-			ga += __shfl_xor_sync(0xffffffffu, ga, 2), gb += __shfl_xor_sync(0xffffffffu, gb, 2);
+			ga += __shfl_xor_sync(0xffffffffu, ga, 1), gb += __shfl_xor_sync(0xffffffffu, gb, 1), g0 += __shfl_xor_sync(0xffffffffu, g0, 1);
+			ga += __shfl_xor_sync(0xffffffffu, ga, 2), gb += __shfl_xor_sync(0xffffffffu, gb, 2), g0 += __shfl_xor_sync(0xffffffffu, g0, 2);
 			const double wl = wk[m] / exp(lk[m]);
 			tot_a = fma(ga, wl, tot_a);
 			tot_b = fma(gb, wl, tot_b);
+			tot_n = fma(g0, wl, tot_n);
 		}
 	}
 	});
-	tot_a = q == 0 ? tot_a : 0.0, tot_b = q == 0 ? tot_b : 0.0;
-	tot_a = phb_warp_sum(tot_a), tot_b = phb_warp_sum(tot_b);
-	if (lane == 0) red[2 * warp] = tot_a, red[2 * warp + 1] = tot_b;
+	tot_a = q == 0 ? tot_a : 0.0, tot_b = q == 0 ? tot_b : 0.0, tot_n = q == 0 ? tot_n : 0.0;
+	tot_a = phb_warp_sum(tot_a), tot_b = phb_warp_sum(tot_b), tot_n = phb_warp_sum(tot_n);
+	if (lane == 0) red[3 * warp] = tot_a, red[3 * warp + 1] = tot_b, red[3 * warp + 2] = tot_n;
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		double sa = 0.0, sb = 0.0;
-		for (int w = 0; w < NWARPS; w++) sa += red[2 * w], sb += red[2 * w + 1];
-		partial[((size_t)op.a * b.C + c) * pstride + blockIdx.x] = sa;
-		partial[((size_t)op.b * b.C + c) * pstride + blockIdx.x] = sb;
+		double sa = 0.0, sb = 0.0, sn = 0.0;
+		for (int w = 0; w < NWARPS; w++) sa += red[3 * w], sb += red[3 * w + 1], sn += red[3 * w + 2];
+		// every non-root node is written exactly once: a tip by its parent's op, an internal node by its own
+		if (a_tip_rt) partial[((size_t)op.a * b.C + c) * pstride + blockIdx.x] = sa;
+		if (b_tip_rt) partial[((size_t)op.b * b.C + c) * pstride + blockIdx.x] = sb;
+		if (!is_root_rt) partial[((size_t)op.node * b.C + c) * pstride + blockIdx.x] = sn;
 	}
 }
 
@@ -1001,7 +1014,7 @@ static int pick_chunks(int slots, int units, int ntiles) {
 
 // packed matrix images [P | dP][node][category][IMG] from the per-node matrices
 template <int S>
-static int dmma_pack(phbc_ctx *ctx) {
+static int dmma_pack(phbc_ctx *ctx, bool adjoint = false, int include_root_freqs = 0) {
 	using Sh = DmmaShape<S>;
 	const int C = ctx->C, N = ctx->N;
 	const size_t img_bytes = ((size_t)2 * N * C + 1) * Sh::IMG * sizeof(double);
@@ -1013,7 +1026,8 @@ static int dmma_pack(phbc_ctx *ctx) {
 		PHBC_CHECK(cudaMalloc((void **)&ctx->d_dmma_img, img_bytes));
 		ctx->dmma_img_bytes = img_bytes;
 	}
-	k_dmma_pack<Sh><<<dim3(N, C, 2), 128, 0, ctx->stream>>>(ctx->T, N, C, ctx->root, ctx->tip_kind == PHBC_TIP_STATES, ctx->d_P, ctx->d_dP, ctx->d_dmma_img);
+	k_dmma_pack<Sh><<<dim3(N, C, 2), 128, 0, ctx->stream>>>(ctx->T, N, C, ctx->root, ctx->tip_kind == PHBC_TIP_STATES, ctx->d_P, ctx->d_dP, ctx->d_dmma_img,
+	                                                         adjoint ? 1 : 0, ctx->d_freqs, include_root_freqs);
 	ctx->launches++;
 	if (ctx->have_eigen) {
 		k_dmma_pack_q<Sh><<<1, 128, 0, ctx->stream>>>(ctx->d_qmat, ctx->d_dmma_img + (size_t)2 * N * C * Sh::IMG);
@@ -1114,11 +1128,11 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 		const bool wide = split && kind == 0 && Cf::UWM_II != Cf::UWM;
 		v.fn = wide ? (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM_II> : (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM>;
 		v.wm = wide ? Cf::UWM_II : Cf::UWM;
-		v.nslots = (split && kind == 0) ? 2 : 5;
+		v.nslots = (split && kind == 0) ? 2 : (S <= 32 ? 6 : 5);
 		const int warps = v.wm * Cf::UNSPLIT;
 		v.threads = 32 * warps;
 		v.tiles = (P + v.wm * Cf::UMT * 8 - 1) / (v.wm * Cf::UMT * 8);
-		v.smem = 128 + ((size_t)v.nslots * Sh::IMG + 2 * Sh::NP + 2 * warps + (size_t)v.wm * AStage<Sh, Cf::UMT, 3>::NSTAGE * AStage<Sh, Cf::UMT, 3>::STG) * sizeof(double);
+		v.smem = 128 + ((size_t)v.nslots * Sh::IMG + 2 * Sh::NP + 4 * warps + (size_t)v.wm * AStage<Sh, Cf::UMT, 3>::NSTAGE * AStage<Sh, Cf::UMT, 3>::STG) * sizeof(double);
 	}
 	for (int kind = 0; kind < 3; kind++) {
 		Variant &v = var[kind];
@@ -1175,10 +1189,10 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	int rc;
 	if ((rc = phbc_generic_prepare(ctx, o))) return rc;
 	Bufs b = phbc_make_bufs(ctx);
-	if ((rc = dmma_pack<S>(ctx))) return rc;
 	// message form: the fast path (unscaled, state tips, eigen system, upper partials not needed as such afterwards)
 	const bool msg = !o->scale && !o->materialize_uppers && ctx->tip_kind == PHBC_TIP_STATES && ctx->have_eigen && !o->explicit_matrices &&
 	                 getenv("PHB_DMMA_LEGACY") == NULL;
+	if ((rc = dmma_pack<S>(ctx, msg, o->include_root_freqs))) return rc;
 	ctx->lower_is_message = msg;
 	ctx->node_evals++;
 	if ((rc = phbc_time_begin(ctx))) return rc;

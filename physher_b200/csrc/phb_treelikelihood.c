@@ -57,6 +57,8 @@ struct phb_tlk {
 	int *post_tip_order, *pre_tip_order, *post_chunk_tip0, *pre_chunk_tip0;
 	int post_first_tips, pre_first_tips;
 	int have_time_tree;
+	int host_exp;  /* exponentials of the transition matrices from the host's libm (PHB_OPT_HOST_EXPONENTIALS; default on for >= 60 states) */
+	double *ex_buf; /* [N][C][S] */
 	int sweep_valid; /* the node-at-a-time buffers hold a full evaluation of the current inputs (phb_tlk_matrix_gradient) */
 
 	/* resident node-at-a-time partials (PHB_OPT_INCREMENTAL): which device buffers hold values of the CURRENT inputs */
@@ -672,6 +674,7 @@ phb_tlk *phb_tlk_create(int ntips, int nstate, int ncat, int npatterns, const in
 	t->compat_scaled_gradient = 0;
 	t->unrooted = 1;
 	t->kernels = PHB_KERNELS_AUTO;
+	t->host_exp = nstate >= 60;
 	int rc = build_level_schedules(t);
 	if (rc == PHB_OK) rc = build_walk_schedules(t);
 	if (rc == PHB_OK) {
@@ -717,6 +720,7 @@ void phb_tlk_free(phb_tlk *t) {
 	free(t->post_chunk_tip0);
 	free(t->pre_chunk_tip0);
 	free(t->lower_ok), free(t->upper_ok), free(t->upper_op_of), free(t->sub_ops), free(t->sub_level_off), free(t->path);
+	free(t->ex_buf);
 	free(t->h_evec), free(t->h_eval), free(t->h_ivec), free(t->h_freqs), free(t->h_rates), free(t->h_props);
 	free(t->st_bl), free(t->st_evec), free(t->st_eval), free(t->st_ivec), free(t->st_freqs), free(t->st_rates), free(t->st_props);
 	free(t);
@@ -759,6 +763,7 @@ phb_tlk *phb_tlk_clone(phb_tlk *src, int device) {
 	t->unrooted = src->unrooted;
 	t->kernels = src->kernels;
 	t->incremental = src->incremental;
+	t->host_exp = src->host_exp;
 	if (src->prepared_gradient) phb_tlk_initialize_gradient(t, src->prepared_gradient);
 	t->eigen_changed = t->freqs_changed = t->site_changed = t->bl_changed = 0;
 	phb_tlk_update_all_nodes(t);
@@ -953,6 +958,11 @@ int phb_tlk_set_option(phb_tlk *t, int option, int value) {
 		t->resident = 0;
 		phb_tlk_update_all_nodes(t);
 		return PHB_OK;
+	case PHB_OPT_HOST_EXPONENTIALS:
+		if (t->host_exp == (value != 0)) return PHB_OK;
+		t->host_exp = value != 0;
+		t->all_dirty = 1;
+		break;
 	case PHB_OPT_TIMING: {
 		int rc = phbc_set_timing(t->ctx, value);
 		if (rc) return dev_fail(rc);
@@ -991,12 +1001,36 @@ static void fill_opts(const phb_tlk *t, phbc_eval_opts *o, int want_gradient, in
 	o->batch_index = batch_index;
 }
 
+/*
+ * Branch lengths of a single evaluation to the device -- and, for models whose tiny transition probabilities come out of the eigen
+ * sum by cancellation (61 states: codons two or three changes apart, P ~ t^2, t^3), the exponentials exp(eval_k * bl_n * rate_c) from
+ * THIS host's libm, the one the reference calls (substmodel.c:539): a one-ulp difference between two correct exp implementations
+ * moves those entries by 1e-9 relative and the gradient of a codon alignment by up to 3e-8, so 1e-10 parity needs the same exp.
+ * N * C * S values per evaluation (12,139 at C5), nothing next to the evaluation itself.
+ */
+static int upload_bl(phb_tlk *t) {
+	int rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1);
+	if (rc) return rc;
+	if (t->host_exp && t->have_eigen && !t->have_matrices && t->h_eval && t->h_rates) {
+		const int N = t->N, C = t->C, S = t->S;
+		if (!t->ex_buf && !(t->ex_buf = (double *)malloc(sizeof(double) * (size_t)N * C * S))) return -3;
+		for (int n = 0; n < N; n++)
+			for (int c = 0; c < C; c++) {
+				const double tt = t->bl[n] * t->h_rates[c];
+				double *dst = t->ex_buf + ((size_t)n * C + c) * S;
+				for (int k = 0; k < S; k++) dst[k] = exp(t->h_eval[k] * tt);
+			}
+		rc = phbc_upload_exponentials(t->ctx, t->ex_buf);
+	}
+	return rc;
+}
+
 /* one full evaluation with the reference's NaN / inf handling (treelikelihood.c:1489-1519) */
 static int evaluate_once(phb_tlk *t, int want_gradient, double *lnl, double *grad_out) {
 	int rc = check_ready(t);
 	if (rc) return rc;
 	if (t->bl_dirty || 1) {
-		if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+		if ((rc = upload_bl(t))) return dev_fail(rc);
 		t->bl_dirty = 0;
 	}
 	phbc_eval_opts o;
@@ -1047,7 +1081,7 @@ static void mark_clean(phb_tlk *t) {
 static int resident_full(phb_tlk *t, int want_gradient, double *lnl, double *grad_out) {
 	int rc = check_ready(t);
 	if (rc) return rc;
-	if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+	if ((rc = upload_bl(t))) return dev_fail(rc);
 	t->bl_dirty = 0;
 	t->resident = 0;
 	for (int attempt = 0; attempt < 2; attempt++) {
@@ -1118,7 +1152,7 @@ static int resident_calculate(phb_tlk *t, double *lnl) {
 				if (!t->lower_ok[t->lower_ops[k].out]) t->sub_ops[nops++] = t->lower_ops[k];
 		}
 		t->sub_level_off[t->n_lower_levels] = nops;
-		if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+		if ((rc = upload_bl(t))) return dev_fail(rc);
 		t->bl_dirty = 0;
 		phbc_eval_opts o;
 		fill_opts_resident(t, &o, 0);
@@ -1338,7 +1372,7 @@ int phb_tlk_get_partials(phb_tlk *t, int index, double *out) {
 		/* tlk->partials as the reference holds them: a node-at-a-time evaluation with every upper partial materialised (the fused paths
 		 * keep no partials, or keep messages P L in their place) */
 		if ((rc = check_ready(t))) return rc;
-		if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+		if ((rc = upload_bl(t))) return dev_fail(rc);
 		phbc_eval_opts o;
 		fill_opts_resident(t, &o, 1);
 		t->resident = 0;
@@ -1361,7 +1395,7 @@ int phb_tlk_get_matrices(phb_tlk *t, double *P, double *dP) {
 int phb_tlk_gradient_device(phb_tlk *t, double *out_device) {
 	int rc = check_ready(t);
 	if (rc) return rc;
-	if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+	if ((rc = upload_bl(t))) return dev_fail(rc);
 	phbc_eval_opts o;
 	fill_opts(t, &o, 1, 0);
 	t->resident = 0;
@@ -1382,7 +1416,7 @@ int phb_tlk_gradient_device(phb_tlk *t, double *out_device) {
 int phb_tlk_evaluate_launch(phb_tlk *t, int want_gradient) {
 	int rc = check_ready(t);
 	if (rc) return rc;
-	if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+	if ((rc = upload_bl(t))) return dev_fail(rc);
 	t->bl_dirty = 0;
 	phbc_eval_opts o;
 	fill_opts(t, &o, want_gradient != 0, 0);
@@ -1456,7 +1490,7 @@ int phb_tlk_matrix_gradient(phb_tlk *t, int nsets, const double *M, double *out)
 	if (nsets < 1 || !M || !out) return fail(PHB_EINVAL, "nsets >= 1, M and out are required");
 	int rc = check_ready(t);
 	if (rc) return rc;
-	if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+	if ((rc = upload_bl(t))) return dev_fail(rc);
 	t->bl_dirty = 0;
 	for (int attempt = 0; attempt < 2; attempt++) {
 		phbc_eval_opts o;
@@ -1487,7 +1521,7 @@ int phb_tlk_root_frequency_gradient(phb_tlk *t, double *out) {
 	if (rc) return rc;
 	const int resident_ok = t->incremental && t->resident && !t->all_dirty && !t->update;
 	if (!resident_ok && (t->update || !t->sweep_valid)) { /* a node-at-a-time evaluation leaves the root partial on the device */
-		if ((rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1))) return dev_fail(rc);
+		if ((rc = upload_bl(t))) return dev_fail(rc);
 		t->bl_dirty = 0;
 		t->resident = 0;
 		for (int attempt = 0; attempt < 2; attempt++) {

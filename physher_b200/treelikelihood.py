@@ -24,6 +24,7 @@ OPT_UNROOTED = 3
 OPT_KERNELS = 4
 OPT_SCALING_THRESHOLD_EXP = 5
 OPT_TIMING = 6
+OPT_HOST_EXPONENTIALS = 8
 OPT_INCREMENTAL = 7
 KERNELS_AUTO, KERNELS_GENERIC, KERNELS_FUSED = 0, 1, 2
 

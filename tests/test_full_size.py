@@ -1,0 +1,129 @@
+"""BASELINE.json's configurations at FULL size on the GPU, checked through properties that do not need the oracle to run the whole
+workload (it would take hours): additivity over pattern shards with one shard pinned on the oracle, exact weight linearity, the
+per-pattern checksum, invariance under a pattern permutation, central finite differences of lnL against the analytic gradient, and
+agreement between kernel families.  Inputs are bench.py's (same seeds, same generator)."""
+import numpy as np
+import pytest
+
+import bench
+import physher_b200 as phb
+from oracle import oracle as O
+from tests.util import RTOL, grad_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _make(cfg, patterns, weights, kernels=phb.KERNELS_AUTO, bl=None, inputs=None):
+    topo, bl0, m, rates, props = inputs
+    tlk = phb.SingleTreeLikelihood(topo.left, topo.right, topo.root, cfg["states"], cfg["cats"], patterns.shape[1], use_tip_states=True, device=0)
+    tlk.set_option(phb.treelikelihood.OPT_KERNELS, kernels)
+    tlk.set_tip_states(patterns)
+    tlk.set_pattern_weights(weights)
+    tlk.set_eigen(m.evec, m.eval, m.ivec)
+    tlk.set_frequencies(m.freqs)
+    tlk.set_site_model(rates, props)
+    tlk.set_branch_lengths(bl0 if bl is None else bl)
+    return tlk
+
+
+def _fd_check(tlk, bl, grad, topo, rng, nbranches=3, h=1e-6):
+    cands = [n for n in range(bl.size) if n != topo.root and n != topo.right[topo.root]]
+    for n in rng.choice(cands, nbranches, replace=False):
+        up, dn = bl.copy(), bl.copy()
+        up[n] += h
+        dn[n] -= h
+        tlk.set_branch_lengths(up)
+        lu = tlk.calculate()
+        tlk.set_branch_lengths(dn)
+        ld = tlk.calculate()
+        fd = (lu - ld) / (2 * h)
+        # truncation ~ h^2, rounding of the two lnL values ~ a few ulp of |lnL| divided by h
+        assert abs(fd - grad[n]) <= 2e-5 * abs(grad[n]) + 8e-15 * abs(lu) / h, (int(n), fd, grad[n])
+    tlk.set_branch_lengths(bl)
+
+
+def test_c2_full_size_properties():
+    """GTR+G4, 1000 taxa x 100,000 patterns (BASELINE config 2)"""
+    cfg = dict(bench.CONFIGS["c2"])
+    topo, bl, m, rates, props, patterns, weights = bench.make_inputs(cfg, 0)
+    inputs = (topo, bl, m, rates, props)
+    P, N = cfg["patterns"], 2 * cfg["taxa"] - 1
+    rng = np.random.default_rng(11)
+    weights = rng.integers(1, 4, P).astype(np.float64)  # non-trivial multiplicities
+    tlk = _make(cfg, patterns, weights, inputs=inputs)
+    lnl, g = tlk.calculate(), tlk.gradient().copy()
+    assert np.isfinite(lnl) and np.isfinite(g).all() and not tlk.rescaling()
+    # checksum of checksums: the weighted sum of the per-pattern log likelihoods is lnL
+    plk = tlk.pattern_log_likelihoods()
+    assert rel_err(float(np.dot(weights, plk)), lnl) < 1e-12
+    # additivity over pattern shards; the first shard (400 patterns) is pinned on the oracle
+    edges = [0, 400, 33_333, 70_001, P]
+    acc_l, acc_g = 0.0, np.zeros(N)
+    for k, (b, e) in enumerate(zip(edges, edges[1:])):
+        sub = _make(cfg, np.ascontiguousarray(patterns[:, b:e]), weights[b:e], inputs=inputs)
+        sl, sg = sub.calculate(), sub.gradient().copy()
+        if k == 0:
+            pb = O.Problem(left=topo.left, right=topo.right, parent=topo.parent, root=topo.root, nstate=4, tip_states=np.ascontiguousarray(patterns[:, b:e]),
+                           weights=weights[b:e], freqs=m.freqs, rates=rates, props=props, bl=bl, evec=m.evec, eval=m.eval, ivec=m.ivec)
+            want = O.evaluate(pb)
+            assert rel_err(sl, want["lnl"]) < RTOL and grad_err(sg, want["grad"]) < RTOL
+            assert np.max(np.abs(plk[b:e] - want["pattern_lnl"]) / np.abs(want["pattern_lnl"])) < RTOL
+        acc_l += sl
+        acc_g += sg
+        sub.close()
+    assert rel_err(acc_l, lnl) < 1e-12 and grad_err(acc_g, g) < 1e-11
+    # exact linearity in the weights (a factor 2 is exact in binary floating point)
+    tlk.set_pattern_weights(2.0 * weights)
+    assert tlk.calculate() == 2.0 * lnl and np.array_equal(tlk.gradient(), 2.0 * g)
+    tlk.set_pattern_weights(weights)
+    # central finite differences on three branches
+    _fd_check(tlk, bl, g, topo, rng)
+    tlk.close()
+    # a permutation of the patterns only reorders the sums
+    perm = rng.permutation(P)
+    shuf = _make(cfg, np.ascontiguousarray(patterns[:, perm]), weights[perm], inputs=inputs)
+    assert rel_err(shuf.calculate(), lnl) < 1e-12 and grad_err(shuf.gradient(), g) < 1e-11
+    shuf.close()
+    # the node-at-a-time kernels agree at full size (38 GB of partials)
+    gen = _make(cfg, patterns, weights, kernels=phb.KERNELS_GENERIC, inputs=inputs)
+    assert rel_err(gen.calculate(), lnl) < 1e-12 and grad_err(gen.gradient(), g) < RTOL
+    gen.close()
+
+
+@pytest.mark.parametrize("name", ["c4", "c5"])
+def test_tensor_core_full_size_properties(name):
+    """LG+G4 200 taxa x 200,000 patterns and GY94 100 taxa x 1,000,000 patterns (BASELINE configs 4 and 5) on one GPU"""
+    cfg = dict(bench.CONFIGS[name])
+    topo, bl, m, rates, props, patterns, weights = bench.make_inputs(cfg, 0)
+    inputs = (topo, bl, m, rates, props)
+    P, N, S = cfg["patterns"], 2 * cfg["taxa"] - 1, cfg["states"]
+    rng = np.random.default_rng(12)
+    weights = rng.integers(1, 4, P).astype(np.float64)
+    tlk = _make(cfg, patterns, weights, inputs=inputs)
+    lnl, g = tlk.calculate(), tlk.gradient().copy()
+    assert np.isfinite(lnl) and np.isfinite(g).all()
+    plk = tlk.pattern_log_likelihoods()
+    assert rel_err(float(np.dot(weights, plk)), lnl) < 1e-12
+    tlk.set_pattern_weights(2.0 * weights)
+    assert tlk.calculate() == 2.0 * lnl and np.array_equal(tlk.gradient(), 2.0 * g)
+    tlk.set_pattern_weights(weights)
+    _fd_check(tlk, bl, g, topo, rng, nbranches=2)
+    tlk.close()
+    # a 300-pattern shard against the oracle, and its share of the full evaluation
+    b, e = P // 2, P // 2 + 300
+    pb = O.Problem(left=topo.left, right=topo.right, parent=topo.parent, root=topo.root, nstate=S, tip_states=np.ascontiguousarray(patterns[:, b:e]),
+                   weights=weights[b:e], freqs=m.freqs, rates=rates, props=props, bl=bl, evec=m.evec, eval=m.eval, ivec=m.ivec)
+    want = O.evaluate(pb)
+    assert np.max(np.abs(plk[b:e] - want["pattern_lnl"]) / np.abs(want["pattern_lnl"])) < RTOL
+    sub = _make(cfg, np.ascontiguousarray(patterns[:, b:e]), weights[b:e], inputs=inputs)
+    assert rel_err(sub.calculate(), want["lnl"]) < RTOL and grad_err(sub.gradient(), want["grad"]) < RTOL
+    if S == 61:
+        # Codons two or three changes apart have transition probabilities ~ t^2, t^3 that come out of the eigen sum by cancellation:
+        # one ulp in an exponential moves them by 1e-9 relative.  The 1e-10 above holds because the exponentials come from the host's
+        # libm, the exp the reference (and the oracle) calls -- PHB_OPT_HOST_EXPONENTIALS, on by default for >= 60 states.  With the
+        # device's own (equally accurate) exp the same evaluation sits at the conditioning of the inputs, not at 1e-10:
+        sub.set_option(phb.treelikelihood.OPT_HOST_EXPONENTIALS, 0)
+        off = grad_err(sub.gradient(), want["grad"])
+        assert rel_err(sub.calculate(), want["lnl"]) < 1e-11 and off < 1e-6
+        print(f"codon gradient vs oracle with the device's exp: {off:.2e}")
+    sub.close()
