@@ -515,7 +515,7 @@ def main():
         tpeak, tsrc = dmma_peak()
         tf = flops / (kms * 1e-3) / 1e12 if kms > 0 else None
         roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": (tf / tpeak) if tf else None, "traffic": traffic,
-                "peak_source": tsrc, "kernel": "k_dmma_lower_msg + k_dmma_upper_msg (FP64 mma.sync m8n8k4, message form: 3 dense products per internal node), all levels of one evaluation",
+                "peak_source": tsrc, "kernel": "k_dmma_lower_msg + k_dmma_upper_msg (FP64 mma.sync m8n8k4, message form, branch gradients in adjoint form: 3 dense products per internal node), all levels of one evaluation",
                 "kernel_ms": kms, "algorithmic_flops_per_launch": flops, "hbm": hbm,
                 "note": "launch = the level-batched kernel sequence of one evaluation; S=20 sits at the FP64 ridge so the HBM view is given too"}
     else:
