@@ -70,7 +70,7 @@ __device__ __forceinline__ bool dm_state_tip(const Bufs &b, int idx) { return id
 // TMA bulk copy instead of an element-wise gather: zero padded [NP][LD] (B-fragment layout) for nodes whose lower partials are
 // an operand, or TRANSPOSED [S][NP] followed by the row sums [NP] for state tips, so that one tip state selects a contiguous
 // column of M (16-byte gathers) and an unknown state selects the row sums (treelikelihoodX.c:878-1001).
-// grid (N, C, 2: P | dP), images laid out [which][node][category][IMG]; one more image behind them: the rate matrix Q (k_dmma_pack_q).
+// grid (N, C, 2: P | dP), images laid out [which][node][category][IMG].
 // adjoint (message form): the dP image of an INTERNAL node is stored transposed and weighted, [j][i] = f_i dP[i][j], the B operand of
 // Z[j] = sum_i U[i] f_i dP[i][j] -- the node's own branch gradient is then sum_j L[j] Z[j] with the reference's dP entries themselves.
 template <class Sh>
@@ -108,15 +108,6 @@ __global__ void k_dmma_pack(int T, int N, int C, int root, int tip_states, const
 			const int i = e / Sh::LD, j = e - i * Sh::LD;
 			dst[e] = (e < Sh::MAT && i < Sh::S && j < Sh::S) ? src[i * Sh::S + j] : 0.0;
 		}
-	}
-}
-
-// Q in the B-fragment layout [NP][LD], zero padded: dP/dt L = Q (P L) for every node and category (message form)
-template <class Sh>
-__global__ void k_dmma_pack_q(const double *__restrict__ Q, double *__restrict__ dst) {
-	for (int e = threadIdx.x; e < Sh::IMG; e += blockDim.x) {
-		const int i = e / Sh::LD, j = e - i * Sh::LD;
-		dst[e] = (e < Sh::MAT && i < Sh::S && j < Sh::S) ? Q[i * Sh::S + j] : 0.0;
 	}
 }
 
@@ -620,10 +611,10 @@ dmma_mtiles<MT, NTW, Sh::KCH>(Da, ca, j, tt, bdA);
 
 // ---------------------------------------------------------------------------------------------
 // Message form (unscaled evaluations with state tips -- the fast path).  What a node hands to its parent is stored instead of its
-// lower partial: M_n = P_n L_n with L_n = M_a o M_b.  The product P_n L_n is needed three times -- by the parent's lower partial,
-// by the sibling's upper partial and by n's own branch gradient (dP_n L_n = Q M_n) -- and the node-at-a-time formulation above
-// computes it twice (lower pass and upper pass); here it is computed once, so an evaluation runs 3 instead of 4 dense products
-// per internal node, and the derivative matrices of internal nodes are never staged (one Q image serves every node and category).
+// lower partial: M_n = P_n L_n with L_n = M_a o M_b.  The product P_n L_n is needed by the parent's lower partial and by the sibling's
+// upper partial, and the node-at-a-time formulation above computes it twice (lower pass and upper pass); here it is computed once.
+// The branch gradient of n is reduced at n's OWN pre-order op from L_n = M_a o M_b and U_n (adjoint form, see k_dmma_upper_msg), so an
+// evaluation runs 3 dense products per internal node (P_n L_n, P_n U_n, U_n (f o dP_n)) instead of 4.
 // HBM traffic is unchanged: M_n takes the place of L_n in the lower buffers.
 //
 // k_dmma_lower_msg: A fragments are formed on the fly as products of the children's messages (staged rows for internal children,
@@ -1017,7 +1008,7 @@ template <int S>
 static int dmma_pack(phbc_ctx *ctx, bool adjoint = false, int include_root_freqs = 0) {
 	using Sh = DmmaShape<S>;
 	const int C = ctx->C, N = ctx->N;
-	const size_t img_bytes = ((size_t)2 * N * C + 1) * Sh::IMG * sizeof(double);
+	const size_t img_bytes = (size_t)2 * N * C * Sh::IMG * sizeof(double);
 	if (img_bytes > ctx->dmma_img_bytes) {
 		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 		if (ctx->d_dmma_img) cudaFree(ctx->d_dmma_img);
@@ -1029,10 +1020,6 @@ static int dmma_pack(phbc_ctx *ctx, bool adjoint = false, int include_root_freqs
 	k_dmma_pack<Sh><<<dim3(N, C, 2), 128, 0, ctx->stream>>>(ctx->T, N, C, ctx->root, ctx->tip_kind == PHBC_TIP_STATES, ctx->d_P, ctx->d_dP, ctx->d_dmma_img,
 	                                                         adjoint ? 1 : 0, ctx->d_freqs, include_root_freqs);
 	ctx->launches++;
-	if (ctx->have_eigen) {
-		k_dmma_pack_q<Sh><<<1, 128, 0, ctx->stream>>>(ctx->d_qmat, ctx->d_dmma_img + (size_t)2 * N * C * Sh::IMG);
-		ctx->launches++;
-	}
 	PHBC_CHECK(cudaGetLastError());
 	return 0;
 }
