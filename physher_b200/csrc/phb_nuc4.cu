@@ -128,7 +128,7 @@ __device__ __forceinline__ void row_store(unsigned char *cell, const double (&x)
 //             2*CHUNK * PB B of tip codes
 //   slots:    nslots * NUC4_SLOT_BYTES
 //   xch:      exchange area for cross-category sums (C * PB doubles; 4 * C * PB under rescaling) + invLw[PB] + sfslot[nslots][NT]
-// (C2's shape, Gamma-4 and 5 slots: 57,344 B.  Four CTAs per SM at a 128-register budget were measured SLOWER than three at 160:
+// (C2's shape, Gamma-4, 5 slots and chunks of 6 ops: 64,256 B.  Four CTAs per SM at a 128-register budget were measured SLOWER than three at 160:
 // 6.62 against 6.29 ms on the same box, round 1 h2.)
 struct Nuc4Stage {
 	uint32_t desc_off, mat_off, code_off, bytes;
