@@ -26,7 +26,6 @@ struct phb_group {
 	int unrooted, scale;
 	double lk;
 	double *gradient, *scratch; /* [N] each, owned */
-	int prepared;
 };
 
 int phb_internal_fail(int code, const char *msg); /* phb_treelikelihood.c: sets phb_last_error() */

@@ -1029,10 +1029,9 @@ static int upload_bl(phb_tlk *t) {
 static int evaluate_once(phb_tlk *t, int want_gradient, double *lnl, double *grad_out) {
 	int rc = check_ready(t);
 	if (rc) return rc;
-	if (t->bl_dirty || 1) {
-		if ((rc = upload_bl(t))) return dev_fail(rc);
-		t->bl_dirty = 0;
-	}
+	/* always: the upload is N doubles, and the batched entry points leave other samples' lengths in the device slots */
+	if ((rc = upload_bl(t))) return dev_fail(rc);
+	t->bl_dirty = 0;
 	phbc_eval_opts o;
 	for (int attempt = 0; attempt < 2; attempt++) {
 		fill_opts(t, &o, want_gradient, 0);
