@@ -194,6 +194,30 @@ void *phb_tlk_stream(phb_tlk *tlk);
 int phb_tlk_synchronize(phb_tlk *tlk);
 
 /*
+ * NCCL inside the C library ("one ncclAllReduce(sum, ncclDouble) over [lnL, grad] per evaluation, on the compute
+ * stream").  One process per GPU: rank 0 calls phb_comm_unique_id, the PHB_NCCL_ID_BYTES bytes travel to the other ranks by
+ * whatever the launcher offers (MPI_Bcast, a file, torch.distributed), every rank calls phb_comm_init_rank with its device.
+ * NCCL is bound at run time (libnccl.so.2); phb_nccl_version() returns 0 when it cannot be loaded.
+ *
+ * phb_tlk_gradient_allreduce_device: this rank's evaluation of ITS pattern shard followed by one in-place all-reduce of
+ * [lnL, grad[N], number of shards whose lnL is +-inf] (N + 2 doubles) on the tlk's stream; only enqueues.  *out_device (may be
+ * NULL) receives the tlk-owned device buffer holding the reduced raw sums once the stream reaches that point.
+ * phb_tlk_gradient_allreduce: the same, then the result on the host with the reference's conventions applied to the reduced
+ * values on every rank alike (rescaling switch treelikelihood.c:1496-1519, NaN fill :328-332, unrooted :3249-3255).
+ * comm == NULL or a communicator of size 1: no collective (single shard).
+ */
+#define PHB_NCCL_ID_BYTES 128
+typedef struct phb_comm phb_comm;
+int phb_nccl_version(void);
+int phb_comm_unique_id(void *id /* [PHB_NCCL_ID_BYTES] */);
+phb_comm *phb_comm_init_rank(int nranks, int rank, const void *id, int device);
+void phb_comm_free(phb_comm *comm);
+int phb_comm_size(const phb_comm *comm);
+int phb_comm_rank(const phb_comm *comm);
+int phb_tlk_gradient_allreduce_device(phb_tlk *tlk, phb_comm *comm, double **out_device /* [N + 2], tlk-owned */);
+int phb_tlk_gradient_allreduce(phb_tlk *tlk, phb_comm *comm, double *lnl, const double **grad);
+
+/*
  * The same for ONE host process driving several devices (physher itself is a single process): launch queues one evaluation of the
  * current inputs on the tlk's stream and returns, collect blocks on that stream and hands back the RAW sums of this object's
  * patterns (lnL and d lnL / d bl by node id; grad may be NULL) -- no inf / NaN / unrooted policy.
@@ -205,7 +229,11 @@ int phb_tlk_evaluate_collect(phb_tlk *tlk, double *lnl, double *grad /* [N] */);
  * phb_group: one tree likelihood sharded over several GPUs from one host thread.  Shard g owns the contiguous
  * pattern range [P g / G, P (g + 1) / G) on devices[g] (a device may appear more than once); pattern-indexed inputs are given
  * for the WHOLE alignment and sliced, model inputs are broadcast, an evaluation is launched on every shard before any result is
- * collected, and the G vectors [lnL, grad[N]] are summed on the host in shard order.  The reference's conventions are applied to
+ * collected.  Reduction: when the shards sit on DISTINCT devices and NCCL is loadable, the group owns one communicator per device
+ * (ncclCommInitAll) and every shard's [lnL, grad[N], inf flag] is all-reduced in place on the shard's own stream inside one NCCL
+ * group call -- no host sum; only shard 0's copy travels to the host.  Otherwise (a device listed twice, no NCCL, or
+ * PHB_GROUP_REDUCE_HOST requested: the cross-check of the tests) the G vectors are summed on the host in shard order.  The
+ * reference's conventions are applied to
  * the REDUCED values: +-inf lnL switches rescaling on on every shard and recomputes (treelikelihood.c:1496-1519), a NaN / inf lnL
  * NaN-fills the gradient (:328-332), PHB_OPT_UNROOTED zeroes the root's right child (:3249-3255).  *grad is owned by the group.
  */
@@ -226,6 +254,10 @@ int phb_group_set_branch_lengths(phb_group *g, const double *bl);
 int phb_group_set_option(phb_group *g, int option, int value);
 int phb_group_use_rescaling(phb_group *g, int use);
 int phb_group_rescaling(const phb_group *g);
+#define PHB_GROUP_REDUCE_HOST 0
+#define PHB_GROUP_REDUCE_NCCL 1
+int phb_group_set_reduction(phb_group *g, int how); /* PHB_ESTATE when NCCL cannot serve this device list */
+int phb_group_reduction(const phb_group *g);
 int phb_group_calculate(phb_group *g, double *lnl);
 int phb_group_gradient(phb_group *g, double *lnl, const double **grad);
 

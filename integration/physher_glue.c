@@ -174,6 +174,7 @@ static double finish(Backend *b, double lnl) {
 	SingleTreeLikelihood *tlk = b->tlk;
 	b->evaluations++;
 	tlk->lk = lnl;
+	if (phb_tlk_rescaling(b->h) && !tlk->scale) printf("_calculate: rescaling %f\n", -INFINITY); /* the reference's own message (:1497) */
 	tlk->scale = phb_tlk_rescaling(b->h) != 0; /* -inf => the device path switched rescaling on and recomputed (:1496-1519) */
 	const bool bad = isnan(lnl);
 	for (int i = 0; i < b->N; i++) tlk->update_nodes[i] = bad;

@@ -5,6 +5,7 @@ holds its sources (csrc/), the in-tree build and a ctypes mirror of the referenc
 the tests and the benchmark.  There is no CPU fallback: importing works anywhere, computing needs a GPU.
 """
 from .treelikelihood import (  # noqa: F401
+    Comm,
     FLAG_TREE_MODEL,
     KERNELS_AUTO,
     KERNELS_FUSED,
@@ -16,9 +17,10 @@ from .treelikelihood import (  # noqa: F401
     compress_patterns,
     device_count,
     load_library,
+    nccl_version,
 )
 
 __all__ = [
-    "SingleTreeLikelihood", "TreeLikelihoodGroup", "PhysherB200Error", "load_library", "device_count", "compress_patterns",
+    "SingleTreeLikelihood", "TreeLikelihoodGroup", "Comm", "nccl_version", "PhysherB200Error", "load_library", "device_count", "compress_patterns",
     "FLAG_TREE_MODEL", "KERNELS_AUTO", "KERNELS_GENERIC", "KERNELS_FUSED", "OPT_INCREMENTAL",
 ]

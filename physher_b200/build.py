@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libphysher_b200.so")
 
 CUDA_SOURCES = ["phb_cuda.cu", "phb_nuc4.cu", "phb_dmma.cu", "phb_timetree.cu", "phb_patterns.cu", "phb_branch.cu"]
-C_SOURCES = ["phb_treelikelihood.c", "phb_group.c"]
+C_SOURCES = ["phb_treelikelihood.c", "phb_group.c", "phb_nccl.c"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    link = [nvcc, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-o", LIB, *objs]
+    link = [nvcc, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-o", LIB, *objs, "-ldl"]
     subprocess.check_call(link)
     return LIB
 

@@ -73,6 +73,7 @@ struct phbc_ctx {
 	int result_cap;
 	double *d_cat_grad;      // [cat_grad_cap][N][C]
 	int cat_grad_cap;
+	double *d_reduce, *h_reduce;  // [N + 2] operand of a sharded evaluation's all-reduce: lnL, grad[N], inf flag (+ pinned host copy)
 	double *d_scratch;       // reduction scratch
 	size_t scratch_bytes;
 

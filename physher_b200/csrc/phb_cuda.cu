@@ -100,7 +100,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	                ctx->d_sf, ctx->d_lower_ops, ctx->d_upper_ops, ctx->d_parent_ops, ctx->d_post_ops, ctx->d_pre_ops, ctx->d_walk_mats,
 	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch,
 	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl, ctx->d_walk_gstat, ctx->d_nuc4_G, ctx->d_ex, ctx->d_post_tip_order, ctx->d_pre_tip_order, ctx->d_dmma_img, ctx->d_tt_lowers, ctx->d_tt_topo, ctx->d_tt_bad,
-	                ctx->d_tt_ratios, ctx->d_tt_rates, ctx->d_tt_heights, ctx->d_tt_adj, ctx->d_tt_out};
+	                ctx->d_tt_ratios, ctx->d_tt_rates, ctx->d_tt_heights, ctx->d_tt_adj, ctx->d_tt_out, ctx->d_reduce};
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		if (bufs[i]) cudaFree(bufs[i]);
 	if (ctx->ev_beg) {
@@ -114,6 +114,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	if (ctx->h_bl) cudaFreeHost(ctx->h_bl);
 	if (ctx->h_ex) cudaFreeHost(ctx->h_ex);
 	if (ctx->h_tt) cudaFreeHost(ctx->h_tt);
+	if (ctx->h_reduce) cudaFreeHost(ctx->h_reduce);
 	free(ctx->h_freqs);
 	free(ctx->h_qmat);
 	free(ctx->h_lower_level_off);
@@ -1078,6 +1079,38 @@ extern "C" int phbc_result_to_device(phbc_ctx *ctx, int batch_index, double *out
 	PHBC_CHECK(cudaSetDevice(ctx->device));
 	PHBC_CHECK(cudaMemcpyAsync(out_device, ctx->d_result + (size_t)batch_index * (1 + ctx->N), (1 + (size_t)ctx->N) * sizeof(double),
 	                           cudaMemcpyDeviceToDevice, ctx->stream));
+	return 0;
+}
+
+// [lnL, grad[N], 1 if this shard's lnL is +-inf] of result slot `batch_index` in a buffer of its own: the operand of the in-place
+// all-reduce of a pattern-sharded evaluation (the rescaling decision travels in the same collective as a flag slot)
+__global__ void k_pack_reduce(const double *__restrict__ result, int N, double *__restrict__ out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i <= N) out[i] = result[i];
+	else if (i == N + 1) out[i] = isinf(result[0]) ? 1.0 : 0.0;
+}
+
+extern "C" int phbc_pack_reduce(phbc_ctx *ctx, int batch_index, double **out_device) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	const int N = ctx->N;
+	if (!ctx->d_reduce) {
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_reduce, (size_t)(N + 2) * sizeof(double)));
+		PHBC_CHECK(cudaMallocHost((void **)&ctx->h_reduce, (size_t)(N + 2) * sizeof(double)));
+	}
+	k_pack_reduce<<<(N + 2 + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_result + (size_t)batch_index * (1 + N), N, ctx->d_reduce);
+	ctx->launches++;
+	PHBC_CHECK(cudaGetLastError());
+	*out_device = ctx->d_reduce;
+	return 0;
+}
+
+extern "C" int phbc_download_reduce(phbc_ctx *ctx, double *host) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	if (!ctx->d_reduce) return -4;
+	const size_t bytes = (size_t)(ctx->N + 2) * sizeof(double);
+	PHBC_CHECK(cudaMemcpyAsync(ctx->h_reduce, ctx->d_reduce, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+	memcpy(host, ctx->h_reduce, bytes);
 	return 0;
 }
 

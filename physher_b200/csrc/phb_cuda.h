@@ -135,6 +135,10 @@ typedef struct phbc_eval_opts {
 int phbc_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
 /* copy results of evaluation slot `batch_index` into out_device[0..N] on the stream (device to device) */
 int phbc_result_to_device(phbc_ctx *ctx, int batch_index, double *out_device);
+/* pattern-sharded evaluations: [lnL, grad[N], inf flag] of a result slot packed into the ctx's all-reduce operand (device pointer
+ * returned, ordered on the ctx stream), and its blocking download through pinned memory */
+int phbc_pack_reduce(phbc_ctx *ctx, int batch_index, double **out_device);
+int phbc_download_reduce(phbc_ctx *ctx, double *host /* [N + 2] */);
 /* blocking download of result slots [0, nbatch): lnl[b], grad[b][N] (either may be NULL) */
 int phbc_download_results(phbc_ctx *ctx, int nbatch, double *lnl, double *grad);
 int phbc_download_cat_grad(phbc_ctx *ctx, double *out);

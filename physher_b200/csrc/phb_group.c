@@ -4,15 +4,19 @@
  * physher is a single-process C program (SURVEY.md 8b threading, 8e); the pattern-sharded scheme of DESIGN.md 5 therefore also
  * exists below the torch.distributed layer, as plain C on top of the C ABI: shard g owns the contiguous pattern range
  * [P g / G, P (g + 1) / G) on its own device, every model input is broadcast to all shards, an evaluation is LAUNCHED on
- * every shard before any result is collected (the shards' streams run concurrently), and the G raw result vectors [lnL, grad[N]]
- * -- N + 1 doubles each -- are summed on the host in shard order (deterministic).  What needs the REDUCED lnL is applied after the
- * sum, exactly as in csrc/phb_treelikelihood.c for one device: +-inf switches rescaling on on every shard and recomputes
+ * every shard before any result is collected (the shards' streams run concurrently).  Reduction of the G raw result vectors:
+ *   NCCL (default when the shards sit on distinct devices): one communicator per device from ncclCommInitAll, every shard's
+ *        [lnL, grad[N], inf flag] all-reduced in place on the shard's OWN stream -- ordered behind its kernels by the stream, no host
+ *        wait, no host sum -- all G calls inside one ncclGroupStart / ncclGroupEnd; only shard 0's copy travels to the host;
+ *   host (a device listed twice, no NCCL, or PHB_GROUP_REDUCE_HOST: the tests' cross-check): N + 1 doubles per shard summed on the
+ *        host in shard order.
+ * What needs the REDUCED lnL is applied after the sum, exactly as in csrc/phb_treelikelihood.c for one device: +-inf switches rescaling on on every shard and recomputes
  * (treelikelihood.c:1496-1519), NaN / inf fills the gradient with NaN (:328-332), the unrooted convention zeroes the root's right
  * child (:3249-3255).
  *
  * Only public entry points of include/physher_b200.h are used here.
  */
-#include "physher_b200.h"
+#include "../../include/physher_b200.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -25,10 +29,19 @@ struct phb_group {
 	int *begin; /* [G + 1] pattern range edges */
 	int unrooted, scale;
 	double lk;
-	double *gradient, *scratch; /* [N] each, owned */
+	double *gradient, *scratch; /* [N] / [N + 2], owned */
+	int reduce;                 /* PHB_GROUP_REDUCE_* */
+	phb_comm **comms;           /* [G] when NCCL serves this device list */
+	int *devices;
+	double **bufs;              /* [G] scratch: per-shard device operands of one all-reduce */
+	void **streams;
 };
 
 int phb_internal_fail(int code, const char *msg); /* phb_treelikelihood.c: sets phb_last_error() */
+int phb_internal_launch_packed(phb_tlk *t, int want_gradient, double **dev_buf, void **stream);
+int phb_internal_collect_packed(phb_tlk *t, double *host);
+int phb_internal_comms_init_all(int n, const int *devices, phb_comm **comms); /* phb_nccl.c */
+int phb_internal_allreduce_all(int n, phb_comm **comms, double **bufs, size_t count, void **streams);
 
 static int group_fail(const char *what) { return phb_internal_fail(PHB_EINVAL, what); }
 
@@ -47,14 +60,18 @@ phb_group *phb_group_create(int nshards, const int *devices, int ntips, int nsta
 	g->shard = (phb_tlk **)calloc(nshards, sizeof(phb_tlk *));
 	g->begin = (int *)malloc(sizeof(int) * (nshards + 1));
 	g->gradient = (double *)calloc(g->N, sizeof(double));
-	g->scratch = (double *)calloc(g->N, sizeof(double));
-	if (!g->shard || !g->begin || !g->gradient || !g->scratch || root < 0 || root >= g->N) {
+	g->scratch = (double *)calloc((size_t)g->N + 2, sizeof(double));
+	g->devices = (int *)malloc(sizeof(int) * nshards);
+	g->bufs = (double **)calloc(nshards, sizeof(double *));
+	g->streams = (void **)calloc(nshards, sizeof(void *));
+	if (!g->shard || !g->begin || !g->gradient || !g->scratch || !g->devices || !g->bufs || !g->streams || root < 0 || root >= g->N) {
 		phb_group_free(g);
 		phb_internal_fail(root < 0 || root >= 2 * ntips - 1 ? PHB_EINVAL : PHB_ENOMEM, "phb_group_create: bad root or out of memory");
 		return NULL;
 	}
 	g->root_right = right[root];
 	for (int s = 0; s <= nshards; s++) g->begin[s] = (int)(((long long)npatterns * s) / nshards);
+	memcpy(g->devices, devices, sizeof(int) * nshards);
 	for (int s = 0; s < nshards; s++) {
 		g->shard[s] = phb_tlk_create(ntips, nstate, ncat, g->begin[s + 1] - g->begin[s], left, right, root, use_tip_states, devices[s]);
 		if (!g->shard[s]) { /* phb_last_error() holds the reason */
@@ -62,14 +79,44 @@ phb_group *phb_group_create(int nshards, const int *devices, int ntips, int nsta
 			return NULL;
 		}
 	}
+	if (nshards > 1 && phb_nccl_version() > 0) phb_group_set_reduction(g, PHB_GROUP_REDUCE_NCCL); /* stays on the host sum when NCCL cannot serve the list */
 	return g;
 }
+
+int phb_group_set_reduction(phb_group *g, int how) {
+	if (how == PHB_GROUP_REDUCE_HOST) {
+		g->reduce = PHB_GROUP_REDUCE_HOST;
+		return PHB_OK;
+	}
+	if (how != PHB_GROUP_REDUCE_NCCL) return group_fail("phb_group_set_reduction: unknown reduction");
+	if (!g->comms) {
+		for (int a = 0; a < g->G; a++)
+			for (int b = a + 1; b < g->G; b++)
+				if (g->devices[a] == g->devices[b]) return phb_internal_fail(PHB_ESTATE, "phb_group: NCCL needs one distinct device per shard");
+		phb_comm **comms = (phb_comm **)calloc(g->G, sizeof(phb_comm *));
+		if (!comms) return phb_internal_fail(PHB_ENOMEM, "out of memory");
+		const int rc = phb_internal_comms_init_all(g->G, g->devices, comms);
+		if (rc) {
+			for (int s = 0; s < g->G; s++) phb_comm_free(comms[s]);
+			free(comms);
+			return rc;
+		}
+		g->comms = comms;
+	}
+	g->reduce = PHB_GROUP_REDUCE_NCCL;
+	return PHB_OK;
+}
+
+int phb_group_reduction(const phb_group *g) { return g->reduce; }
 
 void phb_group_free(phb_group *g) {
 	if (!g) return;
 	if (g->shard)
 		for (int s = 0; s < g->G; s++)
 			if (g->shard[s]) phb_tlk_free(g->shard[s]);
+	if (g->comms)
+		for (int s = 0; s < g->G; s++) phb_comm_free(g->comms[s]);
+	free(g->comms), free(g->devices), free(g->bufs), free(g->streams);
 	free(g->shard), free(g->begin), free(g->gradient), free(g->scratch);
 	free(g);
 }

@@ -108,11 +108,16 @@ static int is_tip(const phb_tlk *t, int n) { return t->left[n] < 0; }
 /* level lists: lower level = 1 + max(children levels) (tips 0); upper level = depth below the root */
 static int build_level_schedules(phb_tlk *t) {
 	const int N = t->N, T = t->T;
+	int rc = PHB_OK;
 	int *level = (int *)calloc(N, sizeof(int));
 	int *depth = (int *)calloc(N, sizeof(int));
 	int *order = (int *)malloc(sizeof(int) * N); /* pre-order */
 	int *stack = (int *)malloc(sizeof(int) * (2 * (size_t)N + 2));
-	if (!level || !depth || !order || !stack) return PHB_ENOMEM;
+	int *fill = (int *)malloc(sizeof(int) * ((size_t)N + 2)); /* per-level fill counters (a level count never exceeds N) */
+	if (!level || !depth || !order || !stack || !fill) {
+		rc = fail(PHB_ENOMEM, "out of memory");
+		goto done;
+	}
 	int sp = 0, cnt = 0;
 	stack[sp++] = t->root;
 	while (sp) {
@@ -131,8 +136,8 @@ static int build_level_schedules(phb_tlk *t) {
 		}
 	}
 	if (cnt != N) {
-		free(level); free(depth); free(order); free(stack);
-		return fail(PHB_EINVAL, "topology is not a rooted binary tree over %d nodes (visited %d)", N, cnt);
+		rc = fail(PHB_EINVAL, "topology is not a rooted binary tree over %d nodes (visited %d)", N, cnt);
+		goto done;
 	}
 	memset(level, 0, sizeof(int) * N); /* drop the visited marks: tips are level 0 */
 	int maxlevel = 0, maxdepth = 0;
@@ -145,10 +150,19 @@ static int build_level_schedules(phb_tlk *t) {
 		if (level[n] > maxlevel) maxlevel = level[n];
 		if (depth[n] > maxdepth) maxdepth = depth[n];
 	}
-	/* lower ops: internal nodes grouped by level 1..maxlevel */
 	t->n_lower_levels = maxlevel;
+	t->n_upper_levels = maxdepth;
 	t->lower_level_off = (int *)calloc(maxlevel + 2, sizeof(int));
 	t->lower_ops = (phbc_op *)malloc(sizeof(phbc_op) * (N - T > 0 ? N - T : 1));
+	t->upper_level_off = (int *)calloc(maxdepth + 2, sizeof(int));
+	t->upper_ops = (phbc_op *)malloc(sizeof(phbc_op) * (N > 1 ? N - 1 : 1));
+	t->parent_level_off = (int *)calloc(maxdepth + 2, sizeof(int));
+	t->parent_ops = (phbc_parent_op *)malloc(sizeof(phbc_parent_op) * (N - T > 0 ? N - T : 1));
+	if (!t->lower_level_off || !t->lower_ops || !t->upper_level_off || !t->upper_ops || !t->parent_level_off || !t->parent_ops) {
+		rc = fail(PHB_ENOMEM, "out of memory"); /* whatever was allocated is released by free_schedules / phb_tlk_free */
+		goto done;
+	}
+	/* lower ops: internal nodes grouped by level 1..maxlevel */
 	for (int n = 0; n < N; n++)
 		if (!is_tip(t, n)) t->lower_level_off[level[n]]++; /* count at index level (1-based) */
 	{
@@ -160,7 +174,7 @@ static int build_level_schedules(phb_tlk *t) {
 		}
 		t->lower_level_off[maxlevel] = acc;
 	}
-	int *fill = (int *)calloc(maxlevel + 1, sizeof(int));
+	memset(fill, 0, sizeof(int) * ((size_t)N + 2));
 	for (int n = 0; n < N; n++) {
 		if (is_tip(t, n)) continue;
 		int l = level[n] - 1;
@@ -172,11 +186,7 @@ static int build_level_schedules(phb_tlk *t) {
 		op->b_mat = t->right[n];
 		op->flags = 0;
 	}
-	free(fill);
 	/* upper ops: every non-root node, grouped by depth 1..maxdepth (update_upper_partials, treelikelihood.c:2129-2161) */
-	t->n_upper_levels = maxdepth;
-	t->upper_level_off = (int *)calloc(maxdepth + 2, sizeof(int));
-	t->upper_ops = (phbc_op *)malloc(sizeof(phbc_op) * (N > 1 ? N - 1 : 1));
 	for (int n = 0; n < N; n++)
 		if (n != t->root) t->upper_level_off[depth[n]]++;
 	{
@@ -188,7 +198,7 @@ static int build_level_schedules(phb_tlk *t) {
 		}
 		t->upper_level_off[maxdepth] = acc;
 	}
-	fill = (int *)calloc(maxdepth + 1, sizeof(int));
+	memset(fill, 0, sizeof(int) * ((size_t)N + 2));
 	for (int n = 0; n < N; n++) {
 		if (n == t->root) continue;
 		int d = depth[n] - 1;
@@ -210,14 +220,11 @@ static int build_level_schedules(phb_tlk *t) {
 			op->flags = 1;
 		}
 	}
-	free(fill);
 	/* parent ops: internal nodes grouped by their own depth 0..maxdepth-1 (their children sit one level deeper) */
-	t->parent_level_off = (int *)calloc(maxdepth + 2, sizeof(int));
-	t->parent_ops = (phbc_parent_op *)malloc(sizeof(phbc_parent_op) * (N - T > 0 ? N - T : 1));
 	for (int n = 0; n < N; n++)
 		if (!is_tip(t, n)) t->parent_level_off[depth[n] + 1]++;
 	for (int d = 0; d < maxdepth; d++) t->parent_level_off[d + 1] += t->parent_level_off[d];
-	fill = (int *)calloc(maxdepth + 1, sizeof(int));
+	memset(fill, 0, sizeof(int) * ((size_t)N + 2));
 	for (int n = 0; n < N; n++) {
 		if (is_tip(t, n)) continue;
 		const int d = depth[n];
@@ -227,19 +234,18 @@ static int build_level_schedules(phb_tlk *t) {
 		op->b = t->right[n];
 		op->flags = n == t->root ? 1 : 0;
 	}
+done:
 	free(fill);
 	free(level);
 	free(depth);
 	free(order);
 	free(stack);
-	return PHB_OK;
+	return rc;
 }
 
 /* Strahler-style register need of the subtree below n (tips need none) */
-static void compute_need(const phb_tlk *t, int *need, int *size) {
+static void compute_need(const phb_tlk *t, int *need, int *size, int *stack /* [6N + 8] scratch of the caller */) {
 	/* node ids are not guaranteed to be a post-order: iterate with an explicit stack */
-	const int N = t->N;
-	int *stack = (int *)malloc(sizeof(int) * (6 * (size_t)N + 8));
 	int sp = 0;
 	stack[sp++] = t->root;
 	stack[sp++] = 0;
@@ -264,7 +270,6 @@ static void compute_need(const phb_tlk *t, int *need, int *size) {
 			size[n] = 1 + size[t->left[n]] + size[t->right[n]];
 		}
 	}
-	free(stack);
 }
 
 typedef struct SlotPool {
@@ -300,6 +305,7 @@ static int slot_alloc(SlotPool *p) {
 static int build_walk_schedules(phb_tlk *t) {
 	const int N = t->N, T = t->T;
 	const int nint = N - T;
+	int rc = PHB_OK;
 	int *need = (int *)malloc(sizeof(int) * N);
 	int *size = (int *)malloc(sizeof(int) * N);
 	int *slot_of = (int *)malloc(sizeof(int) * N);
@@ -313,8 +319,11 @@ static int build_walk_schedules(phb_tlk *t) {
 	pool.high = 0;
 	t->post_ops = (phbc_post_op *)malloc(sizeof(phbc_post_op) * (nint > 0 ? nint : 1));
 	t->pre_ops = (phbc_pre_op *)malloc(sizeof(phbc_pre_op) * (nint > 0 ? nint : 1));
-	if (!need || !size || !slot_of || !row_of || !parked || !pneed || !stack || !pool.used || !t->post_ops || !t->pre_ops) return PHB_ENOMEM;
-	compute_need(t, need, size);
+	if (!need || !size || !slot_of || !row_of || !parked || !pneed || !stack || !pool.used || !t->post_ops || !t->pre_ops) {
+		rc = fail(PHB_ENOMEM, "out of memory");
+		goto done;
+	}
+	compute_need(t, need, size, stack);
 
 	/* ---- post-order: emit ops (larger-need child first), then assign slots in program order ---- */
 	int sp = 0, nops = 0, prev = -1;
@@ -343,8 +352,8 @@ static int build_walk_schedules(phb_tlk *t) {
 				int tmp = a; a = b; b = tmp;
 			}
 			if (!is_tip(t, b) && b != prev) {
-				free(need); free(size); free(slot_of); free(row_of); free(parked); free(pneed); free(stack); free(pool.used);
-				return fail(PHB_EINVAL, "post-order walk: child %d of node %d was not computed by the preceding op", b, n);
+				rc = fail(PHB_EINVAL, "post-order walk: child %d of node %d was not computed by the preceding op", b, n);
+				goto done;
 			}
 			op->node = n;
 			op->a_node = a;
@@ -434,15 +443,10 @@ static int build_walk_schedules(phb_tlk *t) {
 		}
 	}
 	t->pre_slots = pool.high > 0 ? pool.high : 1;
-	free(pneed);
-	free(parked);
-	free(need);
-	free(size);
-	free(slot_of);
-	free(row_of);
-	free(stack);
-	free(pool.used);
-	if (nops != nint || npre != nint) return fail(PHB_EINVAL, "walk schedule covers %d/%d of %d internal nodes", nops, npre, nint);
+	if (nops != nint || npre != nint) {
+		rc = fail(PHB_EINVAL, "walk schedule covers %d/%d of %d internal nodes", nops, npre, nint);
+		goto done;
+	}
 
 	/* number the tip operands in walk order and make the descriptors' tip indices local to their chunk */
 	const int nch = (nint + PHBC_WALK_CHUNK - 1) / PHBC_WALK_CHUNK;
@@ -450,7 +454,10 @@ static int build_walk_schedules(phb_tlk *t) {
 	t->pre_tip_order = (int *)malloc(sizeof(int) * T);
 	t->post_chunk_tip0 = (int *)calloc(nch + 2, sizeof(int));
 	t->pre_chunk_tip0 = (int *)calloc(nch + 2, sizeof(int));
-	if (!t->post_tip_order || !t->pre_tip_order || !t->post_chunk_tip0 || !t->pre_chunk_tip0) return PHB_ENOMEM;
+	if (!t->post_tip_order || !t->pre_tip_order || !t->post_chunk_tip0 || !t->pre_chunk_tip0) {
+		rc = fail(PHB_ENOMEM, "out of memory");
+		goto done;
+	}
 	int k = 0, q = 0;
 	for (int i = 0; i < nint; i++) {
 		if (i % PHBC_WALK_CHUNK == 0) {
@@ -478,7 +485,10 @@ static int build_walk_schedules(phb_tlk *t) {
 	}
 	t->post_chunk_tip0[nch] = k;
 	t->pre_chunk_tip0[nch] = q;
-	if (k != T || q != T) return fail(PHB_EINVAL, "walk schedule consumes %d/%d of %d tips", k, q, T);
+	if (k != T || q != T) {
+		rc = fail(PHB_EINVAL, "walk schedule consumes %d/%d of %d tips", k, q, T);
+		goto done;
+	}
 	/* the first op of chunk ch announces the tip range of chunk ch + 1 (the kernel issues that load while it works on ch) */
 	for (int ch = 0; ch + 1 < nch; ch++) {
 		const int i = ch * PHBC_WALK_CHUNK;
@@ -493,7 +503,16 @@ static int build_walk_schedules(phb_tlk *t) {
 	}
 	t->post_first_tips = nch > 0 ? t->post_chunk_tip0[1] : 0;
 	t->pre_first_tips = nch > 0 ? t->pre_chunk_tip0[1] : 0;
-	return PHB_OK;
+done:
+	free(pneed);
+	free(parked);
+	free(need);
+	free(size);
+	free(slot_of);
+	free(row_of);
+	free(stack);
+	free(pool.used);
+	return rc;
 }
 
 /* ------------------------------------------------------------------------------------------- */
@@ -1032,13 +1051,13 @@ static int evaluate_once(phb_tlk *t, int want_gradient, double *lnl, double *gra
 	/* always: the upload is N doubles, and the batched entry points leave other samples' lengths in the device slots */
 	if ((rc = upload_bl(t))) return dev_fail(rc);
 	t->bl_dirty = 0;
+	t->sweep_valid = 0; /* whatever phb_tlk_matrix_gradient left on the device is overwritten or outdated from here on */
 	phbc_eval_opts o;
 	for (int attempt = 0; attempt < 2; attempt++) {
 		fill_opts(t, &o, want_gradient, 0);
 		if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
 		if ((rc = phbc_download_results(t->ctx, 1, lnl, want_gradient ? grad_out : NULL))) return dev_fail(rc);
 		if (isinf(*lnl) && !t->scale) {
-			fprintf(stdout, "_calculate: rescaling %f\n", *lnl); /* same message as treelikelihood.c:1497 */
 			t->scale = 1;
 			t->all_dirty = 1; /* resident unscaled partials are of no use any more */
 			continue;
@@ -1083,13 +1102,13 @@ static int resident_full(phb_tlk *t, int want_gradient, double *lnl, double *gra
 	if ((rc = upload_bl(t))) return dev_fail(rc);
 	t->bl_dirty = 0;
 	t->resident = 0;
+	t->sweep_valid = 0;
 	for (int attempt = 0; attempt < 2; attempt++) {
 		phbc_eval_opts o;
 		fill_opts_resident(t, &o, want_gradient);
 		if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
 		if ((rc = phbc_download_results(t->ctx, 1, lnl, want_gradient ? grad_out : NULL))) return dev_fail(rc);
 		if (isinf(*lnl) && !t->scale) {
-			fprintf(stdout, "_calculate: rescaling %f\n", *lnl); /* treelikelihood.c:1497 */
 			t->scale = 1;
 			continue;
 		}
@@ -1143,6 +1162,7 @@ static int resident_calculate(phb_tlk *t, double *lnl) {
 	} else {
 		if ((rc = check_ready(t))) return rc;
 		const int N = t->N;
+		t->sweep_valid = 0;
 		resident_invalidate(t);
 		int nops = 0;
 		for (int l = 0; l < t->n_lower_levels; l++) {
@@ -1157,7 +1177,6 @@ static int resident_calculate(phb_tlk *t, double *lnl) {
 		fill_opts_resident(t, &o, 0);
 		if ((rc = phbc_run_ops(t->ctx, &o, nops, t->sub_ops, t->n_lower_levels, t->sub_level_off, 1, 1, &t->lk))) return dev_fail(rc);
 		if (isinf(t->lk) && !t->scale) { /* treelikelihood.c:1496-1519: switch rescaling on and recompute everything */
-			fprintf(stdout, "_calculate: rescaling %f\n", t->lk);
 			t->scale = 1;
 			if ((rc = resident_full(t, 0, &t->lk, NULL))) return rc;
 		} else if (!isnan(t->lk) && !isinf(t->lk)) {
@@ -1367,7 +1386,12 @@ int phb_tlk_cat_branch_gradient(phb_tlk *t, double *out) {
 
 int phb_tlk_get_partials(phb_tlk *t, int index, double *out) {
 	int rc;
-	if (index >= t->T && !(t->incremental && t->resident && !t->all_dirty && !t->update)) {
+	if (index >= t->T && t->incremental && t->resident && !t->all_dirty && (t->update || t->lower_stale)) {
+		/* pending set_branch_length changes, or dirty flags a fused gradient call folded into the validity maps: recompute what they reach */
+		double cur;
+		if ((rc = resident_calculate(t, &cur))) return rc;
+	}
+	if (index >= t->T && !(t->incremental && t->resident && !t->all_dirty && !t->update && !t->lower_stale)) {
 		/* tlk->partials as the reference holds them: a node-at-a-time evaluation with every upper partial materialised (the fused paths
 		 * keep no partials, or keep messages P L in their place) */
 		if ((rc = check_ready(t))) return rc;
@@ -1398,6 +1422,7 @@ int phb_tlk_gradient_device(phb_tlk *t, double *out_device) {
 	phbc_eval_opts o;
 	fill_opts(t, &o, 1, 0);
 	t->resident = 0;
+	t->sweep_valid = 0;
 	if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
 	if ((rc = phbc_result_to_device(t->ctx, 0, out_device))) return dev_fail(rc);
 	/* the device copy holds raw per-shard sums; the caller applies the unrooted convention after the reduction */
@@ -1434,6 +1459,88 @@ int phb_tlk_evaluate_collect(phb_tlk *t, double *lnl, double *grad) {
 	return PHB_OK;
 }
 
+/*
+ * One process per GPU, patterns sharded across the ranks of `comm`: this rank's evaluation, then ONE in-place
+ * ncclAllReduce(sum) of [lnL, grad[N], inf flag] on the tlk's own stream -- kernels and collective are ordered by the stream, the host
+ * does not wait in between.  The _device form only enqueues and hands back the device buffer (raw reduced sums, no policy).
+ */
+int phb_internal_allreduce(phb_comm *c, double *buf, size_t count, void *stream); /* phb_nccl.c */
+
+int phb_tlk_gradient_allreduce_device(phb_tlk *t, phb_comm *comm, double **out_device) {
+	int rc = check_ready(t);
+	if (rc) return rc;
+	if ((rc = upload_bl(t))) return dev_fail(rc);
+	t->bl_dirty = 0;
+	phbc_eval_opts o;
+	fill_opts(t, &o, 1, 0);
+	t->resident = 0;
+	t->sweep_valid = 0;
+	if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
+	double *buf = NULL;
+	if ((rc = phbc_pack_reduce(t->ctx, 0, &buf))) return dev_fail(rc);
+	if (comm && phb_comm_size(comm) > 1 && (rc = phb_internal_allreduce(comm, buf, (size_t)t->N + 2, phbc_stream(t->ctx)))) return rc;
+	if (out_device) *out_device = buf;
+	memset(t->update_nodes, 0, t->N);
+	t->update = 1; /* lk is not known on the host: keep the object dirty */
+	t->update_upper = 1;
+	return PHB_OK;
+}
+
+/* the same with host results and the reference's conventions applied to the REDUCED values on every rank alike: +-inf lnL (or an
+ * inf shard) switches rescaling on and recomputes (treelikelihood.c:1496-1519), NaN / inf NaN-fills the gradient (:328-332), the
+ * unrooted convention zeroes the root's right child (:3249-3255).  *grad is owned by the tlk. */
+int phb_tlk_gradient_allreduce(phb_tlk *t, phb_comm *comm, double *lnl, const double **grad) {
+	if (!grad) return fail(PHB_EINVAL, "grad is required");
+	if (t->gradient == NULL || !(t->prepared_gradient & PHB_FLAG_TREE_MODEL)) {
+		if (phb_tlk_initialize_gradient(t, PHB_FLAG_TREE_MODEL) == 0) return PHB_ENOMEM;
+	}
+	const int N = t->N;
+	double *h = (double *)malloc(sizeof(double) * ((size_t)N + 2));
+	if (!h) return fail(PHB_ENOMEM, "out of memory");
+	int rc = PHB_OK;
+	for (int attempt = 0; attempt < 2; attempt++) {
+		if ((rc = phb_tlk_gradient_allreduce_device(t, comm, NULL))) break;
+		if ((rc = phbc_download_reduce(t->ctx, h))) {
+			rc = dev_fail(rc);
+			break;
+		}
+		if ((isinf(h[0]) || h[N + 1] > 0.0) && !t->scale) { /* every rank reads the same reduced values and takes the same branch */
+			t->scale = 1;
+			t->all_dirty = 1;
+			continue;
+		}
+		break;
+	}
+	if (rc == PHB_OK) {
+		t->lk = h[0];
+		if (isnan(t->lk) || isinf(t->lk)) {
+			for (int n = 0; n < N; n++) t->gradient[n] = NAN;
+		} else {
+			memcpy(t->gradient, h + 1, sizeof(double) * N);
+			apply_unrooted(t, t->gradient);
+		}
+		if (lnl) *lnl = t->lk;
+		*grad = t->gradient;
+	}
+	free(h);
+	return rc;
+}
+
+/* for phb_group.c (one host thread, several devices): an evaluation queued with its result packed for the group's all-reduce */
+int phb_internal_launch_packed(phb_tlk *t, int want_gradient, double **dev_buf, void **stream) {
+	int rc = phb_tlk_evaluate_launch(t, want_gradient);
+	if (rc) return rc;
+	if ((rc = phbc_pack_reduce(t->ctx, 0, dev_buf))) return dev_fail(rc);
+	*stream = phbc_stream(t->ctx);
+	return PHB_OK;
+}
+
+int phb_internal_collect_packed(phb_tlk *t, double *host /* [N + 2] */) {
+	int rc = phbc_download_reduce(t->ctx, host);
+	if (rc) return dev_fail(rc);
+	return PHB_OK;
+}
+
 void *phb_tlk_stream(phb_tlk *t) { return phbc_stream(t->ctx); }
 
 int phb_tlk_synchronize(phb_tlk *t) {
@@ -1464,7 +1571,6 @@ int phb_tlk_gradient_batch(phb_tlk *t, int nbatch, const double *bl, double *lnl
 		int any_inf = 0;
 		for (int b = 0; b < nbatch; b++) any_inf |= isinf(lnl[b]);
 		if (any_inf && !t->scale) {
-			fprintf(stdout, "_calculate: rescaling (batch)\n");
 			t->scale = 1;
 			continue;
 		}
@@ -1499,7 +1605,6 @@ int phb_tlk_matrix_gradient(phb_tlk *t, int nsets, const double *M, double *out)
 		if ((rc = phbc_matrix_gradient(t->ctx, &o, nsets, M, t->unrooted ? t->right[t->root] : -1, &lnl, out))) return dev_fail(rc);
 		t->lk = lnl;
 		if (isinf(lnl) && !t->scale) { /* treelikelihood.c:1496-1519 */
-			fprintf(stdout, "_calculate: rescaling %f\n", lnl);
 			t->scale = 1;
 			continue;
 		}
@@ -1518,7 +1623,11 @@ int phb_tlk_root_frequency_gradient(phb_tlk *t, double *out) {
 	if (!out) return fail(PHB_EINVAL, "out is required");
 	int rc = check_ready(t);
 	if (rc) return rc;
-	const int resident_ok = t->incremental && t->resident && !t->all_dirty && !t->update;
+	if (t->incremental && t->resident && !t->all_dirty && (t->update || t->lower_stale)) {
+		double cur;
+		if ((rc = resident_calculate(t, &cur))) return rc;
+	}
+	const int resident_ok = t->incremental && t->resident && !t->all_dirty && !t->update && !t->lower_stale;
 	if (!resident_ok && (t->update || !t->sweep_valid)) { /* a node-at-a-time evaluation leaves the root partial on the device */
 		if ((rc = upload_bl(t))) return dev_fail(rc);
 		t->bl_dirty = 0;
@@ -1529,7 +1638,6 @@ int phb_tlk_root_frequency_gradient(phb_tlk *t, double *out) {
 			if ((rc = phbc_evaluate(t->ctx, &o))) return dev_fail(rc);
 			if ((rc = phbc_download_results(t->ctx, 1, &t->lk, NULL))) return dev_fail(rc);
 			if (isinf(t->lk) && !t->scale) {
-				fprintf(stdout, "_calculate: rescaling %f\n", t->lk);
 				t->scale = 1;
 				continue;
 			}
@@ -1675,7 +1783,6 @@ int phb_tlk_gradient_batch_time(phb_tlk *t, int nbatch, const double *ratios, co
 		int any_inf = 0;
 		for (int b = 0; b < nbatch; b++) any_inf |= isinf(lnl[b]);
 		if (any_inf && !t->scale) { /* treelikelihood.c:1496-1519 */
-			fprintf(stdout, "_calculate: rescaling (batch)\n");
 			t->scale = 1;
 			continue;
 		}

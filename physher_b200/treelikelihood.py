@@ -87,6 +87,16 @@ SYMBOLS = [
     ("phb_group_set_option", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("phb_group_use_rescaling", C.c_int, [C.c_void_p, C.c_int]),
     ("phb_group_rescaling", C.c_int, [C.c_void_p]),
+    ("phb_group_set_reduction", C.c_int, [C.c_void_p, C.c_int]),
+    ("phb_group_reduction", C.c_int, [C.c_void_p]),
+    ("phb_nccl_version", C.c_int, []),
+    ("phb_comm_unique_id", C.c_int, [C.c_void_p]),
+    ("phb_comm_init_rank", C.c_void_p, [C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    ("phb_comm_free", None, [C.c_void_p]),
+    ("phb_comm_size", C.c_int, [C.c_void_p]),
+    ("phb_comm_rank", C.c_int, [C.c_void_p]),
+    ("phb_tlk_gradient_allreduce_device", C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("phb_tlk_gradient_allreduce", C.c_int, [C.c_void_p, C.c_void_p, _dp, C.POINTER(_dp)]),
     ("phb_group_calculate", C.c_int, [C.c_void_p, _dp]),
     ("phb_group_gradient", C.c_int, [C.c_void_p, _dp, C.POINTER(_dp)]),
     ("phb_tlk_stream", C.c_void_p, [C.c_void_p]),
@@ -160,6 +170,48 @@ def compress_patterns(alignment, device=0, hashtable_size=100, want_site_map=Tru
         if want_site_map:
             lib.phb_free(smap)
     return patterns, weights, site_map
+
+
+NCCL_ID_BYTES = 128
+GROUP_REDUCE_HOST, GROUP_REDUCE_NCCL = 0, 1
+
+
+def nccl_version() -> int:
+    """NCCL_VERSION_CODE of the library the C layer bound at run time (0: not loadable)."""
+    return int(load_library().phb_nccl_version())
+
+
+class Comm:
+    """NCCL communicator owned by the C library (csrc/phb_nccl.c): one rank per process, one GPU per rank.  Rank 0 makes the unique
+    id (`Comm.unique_id()`), the launcher carries its 128 bytes to the other ranks, every rank builds `Comm(nranks, rank, id, device)`."""
+
+    @staticmethod
+    def unique_id() -> bytes:
+        lib = load_library()
+        buf = C.create_string_buffer(NCCL_ID_BYTES)
+        rc = lib.phb_comm_unique_id(buf)
+        if rc != 0:
+            raise PhysherB200Error(f"[{rc}] {(lib.phb_last_error() or b'').decode()}")
+        return buf.raw
+
+    def __init__(self, nranks: int, rank: int, unique_id: bytes, device: int):
+        self.lib = load_library()
+        assert len(unique_id) == NCCL_ID_BYTES
+        self._id = C.create_string_buffer(unique_id, NCCL_ID_BYTES)
+        self.h = self.lib.phb_comm_init_rank(int(nranks), int(rank), self._id, int(device))
+        if not self.h:
+            raise PhysherB200Error((self.lib.phb_last_error() or b"").decode() or "phb_comm_init_rank failed")
+
+    def size(self) -> int:
+        return int(self.lib.phb_comm_size(self.h))
+
+    def rank(self) -> int:
+        return int(self.lib.phb_comm_rank(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.phb_comm_free(self.h)
+            self.h = None
 
 
 class SingleTreeLikelihood:
@@ -378,6 +430,20 @@ class SingleTreeLikelihood:
         """[lnL, grad[0..N)] of this shard into device memory at `out_ptr`, ordered on the tlk stream."""
         self._check(self.lib.phb_tlk_gradient_device(self.h, C.c_void_p(out_ptr)))
 
+    def gradient_allreduce_device(self, comm) -> int:
+        """This rank's shard evaluated and [lnL, grad[N], inf flag] all-reduced in place over `comm` (NCCL, on the tlk's stream);
+        only enqueues.  Returns the device address of the tlk-owned [N + 2] buffer."""
+        out = C.c_void_p(0)
+        self._check(self.lib.phb_tlk_gradient_allreduce_device(self.h, comm.h if comm is not None else None, C.byref(out)))
+        return int(out.value or 0)
+
+    def gradient_allreduce(self, comm):
+        """(lnL, gradient) of the WHOLE alignment on every rank, the reference's inf / NaN / unrooted conventions applied to the
+        reduced values."""
+        lnl, ptr = C.c_double(0.0), _dp()
+        self._check(self.lib.phb_tlk_gradient_allreduce(self.h, comm.h if comm is not None else None, C.byref(lnl), C.byref(ptr)))
+        return lnl.value, np.ctypeslib.as_array(ptr, shape=(self.N,)).copy()
+
     def stream(self) -> int:
         return int(self.lib.phb_tlk_stream(self.h) or 0)
 
@@ -483,6 +549,12 @@ class TreeLikelihoodGroup:
 
     def rescaling(self):
         return bool(self.lib.phb_group_rescaling(self.h))
+
+    def set_reduction(self, how):
+        self._check(self.lib.phb_group_set_reduction(self.h, int(how)))
+
+    def reduction(self) -> int:
+        return int(self.lib.phb_group_reduction(self.h))
 
     def calculate(self):
         v = C.c_double(0.0)
