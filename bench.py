@@ -5,9 +5,14 @@ One "step" = one full lnL + branch-gradient evaluation (protocol of the referenc
 examples/benchmarking.c:498-503: every node dirty, new branch lengths in, transition matrices
 rebuilt, post-order + pre-order passes, lnL and grad[N] back on the host).
 
-Workload at N=1: BASELINE.json configs[1] -- GTR+Γ4 nucleotide, synthetic 1000 taxa × 100k site
-patterns.  Multi-GPU: patterns sharded across ranks (one process per GPU), one NCCL all-reduce of
-[lnL, grad[N]] per step; weak scaling (100k patterns per GPU).
+Headline workload: BASELINE.json configs[1] -- GTR+Γ4 nucleotide, synthetic 1000 taxa × 100k site
+patterns per GPU (weak scaling over ranks: one process per GPU, patterns sharded, ONE ncclAllReduce of
+[lnL, grad[N], inf flag] per step issued by the C library on the evaluation's stream).
+The same JSON line carries a `configs` object with one sub-record per remaining BASELINE config
+(c1 fluA JC69 time tree, c2_1m = the north-star 1000 × 1M, c3 HKY+Γ4 × 128 samples, c4 LG+Γ4 200 × 200k,
+c5 GY94 100 × 1M); at N > 1 those are STRONG splits of the named sizes (1M / N, 200k / N, 1M / N
+patterns per GPU; c3 splits its samples).  Every record is gated on parity with the unmodified
+reference (oracle/_ref) evaluated on a bounded sample of the same workload.
 
     python bench.py --gpus 1 --steps 20 --warmup 3
     torchrun --nproc-per-node N bench.py --gpus N ...
@@ -202,14 +207,16 @@ class ClockSampler:
                 "source": "nvml" if self.samples else "nvidia-smi"}
 
 
-def measured_traffic(config_name, kernels):
+def measured_traffic(config_name, kernels, patterns, lib_version):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel from the committed ncu --set full
-    capture of this workload (profiles/traffic.json, written by tools/ncu_summary.py); None when there is no capture."""
-    if config_name is None:
-        return None
+    capture of this workload (profiles/traffic.json, written by tools/ncu_traffic.py).  A capture only counts for the kernel
+    revision and pattern count it was taken on: None when the library reports another revision (phb_version()) or the launch
+    covers another number of patterns -- a stale constant is worse than no number."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return float(d[f"{config_name}:{kernels}"]["dram_bytes_per_launch"])
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[f"{config_name}:{kernels}"]
+        if int(d.get("patterns", -1)) != int(patterns) or d.get("kernel_rev") not in lib_version:
+            return None
+        return float(d["dram_bytes_per_launch"])
     except Exception:
         return None
 
@@ -230,7 +237,8 @@ def measured_peak_gbs():
 
 def _reference_worker(args):
     """One process = one single-threaded reference tree likelihood on a pattern shard."""
-    cfg, shard_patterns, shard_index, iters, warm = args
+    cfg, shard_patterns, shard_index, iters, warm = args[:5]
+    want_values = len(args) > 5 and args[5]
     devnull = os.open(os.devnull, os.O_WRONLY)
     saved = os.dup(1)
     os.dup2(devnull, 1)  # the reference prints alignment statistics to stdout
@@ -266,26 +274,31 @@ def _reference_worker(args):
         sec = ref.time_gradient(iters, O.FLAG_TREE_MODEL, 0)
         npat = ref.P
         nodes = ref.N
+        values = None
+        if want_values:  # the parity gate of our arm: lnL and branch gradients of this shard from the reference itself
+            values = (ref.logP(), ref.gradient(O.FLAG_TREE_MODEL, 0)[:nodes].copy(), bool(ref.rescaling()))
     finally:
         os.dup2(saved, 1)
         os.close(devnull)
-    return sec, npat, nodes
+    return sec, npat, nodes, values
 
 
-def run_reference(cfg: dict, cores: int, sample_patterns: int, iters: int, warm: int = 1):
+def run_reference(cfg: dict, cores: int, sample_patterns: int, iters: int, warm: int = 1, want_values: bool = False):
     """Throughput of the reference's SSE path: `cores` independent single-threaded processes (the path has no
     intra-likelihood threading) on disjoint pattern shards of a bounded sample."""
     import multiprocessing as mp
+    from concurrent.futures import ProcessPoolExecutor
 
     per = max(64, sample_patterns // cores)
-    ctx = mp.get_context("spawn")
     t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        res = pool.map(_reference_worker, [(cfg, per, i, iters, warm) for i in range(cores)])
+    # an executor, not mp.Pool: a worker the reference takes down (it exits or crashes on what it dislikes) raises here instead of hanging
+    with ProcessPoolExecutor(cores, mp_context=mp.get_context("spawn")) as pool:
+        res = list(pool.map(_reference_worker, [(cfg, per, i, iters, warm, want_values and i == 0) for i in range(cores)]))
     wall = time.perf_counter() - t0
     # aggregate: every process evaluates its shard at its own rate
-    pn_per_s = sum(npat * nodes / sec for sec, npat, nodes in res)
-    return dict(value=pn_per_s, sec_per_eval=[r[0] for r in res], patterns=[r[1] for r in res], nodes=res[0][2], wall=wall, per=per)
+    pn_per_s = sum(npat * nodes / sec for sec, npat, nodes, _ in res)
+    return dict(value=pn_per_s, sec_per_eval=[r[0] for r in res], patterns=[r[1] for r in res], nodes=res[0][2], wall=wall, per=per,
+                values=res[0][3])
 
 
 def reference_main(args, cfg):
@@ -337,168 +350,127 @@ def workload_name(cfg):
 # our arm
 # -------------------------------------------------------------------------------------------------
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
-    ap.add_argument("--patterns", type=int, default=0, help="override patterns per GPU")
-    ap.add_argument("--kernels", default="auto", choices=["auto", "generic", "fused"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    args = ap.parse_args()
-    cfg = dict(CONFIGS[args.config])
-    if args.patterns:
-        cfg["patterns"] = args.patterns
-    if args.impl == "reference":
-        return reference_main(args, cfg)
+SUB_CONFIGS = ["c1", "c2_1m", "c3", "c4", "c5"]  # every other BASELINE config, as sub-records of the one JSON line
+PARITY_PATTERNS = {4: 256, 20: 128, 61: 64}      # sample the reference evaluates for a sub-record's parity gate (one process)
+PARITY_RTOL = 1e-10                              # north_star: lnL and every branch gradient within 1e-10 relative
 
-    import torch
-    import torch.distributed as dist
 
-    import physher_b200 as phb
-    from physher_b200.treelikelihood import OPT_KERNELS, OPT_TIMING
+class Run:
+    """What every config of one bench invocation shares: ranks, the torch plumbing, the library and its NCCL communicator."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the tree-likelihood path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    W, K = max(args.warmup, 3), args.steps
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    topo, bl, m, rates, props, patterns, weights = make_inputs(cfg, rank)
-    sha = inputs_sha256(topo, bl, m, rates, props, patterns, weights) if rank == 0 else None
-    T, P, S, C = cfg["taxa"], cfg["patterns"], cfg["states"], cfg["cats"]
-    N = 2 * T - 1
-    tlk = phb.SingleTreeLikelihood(topo.left, topo.right, topo.root, S, C, P, use_tip_states=True, device=local_rank)
+        import physher_b200 as phb
+
+        self.torch, self.dist, self.phb = torch, dist, phb
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the tree-likelihood path has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.comm = None
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            # the collective of the hot path belongs to the C library (csrc/phb_nccl.c): torch.distributed only carries the
+            # 128-byte NCCL id to the other ranks and the max-over-ranks of the timings after the timed regions
+            box = [phb.Comm.unique_id() if self.rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            self.comm = phb.Comm(self.world, self.rank, box[0], self.local_rank)
+
+    def reduce(self, values, op="max"):
+        if self.world == 1:
+            return [float(v) for v in values]
+        t = self.torch.tensor(list(values), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX if op == "max" else self.dist.ReduceOp.SUM)
+        return [float(v) for v in t.cpu()]
+
+    def sync(self, tlk=None):
+        if tlk is not None:
+            tlk.synchronize()
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
+
+    def close(self):
+        if self.comm is not None:
+            self.comm.close()
+        if self.world > 1:
+            self.dist.destroy_process_group()
+
+
+def grad_err(g, ref):
+    scale = np.maximum(np.abs(ref), np.abs(ref).max() * 1e-6)  # BASELINE.md 4.5
+    return float(np.max(np.abs(g - ref) / np.where(scale == 0, 1.0, scale)))
+
+
+def build_tlk(run, cfg, topo, m, rates, props, patterns, weights, kernels="auto"):
+    phb = run.phb
+    from physher_b200.treelikelihood import OPT_KERNELS
+
+    tlk = phb.SingleTreeLikelihood(topo.left, topo.right, topo.root, cfg["states"], cfg["cats"], patterns.shape[1], use_tip_states=True,
+                                   device=run.local_rank)
     tlk.set_tip_states(patterns)
     tlk.set_pattern_weights(weights)
     tlk.set_eigen(m.evec, m.eval, m.ivec)
     tlk.set_frequencies(m.freqs)
     tlk.set_site_model(rates, props)
-    tlk.set_option(OPT_KERNELS, {"auto": phb.KERNELS_AUTO, "generic": phb.KERNELS_GENERIC, "fused": phb.KERNELS_FUSED}[args.kernels])
+    tlk.set_option(OPT_KERNELS, {"auto": phb.KERNELS_AUTO, "generic": phb.KERNELS_GENERIC, "fused": phb.KERNELS_FUSED}[kernels])
     tlk.initialize_gradient(phb.FLAG_TREE_MODEL)
-    ext = torch.cuda.ExternalStream(tlk.stream(), device=torch.device("cuda", local_rank))
-    out_dev = torch.zeros(1 + N, dtype=torch.float64, device="cuda")
-    rng = np.random.default_rng(7)
+    return tlk
 
-    def new_bl():
-        # every step sees new branch lengths (host buffer), like an optimiser / VI iteration would produce
-        b = bl * rng.uniform(0.98, 1.02, size=bl.shape)
-        b[topo.root] = 0.0
-        b[topo.right[topo.root]] = 0.0
-        return b
 
-    B = int(cfg.get("batch", 1))
+def parity_gate(run, cfg, kernels, cores, sample_patterns, iters):
+    """cpu_baseline leg + parity gate (rank 0): the unmodified reference (oracle/_ref) evaluates a bounded sample of this workload on
+    the host cores -- timed, and its lnL / branch gradients of the first shard are the answers the device path must reproduce on
+    the same patterns before any of its timings is reported."""
+    from oracle import oracle as O
 
-    def step_batch():
-        """BASELINE config 3: B branch-length samples (base x LogNormal(0, 0.1)) per step through phb_tlk_gradient_batch --
-        host buffers in ([B][N] doubles) and out (lnl[B], grad[B][N]); one fused launch for the whole batch."""
-        bls = bl[None, :] * rng.lognormal(0.0, 0.1, size=(B, N))
-        bls[:, topo.root] = 0.0
-        bls[:, topo.right[topo.root]] = 0.0
-        lnls, grads = tlk.gradient_batch(bls)
-        if world > 1:
-            t = torch.from_numpy(np.concatenate([lnls[:, None], grads], axis=1)).cuda()
-            dist.all_reduce(t)
-            h = t.cpu().numpy()
-            lnls, grads = h[:, 0], h[:, 1:]
-        return float(lnls[-1]), grads[-1]
-
-    def step_e2e():
-        """Public API, host in / host out: H2D of the branch lengths, full evaluation, D2H of lnL + gradient."""
-        if B > 1:
-            return step_batch()
-        tlk.set_branch_lengths(new_bl())
-        if world == 1:
-            g = tlk.gradient()
-            return tlk.calculate(), g
-        tlk.gradient_device(out_dev.data_ptr())
-        tlk.synchronize()
-        dist.all_reduce(out_dev)
-        h = out_dev.cpu().numpy()
-        g = h[1:].copy()
-        g[topo.root] = 0.0
-        g[topo.right[topo.root]] = 0.0
-        return float(h[0]), g
-
-    def step_device():
-        """Device-resident step: inputs already in HBM, result left on the device."""
-        if B > 1:  # the batched entry point takes host buffers (2 x B x N doubles per step, ~1 MB each way at C3)
-            step_batch()
-            return
-        tlk.gradient_device(out_dev.data_ptr())
-        if world > 1:
-            tlk.synchronize()
-            dist.all_reduce(out_dev)
-
-    def sync_all():
-        tlk.synchronize()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
-
+    if not O.reference_available():
+        return ({"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"},
+                {"ok": None, "note": "no reference on this box: parity is covered by tests/ only"})
+    T = cfg["taxa"]
+    r = run_reference(cfg, cores, sample_patterns, iters=iters, want_values=True)
+    base = {"value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference",
+            "sample": f"{cores} single-threaded reference process(es) x {r['per']} patterns each, {iters} lnL+gradient evaluations each "
+                      f"({cfg['model']}, {T} taxa, tip partials, SSE on), {r['wall']:.1f} s wall",
+            "one_core_value": float(np.mean([p * r['nodes'] / s for s, p in zip(r['sec_per_eval'], r['patterns'])]))}
+    ref_lnl, ref_grad, ref_scaled = r["values"]
+    sub = dict(cfg, patterns=r["per"])
+    topo, bl, m, rates, props, patterns, weights = make_inputs(sub, rank=1000)  # worker 0's shard, same generator and seed
+    tlk = build_tlk(run, sub, topo, m, rates, props, patterns, weights, kernels)
     tlk.set_branch_lengths(bl)
-    for _ in range(W):
-        lnl, g = step_e2e()
-    if not np.isfinite(lnl):
-        raise SystemExit(f"non-finite lnL {lnl}")
-    for _ in range(W):
-        step_device()
-    sync_all()
+    B = int(cfg.get("batch", 1))
+    if B > 1:  # the batched entry point: sample 0 carries the reference's branch lengths
+        bls = np.stack([bl, bl * 1.1])
+        lnls, grads = tlk.gradient_batch(bls)
+        lnl, g = float(lnls[0]), grads[0]
+    else:
+        g = tlk.gradient()
+        lnl = tlk.calculate()
+    tlk.close()
+    g = g.copy()
+    ref_grad = ref_grad.copy()
+    ref_grad[topo.root] = ref_grad[topo.right[topo.root]] = 0.0
+    le = abs(lnl - ref_lnl) / abs(ref_lnl)
+    ge = grad_err(g, ref_grad)
+    par = {"ok": bool(le < PARITY_RTOL and ge < PARITY_RTOL), "lnl_rel_err": le, "grad_err": ge, "rtol": PARITY_RTOL, "patterns": int(patterns.shape[1]),
+           "against": "unmodified reference (oracle/_ref), TREE_MODEL gradient, include_root_freqs = false", "reference_rescaled": ref_scaled}
+    return base, par
 
-    # ---- timed region 1: device-resident throughput ("value"), CUDA events on the launching stream
-    tlk.set_option(OPT_TIMING, 1)
-    launches0 = tlk.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clocks:
-        sync_all()
-        e0.record(ext)
-        t0 = time.perf_counter()
-        for _ in range(K):
-            step_device()
-        if world > 1:
-            ext.wait_stream(torch.cuda.current_stream())
-        e1.record(ext)
-        sync_all()
-        wall = time.perf_counter() - t0
-    dev_ms = e0.elapsed_time(e1)
-    launches = tlk.launch_count() - launches0
-    kern_ms, kern_n = tlk.kernel_time()
-    tlk.set_option(OPT_TIMING, 0)
-    step_ms = max(dev_ms, 0.0) / K
-    if world > 1:
-        t = torch.tensor([step_ms, wall * 1e3 / K], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        step_ms, wall_ms = float(t[0]), float(t[1])
-        step_ms = max(step_ms, wall_ms) if step_ms <= 0 else step_ms
-    # ---- timed region 2: end to end through the public API with host buffers
-    sync_all()
-    t0 = time.perf_counter()
-    for _ in range(K):
-        lnl, g = step_e2e()
-    sync_all()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / K
-    if world > 1:
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t[0])
 
-    total_pn = float(P) * world * N * B
-    value = total_pn / (step_ms * 1e-3)
-    e2e_value = total_pn / (e2e_ms * 1e-3)
+def roofline_record(name, cfg, P, B, kms, kernels, lib_version):
+    T, S, C = cfg["taxa"], cfg["states"], cfg["cats"]
+    sized = dict(cfg, patterns=P)
     peak, peak_src = measured_peak_gbs()
-    alg = algorithmic_bytes(cfg) * B  # one launch processes the whole batch
-    kms = kern_ms / max(kern_n, 1)
+    alg = algorithmic_bytes(sized) * B  # one launch processes the whole batch
     achieved = alg / (kms * 1e-3) / 1e9 if kms > 0 else None
-    fused = args.kernels != "generic" and S == 4
-    tensor = args.kernels != "generic" and S in (20, 61)
-    traffic = measured_traffic(args.config if not args.patterns else None, args.kernels)
+    fused = kernels != "generic" and S == 4
+    tensor = kernels != "generic" and S in (20, 61)
+    traffic = measured_traffic(name, kernels, P, lib_version)
     hbm = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
            "traffic": traffic, "peak_source": peak_src, "kernel_ms": kms, "algorithmic_bytes_per_launch": alg}
     if traffic and kms > 0:
@@ -507,55 +479,332 @@ def main():
     if fused:
         fused_bytes = float(P) * B * (2 * (T - 1) * C * S * 8 + 2 * T)  # what the fused walk must move: lower rows out and back, tip codes twice
         hbm.update(kernel="k_nuc4_walk<C=%d,scale=0,grad=1>" % C, fused_min_bytes_per_launch=fused_bytes,
+                   fused_min_frac=(fused_bytes / (kms * 1e-3) / 1e9 / peak) if kms > 0 else None,
                    note="achieved = SURVEY.md 8d streaming-model bytes / kernel time; the fused walk keeps upper partials on chip, so it moves "
-                        f"~{fused_bytes/1e9:.1f} GB per launch (traffic = ncu dram bytes) and frac can exceed 1; traffic_frac is the real DRAM utilisation")
-        roof = hbm
-    elif tensor:
-        flops = algorithmic_flops(cfg)
+                        f"~{fused_bytes/1e9:.1f} GB per launch and frac can exceed 1; fused_min_frac (what the kernel must move / time / peak) and "
+                        "traffic_frac (ncu dram bytes, when a capture of this kernel revision is committed) are the real DRAM utilisation")
+        return hbm
+    if tensor:
+        flops = algorithmic_flops(sized)
         tpeak, tsrc = dmma_peak()
         tf = flops / (kms * 1e-3) / 1e12 if kms > 0 else None
-        roof = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": (tf / tpeak) if tf else None, "traffic": traffic,
-                "peak_source": tsrc, "kernel": "k_dmma_lower_msg + k_dmma_upper_msg (FP64 mma.sync m8n8k4, message form, branch gradients in adjoint form: 3 dense products per internal node), all levels of one evaluation",
+        return {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": (tf / tpeak) if tf else None, "traffic": traffic,
+                "peak_source": tsrc, "kernel": "k_dmma_* (FP64 mma.sync m8n8k4, message form, branch gradients in adjoint form), all launches of one evaluation",
                 "kernel_ms": kms, "algorithmic_flops_per_launch": flops, "hbm": hbm,
-                "note": "launch = the level-batched kernel sequence of one evaluation; S=20 sits at the FP64 ridge so the HBM view is given too"}
-    else:
-        hbm.update(kernel="generic node-at-a-time kernels, all levels of one evaluation")
-        roof = hbm
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": step_ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(cfg), "taxa": T, "patterns_per_gpu": P, "states": S, "categories": C, "model": cfg["model"],
-                   "kernels": args.kernels, "l2": "per-evaluation working set (>= 2 GB of partials) exceeds the 126 MB L2; no explicit flush",
-                   "sharding": f"patterns x{world}" if world > 1 else "single GPU", "samples_per_step": B, "inputs_sha256": sha},
-        "evals_per_s": B * 1e3 / step_ms, "lnl": lnl,
-        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * N * B, "d2h_bytes_per_step": 8 * (N + 1) * B,
-                "evals_per_s": B * 1e3 / e2e_ms},
-        "gpu_launches": int(launches),
-        "clocks": clocks.summary(),
-        "roofline": roof,
-    }
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        try:
-            from oracle import oracle as O
+                "note": "launch = the kernel sequence of one evaluation; S=20 sits at the FP64 ridge so the HBM view is given too"}
+    hbm.update(kernel="generic node-at-a-time kernels, all levels of one evaluation")
+    return hbm
 
-            if O.reference_available():
-                cores = min(os.cpu_count() or 1, 32)
-                r = run_reference(cfg, cores, sample_per_core(cfg) * cores, iters=3)
-                line["cpu_baseline"] = {
-                    "value": r["value"], "unit": UNIT, "cores": cores, "kind": "reference",
-                    "sample": f"{cores} single-threaded reference processes x {r['per']} patterns each, 3 lnL+gradient evaluations each "
-                              f"({cfg['model']}, {T} taxa, tip partials, SSE on), {r['wall']:.1f} s wall",
-                    "one_core_value": float(np.mean([p * r['nodes'] / s for s, p in zip(r['sec_per_eval'], r['patterns'])])),
-                }
-            else:
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+
+def run_config(run, name, cfg, K, W, kernels="auto", strong=False, full_cpu_baseline=False, gate=True):
+    """One BASELINE config on this invocation's GPUs: device-resident throughput, end-to-end throughput through the C ABI with host
+    buffers, the live kernel time for the roofline, clocks, and the parity gate against the reference on a bounded sample."""
+    torch = run.torch
+    from physher_b200.treelikelihood import OPT_TIMING
+
+    world, rank = run.world, run.rank
+    T, S, C = cfg["taxa"], cfg["states"], cfg["cats"]
+    N = 2 * T - 1
+    B_total = int(cfg.get("batch", 1))
+    P_total = cfg["patterns"] * (1 if strong or B_total > 1 else world)
+    if B_total > 1:  # batched samples: shard the SAMPLES across ranks (SURVEY.md 8e), no collective on the data path
+        B = (B_total * (rank + 1)) // world - (B_total * rank) // world
+        P = cfg["patterns"]
+        sharding = f"{B_total} samples over {world} GPUs ({B} on rank 0), patterns replicated" if world > 1 else "single GPU"
+    elif strong:
+        P = (cfg["patterns"] * (rank + 1)) // world - (cfg["patterns"] * rank) // world
+        B = 1
+        sharding = f"{cfg['patterns']} patterns split over {world} GPUs (strong scaling)" if world > 1 else "single GPU"
+    else:
+        P, B = cfg["patterns"], 1
+        sharding = f"{P} patterns per GPU x {world} (weak scaling)" if world > 1 else "single GPU"
+    rec = {"workload": workload_name(dict(cfg, patterns=P_total)).replace(" per GPU", " in total"), "taxa": T, "patterns_total": int(P_total),
+           "patterns_per_gpu": int(P), "states": S, "categories": C, "model": cfg["model"], "samples_per_step": B_total, "sharding": sharding,
+           "scaling": "strong" if (strong or B_total > 1) else "weak", "n_gpus": world}
+
+    cpu, par = None, None
+    if rank == 0 and gate:
+        try:
+            cores = min(os.cpu_count() or 1, 32) if full_cpu_baseline else 1
+            sample = sample_per_core(cfg) * cores if full_cpu_baseline else PARITY_PATTERNS.get(S, 64)
+            cpu, par = parity_gate(run, cfg, kernels, cores, sample, iters=3 if full_cpu_baseline else 1)
         except Exception as exc:  # the baseline must never take the GPU number down with it
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {exc!r}"}
-    if rank == 0:
-        print(json.dumps(line))
-    tlk.close()
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {exc!r}"}
+            par = {"ok": None, "note": f"gate did not run: {exc!r}"}
+    ok = run.reduce([0.0 if (par is not None and par.get("ok") is False) else 1.0], "max" if world == 1 else "sum")[0]
     if world > 1:
-        dist.destroy_process_group()
+        ok = 1.0 if ok >= world else 0.0
+    if cpu is not None:
+        rec["cpu_baseline"], rec["parity"] = cpu, par
+    if not ok:
+        rec["error"] = "parity gate failed: the device path does not reproduce the reference on the sample; no timing reported"
+        return rec
+
+    topo, bl, m, rates, props, patterns, weights = make_inputs(dict(cfg, patterns=P), 0 if B_total > 1 else rank)
+    rec["inputs_sha256"] = inputs_sha256(topo, bl, m, rates, props, patterns, weights) if rank == 0 else None
+    tlk = build_tlk(run, cfg, topo, m, rates, props, patterns, weights, kernels)
+    ext = torch.cuda.ExternalStream(tlk.stream(), device=torch.device("cuda", run.local_rank))
+    rng = np.random.default_rng(7)
+
+    def new_bl():
+        # every step sees new branch lengths (host buffer), like an optimiser / VI iteration would produce; the same on every rank
+        b = bl * rng.uniform(0.98, 1.02, size=bl.shape)
+        b[topo.root] = 0.0
+        b[topo.right[topo.root]] = 0.0
+        return b
+
+    def step_batch():
+        """BASELINE config 3: B branch-length samples (base x LogNormal(0, 0.1)) per step through phb_tlk_gradient_batch --
+        host buffers in ([B][N] doubles) and out (lnl[B], grad[B][N]); one fused launch for the whole batch."""
+        bls = bl[None, :] * rng.lognormal(0.0, 0.1, size=(B, N))
+        bls[:, topo.root] = 0.0
+        bls[:, topo.right[topo.root]] = 0.0
+        lnls, grads = tlk.gradient_batch(bls)
+        return float(lnls[-1]), grads[-1]
+
+    def step_e2e():
+        """The call a user makes, host in / host out: H2D of the branch lengths, the evaluation, (N > 1: the library's NCCL all-reduce
+        on the same stream,) D2H of lnL + gradient."""
+        if B_total > 1:
+            return step_batch()
+        tlk.set_branch_lengths(new_bl())
+        if world == 1:
+            g = tlk.gradient()
+            return tlk.calculate(), g
+        return tlk.gradient_allreduce(run.comm)
+
+    def step_device():
+        """Device-resident step: inputs already in HBM, the (reduced) result left on the device; nothing waits on the host."""
+        if B_total > 1:  # the batched entry point takes host buffers (2 x B x N doubles per step, ~1 MB each way at C3)
+            step_batch()
+        else:
+            tlk.gradient_allreduce_device(run.comm)
+
+    tlk.set_branch_lengths(bl)
+    lnl = float("nan")
+    for _ in range(W):
+        lnl, g = step_e2e()
+    if not np.isfinite(lnl):
+        tlk.close()
+        rec["error"] = f"non-finite lnL {lnl}"
+        return rec
+    for _ in range(W):
+        step_device()
+    run.sync(tlk)
+
+    # ---- timed region 1: device-resident throughput ("value"), CUDA events on the launching stream
+    tlk.set_option(OPT_TIMING, 1)
+    launches0 = tlk.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(run.local_rank) as clocks:
+        run.sync(tlk)
+        e0.record(ext)
+        for _ in range(K):
+            step_device()
+        e1.record(ext)
+        run.sync(tlk)
+        dev_ms = e0.elapsed_time(e1)
+        launches = tlk.launch_count() - launches0
+        kern_ms, kern_n = tlk.kernel_time()
+        tlk.set_option(OPT_TIMING, 0)
+        # ---- timed region 2: end to end through the public API with host buffers
+        run.sync(tlk)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            lnl, g = step_e2e()
+        run.sync(tlk)
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+    kms = kern_ms / max(kern_n, 1)
+    step_ms, e2e_ms, kms_max = run.reduce([dev_ms / K, e2e_ms, kms], "max")
+    total_pn = run.reduce([float(P) * N * B], "sum")[0]
+    rec.update({
+        "value": total_pn / (step_ms * 1e-3), "unit": UNIT, "steps": K, "warmup": W, "ms_per_step": step_ms,
+        "evals_per_s": B_total * 1e3 / step_ms, "lnl": lnl,
+        "e2e": {"value": total_pn / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": 8 * N * B, "d2h_bytes_per_step": 8 * (N + 1) * B,
+                "evals_per_s": B_total * 1e3 / e2e_ms},
+        "gpu_launches": int(launches), "launches_per_step": launches / K,
+        "collective": (f"one ncclAllReduce(sum, double, {N + 2}) per step issued by libphysher_b200 on the evaluation's stream" if (world > 1 and B_total == 1)
+                       else "none"),
+        "clocks": clocks.summary(),
+        "roofline": roofline_record(name, cfg, P, B, kms_max, kernels, run.phb.load_library().phb_version().decode()),
+        "l2": "per-evaluation working set exceeds the 126 MB L2; no explicit flush",
+    })
+    tlk.close()
+    return rec
+
+
+def run_c1(run, K, W):
+    """BASELINE config 1 (examples/fluA JC69 strict-clock time tree: 69 taxa x 238 patterns, one rate category): a LATENCY workload.
+    (a) single lnL + gradient evaluations through the C ABI with host buffers (what the glue does per model->logP / dlogP);
+    (b) the ELBO shape of examples/fluA/JC69-time-ELBO.json: 100 reparameterised tree samples per step through
+        phb_tlk_gradient_batch_time (heights, branch lengths, one fused launch, ratio / root-height / clock gradients).
+    The reference's own known answers (tests/test_tree_likelihood.c:28-116, tests/golden/c1_kat.json) gate the record."""
+    phb = run.phb
+    gold = os.path.join(ROOT, "tests", "golden")
+    z = dict(np.load(os.path.join(gold, "c1_jc69_fluA_tipstates.npz")))
+    tt = dict(np.load(os.path.join(gold, "c1_time_tree.npz")))
+    kat = json.load(open(os.path.join(gold, "c1_kat.json")))
+    T, P = z["tip_states"].shape
+    N = 2 * T - 1
+    rec = {"workload": f"JC69 strict clock, fluA {T} taxa x {P} patterns (tests/data/jc69-time.json = the likelihood of examples/fluA/JC69-time-ELBO.json)",
+           "taxa": int(T), "patterns_total": int(P), "states": 4, "categories": 1, "model": "JC69", "n_gpus": 1, "sharding": "rank 0 only (latency-bound, does not shard)"}
+    tlk = phb.SingleTreeLikelihood(z["left"], z["right"], int(z["root"]), 4, 1, P, use_tip_states=True, device=run.local_rank)
+    tlk.set_tip_states(z["tip_states"])
+    tlk.set_pattern_weights(z["weights"])
+    # JC69 as an eigen system: Q = (J - 4 I) / 3 is diagonalised by the 4 x 4 Hadamard matrix (entries +-1/2, exact in binary)
+    vec = 0.5 * np.array([[1, 1, 1, 1], [1, 1, -1, -1], [1, -1, 1, -1], [1, -1, -1, 1]], dtype=np.float64)
+    tlk.set_eigen(vec, np.array([0.0, -4.0 / 3.0, -4.0 / 3.0, -4.0 / 3.0]), vec)
+    tlk.set_frequencies(z["freqs"])
+    tlk.set_site_model(z["rates"], z["props"])
+    tlk.set_option(phb.treelikelihood.OPT_UNROOTED, 0)
+    tlk.initialize_gradient(phb.FLAG_TREE_MODEL)
+    tlk.set_time_tree(tt["tip_heights"])
+    bl = z["bl"].astype(np.float64)
+    # gate: the reference's known answers
+    tlk.set_branch_lengths(bl)
+    lnl = tlk.calculate()
+    l1, lj, gr, gc = tlk.gradient_batch_time(tt["ratios"][:1], tt["rates"][:1, None], include_jacobian=False)
+    want = np.array(kat["ratio_grad"] + [kat["root_height_grad"]])
+    le = abs(lnl - kat["logP"]) / abs(kat["logP"])
+    ge = max(grad_err(gr[0], want), abs(gc[0, 0] - kat["rate_grad"]) / abs(kat["rate_grad"]), abs(l1[0] - kat["logP"]) / abs(kat["logP"]))
+    rec["parity"] = {"ok": bool(le < PARITY_RTOL and ge < PARITY_RTOL), "lnl_rel_err": le, "grad_err": ge, "rtol": PARITY_RTOL,
+                     "against": "known answers of the reference's tests/test_tree_likelihood.c:28-84 (lnL, clock-rate gradient, 67 ratio gradients, root height)"}
+    if not rec["parity"]["ok"]:
+        rec["error"] = "parity gate failed; no timing reported"
+        tlk.close()
+        return rec
+    rng = np.random.default_rng(5)
+    n_single = max(200, 10 * K)
+    launches0 = tlk.launch_count()
+
+    def single():
+        tlk.set_branch_lengths(bl * rng.uniform(0.98, 1.02, size=N))
+        g = tlk.gradient()
+        return tlk.calculate(), g
+
+    for _ in range(max(W, 10)):
+        single()
+    tlk.synchronize()
+    with ClockSampler(run.local_rank) as clocks:
+        t0 = time.perf_counter()
+        for _ in range(n_single):
+            single()
+        tlk.synchronize()
+        single_ms = (time.perf_counter() - t0) * 1e3 / n_single
+        launches = (tlk.launch_count() - launches0) / (n_single + max(W, 10))
+        # (b) the ELBO batch
+        Bs = 100
+        ratios = np.clip(tt["ratios"][0][None, :] + rng.normal(0.0, 0.01, size=(Bs, T - 1)), 1e-3, 1 - 1e-3)
+        ratios[:, -1] = tt["ratios"][0][-1] * rng.lognormal(0.0, 0.01, size=Bs)  # root height
+        rates = tt["rates"][0] * rng.lognormal(0.0, 0.05, size=(Bs, 1))
+        for _ in range(W):
+            tlk.gradient_batch_time(ratios, rates, include_jacobian=True)
+        t0 = time.perf_counter()
+        for _ in range(K):
+            lb, _, _, _ = tlk.gradient_batch_time(ratios, rates, include_jacobian=True)
+        batch_ms = (time.perf_counter() - t0) * 1e3 / K
+    pn = float(P) * N
+    rec.update({
+        "value": pn * 1e3 / single_ms, "unit": UNIT, "ms_per_step": single_ms, "evals_per_s": 1e3 / single_ms, "steps": n_single, "lnl": lnl,
+        "timing": "wall clock around set_branch_lengths + gradient + calculate with host buffers (a latency workload: the host round trip IS the step)",
+        "e2e": {"value": pn * 1e3 / single_ms, "unit": UNIT, "ms_per_step": single_ms, "evals_per_s": 1e3 / single_ms, "h2d_bytes_per_step": 8 * N, "d2h_bytes_per_step": 8 * (N + 1)},
+        "launches_per_step": launches,
+        "elbo_batch": {"samples_per_step": Bs, "ms_per_step": batch_ms, "sample_evals_per_s": Bs * 1e3 / batch_ms, "steps": K,
+                       "call": "phb_tlk_gradient_batch_time (ratios, root height, clock rate in; lnL, log Jacobian, ratio / root-height / clock gradients out)",
+                       "h2d_bytes_per_step": 8 * Bs * T, "d2h_bytes_per_step": 8 * Bs * (T + 2), "lnl_finite": bool(np.isfinite(lb).all())},
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "latency", "note": "23 kB of tip codes and 137 nodes: launch + copy latency bound, no bandwidth roofline applies"},
+    })
+    tlk.close()
+    try:  # cpu_baseline leg: the reference's own evaluation of the same fixture on one host core
+        from oracle import oracle as O
+
+        if O.reference_available():
+            devnull, saved = os.open(os.devnull, os.O_WRONLY), os.dup(1)
+            os.dup2(devnull, 1)
+            try:
+                spec = json.load(open(os.path.join(gold, "c1_jc69_time.json")))["model"]
+                ref = O.Reference(spec)
+                ref.time_gradient(20, O.FLAG_TREE_MODEL | O.FLAG_BRANCH_MODEL, -1)
+                sec = ref.time_gradient(200, O.FLAG_TREE_MODEL | O.FLAG_BRANCH_MODEL, -1)
+                ref.close()
+            finally:
+                os.dup2(saved, 1)
+                os.close(devnull)
+            rec["cpu_baseline"] = {"value": pn / sec, "unit": UNIT, "evals_per_s": 1.0 / sec, "cores": 1, "kind": "reference",
+                                   "sample": "200 lnL+gradient evaluations (tree + clock flags) of tests/data/jc69-time.json, tipstates as the fixture sets them, one core"}
+            rec["elbo_batch"]["cpu_sequential_sample_evals_per_s"] = 1.0 / sec
+    except Exception as exc:
+        rec["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {exc!r}"}
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS), help="headline workload (default: BASELINE configs[1])")
+    ap.add_argument("--sub", default=None, help="comma list of further configs reported as sub-records under `configs` "
+                                                "(default: all of c1,c2_1m,c3,c4,c5 for the default headline; 'none' to skip)")
+    ap.add_argument("--sub-steps", type=int, default=5)
+    ap.add_argument("--patterns", type=int, default=0, help="override patterns per GPU of the headline workload")
+    ap.add_argument("--kernels", default="auto", choices=["auto", "generic", "fused"])
+    ap.add_argument("--strong", action="store_true", help="headline: split --config's patterns over the GPUs instead of weak scaling")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = dict(CONFIGS[args.config])
+    if args.patterns:
+        cfg["patterns"] = args.patterns
+    if args.impl == "reference":
+        return reference_main(args, cfg)
+
+    run = Run()
+    W, K = max(args.warmup, 3), args.steps
+    head = run_config(run, args.config, cfg, K, W, kernels=args.kernels, strong=args.strong, full_cpu_baseline=(run.world == 1),
+                      gate=not args.no_cpu_baseline)
+    if args.sub is None:
+        subs = SUB_CONFIGS if (args.config == "c2" and not args.patterns and args.kernels == "auto") else []
+    else:
+        subs = [] if args.sub in ("none", "") else [s.strip() for s in args.sub.split(",")]
+    records = {}
+    for name in subs:
+        t0 = time.perf_counter()
+        try:
+            if name == "c1":
+                if run.rank == 0:
+                    records[name] = run_c1(run, max(args.sub_steps, 5), W)
+                run.sync()
+            else:
+                records[name] = run_config(run, name, dict(CONFIGS[name]), args.sub_steps, W, strong=True, gate=not args.no_cpu_baseline)
+        except Exception as exc:  # a sub-record must not take the headline down
+            records[name] = {"error": repr(exc)}
+            if run.world > 1:
+                raise
+        if name in records:
+            records[name]["wall_s"] = time.perf_counter() - t0
+    if "error" in head:
+        if run.rank == 0:
+            print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": run.world, "error": head["error"], "parity": head.get("parity")}))
+        run.close()
+        return 1
+    line = {
+        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": run.world, "steps": K, "warmup": W, "ms_per_step": head["ms_per_step"],
+        "higher_is_better": True, "scaling": head["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg), "taxa": cfg["taxa"], "patterns_per_gpu": head["patterns_per_gpu"], "states": cfg["states"],
+                   "categories": cfg["cats"], "model": cfg["model"], "kernels": args.kernels, "l2": head["l2"], "sharding": head["sharding"],
+                   "samples_per_step": head["samples_per_step"], "inputs_sha256": head["inputs_sha256"]},
+        "evals_per_s": head["evals_per_s"], "lnl": head["lnl"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+        "collective": head["collective"], "clocks": head["clocks"], "roofline": head["roofline"],
+    }
+    if "cpu_baseline" in head:
+        line["cpu_baseline"], line["parity"] = head["cpu_baseline"], head["parity"]
+    if records:
+        line["configs"] = records
+    if run.rank == 0:
+        print(json.dumps(line))
+    run.close()
     return 0
 
 

@@ -303,6 +303,14 @@ const char *phb_patterns_last_error(void);
  * (the fused walk kernel, or the sum of the node-at-a-time kernels) since the option was set. Synchronises. */
 int phb_tlk_kernel_time(phb_tlk *tlk, double *total_ms, long long *launches);
 
+/* kernel family the last evaluation ran on (what the function-pointer dispatch of treelikelihood.c:1067-1165 decides by state count in
+ * the reference): 0 none yet, PHB_RAN_GENERIC node-at-a-time kernels, PHB_RAN_WALK the fused 4-state walk, PHB_RAN_TENSOR the FP64
+ * tensor-core kernels.  phb_tlk_get_matrices returns the matrices THAT family consumed (walk-ordered set / packed images, unpacked). */
+#define PHB_RAN_GENERIC 1
+#define PHB_RAN_WALK 2
+#define PHB_RAN_TENSOR 3
+int phb_tlk_last_kernels(const phb_tlk *tlk);
+
 /* number of kernel launches issued by this tlk since creation (bench.py's gpu_launches) */
 long long phb_tlk_launch_count(const phb_tlk *tlk);
 

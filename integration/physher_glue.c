@@ -116,17 +116,43 @@ static void sync_inputs(Backend *b) {
 	}
 	/* substitution model: the host-side eigen system (substmodel.c:518-557), or closed-form matrices (jc69.c:73, hky.c:230) */
 	SubstitutionModel *m = tlk->m;
-	const int has_eigen = m->eigendcmp != NULL && m->modeltype != JC69;
+	/* JC69 and F81 (both carry modeltype JC69: jc69.c:31, f81.c:33) have closed-form p_t / dp_dt and never fill m->eigendcmp.  Their
+	 * rate matrix is Q = beta (1 pi^T - I), beta = 1 / (1 - sum pi^2) (f81.c:45-61, 77; pi = 1/4 gives jc69.c:73-94), whose eigen system
+	 * is known in closed form: eigenvalues (0, -beta, -beta, -beta), V = [1 | e_k - pi_k 1], V^-1 = [pi ; e_k - e_S].  Handing that
+	 * over keeps these models on the eigen path: matrices are built on the device (no 2 N C host p_t calls + upload per evaluation),
+	 * the fused 4-state walk serves them, and the single-branch path can rebuild P, P', P" at a candidate length. */
+	const int f81_like = m->modeltype == JC69 && S == 4;
+	const int has_eigen = f81_like || m->eigendcmp != NULL;
 	if (has_eigen) {
-		if (m->need_update) {
-			m->update_Q(m);
-			update_eigen_system(m);
-		}
-		for (int i = 0; i < S; i++) {
-			eval[i] = m->eigendcmp->eval[i];
-			for (int j = 0; j < S; j++) {
-				evec[i * S + j] = m->eigendcmp->evec[i][j];
-				ivec[i * S + j] = m->eigendcmp->Invevec[i][j];
+		if (f81_like) {
+			const double *pi = m->get_frequencies(m);
+			double ss = 0.0;
+			for (int i = 0; i < S; i++) ss += pi[i] * pi[i];
+			const double beta = 1.0 / (1.0 - ss);
+			memset(evec, 0, sizeof(double) * S * S);
+			memset(ivec, 0, sizeof(double) * S * S);
+			eval[0] = 0.0;
+			for (int i = 0; i < S; i++) {
+				evec[i * S] = 1.0;
+				ivec[i] = pi[i];
+			}
+			for (int k = 1; k < S; k++) {
+				eval[k] = -beta;
+				for (int i = 0; i < S; i++) evec[i * S + k] = (i == k - 1 ? 1.0 : 0.0) - pi[k - 1];
+				ivec[k * S + (k - 1)] = 1.0;
+				ivec[k * S + (S - 1)] = -1.0;
+			}
+		} else {
+			if (m->need_update) {
+				m->update_Q(m);
+				update_eigen_system(m);
+			}
+			for (int i = 0; i < S; i++) {
+				eval[i] = m->eigendcmp->eval[i];
+				for (int j = 0; j < S; j++) {
+					evec[i * S + j] = m->eigendcmp->evec[i][j];
+					ivec[i * S + j] = m->eigendcmp->Invevec[i][j];
+				}
 			}
 		}
 		if (!b->have_model || !same(evec, b->evec, (size_t)S * S) || !same(eval, b->eval, S) || !same(ivec, b->ivec, (size_t)S * S)) {

@@ -84,6 +84,7 @@ void *refh_create_codon(const char *newick, int n, const char **names, const cha
 	SingleTreeLikelihood *tlk = new_SingleTreeLikelihood(tree, m, sm, sp, NULL, false);
 	h->model = new_TreeLikelihoodModel("treelikelihood", tlk, mtree, mm, msm, NULL);
 	h->tlk = tlk;
+	tlk->include_jacobian = false; /* only the JSON factory initialises this field (treelikelihood.c:935): model->logP would add the tree model's Jacobian */
 	extern void refh_use_generic_kernels(void *);
 	refh_use_generic_kernels(h);
 	return h;

@@ -24,7 +24,8 @@
 // P(t), r P'(t), r^2 P"(t) for every (candidate, category): grid (nbl, C); mats [nbl][C][3][S*S]
 // (p_t substmodel.c:518-557 with fabs, dp_dt :695-723, d2p_d2t :801-828; same operation order, no fused multiply-add)
 __global__ void k_branch_matrices(int S, int C, const double *__restrict__ evec, const double *__restrict__ eval, const double *__restrict__ ivec,
-                                  const double *__restrict__ bl, const double *__restrict__ rates, double *__restrict__ mats) {
+                                  const double *__restrict__ bl, const double *__restrict__ rates, const double *__restrict__ ex_host,
+                                  double *__restrict__ mats) {
 	extern __shared__ double sm[];
 	double *e0 = sm, *e1 = sm + S, *e2 = sm + 2 * S;
 	const int k = blockIdx.x, c = blockIdx.y;
@@ -32,7 +33,7 @@ __global__ void k_branch_matrices(int S, int C, const double *__restrict__ evec,
 	const double t = bl[k] * r;
 	for (int q = threadIdx.x; q < S; q += blockDim.x) {
 		const double l = eval[q];
-		const double e = exp(l * t);
+		const double e = ex_host ? ex_host[((size_t)k * C + c) * S + q] : exp(l * t);  // see k_transition_matrices
 		e0[q] = e;
 		e1[q] = l * e;
 		e2[q] = l * l * e;
@@ -138,7 +139,7 @@ __global__ void k_branch_sum(const double *__restrict__ partial, int n, double *
 }
 
 // out_host [nbl][3]: lnL, d lnL / dt, d2 lnL / dt2 of the branch above `node` at each candidate length; U_node and L_node must be resident
-extern "C" int phbc_branch_lnl(phbc_ctx *ctx, const phbc_eval_opts *o, int node, int nbl, const double *bl_host, double *out_host) {
+extern "C" int phbc_branch_lnl(phbc_ctx *ctx, const phbc_eval_opts *o, int node, int nbl, const double *bl_host, const double *ex_host, double *out_host) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));
 	const size_t S = ctx->S, C = ctx->C, P = ctx->P;
 	if (node < 0 || node >= ctx->N || node == ctx->root || nbl < 1) {
@@ -155,8 +156,8 @@ extern "C" int phbc_branch_lnl(phbc_ctx *ctx, const phbc_eval_opts *o, int node,
 		return -4;
 	}
 	const size_t tiles = (P + BR_THREADS - 1) / BR_THREADS;
-	// scratch: bl [nbl] | results [nbl][3] | matrices [nbl][C][3][S*S] | partial [nbl][3][tiles]
-	const size_t need = ((size_t)nbl * (4 + C * 3 * S * S + 3 * tiles)) * sizeof(double);
+	// scratch: bl [nbl] | results [nbl][3] | matrices [nbl][C][3][S*S] | partial [nbl][3][tiles] | host exponentials [nbl][C][S]
+	const size_t need = ((size_t)nbl * (4 + C * 3 * S * S + 3 * tiles + C * S)) * sizeof(double);
 	if (need > ctx->branch_bytes) {
 		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 		if (ctx->d_branch) cudaFree(ctx->d_branch);
@@ -166,10 +167,12 @@ extern "C" int phbc_branch_lnl(phbc_ctx *ctx, const phbc_eval_opts *o, int node,
 		ctx->branch_bytes = need;
 	}
 	double *d_bl = ctx->d_branch, *d_out = d_bl + nbl, *d_mats = d_out + 3 * (size_t)nbl, *d_part = d_mats + (size_t)nbl * C * 3 * S * S;
+	double *d_ex = ex_host ? d_part + (size_t)nbl * 3 * tiles : NULL;
 	PHBC_CHECK(cudaMemcpyAsync(d_bl, bl_host, nbl * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	if (ex_host) PHBC_CHECK(cudaMemcpyAsync(d_ex, ex_host, (size_t)nbl * C * S * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 	const int mthreads = S * S >= 256 ? 256 : (S * S >= 64 ? 64 : 32);
 	k_branch_matrices<<<dim3(nbl, (unsigned)C), mthreads, 3 * S * sizeof(double), ctx->stream>>>((int)S, (int)C, ctx->d_evec, ctx->d_eval, ctx->d_ivec, d_bl,
-	                                                                                        ctx->d_rates, d_mats);
+	                                                                                        ctx->d_rates, d_ex, d_mats);
 	const size_t smem = 3 * S * S * sizeof(double);
 	if (smem > 48 * 1024) PHBC_CHECK(cudaFuncSetAttribute(k_branch_lnl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	Bufs b = phbc_make_bufs(ctx);

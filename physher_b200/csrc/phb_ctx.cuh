@@ -25,7 +25,7 @@ struct phbc_ctx {
 	int bl_cap;
 	bool have_eigen;
 	double *d_ex, *h_ex;     // [N][C][S] host-computed exp(eval * t) of the branch lengths uploaded last (61-state parity), pinned staging
-	bool ex_valid;
+	int ex_cap, ex_count;    // samples the buffers hold / samples whose exponentials belong to the branch lengths uploaded last
 
 	// node-at-a-time state
 	double *d_P, *d_dP;      // [N][C][S*S]
@@ -85,6 +85,8 @@ struct phbc_ctx {
 	double *h_tt;            // pinned staging
 	int tt_cap;
 
+	int last_family;         // kernels of the last evaluation: 1 generic node-at-a-time, 2 fused 4-state walk, 3 FP64 tensor-core
+	int dmma_pack_adjoint, dmma_pack_irf;  // how the dP images of internal nodes were packed last (phbc_download_matrices undoes it)
 	long long launches;
 	long long node_evals;    // full evaluations that rewrote the node-at-a-time buffers (generic / tensor-core paths)
 
@@ -141,6 +143,8 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
 bool phbc_nuc4_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);
 int phbc_nuc4_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int nsets, const double *M_host, int skip_node, double *lnl, double *out_host);  // 1 = declined
 int phbc_nuc4_root_frequency_gradient(phbc_ctx *ctx, double *out_host);
+int phbc_nuc4_download_matrices(phbc_ctx *ctx, double *P, double *dP);  // what the last walk consumed, back in [N][C][4][4] form
+int phbc_dmma_download_matrices(phbc_ctx *ctx, double *P, double *dP);  // the packed images, unpacked
 
 // shared device helpers
 __device__ __forceinline__ double phb_warp_sum(double v) {

@@ -338,24 +338,39 @@ extern "C" int phbc_copy_inputs(phbc_ctx *dst, phbc_ctx *src, int matrices, int 
 
 // exp(eval[k] * bl[n] * rates[c]) for the branch lengths uploaded LAST, [N][C][S], computed by the host (see k_transition_matrices);
 // valid until the next branch-length upload
-extern "C" int phbc_upload_exponentials(phbc_ctx *ctx, const double *ex) {
+extern "C" int phbc_upload_exponentials(phbc_ctx *ctx, const double *ex, int nbatch) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));
-	const size_t n = (size_t)ctx->N * ctx->C * ctx->S;
-	if (!ctx->d_ex) {
+	const size_t n = (size_t)ctx->N * ctx->C * ctx->S * (size_t)nbatch;
+	if (nbatch > ctx->ex_cap) {
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		if (ctx->d_ex) cudaFree(ctx->d_ex);
+		if (ctx->h_ex) cudaFreeHost(ctx->h_ex);
+		ctx->d_ex = ctx->h_ex = NULL;
+		ctx->ex_cap = 0;
 		PHBC_CHECK(cudaMalloc((void **)&ctx->d_ex, n * sizeof(double)));
 		PHBC_CHECK(cudaMallocHost((void **)&ctx->h_ex, n * sizeof(double)));
+		ctx->ex_cap = nbatch;
 	}
 	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));  // the previous copy out of the pinned staging buffer
 	memcpy(ctx->h_ex, ex, n * sizeof(double));
 	PHBC_CHECK(cudaMemcpyAsync(ctx->d_ex, ctx->h_ex, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-	ctx->ex_valid = true;
+	ctx->ex_count = nbatch;
+	return 0;
+}
+
+// branch lengths as the device holds them (the time-tree chain builds them there): [nbatch][N], blocking
+extern "C" int phbc_download_branch_lengths(phbc_ctx *ctx, int nbatch, double *bl) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	if (nbatch > ctx->bl_cap) return -1;
+	PHBC_CHECK(cudaMemcpyAsync(bl, ctx->d_bl, (size_t)nbatch * ctx->N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 	return 0;
 }
 
 extern "C" int phbc_upload_branch_lengths(phbc_ctx *ctx, const double *bl, int nbatch) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));
 	const size_t N = ctx->N;
-	ctx->ex_valid = false;
+	ctx->ex_count = 0;
 	if (nbatch > ctx->bl_cap) {
 		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 		cudaFree(ctx->d_bl);
@@ -638,7 +653,7 @@ static int phbc_launch_transition_matrices(phbc_ctx *ctx, int batch_index) {
 	const int threads = S * S >= 256 ? 256 : (S * S >= 64 ? 64 : 32);
 	k_transition_matrices<<<grid, threads, 2 * S * sizeof(double), ctx->stream>>>(
 	    S, ctx->C, ctx->root, ctx->d_evec, ctx->d_eval, ctx->d_ivec, ctx->d_bl + (size_t)batch_index * ctx->N, ctx->d_rates,
-	    ctx->d_P, ctx->d_dP, (ctx->ex_valid && batch_index == 0) ? ctx->d_ex : NULL);
+	    ctx->d_P, ctx->d_dP, batch_index < ctx->ex_count ? ctx->d_ex + (size_t)batch_index * ctx->N * ctx->C * S : NULL);
 	ctx->launches++;
 	PHBC_CHECK(cudaGetLastError());
 	return 0;
@@ -828,7 +843,9 @@ extern "C" int phbc_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int 
 		const int frc = phbc_nuc4_matrix_gradient(ctx, &e, nsets, M_host, skip_node, lnl, out_host);
 		if (frc != 1) return frc;
 	}
-	int rc = phbc_dmma_supported(ctx, &e) && e.kernels != 1 ? phbc_dmma_evaluate(ctx, &e) : phbc_generic_evaluate(ctx, &e);
+	const bool tensor = phbc_dmma_supported(ctx, &e) && e.kernels != 1;
+	ctx->last_family = tensor ? 3 : 1;
+	int rc = tensor ? phbc_dmma_evaluate(ctx, &e) : phbc_generic_evaluate(ctx, &e);
 	if (rc) return rc;
 	const size_t set = N * C * S * S;
 	double *d_M = NULL, *d_cat = NULL, *d_out = NULL;
@@ -887,6 +904,7 @@ extern "C" int phbc_run_ops(phbc_ctx *ctx, const phbc_eval_opts *o, int nops, co
 		if (ops[k].out >= (int)N) e.want_gradient = 1;  // upper buffers are needed
 	if ((rc = phbc_generic_buffers(ctx, &e))) return rc;
 	const bool dmma = e.kernels != 1 && phbc_dmma_supported(ctx, &e);
+	ctx->last_family = 1;  // the op lists run on the node-at-a-time buffers and matrices (tensor-core products where the shape allows)
 	if (rebuild_matrices) {
 		if (!e.explicit_matrices) {
 			if (!ctx->have_eigen) {
@@ -1056,7 +1074,7 @@ extern "C" int phbc_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "batch %d + %d out of range", o->batch_index, count);
 		return -1;
 	}
-	if (o->kernels != 1 /* PHB_KERNELS_GENERIC */ && phbc_nuc4_supported(ctx, o)) return phbc_nuc4_evaluate(ctx, o);  // one launch for the whole batch
+	if (o->kernels != 1 /* PHB_KERNELS_GENERIC */ && phbc_nuc4_supported(ctx, o)) return phbc_nuc4_evaluate(ctx, o);  // one launch for the whole batch (sets last_family itself: it may decline)
 	if (count > 1) {  // node-at-a-time paths own one set of partials: samples run back to back
 		phbc_eval_opts one = *o;
 		one.batch_count = 1;
@@ -1067,11 +1085,15 @@ extern "C" int phbc_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		}
 		return 0;
 	}
-	if (o->kernels != 1 /* PHB_KERNELS_GENERIC */ && phbc_dmma_supported(ctx, o)) return phbc_dmma_evaluate(ctx, o);
+	if (o->kernels != 1 /* PHB_KERNELS_GENERIC */ && phbc_dmma_supported(ctx, o)) {
+		ctx->last_family = 3;
+		return phbc_dmma_evaluate(ctx, o);
+	}
 	if (o->kernels == 2 /* PHB_KERNELS_FUSED */) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "fused kernels not available for this configuration (S=%d)", ctx->S);
 		return -1;
 	}
+	ctx->last_family = 1;
 	return phbc_generic_evaluate(ctx, o);
 }
 
@@ -1169,7 +1191,11 @@ extern "C" int phbc_download_partials(phbc_ctx *ctx, int index, double *out) {
 	DOWNLOAD(out, ctx->d_upper + (size_t)(index - ctx->N) * psize, psize);
 	return 0;
 }
+// the matrices the LAST evaluation's kernels consumed: the node-at-a-time arrays, the walk-ordered set of the fused 4-state walk
+// or the packed images of the tensor-core path, each brought back to [N][C][S][S] (the root's entry is not a transition matrix)
 extern "C" int phbc_download_matrices(phbc_ctx *ctx, double *P, double *dP) {
+	if (ctx->last_family == 2) return phbc_nuc4_download_matrices(ctx, P, dP);
+	if (ctx->last_family == 3) return phbc_dmma_download_matrices(ctx, P, dP);
 	if (!ctx->d_P) return -4;
 	const size_t n = (size_t)ctx->N * ctx->C * ctx->S * ctx->S;
 	if (P) DOWNLOAD(P, ctx->d_P, n);
@@ -1239,3 +1265,4 @@ extern "C" int phbc_kernel_time(phbc_ctx *ctx, double *total_ms, long long *laun
 }
 extern "C" long long phbc_launch_count(const phbc_ctx *ctx) { return ctx->launches; }
 extern "C" long long phbc_node_eval_count(const phbc_ctx *ctx) { return ctx->node_evals; }
+extern "C" int phbc_last_family(const phbc_ctx *ctx) { return ctx->last_family; }

@@ -109,7 +109,8 @@ int phbc_upload_matrices(phbc_ctx *ctx, const double *P, const double *dP);
 int phbc_upload_freqs(phbc_ctx *ctx, const double *freqs);
 int phbc_upload_site_model(phbc_ctx *ctx, const double *rates, const double *props);
 int phbc_upload_branch_lengths(phbc_ctx *ctx, const double *bl, int nbatch); /* [nbatch][N], pinned staging */
-int phbc_upload_exponentials(phbc_ctx *ctx, const double *ex); /* [N][C][S] exp(eval * bl * rate) from the host's libm, for the vector uploaded last */
+int phbc_upload_exponentials(phbc_ctx *ctx, const double *ex, int nbatch); /* [nbatch][N][C][S] exp(eval * bl * rate) from the host's libm, for the vectors uploaded last */
+int phbc_download_branch_lengths(phbc_ctx *ctx, int nbatch, double *bl); /* [nbatch][N] as the device holds them */
 /* device-to-device copy of the bulky inputs (tips, weights, explicit matrices, time-tree tables) between same-shaped contexts */
 int phbc_copy_inputs(phbc_ctx *dst, phbc_ctx *src, int matrices, int time_tree);
 
@@ -154,7 +155,8 @@ int phbc_root_frequency_gradient(phbc_ctx *ctx, double *out /* [S] */);
 /* K9 / K10 / A11 over every branch from resident upper and lower partials (results in slot 0; lnL slot untouched) */
 int phbc_resident_gradient(phbc_ctx *ctx, const phbc_eval_opts *o);
 /* single-branch fast path (phb_branch.cu): out [nbl][3] = lnL, d lnL/dt, d2 lnL/dt2 at each candidate length of the branch above node */
-int phbc_branch_lnl(phbc_ctx *ctx, const phbc_eval_opts *o, int node, int nbl, const double *bl, double *out);
+/* ex (may be NULL): [nbl][C][S] exp(eval * bl * rate) from the host's libm */
+int phbc_branch_lnl(phbc_ctx *ctx, const phbc_eval_opts *o, int node, int nbl, const double *bl, const double *ex, double *out);
 int phbc_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int nsets, const double *M_host, int skip_node, double *lnl, double *out_host);
 /* time-tree chain, batched (phb_timetree.cu) */
 int phbc_set_time_tree(phbc_ctx *ctx, const double *lowers, const int *parent, const int *preorder, const int *postorder);
@@ -164,6 +166,7 @@ int phbc_time_backward(phbc_ctx *ctx, int nbatch, int nrates, int include_jacobi
 int phbc_synchronize(phbc_ctx *ctx);
 void *phbc_stream(phbc_ctx *ctx);
 long long phbc_launch_count(const phbc_ctx *ctx);
+int phbc_last_family(const phbc_ctx *ctx); /* 1 generic, 2 fused walk, 3 tensor cores; 0 before the first evaluation */
 long long phbc_node_eval_count(const phbc_ctx *ctx); /* full evaluations that rewrote the node-at-a-time partials buffers */
 int phbc_set_timing(phbc_ctx *ctx, int on);
 int phbc_kernel_time(phbc_ctx *ctx, double *total_ms, long long *launches);

@@ -1017,6 +1017,7 @@ static int dmma_pack(phbc_ctx *ctx, bool adjoint = false, int include_root_freqs
 		PHBC_CHECK(cudaMalloc((void **)&ctx->d_dmma_img, img_bytes));
 		ctx->dmma_img_bytes = img_bytes;
 	}
+	ctx->dmma_pack_adjoint = adjoint, ctx->dmma_pack_irf = include_root_freqs;
 	k_dmma_pack<Sh><<<dim3(N, C, 2), 128, 0, ctx->stream>>>(ctx->T, N, C, ctx->root, ctx->tip_kind == PHBC_TIP_STATES, ctx->d_P, ctx->d_dP, ctx->d_dmma_img,
 	                                                         adjoint ? 1 : 0, ctx->d_freqs, include_root_freqs);
 	ctx->launches++;
@@ -1059,7 +1060,7 @@ static int dmma_lower_msg_level(phbc_ctx *ctx, int level) {
 	const size_t ring = (size_t)Cf::WM * AStage<Sh, Cf::MT, 2>::NSTAGE * AStage<Sh, Cf::MT, 2>::STG;
 	const int lthreads = 32 * Cf::WM * Cf::NSPLIT, ltiles = (P + Cf::WM * Cf::MT * 8 - 1) / (Cf::WM * Cf::MT * 8);
 	PHBC_CHECK(cudaFuncSetAttribute(lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 + (3 * Sh::IMG + ring) * sizeof(double))));
-	const bool split = getenv("PHB_DMMA_NOSPLIT") == NULL;
+	const bool split = true;  // per-kind launches (measured faster than one five-slot variant per level, round 1)
 	for (int kind = 0; kind < 3; kind++) {
 		int beg = ctx->h_lower_kind_off[4 * level + kind], end = ctx->h_lower_kind_off[4 * level + kind + 1];
 		int nimg = 1 + kind;
@@ -1103,7 +1104,7 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 	const int C = ctx->C, P = ctx->P, N = ctx->N;
 	int rc;
 	Bufs b = phbc_make_bufs(ctx);
-	const bool split = getenv("PHB_DMMA_NOSPLIT") == NULL;
+	const bool split = true;  // per-kind launches (measured faster than one five-slot variant per level, round 1)
 	typedef void (*upper_fn)(Bufs, const phbc_parent_op *, const double *, const double *, const double *, const double *, int, int, double *, int);
 	struct Variant {
 		upper_fn fn;
@@ -1177,8 +1178,7 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	if ((rc = phbc_generic_prepare(ctx, o))) return rc;
 	Bufs b = phbc_make_bufs(ctx);
 	// message form: the fast path (unscaled, state tips, eigen system, upper partials not needed as such afterwards)
-	const bool msg = !o->scale && !o->materialize_uppers && ctx->tip_kind == PHBC_TIP_STATES && ctx->have_eigen && !o->explicit_matrices &&
-	                 getenv("PHB_DMMA_LEGACY") == NULL;
+	const bool msg = !o->scale && !o->materialize_uppers && ctx->tip_kind == PHBC_TIP_STATES && ctx->have_eigen && !o->explicit_matrices;
 	if ((rc = dmma_pack<S>(ctx, msg, o->include_root_freqs))) return rc;
 	ctx->lower_is_message = msg;
 	ctx->node_evals++;
@@ -1243,6 +1243,51 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	if ((rc = phbc_time_end(ctx))) return rc;
 	PHBC_CHECK(cudaGetLastError());
 	return 0;
+}
+
+// the packed images k_dmma_pack wrote last, brought back to [N][C][S][S]: what the tensor-core kernels actually stage
+template <int S>
+static int dmma_download(phbc_ctx *ctx, double *P, double *dP) {
+	using Sh = DmmaShape<S>;
+	const int C = ctx->C, N = ctx->N, T = ctx->T;
+	if (!ctx->d_dmma_img) return -4;
+	const size_t n = (size_t)2 * N * C * Sh::IMG;
+	double *img = (double *)malloc(n * sizeof(double)), *f = (double *)malloc(S * sizeof(double));
+	if (!img || !f) {
+		free(img), free(f);
+		return -3;
+	}
+	cudaError_t e = cudaMemcpyAsync(img, ctx->d_dmma_img, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(f, ctx->d_freqs, S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (e == cudaSuccess)
+		for (int which = 0; which < 2; which++) {
+			double *dst = which ? dP : P;
+			if (!dst) continue;
+			for (int nd = 0; nd < N; nd++)
+				for (int c = 0; c < C; c++) {
+					const double *src = img + (((size_t)which * N + nd) * C + c) * Sh::IMG;
+					double *M = dst + ((size_t)nd * C + c) * S * S;
+					const bool tip = nd < T && ctx->tip_kind == PHBC_TIP_STATES, adj = which == 1 && ctx->dmma_pack_adjoint && nd >= T;
+					for (int i = 0; i < S; i++)
+						for (int j = 0; j < S; j++) {
+							if (nd == ctx->root) M[i * S + j] = src[i * Sh::LD + j];
+							else if (tip) M[i * S + j] = src[j * Sh::NP + i];
+							else if (adj) M[i * S + j] = src[j * Sh::LD + i] / (ctx->dmma_pack_irf ? 1.0 : f[i]);
+							else M[i * S + j] = src[i * Sh::LD + j];
+						}
+				}
+		}
+	free(img), free(f);
+	PHBC_CHECK(e);
+	return 0;
+}
+
+int phbc_dmma_download_matrices(phbc_ctx *ctx, double *P, double *dP) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	if (ctx->S == 20) return dmma_download<20>(ctx, P, dP);
+	if (ctx->S == 61) return dmma_download<61>(ctx, P, dP);
+	return -1;
 }
 
 int phbc_dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {

@@ -965,6 +965,7 @@ int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 		const int prc = nuc4_prepare_codes(ctx, &usable);
 		if (prc) return prc;
 	}
+	ctx->last_family = ctx->nuc4_codes_bad ? 1 : 2;
 	if (ctx->nuc4_codes_bad) {  // non 0/1 tip partials: node-at-a-time kernels, one sample at a time
 		phbc_eval_opts one = *o;
 		one.batch_count = 1;
@@ -1224,5 +1225,44 @@ int phbc_nuc4_root_frequency_gradient(phbc_ctx *ctx, double *out_host) {
 		for (int c = 0; c < C; c++) s += (C == 1 ? 1.0 : props[c]) * g[c * 16 + i];
 		out_host[i] = s;
 	}
+	return 0;
+}
+
+// The transition matrices of the last walk (first sample), from the walk-ordered set k_nuc4_matrices wrote: an internal node's matrix
+// is entry 0 of its own post-order op, a tip's is entry 1 / 2 of its parent's op.  dP is what the walk contracts, Q P (see the kernel).
+int phbc_nuc4_download_matrices(phbc_ctx *ctx, double *P, double *dP) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	if (!ctx->d_walk_mats) return -4;
+	const int C = ctx->C, N = ctx->N, np = ctx->n_post;
+	double *mats = (double *)malloc((size_t)3 * np * C * 16 * sizeof(double));
+	phbc_post_op *ops = (phbc_post_op *)malloc((size_t)np * sizeof(phbc_post_op));
+	double *Pl = P ? P : (double *)malloc((size_t)N * C * 16 * sizeof(double));
+	if (!mats || !ops || !Pl) {
+		free(mats), free(ops);
+		if (!P) free(Pl);
+		return -3;
+	}
+	cudaError_t e = cudaMemcpyAsync(mats, ctx->d_walk_mats, (size_t)3 * np * C * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(ops, ctx->d_post_ops, (size_t)np * sizeof(phbc_post_op), cudaMemcpyDeviceToHost, ctx->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (e == cudaSuccess) {
+		memset(Pl, 0, (size_t)N * C * 16 * sizeof(double));
+		for (int k = 0; k < np; k++) {
+			const int node[3] = {ops[k].node, ops[k].a_kind == PHBC_W_TIP ? ops[k].a_node : -1, ops[k].b_kind == PHBC_W_TIP ? ops[k].b_node : -1};
+			for (int w = 0; w < 3; w++)
+				if (node[w] >= 0) memcpy(Pl + (size_t)node[w] * C * 16, mats + ((size_t)3 * k + w) * C * 16, (size_t)C * 16 * sizeof(double));
+		}
+		if (dP)
+			for (int nc = 0; nc < N * C; nc++)
+				for (int i = 0; i < 4; i++)
+					for (int j = 0; j < 4; j++) {
+						double acc = 0.0;
+						for (int k = 0; k < 4; k++) acc += ctx->h_qmat[4 * i + k] * Pl[(size_t)nc * 16 + 4 * k + j];
+						dP[(size_t)nc * 16 + 4 * i + j] = acc;
+					}
+	}
+	free(mats), free(ops);
+	if (!P) free(Pl);
+	PHBC_CHECK(e);
 	return 0;
 }

@@ -146,7 +146,7 @@ extern "C" int phbc_time_forward(phbc_ctx *ctx, int B, const double *ratios, con
 	}
 	const size_t N = ctx->N, T = ctx->T;
 	int rc;
-	ctx->ex_valid = false;  // branch lengths are made on the device from here on
+	ctx->ex_count = 0;  // branch lengths are made on the device from here on
 	if ((rc = tt_grow(ctx, B))) return rc;
 	if (B > ctx->bl_cap || B > ctx->result_cap) {  // batch slots of the likelihood (same growth rule as phbc_upload_branch_lengths)
 		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -58,7 +58,8 @@ struct phb_tlk {
 	int post_first_tips, pre_first_tips;
 	int have_time_tree;
 	int host_exp;  /* exponentials of the transition matrices from the host's libm (PHB_OPT_HOST_EXPONENTIALS; default on for >= 60 states) */
-	double *ex_buf; /* [N][C][S] */
+	double *ex_buf; /* [samples][N][C][S] */
+	size_t ex_cap;
 	int sweep_valid; /* the node-at-a-time buffers hold a full evaluation of the current inputs (phb_tlk_matrix_gradient) */
 
 	/* resident node-at-a-time partials (PHB_OPT_INCREMENTAL): which device buffers hold values of the CURRENT inputs */
@@ -1027,20 +1028,32 @@ static void fill_opts(const phb_tlk *t, phbc_eval_opts *o, int want_gradient, in
  * moves those entries by 1e-9 relative and the gradient of a codon alignment by up to 3e-8, so 1e-10 parity needs the same exp.
  * N * C * S values per evaluation (12,139 at C5), nothing next to the evaluation itself.
  */
+static int wants_host_exp(const phb_tlk *t) { return t->host_exp && t->have_eigen && !t->have_matrices && t->h_eval && t->h_rates; }
+
+/* exp(eval_k * bl[b][n] * rate_c) for nbatch branch-length vectors, [nbatch][N][C][S], to the device */
+static int upload_host_exponentials(phb_tlk *t, const double *bl, int nbatch) {
+	const int N = t->N, C = t->C, S = t->S;
+	const size_t need = (size_t)nbatch * N * C * S;
+	if (need > t->ex_cap) {
+		double *nb = (double *)realloc(t->ex_buf, sizeof(double) * need);
+		if (!nb) return -3;
+		t->ex_buf = nb;
+		t->ex_cap = need;
+	}
+	for (int b = 0; b < nbatch; b++)
+		for (int n = 0; n < N; n++)
+			for (int c = 0; c < C; c++) {
+				const double tt = bl[(size_t)b * N + n] * t->h_rates[c];
+				double *dst = t->ex_buf + (((size_t)b * N + n) * C + c) * S;
+				for (int k = 0; k < S; k++) dst[k] = exp(t->h_eval[k] * tt);
+			}
+	return phbc_upload_exponentials(t->ctx, t->ex_buf, nbatch);
+}
+
 static int upload_bl(phb_tlk *t) {
 	int rc = phbc_upload_branch_lengths(t->ctx, t->bl, 1);
 	if (rc) return rc;
-	if (t->host_exp && t->have_eigen && !t->have_matrices && t->h_eval && t->h_rates) {
-		const int N = t->N, C = t->C, S = t->S;
-		if (!t->ex_buf && !(t->ex_buf = (double *)malloc(sizeof(double) * (size_t)N * C * S))) return -3;
-		for (int n = 0; n < N; n++)
-			for (int c = 0; c < C; c++) {
-				const double tt = t->bl[n] * t->h_rates[c];
-				double *dst = t->ex_buf + ((size_t)n * C + c) * S;
-				for (int k = 0; k < S; k++) dst[k] = exp(t->h_eval[k] * tt);
-			}
-		rc = phbc_upload_exponentials(t->ctx, t->ex_buf);
-	}
+	if (wants_host_exp(t)) rc = upload_host_exponentials(t, t->bl, 1);
 	return rc;
 }
 
@@ -1272,7 +1285,19 @@ int phb_tlk_calculate_branch(phb_tlk *t, int node, int nbl, const double *bl, do
 	if (!out) return fail(PHB_ENOMEM, "out of memory");
 	phbc_eval_opts o;
 	fill_opts_resident(t, &o, 1);
-	rc = phbc_branch_lnl(t->ctx, &o, node, nbl, bl, out);
+	double *ex = NULL;
+	if (wants_host_exp(t)) { /* the candidate lengths get the host's exponentials like every other matrix of this model */
+		ex = (double *)malloc(sizeof(double) * (size_t)nbl * t->C * t->S);
+		if (!ex) {
+			free(out);
+			return fail(PHB_ENOMEM, "out of memory");
+		}
+		for (int k = 0; k < nbl; k++)
+			for (int c = 0; c < t->C; c++)
+				for (int q = 0; q < t->S; q++) ex[((size_t)k * t->C + c) * t->S + q] = exp(t->h_eval[q] * (bl[k] * t->h_rates[c]));
+	}
+	rc = phbc_branch_lnl(t->ctx, &o, node, nbl, bl, ex, out);
+	free(ex);
 	if (!rc)
 		for (int k = 0; k < nbl; k++) {
 			if (lnl) lnl[k] = out[3 * k];
@@ -1563,6 +1588,7 @@ int phb_tlk_gradient_batch(phb_tlk *t, int nbatch, const double *bl, double *lnl
 				return fail(PHB_EINVAL, "calculate_partials: sample %d node %d branch length = %E", b, n, bl[(size_t)b * t->N + n]);
 	for (int attempt = 0; attempt < 2; attempt++) {
 		if ((rc = phbc_upload_branch_lengths(t->ctx, bl, nbatch))) return dev_fail(rc);
+		if (wants_host_exp(t) && (rc = upload_host_exponentials(t, bl, nbatch))) return dev_fail(rc);
 		phbc_eval_opts o;
 		fill_opts(t, &o, grad != NULL, 0);
 		o.batch_count = nbatch; /* the fused 4-state walk takes the whole batch in one launch */
@@ -1773,6 +1799,14 @@ int phb_tlk_gradient_batch_time(phb_tlk *t, int nbatch, const double *ratios, co
 	rc = phbc_time_forward(t->ctx, nbatch, ratios, rates, nrates);
 	if (rc == 1) return fail(PHB_EINVAL, "calculate_partials: a sample has a negative branch length (node older than its parent)");
 	if (rc) return dev_fail(rc);
+	if (wants_host_exp(t)) { /* the chain built the branch lengths on the device: fetch them for the host's exp (>= 60 states only) */
+		double *hbl = (double *)malloc(sizeof(double) * (size_t)nbatch * t->N);
+		if (!hbl) return fail(PHB_ENOMEM, "out of memory");
+		rc = phbc_download_branch_lengths(t->ctx, nbatch, hbl);
+		if (!rc) rc = upload_host_exponentials(t, hbl, nbatch);
+		free(hbl);
+		if (rc) return dev_fail(rc);
+	}
 	for (int attempt = 0; attempt < 2; attempt++) {
 		phbc_eval_opts o;
 		fill_opts(t, &o, want_gradient, 0);
@@ -1806,3 +1840,5 @@ int phb_tlk_kernel_time(phb_tlk *t, double *total_ms, long long *launches) {
 }
 
 long long phb_tlk_launch_count(const phb_tlk *t) { return phbc_launch_count(t->ctx); }
+
+int phb_tlk_last_kernels(const phb_tlk *t) { return phbc_last_family(t->ctx); }

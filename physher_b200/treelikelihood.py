@@ -27,6 +27,7 @@ OPT_TIMING = 6
 OPT_HOST_EXPONENTIALS = 8
 OPT_INCREMENTAL = 7
 KERNELS_AUTO, KERNELS_GENERIC, KERNELS_FUSED = 0, 1, 2
+RAN_GENERIC, RAN_WALK, RAN_TENSOR = 1, 2, 3
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -110,6 +111,7 @@ SYMBOLS = [
     ("phb_patterns_last_error", C.c_char_p, []),
     ("phb_tlk_kernel_time", C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_longlong)]),
     ("phb_tlk_launch_count", C.c_longlong, [C.c_void_p]),
+    ("phb_tlk_last_kernels", C.c_int, [C.c_void_p]),
 ]
 
 
@@ -487,6 +489,10 @@ class SingleTreeLikelihood:
 
     def launch_count(self) -> int:
         return int(self.lib.phb_tlk_launch_count(self.h))
+
+    def last_kernels(self) -> int:
+        """Kernel family of the last evaluation: RAN_GENERIC, RAN_WALK (fused 4-state walk) or RAN_TENSOR (FP64 tensor cores)."""
+        return int(self.lib.phb_tlk_last_kernels(self.h))
 
 
 class TreeLikelihoodGroup:

@@ -127,3 +127,86 @@ def test_tensor_core_full_size_properties(name):
         assert rel_err(sub.calculate(), want["lnl"]) < 1e-11 and off < 1e-6
         print(f"codon gradient vs oracle with the device's exp: {off:.2e}")
     sub.close()
+
+
+def test_c2_one_million_patterns_properties():
+    """GTR+G4, 1000 taxa x 1,000,000 patterns: the configuration the north-star's >= 50 % roofline bar is quoted on.  The fused walk
+    keeps no partials, so the whole job needs ~3.5 GB of device memory (the reference would allocate 512 GB)."""
+    cfg = dict(bench.CONFIGS["c2_1m"])
+    topo, bl, m, rates, props, patterns, weights = bench.make_inputs(cfg, 0)
+    inputs = (topo, bl, m, rates, props)
+    P, N = cfg["patterns"], 2 * cfg["taxa"] - 1
+    rng = np.random.default_rng(21)
+    weights = rng.integers(1, 4, P).astype(np.float64)
+    tlk = _make(cfg, patterns, weights, inputs=inputs)
+    lnl, g = tlk.calculate(), tlk.gradient().copy()
+    assert tlk.last_kernels() == phb.treelikelihood.RAN_WALK
+    assert np.isfinite(lnl) and np.isfinite(g).all() and not tlk.rescaling()
+    plk = tlk.pattern_log_likelihoods()
+    assert rel_err(float(np.dot(weights, plk)), lnl) < 1e-12
+    # additivity over ragged pattern shards; the first (400 patterns) and a middle one (333 patterns) are pinned on the oracle
+    edges = [0, 400, 250_001, 250_334, 777_777, P]
+    acc_l, acc_g = 0.0, np.zeros(N)
+    for k, (b, e) in enumerate(zip(edges, edges[1:])):
+        sub = _make(cfg, np.ascontiguousarray(patterns[:, b:e]), weights[b:e], inputs=inputs)
+        sl, sg = sub.calculate(), sub.gradient().copy()
+        if e - b < 1000:
+            pb = O.Problem(left=topo.left, right=topo.right, parent=topo.parent, root=topo.root, nstate=4, tip_states=np.ascontiguousarray(patterns[:, b:e]),
+                           weights=weights[b:e], freqs=m.freqs, rates=rates, props=props, bl=bl, evec=m.evec, eval=m.eval, ivec=m.ivec)
+            want = O.evaluate(pb)
+            assert rel_err(sl, want["lnl"]) < RTOL and grad_err(sg, want["grad"]) < RTOL
+            assert np.max(np.abs(plk[b:e] - want["pattern_lnl"]) / np.abs(want["pattern_lnl"])) < RTOL
+        acc_l += sl
+        acc_g += sg
+        sub.close()
+    assert rel_err(acc_l, lnl) < 1e-12 and grad_err(acc_g, g) < 1e-11
+    tlk.set_pattern_weights(2.0 * weights)
+    assert tlk.calculate() == 2.0 * lnl and np.array_equal(tlk.gradient(), 2.0 * g)
+    tlk.set_pattern_weights(weights)
+    _fd_check(tlk, bl, g, topo, rng, nbranches=2)
+    tlk.close()
+
+
+def test_c3_full_size_batch():
+    """HKY+G4, 500 taxa x 50,000 patterns x 128 branch-length samples (BASELINE config 3) through phb_tlk_gradient_batch: ONE fused
+    launch for the whole batch; three samples pinned on oracle shards, additivity over pattern shards per sample, and agreement
+    with the single-sample entry point."""
+    cfg = dict(bench.CONFIGS["c3"])
+    topo, bl, m, rates, props, patterns, weights = bench.make_inputs(cfg, 0)
+    inputs = (topo, bl, m, rates, props)
+    P, N, B = cfg["patterns"], 2 * cfg["taxa"] - 1, cfg["batch"]
+    rng = np.random.default_rng(31)
+    weights = rng.integers(1, 4, P).astype(np.float64)
+    bls = bl[None, :] * rng.lognormal(0.0, 0.1, size=(B, N))
+    bls[:, topo.root] = 0.0
+    bls[:, topo.right[topo.root]] = 0.0
+    tlk = _make(cfg, patterns, weights, inputs=inputs)
+    tlk.gradient_batch(bls[:2])  # tip encoding and scratch allocation happen once
+    n0 = tlk.launch_count()
+    lnls, grads = tlk.gradient_batch(bls)
+    assert tlk.launch_count() - n0 == 3, "matrices of all samples, ONE walk over (sample, pattern tile) items, fixed-order finalize"
+    assert tlk.last_kernels() == phb.treelikelihood.RAN_WALK
+    assert np.isfinite(lnls).all() and np.isfinite(grads).all() and not tlk.rescaling()
+    # the single-sample entry point sees the same numbers
+    for k in (5, 127):
+        tlk.set_branch_lengths(bls[k])
+        assert rel_err(tlk.calculate(), lnls[k]) < 1e-12 and grad_err(tlk.gradient(), grads[k]) < 1e-11
+    tlk.close()
+    # pattern shards, three samples at once; the 300-pattern shards are pinned on the oracle
+    pick = [0, 63, 127]
+    edges = [0, 300, 20_000, 20_300, P]
+    acc_l, acc_g = np.zeros(3), np.zeros((3, N))
+    for b, e in zip(edges, edges[1:]):
+        sub = _make(cfg, np.ascontiguousarray(patterns[:, b:e]), weights[b:e], inputs=inputs)
+        sl, sg = sub.gradient_batch(bls[pick])
+        if e - b == 300:
+            for i, k in enumerate(pick):
+                pb = O.Problem(left=topo.left, right=topo.right, parent=topo.parent, root=topo.root, nstate=4, tip_states=np.ascontiguousarray(patterns[:, b:e]),
+                               weights=weights[b:e], freqs=m.freqs, rates=rates, props=props, bl=bls[k], evec=m.evec, eval=m.eval, ivec=m.ivec)
+                want = O.evaluate(pb)
+                assert rel_err(sl[i], want["lnl"]) < RTOL and grad_err(sg[i], want["grad"]) < RTOL
+        acc_l += sl
+        acc_g += sg
+        sub.close()
+    for i, k in enumerate(pick):
+        assert rel_err(acc_l[i], lnls[k]) < 1e-12 and grad_err(acc_g[i], grads[k]) < 1e-11

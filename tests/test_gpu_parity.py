@@ -55,6 +55,58 @@ def test_kat_jc69_fluA(kernels):
     tlk.close()
 
 
+def _jc69_eigen(pi=None):
+    """Q = beta (1 pi^T - I), beta = 1 / (1 - sum pi^2): eigenvalues (0, -beta x 3), V = [1 | e_k - pi_k 1], V^-1 = [pi ; e_k - e_4] -- what
+    integration/physher_glue.c hands over for JC69 and F81 (jc69.c:73-94, f81.c:45-110)."""
+    pi = np.full(4, 0.25) if pi is None else np.asarray(pi, dtype=np.float64)
+    beta = 1.0 / (1.0 - float((pi * pi).sum()))
+    evec, ivec = np.zeros((4, 4)), np.zeros((4, 4))
+    evec[:, 0] = 1.0
+    ivec[0] = pi
+    for k in range(1, 4):
+        evec[:, k] = -pi[k - 1]
+        evec[k - 1, k] += 1.0
+        ivec[k, k - 1], ivec[k, 3] = 1.0, -1.0
+    return evec, np.array([0.0, -beta, -beta, -beta]), ivec
+
+
+def test_kat_jc69_fluA_through_the_fused_walk():
+    """The reference's known answers (tests/test_tree_likelihood.c:28-40) with JC69 given as its closed-form EIGEN system, so that
+    C1 runs on k_nuc4_walk (the fixture's explicit matrices can only reach the node-at-a-time kernels); the kernel family that ran
+    is asserted, and the matrices the walk consumed are the reference's jc69_p_t / jc69_dp_dt values."""
+    pb, z = load_golden("c1_jc69_fluA_tipstates")
+    ref_P, ref_dP = pb.P_override, pb.dP_override
+    pb.evec, pb.eval, pb.ivec = _jc69_eigen()
+    pb.P_override = pb.dP_override = None
+    pb.include_root_freqs = True
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=phb.KERNELS_AUTO)
+    lnl = tlk.calculate()
+    assert tlk.last_kernels() == phb.treelikelihood.RAN_WALK
+    assert abs(lnl - float(z["kat_lnl"])) < 1e-8 and rel_err(lnl, float(z["kat_lnl"])) < RTOL
+    g = tlk.gradient()
+    assert tlk.last_kernels() == phb.treelikelihood.RAN_WALK
+    clock = float((g * z["time_elapsed"]).sum())
+    assert rel_err(clock, float(z["kat_clock_grad"])) < RTOL
+    Pm, dPm = tlk.get_matrices()
+    keep = np.arange(pb.nnodes) != pb.root
+    np.testing.assert_allclose(Pm[keep], ref_P[keep], rtol=0, atol=4e-16)
+    np.testing.assert_allclose(dPm[keep], ref_dP[keep], rtol=0, atol=4e-15)
+    np.testing.assert_allclose(tlk.pattern_log_likelihoods(), z["ref_pattern_lnl"], rtol=1e-10, atol=0)
+    tlk.close()
+
+
+def test_f81_closed_form_eigen_system():
+    """F81 (modeltype JC69 in the reference, f81.c:33): the closed-form eigen system of the glue against f81_p_t's formula."""
+    pi = np.array([0.1, 0.2, 0.3, 0.4])
+    evec, ev, ivec = _jc69_eigen(pi)
+    beta = -ev[1]
+    for t in (1e-4, 0.03, 0.7):
+        Pt = np.abs(evec @ np.diag(np.exp(ev * t)) @ ivec)
+        temp = np.exp(-t * beta)
+        want = np.tile(pi * (1.0 - temp), (4, 1)) + temp * np.eye(4)
+        np.testing.assert_allclose(Pt, want, rtol=0, atol=3e-16)  # both forms cancel at small t: 2e-12 relative on the 1e-5 entries
+
+
 @pytest.mark.parametrize("kernels", KERNELS, ids=KIDS)
 @pytest.mark.parametrize("name", [n for n in golden_names() if "deep_scaled" in n or n.startswith("synth_gtr_g4_tip")])
 def test_rescaling(name, kernels):
@@ -77,18 +129,42 @@ def test_rescaling(name, kernels):
 
 @pytest.mark.parametrize("kernels", KERNELS, ids=KIDS)
 def test_transition_matrices_and_partials(kernels):
+    """A4 + K1-K4 + K8 entry by entry against the reference's own buffers.  phb_tlk_get_matrices hands back what the kernels of the
+    LAST evaluation consumed: the node-at-a-time arrays (k_transition_matrices), or, after a fused evaluation, the walk-ordered
+    set k_nuc4_matrices wrote (dP as the walk contracts it, Q P)."""
     pb, z = load_golden("tiny_gtr_g4")
-    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=phb.KERNELS_GENERIC)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=kernels)
     tlk.gradient()
+    assert tlk.last_kernels() == (phb.treelikelihood.RAN_GENERIC if kernels == phb.KERNELS_GENERIC else phb.treelikelihood.RAN_WALK)
     Pm, dPm = tlk.get_matrices()
     keep = np.arange(pb.nnodes) != pb.root
     np.testing.assert_allclose(Pm[keep], z["ref_matrices"][keep], rtol=0, atol=1e-13)
     np.testing.assert_allclose(dPm[keep], z["ref_dmatrices"][keep], rtol=0, atol=1e-12)
+    # tlk->partials as the reference holds them (the fused walk keeps none: get_partials runs the node-at-a-time kernels)
     for n in range(pb.ntips, pb.nnodes):
         np.testing.assert_allclose(tlk.get_partials(n), z["ref_lower"][n], rtol=1e-10, atol=0)
     for n in range(pb.nnodes):
         if n != pb.root:
             np.testing.assert_allclose(tlk.get_partials(pb.nnodes + n), z["ref_upper"][n], rtol=1e-10, atol=1e-300)
+    tlk.close()
+
+
+@pytest.mark.parametrize("name", ["synth_lg_g4_tipstates", "synth_lg_g4_tippartials", "synth_gy94_tippartials", "synth_hky_g4_tipstates",
+                                  "synth_gtr_g4_tippartials"])
+def test_fast_path_matrix_images_match_reference(name):
+    """k_dmma_pack's packed images (transposed tip images, zero-padded operand images, the pi-weighted transposed adjoint images of
+    the message form) and k_nuc4_matrices' walk-ordered set, unpacked, against the reference's p_t / dp_dt entry by entry."""
+    pb, z = load_golden(name)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=phb.KERNELS_AUTO)
+    tlk.gradient()
+    S = pb.nstate
+    assert tlk.last_kernels() == (phb.treelikelihood.RAN_WALK if S == 4 else phb.treelikelihood.RAN_TENSOR)
+    Pm, dPm = tlk.get_matrices()
+    keep = np.arange(pb.nnodes) != pb.root
+    # 61 states: the exponentials come from the host's libm, so the images carry the reference's values exactly (DESIGN.md 3.2);
+    # the adjoint images are divided by pi again on the way back (one rounding)
+    np.testing.assert_allclose(Pm[keep], z["ref_matrices"][keep], rtol=0, atol=1e-13)
+    np.testing.assert_allclose(dPm[keep], z["ref_dmatrices"][keep], rtol=1e-13, atol=1e-12)
     tlk.close()
 
 
@@ -372,4 +448,98 @@ def test_smallest_trees(shape, kernels):
     tlk.use_rescaling(True)
     assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
     assert grad_err(tlk.gradient(), want["grad"]) < 1e-9
+    tlk.close()
+
+
+def _gy94_problem(T=12, P=160, seed=8100):
+    """GY94 (kappa 2.5, omega 0.3): codons two or three changes apart have transition probabilities of order t^2, t^3 -- the entries
+    a one-ulp difference in an exponential moves by 1e-9 relative."""
+    topo = syn.random_topology(T, seed)
+    m = models.gy94(2.5, 0.3)
+    return O.Problem(left=topo.left, right=topo.right, parent=topo.parent, root=topo.root, nstate=61,
+                     tip_states=syn.random_patterns(T, P, 61, 0.1, seed + 1, unknown_frac=0.01),
+                     weights=np.random.default_rng(seed + 2).integers(1, 4, P).astype(np.float64), freqs=m.freqs, rates=np.ones(1), props=np.ones(1),
+                     bl=syn.random_branch_lengths(topo, seed + 3), evec=m.evec, eval=m.eval, ivec=m.ivec)
+
+
+def test_codon_parity_holds_on_every_entry_point():
+    """1e-10 on codon models needs the exponentials of the host's libm (PHB_OPT_HOST_EXPONENTIALS, default for >= 60 states): the
+    batched, the time-tree and the single-branch entry points take them like the plain evaluation does."""
+    pb = _gy94_problem()
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    want = O.evaluate(pb)
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL and grad_err(tlk.gradient(), want["grad"]) < RTOL
+    assert tlk.last_kernels() == phb.treelikelihood.RAN_TENSOR
+    # phb_tlk_gradient_batch
+    rng = np.random.default_rng(8)
+    bls = pb.bl[None, :] * rng.lognormal(0.0, 0.2, size=(3, pb.nnodes))
+    lnl, grad = tlk.gradient_batch(bls)
+    for b in range(3):
+        q = _gy94_problem()
+        q.bl = bls[b]
+        w = O.evaluate(q)
+        assert rel_err(lnl[b], w["lnl"]) < RTOL and grad_err(grad[b], w["grad"]) < RTOL
+    # phb_tlk_calculate_branch
+    from tests.test_branch import deriv_err
+
+    tlk.set_branch_lengths(pb.bl)
+    for n in (1, pb.ntips + 2):
+        cands = pb.bl[n] * np.array([0.5, 1.0, 1.7])
+        l0, d1, d2 = tlk.calculate_branch(n, cands)
+        assert deriv_err(np.stack([l0, d1, d2], 1), O.branch_derivatives(pb, n, cands)) < RTOL
+    # phb_tlk_gradient_batch_time (branch lengths are built on the device and fetched for the host's exp)
+    T, N = pb.ntips, pb.nnodes
+    tip_heights = rng.uniform(0.0, 0.5, T)
+    ratios = rng.uniform(0.3, 0.9, size=(2, T - 1))
+    ratios[:, -1] = tip_heights.max() + rng.uniform(0.5, 1.0, size=2)
+    rates = np.full((2, 1), 0.05)
+    pb.unrooted = False
+    tlk.set_option(phb.treelikelihood.OPT_UNROOTED, 0)
+    tlk.set_time_tree(tip_heights)
+    lt, lj, gr, gc = tlk.gradient_batch_time(ratios, rates, include_jacobian=True)
+    for b in range(2):
+        w = O.time_evaluate(pb, tip_heights, ratios[b], rates[b], include_jacobian=True)
+        assert rel_err(lt[b], w["lnl"]) < RTOL and grad_err(gr[b], w["grad_ratios"]) < RTOL and grad_err(gc[b], w["grad_rates"]) < RTOL
+    tlk.close()
+
+
+def test_evaluations_invalidate_what_matrix_gradient_left_behind():
+    """matrix_gradient -> gradient -> root_frequency_gradient must not reuse statistics / root partials that the
+    gradient call overwrote or outdated (4 states: fused walk statistics; the walk never writes d_lower)."""
+    pb = _synthetic_problem(14, 300, 4, 4, seed=8200)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    M = np.random.default_rng(3).normal(size=(2, pb.nnodes, pb.ncat, 4, 4))
+    tlk.matrix_gradient(M)
+    first = tlk.root_frequency_gradient()
+    tlk.gradient()  # same inputs: a fused walk WITHOUT statistics takes the place of the one that left them
+    assert grad_err(tlk.root_frequency_gradient(), first) < 1e-12
+    pb.bl = pb.bl * 1.3
+    tlk.set_branch_lengths(pb.bl)
+    tlk.gradient()  # a fused walk without statistics
+    got = tlk.root_frequency_gradient()
+    gen = phb.SingleTreeLikelihood.from_problem(pb, kernels=phb.KERNELS_GENERIC)
+    want = gen.root_frequency_gradient()
+    gen.close()
+    assert grad_err(got, want) < RTOL and grad_err(got, first) > 1e-6
+    tlk.close()
+
+
+def test_incremental_reads_see_the_stale_ancestors_recomputed():
+    """incremental mode, set_branch_length + gradient (fused walk: the resident buffers are not touched), then
+    get_partials / root_frequency_gradient must recompute the dirty ancestors first."""
+    pb = _synthetic_problem(12, 200, 4, 2, seed=8300)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    tlk.set_option(phb.OPT_INCREMENTAL, 1)
+    tlk.update_uppers()
+    node = 3
+    pb.bl[node] *= 2.0
+    tlk.set_branch_length(node, pb.bl[node])
+    want = O.evaluate(pb, partials=True)
+    assert grad_err(tlk.gradient(), want["grad"]) < RTOL
+    gen = phb.SingleTreeLikelihood.from_problem(pb, kernels=phb.KERNELS_GENERIC)
+    anc = int(pb.parent[node])
+    np.testing.assert_allclose(tlk.get_partials(anc), gen.get_partials(anc), rtol=1e-12, atol=0)
+    np.testing.assert_allclose(tlk.get_partials(pb.root), gen.get_partials(pb.root), rtol=1e-12, atol=0)
+    assert grad_err(tlk.root_frequency_gradient(), gen.root_frequency_gradient()) < RTOL
+    gen.close()
     tlk.close()
