@@ -156,6 +156,10 @@ int phb_tlk_matrix_gradient(phb_tlk *tlk, int nsets, const double *M, double *ou
  * held fixed = sum_p w_p R[p,i] / L_p, R the category-integrated root partials; the caller contracts it with d pi / d theta
  * (simplex->gradient, or a unit vector).  Reuses the partials phb_tlk_matrix_gradient left on the device when nothing changed since. */
 int phb_tlk_root_frequency_gradient(phb_tlk *tlk, double *out /* [S] */);
+/* The root term of the invariant-site proportion (gradient_pinv_sitemodel / gradient_pinv_W_sitemodel, treelikelihood.c:2943-3001), per
+ * category: out[c] = d lnL / d prop_c with the conditional likelihoods held fixed = sum_p w_p S_c(p) / L_p, S_c(p) = sum_i pi_i
+ * L_root[c,p,i].  The reference's pinv_grad is out[0] - out[1] (two categories) or out[0] - mean(out[1..]) (invariant + Weibull). */
+int phb_tlk_category_gradient(phb_tlk *tlk, double *out /* [C] */);
 
 /*
  * Single-branch fast path (tlk->use_upper: serial_brent_optimize_tree optimizer.c:111-152, NNI / SPR nniopt.c:301-334,
@@ -173,6 +177,17 @@ int phb_tlk_root_frequency_gradient(phb_tlk *tlk, double *out /* [S] */);
  */
 int phb_tlk_update_uppers(phb_tlk *tlk);
 int phb_tlk_calculate_branch(phb_tlk *tlk, int node, int nbl, const double *bl, double *lnl, double *dlnl, double *d2lnl);
+
+/*
+ * phb_tlk_update_partials == the struct slot tlk->update_partials(tlk, out, p1, m1, p2, m2) (treelikelihood.h:91), for the callers
+ * that drive it themselves: update_upper_partials[2] (treelikelihood.c:2129-2190, i.e. the non-virtual
+ * SingleTreeLikelihood_update_uppers[2]), the tripod optimisation of SPR (spropt.c:1578-1608).  ONE partial update on the resident
+ * device buffers, by index as in the reference: out = (P[m1] x[p1]) o (P[m2] x[p2]); p2 < 0: single child; indices < T tips,
+ * T..N-1 lower partials, N + node upper partials.  Lower partials are made current first and the matrices are rebuilt from the
+ * current branch lengths; `mirror` (may be NULL) receives the result [C][P][S] on the host (what asr.c:60-69 reads from tlk->partials).
+ * Switches PHB_OPT_INCREMENTAL on.
+ */
+int phb_tlk_update_partials(phb_tlk *tlk, int out, int p1, int m1, int p2, int m2, double *mirror);
 
 /* Copy of one partials buffer [C][P][S]: index < N lower partials of that node, >= N upper partials of node
  * index-N (tlk->partials[..][index], treelikelihood.h:62; used by asr.c:60).  Generic kernels only. */

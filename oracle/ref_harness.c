@@ -556,3 +556,74 @@ double refh_d2logP_branch(void *vh, int id) {
 	SingleTreeLikelihood_update_all_nodes(h->tlk);
 	return h->model->d2logP(h->model, node->distance);
 }
+
+/* ---- hooks for the boundary rows of tests/test_glue_dropin.py: JSON factory, direct slots, Model.store / restore ---- */
+
+/* like refh_create, through a caller-supplied factory with the signature of new_TreeLikelihoodModel_from_json (the glue's
+ * phb_physher_new_TreeLikelihoodModel_from_json, which understands "backend" / "device") */
+void *refh_create_with(const char *json_text, Model *(*factory)(json_node *, Hashtable *)) {
+	RefH *h = (RefH *)calloc(1, sizeof(RefH));
+	h->hash = new_Hashtable_string(100);
+	hashtable_set_key_ownership(h->hash, false);
+	hashtable_set_value_ownership(h->hash, false);
+	h->json = create_json_tree(json_text);
+	h->model = factory(h->json->children[0], h->hash);
+	h->tlk = (SingleTreeLikelihood *)h->model->obj;
+	if (Tree_is_time_mode(h->tlk->tree)) Tree_update_heights(h->tlk->tree);
+	return h;
+}
+
+/* the NON-VIRTUAL SingleTreeLikelihood_update_uppers (treelikelihood.c:1530-1538): _calculate_simple + update_upper_partials, both of
+ * which drive the struct slots tlk->update_partials / integrate_partials / node_log_likelihoods themselves */
+double refh_update_uppers(void *vh) {
+	RefH *h = (RefH *)vh;
+	SingleTreeLikelihood_update_all_nodes(h->tlk);
+	h->tlk->m->need_update = true;
+	SingleTreeLikelihood_update_uppers(h->tlk);
+	h->tlk->use_upper = false;
+	return h->tlk->lk;
+}
+
+/* the inner step of asr_marginal (asr.c:60-69): per-pattern log likelihood with node `id` pinned to `state` -- the node's lower
+ * partials are masked IN tlk->partials, pushed through the calculate_per_cat_partials / integrate_partials / node_log_likelihoods
+ * slots, and restored.  Upper partials must be current (refh_update_uppers, or a backend's sync).  out [P]. */
+void refh_pinned_state_pattern_lnl(void *vh, int id, int state, double *out) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	const int S = tlk->m->nstate, P = tlk->sp->count;
+	const size_t n = tlk->partials_size;
+	double *partials = tlk->partials[tlk->current_partials_indexes[id]][id];
+	double *backup = (double *)malloc(sizeof(double) * n);
+	double *spare = (double *)malloc(sizeof(double) * n);
+	double *root = (double *)malloc(sizeof(double) * (size_t)P * S);
+	memcpy(backup, partials, sizeof(double) * n);
+	for (size_t i = 0; i < n; i++)
+		if ((int)(i % S) != state) partials[i] = 0;
+	if (id == Node_id(Tree_root(tlk->tree))) memcpy(spare, partials, sizeof(double) * n);
+	else tlk->calculate_per_cat_partials(tlk, spare, tlk->upper_partial_indexes[id], id, id);
+	if (tlk->sm->integrate) tlk->integrate_partials(tlk, spare, tlk->sm->get_proportions(tlk->sm), root);
+	else memcpy(root, spare, sizeof(double) * (size_t)P * S);
+	tlk->node_log_likelihoods(tlk, root, tlk->get_root_frequencies(tlk), out);
+	memcpy(partials, backup, sizeof(double) * n);
+	free(backup), free(spare), free(root);
+}
+
+/* one call of the update_partials slot, as the tripod optimisation of SPR issues it (spropt.c:1578-1608): the upper partial of
+ * `id` from its parent's upper partial and its sibling's lower partial, after the sibling's length changed */
+void refh_slot_update_upper(void *vh, int id) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	Node *node = Tree_node(tlk->tree, id);
+	Node *parent = Node_parent(node), *sib = Node_sibling(node);
+	const int N = Tree_node_count(tlk->tree);
+	SingleTreeLikelihood_update_Q(tlk, sib);
+	if (Node_isroot(parent)) tlk->update_partials(tlk, id + N, Node_id(sib), Node_id(sib), -1, -1);
+	else tlk->update_partials(tlk, id + N, Node_id(parent) + N, Node_id(parent), Node_id(sib), Node_id(sib));
+}
+
+void refh_set_distance(void *vh, int id, double d) {
+	SingleTreeLikelihood *tlk = ((RefH *)vh)->tlk;
+	Node_set_distance(Tree_node(tlk->tree, id), d);
+}
+
+void refh_store(void *vh) { ((RefH *)vh)->model->store(((RefH *)vh)->model); }
+void refh_restore(void *vh) { ((RefH *)vh)->model->restore(((RefH *)vh)->model); }
+double refh_plain_logP(void *vh) { return ((RefH *)vh)->model->logP(((RefH *)vh)->model); } /* no dirty marking: what a driver calls */

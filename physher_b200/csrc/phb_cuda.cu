@@ -1016,6 +1016,36 @@ __global__ void k_root_freq_gradient(Bufs b, int root, const double *__restrict_
 		partial[(size_t)i * gridDim.x + blockIdx.x] = s;
 	}
 }
+// d lnL / d prop_c at fixed conditional likelihoods: A_c = sum_k w_k S_c(k) / L_k with S_c(k) = sum_i pi_i L_root[c,k,i] and
+// L_k = sum_c prop_c S_c(k) -- the root term of the invariant-site proportion in gradient_pinv_sitemodel / gradient_pinv_W_sitemodel
+// (treelikelihood.c:2943-3001: sum_k w_k sum_i pi_i (R_0 - R_1)[k,i] / L_k = A_0 - A_1).  Numerator and denominator come from the same
+// (possibly rescaled) root partial.  grid (pattern tiles, C); partial [C][tiles]
+__global__ void k_root_cat_gradient(Bufs b, int root, const double *__restrict__ freqs, const double *__restrict__ props,
+                                    const double *__restrict__ weights, double *__restrict__ partial) {
+	__shared__ double red[8];
+	const int S = b.S, cc = blockIdx.y;
+	const int p = blockIdx.x * blockDim.x + threadIdx.x;
+	double v = 0.0;
+	if (p < b.P) {
+		double L = 0.0, Sc = 0.0;
+		for (int c = 0; c < b.C; c++) {
+			const double *x = partial_ptr(b, root, c) + (size_t)p * S;
+			double s = 0.0;
+			for (int j = 0; j < S; j++) s += freqs[j] * x[j];
+			L += (b.C == 1) ? s : s * props[c];
+			if (c == cc) Sc = s;
+		}
+		v = weights[p] * Sc / L;
+	}
+	v = phb_warp_sum(v);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double s = 0.0;
+		for (int w = 0; w < (int)(blockDim.x >> 5); w++) s += red[w];
+		partial[(size_t)cc * gridDim.x + blockIdx.x] = s;
+	}
+}
 __global__ void k_sum_rows(const double *__restrict__ partial, int n, double *__restrict__ out) {
 	__shared__ double red[8];
 	const double *in = partial + (size_t)blockIdx.x * n;
@@ -1049,6 +1079,39 @@ extern "C" int phbc_root_frequency_gradient(phbc_ctx *ctx, double *out_host) {
 	ctx->launches += 2;
 	PHBC_CHECK(cudaGetLastError());
 	PHBC_CHECK(cudaMemcpyAsync(out_host, ctx->d_scratch + S * tiles, S * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+	return 0;
+}
+
+// the same root partial (or the root entry of the fused walk's statistics), per category: out[c] = d lnL / d prop_c
+extern "C" int phbc_root_category_gradient(phbc_ctx *ctx, double *out_host) {
+	PHBC_CHECK(cudaSetDevice(ctx->device));
+	const size_t C = ctx->C, S = ctx->S, P = ctx->P;
+	if (ctx->nuc4_G_valid) {  // G[root][c][i] = sum_k w_k / L_k L_root[c,k,i]
+		double g[8 * 16];
+		PHBC_CHECK(cudaMemcpyAsync(g, ctx->d_nuc4_G + (size_t)ctx->root * C * 16, C * 16 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		for (size_t c = 0; c < C; c++) {
+			double s = 0.0;
+			for (int i = 0; i < 4; i++) s += ctx->h_freqs[i] * g[c * 16 + i];
+			out_host[c] = s;
+		}
+		return 0;
+	}
+	if (!ctx->d_lower) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "lower partials are not resident");
+		return -4;
+	}
+	(void)S;
+	const size_t tiles = (P + 255) / 256;
+	int rc;
+	if ((rc = phbc_ensure_scratch(ctx, (C * tiles + C) * sizeof(double)))) return rc;
+	Bufs b = phbc_make_bufs(ctx);
+	k_root_cat_gradient<<<dim3((unsigned)tiles, (unsigned)C), 256, 0, ctx->stream>>>(b, ctx->root, ctx->d_freqs, ctx->d_props, ctx->d_weights, ctx->d_scratch);
+	k_sum_rows<<<(unsigned)C, 256, 0, ctx->stream>>>(ctx->d_scratch, (int)tiles, ctx->d_scratch + C * tiles);
+	ctx->launches += 2;
+	PHBC_CHECK(cudaGetLastError());
+	PHBC_CHECK(cudaMemcpyAsync(out_host, ctx->d_scratch + C * tiles, C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
 	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
 	return 0;
 }

@@ -152,6 +152,8 @@ int phbc_run_ops(phbc_ctx *ctx, const phbc_eval_opts *o, int nops, const phbc_op
                  int do_root, double *lnl_host);
 /* d lnL / d pi_i at fixed partials from the resident root partial (root term of calculate_dlnl_dQ, treelikelihood.c:2371-2404) */
 int phbc_root_frequency_gradient(phbc_ctx *ctx, double *out /* [S] */);
+/* d lnL / d prop_c at fixed conditional likelihoods, from the same root partial (root term of gradient_pinv_sitemodel, treelikelihood.c:2943-3001) */
+int phbc_root_category_gradient(phbc_ctx *ctx, double *out /* [C] */);
 /* K9 / K10 / A11 over every branch from resident upper and lower partials (results in slot 0; lnL slot untouched) */
 int phbc_resident_gradient(phbc_ctx *ctx, const phbc_eval_opts *o);
 /* single-branch fast path (phb_branch.cu): out [nbl][3] = lnL, d lnL/dt, d2 lnL/dt2 at each candidate length of the branch above node */

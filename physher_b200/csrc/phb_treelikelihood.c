@@ -1310,6 +1310,45 @@ int phb_tlk_calculate_branch(phb_tlk *t, int node, int nbl, const double *bl, do
 }
 
 /*
+ * tlk->update_partials(tlk, out, p1, m1, p2, m2) (treelikelihood.h:91; treelikelihoodX.c:1207 and friends): ONE partial update on the
+ * resident buffers, by index like the reference's slot -- out = (P[m1] x[p1]) o (P[m2] x[p2]), p2 < 0: single child (the upper partial of
+ * a child of the root, treelikelihood.c:2147).  Indices: < T tips, T..N-1 lower partials, N + node upper partials
+ * (tlk->upper_partial_indexes, :2131).  This is what the callers that drive the slot themselves go through -- update_upper_partials[2]
+ * (:2129-2190), the tripod optimisation of SPR (spropt.c:1578-1608), _calculate_partials (:1645-1734) -- once the glue has re-pointed
+ * the slot.  Lower partials are made current first (whatever is dirty is recomputed with the current branch lengths), the
+ * transition matrices are rebuilt from the current lengths, and `mirror` (may be NULL) receives a host copy of the result
+ * [C][P][S], so that reference code reading tlk->partials directly (asr.c:60-69) sees what the device computed.
+ */
+int phb_tlk_update_partials(phb_tlk *t, int out, int p1, int m1, int p2, int m2, double *mirror) {
+	const int N = t->N, T = t->T;
+	if (out < T || out >= 2 * N || p1 < 0 || p1 >= 2 * N || m1 < 0 || m1 >= N || p2 >= 2 * N || (p2 >= 0 && (m2 < 0 || m2 >= N)))
+		return fail(PHB_EINVAL, "update_partials(%d, %d, %d, %d, %d): index out of range", out, p1, m1, p2, m2);
+	if (t->have_matrices) return fail(PHB_ESTATE, "update_partials needs the eigen system: explicit matrices belong to one set of branch lengths");
+	if (!t->incremental) {
+		t->incremental = 1;
+		t->resident = 0;
+	}
+	double cur;
+	int rc = resident_calculate(t, &cur);
+	if (rc) return rc;
+	if (isnan(cur) || isinf(cur)) return fail(PHB_ESTATE, "update_partials: lnL = %f", cur);
+	phbc_op op;
+	op.out = out, op.a = p1, op.a_mat = m1, op.b = p2 < 0 ? -1 : p2, op.b_mat = p2 < 0 ? -1 : m2, op.flags = 0;
+	const int off[2] = {0, 1};
+	phbc_eval_opts o;
+	fill_opts_resident(t, &o, out >= N);
+	o.include_root_freqs = 0;
+	if ((rc = phbc_run_ops(t->ctx, &o, 1, &op, 1, off, 1, 0, NULL))) return dev_fail(rc);
+	if (out >= N) {
+		if (t->upper_irf != 0) memset(t->upper_ok, 0, N);
+		t->upper_irf = 0;
+		t->upper_ok[out - N] = 1;
+	}
+	if (mirror && (rc = phbc_download_partials(t->ctx, out, mirror))) return dev_fail(rc);
+	return PHB_OK;
+}
+
+/*
  * Gradient while partials are resident.  A gradient over ALL branches is a whole-tree job whatever changed (one changed branch
  * invalidates every upper partial outside its root path), and the fused kernels do the whole tree faster than the node-at-a-time
  * kernels can patch it (C2: 6.4 ms fused against 46 ms patched, round 1 h6) -- so the evaluation runs on the fast path.  The fused
@@ -1644,9 +1683,8 @@ int phb_tlk_matrix_gradient(phb_tlk *t, int nsets, const double *M, double *out)
 	return PHB_OK;
 }
 
-/* root term of the frequency parameters in calculate_dlnl_dQ (treelikelihood.c:2371-2404): out[i] = d lnL / d pi_i at fixed partials */
-int phb_tlk_root_frequency_gradient(phb_tlk *t, double *out) {
-	if (!out) return fail(PHB_EINVAL, "out is required");
+/* makes the root's lower partial (or the fused walk's root statistics) current on the device; *ok = 0 when lnL is NaN / inf */
+static int ensure_root_partial(phb_tlk *t, int *ok) {
 	int rc = check_ready(t);
 	if (rc) return rc;
 	if (t->incremental && t->resident && !t->all_dirty && (t->update || t->lower_stale)) {
@@ -1654,6 +1692,7 @@ int phb_tlk_root_frequency_gradient(phb_tlk *t, double *out) {
 		if ((rc = resident_calculate(t, &cur))) return rc;
 	}
 	const int resident_ok = t->incremental && t->resident && !t->all_dirty && !t->update && !t->lower_stale;
+	*ok = 1;
 	if (!resident_ok && (t->update || !t->sweep_valid)) { /* a node-at-a-time evaluation leaves the root partial on the device */
 		if ((rc = upload_bl(t))) return dev_fail(rc);
 		t->bl_dirty = 0;
@@ -1671,12 +1710,36 @@ int phb_tlk_root_frequency_gradient(phb_tlk *t, double *out) {
 		}
 		t->update = isnan(t->lk) ? 1 : 0;
 		t->sweep_valid = !(isnan(t->lk) || isinf(t->lk));
-		if (!t->sweep_valid) {
-			for (int i = 0; i < t->S; i++) out[i] = NAN;
-			return PHB_OK;
-		}
+		*ok = t->sweep_valid;
+	}
+	return PHB_OK;
+}
+
+/* root term of the frequency parameters in calculate_dlnl_dQ (treelikelihood.c:2371-2404): out[i] = d lnL / d pi_i at fixed partials */
+int phb_tlk_root_frequency_gradient(phb_tlk *t, double *out) {
+	if (!out) return fail(PHB_EINVAL, "out is required");
+	int ok = 0, rc = ensure_root_partial(t, &ok);
+	if (rc) return rc;
+	if (!ok) {
+		for (int i = 0; i < t->S; i++) out[i] = NAN;
+		return PHB_OK;
 	}
 	if ((rc = phbc_root_frequency_gradient(t->ctx, out))) return dev_fail(rc);
+	return PHB_OK;
+}
+
+/* d lnL / d prop_c at fixed conditional likelihoods: out[c] = sum_k w_k S_c(k) / L_k, S_c(k) the category's site likelihood.  The root
+ * term of the invariant-site proportion (gradient_pinv_sitemodel / gradient_pinv_W_sitemodel, treelikelihood.c:2943-3001) is
+ * out[0] - out[1], respectively out[0] - mean(out[1..]) */
+int phb_tlk_category_gradient(phb_tlk *t, double *out) {
+	if (!out) return fail(PHB_EINVAL, "out is required");
+	int ok = 0, rc = ensure_root_partial(t, &ok);
+	if (rc) return rc;
+	if (!ok) {
+		for (int c = 0; c < t->C; c++) out[c] = NAN;
+		return PHB_OK;
+	}
+	if ((rc = phbc_root_category_gradient(t->ctx, out))) return dev_fail(rc);
 	return PHB_OK;
 }
 

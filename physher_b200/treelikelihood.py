@@ -66,8 +66,10 @@ SYMBOLS = [
     ("phb_tlk_cat_branch_gradient", C.c_int, [C.c_void_p, _dp]),
     ("phb_tlk_matrix_gradient", C.c_int, [C.c_void_p, C.c_int, _dp, _dp]),
     ("phb_tlk_root_frequency_gradient", C.c_int, [C.c_void_p, _dp]),
+    ("phb_tlk_category_gradient", C.c_int, [C.c_void_p, _dp]),
     ("phb_tlk_update_uppers", C.c_int, [C.c_void_p]),
     ("phb_tlk_calculate_branch", C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _dp, _dp, _dp]),
+    ("phb_tlk_update_partials", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _dp]),
     ("phb_tlk_get_partials", C.c_int, [C.c_void_p, C.c_int, _dp]),
     ("phb_tlk_get_matrices", C.c_int, [C.c_void_p, _dp, _dp]),
     ("phb_tlk_gradient_device", C.c_int, [C.c_void_p, C.c_void_p]),
@@ -403,6 +405,12 @@ class SingleTreeLikelihood:
         self._check(self.lib.phb_tlk_root_frequency_gradient(self.h, out.ctypes.data_as(_dp)))
         return out
 
+    def category_gradient(self):
+        """d lnL / d prop_c at fixed conditional likelihoods (root term of gradient_pinv_sitemodel, treelikelihood.c:2943-3001)."""
+        out = np.zeros(self.C)
+        self._check(self.lib.phb_tlk_category_gradient(self.h, out.ctypes.data_as(_dp)))
+        return out
+
     def update_uppers(self):
         """SingleTreeLikelihood_update_uppers (treelikelihood.c:1530-1538): lnL, then every upper partial, kept on the device."""
         self._check(self.lib.phb_tlk_update_uppers(self.h))
@@ -415,6 +423,12 @@ class SingleTreeLikelihood:
         self._check(self.lib.phb_tlk_calculate_branch(self.h, int(node), int(a.size), a.ctypes.data_as(_dp), lnl.ctypes.data_as(_dp),
                                                       d1.ctypes.data_as(_dp), d2.ctypes.data_as(_dp)))
         return lnl, d1, d2
+
+    def update_partials(self, out, p1, m1, p2=-1, m2=-1, mirror=True):
+        """tlk->update_partials(tlk, out, p1, m1, p2, m2) (treelikelihood.h:91) on the resident device buffers; returns the result."""
+        buf = np.zeros((self.C, self.P, self.S)) if mirror else None
+        self._check(self.lib.phb_tlk_update_partials(self.h, int(out), int(p1), int(m1), int(p2), int(m2), buf.ctypes.data_as(_dp) if mirror else None))
+        return buf
 
     def get_partials(self, index):
         out = np.zeros((self.C, self.P, self.S))

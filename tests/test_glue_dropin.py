@@ -264,3 +264,215 @@ def test_model_clone_gets_its_own_device_object(libs):
     assert rel_err(base, L.refh_logP(twin2)) < RTOL
     L.refh_free(twin2)
     ref2.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# round 2: the rest of SURVEY.md 8b -- JSON factory with "backend", C1 on the fused walk, the struct slots callers drive themselves,
+# Model.store / restore, invariant-site / mu gradients, finite-difference substitution routes, use_upper on a time tree
+# ---------------------------------------------------------------------------------------------------------------------------------
+
+def _bind_round2(L, G):
+    import physher_b200 as phb
+
+    lib = phb.load_library()
+    L.refh_create_with.argtypes = [C.c_char_p, C.c_void_p]
+    L.refh_create_with.restype = C.c_void_p
+    L.refh_update_uppers.argtypes = [C.c_void_p]
+    L.refh_update_uppers.restype = C.c_double
+    L.refh_pinned_state_pattern_lnl.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_double)]
+    L.refh_slot_update_upper.argtypes = [C.c_void_p, C.c_int]
+    L.refh_set_distance.argtypes = [C.c_void_p, C.c_int, C.c_double]
+    L.refh_store.argtypes = [C.c_void_p]
+    L.refh_restore.argtypes = [C.c_void_p]
+    L.refh_plain_logP.argtypes = [C.c_void_p]
+    L.refh_plain_logP.restype = C.c_double
+    G.phb_physher_handle.argtypes = [C.c_void_p]
+    G.phb_physher_handle.restype = C.c_void_p
+    G.phb_physher_sync_partials_to_host.argtypes = [C.c_void_p]
+    return lib
+
+
+def _gtr_spec(T=11, sites=400, seed=161, tipstates=True, categories=4, model=None, sitemodel_extra=None):
+    from physher_b200 import synthetic as syn
+
+    topo = syn.random_topology(T, seed)
+    bl = syn.random_branch_lengths(topo, seed + 1)
+    pat = syn.random_patterns(T, sites, 4, 0.3, seed + 2, unknown_frac=0.02)
+    names = [f"t{i}" for i in range(T)]
+    seqs = dict(zip(names, syn.sequences_from_patterns(pat, syn.NUCLEOTIDES)))
+    model = model or O.nucleotide_model_spec("gtr", [0.1, 0.2, 0.3, 0.4], [0.05, 0.3, 0.1, 0.15, 0.3, 0.1])
+    spec = O.treelikelihood_spec(syn.to_newick(topo, bl, names), seqs, model, categories=categories, alpha=0.5, tipstates=tipstates)
+    if sitemodel_extra:
+        spec["sitemodel"].update(sitemodel_extra)
+    return spec, topo
+
+
+def test_json_backend_key_and_c1_on_the_fused_walk(libs):
+    """`"backend": "b200"` on the reference's own "treelikelihood" JSON object (treelikelihood.c:819-943): the glue's factory strips
+    the key, runs the reference's constructor and attaches.  C1 (JC69, closed-form p_t in the reference) reaches the fused 4-state
+    walk through the closed-form eigen system, and reproduces the known answers of tests/test_tree_likelihood.c:28-84."""
+    L, G = libs
+    lib = _bind_round2(L, G)
+    kat = json.load(open(os.path.join(GOLDEN, "c1_kat.json")))
+    spec = dict(_spec(), backend="b200", device=0)
+    factory = C.cast(G.phb_physher_new_TreeLikelihoodModel_from_json, C.c_void_p)
+    h = L.refh_create_with(json.dumps({"model": spec}).encode(), factory)
+    assert h
+    model = L.refh_model_handle(h)
+    assert G.phb_physher_evaluations(model) == 0, "the factory attached the device backend"
+    L.refh_set_include_jacobian(h, 0)
+    lnl = L.refh_logP(h)
+    assert G.phb_physher_evaluations(model) == 1
+    assert abs(lnl - kat["logP"]) < 1e-8 and rel_err(lnl, kat["logP"]) < RTOL
+    assert lib.phb_tlk_last_kernels(G.phb_physher_handle(model)) == 2, "C1 must run on k_nuc4_walk, not on the node-at-a-time kernels"
+    out = np.zeros(80)
+    n = L.refh_kat_dlogP(h, out.ctypes.data_as(C.POINTER(C.c_double)), 80)
+    want = np.array([kat["rate_grad"]] + kat["ratio_grad"] + [kat["root_height_grad"]])
+    assert n == 69 and grad_err(out[:n], want) < RTOL
+    assert lib.phb_tlk_last_kernels(G.phb_physher_handle(model)) == 2
+    # without the key the same factory leaves the reference's CPU path in place
+    h2 = L.refh_create_with(json.dumps({"model": _spec()}).encode(), factory)
+    assert G.phb_physher_evaluations(L.refh_model_handle(h2)) == -1
+    L.refh_set_include_jacobian(h2, 0)
+    assert abs(L.refh_logP(h2) - kat["logP"]) < 1e-8
+    G.phb_physher_detach(model)
+
+
+@pytest.mark.parametrize("tipstates", [True, False])
+def test_direct_struct_slots_run_on_the_device(libs, tipstates):
+    """tlk->update_partials / integrate_partials / node_log_likelihoods / calculate_per_cat_partials (treelikelihood.h:90-94,111) as
+    the reference's own non-virtual code drives them: SingleTreeLikelihood_update_uppers (_calculate_simple + update_upper_partials),
+    the masked-state evaluation of asr_marginal (asr.c:60-69) and one tripod-style upper update of SPR (spropt.c:1578-1608).
+    Same calls on the CPU reference and on an attached model; tlk->partials on the host must mirror what the device computed."""
+    L, G = libs
+    _bind_round2(L, G)
+    spec, topo = _gtr_spec(tipstates=tipstates)
+    dp = C.POINTER(C.c_double)
+
+    def run(ref):
+        out = {"lnl": L.refh_update_uppers(ref.h)}
+        N, T = ref.N, ref.T
+        out["lower"] = {n: ref.partials(n) for n in range(T, N)}
+        out["upper"] = {n: ref.partials(N + n) for n in range(N) if n != ref.root}
+        pinned = np.zeros((2, 4, ref.P))
+        for i, node in enumerate((T + 1, ref.root)):
+            for s in range(4):
+                L.refh_pinned_state_pattern_lnl(ref.h, node, s, pinned[i, s].ctypes.data_as(dp))
+        out["pinned"] = pinned
+        # SPR tripod step: the sibling's length changes, the caller refreshes one upper partial through the slot
+        node = 2
+        sib = int(topo.right[topo.parent[node]]) if int(topo.left[topo.parent[node]]) == node else int(topo.left[topo.parent[node]])
+        L.refh_set_distance(ref.h, sib, 0.123)
+        L.refh_slot_update_upper(ref.h, node)
+        out["tripod_upper"] = ref.partials(N + node)
+        return out
+
+    cpu = O.Reference(spec)
+    want = run(cpu)
+    cpu.close()
+    dev = O.Reference(spec)
+    model = L.refh_model_handle(dev.h)
+    assert G.phb_physher_attach(model, 0) == 0
+    got = run(dev)
+    assert G.phb_physher_evaluations(model) > 0
+    assert rel_err(got["lnl"], want["lnl"]) < RTOL
+    for key in ("lower", "upper"):
+        for n in want[key]:
+            np.testing.assert_allclose(got[key][n], want[key][n], rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(got["pinned"], want["pinned"], rtol=1e-10, atol=0)
+    np.testing.assert_allclose(got["tripod_upper"], want["tripod_upper"], rtol=1e-10, atol=1e-300)
+    G.phb_physher_detach(model)
+    dev.close()
+
+
+def test_model_store_restore_through_the_glue(libs):
+    """Model.store / Model.restore of an attached tree likelihood (_singleTreeLikelihood_store / _restore, treelikelihood.c:126-161):
+    an MCMC reject returns to the stored lnL; the device object is not asked to recompute it."""
+    L, G = libs
+    _bind_round2(L, G)
+    spec, topo = _gtr_spec(seed=261)
+    cpu = O.Reference(spec)
+    base = cpu.logP()
+    cpu.close()
+    dev = O.Reference(spec)
+    model = L.refh_model_handle(dev.h)
+    assert G.phb_physher_attach(model, 0) == 0
+    assert rel_err(L.refh_plain_logP(dev.h), base) < RTOL
+    L.refh_store(dev.h)
+    L.refh_set_distance(dev.h, 3, 0.31)  # a proposal
+    moved = L.refh_plain_logP(dev.h)
+    assert abs(moved - base) > 1e-3
+    evals = G.phb_physher_evaluations(model)
+    L.refh_restore(dev.h)  # reject
+    assert L.refh_plain_logP(dev.h) == pytest.approx(base, rel=1e-12)
+    assert G.phb_physher_evaluations(model) == evals, "a rejected proposal must not cost a device evaluation"
+    # accept path: store after the move, the moved value is what a later restore returns to
+    L.refh_set_distance(dev.h, 3, 0.31)
+    assert rel_err(L.refh_plain_logP(dev.h), moved) < 1e-12
+    L.refh_store(dev.h)
+    L.refh_set_distance(dev.h, 5, 0.2)
+    L.refh_plain_logP(dev.h)
+    L.refh_restore(dev.h)
+    assert rel_err(L.refh_plain_logP(dev.h), moved) < 1e-12
+    G.phb_physher_detach(model)
+    dev.close()
+
+
+@pytest.mark.parametrize("case", ["pinv", "pinv_gamma", "mu"])
+def test_site_model_gradients_with_invariant_sites_and_mu(libs, case):
+    """TREELIKELIHOOD_FLAG_SITE_MODEL with an invariant-site proportion (gradient_pinv_sitemodel / gradient_pinv_W_sitemodel,
+    treelikelihood.c:2943-3001: they read the root partials) and with a mutation-rate multiplier mu (:3245-3249, :3283-3296)."""
+    L, G = libs
+    _bind_round2(L, G)
+    simplex = {"id": "props", "type": "Simplex", "values": [0.2, 0.8]}
+    if case == "pinv":  # +I alone: an invariant category and one variable category (sitemodel.c:1182-1197)
+        spec, topo = _gtr_spec(seed=361, categories=1)
+        spec["sitemodel"]["distribution"] = {"distribution": "discrete", "categories": 1, "proportions": simplex}
+    elif case == "pinv_gamma":  # Weibull + I: five categories, the shape and the invariant proportion both carry a gradient
+        spec, topo = _gtr_spec(seed=361, categories=4)
+        spec["sitemodel"]["distribution"] = {"distribution": "weibull", "categories": 4, "proportions": simplex,
+                                             "parameters": {"shape": {"id": "alpha", "type": "parameter", "value": 0.5, "lower": 0}}}
+    else:
+        spec, topo = _gtr_spec(seed=361, categories=4)
+        spec["sitemodel"]["mu"] = {"id": "mu", "type": "parameter", "value": 1.7, "lower": 0}
+    cpu = O.Reference(spec)
+    flags = O.FLAG_TREE_MODEL | O.FLAG_SITE_MODEL
+    want = cpu.gradient(flags, include_root_freqs=0)
+    lnl_cpu = cpu.logP()
+    cpu.close()
+    dev = O.Reference(spec)
+    model = L.refh_model_handle(dev.h)
+    assert G.phb_physher_attach(model, 0) == 0
+    assert rel_err(dev.logP(), lnl_cpu) < RTOL
+    n = L.refh_initialize_gradient(dev.h, flags, 0)
+    assert n == want.size and n > dev.N, "the request carries site-model entries"
+    L.refh_mark_dirty(dev.h)
+    g = np.ctypeslib.as_array(G.phb_physher_gradient(model), shape=(n,)).copy()
+    assert grad_err(g[:dev.N], want[:dev.N]) < RTOL
+    for k in range(dev.N, n):
+        assert rel_err(g[k], want[k]) < 1e-9, (case, k, g[k], want[k])
+    G.phb_physher_detach(model)
+    dev.close()
+
+
+def test_use_upper_on_a_time_tree_stays_on_the_device(libs):
+    """tlk->use_upper on the JC69 time tree (r1: exit(2)): a changed clock rate or node height moves several branch lengths, the glue
+    pushes them all and lnL comes from the device's resident partials."""
+    L, G = libs
+    _bind_round2(L, G)
+    cpu = O.Reference(_spec())
+    cpu.set_include_jacobian(False)
+    cpu.set_clock_rate(0.003)
+    want = cpu.logP()
+    cpu.close()
+    dev = O.Reference(_spec())
+    dev.set_include_jacobian(False)
+    model = L.refh_model_handle(dev.h)
+    assert G.phb_physher_attach(model, 0) == 0
+    G.phb_physher_update_uppers(model)  # switches use_upper on, partials resident
+    evals = G.phb_physher_evaluations(model)
+    dev.set_clock_rate(0.003)
+    got = L.refh_plain_logP(dev.h)
+    assert rel_err(got, want) < RTOL and G.phb_physher_evaluations(model) > evals
+    G.phb_physher_detach(model)
+    dev.close()
