@@ -276,7 +276,12 @@ def _reference_worker(args):
         nodes = ref.N
         values = None
         if want_values:  # the parity gate of our arm: lnL and branch gradients of this shard from the reference itself
-            values = (ref.logP(), ref.gradient(O.FLAG_TREE_MODEL, 0)[:nodes].copy(), bool(ref.rescaling()))
+            # ... on the inputs as the REFERENCE holds them after its own parsing (it clamps a zero branch length to its lower
+            # bound 1e-8 and moves it to the sibling; its eigen system and Gamma quantiles come from its own eigen.c / gamma.c)
+            pb = ref.problem()
+            values = dict(lnl=ref.logP(), grad=ref.gradient(O.FLAG_TREE_MODEL, 0)[:nodes].copy(), rescaled=bool(ref.rescaling()),
+                          left=pb.left, right=pb.right, root=int(pb.root), tip_states=pb.tip_states, weights=pb.weights, freqs=pb.freqs,
+                          rates=pb.rates, props=pb.props, bl=pb.bl, evec=pb.evec, eval=pb.eval, ivec=pb.ivec)
     finally:
         os.dup2(saved, 1)
         os.close(devnull)
@@ -438,10 +443,22 @@ def parity_gate(run, cfg, kernels, cores, sample_patterns, iters):
             "sample": f"{cores} single-threaded reference process(es) x {r['per']} patterns each, {iters} lnL+gradient evaluations each "
                       f"({cfg['model']}, {T} taxa, tip partials, SSE on), {r['wall']:.1f} s wall",
             "one_core_value": float(np.mean([p * r['nodes'] / s for s, p in zip(r['sec_per_eval'], r['patterns'])]))}
-    ref_lnl, ref_grad, ref_scaled = r["values"]
-    sub = dict(cfg, patterns=r["per"])
-    topo, bl, m, rates, props, patterns, weights = make_inputs(sub, rank=1000)  # worker 0's shard, same generator and seed
-    tlk = build_tlk(run, sub, topo, m, rates, props, patterns, weights, kernels)
+    v = r["values"]
+    ref_lnl, ref_grad, ref_scaled = v["lnl"], v["grad"], v["rescaled"]
+    phb = run.phb
+    from physher_b200.treelikelihood import OPT_KERNELS
+
+    S, C = cfg["states"], cfg["cats"]
+    patterns = np.ascontiguousarray(v["tip_states"], dtype=np.uint8)
+    root, right = v["root"], v["right"]
+    tlk = phb.SingleTreeLikelihood(v["left"], v["right"], root, S, C, patterns.shape[1], use_tip_states=True, device=run.local_rank)
+    tlk.set_tip_states(patterns)
+    tlk.set_pattern_weights(v["weights"])
+    tlk.set_eigen(v["evec"], v["eval"], v["ivec"])
+    tlk.set_frequencies(v["freqs"])
+    tlk.set_site_model(v["rates"], v["props"])
+    tlk.set_option(OPT_KERNELS, {"auto": phb.KERNELS_AUTO, "generic": phb.KERNELS_GENERIC, "fused": phb.KERNELS_FUSED}[kernels])
+    bl = np.asarray(v["bl"], dtype=np.float64)
     tlk.set_branch_lengths(bl)
     B = int(cfg.get("batch", 1))
     if B > 1:  # the batched entry point: sample 0 carries the reference's branch lengths
@@ -451,14 +468,16 @@ def parity_gate(run, cfg, kernels, cores, sample_patterns, iters):
     else:
         g = tlk.gradient()
         lnl = tlk.calculate()
+    family = {1: "generic", 2: "fused 4-state walk", 3: "FP64 tensor cores"}.get(tlk.last_kernels(), "?")
     tlk.close()
     g = g.copy()
     ref_grad = ref_grad.copy()
-    ref_grad[topo.root] = ref_grad[topo.right[topo.root]] = 0.0
+    ref_grad[root] = ref_grad[right[root]] = 0.0
     le = abs(lnl - ref_lnl) / abs(ref_lnl)
     ge = grad_err(g, ref_grad)
     par = {"ok": bool(le < PARITY_RTOL and ge < PARITY_RTOL), "lnl_rel_err": le, "grad_err": ge, "rtol": PARITY_RTOL, "patterns": int(patterns.shape[1]),
-           "against": "unmodified reference (oracle/_ref), TREE_MODEL gradient, include_root_freqs = false", "reference_rescaled": ref_scaled}
+           "against": "unmodified reference (oracle/_ref), TREE_MODEL gradient, include_root_freqs = false, on the inputs as the reference holds them",
+           "reference_rescaled": ref_scaled, "kernels": family}
     return base, par
 
 

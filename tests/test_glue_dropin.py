@@ -387,34 +387,37 @@ def test_direct_struct_slots_run_on_the_device(libs, tipstates):
 
 def test_model_store_restore_through_the_glue(libs):
     """Model.store / Model.restore of an attached tree likelihood (_singleTreeLikelihood_store / _restore, treelikelihood.c:126-161):
-    an MCMC reject returns to the stored lnL; the device object is not asked to recompute it."""
+    an MCMC reject returns to the stored lnL; the device object is not asked to recompute it.  On the JC69 time tree: the reference's
+    own tree-model store dereferences the tree transform (tree.c:1017-1027), so only reparameterised trees can be stored at all."""
     L, G = libs
     _bind_round2(L, G)
-    spec, topo = _gtr_spec(seed=261)
-    cpu = O.Reference(spec)
-    base = cpu.logP()
-    cpu.close()
-    dev = O.Reference(spec)
+    kat = json.load(open(os.path.join(GOLDEN, "c1_kat.json")))
+    dev = O.Reference(_spec())
+    dev.set_include_jacobian(False)
     model = L.refh_model_handle(dev.h)
     assert G.phb_physher_attach(model, 0) == 0
-    assert rel_err(L.refh_plain_logP(dev.h), base) < RTOL
+    base = L.refh_plain_logP(dev.h)
+    assert rel_err(base, kat["logP"]) < RTOL
     L.refh_store(dev.h)
-    L.refh_set_distance(dev.h, 3, 0.31)  # a proposal
+    dev.set_clock_rate(0.003)  # a proposal
     moved = L.refh_plain_logP(dev.h)
     assert abs(moved - base) > 1e-3
     evals = G.phb_physher_evaluations(model)
     L.refh_restore(dev.h)  # reject
-    assert L.refh_plain_logP(dev.h) == pytest.approx(base, rel=1e-12)
+    assert L.refh_plain_logP(dev.h) == pytest.approx(base, rel=1e-13)
     assert G.phb_physher_evaluations(model) == evals, "a rejected proposal must not cost a device evaluation"
-    # accept path: store after the move, the moved value is what a later restore returns to
-    L.refh_set_distance(dev.h, 3, 0.31)
+    # accept: store after the move; the moved value is what a later reject returns to
+    dev.set_clock_rate(0.003)
     assert rel_err(L.refh_plain_logP(dev.h), moved) < 1e-12
     L.refh_store(dev.h)
-    L.refh_set_distance(dev.h, 5, 0.2)
-    L.refh_plain_logP(dev.h)
+    dev.set_clock_rate(0.0007)
+    assert abs(L.refh_plain_logP(dev.h) - moved) > 1e-3
     L.refh_restore(dev.h)
     assert rel_err(L.refh_plain_logP(dev.h), moved) < 1e-12
+    # the reference's own CPU path agrees on the value the chain returned to
     G.phb_physher_detach(model)
+    dev.set_clock_rate(0.003)
+    assert rel_err(dev.logP(), moved) < RTOL
     dev.close()
 
 
