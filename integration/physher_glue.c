@@ -404,6 +404,13 @@ double *phb_physher_gradient(Model *self) {
 			return tlk->gradient;
 		}
 		memcpy(b->branch_gradient, g, sizeof(double) * b->N);
+		if (tlk->sm->mu != NULL) {
+			/* the reference collapses the categories with sm->cat_rates, which do NOT carry mu (gradient_branch_length_from_cat_inplace,
+			 * :3129-3143, against sm->get_rate, sitemodel.c:544-549): what it calls the branch gradient is d lnL / d (mu bl) -- the tree,
+			 * clock and mu blocks below are all built from that array, so a drop-in hands over the same thing */
+			const double mu = Parameter_value(tlk->sm->mu);
+			for (int i = 0; i < b->N; i++) b->branch_gradient[i] /= mu;
+		}
 		/* from here on the reference's own host code (TreeLikelihood_calculate_gradient, :3268-3309) */
 		size_t offset = 0;
 		if (flags & (TREELIKELIHOOD_FLAG_TREE_MODEL)) {

@@ -79,7 +79,13 @@ phb_group *phb_group_create(int nshards, const int *devices, int ntips, int nsta
 			return NULL;
 		}
 	}
-	if (nshards > 1 && phb_nccl_version() > 0) phb_group_set_reduction(g, PHB_GROUP_REDUCE_NCCL); /* stays on the host sum when NCCL cannot serve the list */
+	{ /* NCCL when the shards sit on distinct devices and the library is loadable (bound only then); else the host sum */
+		int distinct = nshards > 1;
+		for (int a = 0; a < nshards && distinct; a++)
+			for (int b = a + 1; b < nshards; b++)
+				if (devices[a] == devices[b]) distinct = 0;
+		if (distinct && phb_nccl_version() > 0) phb_group_set_reduction(g, PHB_GROUP_REDUCE_NCCL);
+	}
 	return g;
 }
 

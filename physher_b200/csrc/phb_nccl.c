@@ -48,7 +48,7 @@ static int nccl_load(void) {
 	nccl.tried = 1;
 	const char *names[] = {"libnccl.so.2", "libnccl.so"};
 	void *h = NULL;
-	for (int i = 0; i < 2 && !h; i++) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+	for (int i = 0; i < 2 && !h; i++) h = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
 	if (!h) return phb_internal_fail(PHB_ESTATE, "NCCL is not loadable (libnccl.so.2): multi-GPU collectives are unavailable");
 #define BIND(field, sym)                                                                   \
 	do {                                                                                   \

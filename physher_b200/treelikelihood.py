@@ -180,8 +180,34 @@ NCCL_ID_BYTES = 128
 GROUP_REDUCE_HOST, GROUP_REDUCE_NCCL = 0, 1
 
 
+_nccl_preloaded = False
+
+
+def _preload_nccl():
+    """The C layer binds NCCL at run time by soname (dlopen "libnccl.so.2").  A Python process that also imports torch must end up with
+    ONE NCCL: torch's wheels bring their own copy (nvidia/nccl/lib/libnccl.so.2, newer than a system package and linked against by
+    libtorch_cuda), so that copy is loaded first when it exists -- the dynamic linker then resolves the soname to it for the C layer
+    and for torch alike, whichever of the two asks first.  Pure C hosts (physher itself) use the system library."""
+    global _nccl_preloaded
+    if _nccl_preloaded:
+        return
+    _nccl_preloaded = True
+    try:
+        import importlib.util
+
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            path = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                C.CDLL(path, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass
+
+
 def nccl_version() -> int:
     """NCCL_VERSION_CODE of the library the C layer bound at run time (0: not loadable)."""
+    _preload_nccl()
     return int(load_library().phb_nccl_version())
 
 
@@ -191,6 +217,7 @@ class Comm:
 
     @staticmethod
     def unique_id() -> bytes:
+        _preload_nccl()
         lib = load_library()
         buf = C.create_string_buffer(NCCL_ID_BYTES)
         rc = lib.phb_comm_unique_id(buf)
@@ -199,6 +226,7 @@ class Comm:
         return buf.raw
 
     def __init__(self, nranks: int, rank: int, unique_id: bytes, device: int):
+        _preload_nccl()
         self.lib = load_library()
         assert len(unique_id) == NCCL_ID_BYTES
         self._id = C.create_string_buffer(unique_id, NCCL_ID_BYTES)
@@ -514,6 +542,8 @@ class TreeLikelihoodGroup:
     whole alignment, model inputs broadcast, every evaluation launched on all shards before any result is collected."""
 
     def __init__(self, devices, left, right, root, nstate, ncat, npatterns, use_tip_states=True):
+        if len(set(int(d) for d in devices)) > 1:
+            _preload_nccl()  # the group reduces over NCCL when its shards sit on distinct devices
         self.lib = load_library()
         self.left = np.ascontiguousarray(left, dtype=np.int32)
         self.right = np.ascontiguousarray(right, dtype=np.int32)
