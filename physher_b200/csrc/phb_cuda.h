@@ -42,6 +42,14 @@ typedef struct phbc_op {
 #define PHBC_W_SLOT 1 /* idx = shared-memory slot                           */
 #define PHBC_W_ROOT 2 /* pre-order only: the parent is the root (W = 1 or pi) */
 #define PHBC_W_REG 3  /* the value is still in the registers of the preceding op   */
+/* Cherry recomputation (unscaled gradient walks): the message M_b = P_b (m_a' o m_b') of a cherry b -- an internal node whose children
+ * are both tips -- costs 24 FP64 operations to rebuild from its tips' matrix columns, against a 32-byte row written by the post-order
+ * pass and read back by the pre-order pass per (pattern, category).  When b's pre-order op directly follows its parent's (it is the
+ * parent's child b), the parent's op forms the two tip messages from the NEXT op's staged matrices and codes, leaves them in the
+ * registers that op will read them from, and multiplies by P_b itself: the row of b is neither written nor read. */
+#define PHBC_POST_NO_ROW 0x100   /* phbc_post_op.a_kind flag: the node's message row is not needed (recomputed by its parent's pre-order op) */
+#define PHBC_PRE_B_RECOMPUTE 1   /* phbc_pre_op.flags: child b is a cherry and its op is the next one: rebuild M_b instead of loading b_row */
+#define PHBC_PRE_TIPS_READY 2    /* phbc_pre_op.flags: this (tip-tip) op finds its two tip messages in registers, left by the preceding op */
 
 typedef struct phbc_post_op { /* one internal node, DFS post-order; 32 bytes (TMA bulk-copy granule)   */
 	int16_t a_kind, b_kind;  /* a tip child always comes first: kind = a_kind + b_kind in {0 tip-tip, 1 tip-internal, 2 internal-internal} */
@@ -60,7 +68,7 @@ typedef struct phbc_pre_op { /* one internal node acting as parent, DFS pre-orde
 	int16_t u_slot;          /* slot holding U_parent                                             */
 	int16_t a_slot, b_slot;  /* slots receiving U_a / U_b for internal children (-1: not kept)    */
 	int16_t a_code, b_code;  /* chunk-local index of a tip child's code row                       */
-	int16_t pad_;
+	int16_t flags;           /* PHBC_PRE_* (honoured by the unscaled gradient walk only)           */
 	int node;                /* parent node id (matrix P_node when not the root)                  */
 	int a_node, b_node;      /* children node ids                                                 */
 	int a_row, b_row;        /* lower-scratch rows (post-order op index) of internal children     */

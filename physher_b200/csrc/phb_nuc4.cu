@@ -220,6 +220,7 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 	constexpr int NTHR = NUC4_NT / PPT;  // threads per CTA
 	constexpr int PBT = PB / PPT;        // patterns per u-plane
 	static_assert(PBT % 32 == 0 || PPT == 1, "a warp must not mix categories");
+	constexpr bool RECOMP = GRAD == 1 && !SCALE;  // cherry recomputation (phb_cuda.h): the descriptors' flags are honoured by this variant only
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const int c = tid / PBT, pl0 = tid - c * PBT;
 	const int cell0 = c * PB + pl0;  // cell index of u = 0; u adds u * PBT
@@ -310,7 +311,9 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 				const int cnt = min(NUC4_CHUNK, prm.n_post - first);
 #pragma unroll 1
 				for (int j = 0; j < cnt; j++) {
-					const int kind = desc[j].a_kind + desc[j].b_kind;
+					const int kind = (desc[j].a_kind & 0xff) + desc[j].b_kind;
+					// a cherry whose parent's pre-order op rebuilds its message (unscaled gradient walks only) keeps no row
+					const bool keep_row = !(RECOMP && (desc[j].a_kind & PHBC_POST_NO_ROW));
 					const int a_idx = desc[j].a_idx, b_idx = desc[j].b_idx, dst_slot = desc[j].dst_slot;
 					const double *MN = reinterpret_cast<const double *>(mats + (j * 3 + 0) * C * 128);
 					const double *MA = reinterpret_cast<const double *>(mats + (j * 3 + 1) * C * 128);
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 #pragma unroll
 					for (int u = 0; u < PPT; u++) {
 						if (dst_slot >= 0) cell_store(slot_cell + dst_slot * NUC4_SLOT_BYTES + u * PBT * 16, out[u]);  // parked for a later kind-2 op
-						if (GRAD) row_store(row_cell + (size_t)(unsigned)(first + j) * NUC4_ROW_BYTES + u * PBT * 16, out[u]);
+						if (GRAD && keep_row) row_store(row_cell + (size_t)(unsigned)(first + j) * NUC4_ROW_BYTES + u * PBT * 16, out[u]);
 					}
 				}
 				loads++;
@@ -450,10 +453,11 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 			// message rows of the internal children of one op (kind: 0 tip-tip, 1 tip-internal, 2 internal-internal)
 			auto fetch = [&](const phbc_pre_op *d, double (&A)[PPT][4], double (&B)[PPT][4]) {
 				const int kind = d->kind;
+				const bool b_row = kind != 0 && !(RECOMP && (d->flags & PHBC_PRE_B_RECOMPUTE));
 #pragma unroll
 				for (int u = 0; u < PPT; u++) {
 					if (kind == 2) row_load(row_cell + (size_t)(unsigned)d->a_row * NUC4_ROW_BYTES + u * PBT * 16, A[u]);
-					if (kind != 0) row_load(row_cell + (size_t)(unsigned)d->b_row * NUC4_ROW_BYTES + u * PBT * 16, B[u]);
+					if (b_row) row_load(row_cell + (size_t)(unsigned)d->b_row * NUC4_ROW_BYTES + u * PBT * 16, B[u]);
 				}
 			};
 			// One op.  Its operands (message rows of the internal children) were loaded into xa / xb by the PREVIOUS op.  ALT: the first
@@ -476,6 +480,28 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 						fetch(reinterpret_cast<const phbc_pre_op *>(stage0 + ((loads + 1) & 1) * lay.bytes + lay.desc_off), na_, nb_);
 					}
 				};
+				// Cherry recomputation: child b is a cherry and its op is the NEXT one.  Its two tip messages are formed here from that op's
+				// staged matrices and codes, straight into the registers that op reads them from (na_ / nb_), and M_b = P_b (m_a' o m_b')
+				// takes the place of the row the post-order pass would have written and this op would have waited for.
+				auto recompute_b = [&]() {
+					const bool same = j + 1 < cnt;
+					const unsigned char *nst = same ? nullptr : stage0 + ((loads + 1) & 1) * lay.bytes;  // the next chunk's stage (its barrier was waited for in prefetch)
+					const phbc_pre_op *dn = same ? d + 1 : reinterpret_cast<const phbc_pre_op *>(nst + lay.desc_off);
+					const unsigned char *nm = same ? mats + (j + 1) * 3 * C * 128 : nst + my_mat;
+					const uint8_t *nc = same ? cds : nst + my_code;
+					const double *NP = reinterpret_cast<const double *>(nm);
+					const double *NA = reinterpret_cast<const double *>(nm + C * 128);
+					const double *NB = reinterpret_cast<const double *>(nm + 2 * C * 128);
+					double lb[PPT][4];
+#pragma unroll
+					for (int u = 0; u < PPT; u++) {
+						tip_message(NA, nc[dn->a_code * PB + u * PBT], na_[u]);
+						tip_message(NB, nc[dn->b_code * PB + u * PBT], nb_[u]);
+#pragma unroll
+						for (int i = 0; i < 4; i++) lb[u][i] = na_[u][i] * nb_[u][i];
+					}
+					matvec_smem_n<PPT>(NP, lb, xb);
+				};
 				if (L2PF) {
 					// the rows the op PHBC_PF_DIST positions later will read go to L2 now (the host put their indices into THIS op's
 					// descriptor): the register prefetch above is one op -- about the loaded HBM latency -- ahead of its use, the hint
@@ -488,6 +514,7 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 				const double *MA = reinterpret_cast<const double *>(mats + (j * 3 + 1) * C * 128);
 				const double *MB = reinterpret_cast<const double *>(mats + (j * 3 + 2) * C * 128);
 				if (ALT) prefetch();
+				if (RECOMP && (d->flags & PHBC_PRE_B_RECOMPUTE)) recompute_b();
 				// W = P_p U_p, the part of the op that does not need the children's rows: computed FIRST, so that the wait for the rows
 				// requested by the previous op (still 9 % of the stall samples with the L2 hints) sits behind 32 FP64 instructions
 				double W[PPT][4];
@@ -632,9 +659,13 @@ __global__ void __launch_bounds__(NUC4_NT / PPT, 3) k_nuc4_walk(const Nuc4Params
 				// messages of the children: the prefetched rows for internal children, matrix columns (or column sums) for tips
 				if (ALT) {
 #pragma unroll
-					for (int u = 0; u < PPT; u++) {
-						if (kind != 2) tip_message(MA, cds[d->a_code * PB + u * PBT], xa[u]);
-						if (kind == 0) tip_message(MB, cds[d->b_code * PB + u * PBT], xb[u]);
+					const bool tips_ready = RECOMP && (d->flags & PHBC_PRE_TIPS_READY);  // a cherry whose tip messages the previous op left in xa / xb
+					if (!tips_ready) {
+#pragma unroll
+						for (int u = 0; u < PPT; u++) {
+							if (kind != 2) tip_message(MA, cds[d->a_code * PB + u * PBT], xa[u]);
+							if (kind == 0) tip_message(MB, cds[d->b_code * PB + u * PBT], xb[u]);
+						}
 					}
 					body(xa, xb);
 				} else {
@@ -1248,7 +1279,7 @@ int phbc_nuc4_download_matrices(phbc_ctx *ctx, double *P, double *dP) {
 	if (e == cudaSuccess) {
 		memset(Pl, 0, (size_t)N * C * 16 * sizeof(double));
 		for (int k = 0; k < np; k++) {
-			const int node[3] = {ops[k].node, ops[k].a_kind == PHBC_W_TIP ? ops[k].a_node : -1, ops[k].b_kind == PHBC_W_TIP ? ops[k].b_node : -1};
+			const int node[3] = {ops[k].node, (ops[k].a_kind & 0xff) == PHBC_W_TIP ? ops[k].a_node : -1, ops[k].b_kind == PHBC_W_TIP ? ops[k].b_node : -1};
 			for (int w = 0; w < 3; w++)
 				if (node[w] >= 0) memcpy(Pl + (size_t)node[w] * C * 16, mats + ((size_t)3 * k + w) * C * 16, (size_t)C * 16 * sizeof(double));
 		}

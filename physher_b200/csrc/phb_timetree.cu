@@ -38,12 +38,15 @@ __global__ void k_time_forward(int T, int N, int B, int root, int nrates, const 
 			const double hp = heights[(size_t)parent[n] * B + b];
 			const double lo = lowers[n];
 			if (n >= T) {
-				h = lo + (hp - lo) * s[n - T];
+				// separately rounded like the host code of the reference (treetransform.c:224-237, compiled without FMA contraction): a height
+				// that differs by an ulp gives branch lengths, and with them exponentials, whose ROUNDING differs -- and the t^2, t^3 entries
+				// of a codon P(t) carry that as 1e-9 of their value
+				h = __dadd_rn(lo, __dmul_rn(__dsub_rn(hp, lo), s[n - T]));
 				lj += log(hp - lo);
 			} else {
 				h = lo;  // a tip's height is its sampling date
 			}
-			const double len = (nrates == 1 ? rt[0] : rt[n]) * (hp - h);
+			const double len = __dmul_rn(nrates == 1 ? rt[0] : rt[n], __dsub_rn(hp, h));  // treelikelihood.c:1652-1663
 			if (len < 0.0) *bad = 1;  // the reference exits on a negative branch length (treelikelihood.c:1659-1662)
 			bl[(size_t)b * N + n] = len;
 		}

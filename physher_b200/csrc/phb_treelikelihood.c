@@ -500,7 +500,21 @@ static int build_walk_schedules(phb_tlk *t) {
 		const int k2 = i + PHBC_PF_DIST;
 		t->pre_ops[i].pf_a_row = k2 < nint ? t->pre_ops[k2].a_row : -1;
 		t->pre_ops[i].pf_b_row = k2 < nint ? t->pre_ops[k2].b_row : -1;
-		t->pre_ops[i].pad_ = 0;
+		t->pre_ops[i].flags = 0;
+	}
+	/* cherry recomputation (see phb_cuda.h): op i + 1 is the op of op i's child b whenever b is internal; when that op is tip-tip, b's
+	 * message is rebuilt by op i and its row is neither written nor read */
+	for (int i = 0; i + 1 < nint; i++) {
+		phbc_pre_op *po = &t->pre_ops[i], *nx = &t->pre_ops[i + 1];
+		if (po->kind >= 1 && nx->kind == 0 && nx->node == po->b_node) {
+			po->flags |= PHBC_PRE_B_RECOMPUTE;
+			nx->flags |= PHBC_PRE_TIPS_READY;
+			t->post_ops[po->b_row].a_kind |= PHBC_POST_NO_ROW;
+		}
+	}
+	for (int i = 0; i < nint; i++) { /* a row that is never read needs no L2 hint */
+		const int k2 = i + PHBC_PF_DIST;
+		if (k2 < nint && (t->pre_ops[k2].flags & PHBC_PRE_B_RECOMPUTE)) t->pre_ops[i].pf_b_row = -1;
 	}
 	t->post_first_tips = nch > 0 ? t->post_chunk_tip0[1] : 0;
 	t->pre_first_tips = nch > 0 ? t->pre_chunk_tip0[1] : 0;
