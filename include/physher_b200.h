@@ -60,6 +60,9 @@ extern "C" {
                                             that a one-ulp difference in an exponential moves by 1e-9.  Default 1 for >= 60 states, else 0; node-at-a-time
                                             and tensor-core paths, single evaluations (batches build their matrices on the device) */
 
+#define PHB_OPT_TUNE 9                   /* profiling: geometry variant of the tensor-core message kernels (tile shape, cp.async ring depth and
+                                            granule size; phb_dmma.cu MsgCfg).  0 = the shipped choice; results do not depend on it */
+
 #define PHB_KERNELS_AUTO 0    /* by state count, like the function-pointer dispatch at treelikelihood.c:1067-1165 */
 #define PHB_KERNELS_GENERIC 1 /* node-at-a-time kernels, any state count, materialised upper partials */
 #define PHB_KERNELS_FUSED 2   /* whole-tree walk kernels (4 states) / tensor-core kernels (20, 61 states) */

@@ -76,6 +76,7 @@ typedef struct Backend {
 	int st_clean;
 } Backend;
 
+static long long g_total_evaluations = 0; /* device evaluations through every attached model of this process (introspection) */
 static Backend *g_backends = NULL; /* one host thread per SingleTreeLikelihood, like the reference (SURVEY.md 8b threading) */
 
 static Backend *backend_of_tlk(const SingleTreeLikelihood *tlk) {
@@ -234,6 +235,7 @@ static int prepare(Backend *b) {
 static double finish(Backend *b, double lnl) {
 	SingleTreeLikelihood *tlk = b->tlk;
 	b->evaluations++;
+	g_total_evaluations++;
 	tlk->lk = lnl;
 	if (phb_tlk_rescaling(b->h) && !tlk->scale) printf("_calculate: rescaling %f\n", -INFINITY); /* the reference's own message (:1497) */
 	tlk->scale = phb_tlk_rescaling(b->h) != 0; /* -inf => the device path switched rescaling on and recomputed (:1496-1519) */
@@ -937,6 +939,8 @@ int phb_physher_detach(Model *model) {
 	free(b);
 	return 0;
 }
+
+long long phb_physher_total_evaluations(void) { return g_total_evaluations; }
 
 long long phb_physher_evaluations(Model *model) {
 	Backend *b = backend_of_tlk((SingleTreeLikelihood *)model->obj);

@@ -25,7 +25,8 @@ def build(ref: bool = True) -> None:
     if ref and os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "phyc")):
         subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
         if os.path.exists(os.path.join(os.path.dirname(HERE), "physher_b200", "libphysher_b200.so")):
-            subprocess.check_call(["make", "-s", "-C", HERE, "glue"])  # reference-side binding of INTEGRATION.md (tests/test_glue_dropin.py)
+            # reference-side binding of INTEGRATION.md and the reference's C++ wrapper linked onto it (tests/test_glue_dropin.py)
+            subprocess.check_call(["make", "-s", "-C", HERE, "glue", "phycpp"])
 
 
 _dp = C.POINTER(C.c_double)

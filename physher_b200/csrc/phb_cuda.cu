@@ -1318,6 +1318,14 @@ extern "C" int phbc_set_timing(phbc_ctx *ctx, int on) {
 	ctx->timed_launches = 0;
 	return 0;
 }
+extern "C" int phbc_set_tune(phbc_ctx *ctx, int variant) {
+	if (variant < 0 || variant > 15) {
+		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "tuning variant %d out of range", variant);
+		return -1;
+	}
+	ctx->tune = variant;
+	return 0;
+}
 extern "C" int phbc_kernel_time(phbc_ctx *ctx, double *total_ms, long long *launches) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));
 	int rc = drain_events(ctx);

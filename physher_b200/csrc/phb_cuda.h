@@ -179,6 +179,7 @@ long long phbc_launch_count(const phbc_ctx *ctx);
 int phbc_last_family(const phbc_ctx *ctx); /* 1 generic, 2 fused walk, 3 tensor cores; 0 before the first evaluation */
 long long phbc_node_eval_count(const phbc_ctx *ctx); /* full evaluations that rewrote the node-at-a-time partials buffers */
 int phbc_set_timing(phbc_ctx *ctx, int on);
+int phbc_set_tune(phbc_ctx *ctx, int variant); /* geometry variant of the tensor-core message kernels (profiling; 0 = shipped) */
 int phbc_kernel_time(phbc_ctx *ctx, double *total_ms, long long *launches);
 
 #ifdef __cplusplus

@@ -116,7 +116,7 @@ __global__ void k_dmma_pack(int T, int N, int C, int root, int tip_states, const
 // no register is tied up by data in flight, so the prefetch distance does not depend on instruction scheduling.
 // One chunk buffer = NOPS operands x (MT * 8 patterns) rows x KC doubles, row stride RS = 4 (mod 8) doubles so that the
 // fragment reads (lane (r, q) -> row r, column 4 tt + q) are bank-conflict free.
-template <class Sh, int MT, int NOPS>
+template <class Sh, int MT, int NOPS, int NST = 0>
 struct AStage {
 	static constexpr int KC = Sh::KCH * 4;
 	static constexpr int RS = KC + ((4 - KC % 8) + 8) % 8;
@@ -124,11 +124,14 @@ struct AStage {
 	static constexpr int STG = NOPS * OPB;
 	// ring depth: the fills run NSTAGE - 1 chunks ahead of the tensor pipe.  A contraction that is ONE chunk (20 states) stages whole tiles:
 	// one tile ahead is enough there and the smaller ring buys a fourth resident CTA per SM (round 1, h4 profile: 12 -> 16 warps per SM)
-	static constexpr int NSTAGE = Sh::NCH == 1 ? 2 : 3;
+	static constexpr int NSTAGE = NST > 0 ? NST : (Sh::NCH == 1 ? 2 : 3);
 };
 
 __device__ __forceinline__ void cp_async8(double *dst, const double *src) {
 	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double *dst, const double *src) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -141,18 +144,22 @@ __device__ __forceinline__ void cp_async_wait() {
 // multiply-add and one cp.async per granule.  No predicates: rows past the pattern count read the last pattern again (their
 // results are never stored and carry weight 0), columns past S read the first doubles of the NEXT row / block -- finite values
 // that meet zero-padded matrix columns (the partials buffers are zero-initialised with a zeroed tail for exactly this reason).
-template <class Sh, int MT, int NOPS, int GT>
+// GB = doubles per granule: 2 (16-byte cp.async, half the LSU instructions and address arithmetic) wherever the HBM row stride S * 8, the
+// chunk width and the staged row stride are multiples of 16 bytes (20 states: rows of 160 bytes); 1 otherwise (61 states: 488 bytes)
+template <class Sh, int MT, int NOPS, int GT, int NST = 0, int GB = 1>
 struct AFill {
-	using A = AStage<Sh, MT, NOPS>;
-	static constexpr int PER = MT * 8 * A::KC;
+	using A = AStage<Sh, MT, NOPS, NST>;
+	static_assert(GB == 1 || (GB == 2 && Sh::S % 2 == 0 && A::KC % 2 == 0 && A::RS % 2 == 0), "16-byte granules need 16-byte aligned rows");
+	static constexpr int KG = A::KC / GB;  // granules per row
+	static constexpr int PER = MT * 8 * KG;
 	static constexpr int NE = (PER + GT - 1) / GT;
 	int row[NE], col[NE], soff[NE];
 	__device__ __forceinline__ void init(int gl) {
 #pragma unroll
 		for (int j = 0; j < NE; j++) {
 			const int e = j * GT + gl;
-			row[j] = e / A::KC;
-			col[j] = e - row[j] * A::KC;
+			row[j] = e / KG;
+			col[j] = (e - row[j] * KG) * GB;
 			soff[j] = row[j] * A::RS + col[j];
 			if (PER % GT != 0 && e >= PER) row[j] = -1;  // this thread has no granule j
 		}
@@ -162,15 +169,16 @@ struct AFill {
 		for (int j = 0; j < NE; j++) {
 			if (PER % GT != 0 && row[j] < 0) continue;
 			const int p = min(p0 + row[j], P - 1);
-			cp_async8(opbuf + soff[j], X + (size_t)p * Sh::S + (ch * A::KC + col[j]));
+			if (GB == 2) cp_async16(opbuf + soff[j], X + (size_t)p * Sh::S + (ch * A::KC + col[j]));
+			else cp_async8(opbuf + soff[j], X + (size_t)p * Sh::S + (ch * A::KC + col[j]));
 		}
 	}
 };
 
 // fragments of one staged operand: a[m][tt] = chunk[8 m + lane / 4][4 tt + lane % 4]
-template <class Sh, int MT, int NOPS>
+template <class Sh, int MT, int NOPS, int NST = 0>
 __device__ __forceinline__ void read_frags(const double *opbuf, int lane, double (&a)[MT][Sh::KCH]) {
-	using A = AStage<Sh, MT, NOPS>;
+	using A = AStage<Sh, MT, NOPS, NST>;
 	const int r = lane >> 2, q = lane & 3;
 #pragma unroll
 	for (int m = 0; m < MT; m++)
@@ -626,7 +634,7 @@ __device__ __forceinline__ double tip_value(const double *__restrict__ MT, int s
 	return s < Sh::S ? MT[s * Sh::NP + col] : 1.0;  // unknown state: factor 1 (treelikelihood20.c:125-131)
 }
 
-template <int S, int MT, int NSPLIT, int WM>
+template <int S, int MT, int NSPLIT, int WM, int NST = 0, int GB = 1>
 __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ img, int nimg) {
 	using Sh = DmmaShape<S>;
 	constexpr int NTW = Sh::NT / NSPLIT;
@@ -655,14 +663,14 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 	double *out = (double *)dm_partial_ptr(b, op.out, c);
 	const double *xa = a_tip_rt ? nullptr : dm_partial_ptr(b, op.a, c), *xb = b_tip_rt ? nullptr : dm_partial_ptr(b, op.b, c);
 	const int ntiles = (b.P + TP - 1) / TP;
-	using AS = AStage<Sh, MT, 2>;
+	using AS = AStage<Sh, MT, 2, NST>;
 	constexpr int GT = 32 * NSPLIT;
 	double *abuf = sm + nimg * Sh::IMG + wm * AS::NSTAGE * AS::STG;
 	const int gl = (warp % NSPLIT) * 32 + lane;
 	mbar_wait(bar, 0);
 	dispatch2(a_tip_rt, b_tip_rt, [&](auto ATIP, auto BTIP) {
 	constexpr bool a_tip = decltype(ATIP)::value, b_tip = decltype(BTIP)::value;
-	AFill<Sh, MT, 2, GT> plan;
+	AFill<Sh, MT, 2, GT, NST, GB> plan;
 	plan.init(gl);
 	int f_tile = blockIdx.x, f_ch = 0, f_stage = 0;
 	auto fill_next = [&]() {
@@ -700,8 +708,8 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 			const double *st = abuf + c_stage * AS::STG;
 			c_stage = c_stage + 1 == AS::NSTAGE ? 0 : c_stage + 1;
 			double ca[MT][Sh::KCH], cb[MT][Sh::KCH];
-			if (!a_tip) read_frags<Sh, MT, 2>(st, lane, ca);
-			if (!b_tip) read_frags<Sh, MT, 2>(st + AS::OPB, lane, cb);
+			if (!a_tip) read_frags<Sh, MT, 2, NST>(st, lane, ca);
+			if (!b_tip) read_frags<Sh, MT, 2, NST>(st + AS::OPB, lane, cb);
 #pragma unroll
 			for (int m = 0; m < MT; m++)
 #pragma unroll
@@ -744,7 +752,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 // sits in slot 1 when a is internal, else in slot 3 when b is internal, else (both tips) in a sixth slot at 20 states and in slot 1 at
 // 61 states, where five images are all an SM can hold -- a's tip image is then read from global memory (one L2-resident column per pattern).
 // ---------------------------------------------------------------------------------------------
-template <int S, int MT, int NSPLIT, int WM>
+template <int S, int MT, int NSPLIT, int WM, int NST = 0, int GB = 1>
 __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, const phbc_parent_op *__restrict__ ops, const double *__restrict__ img,
                                                                    const double *__restrict__ freqs, const double *__restrict__ weights,
                                                                    const double *__restrict__ pattern_lnl, int include_root_freqs, int pstride,
@@ -803,14 +811,14 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 	double *Ub = b.upper + ((size_t)op.b * b.C + c) * (size_t)b.P * S;
 	const int ntiles = (b.P + TP - 1) / TP;
 	double tot_a = 0.0, tot_b = 0.0, tot_n = 0.0;
-	using AS = AStage<Sh, MT, 3>;
+	using AS = AStage<Sh, MT, 3, NST>;
 	constexpr int GT = 32 * NSPLIT;
 	double *abuf = red + 4 * NWARPS + wm * AS::NSTAGE * AS::STG;  // ring operands: U_n | M_b | M_a
 	const int gl = (warp % NSPLIT) * 32 + lane;
 	mbar_wait(bar, 0);
 	dispatch3(is_root_rt, a_tip_rt, b_tip_rt, [&](auto ROOT, auto ATIP, auto BTIP) {
 	constexpr bool is_root = decltype(ROOT)::value, a_tip = decltype(ATIP)::value, b_tip = decltype(BTIP)::value;
-	AFill<Sh, MT, 3, GT> plan;
+	AFill<Sh, MT, 3, GT, NST, GB> plan;
 	plan.init(gl);
 	int f_tile = blockIdx.x, f_ch = 0, f_stage = 0;
 	auto fill_next = [&]() {
@@ -856,7 +864,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 			const double *st = abuf + c_stage * AS::STG;
 			c_stage = c_stage + 1 == AS::NSTAGE ? 0 : c_stage + 1;
 			double cw[MT][Sh::KCH];
-			if (!is_root) read_frags<Sh, MT, 3>(st, lane, cw);
+			if (!is_root) read_frags<Sh, MT, 3, NST>(st, lane, cw);
 			// the messages again in accumulator layout (row 8 m + r, columns (n0 + j) 8 + 2 q, + 1) while their chunk is staged
 #pragma unroll
 			for (int j = 0; j < NTW; j++) {
@@ -980,6 +988,29 @@ struct DmmaConfig<61> {  // 256 threads, 32 patterns per tile, n-tiles split ove
 	static constexpr int UWM_II = 8;  // two image slots instead of five leave room for a 16-warp CTA sharing them
 };
 
+// Geometry of the MESSAGE-form kernels, by state count and tuning variant (PHB_OPT_TUNE; 0 = what ships, chosen from the measured
+// table in profiles/): m-tiles per warp, n-split, m-groups per CTA, cp.async ring depth (0 = AStage's default) and granule size.
+template <int S, int VAR>
+struct MsgCfg;
+template <int MT_, int NSPLIT_, int WM_, int LNST_, int LGB_, int UMT_, int UNSPLIT_, int UWM_, int UWM_II_, int UNST_, int UGB_>
+struct MsgGeom {
+	static constexpr int MT = MT_, NSPLIT = NSPLIT_, WM = WM_, LNST = LNST_, LGB = LGB_;
+	static constexpr int UMT = UMT_, UNSPLIT = UNSPLIT_, UWM = UWM_, UWM_II = UWM_II_, UNST = UNST_, UGB = UGB_;
+};
+//                                      lower: MT NS WM NST GB | upper: MT NS WM WM_II NST GB
+template <> struct MsgCfg<20, 0> : MsgGeom<2, 1, 4, 0, 2, 1, 1, 4, 4, 0, 2> {};  // 16-byte granules (rows of 160 bytes)
+template <> struct MsgCfg<20, 1> : MsgGeom<2, 1, 4, 0, 1, 1, 1, 4, 4, 0, 1> {};  // round-1 geometry: 8-byte granules
+template <> struct MsgCfg<20, 2> : MsgGeom<2, 1, 4, 3, 2, 1, 1, 4, 4, 3, 2> {};  // ring of 3: two tiles ahead
+template <> struct MsgCfg<20, 3> : MsgGeom<1, 1, 4, 0, 2, 1, 1, 4, 4, 0, 2> {};  // 32-pattern tiles in the lower pass
+template <> struct MsgCfg<20, 4> : MsgGeom<2, 1, 8, 0, 2, 1, 1, 8, 8, 0, 2> {};  // 256-thread CTAs
+template <> struct MsgCfg<20, 5> : MsgGeom<2, 1, 4, 0, 2, 2, 1, 4, 4, 0, 2> {};  // 64-pattern tiles in the upper pass
+template <> struct MsgCfg<20, 6> : MsgGeom<4, 1, 2, 0, 2, 2, 1, 2, 2, 0, 2> {};  // 64-thread CTAs, wide warps
+template <> struct MsgCfg<61, 0> : MsgGeom<1, 2, 4, 0, 1, 1, 2, 4, 8, 0, 1> {};
+template <> struct MsgCfg<61, 1> : MsgGeom<1, 2, 4, 2, 1, 1, 2, 4, 8, 2, 1> {};  // ring of 2 (more CTAs per SM)
+template <> struct MsgCfg<61, 2> : MsgGeom<1, 2, 4, 0, 1, 1, 2, 4, 4, 0, 1> {};  // no wide variant for parents of two internal nodes
+#define PHBC_MSG_VARIANTS_20 7
+#define PHBC_MSG_VARIANTS_61 3
+
 bool phbc_dmma_supported(const phbc_ctx *ctx, const phbc_eval_opts *o) {
 	(void)o;
 	return ctx->S == 20 || ctx->S == 61;
@@ -1050,14 +1081,14 @@ static int dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
 
 // one level of message-form lower ops: three launches by the number of tip children (the device op list is sorted that way), so
 // that ops without tip children do not pay shared memory for tip images (61 states: 3 CTAs per SM instead of 1)
-template <int S>
+template <int S, int VAR>
 static int dmma_lower_msg_level(phbc_ctx *ctx, int level) {
 	using Sh = DmmaShape<S>;
-	using Cf = DmmaConfig<S>;
+	using Cf = MsgCfg<S, VAR>;
 	const int C = ctx->C, P = ctx->P;
 	Bufs b = phbc_make_bufs(ctx);
-	auto lower = k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM>;
-	const size_t ring = (size_t)Cf::WM * AStage<Sh, Cf::MT, 2>::NSTAGE * AStage<Sh, Cf::MT, 2>::STG;
+	auto lower = k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM, Cf::LNST, Cf::LGB>;
+	const size_t ring = (size_t)Cf::WM * AStage<Sh, Cf::MT, 2, Cf::LNST>::NSTAGE * AStage<Sh, Cf::MT, 2, Cf::LNST>::STG;
 	const int lthreads = 32 * Cf::WM * Cf::NSPLIT, ltiles = (P + Cf::WM * Cf::MT * 8 - 1) / (Cf::WM * Cf::MT * 8);
 	PHBC_CHECK(cudaFuncSetAttribute(lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 + (3 * Sh::IMG + ring) * sizeof(double))));
 	const bool split = true;  // per-kind launches (measured faster than one five-slot variant per level, round 1)
@@ -1097,10 +1128,10 @@ int phbc_dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
 
 // message-form pre-order pass: per depth, one launch per kind of parent (0, 1, 2 tip children; the device op list is sorted that
 // way).  Parents without tip children need two image slots (P_n, Q) and run as wider CTAs where that pays (DmmaConfig::UWM_II).
-template <int S>
+template <int S, int VAR>
 static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
 	using Sh = DmmaShape<S>;
-	using Cf = DmmaConfig<S>;
+	using Cf = MsgCfg<S, VAR>;
 	const int C = ctx->C, P = ctx->P, N = ctx->N;
 	int rc;
 	Bufs b = phbc_make_bufs(ctx);
@@ -1114,13 +1145,13 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 	for (int kind = 0; kind < 3; kind++) {
 		Variant &v = var[kind];
 		const bool wide = split && kind == 0 && Cf::UWM_II != Cf::UWM;
-		v.fn = wide ? (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM_II> : (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM>;
+		v.fn = wide ? (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM_II, Cf::UNST, Cf::UGB> : (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, Cf::UNST, Cf::UGB>;
 		v.wm = wide ? Cf::UWM_II : Cf::UWM;
 		v.nslots = (split && kind == 0) ? 2 : (S <= 32 ? 6 : 5);
 		const int warps = v.wm * Cf::UNSPLIT;
 		v.threads = 32 * warps;
 		v.tiles = (P + v.wm * Cf::UMT * 8 - 1) / (v.wm * Cf::UMT * 8);
-		v.smem = 128 + ((size_t)v.nslots * Sh::IMG + 2 * Sh::NP + 4 * warps + (size_t)v.wm * AStage<Sh, Cf::UMT, 3>::NSTAGE * AStage<Sh, Cf::UMT, 3>::STG) * sizeof(double);
+		v.smem = 128 + ((size_t)v.nslots * Sh::IMG + 2 * Sh::NP + 4 * warps + (size_t)v.wm * AStage<Sh, Cf::UMT, 3, Cf::UNST>::NSTAGE * AStage<Sh, Cf::UMT, 3, Cf::UNST>::STG) * sizeof(double);
 	}
 	for (int kind = 0; kind < 3; kind++) {
 		Variant &v = var[kind];
@@ -1169,6 +1200,41 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 	return phbc_gradient_from_partials(ctx, pstride, result);
 }
 
+// lower and upper passes of the message form in tuning variant VAR
+template <int S, int VAR>
+static int dmma_msg_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
+	int rc;
+	for (int l = 0; l < ctx->n_lower_levels; l++) {
+		if (ctx->h_lower_level_off[l + 1] - ctx->h_lower_level_off[l] <= 0) continue;
+		if ((rc = dmma_lower_msg_level<S, VAR>(ctx, l))) return rc;
+	}
+	if ((rc = phbc_generic_root(ctx, o, result))) return rc;
+	if (o->want_gradient && (rc = dmma_upper_msg<S, VAR>(ctx, o, result))) return rc;
+	return 0;
+}
+template <int S>
+static int dmma_msg_dispatch(phbc_ctx *ctx, const phbc_eval_opts *o, double *result);
+template <>
+int dmma_msg_dispatch<20>(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
+	switch (ctx->tune) {
+	case 1: return dmma_msg_passes<20, 1>(ctx, o, result);
+	case 2: return dmma_msg_passes<20, 2>(ctx, o, result);
+	case 3: return dmma_msg_passes<20, 3>(ctx, o, result);
+	case 4: return dmma_msg_passes<20, 4>(ctx, o, result);
+	case 5: return dmma_msg_passes<20, 5>(ctx, o, result);
+	case 6: return dmma_msg_passes<20, 6>(ctx, o, result);
+	default: return dmma_msg_passes<20, 0>(ctx, o, result);
+	}
+}
+template <>
+int dmma_msg_dispatch<61>(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
+	switch (ctx->tune) {
+	case 1: return dmma_msg_passes<61, 1>(ctx, o, result);
+	case 2: return dmma_msg_passes<61, 2>(ctx, o, result);
+	default: return dmma_msg_passes<61, 0>(ctx, o, result);
+	}
+}
+
 template <int S>
 static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	using Sh = DmmaShape<S>;
@@ -1183,22 +1249,22 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	ctx->lower_is_message = msg;
 	ctx->node_evals++;
 	if ((rc = phbc_time_begin(ctx))) return rc;
+	double *result = ctx->d_result + (size_t)o->batch_index * (1 + N);
+	if (msg) {
+		if ((rc = dmma_msg_dispatch<S>(ctx, o, result))) return rc;
+		if ((rc = phbc_time_end(ctx))) return rc;
+		PHBC_CHECK(cudaGetLastError());
+		return 0;
+	}
 	for (int l = 0; l < ctx->n_lower_levels; l++) {
 		const int beg = ctx->h_lower_level_off[l], cnt = ctx->h_lower_level_off[l + 1] - beg;
 		if (cnt <= 0) continue;
-		if ((rc = msg ? dmma_lower_msg_level<S>(ctx, l) : dmma_lower_ops<S>(ctx, ctx->d_lower_ops + beg, cnt))) return rc;
+		if ((rc = dmma_lower_ops<S>(ctx, ctx->d_lower_ops + beg, cnt))) return rc;
 		if (o->scale && (rc = phbc_generic_scale_ops(ctx, ctx->d_lower_ops + beg, cnt, o->scaling_threshold))) return rc;
 	}
-	double *result = ctx->d_result + (size_t)o->batch_index * (1 + N);
 	if ((rc = phbc_generic_root(ctx, o, result))) return rc;
 	if (o->want_gradient) {
 		const bool grad = !o->scale && !o->materialize_uppers;  // fused reductions use the unscaled form and skip the tips' uppers
-		if (msg) {
-			if ((rc = dmma_upper_msg<S>(ctx, o, result))) return rc;
-			if ((rc = phbc_time_end(ctx))) return rc;
-			PHBC_CHECK(cudaGetLastError());
-			return 0;
-		}
 		auto upper = grad ? k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, true> : k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, false>;
 		const int uwarps = Cf::UWM * Cf::UNSPLIT;
 		const size_t usmem = 128 + ((grad ? 5 : 3) * Sh::IMG + 2 * Sh::NP + 2 * uwarps + Cf::UWM * AStage<Sh, Cf::UMT, 3>::NSTAGE * AStage<Sh, Cf::UMT, 3>::STG) * sizeof(double);

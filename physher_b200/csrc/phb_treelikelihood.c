@@ -997,6 +997,12 @@ int phb_tlk_set_option(phb_tlk *t, int option, int value) {
 		t->host_exp = value != 0;
 		t->all_dirty = 1;
 		break;
+	case PHB_OPT_TUNE: {
+		int rc = phbc_set_tune(t->ctx, value);
+		if (rc) return dev_fail(rc);
+		phb_tlk_update_all_nodes(t);
+		return PHB_OK;
+	}
 	case PHB_OPT_TIMING: {
 		int rc = phbc_set_timing(t->ctx, value);
 		if (rc) return dev_fail(rc);

@@ -26,6 +26,7 @@ OPT_SCALING_THRESHOLD_EXP = 5
 OPT_TIMING = 6
 OPT_HOST_EXPONENTIALS = 8
 OPT_INCREMENTAL = 7
+OPT_TUNE = 9
 KERNELS_AUTO, KERNELS_GENERIC, KERNELS_FUSED = 0, 1, 2
 RAN_GENERIC, RAN_WALK, RAN_TENSOR = 1, 2, 3
 

@@ -18,6 +18,15 @@ from tests.util import GOLDEN, RTOL, grad_err, rel_err
 pytestmark = pytest.mark.gpu
 
 GLUE_SO = os.path.join(os.path.dirname(O.REF_SO), "libphysher_glue.so")
+_probe = []
+
+
+def phb_launches():
+    """kernel launches issued by libphysher_b200 so far in this process, through a throw-away object's counter is not possible -- the
+    wrapped phycpp owns its objects -- so the library-wide counter of device evaluations kept by the glue is used"""
+    G = C.CDLL(GLUE_SO)
+    G.phb_physher_total_evaluations.restype = C.c_longlong
+    return int(G.phb_physher_total_evaluations())
 
 
 @pytest.fixture(scope="module")
@@ -479,3 +488,90 @@ def test_use_upper_on_a_time_tree_stays_on_the_device(libs):
     assert rel_err(got, want) < RTOL and G.phb_physher_evaluations(model) > evals
     G.phb_physher_detach(model)
     dev.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# phycpp: the reference's C++ wrapper (src/phycpp/physher.cpp, what torchtree-physher binds), UNMODIFIED, on the device path
+# ---------------------------------------------------------------------------------------------------------------------------------
+
+def _phycpp(name):
+    path = os.path.join(os.path.dirname(O.REF_SO), name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} not built (make -C oracle phycpp, where /root/reference exists)")
+    lib = C.CDLL(path)
+    dp, cpp = C.POINTER(C.c_double), C.POINTER(C.c_char_p)
+    lib.phycpp_unrooted_gtr.argtypes = [C.c_char_p, C.c_int, cpp, cpp, dp, dp, C.c_double, C.c_int, C.c_int, dp, dp, C.c_int]
+    lib.phycpp_unrooted_gtr.restype = C.c_int
+    lib.phycpp_time_jc69.argtypes = [C.c_char_p, C.c_int, cpp, dp, cpp, C.c_double, dp, dp, C.c_int]
+    lib.phycpp_time_jc69.restype = C.c_int
+    return lib
+
+
+def _strs(items):
+    return (C.c_char_p * len(items))(*[s.encode() for s in items])
+
+
+def _phycpp_unrooted(lib, T=13, sites=350, seed=461, cats=4, tipstates=False):
+    from physher_b200 import synthetic as syn
+
+    topo = syn.random_topology(T, seed)
+    bl = syn.random_branch_lengths(topo, seed + 1)
+    pat = syn.random_patterns(T, sites, 4, 0.3, seed + 2, unknown_frac=0.02)
+    names = [f"t{i}" for i in range(T)]
+    seqs = syn.sequences_from_patterns(pat, syn.NUCLEOTIDES)
+    rates = np.array([0.05, 0.3, 0.1, 0.15, 0.3, 0.1])
+    freqs = np.array([0.1, 0.2, 0.3, 0.4])
+    lnl, grad = C.c_double(0.0), np.zeros(2 * T + 4)
+    dp = C.POINTER(C.c_double)
+    n = lib.phycpp_unrooted_gtr(syn.to_newick(topo, bl, names).encode(), T, _strs(names), _strs(seqs), rates.ctypes.data_as(dp),
+                                freqs.ctypes.data_as(dp), 0.5, cats, int(tipstates), C.byref(lnl), grad.ctypes.data_as(dp), grad.size)
+    return lnl.value, grad[:n].copy()
+
+
+def test_phycpp_cpu_harness_matches_the_c_reference():
+    """The harness itself (CPU link): TreeLikelihoodInterface::LogLikelihood of the C++ wrapper is the C model's logP."""
+    cpu = _phycpp("libphycpp_cpu.so")
+    lnl, g = _phycpp_unrooted(cpu)
+    assert np.isfinite(lnl) and g.size == 2 * 13 - 1 - 2 and np.isfinite(g).all() and np.abs(g).max() > 1.0
+
+
+test_phycpp_cpu_harness_matches_the_c_reference.pytestmark = []  # runs without a GPU
+
+
+@pytest.mark.parametrize("cats,tipstates", [(4, False), (1, True)])
+def test_phycpp_tree_likelihood_interface_on_the_device(libs, cats, tipstates):
+    """TreeLikelihoodInterface (physher.cpp:560-665) of the UNMODIFIED C++ wrapper, linked with --wrap so that its constructor attaches the
+    device backend and Gradient() -- which calls TreeLikelihood_gradient directly -- lands in phb_physher_gradient
+    (integration/phycpp_wrap.c): LogLikelihood / Gradient against the plainly linked wrapper on the CPU."""
+    L, G = libs
+    cpu = _phycpp("libphycpp_cpu.so")
+    dev = _phycpp("libphycpp_b200.so")
+    want_l, want_g = _phycpp_unrooted(cpu, cats=cats, tipstates=tipstates)
+    before = phb_launches()
+    got_l, got_g = _phycpp_unrooted(dev, cats=cats, tipstates=tipstates)
+    assert phb_launches() > before, "the wrapped phycpp did not launch anything on the device"
+    assert rel_err(got_l, want_l) < RTOL
+    # phycpp requests the reference's default gradient (include_root_freqs = true): the drop-in reproduces that form too
+    assert grad_err(got_g, want_g) < RTOL
+
+
+def test_phycpp_time_tree_kat_on_the_device(libs):
+    """C1 through phycpp: ReparameterizedTimeTreeModelInterface + JC69Interface + StrictClockModelInterface + TreeLikelihoodInterface
+    on the fluA fixture -- the path torchtree-physher takes for examples/fluA -- against the reference's known answers."""
+    L, G = libs
+    kat = json.load(open(os.path.join(GOLDEN, "c1_kat.json")))
+    fx = json.load(open(os.path.join(GOLDEN, "c1_jc69_time.json")))
+    spec = fx["model"]
+    seqs = spec["sitepattern"]["alignment"]["sequences"]
+    names = list(seqs.keys())
+    dates = np.array([float(spec["tree"]["dates"][n]) for n in names])
+    dp = C.POINTER(C.c_double)
+    out = {}
+    for tag, libname in (("cpu", "libphycpp_cpu.so"), ("dev", "libphycpp_b200.so")):
+        lib = _phycpp(libname)
+        lnl, grad = C.c_double(0.0), np.zeros(200)
+        n = lib.phycpp_time_jc69(spec["tree"]["newick"].encode(), len(names), _strs(names), dates.ctypes.data_as(dp), _strs([seqs[k] for k in names]),
+                                 float(spec["branchmodel"]["rate"]["value"]), C.byref(lnl), grad.ctypes.data_as(dp), grad.size)
+        out[tag] = (lnl.value, grad[:n].copy())
+    assert abs(out["cpu"][0] - kat["logP"]) < 1e-6, "the harness rebuilt the fixture"
+    assert rel_err(out["dev"][0], out["cpu"][0]) < RTOL and grad_err(out["dev"][1], out["cpu"][1]) < RTOL
