@@ -71,6 +71,8 @@ struct phbc_ctx {
 	double *d_pattern_lnl;   // [P]
 	double *d_result;        // [result_cap][1+N]
 	int result_cap;
+	double *h_result;        // pinned host copy of the result slots
+	size_t h_result_cap;
 	double *d_cat_grad;      // [cat_grad_cap][N][C]
 	int cat_grad_cap;
 	double *d_reduce, *h_reduce;  // [N + 2] operand of a sharded evaluation's all-reduce: lnL, grad[N], inf flag (+ pinned host copy)

@@ -115,6 +115,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	if (ctx->h_ex) cudaFreeHost(ctx->h_ex);
 	if (ctx->h_tt) cudaFreeHost(ctx->h_tt);
 	if (ctx->h_reduce) cudaFreeHost(ctx->h_reduce);
+	if (ctx->h_result) cudaFreeHost(ctx->h_result);
 	free(ctx->h_freqs);
 	free(ctx->h_qmat);
 	free(ctx->h_lower_level_off);
@@ -1202,18 +1203,21 @@ extern "C" int phbc_download_reduce(phbc_ctx *ctx, double *host) {
 extern "C" int phbc_download_results(phbc_ctx *ctx, int nbatch, double *lnl, double *grad) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));
 	const size_t N = ctx->N, row = 1 + N;
-	double *h = (double *)malloc((size_t)nbatch * row * sizeof(double));
-	if (!h) return -3;
-	cudaError_t e = cudaMemcpyAsync(h, ctx->d_result, (size_t)nbatch * row * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-	if (e == cudaSuccess) {
-		for (int b = 0; b < nbatch; b++) {
-			if (lnl) lnl[b] = h[b * row];
-			if (grad) memcpy(grad + (size_t)b * N, h + b * row + 1, N * sizeof(double));
-		}
+	const size_t need = (size_t)nbatch * row;
+	if (need > ctx->h_result_cap) {  // pinned: a pageable destination makes the copy a staged, synchronous one (C1 is all latency)
+		if (ctx->h_result) cudaFreeHost(ctx->h_result);
+		ctx->h_result = NULL;
+		ctx->h_result_cap = 0;
+		PHBC_CHECK(cudaMallocHost((void **)&ctx->h_result, need * sizeof(double)));
+		ctx->h_result_cap = need;
 	}
-	free(h);
-	PHBC_CHECK(e);
+	double *h = ctx->h_result;
+	PHBC_CHECK(cudaMemcpyAsync(h, ctx->d_result, need * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+	for (int b = 0; b < nbatch; b++) {
+		if (lnl) lnl[b] = h[b * row];
+		if (grad) memcpy(grad + (size_t)b * N, h + b * row + 1, N * sizeof(double));
+	}
 	return 0;
 }
 

@@ -18,6 +18,7 @@
 #include "phb_cuda.h"
 
 #include <math.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1266,7 +1267,7 @@ static int resident_uppers(phb_tlk *t, int node, int irf) {
 }
 
 /* SingleTreeLikelihood_update_uppers (treelikelihood.c:1530-1538): lnL, then every upper partial (root frequencies not folded in) */
-int phb_tlk_update_uppers(phb_tlk *t) {
+static int phb_tlk_update_uppers_impl(phb_tlk *t) {
 	if (!t->incremental) {
 		t->incremental = 1;
 		t->resident = 0;
@@ -1279,7 +1280,7 @@ int phb_tlk_update_uppers(phb_tlk *t) {
 }
 
 /* _calculate_uppper + calculate_dldt_uppper + d2lnldt2_uppper (treelikelihood.c:2592-2686, 2195-2335) at nbl candidate lengths */
-int phb_tlk_calculate_branch(phb_tlk *t, int node, int nbl, const double *bl, double *lnl, double *dlnl, double *d2lnl) {
+static int phb_tlk_calculate_branch_impl(phb_tlk *t, int node, int nbl, const double *bl, double *lnl, double *dlnl, double *d2lnl) {
 	if (node < 0 || node >= t->N || node == t->root) return fail(PHB_EINVAL, "calculate_branch: node %d is not a branch (root %d)", node, t->root);
 	if (nbl < 1 || !bl) return fail(PHB_EINVAL, "calculate_branch: nbl >= 1 and bl are required");
 	if (t->have_matrices) return fail(PHB_ESTATE, "calculate_branch needs the eigen system: explicit matrices cannot be re-evaluated at a new length");
@@ -1339,7 +1340,7 @@ int phb_tlk_calculate_branch(phb_tlk *t, int node, int nbl, const double *bl, do
  * transition matrices are rebuilt from the current lengths, and `mirror` (may be NULL) receives a host copy of the result
  * [C][P][S], so that reference code reading tlk->partials directly (asr.c:60-69) sees what the device computed.
  */
-int phb_tlk_update_partials(phb_tlk *t, int out, int p1, int m1, int p2, int m2, double *mirror) {
+static int phb_tlk_update_partials_impl(phb_tlk *t, int out, int p1, int m1, int p2, int m2, double *mirror) {
 	const int N = t->N, T = t->T;
 	if (out < T || out >= 2 * N || p1 < 0 || p1 >= 2 * N || m1 < 0 || m1 >= N || p2 >= 2 * N || (p2 >= 0 && (m2 < 0 || m2 >= N)))
 		return fail(PHB_EINVAL, "update_partials(%d, %d, %d, %d, %d): index out of range", out, p1, m1, p2, m2);
@@ -1385,7 +1386,7 @@ static int resident_gradient(phb_tlk *t, double *lnl, double *grad_out) {
 	return PHB_OK;
 }
 
-int phb_tlk_calculate(phb_tlk *t, double *lnl) {
+static int phb_tlk_calculate_impl(phb_tlk *t, double *lnl) {
 	if (!t->update) { /* cached, treelikelihood.c:1458-1460 */
 		*lnl = t->lk;
 		return PHB_OK;
@@ -1435,7 +1436,7 @@ static void apply_unrooted(const phb_tlk *t, double *g) {
 	if (t->unrooted) g[t->right[t->root]] = 0.0; /* treelikelihood.c:3249-3255 */
 }
 
-int phb_tlk_gradient(phb_tlk *t, const double **grad) {
+static int phb_tlk_gradient_impl(phb_tlk *t, const double **grad) {
 	if (t->gradient == NULL || !(t->prepared_gradient & PHB_FLAG_TREE_MODEL)) {
 		if (phb_tlk_initialize_gradient(t, PHB_FLAG_TREE_MODEL) == 0) return PHB_ENOMEM;
 	}
@@ -1499,7 +1500,7 @@ int phb_tlk_get_matrices(phb_tlk *t, double *P, double *dP) {
 	return PHB_OK;
 }
 
-int phb_tlk_gradient_device(phb_tlk *t, double *out_device) {
+static int phb_tlk_gradient_device_impl(phb_tlk *t, double *out_device) {
 	int rc = check_ready(t);
 	if (rc) return rc;
 	if ((rc = upload_bl(t))) return dev_fail(rc);
@@ -1521,7 +1522,7 @@ int phb_tlk_gradient_device(phb_tlk *t, double *out_device) {
  * tlk's stream and returns; collect blocks on that stream and returns the RAW sums of this object's patterns -- no inf / NaN /
  * unrooted policy, that belongs to whoever adds the shards up.  The object stays dirty (its lnL is not known here).
  */
-int phb_tlk_evaluate_launch(phb_tlk *t, int want_gradient) {
+static int phb_tlk_evaluate_launch_impl(phb_tlk *t, int want_gradient) {
 	int rc = check_ready(t);
 	if (rc) return rc;
 	if ((rc = upload_bl(t))) return dev_fail(rc);
@@ -1550,7 +1551,7 @@ int phb_tlk_evaluate_collect(phb_tlk *t, double *lnl, double *grad) {
  */
 int phb_internal_allreduce(phb_comm *c, double *buf, size_t count, void *stream); /* phb_nccl.c */
 
-int phb_tlk_gradient_allreduce_device(phb_tlk *t, phb_comm *comm, double **out_device) {
+static int phb_tlk_gradient_allreduce_device_impl(phb_tlk *t, phb_comm *comm, double **out_device) {
 	int rc = check_ready(t);
 	if (rc) return rc;
 	if ((rc = upload_bl(t))) return dev_fail(rc);
@@ -1573,7 +1574,7 @@ int phb_tlk_gradient_allreduce_device(phb_tlk *t, phb_comm *comm, double **out_d
 /* the same with host results and the reference's conventions applied to the REDUCED values on every rank alike: +-inf lnL (or an
  * inf shard) switches rescaling on and recomputes (treelikelihood.c:1496-1519), NaN / inf NaN-fills the gradient (:328-332), the
  * unrooted convention zeroes the root's right child (:3249-3255).  *grad is owned by the tlk. */
-int phb_tlk_gradient_allreduce(phb_tlk *t, phb_comm *comm, double *lnl, const double **grad) {
+static int phb_tlk_gradient_allreduce_impl(phb_tlk *t, phb_comm *comm, double *lnl, const double **grad) {
 	if (!grad) return fail(PHB_EINVAL, "grad is required");
 	if (t->gradient == NULL || !(t->prepared_gradient & PHB_FLAG_TREE_MODEL)) {
 		if (phb_tlk_initialize_gradient(t, PHB_FLAG_TREE_MODEL) == 0) return PHB_ENOMEM;
@@ -1633,7 +1634,7 @@ int phb_tlk_synchronize(phb_tlk *t) {
 	return PHB_OK;
 }
 
-int phb_tlk_gradient_batch(phb_tlk *t, int nbatch, const double *bl, double *lnl, double *grad) {
+static int phb_tlk_gradient_batch_impl(phb_tlk *t, int nbatch, const double *bl, double *lnl, double *grad) {
 	if (nbatch < 1) return fail(PHB_EINVAL, "nbatch must be >= 1");
 	/* inputs other than branch lengths must be in place */
 	const int had_bl = t->have_bl;
@@ -1676,7 +1677,7 @@ int phb_tlk_gradient_batch(phb_tlk *t, int nbatch, const double *bl, double *lnl
 }
 
 /* node sweep of calculate_dlnl_dQ (treelikelihood.c:2337-2583) for `nsets` sets of per-node matrices, e.g. dP/d theta from m->dPdp */
-int phb_tlk_matrix_gradient(phb_tlk *t, int nsets, const double *M, double *out) {
+static int phb_tlk_matrix_gradient_impl(phb_tlk *t, int nsets, const double *M, double *out) {
 	if (nsets < 1 || !M || !out) return fail(PHB_EINVAL, "nsets >= 1, M and out are required");
 	int rc = check_ready(t);
 	if (rc) return rc;
@@ -1868,7 +1869,7 @@ int phb_tlk_set_time_tree(phb_tlk *t, const double *tip_heights) {
 	return PHB_OK;
 }
 
-int phb_tlk_gradient_batch_time(phb_tlk *t, int nbatch, const double *ratios, const double *rates, int nrates, int include_jacobian,
+static int phb_tlk_gradient_batch_time_impl(phb_tlk *t, int nbatch, const double *ratios, const double *rates, int nrates, int include_jacobian,
                                 double *lnl, double *log_jacobian, double *grad_ratios, double *grad_rates) {
 	if (nbatch < 1 || !ratios || !rates || !lnl) return fail(PHB_EINVAL, "nbatch >= 1, ratios, rates and lnl are required");
 	if (nrates != 1 && nrates != t->N) return fail(PHB_EINVAL, "nrates must be 1 (strict clock) or N = %d (one rate per node)", t->N);
@@ -1925,3 +1926,92 @@ int phb_tlk_kernel_time(phb_tlk *t, double *total_ms, long long *launches) {
 long long phb_tlk_launch_count(const phb_tlk *t) { return phbc_launch_count(t->ctx); }
 
 int phb_tlk_last_kernels(const phb_tlk *t) { return phbc_last_family(t->ctx); }
+
+/* ------------------------------------------------------------------------------------------- */
+/* NVTX ranges at the C-ABI entry points that do device work: an nsys / ncu timeline   */
+/* shows one named range per call of the reference-facing API, with the kernels nested inside   */
+/* ------------------------------------------------------------------------------------------- */
+int phb_tlk_calculate(phb_tlk *t, double *lnl) {
+	nvtxRangePushA("phb_tlk_calculate");
+	const int rc = phb_tlk_calculate_impl(t, lnl);
+	nvtxRangePop();
+	return rc;
+}
+
+int phb_tlk_gradient(phb_tlk *t, const double **grad) {
+	nvtxRangePushA("phb_tlk_gradient");
+	const int rc = phb_tlk_gradient_impl(t, grad);
+	nvtxRangePop();
+	return rc;
+}
+
+int phb_tlk_gradient_batch(phb_tlk *t, int nbatch, const double *bl, double *lnl, double *grad) {
+	nvtxRangePushA("phb_tlk_gradient_batch");
+	const int rc = phb_tlk_gradient_batch_impl(t, nbatch, bl, lnl, grad);
+	nvtxRangePop();
+	return rc;
+}
+
+int phb_tlk_gradient_batch_time(phb_tlk *t, int nbatch, const double *ratios, const double *rates, int nrates, int include_jacobian,
+                                double *lnl, double *log_jacobian, double *grad_ratios, double *grad_rates) {
+	nvtxRangePushA("phb_tlk_gradient_batch_time");
+	const int rc = phb_tlk_gradient_batch_time_impl(t, nbatch, ratios, rates, nrates, include_jacobian, lnl, log_jacobian, grad_ratios, grad_rates);
+	nvtxRangePop();
+	return rc;
+}
+
+int phb_tlk_matrix_gradient(phb_tlk *t, int nsets, const double *M, double *out) {
+	nvtxRangePushA("phb_tlk_matrix_gradient");
+	const int rc = phb_tlk_matrix_gradient_impl(t, nsets, M, out);
+	nvtxRangePop();
+	return rc;
+}
+
+int phb_tlk_calculate_branch(phb_tlk *t, int node, int nbl, const double *bl, double *lnl, double *dlnl, double *d2lnl) {
+	nvtxRangePushA("phb_tlk_calculate_branch");
+	const int rc = phb_tlk_calculate_branch_impl(t, node, nbl, bl, lnl, dlnl, d2lnl);
+	nvtxRangePop();
+	return rc;
+}
+
+int phb_tlk_update_uppers(phb_tlk *t) {
+	nvtxRangePushA("phb_tlk_update_uppers");
+	const int rc = phb_tlk_update_uppers_impl(t);
+	nvtxRangePop();
+	return rc;
+}
+
+int phb_tlk_gradient_device(phb_tlk *t, double *out_device) {
+	nvtxRangePushA("phb_tlk_gradient_device");
+	const int rc = phb_tlk_gradient_device_impl(t, out_device);
+	nvtxRangePop();
+	return rc;
+}
+
+int phb_tlk_gradient_allreduce_device(phb_tlk *t, phb_comm *comm, double **out_device) {
+	nvtxRangePushA("phb_tlk_gradient_allreduce_device");
+	const int rc = phb_tlk_gradient_allreduce_device_impl(t, comm, out_device);
+	nvtxRangePop();
+	return rc;
+}
+
+int phb_tlk_gradient_allreduce(phb_tlk *t, phb_comm *comm, double *lnl, const double **grad) {
+	nvtxRangePushA("phb_tlk_gradient_allreduce");
+	const int rc = phb_tlk_gradient_allreduce_impl(t, comm, lnl, grad);
+	nvtxRangePop();
+	return rc;
+}
+
+int phb_tlk_evaluate_launch(phb_tlk *t, int want_gradient) {
+	nvtxRangePushA("phb_tlk_evaluate_launch");
+	const int rc = phb_tlk_evaluate_launch_impl(t, want_gradient);
+	nvtxRangePop();
+	return rc;
+}
+
+int phb_tlk_update_partials(phb_tlk *t, int out, int p1, int m1, int p2, int m2, double *mirror) {
+	nvtxRangePushA("phb_tlk_update_partials");
+	const int rc = phb_tlk_update_partials_impl(t, out, p1, m1, p2, m2, mirror);
+	nvtxRangePop();
+	return rc;
+}
