@@ -90,6 +90,18 @@ struct phbc_ctx {
 	int tune;                // kernel-geometry variant of the tensor-core message kernels (PHB_OPT_TUNE; 0 = shipped)
 	int last_family;         // kernels of the last evaluation: 1 generic node-at-a-time, 2 fused 4-state walk, 3 FP64 tensor-core
 	int dmma_pack_adjoint, dmma_pack_irf;  // how the dP images of internal nodes were packed last (phbc_download_matrices undoes it)
+	bool dmma_pack_tips;     // tips were packed as transposed gather images
+
+	// whole-tree tensor-core walk (phb_dwalk.cu)
+	void *d_dw_post, *d_dw_pre;  // walk descriptors with global tip positions (DwPost / DwPre)
+	int dw_nops;
+	uint8_t *d_dw_codes;     // [2][tiles][T][TP] tip codes in post- / pre-order walk order, tile-major (one bulk copy per tip operand and tile)
+	size_t dw_codes_bytes;
+	int dw_codes_tp;         // patterns per tile the codes were laid out for (0: not valid)
+	bool dw_codes_bad;       // tip partials that are not 0/1 vectors of a single state (or all ones): the walk declines
+	int *d_dw_bad;
+	double *d_dw_spill;      // [spilled slots][C][P][S] upper partials parked beyond the shared-memory slots
+	size_t dw_spill_bytes;
 	long long launches;
 	long long node_evals;    // full evaluations that rewrote the node-at-a-time buffers (generic / tensor-core paths)
 
@@ -141,6 +153,11 @@ int phbc_dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
 bool phbc_dmma_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);
 int phbc_dmma_pack(phbc_ctx *ctx);                                   // packed matrix images from d_P / d_dP
 int phbc_dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt);  // out = (P_a x_a) o (P_b x_b) for a device op list (one level)
+// whole-tree walk on the FP64 tensor cores, 20 states (phb_dwalk.cu)
+int phbc_dwalk_set_schedule(phbc_ctx *ctx, const phbc_schedule *s);
+bool phbc_dwalk_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);
+int phbc_dwalk_usable(phbc_ctx *ctx, const phbc_eval_opts *o);                       // supported AND the tips encode as single states
+int phbc_dwalk_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *result);       // post-order walk, root, pre-order walk, gradient sums
 // fused 4-state walk path (phb_nuc4.cu)
 int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
 bool phbc_nuc4_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);

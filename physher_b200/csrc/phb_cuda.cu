@@ -100,7 +100,8 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	                ctx->d_sf, ctx->d_lower_ops, ctx->d_upper_ops, ctx->d_parent_ops, ctx->d_post_ops, ctx->d_pre_ops, ctx->d_walk_mats,
 	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch,
 	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl, ctx->d_walk_gstat, ctx->d_nuc4_G, ctx->d_ex, ctx->d_post_tip_order, ctx->d_pre_tip_order, ctx->d_dmma_img, ctx->d_tt_lowers, ctx->d_tt_topo, ctx->d_tt_bad,
-	                ctx->d_tt_ratios, ctx->d_tt_rates, ctx->d_tt_heights, ctx->d_tt_adj, ctx->d_tt_out, ctx->d_reduce};
+	                ctx->d_tt_ratios, ctx->d_tt_rates, ctx->d_tt_heights, ctx->d_tt_adj, ctx->d_tt_out, ctx->d_reduce,
+	                ctx->d_dw_post, ctx->d_dw_pre, ctx->d_dw_codes, ctx->d_dw_bad, ctx->d_dw_spill};
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		if (bufs[i]) cudaFree(bufs[i]);
 	if (ctx->ev_beg) {
@@ -207,6 +208,7 @@ extern "C" int phbc_set_schedule(phbc_ctx *ctx, const phbc_schedule *s) {
 	ctx->post_first_tips = s->post_first_tips;
 	ctx->pre_first_tips = s->pre_first_tips;
 	ctx->nuc4_codes_valid = false;
+	if ((rc = phbc_dwalk_set_schedule(ctx, s))) return rc;
 	ctx->n_lower_ops = s->n_lower_ops;
 	ctx->n_upper_ops = s->n_upper_ops;
 	ctx->n_lower_levels = s->n_lower_levels;
@@ -237,12 +239,14 @@ extern "C" int phbc_set_schedule(phbc_ctx *ctx, const phbc_schedule *s) {
 extern "C" int phbc_upload_tip_states(phbc_ctx *ctx, const uint8_t *states) {
 	if (!ctx->d_tip_states) return -1;
 	ctx->nuc4_codes_valid = false;
+	ctx->dw_codes_tp = 0;
 	UPLOAD(ctx->d_tip_states, states, (size_t)ctx->T * ctx->P);
 	return 0;
 }
 extern "C" int phbc_upload_tip_partials(phbc_ctx *ctx, const double *partials) {
 	if (!ctx->d_tip_partials) return -1;
 	ctx->nuc4_codes_valid = false;
+	ctx->dw_codes_tp = 0;
 	UPLOAD(ctx->d_tip_partials, partials, (size_t)ctx->T * ctx->P * ctx->S);
 	return 0;
 }
@@ -318,6 +322,7 @@ extern "C" int phbc_copy_inputs(phbc_ctx *dst, phbc_ctx *src, int matrices, int 
 		PHBC_CHECK(cudaMemcpyPeerAsync(dst->d_tip_partials, dst->device, src->d_tip_partials, src->device, T * P * S * sizeof(double), dst->stream));
 	PHBC_CHECK(cudaMemcpyPeerAsync(dst->d_weights, dst->device, src->d_weights, src->device, P * sizeof(double), dst->stream));
 	dst->nuc4_codes_valid = false;
+	dst->dw_codes_tp = 0;
 	if (matrices && src->d_P && src->d_dP) {
 		int rc = ensure_node_matrices(dst);
 		if (rc) return rc;

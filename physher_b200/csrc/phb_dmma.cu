@@ -22,7 +22,7 @@
 //                 branch-gradient terms sum_i f_i U_x[i] D_x[i] * w_k / L_k reduced in the same pass.
 // Rescaling reuses the generic K5 kernel between levels; under rescaling the gradient reductions (which need
 // cross-category denominators) run through the generic K9/K10 kernel on the uppers this path stored.
-#include "phb_ctx.cuh"
+#include "phb_dmma_common.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -30,26 +30,6 @@
 
 #include <type_traits>
 
-template <int S_>
-struct DmmaShape {
-	static constexpr int S = S_;
-	static constexpr int KP = (S + 3) / 4 * 4;  // padded contraction length
-	static constexpr int NP = (S + 7) / 8 * 8;  // padded output states
-	static constexpr int KT = KP / 4, NT = NP / 8;
-	static constexpr int LD = (KP % 8 == 4) ? KP : KP + 4;  // leading dimension of a staged matrix, = 4 (mod 8)
-	static constexpr int MAT = NP * LD;                     // doubles per staged matrix
-	// the contraction runs in chunks of KCH k-steps; the A fragments of chunk i + 1 are fetched from HBM while the tensor
-	// pipe works on chunk i (register double buffering).  Short contractions are one chunk: the prefetch then spans tiles.
-	static constexpr int KCH = KT <= 6 ? KT : 4;
-	static constexpr int NCH = (KT + KCH - 1) / KCH;
-	// packed matrix image (one TMA bulk copy): [NP][LD] for partial operands, or TRANSPOSED [S][NP] + row sums [NP] for state tips
-	static constexpr int TIP_IMG = S * NP + NP;
-	static constexpr int IMG = ((MAT > TIP_IMG ? MAT : TIP_IMG) + 1) / 2 * 2;  // doubles, 16-byte multiple
-};
-
-__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
-	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 // acc[m][j] (+)= A-fragments[m][tt] x bf for all MT m-tiles of one (k-step, n-tile).
 // (m16n8k4 on pairs of m-tiles was measured on B200: same results, 5-12 % SLOWER end to end than two m8n8k4 -- round 1, s16.)
 template <int MT, int NTW, int KCH>
@@ -92,9 +72,13 @@ __global__ void k_dmma_pack(int T, int N, int C, int root, int tip_states, const
 			dst[e] = i < Sh::S ? src[i * Sh::S + s] : 0.0;
 		}
 		for (int i = threadIdx.x; i < Sh::NP; i += blockDim.x) {
+			// row S = what an unknown state selects: 1 for probabilities (treelikelihood20.c:125-131), the real row sum for derivatives
 			double acc = 0.0;
-			if (i < Sh::S)
-				for (int j = 0; j < Sh::S; j++) acc += src[i * Sh::S + j];
+			if (i < Sh::S) {
+				if (which == 0) acc = 1.0;
+				else
+					for (int j = 0; j < Sh::S; j++) acc += src[i * Sh::S + j];
+			}
 			dst[Sh::S * Sh::NP + i] = acc;
 		}
 		for (int e = Sh::TIP_IMG + threadIdx.x; e < Sh::IMG; e += blockDim.x) dst[e] = 0.0;
@@ -1036,7 +1020,7 @@ static int pick_chunks(int slots, int units, int ntiles) {
 
 // packed matrix images [P | dP][node][category][IMG] from the per-node matrices
 template <int S>
-static int dmma_pack(phbc_ctx *ctx, bool adjoint = false, int include_root_freqs = 0) {
+static int dmma_pack(phbc_ctx *ctx, bool adjoint = false, int include_root_freqs = 0, int tip_images = -1) {
 	using Sh = DmmaShape<S>;
 	const int C = ctx->C, N = ctx->N;
 	const size_t img_bytes = (size_t)2 * N * C * Sh::IMG * sizeof(double);
@@ -1049,7 +1033,8 @@ static int dmma_pack(phbc_ctx *ctx, bool adjoint = false, int include_root_freqs
 		ctx->dmma_img_bytes = img_bytes;
 	}
 	ctx->dmma_pack_adjoint = adjoint, ctx->dmma_pack_irf = include_root_freqs;
-	k_dmma_pack<Sh><<<dim3(N, C, 2), 128, 0, ctx->stream>>>(ctx->T, N, C, ctx->root, ctx->tip_kind == PHBC_TIP_STATES, ctx->d_P, ctx->d_dP, ctx->d_dmma_img,
+	ctx->dmma_pack_tips = tip_images < 0 ? ctx->tip_kind == PHBC_TIP_STATES : tip_images != 0;
+	k_dmma_pack<Sh><<<dim3(N, C, 2), 128, 0, ctx->stream>>>(ctx->T, N, C, ctx->root, ctx->dmma_pack_tips, ctx->d_P, ctx->d_dP, ctx->d_dmma_img,
 	                                                         adjoint ? 1 : 0, ctx->d_freqs, include_root_freqs);
 	ctx->launches++;
 	PHBC_CHECK(cudaGetLastError());
@@ -1115,6 +1100,11 @@ static int dmma_lower_msg_level(phbc_ctx *ctx, int level) {
 	return 0;
 }
 
+int phbc_dmma_pack_images(phbc_ctx *ctx, bool adjoint, int include_root_freqs, bool tip_images) {
+	if (ctx->S == 20) return dmma_pack<20>(ctx, adjoint, include_root_freqs, tip_images ? 1 : 0);
+	if (ctx->S == 61) return dmma_pack<61>(ctx, adjoint, include_root_freqs, tip_images ? 1 : 0);
+	return -1;
+}
 int phbc_dmma_pack(phbc_ctx *ctx) {
 	if (ctx->S == 20) return dmma_pack<20>(ctx);
 	if (ctx->S == 61) return dmma_pack<61>(ctx);
@@ -1241,6 +1231,19 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	using Cf = DmmaConfig<S>;
 	const int C = ctx->C, P = ctx->P, N = ctx->N;
 	int rc;
+	if (phbc_dwalk_usable(ctx, o)) {
+		// whole-tree walk (phb_dwalk.cu): messages in the lower buffers as in the message form below, upper partials never materialised
+		phbc_eval_opts e = *o;
+		e.want_gradient = 0;  // no upper buffers
+		if ((rc = phbc_generic_prepare(ctx, &e))) return rc;
+		ctx->lower_is_message = true;
+		ctx->node_evals++;
+		if ((rc = phbc_time_begin(ctx))) return rc;
+		if ((rc = phbc_dwalk_passes(ctx, o, ctx->d_result + (size_t)o->batch_index * (1 + ctx->N)))) return rc;
+		if ((rc = phbc_time_end(ctx))) return rc;
+		PHBC_CHECK(cudaGetLastError());
+		return 0;
+	}
 	if ((rc = phbc_generic_prepare(ctx, o))) return rc;
 	Bufs b = phbc_make_bufs(ctx);
 	// message form: the fast path (unscaled, state tips, eigen system, upper partials not needed as such afterwards)
@@ -1334,7 +1337,7 @@ static int dmma_download(phbc_ctx *ctx, double *P, double *dP) {
 				for (int c = 0; c < C; c++) {
 					const double *src = img + (((size_t)which * N + nd) * C + c) * Sh::IMG;
 					double *M = dst + ((size_t)nd * C + c) * S * S;
-					const bool tip = nd < T && ctx->tip_kind == PHBC_TIP_STATES, adj = which == 1 && ctx->dmma_pack_adjoint && nd >= T;
+					const bool tip = nd < T && ctx->dmma_pack_tips, adj = which == 1 && ctx->dmma_pack_adjoint && nd >= T;
 					for (int i = 0; i < S; i++)
 						for (int j = 0; j < S; j++) {
 							if (nd == ctx->root) M[i * S + j] = src[i * Sh::LD + j];

@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Geometry sweep of the tensor-core message kernels (phb_dmma.cu MsgCfg, PHB_OPT_TUNE) on the BASELINE workloads:
 
-    python tools/tune_dmma.py c4 [patterns] > profiles/r2_tune_c4.jsonl
+    python tools/tune_dmma.py c4 [patterns] [variants, e.g. 0,9,14] > profiles/r2_tune_c4.jsonl
+
+20 states: variant 0 is the whole-tree walk (phb_dwalk.cu), 9 the level-batched message kernels it replaced (their own geometry
+variants 1-6 are reachable as 9 only through phb_dmma.cu's table), 11-14 the walk's test geometries (one slot / 8 warps / both / 4 warps).
 
 One JSON line per variant: ms per lnL + gradient evaluation (kernel sequence timed with CUDA events inside the library) and the
 largest deviation of its gradient from variant 0's (the variants must agree to rounding)."""
@@ -25,6 +28,7 @@ def main():
     if len(sys.argv) > 2:
         cfg["patterns"] = int(sys.argv[2])
     nvar = {20: 7, 61: 3}[cfg["states"]]
+    variants = [int(v) for v in sys.argv[3].split(",")] if len(sys.argv) > 3 else list(range(nvar)) + [0]
     topo, bl, m, rates, props, patterns, weights = bench.make_inputs(cfg, 0)
     tlk = phb.SingleTreeLikelihood(topo.left, topo.right, topo.root, cfg["states"], cfg["cats"], cfg["patterns"], use_tip_states=True, device=0)
     tlk.set_tip_states(patterns)
@@ -33,7 +37,7 @@ def main():
     tlk.set_frequencies(m.freqs)
     tlk.set_site_model(rates, props)
     base = None
-    for v in list(range(nvar)) + [0]:
+    for v in variants:
         tlk.set_option(OPT_TUNE, v)
         tlk.set_branch_lengths(bl)
         g = tlk.gradient().copy()
