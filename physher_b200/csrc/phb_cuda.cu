@@ -1328,7 +1328,7 @@ extern "C" int phbc_set_timing(phbc_ctx *ctx, int on) {
 	return 0;
 }
 extern "C" int phbc_set_tune(phbc_ctx *ctx, int variant) {
-	if (variant < 0 || variant > 15) {
+	if (variant < 0 || variant > 31) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "tuning variant %d out of range", variant);
 		return -1;
 	}

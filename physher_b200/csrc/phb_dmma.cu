@@ -67,9 +67,11 @@ __global__ void k_dmma_pack(int T, int N, int C, int root, int tip_states, const
 		return;
 	}
 	if (n < T && tip_states) {
+		// tip_states == 2 (whole-tree walk): derivative images carry the frequency weight of the gradient sum, [s][i] = f_i dP[i][s]
+		const bool weighted = which == 1 && tip_states == 2 && !include_root_freqs;
 		for (int e = threadIdx.x; e < Sh::S * Sh::NP; e += blockDim.x) {
 			const int s = e / Sh::NP, i = e - s * Sh::NP;
-			dst[e] = i < Sh::S ? src[i * Sh::S + s] : 0.0;
+			dst[e] = i < Sh::S ? (weighted ? freqs[i] : 1.0) * src[i * Sh::S + s] : 0.0;
 		}
 		for (int i = threadIdx.x; i < Sh::NP; i += blockDim.x) {
 			// row S = what an unknown state selects: 1 for probabilities (treelikelihood20.c:125-131), the real row sum for derivatives
@@ -78,6 +80,7 @@ __global__ void k_dmma_pack(int T, int N, int C, int root, int tip_states, const
 				if (which == 0) acc = 1.0;
 				else
 					for (int j = 0; j < Sh::S; j++) acc += src[i * Sh::S + j];
+				if (weighted) acc *= freqs[i];
 			}
 			dst[Sh::S * Sh::NP + i] = acc;
 		}
@@ -1033,7 +1036,7 @@ static int dmma_pack(phbc_ctx *ctx, bool adjoint = false, int include_root_freqs
 		ctx->dmma_img_bytes = img_bytes;
 	}
 	ctx->dmma_pack_adjoint = adjoint, ctx->dmma_pack_irf = include_root_freqs;
-	ctx->dmma_pack_tips = tip_images < 0 ? ctx->tip_kind == PHBC_TIP_STATES : tip_images != 0;
+	ctx->dmma_pack_tips = tip_images < 0 ? (ctx->tip_kind == PHBC_TIP_STATES ? 1 : 0) : tip_images;
 	k_dmma_pack<Sh><<<dim3(N, C, 2), 128, 0, ctx->stream>>>(ctx->T, N, C, ctx->root, ctx->dmma_pack_tips, ctx->d_P, ctx->d_dP, ctx->d_dmma_img,
 	                                                         adjoint ? 1 : 0, ctx->d_freqs, include_root_freqs);
 	ctx->launches++;
@@ -1100,9 +1103,9 @@ static int dmma_lower_msg_level(phbc_ctx *ctx, int level) {
 	return 0;
 }
 
-int phbc_dmma_pack_images(phbc_ctx *ctx, bool adjoint, int include_root_freqs, bool tip_images) {
-	if (ctx->S == 20) return dmma_pack<20>(ctx, adjoint, include_root_freqs, tip_images ? 1 : 0);
-	if (ctx->S == 61) return dmma_pack<61>(ctx, adjoint, include_root_freqs, tip_images ? 1 : 0);
+int phbc_dmma_pack_images(phbc_ctx *ctx, bool adjoint, int include_root_freqs, int tip_images) {
+	if (ctx->S == 20) return dmma_pack<20>(ctx, adjoint, include_root_freqs, tip_images);
+	if (ctx->S == 61) return dmma_pack<61>(ctx, adjoint, include_root_freqs, tip_images);
 	return -1;
 }
 int phbc_dmma_pack(phbc_ctx *ctx) {
@@ -1341,7 +1344,7 @@ static int dmma_download(phbc_ctx *ctx, double *P, double *dP) {
 					for (int i = 0; i < S; i++)
 						for (int j = 0; j < S; j++) {
 							if (nd == ctx->root) M[i * S + j] = src[i * Sh::LD + j];
-							else if (tip) M[i * S + j] = src[j * Sh::NP + i];
+							else if (tip) M[i * S + j] = src[j * Sh::NP + i] / ((which == 1 && ctx->dmma_pack_tips == 2 && !ctx->dmma_pack_irf) ? f[i] : 1.0);
 							else if (adj) M[i * S + j] = src[j * Sh::LD + i] / (ctx->dmma_pack_irf ? 1.0 : f[i]);
 							else M[i * S + j] = src[i * Sh::LD + j];
 						}

@@ -24,6 +24,11 @@ struct DmmaShape {
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
 	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
+// the same without `volatile`: a pure function of its operands, so the compiler may schedule independent work between the DMMAs
+__device__ __forceinline__ void dmma_m8n8k4_nv(double &d0, double &d1, double a, double b) {
+	asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 // packed matrix images of every (node, category) on the ctx stream (phb_dmma.cu, k_dmma_pack): `adjoint` stores the dP image of an
-// internal node transposed and frequency-weighted, `tip_images` gives tips the transposed [S + 1][NP] gather layout
-int phbc_dmma_pack_images(phbc_ctx *ctx, bool adjoint, int include_root_freqs, bool tip_images);
+// internal node transposed and frequency-weighted, `tip_images` (1) gives tips the transposed [S + 1][NP] gather layout, (2) with the
+// derivative images frequency-weighted as well
+int phbc_dmma_pack_images(phbc_ctx *ctx, bool adjoint, int include_root_freqs, int tip_images);

@@ -58,6 +58,7 @@ struct DwParams {
 	const void *ops;
 	int nops, T, N, C, P, ntiles, nitems, root;
 	int K, nstg, nw, spill;  // shared-memory slots per warp, ring depth, consumer warps, slots beyond K exist
+	int turns;               // warp pairs of a scheduler take turns on the tensor pipe
 	double *spillbuf;        // [slots - K][C][P][S]
 	const double *freqs, *weights, *pattern_lnl;
 	int include_root_freqs, pstride;
@@ -83,19 +84,24 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void bulk_prefetch_l2(const void *g, uint32_t bytes) {
 	asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
 }
+// red.global.add.f64 when addr is not null, as ONE predicated instruction (no branch: the surrounding DMMAs stay in one basic block)
+__device__ __forceinline__ void red_add_f64_if(double *addr, double v) {
+	asm volatile("{\n.reg .pred p;\nsetp.ne.u64 p, %0, 0;\n@p red.global.add.f64 [%0], %1;\n}" ::"l"(addr), "d"(v) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // shared-memory geometry, the same arithmetic on host and device
-template <int S, int MT>
+template <int S, int MT, int NWMAX_>
 struct DwGeom {
 	using Sh = DmmaShape<S>;
 	static_assert(S % 8 == 4, "row-major tiles of stride S are bank-conflict free (and need no k padding) only for S = 4 (mod 8)");
 	static constexpr int ROWS = MT * 8;                 // pattern rows per warp
 	static constexpr int SLICE = ROWS * S;              // doubles per warp and tile slot
 	static constexpr int IMGB = Sh::IMG * 8;            // bytes per matrix image
-	static constexpr int TPMAX = 8 * ROWS;              // patterns per tile at 8 consumer warps
+	static constexpr int NWMAX = NWMAX_;                // consumer warps of the widest launch
+	static constexpr int TPMAX = NWMAX * ROWS;          // patterns per tile then
 	static constexpr int CODE_OFF = 64, IMG_OFF = CODE_OFF + 2 * TPMAX;
 	static constexpr int HDR = 1024;                    // barriers, frequency vectors
 	__host__ __device__ static constexpr int stage_bytes(int nimg) { return (IMG_OFF + nimg * IMGB + 127) / 128 * 128; }
@@ -141,132 +147,215 @@ __global__ void k_dwalk_codes(int T, int P, int S, int TP, int ntiles, int tip_k
 }
 
 // ---------------------------------------------------------------------------------------------
-// producer warp: stages descriptor, tip codes and matrix images of every op of every item of this CTA
+// Shared-memory plan of both kernels
+//   [0, HDR)        mbarriers (image ring full / empty, landing full / empty), frequency vectors
+//   image ring      nstg stages of { descriptor | tip codes of a, b | matrix images }
+//   tiles           slot-major: tile t = [nw warps][ROWS rows][S], so that a tile is ONE contiguous block of the [pattern][state]
+//                   layout in HBM (tile-wide bulk copies by the producer) and a warp's slice of it is contiguous too (per-warp stores)
 // ---------------------------------------------------------------------------------------------
-template <int S, int MT, bool PRE>
-__device__ __forceinline__ void dwalk_producer(const DwParams &p, unsigned char *smraw, uint64_t *full, uint64_t *empty) {
-	using G = DwGeom<S, MT>;
+struct DwBars {
+	uint64_t imgfull[4], imgempty[4], landfull, landempty;
+	uint64_t turn[8];  // tensor-pipe turns of the warp pairs that share a scheduler: [pair][member]
+};
+
+// The two consumer warps of a scheduler (warps w and w + 4) take TURNS on the tensor pipe: left alone they run in lockstep -- both
+// issue DMMAs at half rate, then both run their scalar epilogue with the pipe idle (ncu: 48 % pipe utilisation, `wait` stalls on
+// every DMMA).  With the turn, one warp's DMMA phase runs at full rate inside the other's epilogue / prologue (the ping-pong
+// schedule of warp-specialised GEMMs).  Member 0 goes first; each side waits for the other's hand-over of the SAME op.
+struct DwTurn {
+	uint64_t *mine, *other;
+	uint32_t ph;
+	bool on;
+	__device__ __forceinline__ void init(DwBars *bars, int warp, int nw, int turns) {
+		on = nw == 8 && turns;  // warps w and w + 4 share a scheduler
+		const int pair = warp & 3, member = warp >> 2;
+		mine = &bars->turn[2 * pair + (member & 1)], other = &bars->turn[2 * pair + ((member & 1) ^ 1)];
+		ph = member == 0 ? 1 : 0;  // member 0's first wait passes on the fresh barrier
+	}
+	__device__ __forceinline__ void acquire() {
+		if (on) {
+			mbar_wait(mine, ph);
+			ph ^= 1;
+		}
+	}
+	__device__ __forceinline__ void release(int lane) {
+		if (on) {
+			__syncwarp();
+			if (lane == 0) mbar_arrive(other);
+		}
+	}
+};
+
+// ---------------------------------------------------------------------------------------------
+// producer warp (one lane): every asynchronous load of the CTA.  Images, codes and the descriptor of op g run nstg - 1 ops ahead
+// through the ring; the pre-order pass also gets the message tiles of the children (and a spilled U) of op h into the single landing
+// buffers as soon as every consumer warp has taken op h - 1's copy into registers (landempty).
+// ---------------------------------------------------------------------------------------------
+template <int S, int MT, int NWM, bool PRE>
+__device__ __forceinline__ void dwalk_producer(const DwParams &p, unsigned char *smraw, DwBars *bars, double *tiles) {
+	using G = DwGeom<S, MT, NWM>;
 	using Sh = DmmaShape<S>;
 	constexpr int NIMG = PRE ? 6 : 3;
 	const int stgb = G::stage_bytes(NIMG);
-	const int TP = p.nw * G::ROWS;
+	const int TP = p.nw * G::ROWS, nstg = p.nstg, LA = nstg - 1;
 	const size_t dimg = (size_t)p.N * p.C * Sh::IMG;
-	int s = 0;
-	uint32_t ph = 1;  // a fresh barrier passes a wait on the phase "before" its first one
-	for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
-		const int tile = item / p.C, c = item - tile * p.C;
-		const uint8_t *codes = p.codes + (size_t)tile * p.T * TP;
-		for (int k = 0; k < p.nops; k++) {
+	const size_t PS = (size_t)p.P * S, CPS = (size_t)p.C * PS;
+	const size_t tile_d = (size_t)p.nw * G::SLICE;  // doubles per tile
+	double *cur = tiles + (size_t)p.K * tile_d, *landA = cur + tile_d, *landB = landA + tile_d;
+	const int nmine = blockIdx.x < p.nitems ? (p.nitems - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+	const long long total = (long long)nmine * p.nops;
+	int s = 0, ik = 0, iitem = blockIdx.x, lk = 0, litem = blockIdx.x;
+	uint32_t eph = 1, lfree = 0;  // a fresh barrier passes a wait on the phase "before" its first one
+	for (long long g = 0; g < total + LA; g++) {
+		if (PRE && g >= LA) {  // landing of op h = g - LA
+			const long long h = g - LA;
+			if (h > 0) {
+				mbar_wait(&bars->landempty, lfree);
+				lfree ^= 1;
+			}
+			const DwPre *d = reinterpret_cast<const DwPre *>(p.ops) + lk;
+			const int kind = d->kind, a_node = d->a_node, b_node = d->b_node;
+			const bool lu = d->u_kind == PHBC_W_SLOT && d->u_slot >= p.K;
+			if (kind >= 1 || lu) {
+				const int tile = litem / p.C, c = litem - tile * p.C;
+				const int p0 = tile * TP;
+				const uint32_t bytes = (uint32_t)min(p.P - p0, TP) * S * 8;
+				const size_t off = (size_t)c * PS + (size_t)p0 * S;
+				mbar_expect_tx(&bars->landfull, ((kind == 2) + (kind >= 1) + (lu ? 1 : 0)) * bytes);
+				if (kind == 2) bulk_g2s(landA, p.lower + (size_t)(a_node - p.T) * CPS + off, bytes, &bars->landfull);
+				if (kind >= 1) bulk_g2s(landB, p.lower + (size_t)(b_node - p.T) * CPS + off, bytes, &bars->landfull);
+				if (lu) bulk_g2s(cur, p.spillbuf + (size_t)(d->u_slot - p.K) * CPS + off, bytes, &bars->landfull);
+			}
+			{  // the tiles of the op DW_PF ops later, hinted into L2 so that their landing is an L2 hit
+				const int tile = litem / p.C, c = litem - tile * p.C, p0 = tile * TP;
+				const uint32_t bytes = (uint32_t)min(p.P - p0, TP) * S * 8;
+				const size_t off = (size_t)c * PS + (size_t)p0 * S;
+				if (d->pf_a >= 0) bulk_prefetch_l2(p.lower + (size_t)(d->pf_a - p.T) * CPS + off, bytes);
+				if (d->pf_b >= 0) bulk_prefetch_l2(p.lower + (size_t)(d->pf_b - p.T) * CPS + off, bytes);
+			}
+			if (++lk == p.nops) lk = 0, litem += gridDim.x;
+		}
+		if (g < total) {  // ring stage of op g
+			const int tile = iitem / p.C, c = iitem - tile * p.C;
+			const uint8_t *codes = p.codes + (size_t)tile * p.T * TP;
 			unsigned char *stg = smraw + G::HDR + (size_t)s * stgb;
 			double *im = reinterpret_cast<double *>(stg + G::IMG_OFF);
-			mbar_wait(&empty[s], ph);
+			mbar_wait(&bars->imgempty[s], eph);
 			if (PRE) {
-				const DwPre *d = reinterpret_cast<const DwPre *>(p.ops) + k;
+				const DwPre *d = reinterpret_cast<const DwPre *>(p.ops) + ik;
 				const int node = d->node, a_node = d->a_node, b_node = d->b_node, a_tip = d->a_tip, b_tip = d->b_tip;
 				const bool root = d->u_kind == PHBC_W_ROOT;
 				const int nimg = (root ? 0 : 2) + (a_tip >= 0 ? 2 : 0) + (b_tip >= 0 ? 2 : 0);
-				mbar_expect_tx(&full[s], (uint32_t)(sizeof(DwPre) + nimg * G::IMGB + ((a_tip >= 0) + (b_tip >= 0)) * TP));
-				bulk_g2s(stg, d, sizeof(DwPre), &full[s]);
+				mbar_expect_tx(&bars->imgfull[s], (uint32_t)(sizeof(DwPre) + nimg * G::IMGB + ((a_tip >= 0) + (b_tip >= 0)) * TP));
+				bulk_g2s(stg, d, sizeof(DwPre), &bars->imgfull[s]);
 				if (!root) {
-					bulk_g2s(im, p.img + ((size_t)node * p.C + c) * Sh::IMG, G::IMGB, &full[s]);
-					bulk_g2s(im + Sh::IMG, p.img + dimg + ((size_t)node * p.C + c) * Sh::IMG, G::IMGB, &full[s]);
+					bulk_g2s(im, p.img + ((size_t)node * p.C + c) * Sh::IMG, G::IMGB, &bars->imgfull[s]);
+					bulk_g2s(im + Sh::IMG, p.img + dimg + ((size_t)node * p.C + c) * Sh::IMG, G::IMGB, &bars->imgfull[s]);
 				}
 				if (a_tip >= 0) {
-					bulk_g2s(im + 2 * Sh::IMG, p.img + ((size_t)a_node * p.C + c) * Sh::IMG, G::IMGB, &full[s]);
-					bulk_g2s(im + 3 * Sh::IMG, p.img + dimg + ((size_t)a_node * p.C + c) * Sh::IMG, G::IMGB, &full[s]);
-					bulk_g2s(stg + G::CODE_OFF, codes + (size_t)a_tip * TP, TP, &full[s]);
+					bulk_g2s(im + 2 * Sh::IMG, p.img + ((size_t)a_node * p.C + c) * Sh::IMG, G::IMGB, &bars->imgfull[s]);
+					bulk_g2s(im + 3 * Sh::IMG, p.img + dimg + ((size_t)a_node * p.C + c) * Sh::IMG, G::IMGB, &bars->imgfull[s]);
+					bulk_g2s(stg + G::CODE_OFF, codes + (size_t)a_tip * TP, TP, &bars->imgfull[s]);
 				}
 				if (b_tip >= 0) {
-					bulk_g2s(im + 4 * Sh::IMG, p.img + ((size_t)b_node * p.C + c) * Sh::IMG, G::IMGB, &full[s]);
-					bulk_g2s(im + 5 * Sh::IMG, p.img + dimg + ((size_t)b_node * p.C + c) * Sh::IMG, G::IMGB, &full[s]);
-					bulk_g2s(stg + G::CODE_OFF + G::TPMAX, codes + (size_t)b_tip * TP, TP, &full[s]);
+					bulk_g2s(im + 4 * Sh::IMG, p.img + ((size_t)b_node * p.C + c) * Sh::IMG, G::IMGB, &bars->imgfull[s]);
+					bulk_g2s(im + 5 * Sh::IMG, p.img + dimg + ((size_t)b_node * p.C + c) * Sh::IMG, G::IMGB, &bars->imgfull[s]);
+					bulk_g2s(stg + G::CODE_OFF + G::TPMAX, codes + (size_t)b_tip * TP, TP, &bars->imgfull[s]);
 				}
 			} else {
-				const DwPost *d = reinterpret_cast<const DwPost *>(p.ops) + k;
+				const DwPost *d = reinterpret_cast<const DwPost *>(p.ops) + ik;
 				const int node = d->node, a_node = d->a_node, b_node = d->b_node, a_tip = d->a_tip, b_tip = d->b_tip;
 				const int nimg = 1 + (a_tip >= 0) + (b_tip >= 0);
-				mbar_expect_tx(&full[s], (uint32_t)(sizeof(DwPost) + nimg * G::IMGB + ((a_tip >= 0) + (b_tip >= 0)) * TP));
-				bulk_g2s(stg, d, sizeof(DwPost), &full[s]);
-				bulk_g2s(im, p.img + ((size_t)node * p.C + c) * Sh::IMG, G::IMGB, &full[s]);
+				mbar_expect_tx(&bars->imgfull[s], (uint32_t)(sizeof(DwPost) + nimg * G::IMGB + ((a_tip >= 0) + (b_tip >= 0)) * TP));
+				bulk_g2s(stg, d, sizeof(DwPost), &bars->imgfull[s]);
+				bulk_g2s(im, p.img + ((size_t)node * p.C + c) * Sh::IMG, G::IMGB, &bars->imgfull[s]);
 				if (a_tip >= 0) {
-					bulk_g2s(im + Sh::IMG, p.img + ((size_t)a_node * p.C + c) * Sh::IMG, G::IMGB, &full[s]);
-					bulk_g2s(stg + G::CODE_OFF, codes + (size_t)a_tip * TP, TP, &full[s]);
+					bulk_g2s(im + Sh::IMG, p.img + ((size_t)a_node * p.C + c) * Sh::IMG, G::IMGB, &bars->imgfull[s]);
+					bulk_g2s(stg + G::CODE_OFF, codes + (size_t)a_tip * TP, TP, &bars->imgfull[s]);
 				}
 				if (b_tip >= 0) {
-					bulk_g2s(im + 2 * Sh::IMG, p.img + ((size_t)b_node * p.C + c) * Sh::IMG, G::IMGB, &full[s]);
-					bulk_g2s(stg + G::CODE_OFF + G::TPMAX, codes + (size_t)b_tip * TP, TP, &full[s]);
+					bulk_g2s(im + 2 * Sh::IMG, p.img + ((size_t)b_node * p.C + c) * Sh::IMG, G::IMGB, &bars->imgfull[s]);
+					bulk_g2s(stg + G::CODE_OFF + G::TPMAX, codes + (size_t)b_tip * TP, TP, &bars->imgfull[s]);
 				}
 			}
-			if (++s == p.nstg) s = 0, ph ^= 1;
+			if (++s == nstg) s = 0, eph ^= 1;
+			if (++ik == p.nops) ik = 0, iitem += gridDim.x;
 		}
 	}
 }
 
-// D-layout accumulators (row 8 m + r, columns 8 j + 2 q, + 1) to a row-major tile slice; padding columns are dropped
+// D-layout accumulators (row 8 m + r, columns 8 j + 2 q, + 1) to this lane's places of a row-major slice (`at` = slice + r S + 2 q);
+// padding columns are dropped
 template <int S, int MT>
-__device__ __forceinline__ void dw_store_slice(double *slice, int r, int q, const double (&v)[MT][DmmaShape<S>::NT][2]) {
+__device__ __forceinline__ void dw_store_slice(double *at, int q, const double (&v)[MT][DmmaShape<S>::NT][2]) {
 #pragma unroll
 	for (int m = 0; m < MT; m++)
 #pragma unroll
-		for (int j = 0; j < DmmaShape<S>::NT; j++) {
-			const int col = 8 * j + 2 * q;
-			if (col < S) *reinterpret_cast<double2 *>(slice + (8 * m + r) * S + col) = make_double2(v[m][j][0], v[m][j][1]);
-		}
+		for (int j = 0; j < DmmaShape<S>::NT; j++)
+			if (8 * j + 6 < S || 8 * j + 2 * q < S) *reinterpret_cast<double2 *>(at + 8 * m * S + 8 * j) = make_double2(v[m][j][0], v[m][j][1]);
 }
 
 // ---------------------------------------------------------------------------------------------
 // post-order pass
 // ---------------------------------------------------------------------------------------------
-template <int S, int MT>
-__global__ void __launch_bounds__(288, 1) k_dwalk_post(const DwParams p) {
-	using G = DwGeom<S, MT>;
+template <int S, int MT, int NWM>
+__global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_post(const DwParams p) {
+	using G = DwGeom<S, MT, NWM>;
 	using Sh = DmmaShape<S>;
 	extern __shared__ __align__(128) unsigned char smraw[];
-	uint64_t *full = reinterpret_cast<uint64_t *>(smraw), *empty = full + 8, *lbar = full + 16;
+	DwBars *bars = reinterpret_cast<DwBars *>(smraw);
+	uint64_t *lbar = reinterpret_cast<uint64_t *>(smraw + 256);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int nw = p.nw, nstg = p.nstg, K = p.K;
 	const int stgb = G::stage_bytes(3);
-	const int nslice = K + 2 + (p.spill ? 1 : 0);
+	const int ntile = K + 2 + (p.spill ? 1 : 0);
+	const size_t tile_d = (size_t)nw * G::SLICE;
 	double *tiles = reinterpret_cast<double *>(smraw + G::HDR + (size_t)nstg * stgb);
 	if (threadIdx.x == 0) {
-		for (int i = 0; i < nstg; i++) mbar_init(&full[i], 1), mbar_init(&empty[i], nw);
+		for (int i = 0; i < nstg; i++) mbar_init(&bars->imgfull[i], 1), mbar_init(&bars->imgempty[i], nw);
 		for (int w = 0; w < nw; w++) mbar_init(&lbar[w], 1);
+		for (int i = 0; i < 8; i++) mbar_init(&bars->turn[i], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	for (int i = threadIdx.x; i < nw * nslice * G::SLICE; i += blockDim.x) tiles[i] = 0.0;  // rows past P keep finite values
+	for (int i = threadIdx.x; i < ntile * (int)tile_d; i += blockDim.x) tiles[i] = 0.0;  // rows past P keep finite values
 	__syncthreads();
 	if (warp == nw) {
-		if (lane == 0) dwalk_producer<S, MT, false>(p, smraw, full, empty);
+		if (lane == 0) dwalk_producer<S, MT, NWM, false>(p, smraw, bars, tiles);
 		return;
 	}
 	const int r = lane >> 2, q = lane & 3;
-	double *mine = tiles + (size_t)warp * nslice * G::SLICE;
-	double *cur0 = mine + (size_t)K * G::SLICE, *cur1 = cur0 + G::SLICE, *land = cur1 + G::SLICE;
+	double *mine = tiles + (size_t)warp * G::SLICE;  // this warp's slice of tile 0
+	double *cur0 = mine + (size_t)K * tile_d, *cur1 = cur0 + tile_d, *land = cur1 + tile_d;
 	const int TP = nw * G::ROWS;
-	const size_t PS = (size_t)p.P * S;
+	const size_t PS = (size_t)p.P * S, CPS = (size_t)p.C * PS;
+	const int lofA = r * S + q, lofD = r * S + 2 * q;  // this lane's place in a slice, A-fragment / accumulator layout
+	const int bof = r * Sh::LD + q;
 	int s = 0, cb = 0;
 	uint32_t ph = 0, lph = 0;
+	DwTurn turn;
+	turn.init(bars, warp, nw, p.turns);
 	for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
 		const int tile = item / p.C, c = item - tile * p.C;
 		const int p0 = tile * TP + warp * G::ROWS;
 		const int rows = min(max(p.P - p0, 0), G::ROWS);
 		const uint32_t rbytes = (uint32_t)rows * S * 8;
+		double *rowbase = p.lower + (size_t)c * PS + (size_t)p0 * S;  // + (node - T) CPS
 		for (int k = 0; k < p.nops; k++) {
 			const unsigned char *stg = smraw + G::HDR + (size_t)s * stgb;
-			mbar_wait(&full[s], ph);
+			mbar_wait(&bars->imgfull[s], ph);
 			const DwPost *d = reinterpret_cast<const DwPost *>(stg);
 			const int kind = d->kind, a_slot = d->a_slot, dst_slot = d->dst_slot, node = d->node, a_node = d->a_node;  // the stage is recycled after the arrive below
 			const double *mN = reinterpret_cast<const double *>(stg + G::IMG_OFF), *mA = mN + Sh::IMG, *mB = mA + Sh::IMG;
 			const double *prev = cb ? cur1 : cur0;
 			const double *ta = prev;
 			if (kind == 2) {
-				if (a_slot < K) ta = mine + (size_t)a_slot * G::SLICE;
-				else {  // parked beyond the shared-memory slots: its message row is in HBM already
+				ta = mine + (size_t)a_slot * tile_d;
+				if (a_slot >= K) {  // parked beyond the shared-memory slots: its message row is in HBM already
 					if (rows > 0) {
 						if (lane == 0) {
 							bulk_wait_all<0>();  // the row was written by this thread's own bulk store
 							mbar_expect_tx(&lbar[warp], rbytes);
-							bulk_g2s(land, p.lower + ((size_t)(a_node - p.T) * p.C + c) * PS + (size_t)p0 * S, rbytes, &lbar[warp]);
+							bulk_g2s(land, rowbase + (size_t)(a_node - p.T) * CPS, rbytes, &lbar[warp]);
 						}
 						mbar_wait(&lbar[warp], lph);
 						lph ^= 1;
@@ -274,20 +363,15 @@ __global__ void __launch_bounds__(288, 1) k_dwalk_post(const DwParams p) {
 					ta = land;
 				}
 			}
-			// A fragments: L_n = M_a o M_b
+			// A fragments: L_n = M_a o M_b; an operand is a row of a tile slice or the column a tip's state selects in its image
 			double a[MT][Sh::KT];
 #pragma unroll
 			for (int m = 0; m < MT; m++) {
-				const int row = 8 * m + r;
-				const int sa = kind < 2 ? stg[G::CODE_OFF + warp * G::ROWS + row] : 0;
-				const int sb = kind == 0 ? stg[G::CODE_OFF + G::TPMAX + warp * G::ROWS + row] : 0;
+				const int row = warp * G::ROWS + 8 * m + r;
+				const double *pa = kind < 2 ? mA + stg[G::CODE_OFF + row] * Sh::NP + q : ta + lofA + 8 * m * S;
+				const double *pb = kind == 0 ? mB + stg[G::CODE_OFF + G::TPMAX + row] * Sh::NP + q : prev + lofA + 8 * m * S;
 #pragma unroll
-				for (int tt = 0; tt < Sh::KT; tt++) {
-					const int col = 4 * tt + q;
-					const double va = kind < 2 ? mA[sa * Sh::NP + col] : ta[row * S + col];
-					const double vb = kind == 0 ? mB[sb * Sh::NP + col] : prev[row * S + col];
-					a[m][tt] = va * vb;
-				}
+				for (int tt = 0; tt < Sh::KT; tt++) a[m][tt] = pa[4 * tt] * pb[4 * tt];
 			}
 			// M_n = L_n P_n^T
 			double acc[MT][Sh::NT][2];
@@ -295,30 +379,31 @@ __global__ void __launch_bounds__(288, 1) k_dwalk_post(const DwParams p) {
 			for (int m = 0; m < MT; m++)
 #pragma unroll
 				for (int j = 0; j < Sh::NT; j++) acc[m][j][0] = acc[m][j][1] = 0.0;
-			double bN = mN[r * Sh::LD + q];
+			turn.acquire();
 #pragma unroll
 			for (int tt = 0; tt < Sh::KT; tt++)
 #pragma unroll
 				for (int j = 0; j < Sh::NT; j++) {
-					const int nj = j + 1 < Sh::NT ? j + 1 : 0, nt = j + 1 < Sh::NT ? tt : (tt + 1 < Sh::KT ? tt + 1 : 0);
-					const double nN = mN[(nj * 8 + r) * Sh::LD + 4 * nt + q];
+					const double bN = mN[bof + j * 8 * Sh::LD + 4 * tt];
 #pragma unroll
 					for (int m = 0; m < MT; m++) dmma_m8n8k4(acc[m][j][0], acc[m][j][1], a[m][tt], bN);
-					bN = nN;
 				}
 			__syncwarp();
-			if (lane == 0) mbar_arrive(&empty[s]);  // images and codes of this op are consumed
+			if (lane == 0) {
+				if (turn.on) mbar_arrive(turn.other);
+				mbar_arrive(&bars->imgempty[s]);
+			}  // the pipe goes to the partner; images and codes of this op are consumed
 			// result: parked slot or the other hand-over buffer, then to HBM from there
 			double *dst;
-			if (dst_slot >= 0 && dst_slot < K) dst = mine + (size_t)dst_slot * G::SLICE;
+			if (dst_slot >= 0 && dst_slot < K) dst = mine + (size_t)dst_slot * tile_d;
 			else dst = cb ? cur0 : cur1, cb ^= 1;
 			if (lane == 0) bulk_wait_read<1>();  // every store but the preceding op's has left shared memory
 			__syncwarp();
-			dw_store_slice<S, MT>(dst, r, q, acc);
+			dw_store_slice<S, MT>(dst + lofD, q, acc);
 			fence_async_smem();
 			__syncwarp();
 			if (lane == 0 && rows > 0) {
-				bulk_s2g(p.lower + ((size_t)(node - p.T) * p.C + c) * PS + (size_t)p0 * S, dst, rbytes);
+				bulk_s2g(rowbase + (size_t)(node - p.T) * CPS, dst, rbytes);
 				bulk_commit();
 			}
 			if (++s == nstg) s = 0, ph ^= 1;
@@ -330,66 +415,51 @@ __global__ void __launch_bounds__(288, 1) k_dwalk_post(const DwParams p) {
 // ---------------------------------------------------------------------------------------------
 // pre-order pass with branch gradients
 // ---------------------------------------------------------------------------------------------
-template <int S, int MT>
-__global__ void __launch_bounds__(288, 1) k_dwalk_pre(const DwParams p) {
-	using G = DwGeom<S, MT>;
+template <int S, int MT, int NWM>
+__global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_pre(const DwParams p) {
+	using G = DwGeom<S, MT, NWM>;
 	using Sh = DmmaShape<S>;
 	extern __shared__ __align__(128) unsigned char smraw[];
-	uint64_t *full = reinterpret_cast<uint64_t *>(smraw), *empty = full + 8, *lbar = full + 16;
-	double *fq = reinterpret_cast<double *>(smraw + 256), *wroot = fq + Sh::NP;
+	DwBars *bars = reinterpret_cast<DwBars *>(smraw);
+	double *fq = reinterpret_cast<double *>(smraw + 256), *wroot = fq + Sh::NP, *zeros = wroot + Sh::NP;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int nw = p.nw, nstg = p.nstg, K = p.K;
 	const int stgb = G::stage_bytes(6);
-	const int nslice = K + 3 + (p.spill ? 1 : 0);
+	const int ntile = K + 3 + (p.spill ? 1 : 0);
+	const size_t tile_d = (size_t)nw * G::SLICE;
 	double *tiles = reinterpret_cast<double *>(smraw + G::HDR + (size_t)nstg * stgb);
 	if (threadIdx.x == 0) {
-		for (int i = 0; i < nstg; i++) mbar_init(&full[i], 1), mbar_init(&empty[i], nw);
-		for (int w = 0; w < nw; w++) mbar_init(&lbar[w], 1);
+		for (int i = 0; i < nstg; i++) mbar_init(&bars->imgfull[i], 1), mbar_init(&bars->imgempty[i], nw);
+		mbar_init(&bars->landfull, 1), mbar_init(&bars->landempty, nw);
+		for (int i = 0; i < 8; i++) mbar_init(&bars->turn[i], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	for (int i = threadIdx.x; i < Sh::NP; i += blockDim.x) {
 		const double f = i < S ? p.freqs[i] : 0.0;
 		fq[i] = i < S ? (p.include_root_freqs ? 1.0 : f) : 0.0;
 		wroot[i] = i < S ? (p.include_root_freqs ? f : 1.0) : 0.0;
+		zeros[i] = 0.0;
 	}
-	for (int i = threadIdx.x; i < nw * nslice * G::SLICE; i += blockDim.x) tiles[i] = 0.0;
+	for (int i = threadIdx.x; i < ntile * (int)tile_d; i += blockDim.x) tiles[i] = 0.0;
 	__syncthreads();
 	if (warp == nw) {
-		if (lane == 0) dwalk_producer<S, MT, true>(p, smraw, full, empty);
+		if (lane == 0) dwalk_producer<S, MT, NWM, true>(p, smraw, bars, tiles);
 		return;
 	}
 	const int r = lane >> 2, q = lane & 3;
-	double *mine = tiles + (size_t)warp * nslice * G::SLICE;
-	double *cur = mine + (size_t)K * G::SLICE, *landA = cur + G::SLICE, *landB = landA + G::SLICE, *stage_out = landB + G::SLICE;
+	double *mine = tiles + (size_t)warp * G::SLICE;
+	double *cur = mine + (size_t)K * tile_d, *landA = cur + tile_d, *landB = landA + tile_d, *stage_out = landB + tile_d;
 	const int TP = nw * G::ROWS;
 	const size_t PS = (size_t)p.P * S, CPS = (size_t)p.C * PS;
+	const int lofA = r * S + q, lofD = r * S + 2 * q;
+	const int bof = r * Sh::LD + q;
 	int s = 0;
 	uint32_t ph = 0, lph = 0;
+	DwTurn turn;
+	turn.init(bars, warp, nw, p.turns);
+	double pend_n = 0.0, pend_a = 0.0, pend_b = 0.0;  // the preceding op's per-lane branch sums and where they go
+	double *pend_tn = nullptr, *pend_ta = nullptr, *pend_tb = nullptr;
 	double *grow = p.gacc + (size_t)blockIdx.x * nw + warp;
-
-	// message rows (and a spilled U) of op d for (c, p0): one bulk load each into the landing slices, one mbarrier phase for all
-	auto issue_loads = [&](const DwPre *d, int c, int p0, uint32_t rbytes) -> bool {
-		const bool la = d->kind == 2, lb = d->kind >= 1, lu = d->u_kind == PHBC_W_SLOT && d->u_slot >= K;
-		if (!(la || lb || lu) || rbytes == 0) return false;
-		if (lane == 0) {
-			if (lu) bulk_wait_all<0>();  // the spilled row was written by this thread's own bulk store
-			mbar_expect_tx(&lbar[warp], ((la ? 1u : 0u) + (lb ? 1u : 0u) + (lu ? 1u : 0u)) * rbytes);
-			if (la) bulk_g2s(landA, p.lower + ((size_t)(d->a_node - p.T) * p.C + c) * PS + (size_t)p0 * S, rbytes, &lbar[warp]);
-			if (lb) bulk_g2s(landB, p.lower + ((size_t)(d->b_node - p.T) * p.C + c) * PS + (size_t)p0 * S, rbytes, &lbar[warp]);
-			if (lu) bulk_g2s(cur, p.spillbuf + (size_t)(d->u_slot - K) * CPS + (size_t)c * PS + (size_t)p0 * S, rbytes, &lbar[warp]);
-		}
-		return true;
-	};
-
-	bool armed = false;
-	{  // loads of the first op of the first item (the descriptor comes from global memory: its stage may not have landed)
-		const int item = blockIdx.x;
-		if (item < p.nitems) {
-			const int tile = item / p.C, c = item - tile * p.C, p0 = tile * TP + warp * G::ROWS;
-			const int rows = min(max(p.P - p0, 0), G::ROWS);
-			armed = issue_loads(reinterpret_cast<const DwPre *>(p.ops), c, p0, (uint32_t)rows * S * 8);
-		}
-	}
 	for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
 		const int tile = item / p.C, c = item - tile * p.C;
 		const int p0 = tile * TP + warp * G::ROWS;
@@ -401,150 +471,167 @@ __global__ void __launch_bounds__(288, 1) k_dwalk_pre(const DwParams p) {
 			const int pp = p0 + 8 * m + r;
 			wl[m] = pp < p.P ? __ldg(p.weights + pp) / exp(__ldg(p.pattern_lnl + pp)) : 0.0;
 		}
+		double *gitem = grow + (size_t)c * p.pstride;  // + node C pstride
 		for (int k = 0; k < p.nops; k++) {
 			const unsigned char *stg = smraw + G::HDR + (size_t)s * stgb;
-			mbar_wait(&full[s], ph);
+			mbar_wait(&bars->imgfull[s], ph);
 			const DwPre *d = reinterpret_cast<const DwPre *>(stg);
 			const int kind = d->kind, u_kind = d->u_kind, u_slot = d->u_slot, a_slot = d->a_slot;
-			const int node = d->node, a_node = d->a_node, b_node = d->b_node, pf_a = d->pf_a, pf_b = d->pf_b;  // the stage is recycled after the arrive below
+			const int node = d->node, a_node = d->a_node, b_node = d->b_node;  // the stage is recycled after the arrive below
 			const bool root = u_kind == PHBC_W_ROOT;
+			const bool lu = u_kind == PHBC_W_SLOT && u_slot >= K;
 			const double *mP = reinterpret_cast<const double *>(stg + G::IMG_OFF), *mZ = mP + Sh::IMG;
 			const double *tA = mZ + Sh::IMG, *dA = tA + Sh::IMG, *tB = dA + Sh::IMG, *dB = tB + Sh::IMG;
-			if (armed) {
-				mbar_wait(&lbar[warp], lph);
+			if (kind >= 1 || lu) {  // the same condition the producer armed the landing barrier on
+				mbar_wait(&bars->landfull, lph);
 				lph ^= 1;
 			}
 			// A fragments of U_n
-			const double *usrc = (u_kind == PHBC_W_SLOT && u_slot < K) ? mine + (size_t)u_slot * G::SLICE : cur;
+			const double *usrc = ((u_kind == PHBC_W_SLOT && u_slot < K) ? mine + (size_t)u_slot * tile_d : cur) + lofA;
 			double u[MT][Sh::KT];
-			if (!root) {
-#pragma unroll
-				for (int m = 0; m < MT; m++)
-#pragma unroll
-					for (int tt = 0; tt < Sh::KT; tt++) u[m][tt] = usrc[(8 * m + r) * S + 4 * tt + q];
-			}
-			// the children's messages in accumulator layout
-			int sa[MT], sb[MT];
-#pragma unroll
-			for (int m = 0; m < MT; m++) {
-				sa[m] = kind < 2 ? stg[G::CODE_OFF + warp * G::ROWS + 8 * m + r] : 0;
-				sb[m] = kind == 0 ? stg[G::CODE_OFF + G::TPMAX + warp * G::ROWS + 8 * m + r] : 0;
-			}
-			double Ma[MT][Sh::NT][2], Mb[MT][Sh::NT][2];
 #pragma unroll
 			for (int m = 0; m < MT; m++)
 #pragma unroll
+				for (int tt = 0; tt < Sh::KT; tt++) u[m][tt] = usrc[8 * m * S + 4 * tt];
+			// the children's messages in accumulator layout: a row of the landing tile, or the column a tip's state selects
+			int sa[MT], sb[MT];
+			double Ma[MT][Sh::NT][2], Mb[MT][Sh::NT][2];
+#pragma unroll
+			for (int m = 0; m < MT; m++) {
+				const int row = warp * G::ROWS + 8 * m + r;
+				sa[m] = stg[G::CODE_OFF + row] * Sh::NP + 2 * q;
+				sb[m] = stg[G::CODE_OFF + G::TPMAX + row] * Sh::NP + 2 * q;
+				const double *pa = kind < 2 ? tA + sa[m] : landA + lofD + 8 * m * S;
+				const double *pb = kind == 0 ? tB + sb[m] : landB + lofD + 8 * m * S;
+#pragma unroll
 				for (int j = 0; j < Sh::NT; j++) {
-					const int col = 8 * j + 2 * q;
 					double2 va = make_double2(0.0, 0.0), vb = va;
-					if (col < S) {
-						va = *reinterpret_cast<const double2 *>(kind < 2 ? tA + sa[m] * Sh::NP + col : landA + (8 * m + r) * S + col);
-						vb = *reinterpret_cast<const double2 *>(kind == 0 ? tB + sb[m] * Sh::NP + col : landB + (8 * m + r) * S + col);
+					if (8 * j + 6 < S || 8 * j + 2 * q < S) {
+						va = *reinterpret_cast<const double2 *>(pa + 8 * j);
+						vb = *reinterpret_cast<const double2 *>(pb + 8 * j);
 					}
 					Ma[m][j][0] = va.x, Ma[m][j][1] = va.y;
 					Mb[m][j][0] = vb.x, Mb[m][j][1] = vb.y;
 				}
-			__syncwarp();  // every lane has read the landing slices and the hand-over buffer
-			{  // rows of the next op (of the next item after the last op), and an L2 hint DW_PF ops ahead
-				int nitem = item, nk = k + 1, ns = s + 1 == nstg ? 0 : s + 1;
-				uint32_t nph = s + 1 == nstg ? ph ^ 1 : ph;
-				if (nk == p.nops) nk = 0, nitem = item + gridDim.x;
-				armed = false;
-				if (nitem < p.nitems) {
-					mbar_wait(&full[ns], nph);
-					const DwPre *nd = reinterpret_cast<const DwPre *>(smraw + G::HDR + (size_t)ns * stgb);
-					const int ntile = nitem / p.C, nc = nitem - ntile * p.C, np0 = ntile * TP + warp * G::ROWS;
-					const int nrows = min(max(p.P - np0, 0), G::ROWS);
-					armed = issue_loads(nd, nc, np0, (uint32_t)nrows * S * 8);
-				}
-				if (lane == 0 && rbytes) {
-					if (pf_a >= 0) bulk_prefetch_l2(p.lower + ((size_t)(pf_a - p.T) * p.C + c) * PS + (size_t)p0 * S, rbytes);
-					if (pf_b >= 0) bulk_prefetch_l2(p.lower + ((size_t)(pf_b - p.T) * p.C + c) * PS + (size_t)p0 * S, rbytes);
-				}
-			}
-			// W = U_n P_n^T, Z = U_n (pi o dP_n)
-			double W[MT][Sh::NT][2], Z[MT][Sh::NT][2];
-#pragma unroll
-			for (int m = 0; m < MT; m++)
-#pragma unroll
-				for (int j = 0; j < Sh::NT; j++) W[m][j][0] = W[m][j][1] = Z[m][j][0] = Z[m][j][1] = 0.0;
-			if (!root) {
-				double bP = mP[r * Sh::LD + q], bZ = mZ[r * Sh::LD + q];
-#pragma unroll
-				for (int tt = 0; tt < Sh::KT; tt++)
-#pragma unroll
-					for (int j = 0; j < Sh::NT; j++) {
-						const int nj = j + 1 < Sh::NT ? j + 1 : 0, nt = j + 1 < Sh::NT ? tt : (tt + 1 < Sh::KT ? tt + 1 : 0);
-						const int noff = (nj * 8 + r) * Sh::LD + 4 * nt + q;
-						const double nP = mP[noff], nZ = mZ[noff];
-#pragma unroll
-						for (int m = 0; m < MT; m++) {
-							dmma_m8n8k4(W[m][j][0], W[m][j][1], u[m][tt], bP);
-							dmma_m8n8k4(Z[m][j][0], Z[m][j][1], u[m][tt], bZ);
-						}
-						bP = nP, bZ = nZ;
-					}
-			} else {
-#pragma unroll
-				for (int m = 0; m < MT; m++)
-#pragma unroll
-					for (int j = 0; j < Sh::NT; j++) W[m][j][0] = wroot[8 * j + 2 * q], W[m][j][1] = wroot[8 * j + 2 * q + 1];
-			}
-			// n's own branch (adjoint form), U_a = W o M_b, U_b = W o M_a, the branches of tip children
-			double gn = 0.0, ga = 0.0, gb = 0.0;
-#pragma unroll
-			for (int m = 0; m < MT; m++) {
-				double g0 = 0.0, g1 = 0.0, g2 = 0.0;
-#pragma unroll
-				for (int j = 0; j < Sh::NT; j++) {
-					const int col = 8 * j + 2 * q;
-					g0 = fma(Ma[m][j][0] * Mb[m][j][0], Z[m][j][0], fma(Ma[m][j][1] * Mb[m][j][1], Z[m][j][1], g0));
-					const double ua0 = W[m][j][0] * Mb[m][j][0], ua1 = W[m][j][1] * Mb[m][j][1];
-					const double ub0 = W[m][j][0] * Ma[m][j][0], ub1 = W[m][j][1] * Ma[m][j][1];
-					if (kind < 2 && col < S) {
-						const double2 da = *reinterpret_cast<const double2 *>(dA + sa[m] * Sh::NP + col);
-						g1 = fma(fq[col] * ua0, da.x, fma(fq[col + 1] * ua1, da.y, g1));
-					}
-					if (kind == 0 && col < S) {
-						const double2 db = *reinterpret_cast<const double2 *>(dB + sb[m] * Sh::NP + col);
-						g2 = fma(fq[col] * ub0, db.x, fma(fq[col + 1] * ub1, db.y, g2));
-					}
-					Mb[m][j][0] = ua0, Mb[m][j][1] = ua1;
-					Ma[m][j][0] = ub0, Ma[m][j][1] = ub1;
-				}
-				const bool live = p0 + 8 * m + r < p.P;
-				gn = live ? fma(g0, wl[m], gn) : gn;
-				ga = live ? fma(g1, wl[m], ga) : ga;
-				gb = live ? fma(g2, wl[m], gb) : gb;
 			}
 			__syncwarp();
-			if (lane == 0) mbar_arrive(&empty[s]);  // images and codes of this op are consumed
-			if (kind >= 1) dw_store_slice<S, MT>(cur, r, q, Ma);  // U_b: child b's op is the next one
+			if (lane == 0) mbar_arrive(&bars->landempty);  // landing tiles and the hand-over buffer are in registers: the next op's may land
+			// the derivative columns of tip children (a zero vector for internal ones: their branches are reduced at their own ops)
+			const double *pda[MT], *pdb[MT];
+#pragma unroll
+			for (int m = 0; m < MT; m++) pda[m] = kind < 2 ? dA + sa[m] : zeros + 2 * q, pdb[m] = kind == 0 ? dB + sb[m] : zeros + 2 * q;
+			turn.acquire();
+			// W = U_n P_n^T and Z = U_n (pi o dP_n), one n-tile at a time (four accumulator chains in flight); the element-wise work of a
+			// finished tile -- n's own branch sum_j L[j] Z[j] (adjoint form), U_a = W o M_b, U_b = W o M_a, the tips' branches -- is issued
+			// under the NEXT tile's DMMAs, and so is the shuffle chain that sums the PREVIOUS op's three branch terms over the warp: the
+			// FP64 pipe serves both kinds of work, and outside this warp's turn it belongs to the partner's DMMAs.
+			// Butterfly: lanes 16.. take over (ga, gb), lanes ..15 (gn, 0), then halves again; lane 0 ends with gn, lane 16 ga, lane 24 gb --
+			// one value per branch and warp, added to this warp's own rows (fixed order: deterministic).
+			double g0[MT], g1[MT], g2[MT];
+#pragma unroll
+			for (int m = 0; m < MT; m++) g0[m] = g1[m] = g2[m] = 0.0;
+			auto tile_dmma = [&](int j, double (&W)[MT][2], double (&Z)[MT][2]) {
+#pragma unroll
+				for (int m = 0; m < MT; m++) W[m][0] = W[m][1] = Z[m][0] = Z[m][1] = 0.0;
+#pragma unroll
+				for (int tt = 0; tt < Sh::KT; tt++) {
+					const double bP = mP[bof + j * 8 * Sh::LD + 4 * tt], bZ = mZ[bof + j * 8 * Sh::LD + 4 * tt];
+#pragma unroll
+					for (int m = 0; m < MT; m++) {
+						dmma_m8n8k4(W[m][0], W[m][1], u[m][tt], bP);
+						dmma_m8n8k4(Z[m][0], Z[m][1], u[m][tt], bZ);
+					}
+				}
+			};
+			auto combine = [&](int j, const double (&W)[MT][2], const double (&Z)[MT][2]) {
+				const bool colok = 8 * j + 6 < S || 8 * j + 2 * q < S;
+#pragma unroll
+				for (int m = 0; m < MT; m++) {
+					g0[m] = fma(Ma[m][j][0] * Mb[m][j][0], Z[m][0], fma(Ma[m][j][1] * Mb[m][j][1], Z[m][1], g0[m]));
+					const double ua0 = W[m][0] * Mb[m][j][0], ua1 = W[m][1] * Mb[m][j][1];
+					const double ub0 = W[m][0] * Ma[m][j][0], ub1 = W[m][1] * Ma[m][j][1];
+					Mb[m][j][0] = ua0, Mb[m][j][1] = ua1;
+					Ma[m][j][0] = ub0, Ma[m][j][1] = ub1;
+					const double2 da = *reinterpret_cast<const double2 *>((colok ? pda[m] : zeros) + 8 * j);
+					const double2 db = *reinterpret_cast<const double2 *>((colok ? pdb[m] : zeros) + 8 * j);
+					g1[m] = fma(ua0, da.x, fma(ua1, da.y, g1[m]));
+					g2[m] = fma(ub0, db.x, fma(ub1, db.y, g2[m]));
+				}
+			};
+			const bool hi = lane & 16, hi2 = lane & 8;
+			double bx, by, bz;
+			auto bf1 = [&]() {
+				bx = hi ? pend_a : pend_n, by = hi ? pend_b : 0.0;
+				bx += __shfl_xor_sync(0xffffffffu, hi ? pend_n : pend_a, 16), by += __shfl_xor_sync(0xffffffffu, hi ? 0.0 : pend_b, 16);
+			};
+			auto bf2 = [&]() {
+				bz = hi2 ? by : bx;
+				bz += __shfl_xor_sync(0xffffffffu, hi2 ? bx : by, 8);
+				bz += __shfl_xor_sync(0xffffffffu, bz, 4);
+			};
+			auto bf3 = [&]() {
+				bz += __shfl_xor_sync(0xffffffffu, bz, 2);
+				bz += __shfl_xor_sync(0xffffffffu, bz, 1);
+				red_add_f64_if(lane == 0 ? pend_tn : (lane == 16 ? pend_ta : (lane == 24 ? pend_tb : nullptr)), bz);
+			};
+			static_assert(Sh::NT == 3, "the software pipeline below is written out for three n-tiles");
+			if (!root) {
+				double W0[MT][2], Z0[MT][2], W1[MT][2], Z1[MT][2];
+				bf1();
+				tile_dmma(0, W0, Z0);
+				bf2();
+				tile_dmma(1, W1, Z1);
+				combine(0, W0, Z0);
+				bf3();
+				tile_dmma(2, W0, Z0);
+				combine(1, W1, Z1);
+				combine(2, W0, Z0);
+			} else {
+				bf1(), bf2(), bf3();
+#pragma unroll
+				for (int j = 0; j < Sh::NT; j++) {
+					double W[MT][2], Z[MT][2];
+#pragma unroll
+					for (int m = 0; m < MT; m++) W[m][0] = wroot[8 * j + 2 * q], W[m][1] = wroot[8 * j + 2 * q + 1], Z[m][0] = Z[m][1] = 0.0;
+					combine(j, W, Z);
+				}
+			}
+			turn.release(lane);
+			if (kind >= 1) dw_store_slice<S, MT>(cur + lofD, q, Ma);  // U_b: child b's op is the next one
 			if (kind == 2) {
-				if (a_slot < K) dw_store_slice<S, MT>(mine + (size_t)a_slot * G::SLICE, r, q, Mb);
-				else {  // parked beyond the shared-memory slots: through a staging slice to HBM
-					if (lane == 0) bulk_wait_read<0>();
-					__syncwarp();
-					dw_store_slice<S, MT>(stage_out, r, q, Mb);
+				if (a_slot < K) dw_store_slice<S, MT>(mine + (size_t)a_slot * tile_d + lofD, q, Mb);
+				else {  // parked beyond the shared-memory slots: through a staging slice to HBM; complete before the producer may read it back
+					dw_store_slice<S, MT>(stage_out + lofD, q, Mb);
 					fence_async_smem();
 					__syncwarp();
-					if (lane == 0 && rows > 0) {
-						bulk_s2g(p.spillbuf + (size_t)(a_slot - K) * CPS + (size_t)c * PS + (size_t)p0 * S, stage_out, rbytes);
+					if (lane == 0) {
+						if (rows > 0) bulk_s2g(p.spillbuf + (size_t)(a_slot - K) * CPS + (size_t)c * PS + (size_t)p0 * S, stage_out, rbytes);
 						bulk_commit();
+						bulk_wait_all<0>();
 					}
 				}
 			}
-			// one value per branch and warp, added to this warp's own rows (fixed order: deterministic)
-			if (!root) gn = phb_warp_sum(gn);
-			if (kind < 2) ga = phb_warp_sum(ga);
-			if (kind == 0) gb = phb_warp_sum(gb);
-			if (lane == 0) {
-				if (!root) red_add_f64(grow + ((size_t)node * p.C + c) * p.pstride, gn);
-				if (kind < 2) red_add_f64(grow + ((size_t)a_node * p.C + c) * p.pstride, ga);
-				if (kind == 0) red_add_f64(grow + ((size_t)b_node * p.C + c) * p.pstride, gb);
-			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&bars->imgempty[s]);  // images and codes of this op are consumed
+			pend_n = pend_a = pend_b = 0.0;
+#pragma unroll
+			for (int m = 0; m < MT; m++) pend_n = fma(g0[m], wl[m], pend_n), pend_a = fma(g1[m], wl[m], pend_a), pend_b = fma(g2[m], wl[m], pend_b);
+			pend_tn = root ? nullptr : gitem + (size_t)node * p.C * p.pstride;
+			pend_ta = kind < 2 ? gitem + (size_t)a_node * p.C * p.pstride : nullptr;
+			pend_tb = kind == 0 ? gitem + (size_t)b_node * p.C * p.pstride : nullptr;
 			if (++s == nstg) s = 0, ph ^= 1;
 		}
+	}
+	{  // the last op's sums
+		const bool hi = lane & 16, hi2 = lane & 8;
+		double x = hi ? pend_a : pend_n, y = hi ? pend_b : 0.0;
+		x += __shfl_xor_sync(0xffffffffu, hi ? pend_n : pend_a, 16), y += __shfl_xor_sync(0xffffffffu, hi ? 0.0 : pend_b, 16);
+		double z = hi2 ? y : x;
+		z += __shfl_xor_sync(0xffffffffu, hi2 ? x : y, 8);
+		z += __shfl_xor_sync(0xffffffffu, z, 4);
+		z += __shfl_xor_sync(0xffffffffu, z, 2);
+		z += __shfl_xor_sync(0xffffffffu, z, 1);
+		red_add_f64_if(lane == 0 ? pend_tn : (lane == 16 ? pend_ta : (lane == 24 ? pend_tb : nullptr)), z);
 	}
 	if (lane == 0) bulk_wait_all<0>();
 }
@@ -553,7 +640,6 @@ __global__ void __launch_bounds__(288, 1) k_dwalk_pre(const DwParams p) {
 // host side
 // ---------------------------------------------------------------------------------------------
 #define DW_S 20
-#define DW_MT 2
 
 template <class T>
 static int dw_upload(phbc_ctx *ctx, void **dst, const T *src, size_t n) {
@@ -618,16 +704,16 @@ struct DwPlan {
 
 // launch geometry: 8 consumer warps (128-pattern tiles) when that still gives every SM several items, else 4; as many
 // shared-memory slots as fit beside a ring of 3 stages (2 when that avoids spilling)
-static bool dw_plan(const phbc_ctx *ctx, DwPlan *pl) {
-	using G = DwGeom<DW_S, DW_MT>;
+template <class G>
+static bool dw_plan_g(const phbc_ctx *ctx, DwPlan *pl) {
 	// PHB_OPT_TUNE (profiling / tests): 11 = one shared-memory slot (parked values spill to HBM), 12 = 8 consumer warps whatever the
 	// pattern count, 13 = both, 14 = 4 consumer warps
 	const bool one_slot = ctx->tune == 11 || ctx->tune == 13, force8 = ctx->tune == 12 || ctx->tune == 13, force4 = ctx->tune == 14;
 	const size_t cap = ctx->smem_optin;
-	for (int nw = force4 ? 4 : 8; nw >= 4; nw -= 4) {
+	for (int nw = force4 ? G::NWMAX / 2 : G::NWMAX; nw >= G::NWMAX / 2; nw -= G::NWMAX / 2) {
 		const int TP = nw * G::ROWS, ntiles = (ctx->P + TP - 1) / TP;
 		const long long nitems = (long long)ntiles * ctx->C;
-		if (nw == 8 && !force8 && nitems < 6LL * ctx->num_sms) continue;
+		if (nw == G::NWMAX && !force8 && nitems < ctx->num_sms) continue;  // measured: 8 warps win down to 25k patterns (profiles/r2_l_tune_c4.jsonl)
 		if (nitems > 0x7fffffffLL) return false;
 		const size_t slice = (size_t)nw * G::SLICE * 8;
 		auto fit = [&](int nstg, int stage, int fixed, int want, int *K, int *spill) -> bool {
@@ -662,6 +748,14 @@ static bool dw_plan(const phbc_ctx *ctx, DwPlan *pl) {
 		return true;
 	}
 	return false;
+}
+
+// geometries: 8 consumer warps x 16 patterns (two m-tiles per warp: every B fragment feeds two DMMAs), or -- PHB_OPT_TUNE 16 -- 12 consumer
+// warps x 8 patterns (three warps per scheduler overlap better, at twice the shared-memory reads per DMMA)
+using DwGeomA = DwGeom<DW_S, 2, 8>;
+using DwGeomB = DwGeom<DW_S, 1, 12>;
+static bool dw_plan(const phbc_ctx *ctx, DwPlan *pl) {
+	return ctx->tune == 16 ? dw_plan_g<DwGeomB>(ctx, pl) : dw_plan_g<DwGeomA>(ctx, pl);
 }
 
 bool phbc_dwalk_supported(const phbc_ctx *ctx, const phbc_eval_opts *o) {
@@ -710,8 +804,8 @@ int phbc_dwalk_usable(phbc_ctx *ctx, const phbc_eval_opts *o) {
 }
 
 // the passes of one evaluation on the ctx stream; matrices (d_P, d_dP) are current, the lower buffers exist
-int phbc_dwalk_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
-	using G = DwGeom<DW_S, DW_MT>;
+template <class G, int MT>
+static int dw_passes_g(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
 	DwPlan pl;
 	int rc, usable = 0;
 	if (!dw_plan(ctx, &pl)) {
@@ -723,17 +817,18 @@ int phbc_dwalk_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
 		snprintf(phbc_errbuf, sizeof(phbc_errbuf), "tensor-core walk: tip partials are not single states");
 		return -1;
 	}
-	if ((rc = phbc_dmma_pack_images(ctx, true, o->include_root_freqs, true))) return rc;
+	if ((rc = phbc_dmma_pack_images(ctx, true, o->include_root_freqs, 2))) return rc;
 	const size_t per_walk = (size_t)pl.ntiles * ctx->T * pl.TP;
 	DwParams p;
 	memset(&p, 0, sizeof(p));
 	p.img = ctx->d_dmma_img, p.lower = ctx->d_lower;
 	p.T = ctx->T, p.N = ctx->N, p.C = ctx->C, p.P = ctx->P, p.ntiles = pl.ntiles, p.nitems = pl.nitems, p.root = ctx->root;
 	p.nops = ctx->dw_nops, p.nw = pl.nw;
+	p.turns = ctx->tune == 15;  // PHB_OPT_TUNE 15: warp pairs take turns on the tensor pipe (A/B runs; measured slower than free-running warps)
 	p.freqs = ctx->d_freqs, p.weights = ctx->d_weights, p.pattern_lnl = ctx->d_pattern_lnl, p.include_root_freqs = o->include_root_freqs;
 	const int threads = 32 * (pl.nw + 1);
-	auto post = k_dwalk_post<DW_S, DW_MT>;
-	auto pre = k_dwalk_pre<DW_S, DW_MT>;
+	auto post = k_dwalk_post<DW_S, MT, G::NWMAX>;
+	auto pre = k_dwalk_pre<DW_S, MT, G::NWMAX>;
 	PHBC_CHECK(cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_post));
 	p.codes = ctx->d_dw_codes, p.ops = ctx->d_dw_post;
 	p.K = pl.Kpost, p.nstg = pl.nstg_post, p.spill = pl.spill_post;
@@ -763,6 +858,8 @@ int phbc_dwalk_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
 	pre<<<pl.grid, threads, pl.smem_pre, ctx->stream>>>(p);
 	ctx->launches++;
 	PHBC_CHECK(cudaGetLastError());
-	(void)G::HDR;
 	return phbc_gradient_from_partials(ctx, pstride, result);
+}
+int phbc_dwalk_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
+	return ctx->tune == 16 ? dw_passes_g<DwGeomB, 1>(ctx, o, result) : dw_passes_g<DwGeomA, 2>(ctx, o, result);
 }

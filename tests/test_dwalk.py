@@ -13,7 +13,7 @@ from physher_b200.treelikelihood import OPT_INCLUDE_ROOT_FREQS, OPT_TUNE, RAN_TE
 pytestmark = pytest.mark.gpu
 RTOL = 1e-10  # north_star: lnL and every branch gradient within 1e-10 relative
 
-TUNE_LEVELS, TUNE_ONE_SLOT, TUNE_8_WARPS, TUNE_ONE_SLOT_8_WARPS, TUNE_4_WARPS = 9, 11, 12, 13, 14
+TUNE_LEVELS, TUNE_ONE_SLOT, TUNE_8_WARPS, TUNE_ONE_SLOT_8_WARPS, TUNE_4_WARPS, TUNE_TURNS, TUNE_12_NARROW_WARPS = 9, 11, 12, 13, 14, 15, 16
 
 
 def rel_err(a, b):
@@ -52,7 +52,8 @@ def check(pb, tune, want=None):
     return g, launches
 
 
-@pytest.mark.parametrize("tune", [0, TUNE_8_WARPS, TUNE_ONE_SLOT, TUNE_ONE_SLOT_8_WARPS], ids=["auto", "8warps", "spill", "spill8"])
+@pytest.mark.parametrize("tune", [0, TUNE_8_WARPS, TUNE_ONE_SLOT, TUNE_ONE_SLOT_8_WARPS, TUNE_TURNS, TUNE_12_NARROW_WARPS],
+                         ids=["auto", "8warps", "spill", "spill8", "turns", "12x8"])
 @pytest.mark.parametrize("shape", [(24, 1000, 4), (24, 63, 4), (31, 65, 1), (57, 129, 2), (2, 40, 2), (3, 17, 4)], ids=lambda s: "T%d-P%d-C%d" % s)
 def test_walk_against_oracle(shape, tune):
     """ragged pattern counts around the 64 / 128-pattern tiles, unknown states, two and three taxa; every launch geometry"""

@@ -1,0 +1,4 @@
+set -x
+timeout 300 python -m pytest tests/test_dwalk.py -x -q 2>&1 | tail -15 > gpurun_out/r2_l_tests.log
+timeout 300 python tools/tune_dmma.py c4 200000 0,16,0 > gpurun_out/r2_l_tune_c4.jsonl 2> gpurun_out/r2_l_tune.err
+timeout 300 python tools/tune_dmma.py c4 25000 0,16,9 >> gpurun_out/r2_l_tune_c4.jsonl 2>> gpurun_out/r2_l_tune.err
