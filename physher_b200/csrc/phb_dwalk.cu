@@ -216,7 +216,10 @@ __device__ __forceinline__ void dwalk_producer(const DwParams &p, unsigned char 
 			const DwPre *d = reinterpret_cast<const DwPre *>(p.ops) + lk;
 			const int kind = d->kind, a_node = d->a_node, b_node = d->b_node;
 			const bool lu = d->u_kind == PHBC_W_SLOT && d->u_slot >= p.K;
-			if (kind >= 1 || lu) {
+			// landfull completes once per op, loads or not: a warp cannot start op h + 1 before every warp has released op h's landing
+			// buffers, so the arrivals of two ops never meet in one phase of landempty
+			if (!(kind >= 1 || lu)) mbar_arrive(&bars->landfull);
+			else {
 				const int tile = litem / p.C, c = litem - tile * p.C;
 				const int p0 = tile * TP;
 				const uint32_t bytes = (uint32_t)min(p.P - p0, TP) * S * 8;
@@ -482,10 +485,8 @@ __global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_pre(const DwParams 
 			const bool lu = u_kind == PHBC_W_SLOT && u_slot >= K;
 			const double *mP = reinterpret_cast<const double *>(stg + G::IMG_OFF), *mZ = mP + Sh::IMG;
 			const double *tA = mZ + Sh::IMG, *dA = tA + Sh::IMG, *tB = dA + Sh::IMG, *dB = tB + Sh::IMG;
-			if (kind >= 1 || lu) {  // the same condition the producer armed the landing barrier on
-				mbar_wait(&bars->landfull, lph);
-				lph ^= 1;
-			}
+			mbar_wait(&bars->landfull, lph);  // the message tiles of the children (and a spilled U) have landed; completes for every op
+			lph ^= 1;
 			// A fragments of U_n
 			const double *usrc = ((u_kind == PHBC_W_SLOT && u_slot < K) ? mine + (size_t)u_slot * tile_d : cur) + lofA;
 			double u[MT][Sh::KT];
