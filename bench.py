@@ -535,10 +535,18 @@ def roofline_record(name, cfg, P, B, kms, kernels, lib_version):
         flops = algorithmic_flops(sized)
         tpeak, tsrc = dmma_peak()
         tf = flops / (kms * 1e-3) / 1e12 if kms > 0 else None
-        return {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": (tf / tpeak) if tf else None, "traffic": traffic,
-                "peak_source": tsrc, "kernel": "k_dmma_* (FP64 mma.sync m8n8k4, message form, branch gradients in adjoint form), all launches of one evaluation",
-                "kernel_ms": kms, "algorithmic_flops_per_launch": flops, "hbm": hbm,
-                "note": "launch = the kernel sequence of one evaluation; S=20 sits at the FP64 ridge so the HBM view is given too"}
+        rec = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": (tf / tpeak) if tf else None, "traffic": traffic,
+               "peak_source": tsrc, "kernel": "k_dmma_* (FP64 mma.sync m8n8k4, message form, branch gradients in adjoint form), all launches of one evaluation",
+               "kernel_ms": kms, "algorithmic_flops_per_launch": flops, "hbm": hbm,
+               "note": "launch = the kernel sequence of one evaluation; S=20 sits at the FP64 ridge so the HBM view is given too"}
+        if S == 20:  # whole-tree walk (phb_dwalk.cu): every message row crosses HBM once each way, upper partials stay in shared memory
+            walk_bytes = float(P) * B * ((2 * T - 3) * C * S * 8 + 2 * T)
+            rec["kernel"] = "k_dwalk_post + k_dwalk_pre (whole-tree walk on the FP64 tensor cores, mma.sync m8n8k4, TMA bulk copies), both launches of one evaluation"
+            hbm.update(fused_min_bytes_per_launch=walk_bytes, fused_min_frac=(walk_bytes / (kms * 1e-3) / 1e9 / peak) if kms > 0 else None)
+            rec["note"] = ("launch = the two walk launches (+ root integration) of one evaluation; the walk moves ~%.1f GB where the streaming model "
+                           "(hbm.algorithmic_bytes_per_launch) counts %.1f GB, so the path is bound by the FP64 pipe, which DMMA and the element-wise "
+                           "products share" % (walk_bytes / 1e9, alg / 1e9))
+        return rec
     hbm.update(kernel="generic node-at-a-time kernels, all levels of one evaluation")
     return hbm
 

@@ -99,7 +99,8 @@ const char *phb_last_error(void) { return g_err; }
 /* for the other host translation unit of the library (phb_group.c); not part of the ABI */
 int phb_internal_fail(int code, const char *msg) { return fail(code, "%s", msg); }
 int phb_device_count(void) { return phbc_device_count(); }
-const char *phb_version(void) { return "physher_b200 0.1 (sm_100a)"; }
+/* the kernel revision tag ties committed ncu captures (profiles/traffic.json) to the kernels they were taken on */
+const char *phb_version(void) { return "physher_b200 0.2 (sm_100a; kernels r2m)"; }
 
 /* ------------------------------------------------------------------------------------------- */
 /* schedules                                                                                   */

@@ -3,7 +3,7 @@
 
     ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
         --log-file gpurun_out/traffic_c4.csv python bench.py --config c4 --steps 1 --warmup 2 --no-cpu-baseline
-    python tools/ncu_traffic.py gpurun_out/traffic_c4.csv --kernels 'k_dmma_(lower|upper)' --per k_dmma_pack_q --key c4:auto
+    python tools/ncu_traffic.py gpurun_out/traffic_c4.csv --kernels 'k_dwalk_p' --per k_dmma_pack --key c4:auto --patterns 200000 --kernel-rev r2m
 
 sums the bytes of every launch whose name matches --kernels, divides by the number of evaluations (= launches of the --per
 kernel, which runs once per evaluation) and records it in profiles/traffic.json under --key (bench.py's roofline.traffic).
@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--kernels", required=True)
     ap.add_argument("--per", required=True)
     ap.add_argument("--key", required=True)
+    ap.add_argument("--patterns", type=int, required=True, help="patterns per launch of the captured run (bench.py only trusts a capture of the same size)")
+    ap.add_argument("--kernel-rev", required=True, help="kernel revision tag of phb_version() the capture was taken on")
     a = ap.parse_args()
     rows = list(csv.reader(open(a.csv, errors="replace")))
     h = next(r for r in rows if "Kernel Name" in r and "Metric Name" in r)
@@ -44,7 +46,7 @@ def main():
     entry = {"dram_bytes_per_launch": (total["dram__bytes_read.sum"] + total["dram__bytes_write.sum"]) / n,
              "dram_read_bytes": total["dram__bytes_read.sum"] / n, "dram_write_bytes": total["dram__bytes_write.sum"] / n,
              "kernel": a.kernels, "launches": len(launches) / n, "evaluations": n, "ncu_ms_per_launch": total["gpu__time_duration.sum"] / n,
-             "source": os.path.basename(a.csv), "note": "launch = the kernel sequence of one evaluation"}
+             "source": os.path.basename(a.csv), "note": "launch = the kernel sequence of one evaluation", "patterns": a.patterns, "kernel_rev": a.kernel_rev}
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
     d = json.load(open(path)) if os.path.exists(path) else {}
     d[a.key] = entry
