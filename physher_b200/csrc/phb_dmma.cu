@@ -968,12 +968,17 @@ struct DmmaConfig<20> {  // 128 threads; 64 patterns per tile in the lower pass,
 	static constexpr int UMT = 1, UNSPLIT = 1, UWM = 4;
 	static constexpr int UWM_II = 4;  // message-form upper kernel, parents without tip children
 };
-template <>
-struct DmmaConfig<61> {  // 256 threads, 32 patterns per tile, n-tiles split over two warps
+struct DmmaConfigCodon {  // 256 threads, 32 patterns per tile, n-tiles split over two warps
 	static constexpr int MT = 1, NSPLIT = 2, WM = 4;
 	static constexpr int UMT = 1, UNSPLIT = 2, UWM = 4;
 	static constexpr int UWM_II = 8;  // two image slots instead of five leave room for a 16-warp CTA sharing them
 };
+// codon models: 64 codons minus the stop codons of the genetic code (1 ... 4 of them), the reference's ">= 60 states" dispatch
+// (treelikelihood.c:1086-1090); all four state counts pad to the same 64 x 64 tile grid
+template <> struct DmmaConfig<60> : DmmaConfigCodon {};
+template <> struct DmmaConfig<61> : DmmaConfigCodon {};
+template <> struct DmmaConfig<62> : DmmaConfigCodon {};
+template <> struct DmmaConfig<63> : DmmaConfigCodon {};
 
 // Geometry of the MESSAGE-form kernels, by state count and tuning variant (PHB_OPT_TUNE; 0 = what ships, chosen from the measured
 // table in profiles/): m-tiles per warp, n-split, m-groups per CTA, cp.async ring depth (0 = AStage's default) and granule size.
@@ -993,6 +998,9 @@ template <> struct MsgCfg<20, 4> : MsgGeom<2, 1, 8, 0, 2, 1, 1, 8, 8, 0, 2> {}; 
 template <> struct MsgCfg<20, 5> : MsgGeom<2, 1, 4, 0, 2, 2, 1, 4, 4, 0, 2> {};  // 64-pattern tiles in the upper pass
 template <> struct MsgCfg<20, 6> : MsgGeom<4, 1, 2, 0, 2, 2, 1, 2, 2, 0, 2> {};  // 64-thread CTAs, wide warps
 template <> struct MsgCfg<61, 0> : MsgGeom<1, 2, 4, 0, 1, 1, 2, 4, 8, 0, 1> {};
+template <> struct MsgCfg<60, 0> : MsgCfg<61, 0> {};
+template <> struct MsgCfg<62, 0> : MsgCfg<61, 0> {};
+template <> struct MsgCfg<63, 0> : MsgCfg<61, 0> {};
 template <> struct MsgCfg<61, 1> : MsgGeom<1, 2, 4, 2, 1, 1, 2, 4, 8, 2, 1> {};  // ring of 2 (more CTAs per SM)
 template <> struct MsgCfg<61, 2> : MsgGeom<1, 2, 4, 0, 1, 1, 2, 4, 4, 0, 1> {};  // no wide variant for parents of two internal nodes
 #define PHBC_MSG_VARIANTS_20 7
@@ -1000,7 +1008,7 @@ template <> struct MsgCfg<61, 2> : MsgGeom<1, 2, 4, 0, 1, 1, 2, 4, 4, 0, 1> {}; 
 
 bool phbc_dmma_supported(const phbc_ctx *ctx, const phbc_eval_opts *o) {
 	(void)o;
-	return ctx->S == 20 || ctx->S == 61;
+	return ctx->S == 20 || (ctx->S >= 60 && ctx->S <= 63);
 }
 
 // Pattern chunks for one launch of `units` = C x ops (op, category) pairs on `slots` resident CTA slots: the chunk count whose
@@ -1103,19 +1111,33 @@ static int dmma_lower_msg_level(phbc_ctx *ctx, int level) {
 	return 0;
 }
 
+// the state counts the kernels are instantiated for
+#define PHBC_DMMA_BY_STATES(S_, CALL) \
+	switch (S_) {                     \
+	case 20: return CALL(20);         \
+	case 60: return CALL(60);         \
+	case 61: return CALL(61);         \
+	case 62: return CALL(62);         \
+	case 63: return CALL(63);         \
+	default: break;                   \
+	}
+
 int phbc_dmma_pack_images(phbc_ctx *ctx, bool adjoint, int include_root_freqs, int tip_images) {
-	if (ctx->S == 20) return dmma_pack<20>(ctx, adjoint, include_root_freqs, tip_images);
-	if (ctx->S == 61) return dmma_pack<61>(ctx, adjoint, include_root_freqs, tip_images);
+#define CALL(S) dmma_pack<S>(ctx, adjoint, include_root_freqs, tip_images)
+	PHBC_DMMA_BY_STATES(ctx->S, CALL)
+#undef CALL
 	return -1;
 }
 int phbc_dmma_pack(phbc_ctx *ctx) {
-	if (ctx->S == 20) return dmma_pack<20>(ctx);
-	if (ctx->S == 61) return dmma_pack<61>(ctx);
+#define CALL(S) dmma_pack<S>(ctx)
+	PHBC_DMMA_BY_STATES(ctx->S, CALL)
+#undef CALL
 	return -1;
 }
 int phbc_dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
-	if (ctx->S == 20) return dmma_lower_ops<20>(ctx, d_ops, cnt);
-	if (ctx->S == 61) return dmma_lower_ops<61>(ctx, d_ops, cnt);
+#define CALL(S) dmma_lower_ops<S>(ctx, d_ops, cnt)
+	PHBC_DMMA_BY_STATES(ctx->S, CALL)
+#undef CALL
 	return -1;
 }
 
@@ -1206,7 +1228,9 @@ static int dmma_msg_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *resul
 	return 0;
 }
 template <int S>
-static int dmma_msg_dispatch(phbc_ctx *ctx, const phbc_eval_opts *o, double *result);
+static int dmma_msg_dispatch(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
+	return dmma_msg_passes<S, 0>(ctx, o, result);  // the shipped geometry; tuning variants exist for 20 and 61 states
+}
 template <>
 int dmma_msg_dispatch<20>(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
 	switch (ctx->tune) {
@@ -1357,14 +1381,16 @@ static int dmma_download(phbc_ctx *ctx, double *P, double *dP) {
 
 int phbc_dmma_download_matrices(phbc_ctx *ctx, double *P, double *dP) {
 	PHBC_CHECK(cudaSetDevice(ctx->device));
-	if (ctx->S == 20) return dmma_download<20>(ctx, P, dP);
-	if (ctx->S == 61) return dmma_download<61>(ctx, P, dP);
+#define CALL(S) dmma_download<S>(ctx, P, dP)
+	PHBC_DMMA_BY_STATES(ctx->S, CALL)
+#undef CALL
 	return -1;
 }
 
 int phbc_dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
-	if (ctx->S == 20) return dmma_evaluate<20>(ctx, o);
-	if (ctx->S == 61) return dmma_evaluate<61>(ctx, o);
-	snprintf(phbc_errbuf, sizeof(phbc_errbuf), "tensor-core kernels are instantiated for 20 and 61 states, not %d", ctx->S);
+#define CALL(S) dmma_evaluate<S>(ctx, o)
+	PHBC_DMMA_BY_STATES(ctx->S, CALL)
+#undef CALL
+	snprintf(phbc_errbuf, sizeof(phbc_errbuf), "tensor-core kernels are instantiated for 20 and 60 ... 63 states, not %d", ctx->S);
 	return -1;
 }

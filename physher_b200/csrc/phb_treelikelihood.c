@@ -1121,7 +1121,7 @@ static int evaluate_once(phb_tlk *t, int want_gradient, double *lnl, double *gra
  */
 static void fill_opts_resident(const phb_tlk *t, phbc_eval_opts *o, int want_gradient) {
 	fill_opts(t, o, want_gradient, 0);
-	o->kernels = ((t->S == 20 || t->S == 61) && t->kernels != PHB_KERNELS_GENERIC) ? PHB_KERNELS_AUTO : PHB_KERNELS_GENERIC;
+	o->kernels = ((t->S == 20 || (t->S >= 60 && t->S <= 63)) && t->kernels != PHB_KERNELS_GENERIC) ? PHB_KERNELS_AUTO : PHB_KERNELS_GENERIC;
 	o->materialize_uppers = 1;
 }
 

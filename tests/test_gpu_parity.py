@@ -379,6 +379,22 @@ def test_tensor_core_path_against_oracle(shape):
     tlk.close()
 
 
+@pytest.mark.parametrize("S", [60, 62, 63])
+def test_tensor_core_path_other_codon_tables(S):
+    """Genetic codes with 4, 2 or 1 stop codons (60 / 62 / 63 sense codons; the reference dispatches every state count >= 60 to its
+    codon kernels, treelikelihood.c:1086-1090) run on the tensor cores like the universal code's 61."""
+    pb = _synthetic_problem(11, 97, S, 2 if S == 62 else 1, seed=4050 + S, unknown=0.03)
+    want = O.evaluate(pb)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=phb.KERNELS_AUTO)
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), want["grad"]) < RTOL
+    assert tlk.last_kernels() == phb.treelikelihood.RAN_TENSOR
+    tlk.use_rescaling(True)
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), want["grad"]) < 1e-9
+    tlk.close()
+
+
 @pytest.mark.parametrize("S", [20, 61])
 def test_tensor_core_path_tip_partials(S):
     pb = _synthetic_problem(13, 200, S, 2 if S == 20 else 1, seed=4100 + S, unknown=0.0)
