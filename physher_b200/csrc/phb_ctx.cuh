@@ -90,6 +90,8 @@ struct phbc_ctx {
 	int tune;                // kernel-geometry variant of the tensor-core message kernels (PHB_OPT_TUNE; 0 = shipped)
 	int last_family;         // kernels of the last evaluation: 1 generic node-at-a-time, 2 fused 4-state walk, 3 FP64 tensor-core
 	int dmma_pack_adjoint, dmma_pack_irf;  // how the dP images of internal nodes were packed last (phbc_download_matrices undoes it)
+	uint8_t *d_enc_states;   // [T][P] 0/1 tip partials encoded as states for the message-form kernels (lazily; valid until the next tip upload)
+	bool enc_states_valid, enc_states_bad;
 	int dmma_pack_tips;      // tips were packed as transposed gather images (2: derivative images frequency-weighted)
 
 	// whole-tree tensor-core walk (phb_dwalk.cu)

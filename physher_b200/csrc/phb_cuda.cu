@@ -101,7 +101,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch,
 	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl, ctx->d_walk_gstat, ctx->d_nuc4_G, ctx->d_ex, ctx->d_post_tip_order, ctx->d_pre_tip_order, ctx->d_dmma_img, ctx->d_tt_lowers, ctx->d_tt_topo, ctx->d_tt_bad,
 	                ctx->d_tt_ratios, ctx->d_tt_rates, ctx->d_tt_heights, ctx->d_tt_adj, ctx->d_tt_out, ctx->d_reduce,
-	                ctx->d_dw_post, ctx->d_dw_pre, ctx->d_dw_codes, ctx->d_dw_bad, ctx->d_dw_spill};
+	                ctx->d_dw_post, ctx->d_dw_pre, ctx->d_dw_codes, ctx->d_dw_bad, ctx->d_dw_spill, ctx->d_enc_states};
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		if (bufs[i]) cudaFree(bufs[i]);
 	if (ctx->ev_beg) {
@@ -240,6 +240,7 @@ extern "C" int phbc_upload_tip_states(phbc_ctx *ctx, const uint8_t *states) {
 	if (!ctx->d_tip_states) return -1;
 	ctx->nuc4_codes_valid = false;
 	ctx->dw_codes_tp = 0;
+	ctx->enc_states_valid = false;
 	UPLOAD(ctx->d_tip_states, states, (size_t)ctx->T * ctx->P);
 	return 0;
 }
@@ -247,6 +248,7 @@ extern "C" int phbc_upload_tip_partials(phbc_ctx *ctx, const double *partials) {
 	if (!ctx->d_tip_partials) return -1;
 	ctx->nuc4_codes_valid = false;
 	ctx->dw_codes_tp = 0;
+	ctx->enc_states_valid = false;
 	UPLOAD(ctx->d_tip_partials, partials, (size_t)ctx->T * ctx->P * ctx->S);
 	return 0;
 }
@@ -323,6 +325,7 @@ extern "C" int phbc_copy_inputs(phbc_ctx *dst, phbc_ctx *src, int matrices, int 
 	PHBC_CHECK(cudaMemcpyPeerAsync(dst->d_weights, dst->device, src->d_weights, src->device, P * sizeof(double), dst->stream));
 	dst->nuc4_codes_valid = false;
 	dst->dw_codes_tp = 0;
+	dst->enc_states_valid = false;
 	if (matrices && src->d_P && src->d_dP) {
 		int rc = ensure_node_matrices(dst);
 		if (rc) return rc;

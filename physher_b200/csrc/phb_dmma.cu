@@ -1075,6 +1075,51 @@ static int dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
 	return 0;
 }
 
+// 0/1 tip partials as state codes (what SitePattern_get_partials produces for unambiguous data and gaps: phycpp's default tip mode,
+// examples/fluA/*.json): one-hot -> the state, all ones -> S (unknown).  Anything else -- an ambiguity SET -- raises *bad: its
+// message is a sum of columns, not a gather, and the evaluation stays on the kernels that read the partials.
+__global__ void k_dmma_encode_tips(size_t n, int S, const double *__restrict__ partials, uint8_t *__restrict__ codes, int *__restrict__ bad) {
+	const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const double *v = partials + i * S;
+	int ones = 0, first = -1;
+	for (int j = 0; j < S; j++) {
+		if (v[j] == 1.0) {
+			if (first < 0) first = j;
+			ones++;
+		} else if (v[j] != 0.0) *bad = 1;
+	}
+	if (ones != 1 && ones != S) *bad = 1;
+	codes[i] = (uint8_t)(ones == 1 ? first : S);
+}
+
+// 1 when the tips are states or encode as states (cached until the next tip upload)
+static int dmma_tips_as_states(phbc_ctx *ctx, int *usable) {
+	*usable = 1;
+	if (ctx->tip_kind == PHBC_TIP_STATES) return 0;
+	if (!ctx->enc_states_valid) {
+		const size_t n = (size_t)ctx->T * ctx->P;
+		if (!ctx->d_enc_states) PHBC_CHECK(cudaMalloc((void **)&ctx->d_enc_states, n));
+		if (!ctx->d_dw_bad) PHBC_CHECK(cudaMalloc((void **)&ctx->d_dw_bad, sizeof(int)));
+		PHBC_CHECK(cudaMemsetAsync(ctx->d_dw_bad, 0, sizeof(int), ctx->stream));
+		k_dmma_encode_tips<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(n, ctx->S, ctx->d_tip_partials, ctx->d_enc_states, ctx->d_dw_bad);
+		ctx->launches++;
+		int bad = 0;
+		PHBC_CHECK(cudaMemcpyAsync(&bad, ctx->d_dw_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		ctx->enc_states_bad = bad != 0;
+		ctx->enc_states_valid = true;
+	}
+	*usable = !ctx->enc_states_bad;
+	return 0;
+}
+// the buffers as the message-form kernels see them: tips are states, encoded from 0/1 partials where the caller uploaded those
+static Bufs dmma_msg_bufs(phbc_ctx *ctx) {
+	Bufs b = phbc_make_bufs(ctx);
+	if (ctx->tip_kind != PHBC_TIP_STATES) b.tip_states = ctx->d_enc_states, b.tip_kind = PHBC_TIP_STATES;
+	return b;
+}
+
 // one level of message-form lower ops: three launches by the number of tip children (the device op list is sorted that way), so
 // that ops without tip children do not pay shared memory for tip images (61 states: 3 CTAs per SM instead of 1)
 template <int S, int VAR>
@@ -1082,7 +1127,7 @@ static int dmma_lower_msg_level(phbc_ctx *ctx, int level) {
 	using Sh = DmmaShape<S>;
 	using Cf = MsgCfg<S, VAR>;
 	const int C = ctx->C, P = ctx->P;
-	Bufs b = phbc_make_bufs(ctx);
+	Bufs b = dmma_msg_bufs(ctx);
 	auto lower = k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM, Cf::LNST, Cf::LGB>;
 	const size_t ring = (size_t)Cf::WM * AStage<Sh, Cf::MT, 2, Cf::LNST>::NSTAGE * AStage<Sh, Cf::MT, 2, Cf::LNST>::STG;
 	const int lthreads = 32 * Cf::WM * Cf::NSPLIT, ltiles = (P + Cf::WM * Cf::MT * 8 - 1) / (Cf::WM * Cf::MT * 8);
@@ -1149,7 +1194,7 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 	using Cf = MsgCfg<S, VAR>;
 	const int C = ctx->C, P = ctx->P, N = ctx->N;
 	int rc;
-	Bufs b = phbc_make_bufs(ctx);
+	Bufs b = dmma_msg_bufs(ctx);
 	const bool split = true;  // per-kind launches (measured faster than one five-slot variant per level, round 1)
 	typedef void (*upper_fn)(Bufs, const phbc_parent_op *, const double *, const double *, const double *, const double *, int, int, double *, int);
 	struct Variant {
@@ -1274,8 +1319,13 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	if ((rc = phbc_generic_prepare(ctx, o))) return rc;
 	Bufs b = phbc_make_bufs(ctx);
 	// message form: the fast path (unscaled, state tips, eigen system, upper partials not needed as such afterwards)
-	const bool msg = !o->scale && !o->materialize_uppers && ctx->tip_kind == PHBC_TIP_STATES && ctx->have_eigen && !o->explicit_matrices;
-	if ((rc = dmma_pack<S>(ctx, msg, o->include_root_freqs))) return rc;
+	bool msg = !o->scale && !o->materialize_uppers && ctx->have_eigen && !o->explicit_matrices;
+	if (msg) {
+		int usable = 0;
+		if ((rc = dmma_tips_as_states(ctx, &usable))) return rc;
+		msg = usable != 0;
+	}
+	if ((rc = dmma_pack<S>(ctx, msg, o->include_root_freqs, msg ? 1 : -1))) return rc;
 	ctx->lower_is_message = msg;
 	ctx->node_evals++;
 	if ((rc = phbc_time_begin(ctx))) return rc;

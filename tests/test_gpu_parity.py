@@ -413,6 +413,26 @@ def test_tensor_core_path_tip_partials(S):
     tlk.close()
 
 
+def test_codon_tip_partials_of_single_states_take_the_message_kernels():
+    """0/1 tip partials (phycpp's default tip mode) are encoded to states for the message-form tensor-core kernels; an ambiguity
+    SET keeps the evaluation on the kernels that read the partials"""
+    pb = _synthetic_problem(13, 150, 61, 1, seed=4150, unknown=0.0)
+    pb.use_tip_states = False
+    pb.tip_partials = np.eye(61)[pb.tip_states]
+    pb.tip_partials[3, 5, :] = 1.0  # a gap
+    want = O.evaluate(pb)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), want["grad"]) < RTOL
+    assert tlk.last_kernels() == phb.treelikelihood.RAN_TENSOR
+    pb.tip_partials[7, 9, :30] = 1.0  # the encoding is redone after a tip upload and now declines
+    tlk.set_tip_partials(pb.tip_partials)
+    want = O.evaluate(pb)
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
+    assert grad_err(tlk.gradient(), want["grad"]) < RTOL
+    tlk.close()
+
+
 @pytest.mark.parametrize("S,C", [(20, 4), (61, 1)])
 def test_tensor_core_path_rescaling(S, C):
     """Deep caterpillar with long branches: partials underflow 1e-40, rescaling really triggers."""
