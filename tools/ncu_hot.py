@@ -16,8 +16,10 @@ def main():
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--launch", type=int, default=0)
     ap.add_argument("--listing", action="store_true", help="print the whole SASS with samples and executions")
+    ap.add_argument("--kernel", default="", help="regex on the kernel name (ncu --kernel-name regex:...); --launch then counts within the matches")
     a = ap.parse_args()
-    out = subprocess.run(["ncu", "-i", a.rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", a.rep, "--page", "source", "--csv"] + (["--kernel-name", "regex:" + a.kernel] if a.kernel else [])
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     blocks, h = [], None
     for r in rows:
