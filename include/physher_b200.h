@@ -60,12 +60,16 @@ extern "C" {
                                             that a one-ulp difference in an exponential moves by 1e-9.  Default 1 for >= 60 states, else 0; node-at-a-time
                                             and tensor-core paths, single evaluations (batches build their matrices on the device) */
 
-#define PHB_OPT_TUNE 9                   /* profiling: geometry variant of the tensor-core message kernels (tile shape, cp.async ring depth and
-                                            granule size; phb_dmma.cu MsgCfg).  0 = the shipped choice; results do not depend on it */
+#define PHB_OPT_TUNE 9                   /* profiling / tests: kernel variant of the tensor-core paths; 0 = the shipped choice, results do not depend
+                                            on it beyond rounding.  1 ... 6: geometry of the level-batched message kernels (tile shape, cp.async ring
+                                            depth and granule size; phb_dmma.cu MsgCfg).  20 states: 9 = the level-batched kernels instead of the
+                                            whole-tree walk (phb_dwalk.cu); walk variants 11 = one shared-memory slot (parked values spill to HBM),
+                                            12 / 14 = 8 / 4 consumer warps whatever the pattern count, 13 = 11 + 12, 15 = warp pairs take turns on
+                                            the tensor pipe, 16 = 12 consumer warps x 8 patterns */
 
 #define PHB_KERNELS_AUTO 0    /* by state count, like the function-pointer dispatch at treelikelihood.c:1067-1165 */
 #define PHB_KERNELS_GENERIC 1 /* node-at-a-time kernels, any state count, materialised upper partials */
-#define PHB_KERNELS_FUSED 2   /* whole-tree walk kernels (4 states) / tensor-core kernels (20, 61 states) */
+#define PHB_KERNELS_FUSED 2   /* whole-tree walk kernels (4 states; 20 states on the tensor cores) / level-batched tensor-core kernels (60 ... 63 states) */
 
 typedef struct phb_tlk phb_tlk; /* mirrors SingleTreeLikelihood */
 
