@@ -11,7 +11,7 @@ struct phbc_ctx {
 	int device, T, N, S, C, P, root, tip_kind;
 	cudaStream_t stream;
 	int num_sms;
-	size_t smem_optin;
+	size_t smem_optin, smem_sm;  // dynamic shared memory one CTA may ask for / shared memory of one SM
 
 	// inputs
 	uint8_t *d_tip_states;   // [T][P]

@@ -64,6 +64,7 @@ extern "C" phbc_ctx *phbc_create(int device, int ntips, int nstate, int ncat, in
 	cudaGetDeviceProperties(&prop, device);
 	ctx->num_sms = prop.multiProcessorCount;
 	ctx->smem_optin = prop.sharedMemPerBlockOptin;
+	ctx->smem_sm = prop.sharedMemPerMultiprocessor;
 	const size_t S = nstate, C = ncat, P = npatterns, N = ctx->N, T = ntips;
 	bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
 	ok = ok && dev_alloc(&ctx->d_weights, P) == 0;

@@ -13,7 +13,7 @@
 // pattern rows are contiguous in the [pattern][state] layout of the lower buffers).  Upper partials never leave the SM.
 //
 //   k_dwalk_post   L_n = M_a o M_b formed straight into the A fragments (tips: columns of the transposed matrix image),
-//                  M_n = L_n P_n^T on the tensor pipe, result to shared memory (next op / parked) and to HBM (bulk store).
+//                  M_n = L_n P_n^T on the tensor pipe, result to shared memory (next op / parked) and from the accumulators to HBM.
 //   [phbc_generic_root: site likelihoods from the root's row, all categories]
 //   k_dwalk_pre    per internal node n: W = U_n P_n^T and Z = U_n (pi o dP_n) from the same A fragments, the children's messages
 //                  from HBM (bulk load, one op ahead) or the tips' images, U_a = W o M_b, U_b = W o M_a to shared memory, branch
@@ -302,22 +302,19 @@ __device__ __forceinline__ void dw_store_slice(double *at, int q, const double (
 // post-order pass
 // ---------------------------------------------------------------------------------------------
 template <int S, int MT, int NWM>
-__global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_post(const DwParams p) {
+__global__ void __launch_bounds__(32 * (NWM + 1), 2) k_dwalk_post(const DwParams p) {
 	using G = DwGeom<S, MT, NWM>;
 	using Sh = DmmaShape<S>;
 	extern __shared__ __align__(128) unsigned char smraw[];
 	DwBars *bars = reinterpret_cast<DwBars *>(smraw);
-	uint64_t *lbar = reinterpret_cast<uint64_t *>(smraw + 256);
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const int nw = p.nw, nstg = p.nstg, K = p.K;
 	const int stgb = G::stage_bytes(3);
-	const int ntile = K + 2 + (p.spill ? 1 : 0);
+	const int ntile = K + 1;
 	const size_t tile_d = (size_t)nw * G::SLICE;
 	double *tiles = reinterpret_cast<double *>(smraw + G::HDR + (size_t)nstg * stgb);
 	if (threadIdx.x == 0) {
 		for (int i = 0; i < nstg; i++) mbar_init(&bars->imgfull[i], 1), mbar_init(&bars->imgempty[i], nw);
-		for (int w = 0; w < nw; w++) mbar_init(&lbar[w], 1);
-		for (int i = 0; i < 8; i++) mbar_init(&bars->turn[i], 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	for (int i = threadIdx.x; i < ntile * (int)tile_d; i += blockDim.x) tiles[i] = 0.0;  // rows past P keep finite values
@@ -328,20 +325,23 @@ __global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_post(const DwParams
 	}
 	const int r = lane >> 2, q = lane & 3;
 	double *mine = tiles + (size_t)warp * G::SLICE;  // this warp's slice of tile 0
-	double *cur0 = mine + (size_t)K * tile_d, *cur1 = cur0 + tile_d, *land = cur1 + tile_d;
+	double *cur = mine + (size_t)K * tile_d;         // hand-over buffer: the preceding op's result
 	const int TP = nw * G::ROWS;
 	const size_t PS = (size_t)p.P * S, CPS = (size_t)p.C * PS;
-	const int lofA = r * S + q, lofD = r * S + 2 * q;  // this lane's place in a slice, A-fragment / accumulator layout
+	// Fragment row r of a DMMA works on pattern row rr of the warp's slice, rr = r with its two low bits swapped.  Rows are independent,
+	// so any fixed assignment is valid; this one makes the 128-bit accesses in accumulator layout conflict-free: a quarter-warp (fragment
+	// rows 2k, 2k + 1) then touches slice rows two apart, whose 64-byte quads are 320 bytes = 16 banks (mod 32) apart, where adjacent rows
+	// (160 bytes = 8 banks) overlap in half of their banks (ncu: 8 wavefronts per STS.128 / LDS.128 instead of 4).  The 64-bit
+	// A-fragment reads see the same set of rows per half-warp as before and stay conflict-free.
+	const int rr = (r & 4) | ((r & 1) << 1) | ((r >> 1) & 1);
+	const int lofA = rr * S + q, lofD = rr * S + 2 * q;  // this lane's place in a slice, A-fragment / accumulator layout
 	const int bof = r * Sh::LD + q;
-	int s = 0, cb = 0;
-	uint32_t ph = 0, lph = 0;
-	DwTurn turn;
-	turn.init(bars, warp, nw, p.turns);
+	int s = 0;
+	uint32_t ph = 0;
 	for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
 		const int tile = item / p.C, c = item - tile * p.C;
 		const int p0 = tile * TP + warp * G::ROWS;
 		const int rows = min(max(p.P - p0, 0), G::ROWS);
-		const uint32_t rbytes = (uint32_t)rows * S * 8;
 		double *rowbase = p.lower + (size_t)c * PS + (size_t)p0 * S;  // + (node - T) CPS
 		for (int k = 0; k < p.nops; k++) {
 			const unsigned char *stg = smraw + G::HDR + (size_t)s * stgb;
@@ -349,30 +349,16 @@ __global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_post(const DwParams
 			const DwPost *d = reinterpret_cast<const DwPost *>(stg);
 			const int kind = d->kind, a_slot = d->a_slot, dst_slot = d->dst_slot, node = d->node, a_node = d->a_node;  // the stage is recycled after the arrive below
 			const double *mN = reinterpret_cast<const double *>(stg + G::IMG_OFF), *mA = mN + Sh::IMG, *mB = mA + Sh::IMG;
-			const double *prev = cb ? cur1 : cur0;
-			const double *ta = prev;
-			if (kind == 2) {
-				ta = mine + (size_t)a_slot * tile_d;
-				if (a_slot >= K) {  // parked beyond the shared-memory slots: its message row is in HBM already
-					if (rows > 0) {
-						if (lane == 0) {
-							bulk_wait_all<0>();  // the row was written by this thread's own bulk store
-							mbar_expect_tx(&lbar[warp], rbytes);
-							bulk_g2s(land, rowbase + (size_t)(a_node - p.T) * CPS, rbytes, &lbar[warp]);
-						}
-						mbar_wait(&lbar[warp], lph);
-						lph ^= 1;
-					}
-					ta = land;
-				}
-			}
-			// A fragments: L_n = M_a o M_b; an operand is a row of a tile slice or the column a tip's state selects in its image
+			// A fragments: L_n = M_a o M_b; an operand is a row of a tile slice, the column a tip's state selects in its image, or -- a
+			// child parked beyond the shared-memory slots -- the row of its message in HBM, which this warp wrote itself
+			const bool a_far = kind == 2 && a_slot >= K && rows > 0;
+			const double *ta = a_far ? rowbase + (size_t)(a_node - p.T) * CPS + q : (kind == 2 && a_slot < K ? mine + (size_t)a_slot * tile_d : cur) + lofA;
 			double a[MT][Sh::KT];
 #pragma unroll
 			for (int m = 0; m < MT; m++) {
-				const int row = warp * G::ROWS + 8 * m + r;
-				const double *pa = kind < 2 ? mA + stg[G::CODE_OFF + row] * Sh::NP + q : ta + lofA + 8 * m * S;
-				const double *pb = kind == 0 ? mB + stg[G::CODE_OFF + G::TPMAX + row] * Sh::NP + q : prev + lofA + 8 * m * S;
+				const int row = warp * G::ROWS + 8 * m + rr;
+				const double *pa = kind < 2 ? mA + stg[G::CODE_OFF + row] * Sh::NP + q : ta + (a_far ? min(8 * m + rr, rows - 1) * S : 8 * m * S);
+				const double *pb = kind == 0 ? mB + stg[G::CODE_OFF + G::TPMAX + row] * Sh::NP + q : cur + lofA + 8 * m * S;
 #pragma unroll
 				for (int tt = 0; tt < Sh::KT; tt++) a[m][tt] = pa[4 * tt] * pb[4 * tt];
 			}
@@ -382,7 +368,6 @@ __global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_post(const DwParams
 			for (int m = 0; m < MT; m++)
 #pragma unroll
 				for (int j = 0; j < Sh::NT; j++) acc[m][j][0] = acc[m][j][1] = 0.0;
-			turn.acquire();
 #pragma unroll
 			for (int tt = 0; tt < Sh::KT; tt++)
 #pragma unroll
@@ -391,28 +376,21 @@ __global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_post(const DwParams
 #pragma unroll
 					for (int m = 0; m < MT; m++) dmma_m8n8k4(acc[m][j][0], acc[m][j][1], a[m][tt], bN);
 				}
-			__syncwarp();
-			if (lane == 0) {
-				if (turn.on) mbar_arrive(turn.other);
-				mbar_arrive(&bars->imgempty[s]);
-			}  // the pipe goes to the partner; images and codes of this op are consumed
-			// result: parked slot or the other hand-over buffer, then to HBM from there
-			double *dst;
-			if (dst_slot >= 0 && dst_slot < K) dst = mine + (size_t)dst_slot * tile_d;
-			else dst = cb ? cur0 : cur1, cb ^= 1;
-			if (lane == 0) bulk_wait_read<1>();  // every store but the preceding op's has left shared memory
-			__syncwarp();
-			dw_store_slice<S, MT>(dst + lofD, q, acc);
-			fence_async_smem();
-			__syncwarp();
-			if (lane == 0 && rows > 0) {
-				bulk_s2g(rowbase + (size_t)(node - p.T) * CPS, dst, rbytes);
-				bulk_commit();
-			}
+			__syncwarp();  // every lane has its A fragments out of the hand-over buffer / the slot
+			if (lane == 0) mbar_arrive(&bars->imgempty[s]);  // images and codes of this op are consumed
+			// result: to the parked slot or the hand-over buffer for the ops to come, and straight from the accumulators to its row in HBM
+			// (a quad writes 64 contiguous bytes of a row; streaming stores: the pre-order pass reads the row 50 GB later)
+			dw_store_slice<S, MT>(((dst_slot >= 0 && dst_slot < K) ? mine + (size_t)dst_slot * tile_d : cur) + lofD, q, acc);
+			double *grow = rowbase + (size_t)(node - p.T) * CPS + lofD;
+#pragma unroll
+			for (int m = 0; m < MT; m++)
+#pragma unroll
+				for (int j = 0; j < Sh::NT; j++)
+					if ((8 * j + 6 < S || 8 * j + 2 * q < S) && 8 * m + rr < rows) __stcs(reinterpret_cast<double2 *>(grow + 8 * m * S + 8 * j), make_double2(acc[m][j][0], acc[m][j][1]));
+			__syncwarp();  // the result is visible to the lanes that read it in A-fragment layout
 			if (++s == nstg) s = 0, ph ^= 1;
 		}
 	}
-	if (lane == 0) bulk_wait_all<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -454,7 +432,8 @@ __global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_pre(const DwParams 
 	double *cur = mine + (size_t)K * tile_d, *landA = cur + tile_d, *landB = landA + tile_d, *stage_out = landB + tile_d;
 	const int TP = nw * G::ROWS;
 	const size_t PS = (size_t)p.P * S, CPS = (size_t)p.C * PS;
-	const int lofA = r * S + q, lofD = r * S + 2 * q;
+	const int rr = (r & 4) | ((r & 1) << 1) | ((r >> 1) & 1);  // pattern row of fragment row r (see k_dwalk_post)
+	const int lofA = rr * S + q, lofD = rr * S + 2 * q;
 	const int bof = r * Sh::LD + q;
 	int s = 0;
 	uint32_t ph = 0, lph = 0;
@@ -471,7 +450,7 @@ __global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_pre(const DwParams 
 		double wl[MT];
 #pragma unroll
 		for (int m = 0; m < MT; m++) {
-			const int pp = p0 + 8 * m + r;
+			const int pp = p0 + 8 * m + rr;
 			wl[m] = pp < p.P ? __ldg(p.weights + pp) / exp(__ldg(p.pattern_lnl + pp)) : 0.0;
 		}
 		double *gitem = grow + (size_t)c * p.pstride;  // + node C pstride
@@ -482,7 +461,6 @@ __global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_pre(const DwParams 
 			const int kind = d->kind, u_kind = d->u_kind, u_slot = d->u_slot, a_slot = d->a_slot;
 			const int node = d->node, a_node = d->a_node, b_node = d->b_node;  // the stage is recycled after the arrive below
 			const bool root = u_kind == PHBC_W_ROOT;
-			const bool lu = u_kind == PHBC_W_SLOT && u_slot >= K;
 			const double *mP = reinterpret_cast<const double *>(stg + G::IMG_OFF), *mZ = mP + Sh::IMG;
 			const double *tA = mZ + Sh::IMG, *dA = tA + Sh::IMG, *tB = dA + Sh::IMG, *dB = tB + Sh::IMG;
 			mbar_wait(&bars->landfull, lph);  // the message tiles of the children (and a spilled U) have landed; completes for every op
@@ -499,7 +477,7 @@ __global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_pre(const DwParams 
 			double Ma[MT][Sh::NT][2], Mb[MT][Sh::NT][2];
 #pragma unroll
 			for (int m = 0; m < MT; m++) {
-				const int row = warp * G::ROWS + 8 * m + r;
+				const int row = warp * G::ROWS + 8 * m + rr;
 				sa[m] = stg[G::CODE_OFF + row] * Sh::NP + 2 * q;
 				sb[m] = stg[G::CODE_OFF + G::TPMAX + row] * Sh::NP + 2 * q;
 				const double *pa = kind < 2 ? tA + sa[m] : landA + lofD + 8 * m * S;
@@ -697,7 +675,7 @@ int phbc_dwalk_set_schedule(phbc_ctx *ctx, const phbc_schedule *s) {
 }
 
 struct DwPlan {
-	int nw, TP, ntiles, nitems, grid;
+	int nw, TP, ntiles, nitems, grid, ctas_post;
 	int Kpost, nstg_post, spill_post;
 	int Kpre, nstg_pre, spill_pre;
 	size_t smem_post, smem_pre;
@@ -717,34 +695,37 @@ static bool dw_plan_g(const phbc_ctx *ctx, DwPlan *pl) {
 		if (nw == G::NWMAX && !force8 && nitems < ctx->num_sms) continue;  // measured: 8 warps win down to 25k patterns (profiles/r2_l_tune_c4.jsonl)
 		if (nitems > 0x7fffffffLL) return false;
 		const size_t slice = (size_t)nw * G::SLICE * 8;
-		auto fit = [&](int nstg, int stage, int fixed, int want, int *K, int *spill) -> bool {
+		// `extra` = tiles a spilling launch needs on top of the fixed ones (pre-order: a staging tile for the bulk store of a parked U)
+		auto fit = [&](size_t cap, int nstg, int stage, int fixed, int extra, int want, int *K, int *spill) -> bool {
 			const size_t base = G::HDR + (size_t)nstg * stage;
 			if (one_slot && want > 1) {
 				*K = 1, *spill = 1;
-				return base + (size_t)(fixed + 2) * slice <= cap;
+				return base + (size_t)(fixed + extra + 1) * slice <= cap;
 			}
 			if (base + (size_t)(fixed + want) * slice <= cap) {
 				*K = want, *spill = 0;
 				return true;
 			}
-			if (base + (size_t)(fixed + 1 + 1) * slice > cap) return false;
-			*K = (int)((cap - base) / slice) - fixed - 1, *spill = 1;
+			if (base + (size_t)(fixed + extra + 1) * slice > cap) return false;
+			*K = (int)((cap - base) / slice) - fixed - extra, *spill = 1;
 			return *K >= 1;
 		};
 		pl->nw = nw, pl->TP = TP, pl->ntiles = ntiles, pl->nitems = (int)nitems;
 		pl->grid = nitems < ctx->num_sms ? (int)nitems : ctx->num_sms;
 		int K3, sp3, K2, sp2;
-		// post-order: slices = K slots + 2 hand-over buffers (+ 1 landing slice when spilling)
-		bool ok3 = fit(3, G::stage_bytes(3), 2, ctx->post_slots, &K3, &sp3), ok2 = fit(2, G::stage_bytes(3), 2, ctx->post_slots, &K2, &sp2);
-		if (ok3 && (!sp3 || !ok2 || sp2)) pl->nstg_post = 3, pl->Kpost = K3, pl->spill_post = sp3;
-		else if (ok2) pl->nstg_post = 2, pl->Kpost = K2, pl->spill_post = sp2;
+		// post-order: tiles = K slots + the hand-over buffer; TWO CTAs per SM (16 consumer warps hide the scalar phases of the ops and the
+		// latency of re-reading a child parked beyond K from its message row in HBM), so each gets half of the SM's shared memory
+		const size_t cap2 = (ctx->smem_sm - 2 * 1024) / 2;
+		pl->ctas_post = ctx->tune == 19 ? 1 : 2;  // PHB_OPT_TUNE 19: one CTA per SM (A/B runs)
+		bool ok3 = fit(pl->ctas_post == 2 ? cap2 : cap, 3, G::stage_bytes(3), 1, 0, ctx->post_slots, &K3, &sp3), ok2 = false;
+		if (ok3) pl->nstg_post = 3, pl->Kpost = K3, pl->spill_post = sp3;
 		else continue;
 		// pre-order: K slots + hand-over + two landing slices (+ 1 staging slice when spilling)
-		ok3 = fit(3, G::stage_bytes(6), 3, ctx->pre_slots, &K3, &sp3), ok2 = fit(2, G::stage_bytes(6), 3, ctx->pre_slots, &K2, &sp2);
+		ok3 = fit(cap, 3, G::stage_bytes(6), 3, 1, ctx->pre_slots, &K3, &sp3), ok2 = fit(cap, 2, G::stage_bytes(6), 3, 1, ctx->pre_slots, &K2, &sp2);
 		if (ok3 && (!sp3 || !ok2 || sp2)) pl->nstg_pre = 3, pl->Kpre = K3, pl->spill_pre = sp3;
 		else if (ok2) pl->nstg_pre = 2, pl->Kpre = K2, pl->spill_pre = sp2;
 		else continue;
-		pl->smem_post = G::HDR + (size_t)pl->nstg_post * G::stage_bytes(3) + (size_t)(pl->Kpost + 2 + pl->spill_post) * slice;
+		pl->smem_post = G::HDR + (size_t)pl->nstg_post * G::stage_bytes(3) + (size_t)(pl->Kpost + 1) * slice;
 		pl->smem_pre = G::HDR + (size_t)pl->nstg_pre * G::stage_bytes(6) + (size_t)(pl->Kpre + 3 + pl->spill_pre) * slice;
 		return true;
 	}
@@ -833,7 +814,8 @@ static int dw_passes_g(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
 	PHBC_CHECK(cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_post));
 	p.codes = ctx->d_dw_codes, p.ops = ctx->d_dw_post;
 	p.K = pl.Kpost, p.nstg = pl.nstg_post, p.spill = pl.spill_post;
-	post<<<pl.grid, threads, pl.smem_post, ctx->stream>>>(p);
+	const long long gpost = (long long)pl.ctas_post * ctx->num_sms;
+	post<<<(int)(pl.nitems < gpost ? pl.nitems : gpost), threads, pl.smem_post, ctx->stream>>>(p);
 	ctx->launches++;
 	PHBC_CHECK(cudaGetLastError());
 	if ((rc = phbc_generic_root(ctx, o, result))) return rc;
