@@ -28,6 +28,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 // ---------------------------------------------------------------------------------------------
 // descriptors (device copies of the host's walk schedules with GLOBAL tip positions)
 // ---------------------------------------------------------------------------------------------
@@ -522,7 +524,10 @@ __global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_pre(const DwParams 
 					}
 				}
 			};
-			auto combine = [&](int j, const double (&W)[MT][2], const double (&Z)[MT][2]) {
+			// KIND (compile time): the number of internal children; their derivative columns are not read (shared memory runs at more
+			// than half of its bandwidth beside the tensor pipe, every wavefront counts)
+			auto combine = [&](auto KIND, int j, const double (&W)[MT][2], const double (&Z)[MT][2]) {
+				constexpr int kd = decltype(KIND)::value;
 				const bool colok = 8 * j + 6 < S || 8 * j + 2 * q < S;
 #pragma unroll
 				for (int m = 0; m < MT; m++) {
@@ -531,10 +536,14 @@ __global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_pre(const DwParams 
 					const double ub0 = W[m][0] * Ma[m][j][0], ub1 = W[m][1] * Ma[m][j][1];
 					Mb[m][j][0] = ua0, Mb[m][j][1] = ua1;
 					Ma[m][j][0] = ub0, Ma[m][j][1] = ub1;
-					const double2 da = *reinterpret_cast<const double2 *>((colok ? pda[m] : zeros) + 8 * j);
-					const double2 db = *reinterpret_cast<const double2 *>((colok ? pdb[m] : zeros) + 8 * j);
-					g1[m] = fma(ua0, da.x, fma(ua1, da.y, g1[m]));
-					g2[m] = fma(ub0, db.x, fma(ub1, db.y, g2[m]));
+					if (kd < 2) {
+						const double2 da = *reinterpret_cast<const double2 *>((colok ? pda[m] : zeros) + 8 * j);
+						g1[m] = fma(ua0, da.x, fma(ua1, da.y, g1[m]));
+					}
+					if (kd == 0) {
+						const double2 db = *reinterpret_cast<const double2 *>((colok ? pdb[m] : zeros) + 8 * j);
+						g2[m] = fma(ub0, db.x, fma(ub1, db.y, g2[m]));
+					}
 				}
 			};
 			const bool hi = lane & 16, hi2 = lane & 8;
@@ -554,25 +563,30 @@ __global__ void __launch_bounds__(32 * (NWM + 1), 1) k_dwalk_pre(const DwParams 
 				red_add_f64_if(lane == 0 ? pend_tn : (lane == 16 ? pend_ta : (lane == 24 ? pend_tb : nullptr)), bz);
 			};
 			static_assert(Sh::NT == 3, "the software pipeline below is written out for three n-tiles");
-			if (!root) {
+			auto dphase = [&](auto KIND) {
 				double W0[MT][2], Z0[MT][2], W1[MT][2], Z1[MT][2];
 				bf1();
 				tile_dmma(0, W0, Z0);
 				bf2();
 				tile_dmma(1, W1, Z1);
-				combine(0, W0, Z0);
+				combine(KIND, 0, W0, Z0);
 				bf3();
 				tile_dmma(2, W0, Z0);
-				combine(1, W1, Z1);
-				combine(2, W0, Z0);
-			} else {
+				combine(KIND, 1, W1, Z1);
+				combine(KIND, 2, W0, Z0);
+			};
+			if (!root) {
+				if (kind == 2) dphase(std::integral_constant<int, 2>{});
+				else if (kind == 1) dphase(std::integral_constant<int, 1>{});
+				else dphase(std::integral_constant<int, 0>{});
+			} else {  // once per item: the general form (derivative columns of internal children read as zeros)
 				bf1(), bf2(), bf3();
 #pragma unroll
 				for (int j = 0; j < Sh::NT; j++) {
 					double W[MT][2], Z[MT][2];
 #pragma unroll
 					for (int m = 0; m < MT; m++) W[m][0] = wroot[8 * j + 2 * q], W[m][1] = wroot[8 * j + 2 * q + 1], Z[m][0] = Z[m][1] = 0.0;
-					combine(j, W, Z);
+					combine(std::integral_constant<int, 0>{}, j, W, Z);
 				}
 			}
 			turn.release(lane);
