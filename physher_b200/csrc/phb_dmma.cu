@@ -1003,8 +1003,10 @@ template <> struct MsgCfg<62, 0> : MsgCfg<61, 0> {};
 template <> struct MsgCfg<63, 0> : MsgCfg<61, 0> {};
 template <> struct MsgCfg<61, 1> : MsgGeom<1, 2, 4, 2, 1, 1, 2, 4, 8, 2, 1> {};  // ring of 2 (more CTAs per SM)
 template <> struct MsgCfg<61, 2> : MsgGeom<1, 2, 4, 0, 1, 1, 2, 4, 4, 0, 1> {};  // no wide variant for parents of two internal nodes
+template <> struct MsgCfg<61, 3> : MsgGeom<2, 2, 2, 0, 1, 2, 2, 2, 4, 0, 1> {};  // two m-tiles per warp: every B fragment feeds two DMMAs (half the shared-memory reads)
+template <> struct MsgCfg<61, 4> : MsgGeom<2, 2, 2, 0, 1, 1, 2, 4, 8, 0, 1> {};  // ... in the lower pass only
 #define PHBC_MSG_VARIANTS_20 7
-#define PHBC_MSG_VARIANTS_61 3
+#define PHBC_MSG_VARIANTS_61 5
 
 bool phbc_dmma_supported(const phbc_ctx *ctx, const phbc_eval_opts *o) {
 	(void)o;
@@ -1293,6 +1295,8 @@ int dmma_msg_dispatch<61>(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 	switch (ctx->tune) {
 	case 1: return dmma_msg_passes<61, 1>(ctx, o, result);
 	case 2: return dmma_msg_passes<61, 2>(ctx, o, result);
+	case 3: return dmma_msg_passes<61, 3>(ctx, o, result);
+	case 4: return dmma_msg_passes<61, 4>(ctx, o, result);
 	default: return dmma_msg_passes<61, 0>(ctx, o, result);
 	}
 }

@@ -1,0 +1,9 @@
+set -x
+M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
+for cfg in c2 c3 c4 c5 c2_1m; do
+  timeout 400 ncu --metrics $M --clock-control none --csv --log-file gpurun_out/r2_x_traffic_$cfg.csv python bench.py --config $cfg --steps 1 --warmup 3 --sub none --no-cpu-baseline > gpurun_out/r2_x_${cfg}_under_ncu.log 2>&1
+done
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_dwalk_p --launch-skip 6 -c 2 -o gpurun_out/r2_x_dwalk_c4 python bench.py --config c4 --steps 1 --warmup 3 --sub none --no-cpu-baseline > gpurun_out/r2_x_c4_full.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/r2_x_tests.log
+timeout 600 python bench.py > gpurun_out/r2_x_bench.json 2> gpurun_out/r2_x_bench.err
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r2_x_ref.json 2> gpurun_out/r2_x_ref.err
