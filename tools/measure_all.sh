@@ -1,3 +1,9 @@
+#!/bin/bash
+# The measurement pass behind profiles/r2_x_*: run on a B200 box as
+#     gpurun --timeout 2400 -- 'bash tools/measure_all.sh'
+# then, back in the container, `python tools/ncu_traffic.py gpurun_out/r2_x_traffic_<cfg>.csv ... --kernel-rev <tag of phb_version()>`
+# for every config (profiles/traffic.json) and `python tools/ncu_summary.py gpurun_out/r2_x_dwalk_c4.ncu-rep --out profiles/...`.
+# Numbers printed by the runs under ncu are never bench values; every step is bounded by `timeout`.
 set -x
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
 for cfg in c2 c3 c4 c5 c2_1m; do
