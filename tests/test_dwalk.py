@@ -54,7 +54,8 @@ def check(pb, tune, want=None):
 
 @pytest.mark.parametrize("tune", [0, TUNE_8_WARPS, TUNE_ONE_SLOT, TUNE_ONE_SLOT_8_WARPS, TUNE_TURNS, TUNE_12_NARROW_WARPS],
                          ids=["auto", "8warps", "spill", "spill8", "turns", "12x8"])
-@pytest.mark.parametrize("shape", [(24, 1000, 4), (24, 63, 4), (31, 65, 1), (57, 129, 2), (2, 40, 2), (3, 17, 4)], ids=lambda s: "T%d-P%d-C%d" % s)
+@pytest.mark.parametrize("shape", [(24, 1000, 4), (24, 63, 4), (31, 65, 1), (57, 129, 2), (2, 40, 2), (3, 17, 4), (9, 1, 4), (10, 5, 8)],
+                         ids=lambda s: "T%d-P%d-C%d" % s)
 def test_walk_against_oracle(shape, tune):
     """ragged pattern counts around the 64 / 128-pattern tiles, unknown states, two and three taxa; every launch geometry"""
     T, P, C = shape
@@ -136,4 +137,20 @@ def test_walk_full_width_tiles_and_partial_reads_after_it():
     assert grad_err(tlk.gradient(), want["grad"]) < 1e-9
     tlk.use_rescaling(False)
     assert grad_err(tlk.gradient(), want["grad"]) < RTOL
+    tlk.close()
+
+
+def test_walk_serves_batched_branch_length_samples():
+    """phb_tlk_gradient_batch at 20 states: every sample of the batch is one pair of walk launches into its own result slot"""
+    pb = problem(14, 333, 2, seed=9600)
+    rng = np.random.default_rng(9601)
+    bls = pb.bl[None, :] * rng.uniform(0.5, 1.5, size=(3, pb.nnodes))
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    lnl, grad = tlk.gradient_batch(bls)
+    assert tlk.last_kernels() == RAN_TENSOR
+    for b in range(3):
+        pb.bl = bls[b]
+        want = O.evaluate(pb)
+        assert rel_err(lnl[b], want["lnl"]) < RTOL
+        assert grad_err(grad[b], want["grad"]) < RTOL
     tlk.close()
