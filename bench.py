@@ -133,17 +133,16 @@ class ClockSampler:
         self.proc, self.lines, self.samples, self.stop = None, [], [], threading.Event()
         self.nvml = None
 
-    def _nvml_loop(self):
+    def _nvml_sample(self):
         n = self.nvml
-        h = n.nvmlDeviceGetHandleByIndex(self.index)
-        bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
-                "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
-        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        sm = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        self.samples.append((float(sm), float(self._mx), [k for k, b in self._bits.items() if r & b]))
+
+    def _nvml_loop(self):
         while not self.stop.is_set():
             try:
-                sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
-                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.samples.append((float(sm), float(mx), [k for k, b in bits.items() if r & b]))
+                self._nvml_sample()
             except Exception:
                 pass
             self.stop.wait(self.period)
@@ -152,8 +151,16 @@ class ClockSampler:
         try:
             import pynvml
 
-            pynvml.nvmlInit()
-            self.nvml = pynvml
+            # initialisation, the handle and a first query happen HERE, before the timed region starts: the first NVML calls of a
+            # process take tens of milliseconds, longer than a short timed region (a run once came back with no sample at all)
+            n = pynvml
+            n.nvmlInit()
+            self.nvml = n
+            self._h = n.nvmlDeviceGetHandleByIndex(self.index)
+            self._bits = {"hw_slowdown": n.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": n.nvmlClocksThrottleReasonHwThermalSlowdown,
+                          "sw_thermal_slowdown": n.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": n.nvmlClocksThrottleReasonSwPowerCap}
+            self._mx = n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)
+            n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)  # warm the query path; not a sample (the region has not started)
             self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
             self.thread.start()
             return self
@@ -176,6 +183,11 @@ class ClockSampler:
         self.stop.set()
         if self.nvml is not None:
             self.thread.join(timeout=2)
+            if not self.samples:  # the region ended inside the first polling period: one sample at its very end
+                try:
+                    self._nvml_sample()
+                except Exception:
+                    pass
         if self.proc:
             self.proc.terminate()
             try:
