@@ -62,10 +62,11 @@ def test_walk_against_oracle(shape, tune):
     check(problem(T, P, C, seed=9000 + T + P), tune)
 
 
-@pytest.mark.parametrize("tune", [0, TUNE_ONE_SLOT_8_WARPS], ids=["auto", "spill8"])
+@pytest.mark.parametrize("tune", [0, TUNE_8_WARPS, TUNE_ONE_SLOT_8_WARPS], ids=["auto", "8warps", "spill8"])
 @pytest.mark.parametrize("kind", ["caterpillar", "balanced"])
 def test_walk_extreme_topologies(kind, tune):
-    """a chain (every op hands over to the next) and a perfect tree (the most parked values: 5 slots before-order at 64 taxa)"""
+    """a chain (every op hands over to the next) and a perfect tree (the most parked values: at 64 taxa and 8 warps they fit only beside a
+    TWO-stage image ring, the geometry no other test reaches)"""
     T = 64
     topo = syn.caterpillar_topology(T) if kind == "caterpillar" else syn.balanced_topology(T)
     check(problem(T, 300, 2, seed=9100, topo=topo), tune)
