@@ -155,3 +155,29 @@ def test_walk_serves_batched_branch_length_samples():
         assert rel_err(lnl[b], want["lnl"]) < RTOL
         assert grad_err(grad[b], want["grad"]) < RTOL
     tlk.close()
+
+
+@pytest.mark.parametrize("tune", [0, TUNE_ONE_SLOT_8_WARPS], ids=["auto", "spill8"])
+def test_walk_is_repeatable_under_load(tune):
+    """150 back-to-back evaluations that alternate between two sets of branch lengths: every result must be bit-identical to the first
+    one of its set.  The walk's warps synchronise only through mbarriers (image ring, landing tiles); a lost or doubled arrival shows
+    up here as a wrong number or as a hang long before it shows up in a benchmark."""
+    pb = problem(40, 5000, 4, seed=9700)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    tlk.set_option(OPT_TUNE, tune)
+    bls = [pb.bl, pb.bl * 1.07]
+    first = []
+    for b in bls:
+        tlk.set_branch_lengths(b)
+        first.append((tlk.calculate(), tlk.gradient().copy()))
+    pb2 = problem(40, 5000, 4, seed=9700)
+    pb2.bl = bls[1]
+    want = O.evaluate(pb2)
+    assert rel_err(first[1][0], want["lnl"]) < RTOL and grad_err(first[1][1], want["grad"]) < RTOL
+    for i in range(150):
+        k = i & 1
+        tlk.set_branch_lengths(bls[k])
+        g = tlk.gradient()
+        assert tlk.calculate() == first[k][0]
+        np.testing.assert_array_equal(g, first[k][1])
+    tlk.close()
