@@ -490,7 +490,7 @@ __global__ void k_generic_scale(Bufs b, const phbc_op *__restrict__ ops, double 
 		for (int i = 0; i < S; i++) m = x[i] > m ? x[i] : m;
 	}
 	double sf = 0.0;
-	if (m < threshold) {
+	if (m < threshold && m > 0.0) {  // m == 0: nothing to rescale (an upper partial the fused gradient path never wrote)
 		for (int c = 0; c < b.C; c++) {
 			double *x = (double *)partial_ptr(b, op.out, c) + (size_t)p * S;
 			for (int i = 0; i < S; i++) x[i] /= m;

@@ -382,7 +382,7 @@ template <int S, int MT, int NSPLIT, int WM, bool GRAD>
 __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const phbc_parent_op *__restrict__ ops, const double *__restrict__ img,
                                                                const double *__restrict__ freqs, const double *__restrict__ weights,
                                                                const double *__restrict__ pattern_lnl, int include_root_freqs, int pstride,
-                                                               double *__restrict__ partial) {
+                                                               double *__restrict__ partial, int scaled) {
 	using Sh = DmmaShape<S>;
 	constexpr int NTW = Sh::NT / NSPLIT;
 	constexpr int NWARPS = WM * NSPLIT;
@@ -478,6 +478,17 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const p
 				const int p = p0 + 8 * m + r;
 				wk[m] = p < b.P ? __ldg(weights + p) : 0.0;
 				lk[m] = p < b.P ? __ldg(pattern_lnl + p) : 0.0;
+				// Rescaling: the partials this op combines carry their CUMULATIVE log scaling factors (k_generic_scale: sf[out] = log m +
+				// sf[a] + sf[b]).  U_a = W o M_b is formed here from the parent's upper partial (scale sf[N + n]) and the sibling's lower
+				// partial (sf[b]) and meets L_a (sf[a]) -- and the same three factors in the other order for branch b -- so both branch
+				// terms of this op are the scaled sums times exp(sf[N + n] + sf[a] + sf[b] - lnL_k): the exact gradient
+				// (gradient_cat_branch_lengths with dlikelihood / likelihood, treelikelihood.c:2715-2789, 2464-2474), one exp per pattern.
+				if (scaled && p < b.P) {
+					double e = is_root ? 0.0 : b.sf[(size_t)(b.N + op.node) * b.P + p];
+					if (!a_tip) e += b.sf[(size_t)op.a * b.P + p];
+					if (!b_tip) e += b.sf[(size_t)op.b * b.P + p];
+					lk[m] -= e;
+				}
 			}
 		}
 		double W[MT][NTW][2], Mb[MT][NTW][2], Db[MT][NTW][2], Ma[MT][NTW][2], Da[MT][NTW][2];
@@ -1348,7 +1359,9 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	}
 	if ((rc = phbc_generic_root(ctx, o, result))) return rc;
 	if (o->want_gradient) {
-		const bool grad = !o->scale && !o->materialize_uppers;  // fused reductions use the unscaled form and skip the tips' uppers
+		// fused reductions skip the tips' uppers; under rescaling they give the exact gradient, the reference-compatible per-category
+		// normalisation (PHB_OPT_COMPAT_SCALED_GRADIENT) needs every category's denominator and stays with the generic K9 / K10 kernel
+		const bool grad = !o->materialize_uppers && !(o->scale && o->compat_scaled_gradient);
 		auto upper = grad ? k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, true> : k_dmma_upper<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, false>;
 		const int uwarps = Cf::UWM * Cf::UNSPLIT;
 		const size_t usmem = 128 + ((grad ? 5 : 3) * Sh::IMG + 2 * Sh::NP + 2 * uwarps + Cf::UWM * AStage<Sh, Cf::UMT, 3>::NSTAGE * AStage<Sh, Cf::UMT, 3>::STG) * sizeof(double);
@@ -1376,7 +1389,7 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 					const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
 					upper<<<dim3(pick_chunks(uslots, C * zc, utiles), C, zc), uthreads, usmem, ctx->stream>>>(
 					    b, ctx->d_parent_ops + beg + z0, ctx->d_dmma_img, ctx->d_freqs, ctx->d_weights, ctx->d_pattern_lnl, o->include_root_freqs, pstride,
-					    ctx->d_scratch);
+					    ctx->d_scratch, o->scale ? 1 : 0);
 					ctx->launches++;
 				}
 			}
