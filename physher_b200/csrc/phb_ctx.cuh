@@ -152,6 +152,7 @@ int phbc_generic_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 int phbc_gradient_from_partials(phbc_ctx *ctx, int tiles, double *result);               // cat_grad = sum of [N][C][tiles] scratch, A11
 // FP64 tensor-core path, 20 / 61 states (phb_dmma.cu)
 int phbc_dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
+int phbc_dmma_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int nsets, const double *d_M, double *d_cat);  // node terms of calculate_dlnl_dQ, [nsets][N][C]
 bool phbc_dmma_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);
 int phbc_dmma_pack(phbc_ctx *ctx);                                   // packed matrix images from d_P / d_dP
 int phbc_dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt);  // out = (P_a x_a) o (P_b x_b) for a device op list (one level)
@@ -159,7 +160,7 @@ int phbc_dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt);  // out =
 int phbc_dwalk_set_schedule(phbc_ctx *ctx, const phbc_schedule *s);
 bool phbc_dwalk_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);
 int phbc_dwalk_usable(phbc_ctx *ctx, const phbc_eval_opts *o);                       // supported AND the tips encode as single states
-int phbc_dwalk_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *result);       // post-order walk, root, pre-order walk, gradient sums
+int phbc_dwalk_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *result, int phases);  // 1: post-order walk + root, 2: pre-order walk + gradient sums
 // fused 4-state walk path (phb_nuc4.cu)
 int phbc_nuc4_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o);
 bool phbc_nuc4_supported(const phbc_ctx *ctx, const phbc_eval_opts *o);

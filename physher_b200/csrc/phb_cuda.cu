@@ -859,14 +859,36 @@ extern "C" int phbc_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int 
 	}
 	const bool tensor = phbc_dmma_supported(ctx, &e) && e.kernels != 1;
 	ctx->last_family = tensor ? 3 : 1;
-	int rc = tensor ? phbc_dmma_evaluate(ctx, &e) : phbc_generic_evaluate(ctx, &e);
-	if (rc) return rc;
+	int rc = 0;
 	const size_t set = N * C * S * S;
 	double *d_M = NULL, *d_cat = NULL, *d_out = NULL;
 	cudaError_t err = cudaMalloc((void **)&d_M, (size_t)nsets * set * sizeof(double));
 	if (err == cudaSuccess) err = cudaMalloc((void **)&d_cat, (size_t)nsets * N * C * sizeof(double));
 	if (err == cudaSuccess) err = cudaMalloc((void **)&d_out, (size_t)nsets * sizeof(double));
 	if (err == cudaSuccess) err = cudaMemcpyAsync(d_M, M_host, (size_t)nsets * set * sizeof(double), cudaMemcpyHostToDevice, ctx->stream);
+	if (err == cudaSuccess && tensor) {
+		// 20 / 60..63 states: the forward phase once, one tensor-core gradient phase per set with the set in the place of dP/dt; no
+		// materialised upper partials, no scalar S^2 products (round 2: GY94 100 x 250k, 2 sets, 899 ms -> see profiles/)
+		rc = phbc_dmma_matrix_gradient(ctx, &e, nsets, d_M, d_cat);
+		if (!rc) {
+			k_matrix_gradient_sum<<<nsets, 256, 0, ctx->stream>>>((int)N, (int)C, ctx->root, skip_node, d_cat, ctx->d_props, d_out);
+			ctx->launches++;
+			err = cudaMemcpyAsync(out_host, d_out, (size_t)nsets * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+			if (err == cudaSuccess && lnl)
+				err = cudaMemcpyAsync(lnl, ctx->d_result + (size_t)e.batch_index * (1 + N), sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+		}
+		if (err == cudaSuccess) err = cudaStreamSynchronize(ctx->stream);
+		if (err == cudaSuccess) err = cudaGetLastError();
+		cudaFree(d_M), cudaFree(d_cat), cudaFree(d_out);
+		if (rc) return rc;
+		PHBC_CHECK(err);
+		return 0;
+	}
+	if (err == cudaSuccess) rc = phbc_generic_evaluate(ctx, &e);
+	if (rc) {
+		cudaFree(d_M), cudaFree(d_cat), cudaFree(d_out);
+		return rc;
+	}
 	const size_t gtiles = (P + GEN_PGRAD - 1) / GEN_PGRAD;
 	if (err == cudaSuccess) {
 		rc = phbc_ensure_scratch(ctx, N * C * gtiles * sizeof(double));

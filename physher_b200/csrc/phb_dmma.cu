@@ -1274,64 +1274,71 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 }
 
 // lower and upper passes of the message form in tuning variant VAR
+// phases: PHBC_PH_FORWARD = post-order pass + root integration, PHBC_PH_GRADIENT = pre-order pass with the branch reductions (run alone
+// by phbc_dmma_matrix_gradient, once per matrix set, on the messages the forward phase left)
+#define PHBC_PH_FORWARD 1
+#define PHBC_PH_GRADIENT 2
 template <int S, int VAR>
-static int dmma_msg_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
+static int dmma_msg_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *result, int phases) {
 	int rc;
-	for (int l = 0; l < ctx->n_lower_levels; l++) {
-		if (ctx->h_lower_level_off[l + 1] - ctx->h_lower_level_off[l] <= 0) continue;
-		if ((rc = dmma_lower_msg_level<S, VAR>(ctx, l))) return rc;
+	if (phases & PHBC_PH_FORWARD) {
+		for (int l = 0; l < ctx->n_lower_levels; l++) {
+			if (ctx->h_lower_level_off[l + 1] - ctx->h_lower_level_off[l] <= 0) continue;
+			if ((rc = dmma_lower_msg_level<S, VAR>(ctx, l))) return rc;
+		}
+		if ((rc = phbc_generic_root(ctx, o, result))) return rc;
 	}
-	if ((rc = phbc_generic_root(ctx, o, result))) return rc;
-	if (o->want_gradient && (rc = dmma_upper_msg<S, VAR>(ctx, o, result))) return rc;
+	if ((phases & PHBC_PH_GRADIENT) && o->want_gradient && (rc = dmma_upper_msg<S, VAR>(ctx, o, result))) return rc;
 	return 0;
 }
 template <int S>
-static int dmma_msg_dispatch(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
-	return dmma_msg_passes<S, 0>(ctx, o, result);  // the shipped geometry; tuning variants exist for 20 and 61 states
+static int dmma_msg_dispatch(phbc_ctx *ctx, const phbc_eval_opts *o, double *result, int phases) {
+	return dmma_msg_passes<S, 0>(ctx, o, result, phases);  // the shipped geometry; tuning variants exist for 20 and 61 states
 }
 template <>
-int dmma_msg_dispatch<20>(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
+int dmma_msg_dispatch<20>(phbc_ctx *ctx, const phbc_eval_opts *o, double *result, int phases) {
 	switch (ctx->tune) {
-	case 1: return dmma_msg_passes<20, 1>(ctx, o, result);
-	case 2: return dmma_msg_passes<20, 2>(ctx, o, result);
-	case 3: return dmma_msg_passes<20, 3>(ctx, o, result);
-	case 4: return dmma_msg_passes<20, 4>(ctx, o, result);
-	case 5: return dmma_msg_passes<20, 5>(ctx, o, result);
-	case 6: return dmma_msg_passes<20, 6>(ctx, o, result);
-	default: return dmma_msg_passes<20, 0>(ctx, o, result);
+	case 1: return dmma_msg_passes<20, 1>(ctx, o, result, phases);
+	case 2: return dmma_msg_passes<20, 2>(ctx, o, result, phases);
+	case 3: return dmma_msg_passes<20, 3>(ctx, o, result, phases);
+	case 4: return dmma_msg_passes<20, 4>(ctx, o, result, phases);
+	case 5: return dmma_msg_passes<20, 5>(ctx, o, result, phases);
+	case 6: return dmma_msg_passes<20, 6>(ctx, o, result, phases);
+	default: return dmma_msg_passes<20, 0>(ctx, o, result, phases);
 	}
 }
 template <>
-int dmma_msg_dispatch<61>(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
+int dmma_msg_dispatch<61>(phbc_ctx *ctx, const phbc_eval_opts *o, double *result, int phases) {
 	switch (ctx->tune) {
-	case 1: return dmma_msg_passes<61, 1>(ctx, o, result);
-	case 2: return dmma_msg_passes<61, 2>(ctx, o, result);
-	case 3: return dmma_msg_passes<61, 3>(ctx, o, result);
-	case 4: return dmma_msg_passes<61, 4>(ctx, o, result);
-	default: return dmma_msg_passes<61, 0>(ctx, o, result);
+	case 1: return dmma_msg_passes<61, 1>(ctx, o, result, phases);
+	case 2: return dmma_msg_passes<61, 2>(ctx, o, result, phases);
+	case 3: return dmma_msg_passes<61, 3>(ctx, o, result, phases);
+	case 4: return dmma_msg_passes<61, 4>(ctx, o, result, phases);
+	default: return dmma_msg_passes<61, 0>(ctx, o, result, phases);
 	}
 }
 
 template <int S>
-static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
+static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o, int phases = PHBC_PH_FORWARD | PHBC_PH_GRADIENT) {
 	using Sh = DmmaShape<S>;
 	using Cf = DmmaConfig<S>;
 	const int C = ctx->C, P = ctx->P, N = ctx->N;
+	const bool fwd = phases & PHBC_PH_FORWARD;  // a gradient-only call keeps the transition matrices as they are (d_dP is the caller's)
 	int rc;
 	if (phbc_dwalk_usable(ctx, o)) {
 		// whole-tree walk (phb_dwalk.cu): messages in the lower buffers as in the message form below, upper partials never materialised
 		phbc_eval_opts e = *o;
 		e.want_gradient = 0;  // no upper buffers
-		if ((rc = phbc_generic_prepare(ctx, &e))) return rc;
+		if (fwd && (rc = phbc_generic_prepare(ctx, &e))) return rc;
 		ctx->lower_is_message = true;
-		ctx->node_evals++;
+		if (fwd) ctx->node_evals++;
 		if ((rc = phbc_time_begin(ctx))) return rc;
-		if ((rc = phbc_dwalk_passes(ctx, o, ctx->d_result + (size_t)o->batch_index * (1 + ctx->N)))) return rc;
+		if ((rc = phbc_dwalk_passes(ctx, o, ctx->d_result + (size_t)o->batch_index * (1 + ctx->N), phases))) return rc;
 		if ((rc = phbc_time_end(ctx))) return rc;
 		PHBC_CHECK(cudaGetLastError());
 		return 0;
 	}
-	if ((rc = phbc_generic_prepare(ctx, o))) return rc;
+	if ((rc = fwd ? phbc_generic_prepare(ctx, o) : phbc_generic_buffers(ctx, o))) return rc;
 	Bufs b = phbc_make_bufs(ctx);
 	// message form: the fast path (unscaled, state tips, eigen system, upper partials not needed as such afterwards)
 	bool msg = !o->scale && !o->materialize_uppers && ctx->have_eigen && !o->explicit_matrices;
@@ -1342,23 +1349,23 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {
 	}
 	if ((rc = dmma_pack<S>(ctx, msg, o->include_root_freqs, msg ? 1 : -1))) return rc;
 	ctx->lower_is_message = msg;
-	ctx->node_evals++;
+	if (fwd) ctx->node_evals++;
 	if ((rc = phbc_time_begin(ctx))) return rc;
 	double *result = ctx->d_result + (size_t)o->batch_index * (1 + N);
 	if (msg) {
-		if ((rc = dmma_msg_dispatch<S>(ctx, o, result))) return rc;
+		if ((rc = dmma_msg_dispatch<S>(ctx, o, result, phases))) return rc;
 		if ((rc = phbc_time_end(ctx))) return rc;
 		PHBC_CHECK(cudaGetLastError());
 		return 0;
 	}
-	for (int l = 0; l < ctx->n_lower_levels; l++) {
+	for (int l = 0; fwd && l < ctx->n_lower_levels; l++) {
 		const int beg = ctx->h_lower_level_off[l], cnt = ctx->h_lower_level_off[l + 1] - beg;
 		if (cnt <= 0) continue;
 		if ((rc = dmma_lower_ops<S>(ctx, ctx->d_lower_ops + beg, cnt))) return rc;
 		if (o->scale && (rc = phbc_generic_scale_ops(ctx, ctx->d_lower_ops + beg, cnt, o->scaling_threshold))) return rc;
 	}
-	if ((rc = phbc_generic_root(ctx, o, result))) return rc;
-	if (o->want_gradient) {
+	if (fwd && (rc = phbc_generic_root(ctx, o, result))) return rc;
+	if ((phases & PHBC_PH_GRADIENT) && o->want_gradient) {
 		// fused reductions skip the tips' uppers; under rescaling they give the exact gradient, the reference-compatible per-category
 		// normalisation (PHB_OPT_COMPAT_SCALED_GRADIENT) needs every category's denominator and stays with the generic K9 / K10 kernel
 		const bool grad = !o->materialize_uppers && !(o->scale && o->compat_scaled_gradient);
@@ -1452,6 +1459,44 @@ int phbc_dmma_download_matrices(phbc_ctx *ctx, double *P, double *dP) {
 	PHBC_DMMA_BY_STATES(ctx->S, CALL)
 #undef CALL
 	return -1;
+}
+
+// Node terms of calculate_dlnl_dQ (treelikelihood.c:2337-2583) for nsets per-node matrix sets on the tensor cores: the forward phase
+// once, then ONE gradient phase per set with the set standing in for dP/dt -- the reductions that give d lnL / d t for dP/dt give
+// sum_p w_p / L_p sum_i f_i U_n[i] (M_k L_n)[i] for M_k -- where the node-at-a-time sweep needs every upper partial in HBM and S^2
+// scalar operations per (pattern, node, set).  d_cat [nsets][N][C]: the per-(node, category) sums, before any collapse.
+int phbc_dmma_matrix_gradient(phbc_ctx *ctx, const phbc_eval_opts *o, int nsets, const double *d_M, double *d_cat) {
+	phbc_eval_opts e = *o;
+	e.want_gradient = 1;
+	e.materialize_uppers = 0;
+	int rc = 0;
+	const size_t set = (size_t)ctx->N * ctx->C * ctx->S * ctx->S, nc = (size_t)ctx->N * ctx->C;
+#define CALL(S) dmma_evaluate<S>(ctx, &e, PHBC_PH_FORWARD)
+	switch (ctx->S) {
+	case 20: rc = CALL(20); break;
+	case 60: rc = CALL(60); break;
+	case 61: rc = CALL(61); break;
+	case 62: rc = CALL(62); break;
+	case 63: rc = CALL(63); break;
+	default: return -1;
+	}
+#undef CALL
+	double *own_dP = ctx->d_dP;
+	for (int k = 0; k < nsets && !rc; k++) {
+		ctx->d_dP = const_cast<double *>(d_M) + (size_t)k * set;
+#define CALL(S) dmma_evaluate<S>(ctx, &e, PHBC_PH_GRADIENT)
+		switch (ctx->S) {
+		case 20: rc = CALL(20); break;
+		case 60: rc = CALL(60); break;
+		case 61: rc = CALL(61); break;
+		case 62: rc = CALL(62); break;
+		default: rc = CALL(63); break;
+		}
+#undef CALL
+		if (!rc && cudaMemcpyAsync(d_cat + (size_t)k * nc, ctx->d_cat_grad, nc * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) rc = -2;
+	}
+	ctx->d_dP = own_dP;
+	return rc;
 }
 
 int phbc_dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o) {

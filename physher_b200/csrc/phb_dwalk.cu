@@ -801,7 +801,7 @@ int phbc_dwalk_usable(phbc_ctx *ctx, const phbc_eval_opts *o) {
 
 // the passes of one evaluation on the ctx stream; matrices (d_P, d_dP) are current, the lower buffers exist
 template <class G, int MT>
-static int dw_passes_g(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
+static int dw_passes_g(phbc_ctx *ctx, const phbc_eval_opts *o, double *result, int phases) {
 	DwPlan pl;
 	int rc, usable = 0;
 	if (!dw_plan(ctx, &pl)) {
@@ -825,15 +825,17 @@ static int dw_passes_g(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
 	const int threads = 32 * (pl.nw + 1);
 	auto post = k_dwalk_post<DW_S, MT, G::NWMAX>;
 	auto pre = k_dwalk_pre<DW_S, MT, G::NWMAX>;
-	PHBC_CHECK(cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_post));
-	p.codes = ctx->d_dw_codes, p.ops = ctx->d_dw_post;
-	p.K = pl.Kpost, p.nstg = pl.nstg_post, p.spill = pl.spill_post;
-	const long long gpost = (long long)pl.ctas_post * ctx->num_sms;
-	post<<<(int)(pl.nitems < gpost ? pl.nitems : gpost), threads, pl.smem_post, ctx->stream>>>(p);
-	ctx->launches++;
-	PHBC_CHECK(cudaGetLastError());
-	if ((rc = phbc_generic_root(ctx, o, result))) return rc;
-	if (!o->want_gradient) return 0;
+	if (phases & 1) {  // forward: post-order walk, root integration
+		PHBC_CHECK(cudaFuncSetAttribute(post, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_post));
+		p.codes = ctx->d_dw_codes, p.ops = ctx->d_dw_post;
+		p.K = pl.Kpost, p.nstg = pl.nstg_post, p.spill = pl.spill_post;
+		const long long gpost = (long long)pl.ctas_post * ctx->num_sms;
+		post<<<(int)(pl.nitems < gpost ? pl.nitems : gpost), threads, pl.smem_post, ctx->stream>>>(p);
+		ctx->launches++;
+		PHBC_CHECK(cudaGetLastError());
+		if ((rc = phbc_generic_root(ctx, o, result))) return rc;
+	}
+	if (!(phases & 2) || !o->want_gradient) return 0;
 	if (pl.spill_pre) {
 		const size_t need = (size_t)(ctx->pre_slots - pl.Kpre) * ctx->C * ctx->P * DW_S * sizeof(double);
 		if (need > ctx->dw_spill_bytes) {
@@ -857,6 +859,6 @@ static int dw_passes_g(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
 	PHBC_CHECK(cudaGetLastError());
 	return phbc_gradient_from_partials(ctx, pstride, result);
 }
-int phbc_dwalk_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *result) {
-	return ctx->tune == 16 ? dw_passes_g<DwGeomB, 1>(ctx, o, result) : dw_passes_g<DwGeomA, 2>(ctx, o, result);
+int phbc_dwalk_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *result, int phases) {
+	return ctx->tune == 16 ? dw_passes_g<DwGeomB, 1>(ctx, o, result, phases) : dw_passes_g<DwGeomA, 2>(ctx, o, result, phases);
 }

@@ -55,7 +55,8 @@ def test_gpu_reproduces_reference_dlnl_dq(irf, key, kernels):
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape", [(9, 130, 20, 2), (7, 70, 61, 1), (10, 90, 5, 3)])
 def test_gpu_matrix_gradient_other_state_counts(shape):
-    """20 / 61 states go through the tensor-core lower / upper kernels with every upper partial materialised; 5 states generic."""
+    """20 / 61 states: the forward phase once and one tensor-core gradient phase per matrix set (phbc_dmma_matrix_gradient; the 20-state
+    request runs on the whole-tree walk); 5 states generic."""
     import physher_b200 as phb
     from tests.test_gpu_parity import _synthetic_problem
 
@@ -68,6 +69,37 @@ def test_gpu_matrix_gradient_other_state_counts(shape):
     got = tlk.matrix_gradient(M)
     assert grad_err(got, want) < RTOL
     assert grad_err(tlk.gradient(), O.evaluate(pb)["grad"]) < RTOL
+    tlk.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["rescaled", "ambiguous-tip-partials", "root-freqs-unrooted"])
+@pytest.mark.parametrize("S,C", [(20, 2), (61, 1)])
+def test_gpu_matrix_gradient_tensor_paths(S, C, variant):
+    """the same request on the level-batched kernels the walk / message form decline to: under rescaling (exact gradient from the
+    cumulative scaling factors), with tip partials that carry an ambiguity set, and with the root frequencies folded into the root's
+    children on an unrooted tree (the root's right child is skipped, treelikelihood.c:2408)"""
+    import physher_b200 as phb
+    from physher_b200.treelikelihood import OPT_INCLUDE_ROOT_FREQS, OPT_UNROOTED
+    from tests.test_gpu_parity import _synthetic_problem
+
+    pb = _synthetic_problem(11, 150, S, C, seed=5100 + S, unknown=0.02)
+    if variant == "ambiguous-tip-partials":
+        pb.use_tip_states = False
+        pb.tip_partials = np.eye(S)[np.minimum(pb.tip_states, S - 1)]
+        pb.tip_partials[pb.tip_states >= S] = 1.0
+        pb.tip_partials[2, 7, : S // 3] = 1.0
+    if variant == "root-freqs-unrooted":
+        pb.include_root_freqs = True
+        pb.unrooted = True
+    rng = np.random.default_rng(5101)
+    M = rng.normal(size=(2, pb.nnodes, C, S, S))
+    want = O.matrix_gradient(pb, M)
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    if variant == "rescaled":
+        tlk.use_rescaling(True)
+    got = tlk.matrix_gradient(M)
+    assert grad_err(got, want) < (1e-9 if variant == "rescaled" else RTOL)
     tlk.close()
 
 
