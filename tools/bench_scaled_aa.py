@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """lnL + gradient time of an amino-acid workload that needs rescaling (more taxa than FP64 can hold unscaled, ~230 at 20 states):
 
-    python tools/bench_scaled_aa.py [taxa] [patterns]
+    python tools/bench_scaled_aa.py [taxa] [patterns] [config, default c4]
 
 prints one JSON line: kernel ms per evaluation with rescaling on (what the library switches to by itself after a -inf) and, for
 scale, the unscaled time of the same shape (its lnL is -inf: only the time means anything)."""
@@ -22,15 +22,16 @@ from physher_b200.treelikelihood import OPT_TIMING  # noqa: E402
 def main():
     T = int(sys.argv[1]) if len(sys.argv) > 1 else 400
     P = int(sys.argv[2]) if len(sys.argv) > 2 else 100000
-    cfg = dict(bench.CONFIGS["c4"], taxa=T, patterns=P)
+    base = sys.argv[3] if len(sys.argv) > 3 else "c4"
+    cfg = dict(bench.CONFIGS[base], taxa=T, patterns=P)
     topo, bl, m, rates, props, patterns, weights = bench.make_inputs(cfg, 0)
-    tlk = phb.SingleTreeLikelihood(topo.left, topo.right, topo.root, 20, cfg["cats"], P, use_tip_states=True, device=0)
+    tlk = phb.SingleTreeLikelihood(topo.left, topo.right, topo.root, cfg["states"], cfg["cats"], P, use_tip_states=True, device=0)
     tlk.set_tip_states(patterns)
     tlk.set_pattern_weights(weights)
     tlk.set_eigen(m.evec, m.eval, m.ivec)
     tlk.set_frequencies(m.freqs)
     tlk.set_site_model(rates, props)
-    out = {"taxa": T, "patterns": P}
+    out = {"config": base, "taxa": T, "patterns": P}
     for scaled in (False, True):
         tlk.use_rescaling(scaled)
         tlk.set_branch_lengths(bl)
