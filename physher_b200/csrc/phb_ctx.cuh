@@ -77,6 +77,9 @@ struct phbc_ctx {
 	int cat_grad_cap;
 	double *d_reduce, *h_reduce;  // [N + 2] operand of a sharded evaluation's all-reduce: lnL, grad[N], inf flag (+ pinned host copy)
 	double *d_scratch;       // reduction scratch
+	double *d_rowmax;        // [op slot][C][n-split][P] row maxima left by the tensor-core kernels of a rescaled pass (phb_dmma.cu)
+	size_t rowmax_bytes;
+	int *d_upper_slot;       // [N] child -> 2 x (its parent's index within the sorted level of d_parent_ops) + (child is b)
 	size_t scratch_bytes;
 
 	// time-tree chain (phb_timetree.cu)
@@ -185,6 +188,21 @@ __device__ __forceinline__ const double *partial_ptr(const Bufs &b, int idx, int
 }
 
 __device__ __forceinline__ bool is_state_tip(const Bufs &b, int idx) { return idx < b.T && b.tip_kind == PHBC_TIP_STATES; }
+
+// The dividing half of the rescaling kernels that decide with one thread per (pattern, category): m_s[k] is the maximum of pattern
+// p0 + k where it is rescaled and 0 where it keeps its values.  A category's rows of consecutive patterns are contiguous, so the block
+// sweeps them with coalesced accesses instead of each thread walking its own 8 S-byte row (that walk made the rescaling of upper
+// partials, which happens at most levels, 11 of the 30 ms of a rescaled LG+G4 400 x 50k evaluation).  Same division, same values.
+__device__ __forceinline__ void phbc_rescale_block(const Bufs &b, int out, int p0, int np, const double *m_s) {
+	const int S = b.S, n = (np < b.P - p0 ? np : b.P - p0) * S;
+	for (int c = 0; c < b.C; c++) {
+		double *x = (double *)partial_ptr(b, out, c) + (size_t)p0 * S;
+		for (int e = threadIdx.x; e < n; e += blockDim.x) {
+			const double m = m_s[e / S];
+			if (m > 0.0) x[e] /= m;
+		}
+	}
+}
 
 // message_i = sum_j M[i][j] x[j]; state tips gather a column, unknown states give 1 for probability
 // matrices and the real row sum for derivative matrices (treelikelihoodX.c:166-289, 878-1001).

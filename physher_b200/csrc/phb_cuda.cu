@@ -102,7 +102,7 @@ extern "C" void phbc_destroy(phbc_ctx *ctx) {
 	                ctx->d_walk_lower, ctx->d_walk_gacc, ctx->d_pattern_lnl, ctx->d_result, ctx->d_cat_grad, ctx->d_scratch,
 	                ctx->d_nuc4_codes, ctx->d_nuc4_bad, ctx->d_nuc4_cta_lnl, ctx->d_walk_gstat, ctx->d_nuc4_G, ctx->d_ex, ctx->d_post_tip_order, ctx->d_pre_tip_order, ctx->d_dmma_img, ctx->d_tt_lowers, ctx->d_tt_topo, ctx->d_tt_bad,
 	                ctx->d_tt_ratios, ctx->d_tt_rates, ctx->d_tt_heights, ctx->d_tt_adj, ctx->d_tt_out, ctx->d_reduce,
-	                ctx->d_dw_post, ctx->d_dw_pre, ctx->d_dw_codes, ctx->d_dw_bad, ctx->d_dw_spill, ctx->d_enc_states};
+	                ctx->d_dw_post, ctx->d_dw_pre, ctx->d_dw_codes, ctx->d_dw_bad, ctx->d_dw_spill, ctx->d_enc_states, ctx->d_rowmax, ctx->d_upper_slot};
 	for (size_t i = 0; i < sizeof(bufs) / sizeof(bufs[0]); i++)
 		if (bufs[i]) cudaFree(bufs[i]);
 	if (ctx->ev_beg) {
@@ -198,6 +198,17 @@ extern "C" int phbc_set_schedule(phbc_ctx *ctx, const phbc_schedule *s) {
 	}
 	rc = upload_array(ctx, &ctx->d_lower_ops, lsorted, (size_t)s->n_lower_ops);
 	if (!rc) rc = upload_array(ctx, &ctx->d_parent_ops, psorted, (size_t)s->n_parent_ops);
+	if (!rc) {  // where each child's row maxima sit in its parent's launch (rescaled tensor-core passes)
+		int *slot = (int *)calloc((size_t)ctx->N, sizeof(int));
+		if (!slot) rc = -3;
+		for (int l = 0; !rc && l < s->n_upper_levels; l++)
+			for (int k = s->parent_level_off[l]; k < s->parent_level_off[l + 1]; k++) {
+				slot[psorted[k].a] = 2 * (k - s->parent_level_off[l]);
+				slot[psorted[k].b] = 2 * (k - s->parent_level_off[l]) + 1;
+			}
+		if (!rc) rc = upload_array(ctx, &ctx->d_upper_slot, slot, (size_t)ctx->N);
+		free(slot);
+	}
 	free(lsorted), free(psorted);
 	if (rc) return rc;
 	if ((rc = upload_array(ctx, &ctx->d_upper_ops, s->upper_ops, (size_t)s->n_upper_ops))) return rc;
@@ -507,23 +518,23 @@ __global__ void k_generic_scale(Bufs b, const phbc_op *__restrict__ ops, double 
 // one-thread-per-pattern form (19 of the 33.8 ms of a rescaled LG+G4 400 x 50k evaluation were this kernel), the maximum over the
 // categories by a butterfly over the lane group.  Same values, same factors.
 __global__ void k_generic_scale_split(Bufs b, const phbc_op *__restrict__ ops, double threshold) {
+	__shared__ double m_s[128];
 	const phbc_op op = ops[blockIdx.y];
 	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
 	const int C = b.C, S = b.S;
 	const int p = (int)(t / C), c = (int)(t - (size_t)p * C);
 	const bool live = p < b.P;  // whole lane groups are live or not: P * C is a multiple of C
-	double *x = live ? (double *)partial_ptr(b, op.out, c) + (size_t)p * S : nullptr;
 	double m = 0.0;
-	if (live)
+	if (live) {
+		const double *x = partial_ptr(b, op.out, c) + (size_t)p * S;
 		for (int i = 0; i < S; i++) m = x[i] > m ? x[i] : m;
-	for (int off = C >> 1; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
-	if (!live) return;
-	double sf = 0.0;
-	if (m < threshold && m > 0.0) {
-		for (int i = 0; i < S; i++) x[i] /= m;
-		sf = log(m);
 	}
-	if (c == 0) {
+	for (int off = C >> 1; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+	const bool rescaled = live && m < threshold && m > 0.0;
+	if (c == 0) m_s[threadIdx.x / C] = rescaled ? m : 0.0;
+	if (__syncthreads_or(rescaled)) phbc_rescale_block(b, op.out, (int)((size_t)blockIdx.x * blockDim.x / C), blockDim.x / C, m_s);
+	if (live && c == 0) {
+		double sf = rescaled ? log(m) : 0.0;
 		if (!is_state_tip(b, op.a)) sf += b.sf[(size_t)op.a * b.P + p];
 		if (op.b >= 0 && !is_state_tip(b, op.b)) sf += b.sf[(size_t)op.b * b.P + p];
 		b.sf[(size_t)op.out * b.P + p] = sf;

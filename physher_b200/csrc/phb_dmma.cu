@@ -255,6 +255,57 @@ __device__ __forceinline__ void store_tile(double *__restrict__ U, int p0, int P
 	}
 }
 
+// Rescaling without re-reading the partials: the kernel that produces a partial also leaves, per (op slot, category, n-split, pattern),
+// the largest entry of what it stored (padding columns hold exact zeros).  k_dmma_scale_from_max then decides per pattern from C x
+// NSPLIT numbers instead of C x S, and touches the partial only where a pattern really is rescaled (SingleTreeLikelihood_scalePartials,
+// treelikelihood.c:1790-1836).  The one-thread-per-pattern K5 kernel cost 19 of the 33.8 ms of a rescaled LG+G4 400 x 50k evaluation.
+template <class Sh, int MT, int NTW>
+__device__ __forceinline__ void store_rowmax(double *__restrict__ rowmax, size_t row0 /* ((slot * C + c) * NSPLIT + split) * P */, int p0, int P,
+                                             int n0, int lane, const double (&v)[MT][NTW][2], bool stored) {
+	const int r = lane >> 2, q = lane & 3;
+#pragma unroll
+	for (int m = 0; m < MT; m++) {
+		double mx = 0.0;
+#pragma unroll
+		for (int j = 0; j < NTW; j++) {
+			const int i = (n0 + j) * 8 + 2 * q;  // padding columns are not part of the partial (a gap tip's message is 1 there)
+			if (i < Sh::S) mx = fmax(mx, v[m][j][0]);
+			if (i + 1 < Sh::S) mx = fmax(mx, v[m][j][1]);
+		}
+		mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+		mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+		const int p = p0 + 8 * m + r;
+		if (q == 0 && p < P) rowmax[row0 + p] = stored ? mx : 0.0;  // an upper partial that is not stored: nothing to rescale
+	}
+}
+
+// one thread per (pattern, category); slot_of == NULL: the op's slot is its index in the launch (lower passes), else slot_of[child]
+// (upper passes: 2 x the parent op's index in its level + which child)
+__global__ void k_dmma_scale_from_max(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ rowmax, const int *__restrict__ slot_of,
+                                      int slot0, int nslots, int nsplit, double threshold) {
+	const phbc_op op = ops[blockIdx.y];
+	__shared__ double m_s[128];
+	const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+	const int C = b.C;
+	const int p = (int)(t / C), c = (int)(t - (size_t)p * C);
+	const bool live = p < b.P;
+	const int slot = slot_of ? slot_of[op.out - b.N] - slot0 : (int)blockIdx.y;
+	if (slot < 0 || slot >= nslots) return;  // uniform over the block: this op's producer ran in another chunk of the level
+	double m = 0.0;
+	if (live)
+		for (int k = 0; k < nsplit; k++) m = fmax(m, rowmax[(((size_t)slot * C + c) * nsplit + k) * b.P + p]);
+	for (int off = C >> 1; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, off));
+	const bool rescaled = live && m < threshold && m > 0.0;
+	if (c == 0) m_s[threadIdx.x / C] = rescaled ? m : 0.0;
+	if (__syncthreads_or(rescaled)) phbc_rescale_block(b, op.out, (int)((size_t)blockIdx.x * blockDim.x / C), blockDim.x / C, m_s);
+	if (live && c == 0) {
+		double sf = rescaled ? log(m) : 0.0;
+		if (!is_state_tip(b, op.a)) sf += b.sf[(size_t)op.a * b.P + p];
+		if (op.b >= 0 && !is_state_tip(b, op.b)) sf += b.sf[(size_t)op.b * b.P + p];
+		b.sf[(size_t)op.out * b.P + p] = sf;
+	}
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1-K4: out = (P_a x_a) o (P_b x_b);  grid (pattern chunks, C, ops of the level)
 // warps: WM m-groups x NSPLIT n-groups; a warp owns MT m-tiles and NT / NSPLIT n-tiles.
@@ -262,7 +313,8 @@ __device__ __forceinline__ void store_tile(double *__restrict__ U, int p0, int P
 // busy across its latency) and the A fragments of the next chunk / next tile are in flight while it runs.
 // ---------------------------------------------------------------------------------------------
 template <int S, int MT, int NSPLIT, int WM>
-__global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ img) {
+__global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ img,
+                                                               double *__restrict__ rowmax /* NULL: not rescaling */) {
 	using Sh = DmmaShape<S>;
 	constexpr int NTW = Sh::NT / NSPLIT;
 	static_assert(Sh::NT % NSPLIT == 0, "n-tiles must split evenly");
@@ -366,6 +418,7 @@ dmma_mtiles<MT, NTW, Sh::KCH>(accB, cb, j, tt, bB);
 #pragma unroll
 			for (int j = 0; j < NTW; j++) accA[m][j][0] *= accB[m][j][0], accA[m][j][1] *= accB[m][j][1];
 		store_tile<Sh, MT, NTW>(out, p0, b.P, n0, lane, accA);
+		if (rowmax) store_rowmax<Sh, MT, NTW>(rowmax, (((size_t)blockIdx.z * b.C + c) * NSPLIT + warp % NSPLIT) * b.P, p0, b.P, n0, lane, accA, true);
 	}
 	});
 }
@@ -382,7 +435,7 @@ template <int S, int MT, int NSPLIT, int WM, bool GRAD>
 __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper(Bufs b, const phbc_parent_op *__restrict__ ops, const double *__restrict__ img,
                                                                const double *__restrict__ freqs, const double *__restrict__ weights,
                                                                const double *__restrict__ pattern_lnl, int include_root_freqs, int pstride,
-                                                               double *__restrict__ partial, int scaled) {
+                                                               double *__restrict__ partial, int scaled, double *__restrict__ rowmax) {
 	using Sh = DmmaShape<S>;
 	constexpr int NTW = Sh::NT / NSPLIT;
 	constexpr int NWARPS = WM * NSPLIT;
@@ -580,6 +633,11 @@ dmma_mtiles<MT, NTW, Sh::KCH>(Da, ca, j, tt, bdA);
 			}
 		if (!a_leaf || !GRAD) store_tile<Sh, MT, NTW>(Ua, p0, b.P, n0, lane, Mb);
 		if (!b_leaf || !GRAD) store_tile<Sh, MT, NTW>(Ub, p0, b.P, n0, lane, Ma);
+		if (rowmax) {  // slots 2 z (child a) and 2 z + 1 (child b) of this launch
+			const size_t row = (((size_t)(2 * blockIdx.z) * b.C + c) * NSPLIT + warp % NSPLIT) * b.P;
+			store_rowmax<Sh, MT, NTW>(rowmax, row, p0, b.P, n0, lane, Mb, !a_leaf || !GRAD);
+			store_rowmax<Sh, MT, NTW>(rowmax, row + (size_t)b.C * NSPLIT * b.P, p0, b.P, n0, lane, Ma, !b_leaf || !GRAD);
+		}
 		if (GRAD) {
 #pragma unroll
 			for (int m = 0; m < MT; m++) {
@@ -1066,8 +1124,39 @@ static int dmma_pack(phbc_ctx *ctx, bool adjoint = false, int include_root_freqs
 }
 
 // one level of K1-K4 ops (device list): wave-filling launch geometry, every CTA stages its two matrices once
+// Row maxima scratch of the rescaled passes: `per_op` slots per op of C x nsplit x P doubles, at most 512 MB (a level wider than
+// that is launched in chunks).  *zmax: ops per launch.  Categories must tile a warp (k_dmma_scale_from_max's butterfly).
+static bool dmma_rowmax_usable(const phbc_ctx *ctx) { return ctx->C >= 1 && ctx->C <= 32 && (ctx->C & (ctx->C - 1)) == 0; }
+static int dmma_rowmax_reserve(phbc_ctx *ctx, int nsplit, int per_op, int widest, int *zmax) {
+	const size_t slot = (size_t)ctx->C * nsplit * ctx->P * sizeof(double), cap = (size_t)512 << 20;
+	size_t z = cap / (slot * per_op);
+	if (z < 1) z = 1;
+	if (z > (size_t)widest) z = widest > 0 ? widest : 1;
+	if (z > 65535) z = 65535;
+	const size_t bytes = z * per_op * slot;
+	if (bytes > ctx->rowmax_bytes) {
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		if (ctx->d_rowmax) cudaFree(ctx->d_rowmax);
+		ctx->d_rowmax = NULL, ctx->rowmax_bytes = 0;
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_rowmax, bytes));
+		ctx->rowmax_bytes = bytes;
+	}
+	*zmax = (int)z;
+	return 0;
+}
+static int dmma_scale_from_max(phbc_ctx *ctx, const Bufs &b, const phbc_op *d_ops, int cnt, const int *slot_of, int slot0, int nslots, int nsplit,
+                               double threshold) {
+	const unsigned gx = (unsigned)(((size_t)ctx->P * ctx->C + 127) / 128);
+	for (int y0 = 0; y0 < cnt; y0 += 65535) {
+		const int yc = cnt - y0 < 65535 ? cnt - y0 : 65535;
+		k_dmma_scale_from_max<<<dim3(gx, yc), 128, 0, ctx->stream>>>(b, d_ops + y0, ctx->d_rowmax, slot_of, slot_of ? slot0 : 0, nslots, nsplit, threshold);
+		ctx->launches++;
+	}
+	return 0;
+}
+
 template <int S>
-static int dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
+static int dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt, bool scale = false, double threshold = 0.0) {
 	using Sh = DmmaShape<S>;
 	using Cf = DmmaConfig<S>;
 	const int C = ctx->C, P = ctx->P;
@@ -1079,12 +1168,18 @@ static int dmma_lower_ops(phbc_ctx *ctx, const phbc_op *d_ops, int cnt) {
 	int lper_sm = 1;
 	PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lper_sm, lower, lthreads, lsmem));
 	if (lper_sm < 1) lper_sm = 1;
-	for (int z0 = 0; z0 < cnt; z0 += 65535) {
-		const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
-		lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ltiles), C, zc), lthreads, lsmem, ctx->stream>>>(b, d_ops + z0, ctx->d_dmma_img);
+	int zmax = 65535, rc;
+	const bool fused = scale && dmma_rowmax_usable(ctx);
+	if (fused && (rc = dmma_rowmax_reserve(ctx, Cf::NSPLIT, 1, cnt, &zmax))) return rc;
+	for (int z0 = 0; z0 < cnt; z0 += zmax) {
+		const int zc = cnt - z0 < zmax ? cnt - z0 : zmax;
+		lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ltiles), C, zc), lthreads, lsmem, ctx->stream>>>(b, d_ops + z0, ctx->d_dmma_img,
+		                                                                                                         fused ? ctx->d_rowmax : nullptr);
 		ctx->launches++;
+		if (fused && (rc = dmma_scale_from_max(ctx, b, d_ops + z0, zc, nullptr, 0, zc, Cf::NSPLIT, threshold))) return rc;
 	}
 	PHBC_CHECK(cudaGetLastError());
+	if (scale && !fused) return phbc_generic_scale_ops(ctx, d_ops, cnt, threshold);
 	return 0;
 }
 
@@ -1361,8 +1456,7 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o, int phases = PH
 	for (int l = 0; fwd && l < ctx->n_lower_levels; l++) {
 		const int beg = ctx->h_lower_level_off[l], cnt = ctx->h_lower_level_off[l + 1] - beg;
 		if (cnt <= 0) continue;
-		if ((rc = dmma_lower_ops<S>(ctx, ctx->d_lower_ops + beg, cnt))) return rc;
-		if (o->scale && (rc = phbc_generic_scale_ops(ctx, ctx->d_lower_ops + beg, cnt, o->scaling_threshold))) return rc;
+		if ((rc = dmma_lower_ops<S>(ctx, ctx->d_lower_ops + beg, cnt, o->scale != 0, o->scaling_threshold))) return rc;
 	}
 	if (fwd && (rc = phbc_generic_root(ctx, o, result))) return rc;
 	if ((phases & PHBC_PH_GRADIENT) && o->want_gradient) {
@@ -1389,20 +1483,24 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o, int phases = PH
 		}
 		if ((rc = phbc_ensure_scratch(ctx, (size_t)N * C * pstride * sizeof(double)))) return rc;
 		if (grad) PHBC_CHECK(cudaMemsetAsync(ctx->d_scratch, 0, (size_t)N * C * pstride * sizeof(double), ctx->stream));
+		const bool fused = o->scale && dmma_rowmax_usable(ctx) && ctx->d_upper_slot;
 		for (int l = 0; l < ctx->n_upper_levels; l++) {
 			const int beg = ctx->h_parent_level_off[l], cnt = ctx->h_parent_level_off[l + 1] - beg;
-			if (cnt > 0) {
-				for (int z0 = 0; z0 < cnt; z0 += 65535) {
-					const int zc = cnt - z0 < 65535 ? cnt - z0 : 65535;
-					upper<<<dim3(pick_chunks(uslots, C * zc, utiles), C, zc), uthreads, usmem, ctx->stream>>>(
-					    b, ctx->d_parent_ops + beg + z0, ctx->d_dmma_img, ctx->d_freqs, ctx->d_weights, ctx->d_pattern_lnl, o->include_root_freqs, pstride,
-					    ctx->d_scratch, o->scale ? 1 : 0);
-					ctx->launches++;
-				}
-			}
 			// the children written by this level are the per-child ops of depth l + 1
 			const int ubeg = ctx->h_upper_level_off[l], ucnt = ctx->h_upper_level_off[l + 1] - ubeg;
-			if (o->scale && ucnt > 0 && (rc = phbc_generic_scale_ops(ctx, ctx->d_upper_ops + ubeg, ucnt, o->scaling_threshold))) return rc;
+			int zmax = 65535;
+			if (fused && cnt > 0 && (rc = dmma_rowmax_reserve(ctx, Cf::UNSPLIT, 2, cnt, &zmax))) return rc;
+			for (int z0 = 0; z0 < cnt; z0 += zmax) {
+				const int zc = cnt - z0 < zmax ? cnt - z0 : zmax;
+				upper<<<dim3(pick_chunks(uslots, C * zc, utiles), C, zc), uthreads, usmem, ctx->stream>>>(
+				    b, ctx->d_parent_ops + beg + z0, ctx->d_dmma_img, ctx->d_freqs, ctx->d_weights, ctx->d_pattern_lnl, o->include_root_freqs, pstride,
+				    ctx->d_scratch, o->scale ? 1 : 0, fused ? ctx->d_rowmax : nullptr);
+				ctx->launches++;
+				if (fused && ucnt > 0 &&
+				    (rc = dmma_scale_from_max(ctx, b, ctx->d_upper_ops + ubeg, ucnt, ctx->d_upper_slot, 2 * z0, 2 * zc, Cf::UNSPLIT, o->scaling_threshold)))
+					return rc;
+			}
+			if (o->scale && !fused && ucnt > 0 && (rc = phbc_generic_scale_ops(ctx, ctx->d_upper_ops + ubeg, ucnt, o->scaling_threshold))) return rc;
 		}
 		if (grad) {
 			if ((rc = phbc_gradient_from_partials(ctx, pstride, result))) return rc;
