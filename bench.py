@@ -521,7 +521,7 @@ def parity_gate(run, cfg, kernels, cores, sample_patterns, iters):
     return base, par
 
 
-def roofline_record(name, cfg, P, B, kms, kernels, lib_version):
+def roofline_record(name, cfg, P, B, kms, kernels, lib_version, cherries=0):
     T, S, C = cfg["taxa"], cfg["states"], cfg["cats"]
     sized = dict(cfg, patterns=P)
     peak, peak_src = measured_peak_gbs()
@@ -558,6 +558,16 @@ def roofline_record(name, cfg, P, B, kms, kernels, lib_version):
             rec["note"] = ("launch = the two walk launches (+ root integration) of one evaluation; the walk moves ~%.1f GB where the streaming model "
                            "(hbm.algorithmic_bytes_per_launch) counts %.1f GB, so the path is bound by the FP64 pipe, which DMMA and the element-wise "
                            "products share" % (walk_bytes / 1e9, alg / 1e9))
+        elif P >= 4 * (S + 1) ** 2 and T > 2:
+            # message form: 3 dense products per non-root internal node and pattern (P_n L_n, P_n U_n, U_n (f o dP_n)), padded to 64 states;
+            # cherries are evaluated once per PAIR of tip states and looked up per pattern (k_dmma_cherry_*), their products are not executed
+            executed = 2.0 * 64 * 64 * 3 * (T - 2 - cherries) * C * P
+            rec.update(executed_tensor_flops_per_launch=executed, executed_frac=(executed / (kms * 1e-3) / 1e12 / tpeak) if kms > 0 else None,
+                       cherries=int(cherries))
+            rec["note"] = ("launch = the kernel sequence of one evaluation.  frac is on the ALGORITHMIC flops (SURVEY.md 8d: four S x S mat-vecs per internal "
+                           "operand); the message form executes three products per internal node, and the %d cherries of this tree are evaluated once per "
+                           "pair of tip states ((S+1)^2 = %d pairs against %d patterns) instead of per pattern: executed_frac is what the tensor pipe "
+                           "really issues (padded to 64 states) over the measured DMMA peak" % (cherries, (S + 1) ** 2, P))
         return rec
     hbm.update(kernel="generic node-at-a-time kernels, all levels of one evaluation")
     return hbm
@@ -693,7 +703,8 @@ def run_config(run, name, cfg, K, W, kernels="auto", strong=False, full_cpu_base
         "collective": (f"one ncclAllReduce(sum, double, {N + 2}) per step issued by libphysher_b200 on the evaluation's stream" if (world > 1 and B_total == 1)
                        else "none"),
         "clocks": clocks.summary(),
-        "roofline": roofline_record(name, cfg, P, B, kms_max, kernels, run.phb.load_library().phb_version().decode()),
+        "roofline": roofline_record(name, cfg, P, B, kms_max, kernels, run.phb.load_library().phb_version().decode(),
+                                    cherries=int(np.sum((topo.left[T:] < T) & (topo.right[T:] < T)))),
         "l2": "per-evaluation working set exceeds the 126 MB L2; no explicit flush",
     })
     tlk.close()

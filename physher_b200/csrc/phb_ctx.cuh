@@ -95,6 +95,11 @@ struct phbc_ctx {
 	int dmma_pack_adjoint, dmma_pack_irf;  // how the dP images of internal nodes were packed last (phbc_download_matrices undoes it)
 	uint8_t *d_enc_states;   // [T][P] 0/1 tip partials encoded as states for the message-form kernels (lazily; valid until the next tip upload)
 	bool enc_states_valid, enc_states_bad;
+	double *d_cherry_tab;    // [cherry ops of a launch][C][(S + 1)^2][S] messages of the state pairs (phb_dmma.cu, k_dmma_cherry_gather)
+	size_t cherry_tab_bytes;
+	phbc_op *d_cherry_ops;   // the launch's cherry ops re-pointed at the enumerated pairs
+	int cherry_ops_cap;
+	uint8_t *d_cherry_enum;  // [2][(S + 1)^2] the pairs as two rows of tip states
 	int dmma_pack_tips;      // tips were packed as transposed gather images (2: derivative images frequency-weighted)
 
 	// whole-tree tensor-core walk (phb_dwalk.cu)

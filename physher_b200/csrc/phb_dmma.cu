@@ -685,6 +685,7 @@ dmma_mtiles<MT, NTW, Sh::KCH>(Da, ca, j, tt, bdA);
 // columns of the transposed matrix image for state tips), B is the node's OWN matrix (the identity at the root, whose L then feeds
 // the root integration unchanged).
 // ---------------------------------------------------------------------------------------------
+#define PHBC_OP_TABLE 0x100  // phbc_op.flags of a cherry-table op: the row block of the table is flags >> 9
 template <class Sh>
 __device__ __forceinline__ double tip_value(const double *__restrict__ MT, int s, int col) {
 	return s < Sh::S ? MT[s * Sh::NP + col] : 1.0;  // unknown state: factor 1 (treelikelihood20.c:125-131)
@@ -716,7 +717,8 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 	const int wm = warp / NSPLIT, n0 = (warp % NSPLIT) * NTW;
 	const int r = lane >> 2, q = lane & 3;
 	constexpr int TP = WM * MT * 8;
-	double *out = (double *)dm_partial_ptr(b, op.out, c);
+	// a cherry-table op (see k_dmma_cherry_gather) writes row block flags >> 9 of the table b.lower points at
+	double *out = (op.flags & PHBC_OP_TABLE) ? b.lower + ((size_t)(op.flags >> 9) * b.C + c) * (size_t)b.P * S : (double *)dm_partial_ptr(b, op.out, c);
 	const double *xa = a_tip_rt ? nullptr : dm_partial_ptr(b, op.a, c), *xb = b_tip_rt ? nullptr : dm_partial_ptr(b, op.b, c);
 	const int ntiles = (b.P + TP - 1) / TP;
 	using AS = AStage<Sh, MT, 2, NST>;
@@ -794,6 +796,154 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 		store_tile<Sh, MT, NTW>(out, p0, b.P, n0, lane, acc);
 	}
 	});
+}
+
+// Cherries (both children state tips).  The message of a cherry depends on a pattern only through the PAIR of tip states, and there
+// are (S + 1)^2 pairs (S = unknown) however many patterns there are: 3,844 at 61 states against the 10^6 patterns of C5, where the 34
+// cherry ops were 16.1 of the 38.6 ms of the post-order pass (two shared-memory gathers per A-fragment element, 47 % tensor-pipe use).
+// So the SAME kernel runs on the enumeration of the pairs (k_dmma_cherry_ops re-points the ops at two enumerated "tips" and at a
+// table), and the per-pattern message is a copy of the pair's row: same arithmetic in the same order, bit-identical messages, an
+// HBM-rate kernel instead of a tensor-pipe one.
+__global__ void k_dmma_cherry_ops(const phbc_op *__restrict__ ops, int n, phbc_op *__restrict__ out) {
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	phbc_op op = ops[k];
+	op.a = 0, op.b = 1;  // rows of the enumeration [2][(S + 1)^2]; a_mat / b_mat keep the real tips' matrices, out the node's
+	op.flags = PHBC_OP_TABLE | (k << 9);
+	out[k] = op;
+}
+__global__ void k_dmma_cherry_enum(int S1, uint8_t *__restrict__ e) {
+	const int q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= S1 * S1) return;
+	e[q] = (uint8_t)(q / S1), e[S1 * S1 + q] = (uint8_t)(q % S1);
+}
+template <int S>
+__global__ void __launch_bounds__(256) k_dmma_cherry_gather(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ table) {
+	const phbc_op op = ops[blockIdx.z];
+	const int c = blockIdx.y;
+	constexpr int S1 = S + 1, U = 8;  // U independent (states -> row -> store) chains per thread, resident CTAs looping: one chain per
+	                                 // thread ran at 3 TB/s, and so did two million short-lived CTAs (1,700 waves of one latency chain each)
+	const uint8_t *sta = b.tip_states + (size_t)op.a * b.P, *stb = b.tip_states + (size_t)op.b * b.P;
+	const double *t = table + ((size_t)blockIdx.z * b.C + c) * (size_t)(S1 * S1) * S;
+	double *out = (double *)dm_partial_ptr(b, op.out, c);
+	const size_t n = (size_t)b.P * S, stride = (size_t)gridDim.x * (256 * U);
+	for (size_t e0 = (size_t)blockIdx.x * (256 * U) + threadIdx.x; e0 < n; e0 += stride) {
+		double v[U];
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const size_t e = e0 + (size_t)u * 256;
+			if (e < n) {
+				const int p = (int)(e / S), i = (int)(e - (size_t)p * S);
+				const int sa = min((int)sta[p], S), sb = min((int)stb[p], S);
+				v[u] = t[(size_t)(sa * S1 + sb) * S + i];
+			}
+		}
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const size_t e = e0 + (size_t)u * 256;
+			if (e < n) __stcs(out + e, v[u]);
+		}
+	}
+}
+
+// The pre-order op of a cherry n (children a, b state tips; n not the root) by the same pairs.  Its three branch terms are
+//   g_a = sum_i f_i W[i] M_b[i] dP_a[i][s_a],  g_b likewise,  g_n = sum_j L_n[j] Z[j]     (k_dmma_upper_msg below)
+// with W = P_n U_n and Z = U_n (f o dP_n): every one is LINEAR in U_n with a coefficient row that depends on the pattern only through
+// (s_a, s_b),  g_x = sum_k U_n[k] R_x[pair][k]:   R_a = P_n^T (f o M_b o dP_a[:, s_a]),  R_b likewise,  R_n = f o (dP_n (M_a o M_b)).
+// k_dmma_cherry_upper_tables builds the three rows of every pair (plain FP64: 3 (S + 1)^2 S^2 FMAs per cherry), k_dmma_cherry_upper is
+// then three dot products per pattern against L2-resident rows -- no dense product per pattern at all, where the op ran two.
+// An unknown state selects 1 for a probability column and the row sum for a derivative column, as tip_gather does.
+template <int S>
+__global__ void __launch_bounds__(192) k_dmma_cherry_upper_tables(int C, const phbc_parent_op *__restrict__ ops, const double *__restrict__ Pm,
+                                                                  const double *__restrict__ dPm, const double *__restrict__ freqs,
+                                                                  int include_root_freqs, double *__restrict__ tab) {
+	constexpr int S1 = S + 1, PT = S1 * S1, QB = 2;  // pairs per CTA: the kernel is a latency chain per pair, a level's few cherries need the CTAs
+	__shared__ double v[3][64];
+	const phbc_parent_op op = ops[blockIdx.z];
+	const int c = blockIdx.y;
+	constexpr size_t SS = (size_t)S * S;
+	const double *Pn = Pm + ((size_t)op.node * C + c) * SS, *dPn = dPm + ((size_t)op.node * C + c) * SS;
+	const double *Pa = Pm + ((size_t)op.a * C + c) * SS, *dPa = dPm + ((size_t)op.a * C + c) * SS;
+	const double *Pb = Pm + ((size_t)op.b * C + c) * SS, *dPb = dPm + ((size_t)op.b * C + c) * SS;
+	const int which = threadIdx.x >> 6, k = threadIdx.x & 63;
+	double *t = tab + (((size_t)blockIdx.z * C + c) * 3 + which) * (size_t)PT * S;
+	const int q1 = min(PT, (int)(blockIdx.x + 1) * QB);
+	for (int q = blockIdx.x * QB; q < q1; q++) {
+		const int sa = q / S1, sb = q - sa * S1;
+		__syncthreads();
+		if (threadIdx.x < S) {
+			const int i = threadIdx.x;
+			const double f = include_root_freqs ? 1.0 : freqs[i];
+			double ma = 1.0, mb = 1.0, da = 0.0, db = 0.0;
+			if (sa < S) ma = Pa[i * S + sa], da = dPa[i * S + sa];
+			else
+				for (int j = 0; j < S; j++) da += dPa[i * S + j];
+			if (sb < S) mb = Pb[i * S + sb], db = dPb[i * S + sb];
+			else
+				for (int j = 0; j < S; j++) db += dPb[i * S + j];
+			v[0][i] = ma * mb, v[1][i] = f * mb * da, v[2][i] = f * ma * db;
+		}
+		__syncthreads();
+		if (k < S) {
+			double acc[4] = {0.0, 0.0, 0.0, 0.0};  // four chains, summed in a fixed order
+			if (which == 0) {
+#pragma unroll 4
+				for (int j = 0; j < S; j++) acc[j & 3] = fma(dPn[k * S + j], v[0][j], acc[j & 3]);
+			} else {
+#pragma unroll 4
+				for (int i = 0; i < S; i++) acc[i & 3] = fma(Pn[i * S + k], v[which][i], acc[i & 3]);
+			}
+			const double r = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+			t[(size_t)q * S + k] = which == 0 ? r * (include_root_freqs ? 1.0 : freqs[k]) : r;
+		}
+	}
+}
+template <int S>
+__global__ void __launch_bounds__(256) k_dmma_cherry_upper(Bufs b, const phbc_parent_op *__restrict__ ops, const double *__restrict__ tab,
+                                                           const double *__restrict__ weights, const double *__restrict__ pattern_lnl, int pstride,
+                                                           double *__restrict__ partial) {
+	constexpr int S1 = S + 1, PT = S1 * S1;
+	__shared__ double red[8][3];
+	const phbc_parent_op op = ops[blockIdx.z];
+	const int c = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int l8 = lane & 7, sub = lane >> 3;  // eight lanes to a pattern, four patterns to a warp: 8 x 4 independent loads per thread in flight
+	const double *u = b.upper + ((size_t)op.node * b.C + c) * (size_t)b.P * S;
+	const double *tn = tab + ((size_t)blockIdx.z * b.C + c) * 3 * (size_t)PT * S, *ta = tn + (size_t)PT * S, *tb = ta + (size_t)PT * S;
+	const uint8_t *sta = b.tip_states + (size_t)op.a * b.P, *stb = b.tip_states + (size_t)op.b * b.P;
+	double tot_n = 0.0, tot_a = 0.0, tot_b = 0.0;
+	for (int p0 = (blockIdx.x * 8 + warp) * 4; p0 < b.P; p0 += gridDim.x * 32) {
+		const int p = p0 + sub;
+		const bool live = p < b.P;
+		double gn = 0.0, ga = 0.0, gb = 0.0, wl = 0.0;
+		if (live) {
+			const size_t row = (size_t)(min((int)sta[p], S) * S1 + min((int)stb[p], S)) * S;
+			if (l8 == 0) wl = __ldg(weights + p) / exp(__ldg(pattern_lnl + p));
+			const double *up = u + (size_t)p * S;
+#pragma unroll
+			for (int k0 = 0; k0 < S; k0 += 8) {
+				const int k = k0 + l8;
+				if (k < S) {
+					const double x = __ldcs(up + k);
+					gn = fma(x, tn[row + k], gn), ga = fma(x, ta[row + k], ga), gb = fma(x, tb[row + k], gb);
+				}
+			}
+		}
+#pragma unroll
+		for (int off = 1; off < 8; off <<= 1) {
+			gn += __shfl_xor_sync(0xffffffffu, gn, off), ga += __shfl_xor_sync(0xffffffffu, ga, off), gb += __shfl_xor_sync(0xffffffffu, gb, off);
+		}
+		tot_n = fma(gn, wl, tot_n), tot_a = fma(ga, wl, tot_a), tot_b = fma(gb, wl, tot_b);  // wl = 0 off the group's first lane
+	}
+	tot_n = phb_warp_sum(tot_n), tot_a = phb_warp_sum(tot_a), tot_b = phb_warp_sum(tot_b);
+	if (lane == 0) red[warp][0] = tot_n, red[warp][1] = tot_a, red[warp][2] = tot_b;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		double sn = 0.0, sa = 0.0, sb = 0.0;
+		for (int w = 0; w < 8; w++) sn += red[w][0], sa += red[w][1], sb += red[w][2];
+		partial[((size_t)op.node * b.C + c) * pstride + blockIdx.x] = sn;
+		partial[((size_t)op.a * b.C + c) * pstride + blockIdx.x] = sa;
+		partial[((size_t)op.b * b.C + c) * pstride + blockIdx.x] = sb;
+	}
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1228,6 +1378,35 @@ static Bufs dmma_msg_bufs(phbc_ctx *ctx) {
 	return b;
 }
 
+// cherry tables (k_dmma_cherry_gather, k_dmma_cherry_upper): used where there are (4 x) more patterns than state pairs;
+// PHB_OPT_TUNE 20 / 21: always / never.  One buffer serves both passes, at most 256 MB: wider levels go in chunks of *zmax ops.
+template <int S>
+static bool dmma_cherry_tables_on(const phbc_ctx *ctx) {
+	return ctx->tune != 21 && (ctx->tune == 20 || ctx->P >= 4 * (S + 1) * (S + 1));
+}
+static int dmma_cherry_reserve(phbc_ctx *ctx, size_t per_op, int count, int *zmax) {
+	size_t z = ((size_t)256 << 20) / per_op;
+	if (z < 1) z = 1;
+	if (z > (size_t)count) z = count;
+	if (z > 32767) z = 32767;  // gridDim.z, and phbc_op.flags >> 9 stays positive
+	if (z * per_op > ctx->cherry_tab_bytes) {
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		if (ctx->d_cherry_tab) cudaFree(ctx->d_cherry_tab);
+		ctx->d_cherry_tab = NULL, ctx->cherry_tab_bytes = 0;
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_cherry_tab, z * per_op));
+		ctx->cherry_tab_bytes = z * per_op;
+	}
+	if ((int)z > ctx->cherry_ops_cap) {
+		PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+		if (ctx->d_cherry_ops) cudaFree(ctx->d_cherry_ops);
+		ctx->d_cherry_ops = NULL, ctx->cherry_ops_cap = 0;
+		PHBC_CHECK(cudaMalloc((void **)&ctx->d_cherry_ops, z * sizeof(phbc_op)));
+		ctx->cherry_ops_cap = (int)z;
+	}
+	*zmax = (int)z;
+	return 0;
+}
+
 // one level of message-form lower ops: three launches by the number of tip children (the device op list is sorted that way), so
 // that ops without tip children do not pay shared memory for tip images (61 states: 3 CTAs per SM instead of 1)
 template <int S, int VAR>
@@ -1254,6 +1433,30 @@ static int dmma_lower_msg_level(phbc_ctx *ctx, int level) {
 		int lper_sm = 1;
 		PHBC_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lper_sm, lower, lthreads, lsmem));
 		if (lper_sm < 1) lper_sm = 1;
+		// cherries through the table of state pairs
+		constexpr int S1 = S + 1, PT = S1 * S1;
+		if (kind == 2 && split && dmma_cherry_tables_on<S>(ctx)) {
+			int zmax = 1, rc;
+			if ((rc = dmma_cherry_reserve(ctx, (size_t)C * PT * S * sizeof(double), end - beg, &zmax))) return rc;
+			if (!ctx->d_cherry_enum) {
+				PHBC_CHECK(cudaMalloc((void **)&ctx->d_cherry_enum, 2 * PT));
+				k_dmma_cherry_enum<<<(PT + 255) / 256, 256, 0, ctx->stream>>>(S1, ctx->d_cherry_enum);
+				ctx->launches++;
+			}
+			Bufs bt = b;  // the pairs as a pattern set of their own: two enumerated tips, the table in place of the lower buffers
+			bt.P = PT, bt.tip_states = ctx->d_cherry_enum, bt.tip_kind = PHBC_TIP_STATES, bt.lower = ctx->d_cherry_tab;
+			const int ttiles = (PT + Cf::WM * Cf::MT * 8 - 1) / (Cf::WM * Cf::MT * 8);
+			for (int z0 = beg; z0 < end; z0 += zmax) {
+				const int zc = end - z0 < zmax ? end - z0 : zmax;
+				k_dmma_cherry_ops<<<(zc + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_lower_ops + z0, zc, ctx->d_cherry_ops);
+				lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ttiles), C, zc), lthreads, lsmem, ctx->stream>>>(bt, ctx->d_cherry_ops, ctx->d_dmma_img, nimg);
+				const size_t gtiles = ((size_t)P * S + 8 * 256 - 1) / (8 * 256);
+				const int gx = pick_chunks(8 * ctx->num_sms, C * zc, gtiles > 65535 ? 65535 : (int)gtiles);
+				k_dmma_cherry_gather<S><<<dim3((unsigned)gx, C, zc), 256, 0, ctx->stream>>>(b, ctx->d_lower_ops + z0, ctx->d_cherry_tab);
+				ctx->launches += 3;
+			}
+			continue;
+		}
 		for (int z0 = beg; z0 < end; z0 += 65535) {
 			const int zc = end - z0 < 65535 ? end - z0 : 65535;
 			lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ltiles), C, zc), lthreads, lsmem, ctx->stream>>>(b, ctx->d_lower_ops + z0, ctx->d_dmma_img, nimg);
@@ -1339,6 +1542,8 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 			else end = ctx->h_parent_kind_off[4 * l + 3];
 		}
 	};
+	// cherries (never the root: a tree of more than two taxa) by the table of state pairs
+	const bool cherries = split && ctx->T > 2 && dmma_cherry_tables_on<S>(ctx);
 	int pstride = 1;
 	for (int l = 0; l < ctx->n_upper_levels; l++)
 		for (int kind = 0; kind < 3; kind++) {
@@ -1348,6 +1553,14 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 				const int k = pick_chunks(var[kind].slots, C * (end - z0 < 65535 ? end - z0 : 65535), var[kind].tiles);
 				if (k > pstride) pstride = k;
 			}
+			if (kind == 2 && cherries && end > beg) {  // k_dmma_cherry_upper: 8 resident CTAs of 8 warps per SM, 32 patterns a turn
+				int zmax = 1;
+				if ((rc = dmma_cherry_reserve(ctx, (size_t)3 * C * (S + 1) * (S + 1) * S * sizeof(double), end - beg, &zmax))) return rc;
+				for (int z0 = beg; z0 < end; z0 += zmax) {
+					const int k = pick_chunks(8 * ctx->num_sms, C * (end - z0 < zmax ? end - z0 : zmax), (P + 31) / 32);
+					if (k > pstride) pstride = k;
+				}
+			}
 		}
 	if ((rc = phbc_ensure_scratch(ctx, (size_t)N * C * pstride * sizeof(double)))) return rc;
 	PHBC_CHECK(cudaMemsetAsync(ctx->d_scratch, 0, (size_t)N * C * pstride * sizeof(double), ctx->stream));
@@ -1356,6 +1569,20 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 			int beg, end;
 			group(l, kind, beg, end);
 			const Variant &v = var[kind];
+			if (kind == 2 && cherries && end > beg) {
+				constexpr int PT = (S + 1) * (S + 1);
+				int zmax = 1;
+				if ((rc = dmma_cherry_reserve(ctx, (size_t)3 * C * PT * S * sizeof(double), end - beg, &zmax))) return rc;
+				for (int z0 = beg; z0 < end; z0 += zmax) {
+					const int zc = end - z0 < zmax ? end - z0 : zmax;
+					k_dmma_cherry_upper_tables<S><<<dim3((PT + 1) / 2, C, zc), 192, 0, ctx->stream>>>(C, ctx->d_parent_ops + z0, ctx->d_P, ctx->d_dP, ctx->d_freqs,
+					                                                                                      o->include_root_freqs, ctx->d_cherry_tab);
+					k_dmma_cherry_upper<S><<<dim3(pick_chunks(8 * ctx->num_sms, C * zc, (P + 31) / 32), C, zc), 256, 0, ctx->stream>>>(
+					    b, ctx->d_parent_ops + z0, ctx->d_cherry_tab, ctx->d_weights, ctx->d_pattern_lnl, pstride, ctx->d_scratch);
+					ctx->launches += 2;
+				}
+				continue;
+			}
 			for (int z0 = beg; z0 < end; z0 += 65535) {
 				const int zc = end - z0 < 65535 ? end - z0 : 65535;
 				v.fn<<<dim3(pick_chunks(v.slots, C * zc, v.tiles), C, zc), v.threads, v.smem, ctx->stream>>>(

@@ -100,7 +100,7 @@ const char *phb_last_error(void) { return g_err; }
 int phb_internal_fail(int code, const char *msg) { return fail(code, "%s", msg); }
 int phb_device_count(void) { return phbc_device_count(); }
 /* the kernel revision tag ties committed ncu captures (profiles/traffic.json) to the kernels they were taken on */
-const char *phb_version(void) { return "physher_b200 0.2 (sm_100a; kernels r2w)"; }
+const char *phb_version(void) { return "physher_b200 0.2 (sm_100a; walk kernels r2w, level kernels r2z)"; }
 
 /* ------------------------------------------------------------------------------------------- */
 /* schedules                                                                                   */

@@ -581,3 +581,67 @@ def test_incremental_reads_see_the_stale_ancestors_recomputed():
     assert grad_err(tlk.root_frequency_gradient(), gen.root_frequency_gradient()) < RTOL
     gen.close()
     tlk.close()
+
+
+def _eval_tuned(pb, tune):
+    from physher_b200.treelikelihood import OPT_TUNE
+    tlk = phb.SingleTreeLikelihood.from_problem(pb)
+    tlk.set_option(OPT_TUNE, tune)
+    lnl, plnl, g, launches = tlk.calculate(), tlk.pattern_log_likelihoods().copy(), tlk.gradient().copy(), tlk.launch_count()
+    assert tlk.last_kernels() == phb.treelikelihood.RAN_TENSOR
+    tlk.close()
+    return lnl, plnl, g, launches
+
+
+@pytest.mark.parametrize("shape", [(61, 9, 300, 2), (61, 2, 50, 1), (60, 6, 33, 1), (63, 12, 129, 1)], ids=lambda s: "S%d-T%d-P%d-C%d" % s)
+def test_cherry_tables(shape):
+    """cherries evaluated once per PAIR of tip states (forced on by PHB_OPT_TUNE 20, off by 21).  Post-order pass: the pair's message
+    copied per pattern (k_dmma_cherry_gather) -- the same arithmetic in the same order, so not one bit of any pattern likelihood
+    differs.  Pre-order pass: the cherry's three branch terms as dot products of U_n with the pair's coefficient rows
+    (k_dmma_cherry_upper) -- another summation order, same gradient to rounding.  Both against the oracle; unknown states included."""
+    S, T, P, C = shape
+    pb = _synthetic_problem(T, P, S, C, seed=4200 + S + T, unknown=0.05)
+    want = O.evaluate(pb)
+    a, b = _eval_tuned(pb, 20), _eval_tuned(pb, 21)
+    assert rel_err(a[0], want["lnl"]) < RTOL and grad_err(a[2], want["grad"]) < RTOL
+    assert rel_err(b[0], want["lnl"]) < RTOL and grad_err(b[2], want["grad"]) < RTOL
+    assert a[0] == b[0]
+    np.testing.assert_array_equal(a[1], b[1])
+    assert grad_err(a[2], b[2]) < 1e-11
+    assert a[3] != b[3]  # the table path really ran
+
+
+def test_cherry_tables_include_root_freqs_and_matrix_gradient():
+    """the frequency weights move from the gradient sums into the upper partials (tlk->include_root_freqs); the substitution-model
+    sweep runs the pre-order pass once per matrix set on swapped derivative matrices, tables included"""
+    from physher_b200.treelikelihood import OPT_TUNE
+    pb = _synthetic_problem(10, 120, 61, 1, seed=4290, unknown=0.04)
+    pb.include_root_freqs = True
+    want = O.evaluate(pb)
+    res = {}
+    for tune in (20, 21):
+        tlk = phb.SingleTreeLikelihood.from_problem(pb)
+        tlk.set_option(OPT_TUNE, tune)
+        tlk.set_option(OPT_INCLUDE_ROOT_FREQS, 1)
+        assert grad_err(tlk.gradient(), want["grad"]) < RTOL
+        rng = np.random.default_rng(5)
+        M = rng.standard_normal((2, pb.nnodes, len(pb.rates), 61, 61)) * 1e-2
+        res[tune] = tlk.matrix_gradient(M)
+        tlk.close()
+    np.testing.assert_allclose(res[20], res[21], rtol=1e-9, atol=1e-9 * np.abs(res[21]).max())
+
+
+def test_cherry_tables_switch_on_by_pattern_count_and_take_encoded_tip_partials():
+    """20 states on the level-batched kernels (PHB_OPT_TUNE 9): 441 pairs, tables from 1,764 patterns on; 0/1 tip partials"""
+    pb = _synthetic_problem(14, 2000, 20, 2, seed=4260, unknown=0.03)
+    want = O.evaluate(pb)
+    lnl, plnl, g, launches = _eval_tuned(pb, 9)
+    assert rel_err(lnl, want["lnl"]) < RTOL and grad_err(g, want["grad"]) < RTOL
+    small = _synthetic_problem(14, 1000, 20, 2, seed=4260, unknown=0.03)
+    assert _eval_tuned(small, 9)[3] < launches
+    pb.use_tip_states = False
+    pb.tip_partials = np.eye(21)[np.minimum(pb.tip_states, 20)][:, :, :20]
+    pb.tip_partials[pb.tip_states >= 20] = 1.0
+    lnl2, plnl2, g2, _ = _eval_tuned(pb, 9)
+    assert lnl2 == lnl
+    np.testing.assert_array_equal(g2, g)
