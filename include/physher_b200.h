@@ -66,7 +66,8 @@ extern "C" {
                                             whole-tree walk (phb_dwalk.cu); walk variants 11 = one shared-memory slot (parked values spill to HBM),
                                             12 / 14 = 8 / 4 consumer warps whatever the pattern count, 13 = 11 + 12, 15 = warp pairs take turns on
                                             the tensor pipe, 16 = 12 consumer warps x 8 patterns.  Level-batched message kernels: 20 / 21 =
-                                            cherries by pairs of tip states always / never (default: from 4 (S + 1)^2 patterns on) */
+                                            cherries by pairs of tip states always / never (default: from 4 (S + 1)^2 patterns on), 22 = rescaled
+                                            evaluations on the node-at-a-time tensor-core kernels instead of the message form */
 
 #define PHB_KERNELS_AUTO 0    /* by state count, like the function-pointer dispatch at treelikelihood.c:1067-1165 */
 #define PHB_KERNELS_GENERIC 1 /* node-at-a-time kernels, any state count, materialised upper partials */

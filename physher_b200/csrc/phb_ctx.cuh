@@ -99,6 +99,8 @@ struct phbc_ctx {
 	size_t cherry_tab_bytes;
 	phbc_op *d_cherry_ops;   // the launch's cherry ops re-pointed at the enumerated pairs
 	int cherry_ops_cap;
+	double *d_cherry_pairmax;  // rescaling: [cherry ops of a launch][C][(S + 1)^2] largest entry of the pair's L_n
+	size_t cherry_pairmax_bytes;
 	uint8_t *d_cherry_enum;  // [2][(S + 1)^2] the pairs as two rows of tip states
 	int dmma_pack_tips;      // tips were packed as transposed gather images (2: derivative images frequency-weighted)
 

@@ -692,7 +692,8 @@ __device__ __forceinline__ double tip_value(const double *__restrict__ MT, int s
 }
 
 template <int S, int MT, int NSPLIT, int WM, int NST = 0, int GB = 1>
-__global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ img, int nimg) {
+__global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ img, int nimg,
+                                                                   double *__restrict__ rowmax /* rescaling: [op of the launch][C][P] max of L_n, else NULL */) {
 	using Sh = DmmaShape<S>;
 	constexpr int NTW = Sh::NT / NSPLIT;
 	static_assert(Sh::NT % NSPLIT == 0, "n-tiles must split evenly");
@@ -758,6 +759,9 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 		}
 		double acc[MT][NTW][2];
 		zero_acc<MT, NTW>(acc);
+		double lmax[MT];  // rescaling: the largest entry of L_n per row, what SingleTreeLikelihood_scalePartials compares with the threshold
+#pragma unroll
+		for (int m = 0; m < MT; m++) lmax[m] = 0.0;
 #pragma unroll
 		for (int ch = 0; ch < Sh::NCH; ch++) {
 			cp_async_wait<AS::NSTAGE - 2>();
@@ -777,6 +781,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 						if (a_tip) ca[m][tt] = tip_value<Sh>(mA, sa[m], col);
 						if (b_tip) cb[m][tt] = tip_value<Sh>(mB, sb[m], col);
 						ca[m][tt] *= cb[m][tt];  // L_n = M_a o M_b, straight into the A fragment
+						if (rowmax && col < S) lmax[m] = fmax(lmax[m], ca[m][tt]);
 					} else ca[m][tt] = 0.0;
 				}
 #pragma unroll
@@ -794,6 +799,15 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 			}
 		}
 		store_tile<Sh, MT, NTW>(out, p0, b.P, n0, lane, acc);
+		if (rowmax && warp % NSPLIT == 0) {  // every n-split warp of the group formed the same L_n
+#pragma unroll
+			for (int m = 0; m < MT; m++) {
+				double mx = fmax(lmax[m], __shfl_xor_sync(0xffffffffu, lmax[m], 1));
+				mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+				const int p = p0 + 8 * m + r;
+				if (q == 0 && p < b.P) rowmax[((size_t)blockIdx.z * b.C + c) * b.P + p] = mx;
+			}
+		}
 	}
 	});
 }
@@ -818,7 +832,8 @@ __global__ void k_dmma_cherry_enum(int S1, uint8_t *__restrict__ e) {
 	e[q] = (uint8_t)(q / S1), e[S1 * S1 + q] = (uint8_t)(q % S1);
 }
 template <int S>
-__global__ void __launch_bounds__(256) k_dmma_cherry_gather(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ table) {
+__global__ void __launch_bounds__(256) k_dmma_cherry_gather(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ table,
+                                                            const double *__restrict__ pairmax, double *__restrict__ rowmax) {
 	const phbc_op op = ops[blockIdx.z];
 	const int c = blockIdx.y;
 	constexpr int S1 = S + 1, U = 8;  // U independent (states -> row -> store) chains per thread, resident CTAs looping: one chain per
@@ -836,6 +851,8 @@ __global__ void __launch_bounds__(256) k_dmma_cherry_gather(Bufs b, const phbc_o
 				const int p = (int)(e / S), i = (int)(e - (size_t)p * S);
 				const int sa = min((int)sta[p], S), sb = min((int)stb[p], S);
 				v[u] = t[(size_t)(sa * S1 + sb) * S + i];
+				// rescaling: the row maximum of L_n is the pair's as well ([op of the launch][C][pairs] -> [op][C][P])
+				if (rowmax && i == 0) rowmax[((size_t)blockIdx.z * b.C + c) * b.P + p] = pairmax[((size_t)blockIdx.z * b.C + c) * (S1 * S1) + sa * S1 + sb];
 			}
 		}
 #pragma unroll
@@ -901,7 +918,7 @@ __global__ void __launch_bounds__(192) k_dmma_cherry_upper_tables(int C, const p
 template <int S>
 __global__ void __launch_bounds__(256) k_dmma_cherry_upper(Bufs b, const phbc_parent_op *__restrict__ ops, const double *__restrict__ tab,
                                                            const double *__restrict__ weights, const double *__restrict__ pattern_lnl, int pstride,
-                                                           double *__restrict__ partial) {
+                                                           double *__restrict__ partial, int scaled) {
 	constexpr int S1 = S + 1, PT = S1 * S1;
 	__shared__ double red[8][3];
 	const phbc_parent_op op = ops[blockIdx.z];
@@ -917,7 +934,8 @@ __global__ void __launch_bounds__(256) k_dmma_cherry_upper(Bufs b, const phbc_pa
 		double gn = 0.0, ga = 0.0, gb = 0.0, wl = 0.0;
 		if (live) {
 			const size_t row = (size_t)(min((int)sta[p], S) * S1 + min((int)stb[p], S)) * S;
-			if (l8 == 0) wl = __ldg(weights + p) / exp(__ldg(pattern_lnl + p));
+			// rescaling: U_n carries exp(-sf[N + n]); the children are tips (see k_dmma_upper)
+			if (l8 == 0) wl = __ldg(weights + p) / exp(__ldg(pattern_lnl + p) - (scaled ? b.sf[(size_t)(b.N + op.node) * b.P + p] : 0.0));
 			const double *up = u + (size_t)p * S;
 #pragma unroll
 			for (int k0 = 0; k0 < S; k0 += 8) {
@@ -962,7 +980,7 @@ template <int S, int MT, int NSPLIT, int WM, int NST = 0, int GB = 1>
 __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, const phbc_parent_op *__restrict__ ops, const double *__restrict__ img,
                                                                    const double *__restrict__ freqs, const double *__restrict__ weights,
                                                                    const double *__restrict__ pattern_lnl, int include_root_freqs, int pstride,
-                                                                   double *__restrict__ partial, int nslots) {
+                                                                   double *__restrict__ partial, int nslots, int scaled, double *__restrict__ rowmax) {
 	using Sh = DmmaShape<S>;
 	constexpr int NTW = Sh::NT / NSPLIT;
 	constexpr int NWARPS = WM * NSPLIT;
@@ -1055,6 +1073,12 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 			const int p = p0 + 8 * m + r;
 			wk[m] = p < b.P ? __ldg(weights + p) : 0.0;
 			lk[m] = p < b.P ? __ldg(pattern_lnl + p) : 0.0;
+			if (scaled && p < b.P) {  // every branch term of this op carries exp(-(sf[N + n] + sf[a] + sf[b])), see k_dmma_upper
+				double e = is_root ? 0.0 : b.sf[(size_t)(b.N + op.node) * b.P + p];
+				if (!a_tip) e += b.sf[(size_t)op.a * b.P + p];
+				if (!b_tip) e += b.sf[(size_t)op.b * b.P + p];
+				lk[m] -= e;
+			}
 		}
 		double W[MT][NTW][2], Z[MT][NTW][2], Mb[MT][NTW][2], Ma[MT][NTW][2];
 		zero_acc<MT, NTW>(W);
@@ -1144,6 +1168,11 @@ dmma_mtiles<MT, NTW, Sh::KCH>(Z, cw, j, tt, bZ);
 		}
 		if (!a_tip) store_tile<Sh, MT, NTW>(Ua, p0, b.P, n0, lane, Mb);
 		if (!b_tip) store_tile<Sh, MT, NTW>(Ub, p0, b.P, n0, lane, Ma);
+		if (rowmax) {  // rescaling: slots 2 z (child a) and 2 z + 1 (child b) of this launch, as k_dmma_upper
+			const size_t row = (((size_t)(2 * blockIdx.z) * b.C + c) * NSPLIT + warp % NSPLIT) * b.P;
+			store_rowmax<Sh, MT, NTW>(rowmax, row, p0, b.P, n0, lane, Mb, !a_tip);
+			store_rowmax<Sh, MT, NTW>(rowmax, row + (size_t)b.C * NSPLIT * b.P, p0, b.P, n0, lane, Ma, !b_tip);
+		}
 #pragma unroll
 		for (int m = 0; m < MT; m++) {
 			double ga = 0.0, gb = 0.0, g0 = gn[m];
@@ -1294,6 +1323,16 @@ static int dmma_rowmax_reserve(phbc_ctx *ctx, int nsplit, int per_op, int widest
 	*zmax = (int)z;
 	return 0;
 }
+// the message-form passes scale a whole level at once: [slots][C][n-split][P], 1 / S of the level's partials
+static int dmma_rowmax_reserve_level(phbc_ctx *ctx, size_t bytes) {
+	if (bytes <= ctx->rowmax_bytes) return 0;
+	PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+	if (ctx->d_rowmax) cudaFree(ctx->d_rowmax);
+	ctx->d_rowmax = NULL, ctx->rowmax_bytes = 0;
+	PHBC_CHECK(cudaMalloc((void **)&ctx->d_rowmax, bytes));
+	ctx->rowmax_bytes = bytes;
+	return 0;
+}
 static int dmma_scale_from_max(phbc_ctx *ctx, const Bufs &b, const phbc_op *d_ops, int cnt, const int *slot_of, int slot0, int nslots, int nsplit,
                                double threshold) {
 	const unsigned gx = (unsigned)(((size_t)ctx->P * ctx->C + 127) / 128);
@@ -1410,11 +1449,20 @@ static int dmma_cherry_reserve(phbc_ctx *ctx, size_t per_op, int count, int *zma
 // one level of message-form lower ops: three launches by the number of tip children (the device op list is sorted that way), so
 // that ops without tip children do not pay shared memory for tip images (61 states: 3 CTAs per SM instead of 1)
 template <int S, int VAR>
-static int dmma_lower_msg_level(phbc_ctx *ctx, int level) {
+static int dmma_lower_msg_level(phbc_ctx *ctx, int level, const phbc_eval_opts *o) {
 	using Sh = DmmaShape<S>;
 	using Cf = MsgCfg<S, VAR>;
 	const int C = ctx->C, P = ctx->P;
 	Bufs b = dmma_msg_bufs(ctx);
+	// rescaling (SingleTreeLikelihood_scalePartials, treelikelihood.c:1790-1836, on the message form): the kernels leave the largest
+	// entry of L_n per (op of the level, category, pattern), k_dmma_scale_from_max decides per pattern and divides the MESSAGE --
+	// P_n (L_n / m) = (P_n L_n) / m -- with the cumulative factors in sf as on the node-at-a-time path
+	const int lbeg = ctx->h_lower_level_off[level], lend = ctx->h_lower_level_off[level + 1];
+	const bool scale = o->scale != 0;
+	if (scale) {
+		int rc;
+		if ((rc = dmma_rowmax_reserve_level(ctx, (size_t)(lend - lbeg) * C * P * sizeof(double)))) return rc;
+	}
 	auto lower = k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM, Cf::LNST, Cf::LGB>;
 	const size_t ring = (size_t)Cf::WM * AStage<Sh, Cf::MT, 2, Cf::LNST>::NSTAGE * AStage<Sh, Cf::MT, 2, Cf::LNST>::STG;
 	const int lthreads = 32 * Cf::WM * Cf::NSPLIT, ltiles = (P + Cf::WM * Cf::MT * 8 - 1) / (Cf::WM * Cf::MT * 8);
@@ -1438,6 +1486,13 @@ static int dmma_lower_msg_level(phbc_ctx *ctx, int level) {
 		if (kind == 2 && split && dmma_cherry_tables_on<S>(ctx)) {
 			int zmax = 1, rc;
 			if ((rc = dmma_cherry_reserve(ctx, (size_t)C * PT * S * sizeof(double), end - beg, &zmax))) return rc;
+			if (scale && (size_t)zmax * C * PT * sizeof(double) > ctx->cherry_pairmax_bytes) {
+				PHBC_CHECK(cudaStreamSynchronize(ctx->stream));
+				if (ctx->d_cherry_pairmax) cudaFree(ctx->d_cherry_pairmax);
+				ctx->d_cherry_pairmax = NULL, ctx->cherry_pairmax_bytes = 0;
+				PHBC_CHECK(cudaMalloc((void **)&ctx->d_cherry_pairmax, (size_t)zmax * C * PT * sizeof(double)));
+				ctx->cherry_pairmax_bytes = (size_t)zmax * C * PT * sizeof(double);
+			}
 			if (!ctx->d_cherry_enum) {
 				PHBC_CHECK(cudaMalloc((void **)&ctx->d_cherry_enum, 2 * PT));
 				k_dmma_cherry_enum<<<(PT + 255) / 256, 256, 0, ctx->stream>>>(S1, ctx->d_cherry_enum);
@@ -1449,21 +1504,25 @@ static int dmma_lower_msg_level(phbc_ctx *ctx, int level) {
 			for (int z0 = beg; z0 < end; z0 += zmax) {
 				const int zc = end - z0 < zmax ? end - z0 : zmax;
 				k_dmma_cherry_ops<<<(zc + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_lower_ops + z0, zc, ctx->d_cherry_ops);
-				lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ttiles), C, zc), lthreads, lsmem, ctx->stream>>>(bt, ctx->d_cherry_ops, ctx->d_dmma_img, nimg);
+				lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ttiles), C, zc), lthreads, lsmem, ctx->stream>>>(bt, ctx->d_cherry_ops, ctx->d_dmma_img, nimg,
+				                                                                                                          scale ? ctx->d_cherry_pairmax : nullptr);
 				const size_t gtiles = ((size_t)P * S + 8 * 256 - 1) / (8 * 256);
 				const int gx = pick_chunks(8 * ctx->num_sms, C * zc, gtiles > 65535 ? 65535 : (int)gtiles);
-				k_dmma_cherry_gather<S><<<dim3((unsigned)gx, C, zc), 256, 0, ctx->stream>>>(b, ctx->d_lower_ops + z0, ctx->d_cherry_tab);
+				k_dmma_cherry_gather<S><<<dim3((unsigned)gx, C, zc), 256, 0, ctx->stream>>>(b, ctx->d_lower_ops + z0, ctx->d_cherry_tab, ctx->d_cherry_pairmax,
+				                                                                            scale ? ctx->d_rowmax + (size_t)(z0 - lbeg) * C * P : nullptr);
 				ctx->launches += 3;
 			}
 			continue;
 		}
 		for (int z0 = beg; z0 < end; z0 += 65535) {
 			const int zc = end - z0 < 65535 ? end - z0 : 65535;
-			lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ltiles), C, zc), lthreads, lsmem, ctx->stream>>>(b, ctx->d_lower_ops + z0, ctx->d_dmma_img, nimg);
+			lower<<<dim3(pick_chunks(lper_sm * ctx->num_sms, C * zc, ltiles), C, zc), lthreads, lsmem, ctx->stream>>>(
+			    b, ctx->d_lower_ops + z0, ctx->d_dmma_img, nimg, scale ? ctx->d_rowmax + (size_t)(z0 - lbeg) * C * P : nullptr);
 			ctx->launches++;
 		}
 	}
 	PHBC_CHECK(cudaGetLastError());
+	if (scale) return dmma_scale_from_max(ctx, b, ctx->d_lower_ops + lbeg, lend - lbeg, nullptr, 0, lend - lbeg, 1, o->scaling_threshold);
 	return 0;
 }
 
@@ -1507,7 +1566,7 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 	int rc;
 	Bufs b = dmma_msg_bufs(ctx);
 	const bool split = true;  // per-kind launches (measured faster than one five-slot variant per level, round 1)
-	typedef void (*upper_fn)(Bufs, const phbc_parent_op *, const double *, const double *, const double *, const double *, int, int, double *, int);
+	typedef void (*upper_fn)(Bufs, const phbc_parent_op *, const double *, const double *, const double *, const double *, int, int, double *, int, int, double *);
 	struct Variant {
 		upper_fn fn;
 		int wm, nslots, threads, tiles, slots;
@@ -1564,7 +1623,16 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 		}
 	if ((rc = phbc_ensure_scratch(ctx, (size_t)N * C * pstride * sizeof(double)))) return rc;
 	PHBC_CHECK(cudaMemsetAsync(ctx->d_scratch, 0, (size_t)N * C * pstride * sizeof(double), ctx->stream));
-	for (int l = 0; l < ctx->n_upper_levels; l++)
+	// rescaling: the upper partials a level stores are rescaled like the lower ones (slots 2 z, 2 z + 1 of the level's sorted parent
+	// ops, d_upper_slot); tip children and the children of table cherries store nothing and report 0
+	const bool scale = o->scale != 0;
+	for (int l = 0; l < ctx->n_upper_levels; l++) {
+		const int pbeg = ctx->h_parent_level_off[l], pend = ctx->h_parent_level_off[l + 1];
+		const size_t rm_level = (size_t)2 * (pend - pbeg) * C * Cf::UNSPLIT * P;
+		if (scale && pend > pbeg) {
+			if ((rc = dmma_rowmax_reserve_level(ctx, rm_level * sizeof(double)))) return rc;
+			PHBC_CHECK(cudaMemsetAsync(ctx->d_rowmax, 0, rm_level * sizeof(double), ctx->stream));
+		}
 		for (int kind = 0; kind < 3; kind++) {
 			int beg, end;
 			group(l, kind, beg, end);
@@ -1578,7 +1646,7 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 					k_dmma_cherry_upper_tables<S><<<dim3((PT + 1) / 2, C, zc), 192, 0, ctx->stream>>>(C, ctx->d_parent_ops + z0, ctx->d_P, ctx->d_dP, ctx->d_freqs,
 					                                                                                      o->include_root_freqs, ctx->d_cherry_tab);
 					k_dmma_cherry_upper<S><<<dim3(pick_chunks(8 * ctx->num_sms, C * zc, (P + 31) / 32), C, zc), 256, 0, ctx->stream>>>(
-					    b, ctx->d_parent_ops + z0, ctx->d_cherry_tab, ctx->d_weights, ctx->d_pattern_lnl, pstride, ctx->d_scratch);
+					    b, ctx->d_parent_ops + z0, ctx->d_cherry_tab, ctx->d_weights, ctx->d_pattern_lnl, pstride, ctx->d_scratch, scale ? 1 : 0);
 					ctx->launches += 2;
 				}
 				continue;
@@ -1587,10 +1655,15 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 				const int zc = end - z0 < 65535 ? end - z0 : 65535;
 				v.fn<<<dim3(pick_chunks(v.slots, C * zc, v.tiles), C, zc), v.threads, v.smem, ctx->stream>>>(
 				    b, ctx->d_parent_ops + z0, ctx->d_dmma_img, ctx->d_freqs, ctx->d_weights, ctx->d_pattern_lnl, o->include_root_freqs, pstride, ctx->d_scratch,
-				    v.nslots);
+				    v.nslots, scale ? 1 : 0, scale ? ctx->d_rowmax + (size_t)2 * (z0 - pbeg) * C * Cf::UNSPLIT * P : nullptr);
 				ctx->launches++;
 			}
 		}
+		const int ubeg = ctx->h_upper_level_off[l], ucnt = ctx->h_upper_level_off[l + 1] - ubeg;
+		if (scale && ucnt > 0 && pend > pbeg &&
+		    (rc = dmma_scale_from_max(ctx, b, ctx->d_upper_ops + ubeg, ucnt, ctx->d_upper_slot, 0, 2 * (pend - pbeg), Cf::UNSPLIT, o->scaling_threshold)))
+			return rc;
+	}
 	PHBC_CHECK(cudaGetLastError());
 	return phbc_gradient_from_partials(ctx, pstride, result);
 }
@@ -1606,7 +1679,7 @@ static int dmma_msg_passes(phbc_ctx *ctx, const phbc_eval_opts *o, double *resul
 	if (phases & PHBC_PH_FORWARD) {
 		for (int l = 0; l < ctx->n_lower_levels; l++) {
 			if (ctx->h_lower_level_off[l + 1] - ctx->h_lower_level_off[l] <= 0) continue;
-			if ((rc = dmma_lower_msg_level<S, VAR>(ctx, l))) return rc;
+			if ((rc = dmma_lower_msg_level<S, VAR>(ctx, l, o))) return rc;
 		}
 		if ((rc = phbc_generic_root(ctx, o, result))) return rc;
 	}
@@ -1663,7 +1736,10 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o, int phases = PH
 	if ((rc = fwd ? phbc_generic_prepare(ctx, o) : phbc_generic_buffers(ctx, o))) return rc;
 	Bufs b = phbc_make_bufs(ctx);
 	// message form: the fast path (unscaled, state tips, eigen system, upper partials not needed as such afterwards)
-	bool msg = !o->scale && !o->materialize_uppers && ctx->have_eigen && !o->explicit_matrices;
+	// rescaled evaluations too (round 2, last step), unless the reference-compatible per-category normalisation is asked for, the
+	// categories do not tile a warp (k_dmma_scale_from_max) or PHB_OPT_TUNE 22 keeps them on the node-at-a-time form for comparison
+	bool msg = !o->materialize_uppers && ctx->have_eigen && !o->explicit_matrices &&
+	           (!o->scale || (!o->compat_scaled_gradient && dmma_rowmax_usable(ctx) && ctx->d_upper_slot && ctx->tune != 22));
 	if (msg) {
 		int usable = 0;
 		if ((rc = dmma_tips_as_states(ctx, &usable))) return rc;

@@ -645,3 +645,31 @@ def test_cherry_tables_switch_on_by_pattern_count_and_take_encoded_tip_partials(
     lnl2, plnl2, g2, _ = _eval_tuned(pb, 9)
     assert lnl2 == lnl
     np.testing.assert_array_equal(g2, g)
+
+
+@pytest.mark.parametrize("tune", [0, 20, 22], ids=["message-form", "message-form+cherry-tables", "node-at-a-time"])
+@pytest.mark.parametrize("S,T,P,C", [(61, 14, 130, 1), (61, 9, 75, 2), (20, 17, 300, 4), (63, 8, 40, 1)])
+def test_rescaled_message_form(S, T, P, C, tune):
+    """Rescaling on the message form of the tensor-core level kernels (k_dmma_lower_msg leaves the row maxima of L_n,
+    k_dmma_scale_from_max divides the message; the pre-order ops carry exp(-(sf[N+n] + sf[a] + sf[b]))) with a threshold (1e-2) that
+    makes nearly every node rescale, with and without the cherry tables, against the oracle and the node-at-a-time form
+    (PHB_OPT_TUNE 22).  SingleTreeLikelihood_scalePartials, treelikelihood.c:1790-1836; gradient_cat_branch_lengths :2715-2789."""
+    from physher_b200.treelikelihood import OPT_SCALING_THRESHOLD_EXP, OPT_TUNE
+    pb = _synthetic_problem(T, P, S, C, seed=4400 + S + T, unknown=0.04)
+    base = O.evaluate(pb)
+    pb.scale, pb.scaling_threshold = True, 1e-2
+    want = O.evaluate(pb, partials=True)
+    assert (want["scaling"][pb.root] < 0).any()
+    tlk = phb.SingleTreeLikelihood.from_problem(pb, kernels=phb.KERNELS_FUSED if S != 20 else phb.KERNELS_AUTO)
+    tlk.set_option(OPT_SCALING_THRESHOLD_EXP, 2)
+    tlk.set_option(OPT_TUNE, 9 if (S == 20 and tune == 0) else tune)  # 20 states: 9 = the level kernels (the walk does not rescale anyway)
+    assert tlk.rescaling()
+    assert rel_err(tlk.calculate(), want["lnl"]) < RTOL
+    np.testing.assert_allclose(tlk.pattern_log_likelihoods(), want["pattern_lnl"], rtol=1e-11, atol=0)
+    g = tlk.gradient()
+    assert tlk.last_kernels() == phb.treelikelihood.RAN_TENSOR
+    assert grad_err(g, want["grad"]) < RTOL
+    assert grad_err(g, base["grad"]) < 1e-9
+    tlk.use_rescaling(False)
+    assert grad_err(tlk.gradient(), base["grad"]) < RTOL  # and back
+    tlk.close()
