@@ -691,7 +691,7 @@ __device__ __forceinline__ double tip_value(const double *__restrict__ MT, int s
 	return s < Sh::S ? MT[s * Sh::NP + col] : 1.0;  // unknown state: factor 1 (treelikelihood20.c:125-131)
 }
 
-template <int S, int MT, int NSPLIT, int WM, int NST = 0, int GB = 1>
+template <int S, int MT, int NSPLIT, int WM, int NST = 0, int GB = 1, bool RESCALE = false>
 __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ img, int nimg,
                                                                    double *__restrict__ rowmax /* rescaling: [op of the launch][C][P] max of L_n, else NULL */) {
 	using Sh = DmmaShape<S>;
@@ -781,7 +781,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 						if (a_tip) ca[m][tt] = tip_value<Sh>(mA, sa[m], col);
 						if (b_tip) cb[m][tt] = tip_value<Sh>(mB, sb[m], col);
 						ca[m][tt] *= cb[m][tt];  // L_n = M_a o M_b, straight into the A fragment
-						if (rowmax && col < S) lmax[m] = fmax(lmax[m], ca[m][tt]);
+						if (RESCALE && col < S) lmax[m] = fmax(lmax[m], ca[m][tt]);  // compiled out of the unscaled kernel: DMNMX shares the FP64 pipe with DMMA
 					} else ca[m][tt] = 0.0;
 				}
 #pragma unroll
@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_lower_msg(Bufs b, con
 			}
 		}
 		store_tile<Sh, MT, NTW>(out, p0, b.P, n0, lane, acc);
-		if (rowmax && warp % NSPLIT == 0) {  // every n-split warp of the group formed the same L_n
+		if (RESCALE && warp % NSPLIT == 0) {  // every n-split warp of the group formed the same L_n
 #pragma unroll
 			for (int m = 0; m < MT; m++) {
 				double mx = fmax(lmax[m], __shfl_xor_sync(0xffffffffu, lmax[m], 1));
@@ -831,7 +831,7 @@ __global__ void k_dmma_cherry_enum(int S1, uint8_t *__restrict__ e) {
 	if (q >= S1 * S1) return;
 	e[q] = (uint8_t)(q / S1), e[S1 * S1 + q] = (uint8_t)(q % S1);
 }
-template <int S>
+template <int S, bool RESCALE>
 __global__ void __launch_bounds__(256) k_dmma_cherry_gather(Bufs b, const phbc_op *__restrict__ ops, const double *__restrict__ table,
                                                             const double *__restrict__ pairmax, double *__restrict__ rowmax) {
 	const phbc_op op = ops[blockIdx.z];
@@ -852,7 +852,7 @@ __global__ void __launch_bounds__(256) k_dmma_cherry_gather(Bufs b, const phbc_o
 				const int sa = min((int)sta[p], S), sb = min((int)stb[p], S);
 				v[u] = t[(size_t)(sa * S1 + sb) * S + i];
 				// rescaling: the row maximum of L_n is the pair's as well ([op of the launch][C][pairs] -> [op][C][P])
-				if (rowmax && i == 0) rowmax[((size_t)blockIdx.z * b.C + c) * b.P + p] = pairmax[((size_t)blockIdx.z * b.C + c) * (S1 * S1) + sa * S1 + sb];
+				if (RESCALE && i == 0) rowmax[((size_t)blockIdx.z * b.C + c) * b.P + p] = pairmax[((size_t)blockIdx.z * b.C + c) * (S1 * S1) + sa * S1 + sb];
 			}
 		}
 #pragma unroll
@@ -923,17 +923,31 @@ __global__ void __launch_bounds__(256) k_dmma_cherry_upper(Bufs b, const phbc_pa
 	__shared__ double red[8][3];
 	const phbc_parent_op op = ops[blockIdx.z];
 	const int c = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const int l8 = lane & 7, sub = lane >> 3;  // eight lanes to a pattern, four patterns to a warp: 8 x 4 independent loads per thread in flight
+	// eight lanes to a pattern, four patterns to a warp.  Measured alternatives (C5, ms per evaluation for the 34 cherries): a warp to a
+	// pattern 11.3; this 6.3; every load hoisted above the products (98 registers, 16 warps per SM) 6.8; sixteen lanes to a pattern with
+	// hoisted loads 7.3 -- the kernel lives on resident warps (64 per SM at 48 registers), not on loads in flight per warp
+	const int l8 = lane & 7, sub = lane >> 3;
 	const double *u = b.upper + ((size_t)op.node * b.C + c) * (size_t)b.P * S;
 	const double *tn = tab + ((size_t)blockIdx.z * b.C + c) * 3 * (size_t)PT * S, *ta = tn + (size_t)PT * S, *tb = ta + (size_t)PT * S;
 	const uint8_t *sta = b.tip_states + (size_t)op.a * b.P, *stb = b.tip_states + (size_t)op.b * b.P;
 	double tot_n = 0.0, tot_a = 0.0, tot_b = 0.0;
+	// the states of the NEXT turn are requested a turn ahead: one dependent latency (states -> rows -> sums) less per turn
+	int nsa = S, nsb = S;
+	{
+		const int p = (blockIdx.x * 8 + warp) * 4 + sub;
+		if (p < b.P) nsa = sta[p], nsb = stb[p];
+	}
 	for (int p0 = (blockIdx.x * 8 + warp) * 4; p0 < b.P; p0 += gridDim.x * 32) {
 		const int p = p0 + sub;
 		const bool live = p < b.P;
+		const int sa = nsa, sb = nsb;
+		{
+			const int np = p + gridDim.x * 32;
+			if (np < b.P) nsa = sta[np], nsb = stb[np];
+		}
 		double gn = 0.0, ga = 0.0, gb = 0.0, wl = 0.0;
 		if (live) {
-			const size_t row = (size_t)(min((int)sta[p], S) * S1 + min((int)stb[p], S)) * S;
+			const size_t row = (size_t)(min(sa, S) * S1 + min(sb, S)) * S;
 			// rescaling: U_n carries exp(-sf[N + n]); the children are tips (see k_dmma_upper)
 			if (l8 == 0) wl = __ldg(weights + p) / exp(__ldg(pattern_lnl + p) - (scaled ? b.sf[(size_t)(b.N + op.node) * b.P + p] : 0.0));
 			const double *up = u + (size_t)p * S;
@@ -976,7 +990,7 @@ __global__ void __launch_bounds__(256) k_dmma_cherry_upper(Bufs b, const phbc_pa
 // sits in slot 1 when a is internal, else in slot 3 when b is internal, else (both tips) in a sixth slot at 20 states and in slot 1 at
 // 61 states, where five images are all an SM can hold -- a's tip image is then read from global memory (one L2-resident column per pattern).
 // ---------------------------------------------------------------------------------------------
-template <int S, int MT, int NSPLIT, int WM, int NST = 0, int GB = 1>
+template <int S, int MT, int NSPLIT, int WM, int NST = 0, int GB = 1, bool RESCALE = false>
 __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, const phbc_parent_op *__restrict__ ops, const double *__restrict__ img,
                                                                    const double *__restrict__ freqs, const double *__restrict__ weights,
                                                                    const double *__restrict__ pattern_lnl, int include_root_freqs, int pstride,
@@ -1073,7 +1087,7 @@ __global__ void __launch_bounds__(32 * WM * NSPLIT) k_dmma_upper_msg(Bufs b, con
 			const int p = p0 + 8 * m + r;
 			wk[m] = p < b.P ? __ldg(weights + p) : 0.0;
 			lk[m] = p < b.P ? __ldg(pattern_lnl + p) : 0.0;
-			if (scaled && p < b.P) {  // every branch term of this op carries exp(-(sf[N + n] + sf[a] + sf[b])), see k_dmma_upper
+			if (RESCALE && scaled && p < b.P) {  // every branch term of this op carries exp(-(sf[N + n] + sf[a] + sf[b])), see k_dmma_upper
 				double e = is_root ? 0.0 : b.sf[(size_t)(b.N + op.node) * b.P + p];
 				if (!a_tip) e += b.sf[(size_t)op.a * b.P + p];
 				if (!b_tip) e += b.sf[(size_t)op.b * b.P + p];
@@ -1168,7 +1182,7 @@ dmma_mtiles<MT, NTW, Sh::KCH>(Z, cw, j, tt, bZ);
 		}
 		if (!a_tip) store_tile<Sh, MT, NTW>(Ua, p0, b.P, n0, lane, Mb);
 		if (!b_tip) store_tile<Sh, MT, NTW>(Ub, p0, b.P, n0, lane, Ma);
-		if (rowmax) {  // rescaling: slots 2 z (child a) and 2 z + 1 (child b) of this launch, as k_dmma_upper
+		if (RESCALE && rowmax) {  // rescaling: slots 2 z (child a) and 2 z + 1 (child b) of this launch, as k_dmma_upper
 			const size_t row = (((size_t)(2 * blockIdx.z) * b.C + c) * NSPLIT + warp % NSPLIT) * b.P;
 			store_rowmax<Sh, MT, NTW>(rowmax, row, p0, b.P, n0, lane, Mb, !a_tip);
 			store_rowmax<Sh, MT, NTW>(rowmax, row + (size_t)b.C * NSPLIT * b.P, p0, b.P, n0, lane, Ma, !b_tip);
@@ -1463,7 +1477,7 @@ static int dmma_lower_msg_level(phbc_ctx *ctx, int level, const phbc_eval_opts *
 		int rc;
 		if ((rc = dmma_rowmax_reserve_level(ctx, (size_t)(lend - lbeg) * C * P * sizeof(double)))) return rc;
 	}
-	auto lower = k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM, Cf::LNST, Cf::LGB>;
+	auto lower = o->scale ? k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM, Cf::LNST, Cf::LGB, true> : k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM, Cf::LNST, Cf::LGB, false>;
 	const size_t ring = (size_t)Cf::WM * AStage<Sh, Cf::MT, 2, Cf::LNST>::NSTAGE * AStage<Sh, Cf::MT, 2, Cf::LNST>::STG;
 	const int lthreads = 32 * Cf::WM * Cf::NSPLIT, ltiles = (P + Cf::WM * Cf::MT * 8 - 1) / (Cf::WM * Cf::MT * 8);
 	PHBC_CHECK(cudaFuncSetAttribute(lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 + (3 * Sh::IMG + ring) * sizeof(double))));
@@ -1508,8 +1522,11 @@ static int dmma_lower_msg_level(phbc_ctx *ctx, int level, const phbc_eval_opts *
 				                                                                                                          scale ? ctx->d_cherry_pairmax : nullptr);
 				const size_t gtiles = ((size_t)P * S + 8 * 256 - 1) / (8 * 256);
 				const int gx = pick_chunks(8 * ctx->num_sms, C * zc, gtiles > 65535 ? 65535 : (int)gtiles);
-				k_dmma_cherry_gather<S><<<dim3((unsigned)gx, C, zc), 256, 0, ctx->stream>>>(b, ctx->d_lower_ops + z0, ctx->d_cherry_tab, ctx->d_cherry_pairmax,
-				                                                                            scale ? ctx->d_rowmax + (size_t)(z0 - lbeg) * C * P : nullptr);
+				if (scale)
+					k_dmma_cherry_gather<S, true><<<dim3((unsigned)gx, C, zc), 256, 0, ctx->stream>>>(b, ctx->d_lower_ops + z0, ctx->d_cherry_tab, ctx->d_cherry_pairmax,
+					                                                                                  ctx->d_rowmax + (size_t)(z0 - lbeg) * C * P);
+				else
+					k_dmma_cherry_gather<S, false><<<dim3((unsigned)gx, C, zc), 256, 0, ctx->stream>>>(b, ctx->d_lower_ops + z0, ctx->d_cherry_tab, nullptr, nullptr);
 				ctx->launches += 3;
 			}
 			continue;
@@ -1575,7 +1592,10 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 	for (int kind = 0; kind < 3; kind++) {
 		Variant &v = var[kind];
 		const bool wide = split && kind == 0 && Cf::UWM_II != Cf::UWM;
-		v.fn = wide ? (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM_II, Cf::UNST, Cf::UGB> : (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, Cf::UNST, Cf::UGB>;
+		if (o->scale)
+			v.fn = wide ? (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM_II, Cf::UNST, Cf::UGB, true> : (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, Cf::UNST, Cf::UGB, true>;
+		else
+			v.fn = wide ? (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM_II, Cf::UNST, Cf::UGB, false> : (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, Cf::UNST, Cf::UGB, false>;
 		v.wm = wide ? Cf::UWM_II : Cf::UWM;
 		v.nslots = (split && kind == 0) ? 2 : (S <= 32 ? 6 : 5);
 		const int warps = v.wm * Cf::UNSPLIT;
