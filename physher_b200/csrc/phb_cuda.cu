@@ -76,6 +76,8 @@ extern "C" phbc_ctx *phbc_create(int device, int ntips, int nstate, int ncat, in
 	ctx->cat_grad_cap = 1;
 	ctx->result_cap = 1;
 	ok = ok && dev_alloc(&ctx->d_result, (size_t)ctx->result_cap * (1 + N)) == 0;
+	// [lnL, gradient[N]] travels to the host as one block, also after a likelihood-only evaluation: the gradient slots must be defined
+	ok = ok && cudaMemset(ctx->d_result, 0, (size_t)ctx->result_cap * (1 + N) * sizeof(double)) == cudaSuccess;
 	ctx->bl_cap = 1;
 	ok = ok && dev_alloc(&ctx->d_bl, N) == 0;
 	ok = ok && cudaMallocHost((void **)&ctx->h_bl, N * sizeof(double)) == cudaSuccess;
@@ -407,6 +409,7 @@ extern "C" int phbc_upload_branch_lengths(phbc_ctx *ctx, const double *bl, int n
 		cudaFree(ctx->d_result);
 		ctx->d_result = NULL;
 		PHBC_CHECK(cudaMalloc((void **)&ctx->d_result, (size_t)nbatch * (1 + N) * sizeof(double)));
+		PHBC_CHECK(cudaMemset(ctx->d_result, 0, (size_t)nbatch * (1 + N) * sizeof(double)));
 		ctx->result_cap = nbatch;
 	}
 	// the previous async copy out of the pinned staging buffer must have completed
