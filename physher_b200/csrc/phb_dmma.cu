@@ -1477,7 +1477,10 @@ static int dmma_lower_msg_level(phbc_ctx *ctx, int level, const phbc_eval_opts *
 		int rc;
 		if ((rc = dmma_rowmax_reserve_level(ctx, (size_t)(lend - lbeg) * C * P * sizeof(double)))) return rc;
 	}
-	auto lower = o->scale ? k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM, Cf::LNST, Cf::LGB, true> : k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM, Cf::LNST, Cf::LGB, false>;
+	// the rescaling instantiation exists for the shipped geometry only (dmma_evaluate keeps rescaled evaluations off the tuning variants)
+	constexpr bool RS = VAR == 0;
+	auto lower = (RS && o->scale) ? k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM, Cf::LNST, Cf::LGB, RS> : k_dmma_lower_msg<S, Cf::MT, Cf::NSPLIT, Cf::WM, Cf::LNST, Cf::LGB, false>;
+	if (o->scale && !RS) return -1;
 	const size_t ring = (size_t)Cf::WM * AStage<Sh, Cf::MT, 2, Cf::LNST>::NSTAGE * AStage<Sh, Cf::MT, 2, Cf::LNST>::STG;
 	const int lthreads = 32 * Cf::WM * Cf::NSPLIT, ltiles = (P + Cf::WM * Cf::MT * 8 - 1) / (Cf::WM * Cf::MT * 8);
 	PHBC_CHECK(cudaFuncSetAttribute(lower, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(128 + (3 * Sh::IMG + ring) * sizeof(double))));
@@ -1592,8 +1595,10 @@ static int dmma_upper_msg(phbc_ctx *ctx, const phbc_eval_opts *o, double *result
 	for (int kind = 0; kind < 3; kind++) {
 		Variant &v = var[kind];
 		const bool wide = split && kind == 0 && Cf::UWM_II != Cf::UWM;
+		constexpr bool RS = VAR == 0;  // see dmma_lower_msg_level
+		if (o->scale && !RS) return -1;
 		if (o->scale)
-			v.fn = wide ? (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM_II, Cf::UNST, Cf::UGB, true> : (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, Cf::UNST, Cf::UGB, true>;
+			v.fn = wide ? (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM_II, Cf::UNST, Cf::UGB, RS> : (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, Cf::UNST, Cf::UGB, RS>;
 		else
 			v.fn = wide ? (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM_II, Cf::UNST, Cf::UGB, false> : (upper_fn)k_dmma_upper_msg<S, Cf::UMT, Cf::UNSPLIT, Cf::UWM, Cf::UNST, Cf::UGB, false>;
 		v.wm = wide ? Cf::UWM_II : Cf::UWM;
@@ -1759,7 +1764,7 @@ static int dmma_evaluate(phbc_ctx *ctx, const phbc_eval_opts *o, int phases = PH
 	// rescaled evaluations too (round 2, last step), unless the reference-compatible per-category normalisation is asked for, the
 	// categories do not tile a warp (k_dmma_scale_from_max) or PHB_OPT_TUNE 22 keeps them on the node-at-a-time form for comparison
 	bool msg = !o->materialize_uppers && ctx->have_eigen && !o->explicit_matrices &&
-	           (!o->scale || (!o->compat_scaled_gradient && dmma_rowmax_usable(ctx) && ctx->d_upper_slot && ctx->tune != 22));
+	           (!o->scale || (!o->compat_scaled_gradient && dmma_rowmax_usable(ctx) && ctx->d_upper_slot && ctx->tune != 22 && !(ctx->tune >= 1 && ctx->tune <= 6)));
 	if (msg) {
 		int usable = 0;
 		if ((rc = dmma_tips_as_states(ctx, &usable))) return rc;
