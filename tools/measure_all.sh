@@ -3,6 +3,8 @@
 #     gpurun --timeout 2400 -- 'bash tools/measure_all.sh'
 # then, back in the container, `python tools/ncu_traffic.py gpurun_out/r2_x_traffic_<cfg>.csv ... --kernel-rev <tag of phb_version()>`
 # for every config (profiles/traffic.json) and `python tools/ncu_summary.py gpurun_out/r2_x_dwalk_c4.ncu-rep --out profiles/...`.
+# Kernel revision tags (phb_version()): the walks' captures are r2w, the level-batched tensor-core kernels' (c5) r2z, e.g.
+#     python tools/ncu_traffic.py profiles/r2_z_traffic_c5.csv --kernels 'k_dmma_(lower|upper|cherry)' --per k_dmma_pack --key c5:auto --patterns 1000000 --kernel-rev r2z
 # Numbers printed by the runs under ncu are never bench values; every step is bounded by `timeout`.
 set -x
 M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum
