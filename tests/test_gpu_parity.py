@@ -593,7 +593,7 @@ def _eval_tuned(pb, tune):
     return lnl, plnl, g, launches
 
 
-@pytest.mark.parametrize("shape", [(61, 9, 300, 2), (61, 2, 50, 1), (60, 6, 33, 1), (63, 12, 129, 1)], ids=lambda s: "S%d-T%d-P%d-C%d" % s)
+@pytest.mark.parametrize("shape", [(61, 9, 300, 2), (61, 2, 50, 1), (60, 6, 33, 1), (63, 12, 129, 1), (61, 7, 77, 2)], ids=lambda s: "S%d-T%d-P%d-C%d" % s)
 def test_cherry_tables(shape):
     """cherries evaluated once per PAIR of tip states (forced on by PHB_OPT_TUNE 20, off by 21).  Post-order pass: the pair's message
     copied per pattern (k_dmma_cherry_gather) -- the same arithmetic in the same order, so not one bit of any pattern likelihood
